@@ -1,0 +1,50 @@
+"""Shared helpers for the parity tests: rebuild inputs of the golden cases."""
+from __future__ import annotations
+
+import numpy as np
+
+from ood_in_object_detection_b200 import synth
+
+F32 = np.float32
+
+
+def unpack_nested(g, prefix, ncls, as_threshold=False):
+    """npz -> [cls][stride] nested lists (inverse of make_golden._pack_nested)."""
+    out = []
+    for c in range(ncls):
+        row = []
+        for s in range(3):
+            v = g[f"{prefix}_{c}_{s}"]
+            if as_threshold:
+                row.append(float(v) if v.ndim == 0 else [])
+            else:
+                row.append(v)
+        out.append(row)
+    return out
+
+
+def split(a, counts):
+    idx = np.cumsum(counts)[:-1]
+    return np.split(a, idx)
+
+
+def scoring_case(g):
+    """Rebuild the test images of a golden_scoring file: maps from the seed, detections from the file."""
+    seed, img, B = int(g["seed"]), int(g["img"]), int(g["batch"])
+    ch = tuple(int(c) for c in g["channels"])
+    hw = tuple(img // s for s in synth.STRIDES)
+    maps = synth.feature_maps(seed + 2, B, ch, hw)
+    n = g["n_boxes"]
+    boxes, cls, strides = split(g["boxes"], n), split(g["cls"], n), split(g["strides"], n)
+    images = [dict(maps=[m[i] for m in maps], boxes=boxes[i], cls=cls[i], strides=strides[i], img_hw=(img, img))
+              for i in range(B)]
+    return images, maps
+
+
+def train_case(g):
+    seed, img, B = int(g["seed"]), int(g["img"]), int(g["batch"])
+    ch = tuple(int(c) for c in g["channels"])
+    hw = tuple(img // s for s in synth.STRIDES)
+    maps = synth.feature_maps(seed, B, ch, hw)
+    n = g["train_n_boxes"]
+    return maps, split(g["train_boxes"], n), split(g["train_cls"], n), split(g["train_strides"], n)

@@ -1,0 +1,214 @@
+"""The CPU oracle against the golden vectors frozen from the real reference (CPU-only tests)."""
+import numpy as np
+import pytest
+
+from oracle import decide, distance, fit, kmeans, logits, roi_align
+from tests.helpers import scoring_case, split, train_case, unpack_nested
+
+F32 = np.float32
+
+
+def test_roi_align_matches_torchvision():
+    """numpy restatement == torchvision's C++ op, bit for bit, incl. Q5 border boxes."""
+    import torch
+    import torchvision
+    rng = np.random.default_rng(0)
+    for (C, H, W, img) in [(16, 80, 80, 640), (8, 20, 20, 640), (8, 25, 23, 736)]:
+        fm = rng.standard_normal((3, C, H, W)).astype(F32)
+        K = 60
+        ctr = rng.uniform(0, img, (K, 2))
+        sz = np.exp(rng.uniform(np.log(4), np.log(img * 0.9), (K, 2)))
+        rois = np.stack([rng.integers(0, 3, K), np.clip(ctr[:, 0] - sz[:, 0] / 2, 0, img), np.clip(ctr[:, 1] - sz[:, 1] / 2, 0, img),
+                         np.clip(ctr[:, 0] + sz[:, 0] / 2, 0, img), np.clip(ctr[:, 1] + sz[:, 1] / 2, 0, img)], 1).astype(F32)
+        rois[0, 1:] = [img - 10, img - 10, img, img]
+        rois[1, 1:] = [0, 0, img, img]
+        rois[2, 1:] = [5, 5, 5, 5]
+        rois[3, 1:] = [-20, -30, 50, 60]
+        rois[4, 1:] = [img - 5, img - 5, img + 40, img + 40]
+        ref = torchvision.ops.roi_align(torch.from_numpy(fm), torch.from_numpy(rois), (1, 1), spatial_scale=W / img,
+                                        aligned=False).numpy()[:, :, 0, 0]
+        assert np.array_equal(roi_align.roi_align_1x1(fm, rois, W / img), ref)
+
+
+def test_extractor_edges(golden):
+    g = golden("golden_roi_edges.npz")
+    n = g["n_boxes"]
+    maps = [g[f"map{s}"] for s in range(3)]
+    boxes, strides = split(g["boxes"], n), split(g["strides"], n)
+    for all_strides in (False, True):
+        out = roi_align.extract_roi_aligned_features_from_correct_stride(maps, boxes, strides, (int(g["img"]),) * 2,
+                                                                         extract_all_strides=all_strides)
+        for i in range(3):
+            for s in range(3):
+                assert np.array_equal(out[i][s][0], g[f"all{int(all_strides)}_idx_{i}_{s}"])
+                exp = g[f"all{int(all_strides)}_feat_{i}_{s}"]
+                got = np.asarray(out[i][s][1], F32).reshape(exp.shape)
+                assert np.array_equal(got, exp)
+
+
+def test_separable_weights_equal_sample_sum(golden):
+    """The factorised form the CUDA kernel uses is the same function (to float32 rounding)."""
+    g = golden("golden_roi_edges.npz")
+    fm = g["map0"]
+    H = W = fm.shape[-1]
+    sc = W / int(g["img"])
+    for b in g["boxes"]:
+        ref = roi_align.roi_align_1x1(fm, np.concatenate([[0], b])[None], sc)[0]
+        sw, sh, rw, rh, gw, gh = roi_align.roi_params(b, sc)
+        y0, wy = roi_align.axis_weights(sh, rh, gh, H)
+        x0, wx = roi_align.axis_weights(sw, rw, gw, W)
+        if len(wy) == 0 or len(wx) == 0:
+            assert not ref.any()
+            continue
+        win = fm[0, :, y0:y0 + len(wy), x0:x0 + len(wx)].astype(np.float64)
+        sep = np.einsum("cyx,y,x->c", win, wy.astype(np.float64), wx.astype(np.float64)) / max(gh * gw, 1)
+        np.testing.assert_allclose(sep, ref, rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["golden_c1_one.npz", "golden_small_kmeans5.npz"])
+def test_decisions_and_distances(golden, name):
+    g = golden(name)
+    images, _ = scoring_case(g)
+    nc = int(g["nc"])
+    for tag, metric in (("l1", "l1"), ("l2", "l2"), ("cos", "cosine")):
+        clusters = unpack_nested(g, f"{tag}_clusters", nc)
+        thr = unpack_nested(g, f"{tag}_thr", nc, as_threshold=True)
+        dec, det = decide.distance_decisions(images, clusters, thr, metric, return_details=True)
+        assert np.array_equal(np.concatenate([np.asarray(d, np.int8) for d in dec]), g[f"{tag}_decisions"])
+        d = np.array([t[0] for im in det for t in im])
+        np.testing.assert_allclose(d, g[f"{tag}_dist"], rtol=1e-6, atol=1e-7)
+        assert np.array_equal(np.array([t[2] for im in det for t in im]), g[f"{tag}_cls_used"])
+        assert np.array_equal(np.array([t[4] for im in det for t in im]), g[f"{tag}_box_of"])
+    assert np.all(g["cos_indness"] == -1)       # Q2
+
+
+def test_fit_clusters_scores_thresholds(golden):
+    g = golden("golden_c1_one.npz")
+    nc = int(g["nc"])
+    maps, boxes, cls, strides = train_case(g)
+    img = int(g["img"])
+    acts = [[[] for _ in range(3)] for _ in range(nc)]
+    for i in range(len(boxes)):
+        feats = roi_align.extract_roi_aligned_features_from_correct_stride([m[i:i + 1] for m in maps], [boxes[i]], [strides[i]], (img, img))[0]
+        for s, (idx, fm) in enumerate(feats):
+            for j, b in enumerate(idx):
+                acts[int(cls[i][int(b)])][s].append(fm[j])
+    acts = [[np.stack(v, 0) if len(v) else np.empty(0) for v in row] for row in acts]
+    for tag, metric in (("l1", "l1"), ("l2", "l2"), ("cos", "cosine")):
+        clusters = fit.generate_clusters(acts, "one")
+        scores, mn, mx = fit.compute_scores_from_activations(acts, clusters, metric)
+        thr = fit.generate_thresholds(scores, 0.95, True, True)
+        for c in range(nc):
+            for s in range(3):
+                np.testing.assert_allclose(clusters[c][s], g[f"{tag}_clusters_{c}_{s}"], rtol=1e-6, atol=1e-7)
+                np.testing.assert_allclose(np.asarray(scores[c][s], np.float64), g[f"{tag}_fitscores_{c}_{s}"], rtol=2e-6, atol=2e-7)
+                gt = g[f"{tag}_thr_{c}_{s}"]
+                if gt.ndim == 0:
+                    assert thr[c][s] == pytest.approx(float(gt), rel=2e-6, abs=2e-7)
+                else:
+                    assert thr[c][s] == []
+
+
+def test_quirks(golden):
+    g = golden("golden_quirks.npz")
+    img = int(g["img"])
+    im = dict(maps=[g[f"map{s}"][0] for s in range(3)], boxes=g["boxes"], cls=g["cls"], strides=g["strides"], img_hw=(img, img))
+    clusters = unpack_nested(g, "clusters", 3)
+    cases = {"q1": [[1e9] * 3, [1e-9] * 3, [1e-9] * 3], "q4_zero": [[0.0] * 3, [1e9] * 3, [1e9] * 3],
+             "q4_empty": [[[]] * 3, [1e9] * 3, [1e9] * 3]}
+    for k, thr in cases.items():
+        assert decide.distance_decisions([im], clusters, thr, "l2")[0] == g[f"{k}_decisions"].tolist()
+    assert decide.distance_decisions([im], clusters, cases["q1"], "l2", compat_q1=False)[0] == [0, 1, 0]
+    miss = [clusters[0], [np.empty(0), clusters[1][1], clusters[1][2]], clusters[2]]
+    assert decide.distance_decisions([im], miss, [[1e9] * 3] * 3, "l2")[0] == g["missing_cluster_decisions"].tolist()
+    assert decide.distance_decisions([im], miss, [[999.0] * 3] * 3, "l2")[0] == g["missing_cluster_thr999_decisions"].tolist()
+
+
+def test_logits(golden):
+    g = golden("golden_logits.npz")
+    n = g["n_boxes"]
+    images = [dict(cls=c, logits=z) for c, z in zip(split(g["cls"], n), split(g["logits"], n))]
+    nc = int(g["nc"])
+    acts = [g["train_logits"][g["train_cls"] == c] for c in range(nc)]
+    for tag, temper in (("MSP", 1.0), ("Energy", 1.0), ("ODIN", 1000.0), ("Sigmoid", 1.0)):
+        sc = logits.scores(g["logits"], g["cls"], tag, temper)
+        np.testing.assert_allclose(sc, g[f"{tag}_scores"], rtol=2e-6, atol=1e-7)
+        fs, mn, mx = fit.logits_scores_from_activations(acts, tag, temper)
+        np.testing.assert_allclose(np.concatenate(fs), g[f"{tag}_fitscores"], rtol=2e-6, atol=1e-7)
+        thr = fit.generate_thresholds(fs, 0.95, False, False)
+        np.testing.assert_allclose(thr, g[f"{tag}_thr"], rtol=2e-6, atol=1e-7)
+        # decide with the reference's thresholds so that rounding of the oracle's own fit cannot move a decision
+        dec = decide.logit_decisions(images, tag, g[f"{tag}_thr"], temper)
+        assert np.array_equal(np.concatenate([np.asarray(d, np.int8) for d in dec]), g[f"{tag}_decisions"])
+        fitted = [dict(cls=im["cls"][im["cls"] != 7], logits=im["logits"][im["cls"] != 7]) for im in images]
+        ind = decide.logit_indness(fitted, tag, g[f"{tag}_thr"], g[f"{tag}_min"], g[f"{tag}_max"], temper)
+        tol = 2e-2 if tag == "ODIN" else 1e-4     # ODIN's score range is ~1e-4 wide: INDness amplifies f32 rounding
+        np.testing.assert_allclose(np.concatenate([np.asarray(v) for v in ind]), g[f"{tag}_indness"], atol=tol)
+
+
+def test_fusion(golden):
+    g = golden("golden_fusion.npz")
+    n = g["n"]
+    d1, d2, d3 = (list(map(list, split(g[k], n))) for k in ("d1", "d2", "d3"))
+    s1, s2 = (list(map(list, split(g[k], n))) for k in ("s1", "s2"))
+    cat = lambda x: np.concatenate([np.asarray(v, np.int8) for v in x])
+    assert np.array_equal(cat(decide.fuse(d1, d2, "and")), g["fuse_and"])
+    assert np.array_equal(cat(decide.fuse(d1, d2, "or")), g["fuse_or"])
+    assert np.array_equal(cat(decide.fuse(s1, s2, "score")), g["fuse_score"])
+    assert np.array_equal(cat(decide.fuse3(d1, d2, d3)), g["fuse_majority"])
+
+
+def test_thresholds_percentile_lower(golden):
+    g = golden("golden_thresholds.npz")
+    for n in (5, 6, 11, 21, 101, 1001, 4097):
+        v = g[f"v_{n}"]
+        for tpr in (0.9, 0.95, 0.99, 0.8):
+            t = fit.generate_thresholds([[v, v.astype(np.float64), np.empty(0)]], tpr, True, True)[0]
+            exp = g[f"dist_{n}_{tpr}"]
+            for a, b in zip(t, exp):
+                assert (a == [] and np.isnan(b)) or a == b
+            assert np.array_equal(np.asarray(fit.generate_thresholds([v], tpr, False, False), np.float64), g[f"logit_{n}_{tpr}"])
+            if n > 5:   # explicit order-statistic form used by the GPU radix select
+                k = fit.percentile_lower_index(n, 100 * tpr)
+                assert float(np.sort(v)[k]) == exp[0]
+                k = fit.percentile_lower_index(n, (1 - tpr) * 100)
+                assert float(np.sort(v)[k]) == g[f"logit_{n}_{tpr}"][0]
+
+
+def test_kmeans_labels(golden):
+    """numpy restatement of sklearn KMeans == labels from the reference's call site."""
+    g = golden("golden_kmeans.npz")
+    for tag in "abc":
+        x, k = g[f"{tag}_x"], int(g[f"{tag}_k"])
+        lab = kmeans.kmeans_fit_predict(x, min(k, len(x)), random_state=10)[0]
+        assert np.array_equal(lab, g[f"{tag}_labels"]), tag
+    acts = unpack_nested(g, "fit_acts", 3)
+    clusters = fit.generate_clusters(acts, "KMeans_5")
+    scores, _, _ = fit.compute_scores_from_activations(acts, clusters, "l2")
+    thr = fit.generate_thresholds(scores, 0.95, True, True)
+    for c in range(3):
+        for s in range(3):
+            np.testing.assert_allclose(clusters[c][s], g[f"fit_clusters_{c}_{s}"], rtol=1e-5, atol=1e-6)
+            gt = g[f"fit_thr_{c}_{s}"]
+            assert (thr[c][s] == [] and gt.ndim == 1) or thr[c][s] == pytest.approx(float(gt), rel=1e-5)
+
+
+def test_cpu_port_matches_golden(golden):
+    """The timing port (same library calls as the reference) returns the reference's decisions."""
+    import torch
+    from oracle import cpu_path
+    g = golden("golden_small_kmeans5.npz")
+    images, _ = scoring_case(g)
+    nc = int(g["nc"])
+    timg = [dict(maps=[torch.from_numpy(m) for m in im["maps"]], boxes=torch.from_numpy(im["boxes"]),
+                 cls=torch.from_numpy(im["cls"]), strides=torch.from_numpy(im["strides"]), img_hw=im["img_hw"]) for im in images]
+    for tag, metric in (("l1", "l1"), ("l2", "l2"), ("cos", "cosine")):
+        dec = cpu_path.distance_decisions(timg, unpack_nested(g, f"{tag}_clusters", nc),
+                                          unpack_nested(g, f"{tag}_thr", nc, as_threshold=True), metric)
+        assert np.array_equal(np.concatenate([np.asarray(d, np.int8) for d in dec]), g[f"{tag}_decisions"])
+    gl = golden("golden_logits.npz")
+    n = gl["n_boxes"]
+    limg = [dict(cls=torch.from_numpy(c), logits=torch.from_numpy(z)) for c, z in zip(split(gl["cls"], n), split(gl["logits"], n))]
+    for tag, temper in (("MSP", 1.0), ("Energy", 1.0), ("ODIN", 1000.0), ("Sigmoid", 1.0)):
+        dec = cpu_path.logit_decisions(limg, tag, gl[f"{tag}_thr"].tolist(), temper)
+        assert np.array_equal(np.concatenate([np.asarray(d, np.int8) for d in dec]), gl[f"{tag}_decisions"])
