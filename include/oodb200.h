@@ -1,0 +1,133 @@
+/* oodb200.h -- C ABI of the B200-native OoD-scoring hot path (liboodb200.so).
+ *
+ * The reference (aitor-martinez-seras/OoD_in_Object_Detection) is pure Python and has no
+ * FFI; the boundary it offers is the `OODMethod` class surface of `ood_utils.py`.  The
+ * entry points below are what a binding for that path would call: each one replaces the
+ * *inside* of the reference function cited next to it.  The Python classes in
+ * `ood_in_object_detection_b200/ood_utils.py` (same names / arguments / error behaviour as the
+ * reference's) call these through ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - every function only enqueues work on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises, never allocates, and returns 0 or a negative OODB200_ERR_* code;
+ *     `oodb200_last_error()` gives the message for the calling thread;
+ *   - no torch types anywhere: plain pointers and sizes.
+ *   - 1 = in-distribution, 0 = out-of-distribution, as in /root/reference/ood_utils.py:148-158.
+ */
+#ifndef OODB200_H_
+#define OODB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OODB200_ABI_VERSION 1
+
+#define OODB200_OK 0
+#define OODB200_ERR_INVALID (-1)  /* bad argument (null pointer, size out of range, ...) */
+#define OODB200_ERR_CUDA (-2)     /* CUDA runtime reported an error at launch            */
+
+/* metric slots / bit masks (reference: `metric` of the DistanceMethod subclasses,
+ * /root/reference/ood_utils.py:2574-2595) */
+#define OODB200_METRIC_L1 0
+#define OODB200_METRIC_L2 1
+#define OODB200_METRIC_COS 2
+#define OODB200_N_METRICS 3
+
+/* logit-method slots (reference: /root/reference/ood_utils.py:1388-1443; MaxLogit has no
+ * counterpart there) */
+#define OODB200_LOGIT_MSP 0
+#define OODB200_LOGIT_ENERGY 1
+#define OODB200_LOGIT_ODIN 2
+#define OODB200_LOGIT_SIGMOID 3
+#define OODB200_LOGIT_MAXLOGIT 4
+#define OODB200_N_LOGIT 5
+
+/* fusion strategies (reference: FusionMethod.fuse_ood_decisions :2906-2940,
+ * TripleFusionMethod.fuse_ood_decisions :3282-3301) */
+#define OODB200_FUSE_AND 0      /* elementwise max  */
+#define OODB200_FUSE_OR 1       /* elementwise min  */
+#define OODB200_FUSE_MAJORITY 2 /* a+b+c >= 2       */
+
+int oodb200_abi_version(void);
+const char* oodb200_last_error(void);
+
+/* ---- K1: per-detection RoIAlign pooling --------------------------------------------------
+ * Replaces `extract_roi_aligned_features_from_correct_stride`
+ * (/root/reference/ultralytics/models/yolo/detect/predict.py:13-90), i.e. torchvision
+ * roi_align(output_size=(1,1), sampling_ratio=-1, aligned=False) of every box on the map of its
+ * own stride.
+ *   map_ptrs   [n_img*3] device array of device pointers; map_ptrs[img*3+s] -> float32 [C_s,H_s,W_s]
+ *              contiguous (the per-image CHW tensors `Results.extra_item[0]` holds, no copy)
+ *   map_chw    host int32[9]: C,H,W of stride 0,1,2
+ *   scale      host float[3]: spatial_scale per stride = (float)(W_s / img_w)  (predict.py:68)
+ *   boxes      [n,4] xyxy float32 in input-image pixels; img_idx/stride_idx [n] int32
+ *   out        [n, out_ld] float32; row i gets C_{stride_idx[i]} values (rest untouched)
+ * A box whose stride_idx is outside {0,1,2} is skipped (the reference never pools it either).
+ */
+int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
+                         const float* boxes, const int32_t* img_idx, const int32_t* stride_idx, int n,
+                         float* out, int out_ld, void* stream);
+
+/* ---- K1+K2 fused: pool -> L2-normalise -> distance to the class/stride centroids -> min ->
+ *      threshold.  Replaces the per-image/per-stride/per-box loop of
+ * `DistanceMethod.compute_ood_decision_on_results` + `_compute_ood_decision_for_one_result_...`
+ * (/root/reference/ood_utils.py:2038-2180), `activations_transformation` (:2404-2409) and
+ * `compute_distance` (:2422-2430).
+ *   cls          [n] class used for the centroid/threshold lookup (the host passes the Q1 class
+ *                from oodb200_q1_plan_i32 in compat mode)
+ *   out_index    [n] or NULL: where box i writes its results (Q1 stride-major order); NULL = i
+ *   metric_mask  OR of (1<<OODB200_METRIC_*): every requested metric is scored in the same pass
+ *   normalize    1 = L2-normalise the pooled vector first (vanilla FMap methods); 0 = score as is
+ *   cent         packed float32 centroids; (stride s, class c) has cent_k[s*nc+c] rows of C_s floats
+ *                starting at element cent_off[s*nc+c]; cent_unit = same layout, rows L2-normalised
+ *                (needed for cosine only, may be NULL otherwise)
+ *   thr          [3 metrics][3*nc] float64, NaN = "no threshold" ([] / 0 / 0.0 in the reference,
+ *                ood_utils.py:2173) -> OoD
+ *   dist/argmin/decision   [3][n] (slot = metric id); only requested slots are written.
+ *                No cluster: dist 1000, argmin -1 (ood_utils.py:2159-2164).
+ *   pooled       optional [n, pooled_ld] raw pooled vectors (NULL to skip)
+ */
+int oodb200_fmap_score_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
+                           const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
+                           const int32_t* cls, const int32_t* out_index, int n,
+                           int metric_mask, int normalize,
+                           const float* cent, const float* cent_unit, const int64_t* cent_off, const int32_t* cent_k,
+                           int nc, const double* thr,
+                           float* dist, int32_t* argmin, uint8_t* decision,
+                           float* pooled, int pooled_ld, void* stream);
+
+/* ---- Q1 plan: the reference looks the class up with the in-stride index and emits decisions
+ * stride-major (/root/reference/ood_utils.py:2152-2154).  For box b of an image
+ * (local index b, stride s, j = number of earlier boxes of the same stride):
+ *   cls_used[b] = cls[img_start + j]      out_index[b] = img_start + #boxes(stride < s) + j
+ *   img_start  [n_img+1] int32 prefix of boxes per image
+ */
+int oodb200_q1_plan_i32(const int32_t* img_start, const int32_t* stride_idx, const int32_t* cls, int n_img,
+                        int32_t* cls_used, int32_t* out_index, void* stream);
+
+/* ---- K3: logit methods.  Replaces `LogitsMethod.compute_ood_decision_on_results` /
+ * `compute_INDness_scores_on_results` (/root/reference/ood_utils.py:1195-1257) and the scorers
+ * (:1388-1443).  One pass computes every method in method_mask.
+ *   logits [n, nc] float32 raw (pre-sigmoid) class logits; cls [n] int32
+ *   thr/smin/smax [5][nc] float64 (per-class threshold, min, max InD score); may be NULL -> only scores
+ *   scores [5][n] f32, indness [5][n] f32 (NULL to skip), decision [5][n] u8 (0 if score < thr else 1)
+ *   sigmoid_mismatch  optional int32[1] counter of boxes whose class is not the arg-max logit
+ *                     (the reference asserts on it, :1442)
+ */
+int oodb200_logit_score_f32(const float* logits, const int32_t* cls, int n, int nc, int method_mask,
+                            float t_energy, float t_odin, const double* thr, const double* smin, const double* smax,
+                            int clip_indness, float* scores, float* indness, uint8_t* decision,
+                            int32_t* sigmoid_mismatch, void* stream);
+
+/* ---- K6: fusion rules, position-wise (/root/reference/ood_utils.py:2906-2940, 3282-3301). */
+int oodb200_fuse_u8(const uint8_t* a, const uint8_t* b, const uint8_t* c, int n, int strategy, uint8_t* out, void* stream);
+int oodb200_fuse_score_f32(const float* s1, const float* s2, int n, uint8_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OODB200_H_ */

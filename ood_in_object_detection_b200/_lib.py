@@ -1,0 +1,66 @@
+"""ctypes binding of liboodb200.so (the C ABI declared in include/oodb200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if that fails, or a
+call returns an error code, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(_HERE, "..", "include", "oodb200.h")
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+_L = C.c_int64
+
+# name -> argtypes (restype is int unless listed in _RESTYPE); must mirror include/oodb200.h
+SIGNATURES = {
+    "oodb200_abi_version": [],
+    "oodb200_last_error": [],
+    "oodb200_roi_pool_f32": [_P, _P, _P, _I, _P, _P, _P, _I, _P, _I, _P],
+    "oodb200_fmap_score_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P,
+                               _P, _I, _P],
+    "oodb200_q1_plan_i32": [_P, _P, _P, _I, _P, _P, _P],
+    "oodb200_logit_score_f32": [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _I, _P, _P, _P, _P, _P],
+    "oodb200_fuse_u8": [_P, _P, _P, _I, _I, _P, _P],
+    "oodb200_fuse_score_f32": [_P, _P, _I, _P, _P],
+}
+_RESTYPE = {"oodb200_last_error": C.c_char_p}
+
+_lib = None
+
+
+def declared_symbols() -> list:
+    """Function names declared in include/oodb200.h."""
+    with open(HEADER) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(oodb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def load() -> C.CDLL:
+    """Load (building first if needed) the shared library; raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    lib = C.CDLL(path)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, C.c_int)
+    if lib.oodb200_abi_version() != 1:
+        raise RuntimeError("liboodb200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().oodb200_last_error()
+        raise RuntimeError(f"{what} failed ({code}): {msg.decode() if msg else ''}")

@@ -1,0 +1,281 @@
+"""Thin torch-tensor wrappers over the C ABI (include/oodb200.h).
+
+torch is used for device memory and streams only; every computation below happens in the
+hand-written CUDA kernels of liboodb200.so.  Nothing here has a CPU path: tensors that arrive
+on the host are copied to the device, the kernels run there.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+METRIC_SLOT = {"l1": 0, "manhattan": 0, "cityblock": 0, "l2": 1, "euclidean": 1, "cosine": 2}
+LOGIT_SLOT = {"MSP": 0, "Energy": 1, "ODIN": 2, "Sigmoid": 3, "MaxLogit": 4}
+FUSE_SLOT = {"and": 0, "or": 1, "majority_voting": 2}
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("ood_in_object_detection_b200 needs a CUDA device: there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _dev(t, device, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+@dataclass
+class DetectionBatch:
+    """Flat device-side view of a batch of detections and their hooked feature maps
+    (what `Results.boxes` / `Results.extra_item` hold per image in the reference, T1 in SURVEY.md §8a)."""
+    map_ptrs: torch.Tensor          # int64 [n_img*3] device pointers to the CHW maps
+    map_chw: np.ndarray             # host int32 [9]
+    scale: np.ndarray               # host float32 [3]
+    n_img: int
+    boxes: torch.Tensor             # [n,4] f32
+    img_idx: torch.Tensor           # [n] i32
+    stride_idx: torch.Tensor        # [n] i32
+    cls: torch.Tensor               # [n] i32
+    img_start: torch.Tensor         # [n_img+1] i32
+    counts: List[int]               # host copy of boxes per image
+    keepalive: tuple = ()           # tensors whose storage map_ptrs points into
+
+    @property
+    def n(self) -> int:
+        return int(self.boxes.shape[0])
+
+
+def make_batch(maps, boxes: Sequence, strides: Sequence, cls: Sequence, img_w: int, device=None) -> DetectionBatch:
+    """maps: either 3 batched tensors [B,C_s,H_s,W_s] or a per-image list of 3 CHW tensors.
+    boxes/strides/cls: per-image sequences ([M_i,4], [M_i], [M_i]); strides in {0,1,2}.
+    img_w: width of the network input (`res.orig_img.shape[2]`, predict.py:68)."""
+    device = device or default_device()
+    n_img = len(boxes)
+    keep = []
+    if len(maps) == 3 and all(isinstance(m, torch.Tensor) and m.dim() == 4 for m in maps):
+        mt = [_dev(m, device, torch.float32) for m in maps]
+        assert all(m.shape[0] == n_img for m in mt), "batched maps must have one slice per image"
+        chw = [tuple(m.shape[1:]) for m in mt]
+        ptrs = np.empty((n_img, 3), dtype=np.int64)
+        for s, m in enumerate(mt):
+            ptrs[:, s] = m.data_ptr() + np.arange(n_img, dtype=np.int64) * (m.stride(0) * 4)
+        keep = mt
+    else:
+        assert len(maps) == n_img, "maps must be 3 batched tensors or one list of 3 CHW tensors per image"
+        ptrs = np.empty((n_img, 3), dtype=np.int64)
+        chw = None
+        for i, per_img in enumerate(maps):
+            ts = [_dev(m, device, torch.float32) for m in per_img]
+            assert len(ts) == 3 and all(t.dim() == 3 for t in ts), "each image needs 3 CHW maps"
+            shp = [tuple(t.shape) for t in ts]
+            assert chw is None or shp == chw, "all images must share the map shapes"
+            chw = shp
+            ptrs[i] = [t.data_ptr() for t in ts]
+            keep.extend(ts)
+        if chw is None:
+            chw = [(1, 1, 1)] * 3
+    counts = [int(len(b)) for b in boxes]
+    n = sum(counts)
+    if n:
+        bx = torch.cat([_dev(b, device, torch.float32).reshape(-1, 4) for b in boxes])
+        st = torch.cat([_dev(s, device).reshape(-1) for s in strides]).to(torch.int32)
+        cl = torch.cat([_dev(c, device).reshape(-1) for c in cls]).to(torch.int32)
+    else:
+        bx = torch.zeros((0, 4), dtype=torch.float32, device=device)
+        st = torch.zeros(0, dtype=torch.int32, device=device)
+        cl = torch.zeros(0, dtype=torch.int32, device=device)
+    start = np.zeros(n_img + 1, dtype=np.int32)
+    np.cumsum(counts, out=start[1:])
+    img_idx = np.repeat(np.arange(n_img, dtype=np.int32), counts)
+    return DetectionBatch(
+        map_ptrs=torch.from_numpy(ptrs.reshape(-1)).to(device, non_blocking=True),
+        map_chw=np.asarray(chw, dtype=np.int32).reshape(9),
+        scale=np.asarray([np.float32(c[2] / img_w) for c in chw], dtype=np.float32),
+        n_img=n_img, boxes=bx, img_idx=torch.from_numpy(img_idx).to(device, non_blocking=True),
+        stride_idx=st, cls=cl, img_start=torch.from_numpy(start).to(device, non_blocking=True),
+        counts=counts, keepalive=tuple(keep))
+
+
+@dataclass
+class CentroidTable:
+    """Device-side packing of `clusters[cls][stride]` / `thresholds[cls][stride]` (SURVEY.md §5 format contract)."""
+    cent: torch.Tensor
+    cent_unit: torch.Tensor
+    cent_off: torch.Tensor     # int64 [3*nc]
+    cent_k: torch.Tensor       # int32 [3*nc]
+    thr: torch.Tensor          # float64 [3 metrics, 3*nc]
+    nc: int
+    k_host: np.ndarray         # [3, nc]
+
+
+def _unit_rows(a: np.ndarray) -> np.ndarray:
+    """sklearn.preprocessing.normalize on float32 rows (what cosine_distances applies to the centroids)."""
+    a = np.array(a, dtype=np.float32, copy=True)
+    nrm = np.sqrt(np.einsum("ij,ij->i", a, a))
+    nrm[nrm < 10 * np.finfo(np.float32).eps] = 1.0
+    a /= nrm[:, None]
+    return a
+
+
+def pack_centroids(clusters, thresholds_by_metric: dict, dims: Sequence[int], device=None) -> CentroidTable:
+    """clusters[cls][stride] = ndarray [K, C_s] or empty; thresholds_by_metric = {metric_slot: thresholds[cls][stride]}
+    with python floats or falsy entries ([] / 0 / 0.0 -> "no threshold", ood_utils.py:2173)."""
+    device = device or default_device()
+    nc = len(clusters)
+    off = np.zeros((3, nc), dtype=np.int64)
+    kk = np.zeros((3, nc), dtype=np.int32)
+    chunks, units = [], []
+    pos = 0
+    for s in range(3):
+        for c in range(nc):
+            a = clusters[c][s] if s < len(clusters[c]) else []
+            a = np.asarray(a, dtype=np.float32)
+            off[s, c] = pos
+            if a.size == 0:
+                continue
+            a = a.reshape(-1, a.shape[-1]) if a.ndim > 1 else a.reshape(1, -1)
+            if a.shape[1] != dims[s]:
+                raise ValueError(f"clusters[{c}][{s}] has {a.shape[1]} features, the stride-{s} map has {dims[s]} channels")
+            kk[s, c] = a.shape[0]
+            chunks.append(a.reshape(-1))
+            units.append(_unit_rows(a).reshape(-1))
+            pos += a.size
+            pos = (pos + 3) & ~3           # keep every slice 16-byte aligned for 128-bit loads
+            pad = pos - (int(off[s, c]) + a.size)
+            if pad:
+                chunks.append(np.zeros(pad, np.float32))
+                units.append(np.zeros(pad, np.float32))
+    flat = np.concatenate(chunks) if chunks else np.zeros(4, np.float32)
+    flat_u = np.concatenate(units) if units else np.zeros(4, np.float32)
+    thr = np.full((3, 3, nc), np.nan, dtype=np.float64)
+    for slot, th in thresholds_by_metric.items():
+        if th is None:
+            continue
+        for c in range(min(nc, len(th))):
+            for s in range(3):
+                v = th[c][s] if s < len(th[c]) else []
+                if isinstance(v, (list, tuple, np.ndarray)) and np.size(v) == 0:
+                    continue
+                if v:                                  # python truthiness, like the reference
+                    thr[slot, s, c] = float(v)
+    t = lambda a: torch.from_numpy(a).to(device, non_blocking=True)
+    return CentroidTable(cent=t(flat), cent_unit=t(flat_u), cent_off=t(off.reshape(-1)), cent_k=t(kk.reshape(-1)),
+                         thr=t(thr.reshape(3, 3 * nc)), nc=nc, k_host=kk)
+
+
+def q1_plan(batch: DetectionBatch):
+    """(cls_used, out_index) of the reference's quirk Q1 (ood_utils.py:2152-2154)."""
+    lib = _lib.load()
+    cls_used = torch.empty_like(batch.cls)
+    out_index = torch.empty_like(batch.cls)
+    _lib.check(lib.oodb200_q1_plan_i32(_ptr(batch.img_start), _ptr(batch.stride_idx), _ptr(batch.cls), batch.n_img,
+                                       _ptr(cls_used), _ptr(out_index), _stream()), "oodb200_q1_plan_i32")
+    return cls_used, out_index
+
+
+def roi_pool(batch: DetectionBatch, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K1: [n, Cmax] pooled vectors (row i valid up to C of its stride)."""
+    lib = _lib.load()
+    cmax = int(batch.map_chw.reshape(3, 3)[:, 0].max())
+    if out is None:
+        out = torch.zeros((batch.n, cmax), dtype=torch.float32, device=batch.boxes.device)
+    _lib.check(lib.oodb200_roi_pool_f32(
+        _ptr(batch.map_ptrs), batch.map_chw.ctypes.data_as(C.c_void_p), batch.scale.ctypes.data_as(C.c_void_p),
+        batch.n_img, _ptr(batch.boxes), _ptr(batch.img_idx), _ptr(batch.stride_idx), batch.n,
+        _ptr(out), int(out.stride(0)), _stream()), "oodb200_roi_pool_f32")
+    return out
+
+
+@dataclass
+class FmapScores:
+    dist: torch.Tensor        # [3, n] f32 (slot = metric)
+    argmin: torch.Tensor      # [3, n] i32
+    decision: torch.Tensor    # [3, n] u8
+    pooled: Optional[torch.Tensor]
+
+
+def fmap_score(batch: DetectionBatch, table: CentroidTable, metric_mask: int, normalize: bool = True,
+               cls: Optional[torch.Tensor] = None, out_index: Optional[torch.Tensor] = None,
+               want_pooled: bool = False, out: Optional[FmapScores] = None) -> FmapScores:
+    """K1+K2 fused pass over every box of the batch."""
+    lib = _lib.load()
+    dev = batch.boxes.device
+    n = batch.n
+    if out is None:
+        cmax = int(batch.map_chw.reshape(3, 3)[:, 0].max())
+        out = FmapScores(dist=torch.empty((3, n), dtype=torch.float32, device=dev),
+                         argmin=torch.empty((3, n), dtype=torch.int32, device=dev),
+                         decision=torch.zeros((3, n), dtype=torch.uint8, device=dev),
+                         pooled=torch.zeros((n, cmax), dtype=torch.float32, device=dev) if want_pooled else None)
+    _lib.check(lib.oodb200_fmap_score_f32(
+        _ptr(batch.map_ptrs), batch.map_chw.ctypes.data_as(C.c_void_p), batch.scale.ctypes.data_as(C.c_void_p),
+        batch.n_img, _ptr(batch.boxes), _ptr(batch.img_idx), _ptr(batch.stride_idx),
+        _ptr(batch.cls if cls is None else cls), _ptr(out_index), n, int(metric_mask), int(bool(normalize)),
+        _ptr(table.cent), _ptr(table.cent_unit), _ptr(table.cent_off), _ptr(table.cent_k), table.nc, _ptr(table.thr),
+        _ptr(out.dist), _ptr(out.argmin), _ptr(out.decision),
+        _ptr(out.pooled), int(out.pooled.stride(0)) if out.pooled is not None else 0, _stream()),
+        "oodb200_fmap_score_f32")
+    return out
+
+
+@dataclass
+class LogitScores:
+    scores: torch.Tensor      # [5, n] f32
+    indness: Optional[torch.Tensor]
+    decision: Optional[torch.Tensor]
+    sigmoid_mismatch: torch.Tensor   # int32[1]
+
+
+def logit_score(logits: torch.Tensor, cls: torch.Tensor, method_mask: int, t_energy: float = 1.0,
+                t_odin: float = 1000.0, thr: Optional[torch.Tensor] = None, smin: Optional[torch.Tensor] = None,
+                smax: Optional[torch.Tensor] = None, clip: bool = True, out: Optional[LogitScores] = None) -> LogitScores:
+    """K3: every requested logit method in one pass. thr/smin/smax: float64 [5, nc] device tensors."""
+    lib = _lib.load()
+    dev = logits.device
+    n, nc = int(logits.shape[0]), int(logits.shape[1])
+    if out is None:
+        out = LogitScores(scores=torch.zeros((5, n), dtype=torch.float32, device=dev),
+                          indness=torch.zeros((5, n), dtype=torch.float32, device=dev) if smin is not None else None,
+                          decision=torch.ones((5, n), dtype=torch.uint8, device=dev) if thr is not None else None,
+                          sigmoid_mismatch=torch.zeros(1, dtype=torch.int32, device=dev))
+    _lib.check(lib.oodb200_logit_score_f32(
+        _ptr(logits), _ptr(cls), n, nc, int(method_mask), float(t_energy), float(t_odin), _ptr(thr), _ptr(smin),
+        _ptr(smax), int(bool(clip)), _ptr(out.scores), _ptr(out.indness), _ptr(out.decision),
+        _ptr(out.sigmoid_mismatch), _stream()), "oodb200_logit_score_f32")
+    return out
+
+
+def fuse_decisions(a: torch.Tensor, b: torch.Tensor, strategy: str, c: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty_like(a)
+    _lib.check(lib.oodb200_fuse_u8(_ptr(a), _ptr(b), _ptr(c), int(a.numel()), FUSE_SLOT[strategy], _ptr(out), _stream()),
+               "oodb200_fuse_u8")
+    return out
+
+
+def fuse_scores(s1: torch.Tensor, s2: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(s1.shape, dtype=torch.uint8, device=s1.device)
+    _lib.check(lib.oodb200_fuse_score_f32(_ptr(s1), _ptr(s2), int(s1.numel()), _ptr(out), _stream()),
+               "oodb200_fuse_score_f32")
+    return out
