@@ -183,11 +183,11 @@ def pack_centroids(clusters, thresholds_by_metric: dict, dims: Sequence[int], de
                          thr=t(thr.reshape(3, 3 * nc)), nc=nc, k_host=kk)
 
 
-def q1_plan(batch: DetectionBatch):
+def q1_plan(batch: DetectionBatch, cls_used: Optional[torch.Tensor] = None, out_index: Optional[torch.Tensor] = None):
     """(cls_used, out_index) of the reference's quirk Q1 (ood_utils.py:2152-2154)."""
     lib = _lib.load()
-    cls_used = torch.empty_like(batch.cls)
-    out_index = torch.empty_like(batch.cls)
+    cls_used = torch.empty_like(batch.cls) if cls_used is None else cls_used
+    out_index = torch.empty_like(batch.cls) if out_index is None else out_index
     _lib.check(lib.oodb200_q1_plan_i32(_ptr(batch.img_start), _ptr(batch.stride_idx), _ptr(batch.cls), batch.n_img,
                                        _ptr(cls_used), _ptr(out_index), _stream()), "oodb200_q1_plan_i32")
     return cls_used, out_index
