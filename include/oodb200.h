@@ -64,22 +64,31 @@ const char* oodb200_last_error(void);
  *              contiguous (the per-image CHW tensors `Results.extra_item[0]` holds, no copy)
  *   map_chw    host int32[9]: C,H,W of stride 0,1,2
  *   scale      host float[3]: spatial_scale per stride = (float)(W_s / img_w)  (predict.py:68)
- *   boxes      [n,4] xyxy float32 in input-image pixels; img_idx/stride_idx [n] int32
+ *   boxes      [n,4] xyxy float32 in input-image pixels; img_idx/stride_idx [n] int32 (boxes of one image
+ *              are contiguous); img_start [n_img+1] int32 prefix of boxes per image
  *   out        [n, out_ld] float32; row i gets C_{stride_idx[i]} values (rest untouched)
  * A box whose stride_idx is outside {0,1,2} is skipped (the reference never pools it either).
  */
 int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
-                         const float* boxes, const int32_t* img_idx, const int32_t* stride_idx, int n,
-                         float* out, int out_ld, void* stream);
+                         const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
+                         const int32_t* img_start, int n,
+                         float* out, int out_ld, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Scratch the two pooling entry points need (device memory, 256-byte aligned, owned by the caller; its
+ * contents need not be preserved between calls).  need_pooled = 1 when fmap_score is called with
+ * pooled == NULL (the pooled vectors then live in the workspace). */
+int64_t oodb200_fmap_workspace_bytes(int n, const int32_t* map_chw, int need_pooled);
 
 /* ---- K1+K2 fused: pool -> L2-normalise -> distance to the class/stride centroids -> min ->
  *      threshold.  Replaces the per-image/per-stride/per-box loop of
  * `DistanceMethod.compute_ood_decision_on_results` + `_compute_ood_decision_for_one_result_...`
  * (/root/reference/ood_utils.py:2038-2180), `activations_transformation` (:2404-2409) and
  * `compute_distance` (:2422-2430).
- *   cls          [n] class used for the centroid/threshold lookup (the host passes the Q1 class
- *                from oodb200_q1_plan_i32 in compat mode)
- *   out_index    [n] or NULL: where box i writes its results (Q1 stride-major order); NULL = i
+ *   cls          [n] predicted class of every box (`res.boxes.cls`)
+ *   img_start    [n_img+1] int32 prefix of boxes per image
+ *   compat_q1    1 = the reference's behaviour (ood_utils.py:2152-2154): the class used for
+ *                the centroid / threshold lookup is the one of the box with the same IN-STRIDE index, and
+ *                results are written stride-major within each image.  0: class of the box itself, box order.
  *   metric_mask  OR of (1<<OODB200_METRIC_*): every requested metric is scored in the same pass
  *   normalize    1 = L2-normalise the pooled vector first (vanilla FMap methods); 0 = score as is
  *   cent         packed float32 centroids; (stride s, class c) has cent_k[s*nc+c] rows of C_s floats
@@ -89,18 +98,22 @@ int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t* map_chw, c
  *                ood_utils.py:2173) -> OoD
  *   dist/argmin/decision   [3][n] (slot = metric id); only requested slots are written.
  *                No cluster: dist 1000, argmin -1 (ood_utils.py:2159-2164).
- *   pooled       optional [n, pooled_ld] raw pooled vectors (NULL to skip)
+ *   pooled       optional [n, pooled_ld] raw pooled vectors (NULL to skip), rows in OUTPUT order
+ *   cls_used_out / out_index_out   optional [n] int32: class used and output slot of every box
+ *   workspace    see oodb200_fmap_workspace_bytes
  */
 int oodb200_fmap_score_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
                            const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
-                           const int32_t* cls, const int32_t* out_index, int n,
+                           const int32_t* cls, const int32_t* img_start, int compat_q1, int n,
                            int metric_mask, int normalize,
                            const float* cent, const float* cent_unit, const int64_t* cent_off, const int32_t* cent_k,
                            int nc, const double* thr,
                            float* dist, int32_t* argmin, uint8_t* decision,
-                           float* pooled, int pooled_ld, void* stream);
+                           float* pooled, int pooled_ld, int32_t* cls_used_out, int32_t* out_index_out,
+                           void* workspace, int64_t workspace_bytes, void* stream);
 
-/* ---- Q1 plan: the reference looks the class up with the in-stride index and emits decisions
+/* ---- Q1 plan (standalone; oodb200_fmap_score_f32 does the same internally when img_start != NULL):
+ * the reference looks the class up with the in-stride index and emits decisions
  * stride-major (/root/reference/ood_utils.py:2152-2154).  For box b of an image
  * (local index b, stride s, j = number of earlier boxes of the same stride):
  *   cls_used[b] = cls[img_start + j]      out_index[b] = img_start + #boxes(stride < s) + j

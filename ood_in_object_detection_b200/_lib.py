@@ -23,15 +23,16 @@ _L = C.c_int64
 SIGNATURES = {
     "oodb200_abi_version": [],
     "oodb200_last_error": [],
-    "oodb200_roi_pool_f32": [_P, _P, _P, _I, _P, _P, _P, _I, _P, _I, _P],
-    "oodb200_fmap_score_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P,
-                               _P, _I, _P],
+    "oodb200_roi_pool_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _L, _P],
+    "oodb200_fmap_workspace_bytes": [_I, _P, _I],
+    "oodb200_fmap_score_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P,
+                               _P, _I, _P, _P, _P, _L, _P],
     "oodb200_q1_plan_i32": [_P, _P, _P, _I, _P, _P, _P],
     "oodb200_logit_score_f32": [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "oodb200_fuse_u8": [_P, _P, _P, _I, _I, _P, _P],
     "oodb200_fuse_score_f32": [_P, _P, _I, _P, _P],
 }
-_RESTYPE = {"oodb200_last_error": C.c_char_p}
+_RESTYPE = {"oodb200_last_error": C.c_char_p, "oodb200_fmap_workspace_bytes": C.c_int64}
 
 _lib = None
 
@@ -48,7 +49,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    path = os.environ.get("OODB200_LIB") or _build.build()     # OODB200_LIB: a pre-built variant (tuning runs)
     lib = C.CDLL(path)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)

@@ -4,19 +4,25 @@
 // with output 1x1, adaptive sampling grid, aligned=False) and the per-box loop of
 // /root/reference/ood_utils.py:2038-2180 (+ :2404-2409 normalize, :2422-2430 pairwise distance + min).
 //
-// One CTA per detection.
-//  1. The RoIAlign sample grid factorises: sum_{iy,ix} bilinear(y_iy, x_ix) = sum_r sum_c wy[r] wx[c] v[r,c],
-//     because both the bilinear weights and the "sample outside [-1,H]x[-1,W] contributes 0" mask are
-//     products of a y-term and an x-term.  Each CTA builds wy[], wx[] (sample coordinates are evaluated
-//     with the exact float32 operation order of the reference kernel, no FMA contraction), so every
-//     feature-map element of the window is read ONCE instead of ~4 times.
-//  2. Window gather: lanes run over the flattened window (x fastest -> consecutive lanes read consecutive
-//     addresses of a row), warps run over channels, 4 channels x R positions of loads in flight per lane,
-//     warp-shuffle reduction per channel.  NCHW rows are short (8..52 B per box), so the unit of DRAM
-//     traffic is the 32-byte sector; see DESIGN.md for the roofline accounting.
-//  3. Pooled vector stays in shared memory: L2 norm, then every centroid of (class, stride) is streamed
-//     once (128-bit loads, L2-resident table), L1 / L2 / cosine evaluated in the same sweep, first-minimum
-//     arg-min, threshold compare in float64.
+// Two launches per batch:
+//  plan_kernel  one small CTA per image: quirk-Q1 class / output slot of every box, and three per-stride box
+//               lists so that the main grid runs the heaviest boxes (largest stride = most channels) first and
+//               keeps boxes of one image adjacent (overlapping windows then hit in L2).
+//  fmap_kernel  one CTA (8 warps) per detection.
+//   1. The RoIAlign sample grid factorises: sum_{iy,ix} bilinear(y_iy, x_ix) = sum_r sum_c wy[r] wx[c] v[r,c],
+//      because both the bilinear weights and the "sample outside [-1,H]x[-1,W] contributes 0" mask are
+//      products of a y-term and an x-term.  Each CTA builds wy[], wx[] (sample coordinates are evaluated
+//      with the exact float32 operation order of the reference kernel, no FMA contraction), so every
+//      feature-map element of the window is read ONCE instead of ~4 times.
+//   2. Window gather: lanes run over the flattened window (x fastest -> consecutive lanes read consecutive
+//      addresses of an NCHW row), warps run over groups of CU channels.  Loads of the next channel group are
+//      issued before the current group is reduced (double buffer in registers); channel offsets are immediates
+//      of the load for the usual map sizes; one butterfly reduction per CU channels instead of CU full
+//      warp reductions.  NCHW rows of a box are short (8..52 B), so the unit of DRAM traffic is the 32-byte
+//      sector; see DESIGN.md for the roofline accounting.
+//   3. Pooled vector stays in shared memory: L2 norm, then every centroid of (class, stride) is streamed
+//      once (128-bit loads, L2-resident table), L1 / L2 / cosine evaluated in the same sweep, first-minimum
+//      arg-min, threshold compare in float64.
 #include "common.cuh"
 
 #include <float.h>
@@ -26,19 +32,25 @@ namespace oodb200 {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kCU = 4;   // channels in flight per warp
+constexpr unsigned kFull = 0xffffffffu;
+#ifndef OODB200_FMAP_DOUBLE_BUFFER
+#define OODB200_FMAP_DOUBLE_BUFFER 0
+#endif
+#ifndef OODB200_FMAP_MIN_BLOCKS
+#define OODB200_FMAP_MIN_BLOCKS 6
+#endif
 
 struct FmapParams {
     const float* const* map_ptrs;
     int C[3], H[3], W[3];
     float scale[3];
-    int n_img;
     const float* boxes;
     const int32_t* img_idx;
     const int32_t* stride_idx;
     const int32_t* cls;
-    const int32_t* out_index;
-    int n;
+    const int32_t* img_start;   // [n_img+1] prefix of boxes per image
+    int compat_q1;              // quirk Q1: class by in-stride index, stride-major output
+    int n, n_img;
     int metric_mask;
     int normalize;
     const float* cent;
@@ -52,8 +64,13 @@ struct FmapParams {
     uint8_t* decision;
     float* pooled;
     int pooled_ld;
-    int ext_pad;   // smem floats reserved for each of wy / wx
-    int c_pad;     // smem floats reserved for each of xs / xu
+    // plan (workspace or caller-provided)
+    int* counts;                // [4] boxes per stride (device counters, zeroed by a memset)
+    int* lists;                 // [3][n] box ids per stride, image-major
+    int32_t* cls_used;          // [n]
+    int32_t* out_index;         // [n]
+    int ext_pad;                // smem floats reserved for each of wy / wx
+    int c_pad;                  // smem floats reserved for each of xs / xu
 };
 
 struct AxisSample {
@@ -114,22 +131,50 @@ __device__ __forceinline__ float axis_weight(float start, float size, int grid, 
     return acc;
 }
 
-// Accumulate sum_p w_p * v[c, p] for every channel into acc_s[c]; window positions are consumed in chunks
-// of 32*R so that offsets/weights live in registers.
-template <int R>
-__device__ __forceinline__ void pool_window(const float* __restrict__ img, int C, int HW, int W, int y0, int x0,
+// Reduce N per-lane partial sums to N channel totals; afterwards every lane of group (lane >> (5 - log2 N))
+// holds the total of channel (lane >> (5 - log2 N)).
+template <int N>
+__device__ __forceinline__ float butterfly(float (&v)[N], int lane) {
+    int o = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1, o >>= 1) {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, o);
+        }
+    }
+    float r = v[0];
+    for (; o > 0; o >>= 1) r += __shfl_xor_sync(kFull, r, o);
+    return r;
+}
+
+template <int N> struct Log2 { static constexpr int v = 1 + Log2<N / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
+
+// Accumulate sum_p w_p * v[c, p] for every channel into acc_s[c].  R window positions per lane (chunks of 32*R),
+// CU channels per warp step, HWC = H*W when known at compile time (0: run-time stride).
+template <int R, int CU, int HWC>
+__device__ __forceinline__ void pool_window(const float* __restrict__ img, int C, int hw_rt, int W, int y0, int x0,
                                             int wh, int ww, const float* wy, const float* wx, float* acc_s) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int HW = HWC ? HWC : hw_rt;
     const int P = wh * ww;
+    const float inv_ww = 1.0f / (float)ww;
+    constexpr int kStep = kWarps * CU;
     for (int base = 0; base < P; base += 32 * R) {
         int off[R];
         float wt[R];
 #pragma unroll
         for (int t = 0; t < R; ++t) {
-            const int p = base + lane + 32 * t;
-            if (p < P) {
-                const int y = p / ww;
-                const int x = p - y * ww;
+            const int q = base + lane + 32 * t;
+            if (q < P) {
+                int y = (int)(((float)q + 0.5f) * inv_ww);
+                if (y * ww > q) --y;
+                else if ((y + 1) * ww <= q) ++y;
+                const int x = q - y * ww;
                 off[t] = (y0 + y) * W + (x0 + x);
                 wt[t] = wy[y] * wx[x];
             } else {
@@ -137,29 +182,71 @@ __device__ __forceinline__ void pool_window(const float* __restrict__ img, int C
                 wt[t] = 0.f;
             }
         }
-        for (int c0 = warp * kCU; c0 < C; c0 += kWarps * kCU) {
-            float a[kCU];
+        auto load = [&](float (&v)[CU][R], int c0) {
+            const float* __restrict__ b = img + (size_t)c0 * HW;
+            if (c0 + CU <= C) {
 #pragma unroll
-            for (int u = 0; u < kCU; ++u) {
-                const int c = (c0 + u < C) ? c0 + u : C - 1;
-                const float* __restrict__ b = img + (size_t)c * HW;
+                for (int t = 0; t < R; ++t) {
+                    const float* __restrict__ pt = b + off[t];
+#pragma unroll
+                    for (int u = 0; u < CU; ++u) v[u][t] = ldg_f32(pt + u * HW);
+                }
+            } else {                                     // C % CU != 0: clamp (results of the extra channels are dropped)
+#pragma unroll
+                for (int t = 0; t < R; ++t)
+#pragma unroll
+                    for (int u = 0; u < CU; ++u) v[u][t] = ldg_f32(b + min(u, C - 1 - c0) * HW + off[t]);
+            }
+        };
+        auto consume = [&](float (&v)[CU][R], int c0) {
+            float a[CU];
+#pragma unroll
+            for (int u = 0; u < CU; ++u) {
                 float s = 0.f;
 #pragma unroll
-                for (int t = 0; t < R; ++t) s = fmaf(wt[t], ldg_f32(b + off[t]), s);
+                for (int t = 0; t < R; ++t) s = fmaf(wt[t], v[u][t], s);
                 a[u] = s;
             }
-#pragma unroll
-            for (int u = 0; u < kCU; ++u) a[u] = warp_sum(a[u]);
-            if (lane == 0) {
-#pragma unroll
-                for (int u = 0; u < kCU; ++u)
-                    if (c0 + u < C) acc_s[c0 + u] = (base == 0) ? a[u] : acc_s[c0 + u] + a[u];
-            }
+            const float tot = butterfly<CU>(a, lane);
+            const int c = c0 + (lane >> (5 - Log2<CU>::v));
+            if ((lane & (32 / CU - 1)) == 0 && c < C) acc_s[c] = (base == 0) ? tot : acc_s[c] + tot;
+        };
+#if OODB200_FMAP_DOUBLE_BUFFER
+        float va[CU][R], vb[CU][R];
+        int c0 = warp * CU;
+        if (c0 < C) load(va, c0);
+        while (c0 < C) {                                 // ping-pong: next group's loads fly under this group's math
+            int cn = c0 + kStep;
+            if (cn < C) load(vb, cn);
+            consume(va, c0);
+            c0 = cn;
+            if (c0 >= C) break;
+            cn = c0 + kStep;
+            if (cn < C) load(va, cn);
+            consume(vb, c0);
+            c0 = cn;
         }
+#else
+        for (int c0 = warp * CU; c0 < C; c0 += kStep) {
+            float va[CU][R];
+            load(va, c0);
+            consume(va, c0);
+        }
+#endif
     }
 }
 
-__global__ void __launch_bounds__(kThreads) fmap_kernel(const FmapParams p) {
+template <int HWC>
+__device__ __forceinline__ void pool_dispatch(const float* img, int C, int hw, int W, int y0, int x0, int wh, int ww,
+                                              const float* wy, const float* wx, float* acc_s) {
+    const int P = wh * ww;
+    if (P <= 32) pool_window<1, 8, HWC>(img, C, hw, W, y0, x0, wh, ww, wy, wx, acc_s);
+    else if (P <= 64) pool_window<2, 4, HWC>(img, C, hw, W, y0, x0, wh, ww, wy, wx, acc_s);
+    else if (P <= 128) pool_window<4, 2, HWC>(img, C, hw, W, y0, x0, wh, ww, wy, wx, acc_s);
+    else pool_window<8, 2, HWC>(img, C, hw, W, y0, x0, wh, ww, wy, wx, acc_s);
+}
+
+__global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) fmap_kernel(const FmapParams p) {
     extern __shared__ __align__(16) float smem[];
     float* wy = smem;
     float* wx = wy + p.ext_pad;
@@ -171,11 +258,16 @@ __global__ void __launch_bounds__(kThreads) fmap_kernel(const FmapParams p) {
     __shared__ int s_warg[OODB200_N_METRICS][kWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int box = blockIdx.x;
+    // heaviest stride first (largest-processing-time-first keeps the tail short)
+    int i = blockIdx.x, box;
+    const int n2 = p.counts[2], n1 = p.counts[1], n0 = p.counts[0];
+    if (i < n2) box = p.lists[2 * p.n + i];
+    else if ((i -= n2) < n1) box = p.lists[p.n + i];
+    else if ((i -= n1) < n0) box = p.lists[i];
+    else return;                                      // boxes with an invalid stride were answered by the plan kernel
     const int s = p.stride_idx[box];
-    if (s < 0 || s > 2) return;                       // never pooled by the reference either
     const int img = p.img_idx[box];
-    const int out = p.out_index ? p.out_index[box] : box;
+    const int out = p.out_index[box];
     const int C = p.C[s], H = p.H[s], W = p.W[s];
 
     // ---- ROI geometry (predict.py:64-70 -> roi_align, aligned=False) ----
@@ -191,9 +283,9 @@ __global__ void __launch_bounds__(kThreads) fmap_kernel(const FmapParams p) {
         s_win[0] = INT_MAX; s_win[1] = -1; s_win[2] = INT_MAX; s_win[3] = -1;
     }
     __syncthreads();
-    for (int i = tid; i < gh + gw; i += kThreads) {
-        const bool isy = i < gh;
-        const AxisSample a = isy ? axis_sample(sh, rh, gh, H, i) : axis_sample(sw, rw, gw, W, i - gh);
+    for (int k = tid; k < gh + gw; k += kThreads) {
+        const bool isy = k < gh;
+        const AxisSample a = isy ? axis_sample(sh, rh, gh, H, k) : axis_sample(sw, rw, gw, W, k - gh);
         if (a.valid) {
             atomicMin(&s_win[isy ? 0 : 2], a.low);
             atomicMax(&s_win[isy ? 1 : 3], a.high);
@@ -217,32 +309,34 @@ __global__ void __launch_bounds__(kThreads) fmap_kernel(const FmapParams p) {
         for (int c = tid; c < C; c += kThreads) xs[c] = 0.f;
     } else {
         const float* img_base = p.map_ptrs[img * 3 + s];
-        const int P = wh * ww;
         const int HW = H * W;
-        if (P <= 32) pool_window<1>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs);
-        else if (P <= 64) pool_window<2>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs);
-        else if (P <= 128) pool_window<4>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs);
-        else pool_window<8>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs);
+        switch (HW) {                                 // map sizes of 320/640/1280-pixel inputs: immediate channel offsets
+            case 400: pool_dispatch<400>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs); break;
+            case 1600: pool_dispatch<1600>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs); break;
+            case 6400: pool_dispatch<6400>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs); break;
+            case 25600: pool_dispatch<25600>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs); break;
+            default: pool_dispatch<0>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs); break;
+        }
     }
     __syncthreads();
+    // ---- average (roi_align.py:192-196) and, for K2, the squared norm in the same sweep ----
+    float ss = 0.f;
     for (int c = tid; c < C; c += kThreads) {
         const float v = empty ? 0.f : __fdiv_rn(xs[c], count);
         xs[c] = v;
+        ss = fmaf(v, v, ss);
         if (p.pooled) p.pooled[(size_t)out * p.pooled_ld + c] = v;
     }
     if (p.cent == nullptr) return;                    // K1 only
 
     // ---- K2: normalise (ood_utils.py:2409 -> sklearn normalize) ----
-    float ss = 0.f;
-    __syncthreads();
     if (p.normalize) {
-        for (int c = tid; c < C; c += kThreads) ss = fmaf(xs[c], xs[c], ss);
         ss = block_sum<kWarps>(ss, s_red);
         float nrm = sqrtf(ss);
         if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;      // _handle_zeros_in_scale
         for (int c = tid; c < C; c += kThreads) xs[c] = __fdiv_rn(xs[c], nrm);
-        __syncthreads();
     }
+    __syncthreads();
     const bool want_l1 = p.metric_mask & (1 << OODB200_METRIC_L1);
     const bool want_l2 = p.metric_mask & (1 << OODB200_METRIC_L2);
     const bool want_cos = p.metric_mask & (1 << OODB200_METRIC_COS);
@@ -250,14 +344,14 @@ __global__ void __launch_bounds__(kThreads) fmap_kernel(const FmapParams p) {
         float s2 = 0.f;
         for (int c = tid; c < C; c += kThreads) s2 = fmaf(xs[c], xs[c], s2);
         s2 = block_sum<kWarps>(s2, s_red);
-        float n2 = sqrtf(s2);
-        if (n2 < 10.f * FLT_EPSILON) n2 = 1.f;
-        for (int c = tid; c < C; c += kThreads) xu[c] = __fdiv_rn(xs[c], n2);
+        float n2v = sqrtf(s2);
+        if (n2v < 10.f * FLT_EPSILON) n2v = 1.f;
+        for (int c = tid; c < C; c += kThreads) xu[c] = __fdiv_rn(xs[c], n2v);
         __syncthreads();
     }
 
     // ---- distances to the centroids of (class, stride); warps stride over centroids ----
-    const int cls = p.cls[box];
+    const int cls = p.cls_used[box];
     const bool cls_ok = cls >= 0 && cls < p.nc;
     const int K = cls_ok ? p.cent_k[s * p.nc + cls] : 0;
     float best[OODB200_N_METRICS] = {FLT_MAX, FLT_MAX, FLT_MAX};
@@ -333,33 +427,98 @@ __global__ void __launch_bounds__(kThreads) fmap_kernel(const FmapParams p) {
     }
 }
 
-// per-image plan for quirk Q1 (ood_utils.py:2152-2154): one CTA per image
+// One CTA per image: quirk Q1 (ood_utils.py:2152-2154) and the per-stride box lists (image-major inside a stride).
+__global__ void __launch_bounds__(128) plan_kernel(const FmapParams p) {
+    const int img = blockIdx.x;
+    const int b0 = p.img_start[img], m = p.img_start[img + 1] - b0;
+    __shared__ int s_cnt[4], s_base[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int b = threadIdx.x; b < m; b += blockDim.x) {
+        const int s = p.stride_idx[b0 + b];
+        atomicAdd(&s_cnt[(s >= 0 && s <= 2) ? s : 3], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&p.counts[threadIdx.x], s_cnt[threadIdx.x]) : 0;
+    __syncthreads();
+    for (int b = threadIdx.x; b < m; b += blockDim.x) {
+        const int s = p.stride_idx[b0 + b];
+        const bool ok = s >= 0 && s <= 2;
+        int j = 0;                                    // rank among earlier boxes of the same kind (m <= 300)
+        for (int e = 0; e < b; ++e) {
+            const int se = p.stride_idx[b0 + e];
+            j += ok ? (se == s) : !(se >= 0 && se <= 2);
+        }
+        int before = 0;
+        for (int t = 0; t < (ok ? s : 3); ++t) before += s_cnt[t];
+        int cls_u = p.cls ? p.cls[b0 + b] : 0, out = b0 + b;
+        if (p.compat_q1) {
+            cls_u = ok ? p.cls[b0 + j] : -1;
+            out = b0 + before + j;
+        }
+        p.cls_used[b0 + b] = cls_u;
+        p.out_index[b0 + b] = out;
+        if (ok) {
+            p.lists[s * p.n + s_base[s] + j] = b0 + b;
+        } else if (p.cent) {                          // never pooled by the reference either: answered here
+            for (int k = 0; k < OODB200_N_METRICS; ++k)
+                if (p.metric_mask >> k & 1) {
+                    const size_t o = (size_t)k * p.n + out;
+                    p.dist[o] = nanf("");
+                    p.argmin[o] = -1;
+                    p.decision[o] = 0;
+                }
+        }
+    }
+}
+
+// standalone Q1 plan (same arithmetic as plan_kernel, without the lists)
 __global__ void q1_plan_kernel(const int32_t* __restrict__ img_start, const int32_t* __restrict__ stride_idx,
                                const int32_t* __restrict__ cls, int32_t* __restrict__ cls_used,
                                int32_t* __restrict__ out_index) {
     const int img = blockIdx.x;
     const int b0 = img_start[img], m = img_start[img + 1] - b0;
-    __shared__ int s_cnt[3];
-    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __shared__ int s_cnt[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     for (int b = threadIdx.x; b < m; b += blockDim.x) {
         const int s = stride_idx[b0 + b];
-        if (s >= 0 && s <= 2) atomicAdd(&s_cnt[s], 1);
+        atomicAdd(&s_cnt[(s >= 0 && s <= 2) ? s : 3], 1);
     }
     __syncthreads();
     for (int b = threadIdx.x; b < m; b += blockDim.x) {
         const int s = stride_idx[b0 + b];
-        if (s < 0 || s > 2) { cls_used[b0 + b] = -1; out_index[b0 + b] = b0 + b; continue; }
-        int j = 0;                                    // rank among earlier boxes of the same stride (m <= 300)
-        for (int e = 0; e < b; ++e) j += (stride_idx[b0 + e] == s);
+        const bool ok = s >= 0 && s <= 2;
+        int j = 0;
+        for (int e = 0; e < b; ++e) {
+            const int se = stride_idx[b0 + e];
+            j += ok ? (se == s) : !(se >= 0 && se <= 2);
+        }
         int before = 0;
-        for (int t = 0; t < s; ++t) before += s_cnt[t];
-        cls_used[b0 + b] = cls[b0 + j];
+        for (int t = 0; t < (ok ? s : 3); ++t) before += s_cnt[t];
+        cls_used[b0 + b] = ok ? cls[b0 + j] : -1;
         out_index[b0 + b] = b0 + before + j;
     }
 }
 
-static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale, void* stream, const char* what) {
+struct WorkspaceLayout {
+    size_t counts, lists, cls_used, out_index, total;
+};
+
+static WorkspaceLayout layout_of(int n) {
+    WorkspaceLayout L;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = 0;
+    L.counts = o; o = up(o + 16);
+    L.lists = o; o = up(o + sizeof(int) * 3 * (size_t)n);
+    L.cls_used = o; o = up(o + sizeof(int) * (size_t)n);
+    L.out_index = o; o = up(o + sizeof(int) * (size_t)n);
+    L.total = o;
+    return L;
+}
+
+static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale, int32_t* cls_used_out,
+                       int32_t* out_index_out, void* workspace, int64_t workspace_bytes, void* stream, const char* what) {
     int ext = 1, cmax = 1;
     for (int s = 0; s < 3; ++s) {
         p.C[s] = map_chw[3 * s];
@@ -375,11 +534,26 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     const size_t smem = sizeof(float) * (2 * (size_t)p.ext_pad + 2 * (size_t)p.c_pad);
     OODB200_REQUIRE(smem <= 200 * 1024, "%s: maps too large for the shared-memory layout (%zu B)", what, smem);
     if (p.n == 0) return OODB200_OK;
+    const WorkspaceLayout L = layout_of(p.n);
+    OODB200_REQUIRE(workspace && workspace_bytes >= (int64_t)L.total, "%s: workspace too small (%lld < %zu bytes)", what,
+                    (long long)workspace_bytes, L.total);
+    OODB200_REQUIRE(((uintptr_t)workspace & 255) == 0, "%s: workspace must be 256-byte aligned", what);
+    char* ws = (char*)workspace;
+    p.counts = (int*)(ws + L.counts);
+    p.lists = (int*)(ws + L.lists);
+    p.cls_used = cls_used_out ? cls_used_out : (int32_t*)(ws + L.cls_used);
+    p.out_index = out_index_out ? out_index_out : (int32_t*)(ws + L.out_index);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(p.counts, 0, 16, st);
+    if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+    plan_kernel<<<p.n_img, 128, 0, st>>>(p);
+    int rc = check_launch(what);
+    if (rc) return rc;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(fmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(fmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
     }
-    fmap_kernel<<<p.n, kThreads, smem, (cudaStream_t)stream>>>(p);
+    fmap_kernel<<<p.n, kThreads, smem, st>>>(p);
     return check_launch(what);
 }
 
@@ -387,41 +561,50 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
 
 using namespace oodb200;
 
+extern "C" int64_t oodb200_fmap_workspace_bytes(int n, const int32_t* map_chw, int need_pooled) {
+    (void)map_chw; (void)need_pooled;
+    if (n <= 0) return 256;
+    return (int64_t)layout_of(n).total;
+}
+
 extern "C" int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
-                                    const float* boxes, const int32_t* img_idx, const int32_t* stride_idx, int n,
-                                    float* out, int out_ld, void* stream) {
+                                    const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
+                                    const int32_t* img_start, int n,
+                                    float* out, int out_ld, void* workspace, int64_t workspace_bytes, void* stream) {
     OODB200_REQUIRE(n >= 0 && n_img >= 0, "roi_pool: negative size");
     OODB200_REQUIRE(map_chw && scale, "roi_pool: map_chw/scale must be host arrays");
     if (n == 0) return OODB200_OK;
-    OODB200_REQUIRE(map_ptrs && boxes && img_idx && stride_idx && out, "roi_pool: null pointer");
+    OODB200_REQUIRE(map_ptrs && boxes && img_idx && stride_idx && img_start && out, "roi_pool: null pointer");
     FmapParams p = {};
-    p.map_ptrs = map_ptrs; p.n_img = n_img; p.boxes = boxes; p.img_idx = img_idx; p.stride_idx = stride_idx;
-    p.n = n; p.pooled = out; p.pooled_ld = out_ld;
-    return launch_fmap(p, map_chw, scale, stream, "roi_pool");
+    p.map_ptrs = map_ptrs; p.boxes = boxes; p.img_idx = img_idx; p.stride_idx = stride_idx; p.img_start = img_start;
+    p.n = n; p.n_img = n_img; p.pooled = out; p.pooled_ld = out_ld;
+    return launch_fmap(p, map_chw, scale, nullptr, nullptr, workspace, workspace_bytes, stream, "roi_pool");
 }
 
 extern "C" int oodb200_fmap_score_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
                                       const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
-                                      const int32_t* cls, const int32_t* out_index, int n,
+                                      const int32_t* cls, const int32_t* img_start, int compat_q1, int n,
                                       int metric_mask, int normalize,
                                       const float* cent, const float* cent_unit, const int64_t* cent_off,
                                       const int32_t* cent_k, int nc, const double* thr,
                                       float* dist, int32_t* argmin, uint8_t* decision,
-                                      float* pooled, int pooled_ld, void* stream) {
+                                      float* pooled, int pooled_ld, int32_t* cls_used_out, int32_t* out_index_out,
+                                      void* workspace, int64_t workspace_bytes, void* stream) {
     OODB200_REQUIRE(n >= 0 && n_img >= 0 && nc > 0, "fmap_score: bad size");
     OODB200_REQUIRE(map_chw && scale, "fmap_score: map_chw/scale must be host arrays");
     OODB200_REQUIRE(metric_mask > 0 && metric_mask < (1 << OODB200_N_METRICS), "fmap_score: metric_mask %d", metric_mask);
     if (n == 0) return OODB200_OK;
-    OODB200_REQUIRE(map_ptrs && boxes && img_idx && stride_idx && cls, "fmap_score: null input pointer");
+    OODB200_REQUIRE(map_ptrs && boxes && img_idx && stride_idx && cls && img_start, "fmap_score: null input pointer");
     OODB200_REQUIRE(cent && cent_off && cent_k && thr, "fmap_score: null centroid/threshold table");
     OODB200_REQUIRE(!(metric_mask & (1 << OODB200_METRIC_COS)) || cent_unit, "fmap_score: cosine needs cent_unit");
     OODB200_REQUIRE(dist && argmin && decision, "fmap_score: null output pointer");
     FmapParams p = {};
-    p.map_ptrs = map_ptrs; p.n_img = n_img; p.boxes = boxes; p.img_idx = img_idx; p.stride_idx = stride_idx;
-    p.cls = cls; p.out_index = out_index; p.n = n; p.metric_mask = metric_mask; p.normalize = normalize;
+    p.map_ptrs = map_ptrs; p.boxes = boxes; p.img_idx = img_idx; p.stride_idx = stride_idx;
+    p.cls = cls; p.img_start = img_start; p.compat_q1 = compat_q1; p.n = n; p.n_img = n_img;
+    p.metric_mask = metric_mask; p.normalize = normalize;
     p.cent = cent; p.cent_unit = cent_unit; p.cent_off = cent_off; p.cent_k = cent_k; p.nc = nc; p.thr = thr;
     p.dist = dist; p.argmin = argmin; p.decision = decision; p.pooled = pooled; p.pooled_ld = pooled_ld;
-    return launch_fmap(p, map_chw, scale, stream, "fmap_score");
+    return launch_fmap(p, map_chw, scale, cls_used_out, out_index_out, workspace, workspace_bytes, stream, "fmap_score");
 }
 
 extern "C" int oodb200_q1_plan_i32(const int32_t* img_start, const int32_t* stride_idx, const int32_t* cls, int n_img,

@@ -184,7 +184,7 @@ def pack_centroids(clusters, thresholds_by_metric: dict, dims: Sequence[int], de
 
 
 def q1_plan(batch: DetectionBatch, cls_used: Optional[torch.Tensor] = None, out_index: Optional[torch.Tensor] = None):
-    """(cls_used, out_index) of the reference's quirk Q1 (ood_utils.py:2152-2154)."""
+    """(cls_used, out_index) of the reference's quirk Q1 (ood_utils.py:2152-2154), standalone."""
     lib = _lib.load()
     cls_used = torch.empty_like(batch.cls) if cls_used is None else cls_used
     out_index = torch.empty_like(batch.cls) if out_index is None else out_index
@@ -193,16 +193,32 @@ def q1_plan(batch: DetectionBatch, cls_used: Optional[torch.Tensor] = None, out_
     return cls_used, out_index
 
 
+_workspaces = {}
+
+
+def _workspace(batch: DetectionBatch, need_pooled: bool) -> torch.Tensor:
+    """Scratch for the pooling kernels (grown on demand, one per device; kernels on one stream reuse it in order)."""
+    lib = _lib.load()
+    need = int(lib.oodb200_fmap_workspace_bytes(batch.n, batch.map_chw.ctypes.data_as(C.c_void_p), int(need_pooled)))
+    dev = batch.boxes.device
+    ws = _workspaces.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+        _workspaces[dev] = ws
+    return ws
+
+
 def roi_pool(batch: DetectionBatch, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """K1: [n, Cmax] pooled vectors (row i valid up to C of its stride)."""
     lib = _lib.load()
     cmax = int(batch.map_chw.reshape(3, 3)[:, 0].max())
     if out is None:
         out = torch.zeros((batch.n, cmax), dtype=torch.float32, device=batch.boxes.device)
+    ws = _workspace(batch, False)
     _lib.check(lib.oodb200_roi_pool_f32(
         _ptr(batch.map_ptrs), batch.map_chw.ctypes.data_as(C.c_void_p), batch.scale.ctypes.data_as(C.c_void_p),
-        batch.n_img, _ptr(batch.boxes), _ptr(batch.img_idx), _ptr(batch.stride_idx), batch.n,
-        _ptr(out), int(out.stride(0)), _stream()), "oodb200_roi_pool_f32")
+        batch.n_img, _ptr(batch.boxes), _ptr(batch.img_idx), _ptr(batch.stride_idx), _ptr(batch.img_start), batch.n,
+        _ptr(out), int(out.stride(0)), _ptr(ws), int(ws.numel()), _stream()), "oodb200_roi_pool_f32")
     return out
 
 
@@ -211,29 +227,39 @@ class FmapScores:
     dist: torch.Tensor        # [3, n] f32 (slot = metric)
     argmin: torch.Tensor      # [3, n] i32
     decision: torch.Tensor    # [3, n] u8
-    pooled: Optional[torch.Tensor]
+    pooled: Optional[torch.Tensor] = None
+    cls_used: Optional[torch.Tensor] = None     # [n] i32, per input box
+    out_index: Optional[torch.Tensor] = None    # [n] i32, output slot of every input box
+
+
+def alloc_fmap_scores(n: int, device, cmax: int = 0, want_pooled: bool = False, want_plan: bool = False) -> FmapScores:
+    return FmapScores(dist=torch.empty((3, n), dtype=torch.float32, device=device),
+                      argmin=torch.empty((3, n), dtype=torch.int32, device=device),
+                      decision=torch.zeros((3, n), dtype=torch.uint8, device=device),
+                      pooled=torch.zeros((n, cmax), dtype=torch.float32, device=device) if want_pooled else None,
+                      cls_used=torch.empty(n, dtype=torch.int32, device=device) if want_plan else None,
+                      out_index=torch.empty(n, dtype=torch.int32, device=device) if want_plan else None)
 
 
 def fmap_score(batch: DetectionBatch, table: CentroidTable, metric_mask: int, normalize: bool = True,
-               cls: Optional[torch.Tensor] = None, out_index: Optional[torch.Tensor] = None,
-               want_pooled: bool = False, out: Optional[FmapScores] = None) -> FmapScores:
-    """K1+K2 fused pass over every box of the batch."""
+               compat_q1: bool = True, want_pooled: bool = False, want_plan: bool = False,
+               out: Optional[FmapScores] = None) -> FmapScores:
+    """K1+K2 fused pass over every box of the batch.  compat_q1=True reproduces the reference's class lookup by
+    in-stride index and its stride-major output order; False = class of the box itself, box order."""
     lib = _lib.load()
-    dev = batch.boxes.device
     n = batch.n
     if out is None:
         cmax = int(batch.map_chw.reshape(3, 3)[:, 0].max())
-        out = FmapScores(dist=torch.empty((3, n), dtype=torch.float32, device=dev),
-                         argmin=torch.empty((3, n), dtype=torch.int32, device=dev),
-                         decision=torch.zeros((3, n), dtype=torch.uint8, device=dev),
-                         pooled=torch.zeros((n, cmax), dtype=torch.float32, device=dev) if want_pooled else None)
+        out = alloc_fmap_scores(n, batch.boxes.device, cmax, want_pooled, want_plan)
+    ws = _workspace(batch, out.pooled is None)
     _lib.check(lib.oodb200_fmap_score_f32(
         _ptr(batch.map_ptrs), batch.map_chw.ctypes.data_as(C.c_void_p), batch.scale.ctypes.data_as(C.c_void_p),
-        batch.n_img, _ptr(batch.boxes), _ptr(batch.img_idx), _ptr(batch.stride_idx),
-        _ptr(batch.cls if cls is None else cls), _ptr(out_index), n, int(metric_mask), int(bool(normalize)),
+        batch.n_img, _ptr(batch.boxes), _ptr(batch.img_idx), _ptr(batch.stride_idx), _ptr(batch.cls),
+        _ptr(batch.img_start), int(bool(compat_q1)), n, int(metric_mask), int(bool(normalize)),
         _ptr(table.cent), _ptr(table.cent_unit), _ptr(table.cent_off), _ptr(table.cent_k), table.nc, _ptr(table.thr),
         _ptr(out.dist), _ptr(out.argmin), _ptr(out.decision),
-        _ptr(out.pooled), int(out.pooled.stride(0)) if out.pooled is not None else 0, _stream()),
+        _ptr(out.pooled), int(out.pooled.stride(0)) if out.pooled is not None else 0,
+        _ptr(out.cls_used), _ptr(out.out_index), _ptr(ws), int(ws.numel()), _stream()),
         "oodb200_fmap_score_f32")
     return out
 

@@ -76,15 +76,16 @@ def test_fused_scoring_matches_reference(ops, golden, name):
     thr = {ops.METRIC_SLOT[m]: unpack_nested(g, f"{t}_thr", nc, as_threshold=True)
            for t, m in (("l1", "l1"), ("l2", "l2"), ("cos", "cosine"))}
     table = ops.pack_centroids(clusters, thr, dims)
-    cls_used, out_index = ops.q1_plan(batch)
-    res = ops.fmap_score(batch, table, 0b111, True, cls=cls_used, out_index=out_index)
+    res = ops.fmap_score(batch, table, 0b111, True, compat_q1=True, want_plan=True)
     torch.cuda.synchronize()
     dist, dec, arg = res.dist.cpu().numpy(), res.decision.cpu().numpy(), res.argmin.cpu().numpy()
     # Q1 bookkeeping: class looked up with the in-stride index, stride-major output order
-    pos = out_index.cpu().numpy()
+    pos = res.out_index.cpu().numpy()
     assert np.array_equal(np.sort(pos), np.arange(batch.n))
     cls_out = np.empty(batch.n, np.int32)
-    cls_out[pos] = cls_used.cpu().numpy()
+    cls_out[pos] = res.cls_used.cpu().numpy()
+    cu2, oi2 = ops.q1_plan(batch)                      # the standalone plan entry agrees
+    assert np.array_equal(oi2.cpu().numpy(), pos) and np.array_equal(cu2.cpu().numpy(), res.cls_used.cpu().numpy())
     n_exempt = 0
     for tag, metric in (("l1", "l1"), ("l2", "l2"), ("cos", "cosine")):
         m = ops.METRIC_SLOT[metric]
@@ -109,12 +110,10 @@ def test_quirks(ops, golden):
     batch = _batch_from_images(ops, [im], img)
     clusters = unpack_nested(g, "clusters", 3)
     dims = [c.shape[1] for c in clusters[0]]
-    cls_used, out_index = ops.q1_plan(batch)
 
     def run(cl, thr, compat=True):
         table = ops.pack_centroids(cl, {1: thr}, dims)
-        r = ops.fmap_score(batch, table, 0b010, True, cls=cls_used if compat else None,
-                           out_index=out_index if compat else None)
+        r = ops.fmap_score(batch, table, 0b010, True, compat_q1=compat)
         return r.decision[1].cpu().numpy().tolist(), r.dist[1].cpu().numpy()
 
     cases = {"q1": [[1e9] * 3, [1e-9] * 3, [1e-9] * 3], "q4_zero": [[0.0] * 3, [1e9] * 3, [1e9] * 3],
@@ -182,7 +181,6 @@ def test_fused_scoring_vs_oracle_at_config_shapes(ops, cfg, batch, lam, k):
     images = [dict(maps=[m[i] for m in maps], boxes=det["boxes"][i], cls=det["cls"][i], strides=det["strides"][i],
                    img_hw=(wl.img, wl.img)) for i in range(batch)]
     batch_d = _batch_from_images(ops, images, wl.img)
-    cls_used, out_index = ops.q1_plan(batch_d)
     thr_by = {}
     oracle_out = {}
     for metric in ("l1", "l2", "cosine"):
@@ -194,7 +192,7 @@ def test_fused_scoring_vs_oracle_at_config_shapes(ops, cfg, batch, lam, k):
         thr_by[ops.METRIC_SLOT[metric]] = thr
         oracle_out[metric] = (d, np.array([t[1] for im in det_o for t in im]), med)
     table = ops.pack_centroids(clusters, thr_by, list(wl.channels))
-    res = ops.fmap_score(batch_d, table, 0b111, True, cls=cls_used, out_index=out_index)
+    res = ops.fmap_score(batch_d, table, 0b111, True, compat_q1=True)
     torch.cuda.synchronize()
     for metric, (d, a, med) in oracle_out.items():
         m = ops.METRIC_SLOT[metric]
