@@ -140,6 +140,58 @@ int oodb200_logit_score_f32(const float* logits, const int32_t* cls, int n, int 
 int oodb200_fuse_u8(const uint8_t* a, const uint8_t* b, const uint8_t* c, int n, int strategy, uint8_t* out, void* stream);
 int oodb200_fuse_score_f32(const float* s1, const float* s2, int n, uint8_t* out, void* stream);
 
+/* ---- K2 standalone on already-pooled vectors (fit-time scoring), segmented.
+ * Replaces `compute_scores_one_class_one_stride` (/root/reference/ood_utils.py:2000-2036):
+ * normalize + pairwise_distances(...).min(axis=0) per (class, stride) segment.
+ *   x [n_rows, ld] float32 (first `dim` columns used); seg_off device int64 [n_seg+1] row offsets;
+ *   segment g is scored against rows cent_row_off[g] .. +cent_k[g] of cent [*, dim]
+ *   dist / argmin [3][n_rows] (slot = metric id; only requested slots written)
+ */
+int oodb200_vec_score_f32(const float* x, int64_t ld, int dim, const int64_t* seg_off, int n_seg, int64_t n_rows,
+                          int metric_mask, int normalize,
+                          const float* cent, const float* cent_unit, const int64_t* cent_row_off, const int32_t* cent_k,
+                          float* dist, int32_t* argmin, void* stream);
+
+/* ---- K5: one pass of an exact radix select over float32 score bit patterns, segmented.
+ * Replaces `np.percentile(scores, q, method='lower')` (/root/reference/ood_utils.py:613,626): the host
+ * computes the order-statistic index numpy would use, then narrows 11+11+10 key bits with three passes.
+ *   hist [n_seg, 1<<bits] uint32 is ACCUMULATED INTO (caller zeroes); a key is counted when its bits above
+ *   (shift+bits) equal prefix[g] (no condition when shift+bits == 32); bin = (key >> shift) & ((1<<bits)-1).
+ *   key = order-preserving transform of the float32 bits (negative: ~b, else b | 0x80000000).
+ *   minmax optional [n_seg][2] uint32 keys, min/max ACCUMULATED with integer atomics (caller sets 0xFFFFFFFF / 0).
+ */
+int oodb200_radix_hist_u32(const float* scores, const int64_t* seg_off, int n_seg, int64_t n_rows,
+                           const uint32_t* prefix, int shift, int bits, uint32_t* hist, uint32_t* minmax, void* stream);
+
+/* ---- K4: k-means (Lloyd) over segmented data: every (class, stride) problem advances in the same launches.
+ * Replaces sklearn `lloyd_iter_chunked_dense` / `_average_centers` / `_center_shift` behind
+ * `KMeans(n_clusters=k, random_state=10).fit_predict(X)` (/root/reference/cluster_utils.py:62-73).
+ *
+ * kmeans_step: one CTA per block of rows (block b covers rows [block_row0[b], block_row1[b]) of segment
+ *   block_seg[b]; blocks never straddle segments).  labels[r] = argmin_k ||c_k||^2 - 2 x_r.c_k (first minimum);
+ *   n_changed[g] += rows whose label changed (labels is read as the previous assignment; -1 initially).
+ *   update != 0: psums [n_blocks, k, dim] / pcounts [n_blocks, k] receive the block's per-cluster sums and
+ *   counts, accumulated in row order (bit-reproducible).  active [n_seg] (or NULL): segments with 0 are skipped.
+ *   x [n_rows, dim] float32, already mean-centred per segment by the caller; cent [n_seg, k, dim]; seg_k [n_seg].
+ * kmeans_reduce: out[grp] = sum of in[b] for b in [first[grp], first[grp+1]) in increasing b (fixed order).
+ * kmeans_update: centres = sums * (1/count) (sklearn arithmetic), empty clusters keep the old centre and are
+ *   counted in n_empty[g]; shift_sq[g] = sum_k ||new_k - old_k||^2.
+ * sqdist_cand (k-means++ seeding): out_d[j, r] = min(closest[r], d(x_r, cand[g,j,:])) with d evaluated like
+ *   sklearn's float64 expansion cast to float32; pot[g, j] += sum_r out_d[j, r] (float64).
+ */
+int64_t oodb200_kmeans_smem_bytes(int k, int dim);
+int oodb200_kmeans_step_f32(const float* x, int dim, int n_seg, int k, const int32_t* seg_k, const float* cent,
+                            const int32_t* block_seg, const int64_t* block_row0, const int64_t* block_row1, int n_blocks,
+                            const int32_t* active, int32_t* labels, float* psums, float* pcounts, int32_t* n_changed,
+                            int update, void* stream);
+int oodb200_kmeans_reduce_f32(const float* in, const int32_t* first, int n_groups, int64_t elems, float* out, void* stream);
+int oodb200_kmeans_update_f32(const float* sums, const float* counts, const float* cent_old, const int32_t* seg_k,
+                              const int32_t* active, int n_seg, int k, int dim, float* cent_new, float* shift_sq,
+                              int32_t* n_empty, void* stream);
+int oodb200_sqdist_cand_f32(const float* x, int dim, const int64_t* seg_off, int n_seg, int64_t max_seg_rows,
+                            const float* cand, int n_cand, const float* closest, float* out_d, double* pot,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

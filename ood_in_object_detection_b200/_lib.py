@@ -31,8 +31,16 @@ SIGNATURES = {
     "oodb200_logit_score_f32": [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "oodb200_fuse_u8": [_P, _P, _P, _I, _I, _P, _P],
     "oodb200_fuse_score_f32": [_P, _P, _I, _P, _P],
+    "oodb200_vec_score_f32": [_P, _L, _I, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "oodb200_radix_hist_u32": [_P, _P, _I, _L, _P, _I, _I, _P, _P, _P],
+    "oodb200_kmeans_smem_bytes": [_I, _I],
+    "oodb200_kmeans_step_f32": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P],
+    "oodb200_kmeans_reduce_f32": [_P, _P, _I, _L, _P, _P],
+    "oodb200_kmeans_update_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "oodb200_sqdist_cand_f32": [_P, _I, _P, _I, _L, _P, _I, _P, _P, _P, _P],
 }
-_RESTYPE = {"oodb200_last_error": C.c_char_p, "oodb200_fmap_workspace_bytes": C.c_int64}
+_RESTYPE = {"oodb200_last_error": C.c_char_p, "oodb200_fmap_workspace_bytes": C.c_int64,
+            "oodb200_kmeans_smem_bytes": C.c_int64}
 
 _lib = None
 

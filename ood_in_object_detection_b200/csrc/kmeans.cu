@@ -1,0 +1,387 @@
+// K4: k-means (Lloyd) over segmented data -- every (class, stride) problem in one launch, sm_100a.
+//
+// Replaces sklearn's `lloyd_iter_chunked_dense` (+ `_average_centers`, `_center_shift`) behind
+// `KMeans(n_clusters=k, random_state=10).fit_predict(X)`  (/root/reference/cluster_utils.py:62-73, called per
+// (class, stride) from /root/reference/ood_utils.py:2345), and the distance passes of `_kmeans_plusplus`.
+//
+//  kmeans_step    one CTA per fixed block of rows of one segment.  Centroids of the segment are resident in
+//                 shared memory.  Each warp takes one row into registers (128-bit coalesced loads), computes
+//                 ||c||^2 - 2 x.c against all centroids (16 partial dots per lane, one butterfly reduction per
+//                 16 centroids) and the first-minimum label.  The 8 rows of a chunk are then added into the
+//                 block's shared-memory sums column-wise (thread = column, rows in order): no atomics, so the
+//                 block partial is bit-reproducible.  Partials go to global memory.
+//  kmeans_reduce  sums consecutive block partials in a FIXED order -> the result does not depend on how blocks
+//                 were scheduled, nor (with the two-level scheme of kmeans.py) on the number of GPUs.
+//  kmeans_update  new centres (sklearn `_average_centers` arithmetic), squared centre shift per segment.
+//  sqdist_cand    squared distances of candidate seeds to every row, float64 expansion cast to float32 like
+//                 sklearn's `_euclidean_distances_upcast`, fused with the min against `closest` and the
+//                 per-candidate potential.
+// HBM-bound stream over X (4*D bytes per row per iteration); K=16 needs 2*K flop per 4 bytes = 8 flop/B, below the
+// FP32 ridge, so the dot products stay on the FP32 pipe.
+#include "common.cuh"
+
+#include <float.h>
+#include <limits.h>
+
+namespace oodb200 {
+
+constexpr int kKmThreads = 256;
+constexpr int kKmWarps = kKmThreads / 32;
+constexpr int kKG = 16;                       // centroids per butterfly group
+constexpr unsigned kFullMask = 0xffffffffu;
+
+struct KmParams {
+    const float* x;
+    int dim, d_pad;
+    int k;                                    // centroids per segment (table stride)
+    const int32_t* seg_k;                     // [n_seg] centroids actually used (<= k)
+    const float* cent;                        // [n_seg, k, dim]
+    const int32_t* block_seg;                 // [n_blocks]
+    const int64_t* block_row0;                // [n_blocks + 1]... row range = [row0[b], row_end[b])
+    const int64_t* block_row1;
+    const int32_t* active;                    // [n_seg] or null
+    int32_t* labels;
+    float* psums;                             // [n_blocks, k, dim]
+    float* pcounts;                           // [n_blocks, k]
+    int32_t* n_changed;                       // [n_seg]
+    int update;
+};
+
+__device__ __forceinline__ float butterfly16(float (&v)[kKG], int lane) {
+#pragma unroll
+    for (int o = 16, n = kKG; n > 1; o >>= 1, n >>= 1) {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFullMask, send, o);
+        }
+    }
+    return v[0] + __shfl_xor_sync(kFullMask, v[0], 1);   // lanes 2u, 2u+1 hold value u
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(kKmThreads) kmeans_step_kernel(const KmParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int D = p.dim, Dp = p.d_pad, K = p.k;
+    float* s_cent = smem;                          // [K][Dp]
+    float* s_sum = s_cent + (size_t)K * Dp;        // [K][Dp]
+    float* s_stage = s_sum + (size_t)K * Dp;       // [8][Dp]
+    float* s_csn = s_stage + (size_t)kKmWarps * Dp; // [K]
+    float* s_cnt = s_csn + K;                      // [K]
+    __shared__ int s_lab[kKmWarps];
+    __shared__ int s_changed;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    const int g = p.block_seg[b];
+    if (p.active && !p.active[g]) return;
+    const int Kg = p.seg_k[g];
+    const int64_t r0 = p.block_row0[b], r1 = p.block_row1[b];
+    const float* __restrict__ cg = p.cent + (size_t)g * K * D;
+    for (int i = tid; i < K * Dp; i += kKmThreads) {
+        const int k = i / Dp, d = i - k * Dp;
+        s_cent[i] = (k < Kg && d < D) ? __ldg(cg + (size_t)k * D + d) : 0.f;
+        s_sum[i] = 0.f;
+    }
+    if (tid < K) s_cnt[tid] = 0.f;
+    if (tid == 0) s_changed = 0;
+    __syncthreads();
+    for (int k = warp; k < K; k += kKmWarps) {     // ||c||^2 (row_norms(centers, squared=True))
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) s = fmaf(s_cent[k * Dp + d], s_cent[k * Dp + d], s);
+        s = warp_sum(s);
+        if (lane == 0) s_csn[k] = s;
+    }
+    __syncthreads();
+    const int n_groups = (Kg + kKG - 1) / kKG;
+    for (int64_t base = r0; base < r1; base += kKmWarps) {
+        const int64_t r = base + warp;
+        const bool have = r < r1;
+        if (have) {
+            const float* __restrict__ xr = p.x + r * D;
+            float4 xv[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int d = lane * 4 + 128 * j;
+                if (d + 3 < D) xv[j] = __ldg(reinterpret_cast<const float4*>(xr + d));
+                else {
+                    xv[j].x = d < D ? __ldg(xr + d) : 0.f;
+                    xv[j].y = d + 1 < D ? __ldg(xr + d + 1) : 0.f;
+                    xv[j].z = d + 2 < D ? __ldg(xr + d + 2) : 0.f;
+                    xv[j].w = 0.f;
+                }
+                if (p.update && d < Dp) *reinterpret_cast<float4*>(s_stage + (size_t)warp * Dp + d) = xv[j];
+            }
+            float best = FLT_MAX;
+            int barg = 0;
+            for (int grp = 0; grp < n_groups; ++grp) {
+                float dot[kKG];
+#pragma unroll
+                for (int u = 0; u < kKG; ++u) {
+                    const float* __restrict__ ck = s_cent + (size_t)min(grp * kKG + u, K - 1) * Dp;
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int d = lane * 4 + 128 * j;
+                        if (d < Dp) {
+                            const float4 c4 = *reinterpret_cast<const float4*>(ck + d);
+                            s = fmaf(xv[j].x, c4.x, s); s = fmaf(xv[j].y, c4.y, s);
+                            s = fmaf(xv[j].z, c4.z, s); s = fmaf(xv[j].w, c4.w, s);
+                        }
+                    }
+                    dot[u] = s;
+                }
+                const float tot = butterfly16(dot, lane);
+                const int kk = grp * kKG + (lane >> 1);
+                float pd = kk < Kg ? fmaf(-2.0f, tot, s_csn[kk]) : FLT_MAX;   // gemm(alpha=-2, beta=1) on ||c||^2
+                int pk = kk < Kg ? kk : INT_MAX;
+#pragma unroll
+                for (int o = 16; o > 1; o >>= 1) {                           // first minimum across the group
+                    const float od = __shfl_xor_sync(kFullMask, pd, o);
+                    const int ok = __shfl_xor_sync(kFullMask, pk, o);
+                    if (od < pd || (od == pd && ok < pk)) { pd = od; pk = ok; }
+                }
+                if (pd < best) { best = pd; barg = pk; }                     // strict <: earlier group wins ties
+            }
+            if (lane == 0) {
+                s_lab[warp] = barg;
+                if (p.labels[r] != barg) atomicAdd(&s_changed, 1);
+                p.labels[r] = barg;
+            }
+        } else if (lane == 0) {
+            s_lab[warp] = -1;
+        }
+        if (!p.update) continue;
+        __syncthreads();
+        // column-wise accumulation of the chunk's rows, in row order: deterministic
+        for (int d = tid; d < D; d += kKmThreads) {
+#pragma unroll
+            for (int w = 0; w < kKmWarps; ++w) {
+                const int l = s_lab[w];
+                if (l >= 0) s_sum[(size_t)l * Dp + d] += s_stage[(size_t)w * Dp + d];
+            }
+        }
+        if (tid == 0) {
+#pragma unroll
+            for (int w = 0; w < kKmWarps; ++w)
+                if (s_lab[w] >= 0) s_cnt[s_lab[w]] += 1.f;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0 && s_changed) atomicAdd(&p.n_changed[g], s_changed);
+    if (p.update) {
+        float* __restrict__ ps = p.psums + (size_t)b * K * D;
+        for (int i = tid; i < K * D; i += kKmThreads) {
+            const int k = i / D, d = i - k * D;
+            ps[i] = s_sum[(size_t)k * Dp + d];
+        }
+        if (tid < K) p.pcounts[(size_t)b * K + tid] = s_cnt[tid];
+    }
+}
+
+// out[grp, e] = sum over blocks b in [first[grp], first[grp+1]) of in[b, e], sequentially in b
+__global__ void kmeans_reduce_kernel(const float* __restrict__ in, const int32_t* __restrict__ first, int n_groups,
+                                     int64_t elems, float* __restrict__ out) {
+    const int grp = blockIdx.y;
+    const int b0 = first[grp], b1 = first[grp + 1];
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < elems; e += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int b = b0; b < b1; ++b) s += in[(size_t)b * elems + e];
+        out[(size_t)grp * elems + e] = s;
+    }
+}
+
+// sklearn _average_centers + _center_shift (squared, summed per segment); empty clusters keep their old centre
+__global__ void kmeans_update_kernel(const float* __restrict__ sums, const float* __restrict__ counts,
+                                     const float* __restrict__ cent_old, const int32_t* __restrict__ seg_k,
+                                     const int32_t* __restrict__ active, int k, int dim, float* __restrict__ cent_new,
+                                     float* __restrict__ shift_sq, int32_t* __restrict__ n_empty) {
+    const int g = blockIdx.x;
+    if (active && !active[g]) return;
+    __shared__ float s_red[32];
+    const int Kg = seg_k[g];
+    float tot = 0.f;
+    for (int kk = 0; kk < Kg; ++kk) {
+        const float w = counts[(size_t)g * k + kk];
+        const float alpha = w > 0.f ? (float)(1.0 / (double)w) : 0.f;
+        float sh = 0.f;
+        for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+            const size_t i = ((size_t)g * k + kk) * dim + d;
+            const float c = w > 0.f ? sums[i] * alpha : cent_old[i];
+            cent_new[i] = c;
+            const float df = c - cent_old[i];
+            sh = fmaf(df, df, sh);
+        }
+        sh = warp_sum(sh);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sh;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+            tot += t;                                   // (sqrt(t))^2 in sklearn; equal up to one rounding
+            if (!(w > 0.f)) atomicAdd(&n_empty[g], 1);
+        }
+    }
+    if (threadIdx.x == 0) shift_sq[g] = tot;
+}
+
+// d[j, r] = max(float32(||y_j||^2 - 2 x_r.y_j + ||x_r||^2 in float64), 0); newd = min(closest, d); pot[j] += sum newd
+struct CandParams {
+    const float* x;
+    int dim;
+    const int64_t* seg_off;
+    int n_seg;
+    const float* cand;                         // [n_seg, n_cand, dim] candidate vectors
+    int n_cand;
+    const float* closest;                      // [n_rows] or null (first centre)
+    float* out_d;                              // [n_cand, n_rows] min(closest, d)
+    double* pot;                               // [n_seg, n_cand]
+};
+
+__global__ void __launch_bounds__(256) sqdist_cand_kernel(const CandParams p) {
+    extern __shared__ __align__(16) double s_y[];              // [n_cand][dim] + norms
+    const int g = blockIdx.y;
+    const int D = p.dim, NC = p.n_cand;
+    double* s_yy = s_y + (size_t)NC * D;
+    __shared__ double s_pot[8][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < NC * D; i += blockDim.x) {
+        const int j = i / D, d = i - j * D;
+        s_y[i] = (double)p.cand[((size_t)g * NC + j) * D + d];
+    }
+    __syncthreads();
+    if (warp < NC) {
+        double s = 0.0;
+        for (int d = lane; d < D; d += 32) s += s_y[warp * D + d] * s_y[warp * D + d];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+        if (lane == 0) s_yy[warp] = s;
+    }
+    __syncthreads();
+    const int64_t r0 = p.seg_off[g], r1 = p.seg_off[g + 1];
+    const int64_t n_rows = p.seg_off[p.n_seg];
+    double pot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t r = r0 + (int64_t)blockIdx.x * 8 + warp; r < r1; r += (int64_t)gridDim.x * 8) {
+        const float* __restrict__ xr = p.x + r * D;
+        double xx = 0.0, dot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int d = lane; d < D; d += 32) {
+            const double v = (double)__ldg(xr + d);
+            xx += v * v;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < NC) dot[j] += v * s_y[j * D + d];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            xx += __shfl_xor_sync(kFullMask, xx, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < NC) dot[j] += __shfl_xor_sync(kFullMask, dot[j], o);
+        }
+        if (lane == 0) {
+            const float cl = p.closest ? p.closest[r] : FLT_MAX;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < NC) {
+                    float d32 = (float)(-2.0 * dot[j] + s_yy[j] + xx);
+                    d32 = fminf(fmaxf(d32, 0.f), cl);
+                    p.out_d[(size_t)j * n_rows + r] = d32;
+                    pot[j] += (double)d32;
+                }
+        }
+    }
+    if (lane == 0)
+        for (int j = 0; j < 8; ++j) s_pot[warp][j] = pot[j];
+    __syncthreads();
+    if (threadIdx.x < NC) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_pot[w][threadIdx.x];
+        atomicAdd(&p.pot[(size_t)g * NC + threadIdx.x], t);
+    }
+}
+
+}  // namespace oodb200
+
+using namespace oodb200;
+
+extern "C" int64_t oodb200_kmeans_smem_bytes(int k, int dim) {
+    const int dp = (dim + 3) & ~3;
+    return (int64_t)sizeof(float) * ((size_t)2 * k * dp + (size_t)kKmWarps * dp + 2 * k);
+}
+
+extern "C" int oodb200_kmeans_step_f32(const float* x, int dim, int n_seg, int k, const int32_t* seg_k, const float* cent,
+                                       const int32_t* block_seg, const int64_t* block_row0, const int64_t* block_row1,
+                                       int n_blocks, const int32_t* active, int32_t* labels, float* psums, float* pcounts,
+                                       int32_t* n_changed, int update, void* stream) {
+    OODB200_REQUIRE(dim > 0 && dim <= 1024 && k > 0 && n_seg >= 0 && n_blocks >= 0, "kmeans_step: bad size (dim <= 1024)");
+    if (n_blocks == 0) return OODB200_OK;
+    OODB200_REQUIRE(x && seg_k && cent && block_seg && block_row0 && block_row1 && labels && n_changed, "kmeans_step: null pointer");
+    OODB200_REQUIRE(!update || (psums && pcounts), "kmeans_step: update needs the partial buffers");
+    const int64_t smem = oodb200_kmeans_smem_bytes(k, dim);
+    OODB200_REQUIRE(smem <= 220 * 1024, "kmeans_step: k*dim = %d*%d does not fit shared memory (%lld B)", k, dim, (long long)smem);
+    KmParams p = {x, dim, (dim + 3) & ~3, k, seg_k, cent, block_seg, block_row0, block_row1, active, labels, psums, pcounts,
+                  n_changed, update};
+    const int nj = (dim + 127) / 128;
+    cudaStream_t st = (cudaStream_t)stream;
+#define OODB200_KM_LAUNCH(NJ)                                                                                          \
+    case NJ: {                                                                                                         \
+        if (smem > 48 * 1024) {                                                                                        \
+            cudaError_t e = cudaFuncSetAttribute(kmeans_step_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                                 (int)smem);                                                           \
+            if (e != cudaSuccess) { set_error("kmeans_step: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }    \
+        }                                                                                                              \
+        kmeans_step_kernel<NJ><<<n_blocks, kKmThreads, smem, st>>>(p);                                                 \
+    } break;
+    switch (nj) {
+        OODB200_KM_LAUNCH(1) OODB200_KM_LAUNCH(2) OODB200_KM_LAUNCH(3) OODB200_KM_LAUNCH(4)
+        OODB200_KM_LAUNCH(5) OODB200_KM_LAUNCH(6) OODB200_KM_LAUNCH(7) OODB200_KM_LAUNCH(8)
+        default: set_error("kmeans_step: dim %d", dim); return OODB200_ERR_INVALID;
+    }
+#undef OODB200_KM_LAUNCH
+    return check_launch("kmeans_step");
+}
+
+extern "C" int oodb200_kmeans_reduce_f32(const float* in, const int32_t* first, int n_groups, int64_t elems, float* out,
+                                         void* stream) {
+    OODB200_REQUIRE(n_groups >= 0 && elems >= 0, "kmeans_reduce: negative size");
+    if (n_groups == 0 || elems == 0) return OODB200_OK;
+    OODB200_REQUIRE(in && first && out, "kmeans_reduce: null pointer");
+    OODB200_REQUIRE(n_groups <= 65535, "kmeans_reduce: too many groups");
+    long long gx = (elems + 255) / 256;
+    if (gx > 1024) gx = 1024;
+    kmeans_reduce_kernel<<<dim3((unsigned)gx, (unsigned)n_groups), 256, 0, (cudaStream_t)stream>>>(in, first, n_groups, elems, out);
+    return check_launch("kmeans_reduce");
+}
+
+extern "C" int oodb200_kmeans_update_f32(const float* sums, const float* counts, const float* cent_old, const int32_t* seg_k,
+                                         const int32_t* active, int n_seg, int k, int dim, float* cent_new, float* shift_sq,
+                                         int32_t* n_empty, void* stream) {
+    OODB200_REQUIRE(n_seg >= 0 && k > 0 && dim > 0, "kmeans_update: bad size");
+    if (n_seg == 0) return OODB200_OK;
+    OODB200_REQUIRE(sums && counts && cent_old && seg_k && cent_new && shift_sq && n_empty, "kmeans_update: null pointer");
+    kmeans_update_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(sums, counts, cent_old, seg_k, active, k, dim, cent_new,
+                                                                   shift_sq, n_empty);
+    return check_launch("kmeans_update");
+}
+
+extern "C" int oodb200_sqdist_cand_f32(const float* x, int dim, const int64_t* seg_off, int n_seg, int64_t max_seg_rows,
+                                       const float* cand, int n_cand, const float* closest, float* out_d, double* pot,
+                                       void* stream) {
+    OODB200_REQUIRE(dim > 0 && n_seg >= 0 && n_cand >= 1 && n_cand <= 8, "sqdist_cand: bad size (n_cand <= 8)");
+    if (n_seg == 0 || max_seg_rows == 0) return OODB200_OK;
+    OODB200_REQUIRE(x && seg_off && cand && out_d && pot, "sqdist_cand: null pointer");
+    OODB200_REQUIRE(n_seg <= 65535, "sqdist_cand: too many segments");
+    const size_t smem = sizeof(double) * ((size_t)n_cand * dim + 8);
+    OODB200_REQUIRE(smem <= 200 * 1024, "sqdist_cand: dim too large");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(sqdist_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("sqdist_cand: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+    }
+    CandParams p = {x, dim, seg_off, n_seg, cand, n_cand, closest, out_d, pot};
+    long long gx = (max_seg_rows + 63) / 64;
+    if (gx > 592) gx = 592;
+    if (gx < 1) gx = 1;
+    sqdist_cand_kernel<<<dim3((unsigned)gx, (unsigned)n_seg), 256, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("sqdist_cand");
+}

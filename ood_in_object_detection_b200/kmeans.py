@@ -1,0 +1,413 @@
+"""Segmented k-means fit on the GPU: every (class, stride) problem advances in the same kernel launches.
+
+Replaces `KMeans(n_clusters=k, random_state=10).fit_predict(X)` (/root/reference/cluster_utils.py:62-73),
+called once per (class, stride) by /root/reference/ood_utils.py:2345.  What runs where:
+
+  device (liboodb200.so)   distance passes of k-means++ (`oodb200_sqdist_cand_f32`), Lloyd assignment + block
+                           partial sums (`oodb200_kmeans_step_f32`), fixed-order reduction, centre update
+  host (numpy)             the scalar decisions of sklearn's `_kmeans_plusplus` (RandomState stream, float32
+                           cumsum + searchsorted, candidate potentials), written with sklearn's own expressions so
+                           that the chosen seeds are the ones sklearn picks; convergence bookkeeping
+  torch.distributed        N > 1: rows of every segment are block-sharded across ranks; per Lloyd iteration ONE
+                           all-reduce of [n_seg, K, D] sums + [n_seg, K] counts (+ changed-label counts), or, with
+                           reduce="ordered", an all-gather of super-block partials summed in a fixed order so
+                           that 1/2/4/8-rank runs give identical bits.
+
+All tensor arithmetic on N rows happens in the CUDA kernels; torch is used for memory and collectives.  The
+`backend` indirection exists so that the distributed control flow can be exercised on CPU (gloo) in the tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+BLOCK_ROWS = 512          # rows per CTA partial
+SUPER_BLOCKS = 32         # block partials per super-block (unit of ownership for reduce="ordered")
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class CudaBackend:
+    """Device steps of the fit, through the C ABI."""
+
+    def __init__(self, device):
+        from . import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.device = device
+
+    def sqdist_cand(self, x, seg_off_d, max_seg_rows, cand, closest):
+        n_seg, n_cand = cand.shape[0], cand.shape[1]
+        cand = cand.contiguous()
+        n = x.shape[0]
+        out = torch.empty((n_cand, n), dtype=torch.float32, device=x.device)
+        pot = torch.zeros((n_seg, n_cand), dtype=torch.float64, device=x.device)
+        self._lib.check(self.lib.oodb200_sqdist_cand_f32(_ptr(x), x.shape[1], _ptr(seg_off_d), n_seg, int(max_seg_rows),
+                                                         _ptr(cand), n_cand, _ptr(closest), _ptr(out), _ptr(pot),
+                                                         _stream()), "oodb200_sqdist_cand_f32")
+        return out, pot
+
+    def step(self, x, k, seg_k, cent, blocks, active, labels, n_changed, update):
+        n_blocks = blocks.n_blocks
+        psums = torch.empty((n_blocks, k, x.shape[1]), dtype=torch.float32, device=x.device) if update else None
+        pcounts = torch.empty((n_blocks, k), dtype=torch.float32, device=x.device) if update else None
+        self._lib.check(self.lib.oodb200_kmeans_step_f32(
+            _ptr(x), x.shape[1], int(seg_k.shape[0]), k, _ptr(seg_k), _ptr(cent), _ptr(blocks.seg), _ptr(blocks.row0),
+            _ptr(blocks.row1), n_blocks, _ptr(active), _ptr(labels), _ptr(psums), _ptr(pcounts), _ptr(n_changed),
+            int(update), _stream()), "oodb200_kmeans_step_f32")
+        return psums, pcounts
+
+    def reduce(self, part, first, n_groups):
+        elems = int(np.prod(part.shape[1:]))
+        out = torch.empty((n_groups,) + tuple(part.shape[1:]), dtype=torch.float32, device=part.device)
+        self._lib.check(self.lib.oodb200_kmeans_reduce_f32(_ptr(part), _ptr(first), n_groups, elems, _ptr(out), _stream()),
+                        "oodb200_kmeans_reduce_f32")
+        return out
+
+    def update(self, sums, counts, cent, seg_k, active):
+        n_seg, k, dim = cent.shape
+        new = cent.clone()
+        shift = torch.zeros(n_seg, dtype=torch.float32, device=cent.device)
+        n_empty = torch.zeros(n_seg, dtype=torch.int32, device=cent.device)
+        self._lib.check(self.lib.oodb200_kmeans_update_f32(_ptr(sums), _ptr(counts), _ptr(cent), _ptr(seg_k), _ptr(active),
+                                                           n_seg, k, dim, _ptr(new), _ptr(shift), _ptr(n_empty), _stream()),
+                        "oodb200_kmeans_update_f32")
+        return new, shift, n_empty
+
+
+@dataclass
+class BlockTable:
+    """Fixed partition of the (global) row space of every segment into blocks and super-blocks.
+    The partition depends only on the GLOBAL segment sizes, never on the number of ranks."""
+    seg: torch.Tensor          # [n_blocks] int32 (local blocks)
+    row0: torch.Tensor         # [n_blocks] int64 local row range
+    row1: torch.Tensor
+    n_blocks: int
+    super_first: torch.Tensor  # [n_super_local+1] int32: local blocks per local super-block
+    n_super_local: int
+    super_seg_first: torch.Tensor  # [n_seg+1] int32 over ALL super-blocks (global, rank-major = row order)
+    n_super_global: int
+    super_owner_counts: List[int]  # super-blocks per rank
+
+
+def build_blocks(global_sizes: Sequence[int], world: int, rank: int, device) -> tuple:
+    """Row sharding + block tables.  Rank r owns a contiguous range of super-blocks of every segment."""
+    seg_l, r0_l, r1_l, sfirst = [], [], [], [0]
+    local_sizes, local_off = [], [0]
+    super_seg_first = [0]
+    owner_counts = [0] * world
+    shard = []                                           # per segment: (global start row, rows) owned by this rank
+    for g, n in enumerate(global_sizes):
+        n_super = (n + BLOCK_ROWS * SUPER_BLOCKS - 1) // (BLOCK_ROWS * SUPER_BLOCKS)
+        bounds = [(n_super * r) // world for r in range(world + 1)]       # super-blocks per rank, contiguous
+        for r in range(world):
+            owner_counts[r] += bounds[r + 1] - bounds[r]
+        super_seg_first.append(super_seg_first[-1] + n_super)
+        s0, s1 = bounds[rank], bounds[rank + 1]
+        row_a = min(n, s0 * BLOCK_ROWS * SUPER_BLOCKS)
+        row_b = min(n, s1 * BLOCK_ROWS * SUPER_BLOCKS)
+        shard.append((row_a, row_b - row_a))
+        base = local_off[-1]
+        for sb in range(s0, s1):
+            a = sb * BLOCK_ROWS * SUPER_BLOCKS
+            b = min(n, a + BLOCK_ROWS * SUPER_BLOCKS)
+            for blk in range(a, b, BLOCK_ROWS):
+                seg_l.append(g)
+                r0_l.append(base + blk - row_a)
+                r1_l.append(base + min(b, blk + BLOCK_ROWS) - row_a)
+            sfirst.append(len(seg_l))
+        local_sizes.append(row_b - row_a)
+        local_off.append(base + row_b - row_a)
+    t = lambda a, dt: torch.tensor(a, dtype=dt, device=device)
+    table = BlockTable(seg=t(seg_l, torch.int32), row0=t(r0_l, torch.int64), row1=t(r1_l, torch.int64),
+                       n_blocks=len(seg_l), super_first=t(sfirst, torch.int32), n_super_local=len(sfirst) - 1,
+                       super_seg_first=t(super_seg_first, torch.int32), n_super_global=super_seg_first[-1],
+                       super_owner_counts=owner_counts)
+    return table, shard, local_off
+
+
+@dataclass
+class KMeansResult:
+    labels: torch.Tensor            # [n_local] int32
+    centers: torch.Tensor           # [n_seg, k, dim] float32 in the ORIGINAL coordinates
+    counts: torch.Tensor            # [n_seg, k]
+    n_iter: List[int]
+    strict: List[bool]
+    n_empty: List[int]
+    seconds: dict = field(default_factory=dict)
+
+
+def _sklearn_first_center(rs: np.random.RandomState, n: int) -> int:
+    w = np.ones(n, dtype=np.float32)
+    return int(rs.choice(n, p=w / w.sum()))           # _kmeans.py:234
+
+
+def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table: BlockTable, local_off: Sequence[int],
+               shard: Sequence[tuple], random_state: int = 10, max_iter: int = 300, tol: float = 1e-4,
+               backend=None, group=None, reduce: str = "allreduce") -> KMeansResult:
+    """x_local: this rank's rows [n_local, dim] (segment-major, each segment's shard contiguous), float32.
+    global_sizes: rows per segment over all ranks.  Returns labels for the local rows and the global centres."""
+    import time
+    import torch.distributed as dist
+    distributed = group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    dev = x_local.device
+    backend = backend or CudaBackend(dev)
+    n_seg, dim = len(global_sizes), int(x_local.shape[1])
+    seg_k_host = [min(k, int(n)) for n in global_sizes]
+    seg_k = torch.tensor(seg_k_host, dtype=torch.int32, device=dev)
+    seg_off_d = torch.tensor(list(local_off), dtype=torch.int64, device=dev)
+    timing = {}
+    t0 = time.perf_counter()
+
+    def allreduce(t, op=None):
+        if distributed:
+            dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=group)
+        return t
+
+    # ---- mean-centre every segment (KMeans.fit: X -= X.mean(axis=0)) and the sklearn tolerance ----
+    mean = torch.zeros((n_seg, dim), dtype=torch.float64, device=dev)
+    for g in range(n_seg):
+        a, b = local_off[g], local_off[g + 1]
+        if b > a:
+            mean[g] = x_local[a:b].sum(dim=0, dtype=torch.float64)
+    allreduce(mean)
+    gs = torch.tensor([max(int(n), 1) for n in global_sizes], dtype=torch.float64, device=dev)
+    mean = (mean / gs[:, None]).to(torch.float32)
+    x = torch.empty_like(x_local)
+    var = torch.zeros(n_seg, dtype=torch.float64, device=dev)
+    for g in range(n_seg):
+        a, b = local_off[g], local_off[g + 1]
+        if b > a:
+            x[a:b] = x_local[a:b] - mean[g]
+            var[g] = (x[a:b].to(torch.float64) ** 2).sum()
+    allreduce(var)
+    tol_abs = (var / gs / dim * tol).cpu().numpy()                         # mean over features of the variance
+    if distributed:
+        torch.cuda.synchronize() if dev.type == "cuda" else None
+    timing["center"] = time.perf_counter() - t0
+
+    # ---- k-means++ seeding, all segments in lock-step (sklearn _kmeans_plusplus, _kmeans.py:180-278) ----
+    t0 = time.perf_counter()
+    # sklearn: n_local_trials = 2 + int(log(n_clusters)) with the segment's OWN n_clusters = min(k, n)
+    trials = [2 + int(np.log(kk)) if kk > 1 else 1 for kk in seg_k_host]
+    n_trials = max(trials + [1])
+    rs = [np.random.RandomState(random_state) for _ in range(n_seg)]
+    cent = torch.zeros((n_seg, k, dim), dtype=torch.float32, device=dev)
+    max_rows = max([local_off[g + 1] - local_off[g] for g in range(n_seg)] + [0])
+
+    n_local = int(x.shape[0])
+    local_sizes = [local_off[g + 1] - local_off[g] for g in range(n_seg)]
+    if distributed:
+        meta = torch.tensor([n_local] + local_sizes, dtype=torch.int64, device=dev)
+        metas = [torch.empty_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta, group=group)
+        metas = [m.cpu().numpy() for m in metas]
+        max_local = max(int(m[0]) for m in metas)
+
+    def gather_rows(arr_local):
+        """local per-row values [m, n_local] -> list over segments of global arrays [m, n_g] (numpy, row order)."""
+        if not distributed:
+            a = arr_local.cpu().numpy()
+            return [a[:, local_off[g]:local_off[g + 1]] for g in range(n_seg)]
+        m = arr_local.shape[0]
+        pad = torch.zeros((m, max_local), dtype=arr_local.dtype, device=dev)
+        pad[:, :n_local] = arr_local
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)                            # equal-sized: works on nccl and gloo
+        host = [b.cpu().numpy() for b in bufs]
+        out = []
+        for g in range(n_seg):
+            parts = []
+            for r in range(world):
+                o = int(metas[r][1:1 + g].sum())
+                parts.append(host[r][:, o:o + int(metas[r][1 + g])])
+            out.append(np.concatenate(parts, axis=1))
+        return out
+
+    def fetch_vectors(global_ids):
+        """rows (global index within segment) [n_seg, m] -> centred vectors [n_seg, m, dim] on every rank."""
+        m = global_ids.shape[1]
+        vec = torch.zeros((n_seg, m, dim), dtype=torch.float32, device=dev)
+        for g in range(n_seg):
+            a, cnt = shard[g]
+            for j in range(m):
+                gid = int(global_ids[g, j])
+                if a <= gid < a + cnt:
+                    vec[g, j] = x[local_off[g] + gid - a]
+        return allreduce(vec)                                               # exactly one rank contributes each row
+
+    def cand_distances(vectors, closest):
+        """min(closest, squared distance to each candidate vector) for the local rows: [m, n_local]."""
+        d, _ = backend.sqdist_cand(x, seg_off_d, max_rows, vectors, closest)
+        return d
+
+    seg_of_row = torch.repeat_interleave(torch.arange(n_seg, device=dev), torch.tensor(local_sizes, device=dev))
+    active_seg = [g for g in range(n_seg) if global_sizes[g] > 0]
+    first = np.zeros((n_seg, 1), dtype=np.int64)
+    for g in active_seg:
+        first[g, 0] = _sklearn_first_center(rs[g], int(global_sizes[g]))
+    v0 = fetch_vectors(first)
+    cent[:, 0] = v0[:, 0]
+    closest = cand_distances(v0, None)[0].contiguous()                      # [n_local]
+    closest_g = gather_rows(closest[None])
+    pot = [np.float32(0)] * n_seg
+    for g in active_seg:
+        pot[g] = closest_g[g] @ np.ones(closest_g[g].shape[1], dtype=np.float32)         # _kmeans.py:246, shape (1,)
+    for c in range(1, k):
+        cand = np.zeros((n_seg, n_trials), dtype=np.int64)
+        for g in active_seg:
+            if c >= seg_k_host[g]:
+                continue
+            cd = closest_g[g][0]
+            rand_vals = rs[g].uniform(size=trials[g]) * pot[g]                             # _kmeans.py:252
+            ids = np.searchsorted(np.cumsum(np.ones(cd.size, dtype=np.float32) * cd), rand_vals)
+            np.clip(ids, None, cd.size - 1, out=ids)
+            cand[g, :trials[g]] = ids
+            cand[g, trials[g]:] = ids[0]                                                   # padding, ignored below
+        vec = fetch_vectors(cand)
+        newd = cand_distances(vec, closest)                                                # min(closest, d) on device
+        newd_g = gather_rows(newd)
+        best = np.zeros(n_seg, dtype=np.int64)
+        for g in active_seg:
+            if c >= seg_k_host[g]:
+                continue
+            nd = newd_g[g][:trials[g]]
+            pots = nd @ np.ones((nd.shape[1], 1), dtype=np.float32)                        # _kmeans.py:268
+            bj = int(np.argmin(pots))
+            best[g] = bj
+            pot[g] = pots[bj]
+            closest_g[g] = newd_g[g][bj:bj + 1].copy()
+        best_d = torch.from_numpy(best).to(dev)
+        take = torch.zeros(n_seg, dtype=torch.bool, device=dev)
+        for g in active_seg:
+            take[g] = c < seg_k_host[g]
+        cent[:, c] = torch.where(take[:, None], vec[torch.arange(n_seg, device=dev), best_d], cent[:, c])
+        if x.shape[0]:
+            sel = newd[best_d[seg_of_row], torch.arange(x.shape[0], device=dev)]
+            closest = torch.where(take[seg_of_row], sel, closest).contiguous()
+    timing["init"] = time.perf_counter() - t0
+
+    # ---- Lloyd iterations (sklearn _kmeans_single_lloyd, _kmeans.py:630-758) ----
+    t0 = time.perf_counter()
+    labels = torch.full((x.shape[0],), -1, dtype=torch.int32, device=dev)
+    active = torch.tensor([1 if global_sizes[g] > 0 else 0 for g in range(n_seg)], dtype=torch.int32, device=dev)
+    active_h = active.cpu().numpy().astype(bool)
+    need_final = np.zeros(n_seg, dtype=bool)
+    n_iter = [0] * n_seg
+    strict = [False] * n_seg
+    n_empty_tot = [0] * n_seg
+    seg_first = _seg_first_local(table, n_seg, dev)
+    counts = torch.zeros((n_seg, k), dtype=torch.float32, device=dev)
+    lloyd_iters = 0
+    for it in range(max_iter):
+        n_changed = torch.zeros(n_seg, dtype=torch.int32, device=dev)
+        psums, pcounts = backend.step(x, k, seg_k, cent, table, active, labels, n_changed, True)
+        if reduce == "ordered" and distributed:
+            sums, cnts = _ordered_reduce(backend, psums, pcounts, table, n_seg, world, group)
+        else:
+            sums = backend.reduce(psums, seg_first, n_seg) if table.n_blocks else torch.zeros_like(cent)
+            cnts = backend.reduce(pcounts, seg_first, n_seg) if table.n_blocks else torch.zeros_like(counts)
+            if distributed:
+                flat = torch.cat([sums.reshape(-1), cnts.reshape(-1), n_changed.to(torch.float32)])
+                allreduce(flat)                                            # the one collective of the iteration
+                sums = flat[:sums.numel()].reshape(sums.shape)
+                cnts = flat[sums.numel():sums.numel() + cnts.numel()].reshape(cnts.shape)
+                n_changed = flat[sums.numel() + cnts.numel():].to(torch.int32)
+        if reduce == "ordered" and distributed:
+            allreduce(n_changed)
+        new_cent, shift, n_empty = backend.update(sums, cnts, cent, seg_k, active)
+        flags = torch.stack([n_changed.to(torch.float64), shift.to(torch.float64), n_empty.to(torch.float64)]).cpu().numpy()
+        cent = new_cent
+        am = active.to(torch.bool)
+        counts = torch.where(am[:, None], cnts, counts)
+        lloyd_iters += 1
+        for g in range(n_seg):
+            if not active_h[g]:
+                continue
+            n_iter[g] = it + 1
+            n_empty_tot[g] += int(flags[2, g])
+            if flags[0, g] == 0:
+                strict[g] = True
+                active_h[g] = False
+            elif flags[1, g] <= tol_abs[g]:
+                active_h[g] = False
+                need_final[g] = True
+        active = torch.from_numpy(active_h.astype(np.int32)).to(dev)
+        if not active_h.any():
+            break
+    need_final |= active_h                                                  # max_iter reached without convergence
+    if need_final.any():                                                    # E-step with the final centres (:742-754)
+        fin = torch.from_numpy(need_final.astype(np.int32)).to(dev)
+        dummy = torch.zeros(n_seg, dtype=torch.int32, device=dev)
+        backend.step(x, k, seg_k, cent, table, fin, labels, dummy, False)
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    timing["lloyd"] = time.perf_counter() - t0
+    timing["lloyd_iters"] = lloyd_iters
+    return KMeansResult(labels=labels, centers=cent + mean[:, None, :], counts=counts, n_iter=n_iter, strict=strict,
+                        n_empty=n_empty_tot, seconds=timing)
+
+
+def _seg_first_local(table: BlockTable, n_seg: int, dev) -> torch.Tensor:
+    seg = table.seg.cpu().numpy()
+    first = np.zeros(n_seg + 1, dtype=np.int32)
+    if len(seg):
+        first[1:] = np.cumsum(np.bincount(seg, minlength=n_seg))
+    return torch.from_numpy(first).to(dev)
+
+
+def _ordered_reduce(backend, psums, pcounts, table: BlockTable, n_seg: int, world: int, group):
+    """Rank-count-invariant reduction: block partials -> super-block partials (fixed order inside a super-block),
+    all-gather of the super-block partials in global row order, then a fixed-order sum per segment."""
+    import torch.distributed as dist
+    dev = table.seg.device
+    k, dim = psums.shape[1], psums.shape[2]
+    sup_s = backend.reduce(psums, table.super_first, table.n_super_local) if table.n_super_local else psums.new_zeros((0, k, dim))
+    sup_c = backend.reduce(pcounts, table.super_first, table.n_super_local) if table.n_super_local else pcounts.new_zeros((0, k))
+    packed = torch.cat([sup_s.reshape(sup_s.shape[0], -1), sup_c], dim=1)                 # [n_super_local, k*dim + k]
+    cmax = max(table.super_owner_counts)
+    pad = torch.zeros((cmax, k * dim + k), dtype=torch.float32, device=dev)
+    pad[:packed.shape[0]] = packed
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    # global order = segment-major, and inside a segment rank-major (= row order)
+    per_rank_seg = _super_per_rank_seg(table, n_seg, world)
+    rows, offs = [], [0] * world
+    for g in range(n_seg):
+        for r in range(world):
+            c = per_rank_seg[r][g]
+            rows.append(bufs[r][offs[r]:offs[r] + c])
+            offs[r] += c
+    allp = torch.cat(rows, dim=0).contiguous()
+    sums = backend.reduce(allp[:, :k * dim].contiguous(), table.super_seg_first, n_seg).reshape(n_seg, k, dim)
+    cnts = backend.reduce(allp[:, k * dim:].contiguous(), table.super_seg_first, n_seg).reshape(n_seg, k)
+    return sums, cnts
+
+
+def _super_per_rank_seg(table: BlockTable, n_seg: int, world: int):
+    first = table.super_seg_first.cpu().numpy()
+    out = [[0] * n_seg for _ in range(world)]
+    for g in range(n_seg):
+        n_super = int(first[g + 1] - first[g])
+        bounds = [(n_super * r) // world for r in range(world + 1)]
+        for r in range(world):
+            out[r][g] = bounds[r + 1] - bounds[r]
+    return out
+
+
+def kmeans_fit_predict_single(x: torch.Tensor, sizes: Sequence[int], k: int, random_state: int = 10, **kw) -> KMeansResult:
+    """Single-process convenience wrapper: x [sum(sizes), dim] holds the segments back to back."""
+    table, shard, local_off = build_blocks(sizes, 1, 0, x.device)
+    return kmeans_fit(x, sizes, k, table, local_off, shard, random_state=random_state, **kw)

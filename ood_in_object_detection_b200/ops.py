@@ -278,6 +278,9 @@ def logit_score(logits: torch.Tensor, cls: torch.Tensor, method_mask: int, t_ene
     """K3: every requested logit method in one pass. thr/smin/smax: float64 [5, nc] device tensors."""
     lib = _lib.load()
     dev = logits.device
+    if logits.dtype != torch.float32 or cls.dtype != torch.int32 or not logits.is_cuda:
+        raise TypeError("logit_score: logits must be float32 and cls int32 CUDA tensors")
+    logits = logits.contiguous()
     n, nc = int(logits.shape[0]), int(logits.shape[1])
     if out is None:
         out = LogitScores(scores=torch.zeros((5, n), dtype=torch.float32, device=dev),
@@ -305,3 +308,26 @@ def fuse_scores(s1: torch.Tensor, s2: torch.Tensor) -> torch.Tensor:
     _lib.check(lib.oodb200_fuse_score_f32(_ptr(s1), _ptr(s2), int(s1.numel()), _ptr(out), _stream()),
                "oodb200_fuse_score_f32")
     return out
+
+
+def vec_score(x: torch.Tensor, seg_off: Sequence[int], cent: torch.Tensor, cent_unit: Optional[torch.Tensor],
+              cent_row_off: Sequence[int], cent_k: Sequence[int], metric_mask: int, normalize: bool = True):
+    """K2 on already pooled vectors: x [n, D] (device), rows of segment g = [seg_off[g], seg_off[g+1]) scored against
+    cent rows cent_row_off[g] .. +cent_k[g].  -> (dist [3, n] f32, argmin [3, n] i32)."""
+    lib = _lib.load()
+    dev = x.device
+    for name, ten in (("x", x), ("cent", cent), ("cent_unit", cent_unit)):
+        if ten is not None and (ten.dtype != torch.float32 or ten.device != dev):
+            raise TypeError(f"vec_score: {name} must be a float32 tensor on {dev}, got {ten.dtype} on {ten.device}")
+    x = x.contiguous()
+    n, dim = int(x.shape[0]), int(x.shape[1])
+    n_seg = len(seg_off) - 1
+    dist = torch.empty((3, n), dtype=torch.float32, device=dev)
+    arg = torch.empty((3, n), dtype=torch.int32, device=dev)
+    t = lambda a, dt: torch.tensor(list(a), dtype=dt, device=dev)
+    off_d, crow_d, ck_d = t(seg_off, torch.int64), t(cent_row_off, torch.int64), t(cent_k, torch.int32)   # keep alive
+    _lib.check(lib.oodb200_vec_score_f32(_ptr(x), int(x.stride(0)), dim, _ptr(off_d), n_seg, n,
+                                         int(metric_mask), int(bool(normalize)), _ptr(cent.contiguous()),
+                                         _ptr(cent_unit), _ptr(crow_d), _ptr(ck_d), _ptr(dist),
+                                         _ptr(arg), _stream()), "oodb200_vec_score_f32")
+    return dist, arg
