@@ -152,6 +152,10 @@ int oodb200_vec_score_f32(const float* x, int64_t ld, int dim, const int64_t* se
                           const float* cent, const float* cent_unit, const int64_t* cent_row_off, const int32_t* cent_k,
                           float* dist, int32_t* argmin, void* stream);
 
+/* Row-wise L2 normalisation, `sklearn.preprocessing.normalize(x, axis=1)` on float32 rows
+ * (`DistanceMethod.activations_transformation`, /root/reference/ood_utils.py:2404-2409). out may alias x. */
+int oodb200_normalize_rows_f32(const float* x, int64_t ld, int dim, int64_t n_rows, float* out, int64_t out_ld, void* stream);
+
 /* ---- K5: one pass of an exact radix select over float32 score bit patterns, segmented.
  * Replaces `np.percentile(scores, q, method='lower')` (/root/reference/ood_utils.py:613,626): the host
  * computes the order-statistic index numpy would use, then narrows 11+11+10 key bits with three passes.
@@ -170,6 +174,7 @@ int oodb200_radix_hist_u32(const float* scores, const int64_t* seg_off, int n_se
  * kmeans_step: one CTA per block of rows (block b covers rows [block_row0[b], block_row1[b]) of segment
  *   block_seg[b]; blocks never straddle segments).  labels[r] = argmin_k ||c_k||^2 - 2 x_r.c_k (first minimum);
  *   n_changed[g] += rows whose label changed (labels is read as the previous assignment; -1 initially).
+ *   update == 2: labels are NOT recomputed; the sums/counts of the given labels are produced (member means).
  *   update != 0: psums [n_blocks, k, dim] / pcounts [n_blocks, k] receive the block's per-cluster sums and
  *   counts, accumulated in row order (bit-reproducible).  active [n_seg] (or NULL): segments with 0 are skipped.
  *   x [n_rows, dim] float32, already mean-centred per segment by the caller; cent [n_seg, k, dim]; seg_k [n_seg].

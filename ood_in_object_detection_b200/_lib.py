@@ -32,6 +32,7 @@ SIGNATURES = {
     "oodb200_fuse_u8": [_P, _P, _P, _I, _I, _P, _P],
     "oodb200_fuse_score_f32": [_P, _P, _I, _P, _P],
     "oodb200_vec_score_f32": [_P, _L, _I, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "oodb200_normalize_rows_f32": [_P, _L, _I, _L, _P, _L, _P],
     "oodb200_radix_hist_u32": [_P, _P, _I, _L, _P, _I, _I, _P, _P, _P],
     "oodb200_kmeans_smem_bytes": [_I, _I],
     "oodb200_kmeans_step_f32": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P],

@@ -119,6 +119,20 @@ __global__ void __launch_bounds__(kVecThreads) vec_score_kernel(const VecParams 
     }
 }
 
+// sklearn.preprocessing.normalize(x, axis=1) for float32 rows: one warp per row
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ x, int64_t ld, int dim, int64_t n_rows,
+                                                             float* __restrict__ out, int64_t out_ld) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += (int64_t)gridDim.x * 8) {
+        const float* __restrict__ xr = x + row * ld;
+        float ss = 0.f;
+        for (int d = lane; d < dim; d += 32) { const float v = __ldg(xr + d); ss = fmaf(v, v, ss); }
+        float nrm = sqrtf(warp_sum(ss));
+        if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;
+        for (int d = lane; d < dim; d += 32) out[row * out_ld + d] = __fdiv_rn(__ldg(xr + d), nrm);
+    }
+}
+
 // order-preserving map float32 -> uint32 (negative floats reversed, positives above them)
 __device__ __forceinline__ uint32_t float_key(float f) {
     const uint32_t b = __float_as_uint(f);
@@ -182,6 +196,17 @@ extern "C" int oodb200_vec_score_f32(const float* x, int64_t ld, int dim, const 
     if (grid > 148LL * 32) grid = 148LL * 32;
     vec_score_kernel<<<(int)grid, kVecThreads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("vec_score");
+}
+
+extern "C" int oodb200_normalize_rows_f32(const float* x, int64_t ld, int dim, int64_t n_rows, float* out, int64_t out_ld,
+                                          void* stream) {
+    OODB200_REQUIRE(dim > 0 && n_rows >= 0 && ld >= dim && out_ld >= dim, "normalize_rows: bad size");
+    if (n_rows == 0) return OODB200_OK;
+    OODB200_REQUIRE(x && out, "normalize_rows: null pointer");
+    long long grid = (n_rows + 7) / 8;
+    if (grid > 148LL * 32) grid = 148LL * 32;
+    normalize_rows_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(x, ld, dim, n_rows, out, out_ld);
+    return check_launch("normalize_rows");
 }
 
 extern "C" int oodb200_radix_hist_u32(const float* scores, const int64_t* seg_off, int n_seg, int64_t n_rows,

@@ -115,7 +115,11 @@ __global__ void __launch_bounds__(kKmThreads) kmeans_step_kernel(const KmParams 
             }
             float best = FLT_MAX;
             int barg = 0;
-            for (int grp = 0; grp < n_groups; ++grp) {
+            if (p.update == 2) {                     // sums of the GIVEN labels (member means), no re-assignment
+                barg = p.labels[r];
+                if (barg < 0 || barg >= Kg) barg = 0;
+            }
+            for (int grp = 0; grp < (p.update == 2 ? 0 : n_groups); ++grp) {
                 float dot[kKG];
 #pragma unroll
                 for (int u = 0; u < kKG; ++u) {

@@ -331,3 +331,15 @@ def vec_score(x: torch.Tensor, seg_off: Sequence[int], cent: torch.Tensor, cent_
                                          _ptr(cent_unit), _ptr(crow_d), _ptr(ck_d), _ptr(dist),
                                          _ptr(arg), _stream()), "oodb200_vec_score_f32")
     return dist, arg
+
+
+def normalize_rows(x: torch.Tensor) -> torch.Tensor:
+    """sklearn normalize(axis=1) of float32 rows on the device (ood_utils.py:2404-2409)."""
+    lib = _lib.load()
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise TypeError("normalize_rows: float32 CUDA tensor expected")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _lib.check(lib.oodb200_normalize_rows_f32(_ptr(x), int(x.stride(0)), int(x.shape[1]), int(x.shape[0]), _ptr(out),
+                                              int(out.stride(0)), _stream()), "oodb200_normalize_rows_f32")
+    return out
