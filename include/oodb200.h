@@ -145,12 +145,22 @@ int oodb200_fuse_score_f32(const float* s1, const float* s2, int n, uint8_t* out
  * normalize + pairwise_distances(...).min(axis=0) per (class, stride) segment.
  *   x [n_rows, ld] float32 (first `dim` columns used); seg_off device int64 [n_seg+1] row offsets;
  *   segment g is scored against rows cent_row_off[g] .. +cent_k[g] of cent [*, dim]
- *   dist / argmin [3][n_rows] (slot = metric id; only requested slots written)
+ *   dist / argmin [3][n_rows] (slot = metric id; only requested slots written); a segment without centroids
+ *   (cent_k == 0) gives 1000 / -1 (ood_utils.py:2159-2164)
+ *   thr [3][n_seg] float64 (NaN = no threshold) and decision [3][n_rows] are optional (both NULL to skip):
+ *   decision = dist < thr (ood_utils.py:2173-2180)
  */
 int oodb200_vec_score_f32(const float* x, int64_t ld, int dim, const int64_t* seg_off, int n_seg, int64_t n_rows,
                           int metric_mask, int normalize,
                           const float* cent, const float* cent_unit, const int64_t* cent_row_off, const int32_t* cent_k,
-                          float* dist, int32_t* argmin, void* stream);
+                          float* dist, int32_t* argmin, const double* thr, uint8_t* decision, void* stream);
+
+/* INDness of a distance score as the reference intends it (/root/reference/ood_utils.py:1599-1604): piecewise linear
+ * through (min_dist, +1), (thr, 0), (max_dist, -1), clipped to [-1, 1] when clip != 0.  slot[i] indexes the
+ * thr / dmin / dmax tables (float64; NaN thr or slot < 0 -> -1).  The shipped reference always returns -1
+ * (SURVEY.md Q2); the host class does the same in compat mode without calling this. */
+int oodb200_dist_indness_f32(const float* dist, const int32_t* slot, int64_t n, const double* thr, const double* dmin,
+                             const double* dmax, int clip, float* out, void* stream);
 
 /* Row-wise L2 normalisation, `sklearn.preprocessing.normalize(x, axis=1)` on float32 rows
  * (`DistanceMethod.activations_transformation`, /root/reference/ood_utils.py:2404-2409). out may alias x. */

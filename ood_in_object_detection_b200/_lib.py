@@ -31,7 +31,8 @@ SIGNATURES = {
     "oodb200_logit_score_f32": [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "oodb200_fuse_u8": [_P, _P, _P, _I, _I, _P, _P],
     "oodb200_fuse_score_f32": [_P, _P, _I, _P, _P],
-    "oodb200_vec_score_f32": [_P, _L, _I, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "oodb200_vec_score_f32": [_P, _L, _I, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "oodb200_dist_indness_f32": [_P, _P, _L, _P, _P, _P, _I, _P, _P],
     "oodb200_normalize_rows_f32": [_P, _L, _I, _L, _P, _L, _P],
     "oodb200_radix_hist_u32": [_P, _P, _I, _L, _P, _I, _I, _P, _P, _P],
     "oodb200_kmeans_smem_bytes": [_I, _I],

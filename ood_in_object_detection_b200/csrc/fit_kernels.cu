@@ -28,6 +28,8 @@ struct VecParams {
     float* dist;
     int32_t* argmin;
     int d_pad;
+    const double* thr;        // optional [3][n_seg], NaN = no threshold
+    uint8_t* decision;        // optional [3][n_rows]
 };
 
 __device__ __forceinline__ int find_segment(const int64_t* __restrict__ seg_off, int n_seg, int64_t row) {
@@ -112,8 +114,13 @@ __global__ void __launch_bounds__(kVecThreads) vec_score_kernel(const VecParams 
         }
         if (lane < OODB200_N_METRICS && (p.metric_mask >> lane & 1)) {
             const size_t o = (size_t)lane * p.n_rows + row;
-            p.dist[o] = K > 0 ? best[lane] : 1000.f;
+            const float dv = K > 0 ? best[lane] : 1000.f;          // no cluster: ood_utils.py:2159-2164
+            p.dist[o] = dv;
             p.argmin[o] = K > 0 ? barg[lane] : -1;
+            if (p.decision) {                                        // :2173-2180 (NaN = falsy threshold -> OoD)
+                const double t = p.thr[(size_t)lane * p.n_seg + g];
+                p.decision[o] = (t == t && (double)dv < t) ? 1 : 0;
+            }
         }
         __syncwarp();
     }
@@ -131,6 +138,30 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
         if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;
         for (int d = lane; d < dim; d += 32) out[row * out_ld + d] = __fdiv_rn(__ldg(xr + d), nrm);
     }
+}
+
+// DistanceMethod.compute_indness as the reference INTENDS it (ood_utils.py:1599-1604; the shipped code always
+// returns -1, SURVEY.md Q2 -- the host keeps that behaviour in compat mode and never calls this kernel then).
+// Piecewise linear through (min_dist, +1), (thr, 0), (max_dist, -1), python-float arithmetic.
+__global__ void dist_indness_kernel(const float* __restrict__ dist, const int32_t* __restrict__ slot, int64_t n,
+                                    const double* __restrict__ thr, const double* __restrict__ dmin,
+                                    const double* __restrict__ dmax, int clip, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g = slot[i];
+    float r = -1.f;
+    if (g >= 0) {
+        const double t = thr[g], s = (double)dist[i];
+        if (t == t) {
+            double a = 0.0, b = 0.0;
+            if (s > t) { a = -1.0 / (dmax[g] - t); b = t / (dmax[g] - t); }
+            else if (s < t) { a = 1.0 / (dmin[g] - t); b = -t / (dmin[g] - t); }
+            double v = a * s + b;
+            if (clip) v = fmax(-1.0, fmin(v, 1.0));
+            r = (float)v;
+        }
+    }
+    out[i] = r;
 }
 
 // order-preserving map float32 -> uint32 (negative floats reversed, positives above them)
@@ -178,14 +209,16 @@ using namespace oodb200;
 extern "C" int oodb200_vec_score_f32(const float* x, int64_t ld, int dim, const int64_t* seg_off, int n_seg, int64_t n_rows,
                                      int metric_mask, int normalize,
                                      const float* cent, const float* cent_unit, const int64_t* cent_row_off,
-                                     const int32_t* cent_k, float* dist, int32_t* argmin, void* stream) {
+                                     const int32_t* cent_k, float* dist, int32_t* argmin, const double* thr,
+                                     uint8_t* decision, void* stream) {
     OODB200_REQUIRE(dim > 0 && n_seg >= 0 && n_rows >= 0 && ld >= dim, "vec_score: bad size");
     OODB200_REQUIRE(metric_mask > 0 && metric_mask < (1 << OODB200_N_METRICS), "vec_score: metric_mask %d", metric_mask);
     if (n_rows == 0 || n_seg == 0) return OODB200_OK;
     OODB200_REQUIRE(x && seg_off && cent && cent_row_off && cent_k && dist && argmin, "vec_score: null pointer");
     OODB200_REQUIRE(!(metric_mask & (1 << OODB200_METRIC_COS)) || cent_unit, "vec_score: cosine needs cent_unit");
+    OODB200_REQUIRE(!decision || thr, "vec_score: decision output needs thresholds");
     VecParams p = {x, ld, dim, seg_off, n_seg, n_rows, metric_mask, normalize, cent, cent_unit, cent_row_off, cent_k,
-                   dist, argmin, (dim + 3) & ~3};
+                   dist, argmin, (dim + 3) & ~3, thr, decision};
     const size_t smem = sizeof(float) * 2 * (size_t)p.d_pad * kVecWarps;
     OODB200_REQUIRE(smem <= 200 * 1024, "vec_score: dim %d too large", dim);
     if (smem > 48 * 1024) {
@@ -196,6 +229,15 @@ extern "C" int oodb200_vec_score_f32(const float* x, int64_t ld, int dim, const 
     if (grid > 148LL * 32) grid = 148LL * 32;
     vec_score_kernel<<<(int)grid, kVecThreads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("vec_score");
+}
+
+extern "C" int oodb200_dist_indness_f32(const float* dist, const int32_t* slot, int64_t n, const double* thr,
+                                        const double* dmin, const double* dmax, int clip, float* out, void* stream) {
+    OODB200_REQUIRE(n >= 0, "dist_indness: negative n");
+    if (n == 0) return OODB200_OK;
+    OODB200_REQUIRE(dist && slot && thr && dmin && dmax && out, "dist_indness: null pointer");
+    dist_indness_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dist, slot, n, thr, dmin, dmax, clip, out);
+    return check_launch("dist_indness");
 }
 
 extern "C" int oodb200_normalize_rows_f32(const float* x, int64_t ld, int dim, int64_t n_rows, float* out, int64_t out_ld,

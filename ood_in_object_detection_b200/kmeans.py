@@ -314,7 +314,7 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
     for it in range(max_iter):
         n_changed = torch.zeros(n_seg, dtype=torch.int32, device=dev)
         psums, pcounts = backend.step(x, k, seg_k, cent, table, active, labels, n_changed, True)
-        if reduce == "ordered" and distributed:
+        if reduce == "ordered":
             sums, cnts = _ordered_reduce(backend, psums, pcounts, table, n_seg, world, group)
         else:
             sums = backend.reduce(psums, seg_first, n_seg) if table.n_blocks else torch.zeros_like(cent)
@@ -380,8 +380,11 @@ def _ordered_reduce(backend, psums, pcounts, table: BlockTable, n_seg: int, worl
     cmax = max(table.super_owner_counts)
     pad = torch.zeros((cmax, k * dim + k), dtype=torch.float32, device=dev)
     pad[:packed.shape[0]] = packed
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
+    if world > 1:
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+    else:
+        bufs = [pad]
     # global order = segment-major, and inside a segment rank-major (= row order)
     per_rank_seg = _super_per_rank_seg(table, n_seg, world)
     rows, offs = [], [0] * world
@@ -405,6 +408,61 @@ def _super_per_rank_seg(table: BlockTable, n_seg: int, world: int):
         for r in range(world):
             out[r][g] = bounds[r + 1] - bounds[r]
     return out
+
+
+def kmeans_fit_sharded(x_local: torch.Tensor, local_sizes: Sequence[int], global_sizes: Sequence[int], k: int, world: int,
+                       rank: int, group=None, random_state: int = 10, **kw) -> KMeansResult:
+    """N > 1 entry: this rank holds `local_sizes[g]` rows of segment g (segment-major in x_local).  The block table
+    only depends on the GLOBAL sizes, and build_blocks prescribes which rows each rank owns; the caller must have
+    sharded accordingly (see shard_rows)."""
+    table, shard, local_off = build_blocks(global_sizes, world, rank, x_local.device)
+    mine = [cnt for _, cnt in shard]
+    if list(mine) != [int(v) for v in local_sizes]:
+        raise ValueError(f"rank {rank}: row shard {list(local_sizes)} does not match the block table's {mine}; "
+                         f"use kmeans.shard_rows() to split the segments")
+    return kmeans_fit(x_local, global_sizes, k, table, local_off, shard, random_state=random_state, group=group, **kw)
+
+
+def shard_rows(global_sizes: Sequence[int], world: int, rank: int) -> List[tuple]:
+    """(first row, row count) of every segment owned by `rank` (contiguous super-block ranges, build_blocks)."""
+    out = []
+    for n in global_sizes:
+        n_super = (n + BLOCK_ROWS * SUPER_BLOCKS - 1) // (BLOCK_ROWS * SUPER_BLOCKS)
+        s0, s1 = (n_super * rank) // world, (n_super * (rank + 1)) // world
+        a, b = min(n, s0 * BLOCK_ROWS * SUPER_BLOCKS), min(n, s1 * BLOCK_ROWS * SUPER_BLOCKS)
+        out.append((a, b - a))
+    return out
+
+
+def member_means(x: torch.Tensor, sizes: Sequence[int], labels: Optional[torch.Tensor], k: int, group=None, backend=None):
+    """Per segment, per label: mean of the member rows -- `np.mean(X[labels == j], axis=0)` of
+    /root/reference/ood_utils.py:2359-2366 (labels=None: one cluster = the segment mean, :2306).
+    Sums run through the k-means step kernel in its update==2 mode (block partials in row order + fixed-order
+    reduction); N > 1: one all-reduce of the sums and counts.  -> (means [n_seg, k, dim], counts [n_seg, k])."""
+    import torch.distributed as dist
+    dev = x.device
+    backend = backend or CudaBackend(dev)
+    n_seg, dim = len(sizes), int(x.shape[1])
+    table, _, _ = build_blocks(sizes, 1, 0, dev)
+    if labels is None:
+        labels = torch.zeros(x.shape[0], dtype=torch.int32, device=dev)
+    labels = labels.to(torch.int32).contiguous()
+    seg_k = torch.full((n_seg,), k, dtype=torch.int32, device=dev)
+    cent = torch.zeros((n_seg, k, dim), dtype=torch.float32, device=dev)
+    dummy = torch.zeros(n_seg, dtype=torch.int32, device=dev)
+    if table.n_blocks:
+        psums, pcounts = backend.step(x.contiguous(), k, seg_k, cent, table, None, labels, dummy, 2)
+        first = _seg_first_local(table, n_seg, dev)
+        sums = backend.reduce(psums, first, n_seg)
+        cnts = backend.reduce(pcounts, first, n_seg)
+    else:
+        sums, cnts = cent, torch.zeros((n_seg, k), dtype=torch.float32, device=dev)
+    if group is not None:
+        flat = torch.cat([sums.reshape(-1), cnts.reshape(-1)])
+        dist.all_reduce(flat, group=group)
+        sums, cnts = flat[:sums.numel()].reshape(sums.shape), flat[sums.numel():].reshape(cnts.shape)
+    means = sums / cnts.clamp_min(1.0)[..., None]
+    return means, cnts
 
 
 def kmeans_fit_predict_single(x: torch.Tensor, sizes: Sequence[int], k: int, random_state: int = 10, **kw) -> KMeansResult:

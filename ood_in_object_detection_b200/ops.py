@@ -18,6 +18,7 @@ from . import _lib
 METRIC_SLOT = {"l1": 0, "manhattan": 0, "cityblock": 0, "l2": 1, "euclidean": 1, "cosine": 2}
 LOGIT_SLOT = {"MSP": 0, "Energy": 1, "ODIN": 2, "Sigmoid": 3, "MaxLogit": 4}
 FUSE_SLOT = {"and": 0, "or": 1, "majority_voting": 2}
+N_LOGIT = 5
 
 
 def _stream() -> C.c_void_p:
@@ -137,6 +138,23 @@ def _unit_rows(a: np.ndarray) -> np.ndarray:
     return a
 
 
+def pack_thresholds(thresholds_by_metric: dict, nc: int) -> np.ndarray:
+    """{metric_slot: thresholds[cls][stride]} -> float64 [3 metrics, 3*nc] (index s*nc + c), NaN = "no threshold":
+    python floats are taken, falsy entries ([] / 0 / 0.0 / None) mean OoD like in the reference (ood_utils.py:2173)."""
+    thr = np.full((3, 3, nc), np.nan, dtype=np.float64)
+    for slot, th in thresholds_by_metric.items():
+        if th is None:
+            continue
+        for c in range(min(nc, len(th))):
+            for s in range(3):
+                v = th[c][s] if s < len(th[c]) else []
+                if v is None or (isinstance(v, (list, tuple, np.ndarray)) and np.size(v) == 0):
+                    continue
+                if v:                                  # python truthiness, like the reference
+                    thr[slot, s, c] = float(v)
+    return thr.reshape(3, 3 * nc)
+
+
 def pack_centroids(clusters, thresholds_by_metric: dict, dims: Sequence[int], device=None) -> CentroidTable:
     """clusters[cls][stride] = ndarray [K, C_s] or empty; thresholds_by_metric = {metric_slot: thresholds[cls][stride]}
     with python floats or falsy entries ([] / 0 / 0.0 -> "no threshold", ood_utils.py:2173)."""
@@ -167,20 +185,10 @@ def pack_centroids(clusters, thresholds_by_metric: dict, dims: Sequence[int], de
                 units.append(np.zeros(pad, np.float32))
     flat = np.concatenate(chunks) if chunks else np.zeros(4, np.float32)
     flat_u = np.concatenate(units) if units else np.zeros(4, np.float32)
-    thr = np.full((3, 3, nc), np.nan, dtype=np.float64)
-    for slot, th in thresholds_by_metric.items():
-        if th is None:
-            continue
-        for c in range(min(nc, len(th))):
-            for s in range(3):
-                v = th[c][s] if s < len(th[c]) else []
-                if isinstance(v, (list, tuple, np.ndarray)) and np.size(v) == 0:
-                    continue
-                if v:                                  # python truthiness, like the reference
-                    thr[slot, s, c] = float(v)
+    thr = pack_thresholds(thresholds_by_metric, nc)
     t = lambda a: torch.from_numpy(a).to(device, non_blocking=True)
     return CentroidTable(cent=t(flat), cent_unit=t(flat_u), cent_off=t(off.reshape(-1)), cent_k=t(kk.reshape(-1)),
-                         thr=t(thr.reshape(3, 3 * nc)), nc=nc, k_host=kk)
+                         thr=t(thr), nc=nc, k_host=kk)
 
 
 def q1_plan(batch: DetectionBatch, cls_used: Optional[torch.Tensor] = None, out_index: Optional[torch.Tensor] = None):
@@ -311,9 +319,11 @@ def fuse_scores(s1: torch.Tensor, s2: torch.Tensor) -> torch.Tensor:
 
 
 def vec_score(x: torch.Tensor, seg_off: Sequence[int], cent: torch.Tensor, cent_unit: Optional[torch.Tensor],
-              cent_row_off: Sequence[int], cent_k: Sequence[int], metric_mask: int, normalize: bool = True):
+              cent_row_off: Sequence[int], cent_k: Sequence[int], metric_mask: int, normalize: bool = True,
+              thr: Optional[torch.Tensor] = None):
     """K2 on already pooled vectors: x [n, D] (device), rows of segment g = [seg_off[g], seg_off[g+1]) scored against
-    cent rows cent_row_off[g] .. +cent_k[g].  -> (dist [3, n] f32, argmin [3, n] i32)."""
+    cent rows cent_row_off[g] .. +cent_k[g].  -> (dist [3, n] f32, argmin [3, n] i32), plus decision [3, n] u8 when
+    `thr` (float64 [3, n_seg], NaN = no threshold) is given."""
     lib = _lib.load()
     dev = x.device
     for name, ten in (("x", x), ("cent", cent), ("cent_unit", cent_unit)):
@@ -324,13 +334,34 @@ def vec_score(x: torch.Tensor, seg_off: Sequence[int], cent: torch.Tensor, cent_
     n_seg = len(seg_off) - 1
     dist = torch.empty((3, n), dtype=torch.float32, device=dev)
     arg = torch.empty((3, n), dtype=torch.int32, device=dev)
+    dec = None
+    if thr is not None:
+        if thr.dtype != torch.float64 or tuple(thr.shape) != (3, n_seg) or thr.device != dev:
+            raise TypeError("vec_score: thr must be a float64 [3, n_seg] tensor on the device of x")
+        thr = thr.contiguous()
+        dec = torch.zeros((3, n), dtype=torch.uint8, device=dev)
     t = lambda a, dt: torch.tensor(list(a), dtype=dt, device=dev)
     off_d, crow_d, ck_d = t(seg_off, torch.int64), t(cent_row_off, torch.int64), t(cent_k, torch.int32)   # keep alive
+    cent = cent.contiguous()
     _lib.check(lib.oodb200_vec_score_f32(_ptr(x), int(x.stride(0)), dim, _ptr(off_d), n_seg, n,
-                                         int(metric_mask), int(bool(normalize)), _ptr(cent.contiguous()),
+                                         int(metric_mask), int(bool(normalize)), _ptr(cent),
                                          _ptr(cent_unit), _ptr(crow_d), _ptr(ck_d), _ptr(dist),
-                                         _ptr(arg), _stream()), "oodb200_vec_score_f32")
+                                         _ptr(arg), _ptr(thr), _ptr(dec), _stream()), "oodb200_vec_score_f32")
+    if thr is not None:
+        return dist, arg, dec
     return dist, arg
+
+
+def dist_indness(dist: torch.Tensor, slot: torch.Tensor, thr: torch.Tensor, dmin: torch.Tensor, dmax: torch.Tensor,
+                 clip: bool = True) -> torch.Tensor:
+    """Intended `DistanceMethod.compute_indness` (ood_utils.py:1599-1604) for n distances; slot [n] int32 indexes the
+    float64 thr / dmin / dmax tables."""
+    lib = _lib.load()
+    out = torch.empty(dist.shape, dtype=torch.float32, device=dist.device)
+    _lib.check(lib.oodb200_dist_indness_f32(_ptr(dist.contiguous()), _ptr(slot.contiguous()), int(dist.numel()),
+                                            _ptr(thr), _ptr(dmin), _ptr(dmax), int(bool(clip)), _ptr(out), _stream()),
+               "oodb200_dist_indness_f32")
+    return out
 
 
 def normalize_rows(x: torch.Tensor) -> torch.Tensor:

@@ -31,19 +31,29 @@ def _key_to_float(key: np.ndarray) -> np.ndarray:
     return bits.astype(np.uint32).view(np.float32)
 
 
-def segment_select(scores: torch.Tensor, seg_off: Sequence[int], ranks: Sequence[Optional[int]], group=None):
+class _CudaHist:
+    """One radix pass through the C ABI (oodb200_radix_hist_u32)."""
+
+    def radix_hist(self, scores, seg_off, prefix, shift, bits, hist, minmax):
+        lib = _lib.load()
+        ptr = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        off_d = torch.tensor(list(seg_off), dtype=torch.int64, device=scores.device)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.oodb200_radix_hist_u32(ptr(scores), ptr(off_d), len(seg_off) - 1, int(scores.numel()), ptr(prefix),
+                                              shift, bits, ptr(hist), ptr(minmax), stream), "oodb200_radix_hist_u32")
+
+
+def segment_select(scores: torch.Tensor, seg_off: Sequence[int], ranks: Sequence[Optional[int]], group=None, backend=None):
     """scores [n_local] float32 on the device, seg_off local row offsets [n_seg+1], ranks[g] = GLOBAL order-statistic
     index wanted in segment g (None: skip).  -> (values[float or None], min[float], max[float]) per segment;
-    min/max are None for empty segments."""
+    min/max are None for empty segments.  `backend` (tests only): object with `radix_hist`, so that the multi-rank
+    exchange can be exercised on CPU under gloo."""
     import torch.distributed as dist
-    lib = _lib.load()
+    backend = backend or _CudaHist()
     dev = scores.device
     n_seg = len(seg_off) - 1
     distributed = group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
     scores = scores.contiguous()
-    off_d = torch.tensor(list(seg_off), dtype=torch.int64, device=dev)
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    ptr = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
     want = np.array([-1 if r is None else int(r) for r in ranks], dtype=np.int64)
     prefix = np.zeros(n_seg, dtype=np.uint32)
     remaining = want.copy()
@@ -52,9 +62,7 @@ def segment_select(scores: torch.Tensor, seg_off: Sequence[int], ranks: Sequence
     for p, (shift, bits) in enumerate(PASSES):
         hist = torch.zeros((n_seg, 1 << bits), dtype=torch.int32, device=dev)
         pfx = torch.from_numpy(prefix.view(np.int32).copy()).to(dev)
-        _lib.check(lib.oodb200_radix_hist_u32(ptr(scores), ptr(off_d), n_seg, int(scores.numel()), ptr(pfx), shift, bits,
-                                              ptr(hist), ptr(minmax_i) if p == 0 else None, stream),
-                   "oodb200_radix_hist_u32")
+        backend.radix_hist(scores, list(seg_off), pfx, shift, bits, hist, minmax_i if p == 0 else None)
         if distributed:
             dist.all_reduce(hist, group=group)                              # one exchange per radix pass
         h = hist.cpu().numpy().astype(np.int64)

@@ -332,8 +332,53 @@ def golden_thresholds(ref):
     print("golden_thresholds ok")
 
 
+def golden_matching(ref):
+    """`match_predicted_boxes_to_targets` (ood_utils.py:233-292) and `create_targets_dict` (:201-231) on jittered
+    copies of ground-truth boxes: more predictions than targets, fewer, equal, none."""
+    ou = ref.ood_utils
+    rng = np.random.default_rng(31)
+    store = {}
+    shapes = [(9, 4), (3, 7), (5, 5), (0, 3), (4, 0), (12, 6)]
+    store["shapes"] = np.array(shapes)
+    for k, (P, G) in enumerate(shapes):
+        c = rng.uniform(40, 600, size=(G, 2))
+        wh = rng.uniform(20, 120, size=(G, 2))
+        gt = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(F32)
+        gcls = rng.integers(0, 3, size=G).astype(F32)
+        if G:
+            src = rng.integers(0, G, size=P)
+            pred = gt[src] + rng.normal(0, 6, size=(P, 4)).astype(F32)
+            pcls = np.where(rng.uniform(size=P) < 0.8, gcls[src], (gcls[src] + 1) % 3).astype(F32)
+        else:
+            pred = rng.uniform(0, 600, size=(P, 4)).astype(F32)
+            pred[:, 2:] += pred[:, :2]
+            pcls = rng.integers(0, 3, size=P).astype(F32)
+        b6 = torch.from_numpy(np.concatenate([pred, np.full((P, 1), 0.5, F32), pcls[:, None]], 1).astype(F32))
+        res = ref_shim.make_results(ref, None, [b6], logits=[torch.zeros(P, 3)], n_batch=1)
+        targets = dict(bboxes=[torch.from_numpy(gt)], cls=[torch.from_numpy(gcls)])
+        for thr in (0.5, 0.3):
+            ou.OODMethod.match_predicted_boxes_to_targets(res, targets, thr)
+            store[f"valid_{k}_{thr}"] = np.asarray(res[0].valid_preds, np.int64)
+        store[f"pred_{k}"], store[f"pcls_{k}"], store[f"gt_{k}"], store[f"gcls_{k}"] = pred, pcls, gt, gcls
+    data = dict(im_file=["a", "b", "c"], batch_idx=torch.tensor([0., 2., 0., 2., 2.]),
+                bboxes=torch.from_numpy(rng.uniform(0.1, 0.6, size=(5, 4)).astype(F32)),
+                cls=torch.from_numpy(rng.integers(0, 5, size=(5, 1)).astype(F32)),
+                resized_shape=[(640, 480), (320, 320), (512, 640)])
+    t = ou.OODMethod.create_targets_dict(data)
+    store["td_batch_idx"], store["td_bboxes"], store["td_cls"] = data["batch_idx"].numpy(), data["bboxes"].numpy(), data["cls"].numpy()
+    store["td_shapes"] = np.array(data["resized_shape"])
+    for i in range(3):
+        store[f"td_out_bboxes_{i}"] = np.asarray(t["bboxes"][i], np.float64)
+        store[f"td_out_cls_{i}"] = np.asarray(t["cls"][i], F32)
+    np.savez_compressed(os.path.join(OUT, "golden_matching.npz"), **store)
+    print("golden_matching", {k: store[k].tolist() for k in store if k.startswith("valid_") and k.endswith("0.5")})
+
+
 def main():
     ref = ref_shim.load()
+    if "--only-matching" in sys.argv:
+        return golden_matching(ref)
+    golden_matching(ref)
     golden_roi_edges(ref)
     golden_quirks(ref)
     golden_fusion(ref)

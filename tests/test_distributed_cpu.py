@@ -1,0 +1,149 @@
+"""world_size-2 `gloo` runs of the sharded fit path on CPU (no GPU needed): row sharding of every segment, the one
+all-reduce per Lloyd iteration, the rank-count-invariant ordered reduction, the per-pass histogram exchange of the
+exact percentile, and sharded member means.  The device steps are replaced by tests/cpu_backend.py; what is under
+test is the host control flow of ood_in_object_detection_b200/{kmeans,select}.py that runs unchanged on NCCL."""
+from __future__ import annotations
+
+import os
+import socket
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ood_in_object_detection_b200 import kmeans, select, synth
+from tests.cpu_backend import NumpyBackend
+
+SIZES = [40000, 17000, 5, 0, 33000]        # ragged segments: several super-blocks, a tiny one, an empty one
+DIM, K = 12, 4
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _data():
+    segs = [synth.blob_vectors(10 + i, n, DIM, K, 7.0)[0] if n else np.zeros((0, DIM), np.float32) for i, n in enumerate(SIZES)]
+    return segs
+
+
+def _scores():
+    rng = np.random.default_rng(5)
+    out = [rng.normal(0, 1, size=n).astype(np.float32) for n in (70000, 11, 0, 3000)]
+    out[0][:5000] = out[0][0]              # ties
+    return out
+
+
+def _worker(rank: int, world: int, port: int, outdir: str):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        be = NumpyBackend()
+        segs = _data()
+        shard = kmeans.shard_rows(SIZES, world, rank)
+        local = [s[a:a + n] for s, (a, n) in zip(segs, shard)]
+        x = torch.from_numpy(np.concatenate(local))
+        res = {}
+        for mode in ("allreduce", "ordered"):
+            r = kmeans.kmeans_fit_sharded(x, [len(v) for v in local], SIZES, K, world, rank, group=dist.group.WORLD,
+                                          backend=be, reduce=mode)
+            res[f"labels_{mode}"] = r.labels.numpy()
+            res[f"centers_{mode}"] = r.centers.numpy()
+            res[f"n_iter_{mode}"] = np.array(r.n_iter)
+        means, counts = kmeans.member_means(x, [len(v) for v in local], torch.from_numpy(res["labels_ordered"]), K,
+                                            group=dist.group.WORLD, backend=be)
+        res["means"], res["counts"] = means.numpy(), counts.numpy()
+        # exact percentile over sharded scores: rank r holds every world-th score of each segment
+        sc = _scores()
+        mine = [v[rank::world] for v in sc]
+        off = np.concatenate([[0], np.cumsum([len(v) for v in mine])]).tolist()
+        ranks = [select.lower_index(len(v), 95.0) if len(v) > 5 else None for v in sc]
+        vals, mn, mx = select.segment_select(torch.from_numpy(np.concatenate(mine)), off, ranks, group=dist.group.WORLD, backend=be)
+        res["sel"] = np.array([np.nan if v is None else v for v in vals])
+        res["mn"] = np.array([np.nan if v is None else v for v in mn])
+        res["mx"] = np.array([np.nan if v is None else v for v in mx])
+        np.savez(os.path.join(outdir, f"rank{rank}.npz"), **res)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.fixture(scope="module")
+def two_rank_run():
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(2, _free_port(), d), nprocs=2, join=True)
+        yield [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(2)]
+
+
+@pytest.fixture(scope="module")
+def single_run():
+    be = NumpyBackend()
+    x = torch.from_numpy(np.concatenate(_data()))
+    return kmeans.kmeans_fit_predict_single(x, SIZES, K, backend=be), kmeans.kmeans_fit_predict_single(x, SIZES, K, backend=be, reduce="ordered")
+
+
+def test_sharded_kmeans_equals_single_process(two_rank_run, single_run):
+    single_run, single_ordered = single_run
+    assert np.array_equal(single_ordered.labels.numpy(), single_run.labels.numpy())
+    labels1 = single_run.labels.numpy()
+    off = np.concatenate([[0], np.cumsum(SIZES)])
+    for mode in ("allreduce", "ordered"):
+        parts = []
+        for g, n in enumerate(SIZES):                       # re-assemble global row order from the two row shards
+            for r in range(2):
+                a, cnt = kmeans.shard_rows(SIZES, 2, r)[g]
+                loc_off = np.concatenate([[0], np.cumsum([c for _, c in kmeans.shard_rows(SIZES, 2, r)])])
+                parts.append(two_rank_run[r][f"labels_{mode}"][loc_off[g]:loc_off[g] + cnt])
+        labels2 = np.concatenate(parts)
+        assert len(labels2) == off[-1]
+        assert np.array_equal(labels2, labels1), mode        # k-means labels: bit-exact across rank counts
+        assert np.array_equal(two_rank_run[0][f"centers_{mode}"], two_rank_run[1][f"centers_{mode}"])   # ranks agree
+        assert np.array_equal(two_rank_run[0][f"n_iter_{mode}"], np.array(single_run.n_iter))
+    # the ordered reduction is invariant to the number of ranks: identical centre bits for world 1 and 2
+    assert np.array_equal(two_rank_run[0]["centers_ordered"], single_ordered.centers.numpy())
+    np.testing.assert_allclose(two_rank_run[0]["centers_allreduce"], single_run.centers.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_sharded_member_means(two_rank_run, single_run):
+    single_run = single_run[0]
+    segs = _data()
+    lab = single_run.labels.numpy()
+    off = np.concatenate([[0], np.cumsum(SIZES)])
+    for g, n in enumerate(SIZES):
+        for j in range(K):
+            m = lab[off[g]:off[g + 1]] == j
+            assert two_rank_run[0]["counts"][g, j] == m.sum()
+            if m.any():
+                np.testing.assert_allclose(two_rank_run[0]["means"][g, j], segs[g][m].mean(0), rtol=1e-5, atol=1e-6)
+    assert np.array_equal(two_rank_run[0]["means"], two_rank_run[1]["means"])
+
+
+def test_sharded_percentile_is_exact(two_rank_run):
+    sc = _scores()
+    for r in range(2):
+        for g, v in enumerate(sc):
+            if len(v) > 5:
+                assert two_rank_run[r]["sel"][g] == np.percentile(v, 95.0, method="lower"), g
+                assert two_rank_run[r]["mn"][g] == v.min() and two_rank_run[r]["mx"][g] == v.max()
+            else:
+                assert np.isnan(two_rank_run[r]["sel"][g])
+        assert np.isnan(two_rank_run[r]["mn"][2])           # empty segment
+
+
+def test_block_table_is_rank_count_invariant():
+    for world in (1, 2, 4, 8):
+        owned = [kmeans.shard_rows(SIZES, world, r) for r in range(world)]
+        for g, n in enumerate(SIZES):
+            pos = 0
+            for r in range(world):                           # contiguous, ordered, complete cover of every segment
+                a, cnt = owned[r][g]
+                assert a == pos or cnt == 0
+                pos += cnt
+            assert pos == n
+        tabs = [kmeans.build_blocks(SIZES, world, r, torch.device("cpu"))[0] for r in range(world)]
+        assert sum(t.n_super_local for t in tabs) == tabs[0].n_super_global
+        assert sum(t.n_blocks for t in tabs) == kmeans.build_blocks(SIZES, 1, 0, torch.device("cpu"))[0].n_blocks

@@ -1,0 +1,332 @@
+"""The reference's class surface (ood_in_object_detection_b200.ood_utils) against golden vectors frozen from the
+reference's own classes (tests/golden/make_golden.py).  Reads like the reference's usage in ood_evaluation.py:
+construct -> extract activations -> generate_clusters -> compute_scores_from_activations -> generate_thresholds ->
+compute_ood_decision_on_results."""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import scoring_case, split, train_case, unpack_nested
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+LOG = logging.getLogger("test")
+LOG.setLevel(logging.ERROR)
+
+DIST_KW = dict(agg_method="mean", cluster_method="one", cluster_optimization_metric="silhouette",
+               ind_info_creation_option="valid_preds_one_stride", which_internal_activations="ftmaps_and_strides",
+               iou_threshold_for_matching=0.5, min_conf_threshold_train=0.15, min_conf_threshold_test=0.15)
+LOGIT_KW = dict(per_class=True, per_stride=False, iou_threshold_for_matching=0.5, min_conf_threshold_train=0.15,
+                min_conf_threshold_test=0.15, use_values_before_sigmoid=True)
+COMMON = dict(iou_threshold_for_matching=0.5, min_conf_threshold_train=0.15, min_conf_threshold_test=0.15)
+
+
+@pytest.fixture(scope="module")
+def ou():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from ood_in_object_detection_b200 import ood_utils
+    return ood_utils
+
+
+def _results(maps, boxes, cls, strides, img, device="cuda"):
+    """Our Results stand-ins for a batch; maps = 3 arrays [B, C, H, W] (kept as per-image CHW device tensors)."""
+    from ood_in_object_detection_b200.results import Results, batch_shape
+    tm = [torch.from_numpy(np.ascontiguousarray(m)).to(device) for m in maps]
+    out = []
+    for i in range(len(boxes)):
+        b6 = np.concatenate([boxes[i], np.full((len(boxes[i]), 1), 0.5, np.float32), cls[i][:, None]], 1).astype(np.float32)
+        out.append(Results(orig_img=batch_shape(len(boxes), img, img), boxes=torch.from_numpy(b6).to(device),
+                           extra_item=([t[i] for t in tm], torch.from_numpy(strides[i]).to(device))))
+    return out
+
+
+def _classes(ou):
+    return (("l1", ou.L1DistanceOneClusterPerStride), ("l2", ou.L2DistanceOneClusterPerStride),
+            ("cos", ou.CosineDistanceOneClusterPerStride))
+
+
+@pytest.mark.parametrize("name", ["golden_c1_one.npz", "golden_small_kmeans5.npz"])
+def test_distance_methods_fit_and_decide(ou, golden, name):
+    g = golden(name)
+    nc, img = int(g["nc"]), int(g["img"])
+    cluster_method = str(g["cluster_method"])
+    tmaps, tboxes, tcls, tstrides = train_case(g)
+    train = _results(tmaps, tboxes, tcls, tstrides, img)
+    for r, b in zip(train, tboxes):
+        r.valid_preds = list(range(len(b)))            # the golden fit takes every prediction as valid
+    images, maps = scoring_case(g)
+    test = _results(maps, [im["boxes"] for im in images], [im["cls"] for im in images], [im["strides"] for im in images], img)
+    n_exempt = 0
+    for tag, cls in _classes(ou):
+        m = cls(**dict(DIST_KW, cluster_method=cluster_method))
+        acts = m._empty_activation_lists(nc)
+        m.extract_internal_activations(train, acts, None)
+        m.format_internal_activations(acts)
+        # ---- fit: clusters, InD scores, thresholds
+        clusters = m.generate_clusters(acts, LOG)
+        ref_clusters = unpack_nested(g, f"{tag}_clusters", nc)
+        for c in range(nc):
+            for s in range(3):
+                assert clusters[c][s].shape == ref_clusters[c][s].shape, (tag, c, s)
+                if ref_clusters[c][s].size:
+                    np.testing.assert_allclose(clusters[c][s], ref_clusters[c][s], rtol=RTOL, atol=1e-7)
+        m.clusters = ref_clusters                       # pin the state so the next stages compare like for like
+        scores = m.compute_scores_from_activations(acts, LOG)
+        for c in range(nc):
+            for s in range(3):
+                ref = g[f"{tag}_fitscores_{c}_{s}"]
+                assert len(scores[c][s]) == len(ref), (tag, c, s)
+                if len(ref):
+                    np.testing.assert_allclose(scores[c][s], ref, rtol=RTOL, atol=1e-6)   # a lone member is its own centroid: 0 vs 1 ulp * D
+                    np.testing.assert_allclose(m.min_dist[c][s], float(g[f"{tag}_mindist_{c}_{s}"]), rtol=RTOL, atol=1e-6)
+                    np.testing.assert_allclose(m.max_dist[c][s], float(g[f"{tag}_maxdist_{c}_{s}"]), rtol=RTOL, atol=1e-6)
+        thr = m.generate_thresholds(scores, 0.95, LOG)
+        ref_thr = unpack_nested(g, f"{tag}_thr", nc, as_threshold=True)
+        for c in range(nc):
+            for s in range(3):
+                if ref_thr[c][s] == []:
+                    assert thr[c][s] == [], (tag, c, s)
+                else:
+                    assert isinstance(thr[c][s], float)
+                    np.testing.assert_allclose(thr[c][s], ref_thr[c][s], rtol=RTOL, atol=1e-6)
+        # ---- decide, with the reference's fitted state
+        m.thresholds = ref_thr
+        dec = m.compute_ood_decision_on_results(test, LOG)
+        assert [len(d) for d in dec] == [int(v) for v in g["n_boxes"]]
+        flat = np.array([v for d in dec for v in d], np.int8)
+        ref_d = g[f"{tag}_dist"]
+        thr_flat = np.array([ref_thr[c][s] if ref_thr[c][s] != [] else np.nan
+                             for c, s in zip(g[f"{tag}_cls_used"], g[f"{tag}_stride_of"])], np.float64)
+        near = np.abs(ref_d - thr_flat) <= RTOL * np.abs(thr_flat)
+        n_exempt += int(near.sum())
+        assert np.array_equal(flat[~near], g[f"{tag}_decisions"][~near]), tag
+        r = m.score_results(test)
+        np.testing.assert_allclose(r["dist"], ref_d, rtol=RTOL, atol=5e-7 if tag == "cos" else 0)
+        assert np.array_equal(r["cls_used"], g[f"{tag}_cls_used"]) and np.array_equal(r["stride"], g[f"{tag}_stride_of"])
+        if tag == "cos":                                # Q2: the reference's INDness is -1 for every box
+            ind = m.compute_INDness_scores_on_results(test, LOG)
+            assert np.array_equal(np.array([v for d in ind for v in d], np.float64), g["cos_indness"])
+            m.min_dist = unpack_nested(g, "cos_mindist", nc)
+            m.max_dist = unpack_nested(g, "cos_maxdist", nc)
+            m.reference_compat = False                  # intended semantics: in [-1, 1], sign agrees with the decision
+            ind2 = np.array([v for d in m.compute_INDness_scores_on_results(test, LOG) for v in d])
+            dec2 = np.array([v for d in m.compute_ood_decision_on_results(test, LOG) for v in d])
+            assert ind2.min() >= -1 and ind2.max() <= 1
+            assert np.all((ind2 > 0) <= (dec2 == 1)) and np.all(ind2[dec2 == 0] <= 0)
+    assert n_exempt <= 2
+
+
+def test_pre_pooled_and_box_order_modes(ou, golden):
+    """'roi_aligned_ftmaps' (vectors pooled by the detector side) gives the decisions of 'ftmaps_and_strides';
+    reference_compat=False returns them in box order with the box's own class."""
+    g = golden("golden_small_kmeans5.npz")
+    nc, img = int(g["nc"]), int(g["img"])
+    images, maps = scoring_case(g)
+    boxes, cls, strides = [im["boxes"] for im in images], [im["cls"] for im in images], [im["strides"] for im in images]
+    test = _results(maps, boxes, cls, strides, img)
+    m = ou.L2DistanceOneClusterPerStride(**dict(DIST_KW, cluster_method="KMeans_5"))
+    m.clusters = unpack_nested(g, "l2_clusters", nc)
+    m.thresholds = unpack_nested(g, "l2_thr", nc, as_threshold=True)
+    fused = m.score_results(test)
+    tm = [torch.from_numpy(x).cuda() for x in maps]
+    pooled = ou.extract_roi_aligned_features_from_correct_stride(
+        tm, [torch.from_numpy(b) for b in boxes], [torch.from_numpy(s) for s in strides], (img, img), "cuda")
+    from ood_in_object_detection_b200.results import Results, batch_shape
+    pre = [Results(orig_img=batch_shape(len(boxes), img, img), boxes=r.boxes, extra_item=pooled[i]) for i, r in enumerate(test)]
+    m2 = ou.L2DistanceOneClusterPerStride(**dict(DIST_KW, cluster_method="KMeans_5", which_internal_activations="roi_aligned_ftmaps"))
+    m2.clusters, m2.thresholds = m.clusters, m.thresholds
+    r2 = m2.score_results(pre)
+    np.testing.assert_allclose(r2["dist"], fused["dist"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(r2["decision"], fused["decision"]) and np.array_equal(r2["cls_used"], fused["cls_used"])
+    assert m2.compute_ood_decision_on_results(pre, LOG) == m.compute_ood_decision_on_results(test, LOG)
+    # box-order semantics: same multiset of (box -> distance) when the class lookup happens to agree, and always the
+    # box's own class
+    m.reference_compat = m2.reference_compat = False
+    a, b = m.score_results(test), m2.score_results(pre)
+    assert np.array_equal(a["cls_used"], np.concatenate(cls).astype(np.int64))
+    assert np.array_equal(a["stride"], np.concatenate(strides).astype(np.int64))
+    np.testing.assert_allclose(b["dist"], a["dist"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(a["decision"], b["decision"])
+
+
+def test_extractor_helper_matches_reference(ou, golden):
+    g = golden("golden_roi_edges.npz")
+    img = int(g["img"])
+    n = g["n_boxes"]
+    boxes, strides = split(g["boxes"], n), split(g["strides"], n)
+    maps = [torch.from_numpy(g[f"map{s}"]).cuda() for s in range(3)]
+    for all_strides in (False, True):
+        out = ou.extract_roi_aligned_features_from_correct_stride(
+            maps, [torch.from_numpy(b) for b in boxes], [torch.from_numpy(s) for s in strides], (img, img), "cuda",
+            extract_all_strides=all_strides)
+        for i in range(3):
+            for s in range(3):
+                idx, feats = out[i][s]
+                ref_idx, ref = g[f"all{int(all_strides)}_idx_{i}_{s}"], g[f"all{int(all_strides)}_feat_{i}_{s}"]
+                assert idx.dtype == torch.int16 and np.array_equal(idx.cpu().numpy(), ref_idx)
+                if len(ref_idx):
+                    assert tuple(feats.shape) == (len(ref_idx), ref.shape[1], 1, 1)
+                    got = feats.reshape(len(ref_idx), -1).cpu().numpy()
+                    scale = np.abs(ref).max(axis=1, keepdims=True) + 1e-30
+                    assert np.all(np.abs(got - ref) <= RTOL * scale)
+
+
+def test_quirks_through_the_class(ou, golden):
+    g = golden("golden_quirks.npz")
+    img = int(g["img"])
+    maps = [g[f"map{s}"] for s in range(3)]
+    res = _results(maps, [g["boxes"]], [g["cls"]], [g["strides"]], img)
+    clusters = unpack_nested(g, "clusters", 3)
+    m = ou.L2DistanceOneClusterPerStride(**DIST_KW)
+    m.clusters = clusters
+    cases = {"q1": [[1e9] * 3, [1e-9] * 3, [1e-9] * 3], "q4_zero": [[0.0] * 3, [1e9] * 3, [1e9] * 3],
+             "q4_empty": [[[]] * 3, [1e9] * 3, [1e9] * 3]}
+    for k, thr in cases.items():
+        m.thresholds = thr
+        assert m.compute_ood_decision_on_results(res, LOG) == [g[f"{k}_decisions"].tolist()], k
+    m.thresholds = [[1e9] * 3] * 3
+    m.clusters = [clusters[0], [np.empty(0), clusters[1][1], clusters[1][2]], clusters[2]]
+    assert m.compute_ood_decision_on_results(res, LOG) == [g["missing_cluster_decisions"].tolist()]
+    for c in range(3):                                  # in-place edit of the thresholds is honoured
+        m.thresholds[c] = [999.0] * 3
+    assert m.compute_ood_decision_on_results(res, LOG) == [g["missing_cluster_thr999_decisions"].tolist()]
+    assert m.compute_ood_decision_on_results([], LOG) == []
+    with pytest.raises(AssertionError):
+        ou.L2DistanceOneClusterPerStride(**dict(DIST_KW, which_internal_activations="logits"))
+    with pytest.raises(AssertionError):
+        ou.L2DistanceOneClusterPerStride(**dict(DIST_KW, cluster_method="nope"))
+
+
+def test_logits_methods(ou, golden):
+    g = golden("golden_logits.npz")
+    nc = int(g["nc"])
+    from ood_in_object_detection_b200.results import Results, batch_shape
+    n = g["n_boxes"]
+    cls, logits = split(g["cls"], n), split(g["logits"], n)
+    keep = split(g["fitted_mask"], n)
+
+    def mk(mask=None):
+        out = []
+        for i in range(len(n)):
+            sel = np.ones(len(cls[i]), bool) if mask is None else mask[i]
+            b6 = np.zeros((int(sel.sum()), 6), np.float32)
+            b6[:, 5] = cls[i][sel]
+            out.append(Results(orig_img=batch_shape(len(n), 640, 640), boxes=torch.from_numpy(b6),
+                               extra_item=torch.from_numpy(logits[i][sel])))
+        return out
+    results, results_fitted = mk(), mk(keep)
+    acts = [torch.from_numpy(g["train_logits"][g["train_cls"] == c]) if (g["train_cls"] == c).any() else torch.tensor([])
+            for c in range(nc)]
+    for tag, m in (("MSP", ou.MSP(**LOGIT_KW)), ("Energy", ou.Energy(temper=1, **LOGIT_KW)),
+                   ("ODIN", ou.ODIN(temper=1000, **LOGIT_KW)), ("Sigmoid", ou.Sigmoid(**LOGIT_KW))):
+        scores = m.compute_scores_from_activations(acts, LOG)
+        np.testing.assert_allclose(np.concatenate(scores), g[f"{tag}_fitscores"], rtol=RTOL)
+        np.testing.assert_allclose(m.min_score, g[f"{tag}_min"], rtol=RTOL)
+        np.testing.assert_allclose(m.max_score, g[f"{tag}_max"], rtol=RTOL)
+        thr = m.generate_thresholds(scores, 0.95, LOG)
+        assert thr[7] == 0                                   # class without samples keeps 0
+        np.testing.assert_allclose(thr, g[f"{tag}_thr"], rtol=RTOL)
+        m.thresholds = g[f"{tag}_thr"].tolist()
+        m.min_score, m.max_score = g[f"{tag}_min"].tolist(), g[f"{tag}_max"].tolist()
+        sc = np.array([m.compute_scores(torch.from_numpy(z), int(c))[0] for z, c in zip(g["logits"][:40], g["cls"][:40])])
+        np.testing.assert_allclose(sc, g[f"{tag}_scores"][:40], rtol=RTOL)
+        all_sc = m.compute_scores(torch.from_numpy(g["logits"]), g["cls"])
+        np.testing.assert_allclose(all_sc, g[f"{tag}_scores"], rtol=RTOL)
+        dec = m.compute_ood_decision_on_results(results, LOG)
+        assert [len(d) for d in dec] == [int(v) for v in n]
+        flat = np.array([v for d in dec for v in d], np.int8)
+        thr_box = np.asarray(m.thresholds)[g["cls"].astype(int)]
+        near = np.abs(g[f"{tag}_scores"] - thr_box) <= RTOL * np.abs(thr_box)
+        assert near.sum() <= 2 and np.array_equal(flat[~near], g[f"{tag}_decisions"][~near]), tag
+        ind = m.compute_INDness_scores_on_results(results_fitted, LOG)
+        tol = 2e-2 if tag == "ODIN" else 1e-4           # ODIN's InD score range is ~1e-4 wide: INDness amplifies f32 rounding
+        np.testing.assert_allclose(np.array([v for d in ind for v in d]), g[f"{tag}_indness"], atol=tol)
+    no = ou.NoMethod(**LOGIT_KW)
+    assert no.compute_ood_decision_on_results(results, LOG) == [[1] * int(v) for v in n]
+    bad = ou.Sigmoid(**LOGIT_KW)                         # the reference asserts cls == argmax (ood_utils.py:1442)
+    z = g["logits"][:4].copy()
+    z[0, (int(g["cls"][0]) + 1) % nc] = 50.0
+    with pytest.raises(AssertionError):
+        bad.compute_scores(torch.from_numpy(z), g["cls"][:4])
+    ml = ou.MaxLogit(**LOGIT_KW)
+    np.testing.assert_array_equal(ml.compute_scores(torch.from_numpy(g["logits"]), g["cls"]), g["logits"].max(1))
+
+
+def test_fusion_rules(ou, golden):
+    g = golden("golden_fusion.npz")
+    n = g["n"]
+    lists = lambda a, cast: [[cast(v) for v in p] for p in split(a, n)]
+    m1, m2, m3 = ou.MSP(**LOGIT_KW), ou.MSP(**LOGIT_KW), ou.MSP(**LOGIT_KW)
+    for strat in ("and", "or", "score"):
+        f = ou.FusionMethod(m1, m2, strat, fusion_method_name="fusion-MSP-MSP", cluster_method="one", **COMMON)
+        a, b = (lists(g["s1"], float), lists(g["s2"], float)) if strat == "score" else (lists(g["d1"], int), lists(g["d2"], int))
+        out = f.fuse_ood_decisions(a, b)
+        assert [len(v) for v in out] == n.tolist()
+        assert [v for p in out for v in p] == g[f"fuse_{strat}"].tolist(), strat
+    t = ou.TripleFusionMethod(m1, m2, m3, cluster_method="one", **COMMON)
+    out = t.fuse_ood_decisions(lists(g["d1"], int), lists(g["d2"], int), lists(g["d3"], int))
+    assert [v for p in out for v in p] == g["fuse_majority"].tolist()
+    f = ou.FusionMethod(m1, m2, "and", fusion_method_name="x", cluster_method="one", **COMMON)
+    f.thresholds = ([1.0], [2.0])
+    assert m1.thresholds == [1.0] and m2.thresholds == [2.0] and f.thresholds == ([1.0], [2.0])
+    with pytest.raises(ValueError):
+        f.thresholds = ([1.0],)
+    with pytest.raises(ValueError):
+        f.clusters = []
+    assert f.cluster_method == 'None' and not f.is_distance_method
+
+
+def test_generate_thresholds_matches_numpy_lower(ou, golden):
+    g = golden("golden_thresholds.npz")
+    dm = ou.L2DistanceOneClusterPerStride(**DIST_KW)
+    lm = ou.MSP(**LOGIT_KW)
+    for n in (5, 6, 11, 21, 101, 1001, 4097):
+        v = g[f"v_{n}"]
+        for tpr in (0.9, 0.95, 0.99, 0.8):
+            t = dm.generate_thresholds([[v, v.astype(np.float64), np.empty(0)]], tpr, LOG)[0]
+            got = np.array([x if x != [] else np.nan for x in t], np.float64)
+            assert np.array_equal(got, g[f"dist_{n}_{tpr}"], equal_nan=True), (n, tpr)
+            assert np.array_equal(np.array(lm.generate_thresholds([v], tpr, LOG), np.float64), g[f"logit_{n}_{tpr}"]), (n, tpr)
+
+
+def test_kmeans_fit_through_the_class(ou, golden):
+    g = golden("golden_kmeans.npz")
+    acts = unpack_nested(g, "fit_acts", 3)
+    m = ou.L2DistanceOneClusterPerStride(**dict(DIST_KW, cluster_method="KMeans_5"))
+    m.clusters = m.generate_clusters(acts, LOG)
+    ref = unpack_nested(g, "fit_clusters", 3)
+    for c in range(3):
+        for s in range(3):
+            assert m.clusters[c][s].shape == ref[c][s].shape, (c, s)
+    # (class 0, stride 0): 5 blobs, k = 5 -> well separated, centroids to float32 rounding
+    np.testing.assert_allclose(m.clusters[0][0], ref[0][0], rtol=RTOL, atol=1e-7)
+    # (class 1, stride 2): 4 blobs, k = 5 -> one blob is split in two; which of its points go where depends on the
+    # summation order of the x.c dot products (BLAS in the reference), so only the 3 unsplit centroids are comparable
+    # to rounding; the split pair must still partition the same blob with the same inertia (k-means parity)
+    got, want = m.clusters[1][2], ref[1][2]
+    d = np.abs(got[:, None, :] - want[None, :, :]).max(-1)
+    assert (d.min(1) < 1e-5).sum() == 3 and np.array_equal(d.argmin(1), np.arange(5))
+    x = m.activations_transformation(acts[1][2])
+    inertia = lambda cen: float(((x[:, None, :] - cen[None]) ** 2).sum(-1).min(1).sum())
+    assert abs(inertia(got) - inertia(want)) <= 2e-3 * inertia(want)
+    m.clusters = ref
+    scores = m.compute_scores_from_activations(acts, LOG)
+    thr = m.generate_thresholds(scores, 0.95, LOG)
+    ref_thr = unpack_nested(g, "fit_thr", 3, as_threshold=True)
+    for c in range(3):
+        for s in range(3):
+            if ref_thr[c][s] == []:
+                assert thr[c][s] == []
+            else:
+                np.testing.assert_allclose(thr[c][s], ref_thr[c][s], rtol=RTOL, atol=1e-6)
+    # labels through the cluster_utils mirror (cluster_utils.py:62-73)
+    from ood_in_object_detection_b200 import cluster_utils
+    for tag in "abc":
+        lab = cluster_utils.find_optimal_number_of_clusters_one_class_one_stride_and_return_labels(
+            g[f"{tag}_x"], f"KMeans_{int(g[f'{tag}_k'])}", "l2", "silhouette", "", LOG)
+        assert np.array_equal(lab, g[f"{tag}_labels"]), tag

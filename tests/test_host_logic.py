@@ -1,0 +1,92 @@
+"""Host-side logic of the class surface that needs no GPU: prediction <-> ground-truth matching and the target
+dictionary (golden vectors from the reference, tests/golden/make_golden.py::golden_matching), constructor
+validation, fitted-state plumbing of the fusion classes."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from ood_in_object_detection_b200 import ood_utils as ou
+from ood_in_object_detection_b200.results import Results, batch_shape
+
+DIST_KW = dict(agg_method="mean", cluster_method="one", cluster_optimization_metric="silhouette",
+               ind_info_creation_option="valid_preds_one_stride", which_internal_activations="ftmaps_and_strides",
+               iou_threshold_for_matching=0.5, min_conf_threshold_train=0.15, min_conf_threshold_test=0.15)
+LOGIT_KW = dict(per_class=True, per_stride=False, iou_threshold_for_matching=0.5, min_conf_threshold_train=0.15,
+                min_conf_threshold_test=0.15, use_values_before_sigmoid=True)
+COMMON = dict(iou_threshold_for_matching=0.5, min_conf_threshold_train=0.15, min_conf_threshold_test=0.15)
+
+
+def test_matching_matches_reference(golden):
+    g = golden("golden_matching.npz")
+    for k, (P, G) in enumerate(g["shapes"]):
+        b6 = np.concatenate([g[f"pred_{k}"], np.full((P, 1), 0.5, np.float32), g[f"pcls_{k}"][:, None]], 1).astype(np.float32)
+        res = [Results(orig_img=batch_shape(1, 640, 640), boxes=torch.from_numpy(b6).reshape(P, 6))]
+        targets = dict(bboxes=[torch.from_numpy(g[f"gt_{k}"])], cls=[torch.from_numpy(g[f"gcls_{k}"])])
+        for thr in (0.5, 0.3):
+            ou.OODMethod.match_predicted_boxes_to_targets(res, targets, thr)
+            assert res[0].valid_preds == g[f"valid_{k}_{thr}"].tolist(), (k, thr)
+        # intended semantics: every kept prediction really overlaps a same-class target above the threshold
+        ou.OODMethod.match_predicted_boxes_to_targets(res, targets, 0.5, compat=False)
+        m = res[0].assignment_score_matrix
+        assert all(float(m[i].max()) > 0.5 for i in res[0].valid_preds)
+        if P <= G:
+            assert res[0].valid_preds == g[f"valid_{k}_0.5"].tolist()
+
+
+def test_targets_dict_matches_reference(golden):
+    g = golden("golden_matching.npz")
+    data = dict(im_file=["a", "b", "c"], batch_idx=torch.from_numpy(g["td_batch_idx"]), bboxes=torch.from_numpy(g["td_bboxes"]),
+                cls=torch.from_numpy(g["td_cls"]), resized_shape=[tuple(int(v) for v in r) for r in g["td_shapes"]])
+    t = ou.OODMethod.create_targets_dict(data)
+    for i in range(3):
+        np.testing.assert_allclose(np.asarray(t["bboxes"][i], np.float64), g[f"td_out_bboxes_{i}"], rtol=1e-6, atol=1e-4)
+        assert np.array_equal(np.asarray(t["cls"][i]), g[f"td_out_cls_{i}"])
+
+
+def test_constructor_contracts():
+    m = ou.L2DistanceOneClusterPerStride(**DIST_KW)
+    assert (m.name, m.metric, m.is_distance_method, m.per_class, m.per_stride) == ("L2DistancePerStride", "l2", True, True, True)
+    assert ou.L1DistanceOneClusterPerStride(**DIST_KW).name == "L1DistancePerStride"
+    assert ou.CosineDistanceOneClusterPerStride(**DIST_KW).metric == "cosine"
+    assert ou.L2DistanceOneClusterPerStride(**dict(DIST_KW, cluster_method="KMeans_16")).cluster_method == "KMeans_16"
+    for bad in (dict(which_internal_activations="logits"), dict(cluster_method="nope"), dict(agg_method="max"),
+                dict(ind_info_creation_option="x"), dict(cluster_optimization_metric="x")):
+        with pytest.raises(AssertionError):
+            ou.L2DistanceOneClusterPerStride(**dict(DIST_KW, **bad))
+    a, e, o, s = ou.MSP(**LOGIT_KW), ou.Energy(temper=1, **LOGIT_KW), ou.ODIN(temper=1000, **LOGIT_KW), ou.Sigmoid(**LOGIT_KW)
+    assert (a.name, e.name, o.name, s.name) == ("MSP", "Energy", "ODIN", "MSP")          # Sigmoid's name is 'MSP' upstream too
+    assert a.which_internal_activations == "logits" and a.cluster_method == "None" and not a.is_distance_method
+    assert ou.NoMethod(**LOGIT_KW).compute_scores(torch.zeros(4, 20), 3).tolist() == [1.0] * 4
+    with pytest.raises(NotImplementedError):
+        a.compute_distance(None, None)
+    assert a.compute_indness.__doc__ and m.thresholds is None and m.clusters is None
+
+
+def test_fusion_state_plumbing():
+    a, m = ou.MSP(**LOGIT_KW), ou.L2DistanceOneClusterPerStride(**DIST_KW)
+    f = ou.FusionMethod(a, m, "score", fusion_method_name="fusion-MSP-L2_cl_stride", cluster_method="one", **COMMON)
+    assert f.is_distance_method and f.cluster_method == "one" and f.which_internal_activations == "none"
+    f.clusters = [[np.ones((1, 4), np.float32)] * 3]
+    assert m.clusters is f.clusters
+    f.thresholds = ([0.1], [[1.0, 2.0, 3.0]])
+    assert a.thresholds == [0.1] and m.thresholds == [[1.0, 2.0, 3.0]]
+    f.thresholds = None
+    assert a.thresholds is None and m.thresholds is None
+    t = ou.TripleFusionMethod(a, ou.Energy(temper=1, **LOGIT_KW), m, cluster_method="one", **COMMON)
+    assert t.name == "fusion-MSP-Energy_L2DistancePerStride" and t.fusion_strategy == "majority_voting"
+    t.clusters = [[np.zeros((1, 4), np.float32)] * 3]
+    assert m.clusters is t.clusters
+    with pytest.raises(ValueError):
+        t.thresholds = ([], [])
+
+    class _M:                                           # configure_extra_output_of_the_model is attribute plumbing
+        class model:
+            model = [type("Head", (), {})()]
+        ckpt_path = "yolov8n.pt"
+    ou.configure_extra_output_of_the_model(_M, a)
+    assert _M.model.which_layers_to_extract == "logits" and _M.model.model[-1].output_values_before_sigmoid is True
+    ou.configure_extra_output_of_the_model(_M, m)
+    assert _M.model.which_layers_to_extract == "convolutional_layers" and _M.model.extraction_mode == "ftmaps_and_strides"
+    assert _M.model.model[-1].output_values_before_sigmoid is False
