@@ -4,25 +4,26 @@
 // with output 1x1, adaptive sampling grid, aligned=False) and the per-box loop of
 // /root/reference/ood_utils.py:2038-2180 (+ :2404-2409 normalize, :2422-2430 pairwise distance + min).
 //
-// Two launches per batch:
-//  plan_kernel  one small CTA per image: quirk-Q1 class / output slot of every box, and three per-stride box
-//               lists so that the main grid runs the heaviest boxes (largest stride = most channels) first and
-//               keeps boxes of one image adjacent (overlapping windows then hit in L2).
-//  fmap_kernel  one CTA (8 warps) per detection.
-//   1. The RoIAlign sample grid factorises: sum_{iy,ix} bilinear(y_iy, x_ix) = sum_r sum_c wy[r] wx[c] v[r,c],
-//      because both the bilinear weights and the "sample outside [-1,H]x[-1,W] contributes 0" mask are
-//      products of a y-term and an x-term.  Each CTA builds wy[], wx[] (sample coordinates are evaluated
-//      with the exact float32 operation order of the reference kernel, no FMA contraction), so every
-//      feature-map element of the window is read ONCE instead of ~4 times.
-//   2. Window gather: lanes run over the flattened window (x fastest -> consecutive lanes read consecutive
-//      addresses of an NCHW row), warps run over groups of CU channels.  Loads of the next channel group are
-//      issued before the current group is reduced (double buffer in registers); channel offsets are immediates
-//      of the load for the usual map sizes; one butterfly reduction per CU channels instead of CU full
-//      warp reductions.  NCHW rows of a box are short (8..52 B), so the unit of DRAM traffic is the 32-byte
-//      sector; see DESIGN.md for the roofline accounting.
-//   3. Pooled vector stays in shared memory: L2 norm, then every centroid of (class, stride) is streamed
-//      once (128-bit loads, L2-resident table), L1 / L2 / cosine evaluated in the same sweep, first-minimum
-//      arg-min, threshold compare in float64.
+// Two launches per batch (plus a 16-byte memset of the counters):
+//  plan_kernel   one CTA per image.  (a) quirk-Q1 class / output slot of every box.  (b) one warp per box: ROI
+//                geometry, window, and the separable RoIAlign weights.  With a 1x1 output bin
+//                    sum_{iy,ix} bilinear(y_iy, x_ix) = sum_r sum_c wy[r] wx[c] v[r,c]
+//                because both the bilinear weights and the "sample outside [-1,H]x[-1,W] contributes 0" mask are
+//                products of a y-term and an x-term.  Sample coordinates use the float32 operation order of the
+//                reference kernel (no FMA contraction).  Every window element is then read ONCE, not ~4 times.
+//                (c) the work list: a box is cut into channel slices of `cs` channels (item = box x slice,
+//                a few KB of window data), items of one (image, stride) are laid out slice-major so that the
+//                overlapping windows of one image are gathered at the same time (L1 / L2 hits).
+//  items_kernel  persistent grid, ONE WARP per work item pulled from an atomic queue: no block barriers, no tail of
+//                big boxes.  A window is addressed in 16-byte chunks (NCHW rows are 16-byte aligned for the usual map
+//                widths): lane = chunk, one LDG.128 per lane per channel, 8 channels in flight, 4 FMAs per load
+//                against the lane's fixed weight vector, and ONE transposing butterfly per 8 channels instead of 8
+//                warp reductions.  Small windows put 2/4/8 channels into one 32-lane request.  The warp that completes
+//                the last slice of a box (per-box counter) runs the distance phase: L2 norm, then L1 / L2 / cosine
+//                against the K centroids of (class, stride) in one sweep over the L2-resident table (128-bit loads,
+//                vector in registers), first-minimum arg-min and the float64 threshold compare.
+// Results do not depend on the order in which items are executed: each pooled element is produced by exactly one warp
+// in a fixed order, and the distance phase reads a completed vector.
 #include "common.cuh"
 
 #include <float.h>
@@ -33,17 +34,18 @@ namespace oodb200 {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
-#ifndef OODB200_FMAP_DOUBLE_BUFFER
-#define OODB200_FMAP_DOUBLE_BUFFER 0
-#endif
+constexpr int kPlanThreads = 128;
+constexpr int kSliceChannels = 32;          // channels per work item
+constexpr int kMaxSlices = 255;
 #ifndef OODB200_FMAP_MIN_BLOCKS
-#define OODB200_FMAP_MIN_BLOCKS 6
+#define OODB200_FMAP_MIN_BLOCKS 2
 #endif
 
 struct FmapParams {
     const float* const* map_ptrs;
     int C[3], H[3], W[3];
     float scale[3];
+    int ns[3];                  // slices per box, per stride
     const float* boxes;
     const int32_t* img_idx;
     const int32_t* stride_idx;
@@ -62,15 +64,20 @@ struct FmapParams {
     float* dist;
     int32_t* argmin;
     uint8_t* decision;
-    float* pooled;
-    int pooled_ld;
-    // plan (workspace or caller-provided)
-    int* counts;                // [4] boxes per stride (device counters, zeroed by a memset)
-    int* lists;                 // [3][n] box ids per stride, image-major
+    float* pooled_user;         // optional caller buffer [n, pooled_user_ld], rows in output order
+    int pooled_user_ld;
+    // workspace
+    int* counters;              // [0] items emitted by the plan, [1] queue head
     int32_t* cls_used;          // [n]
     int32_t* out_index;         // [n]
-    int ext_pad;                // smem floats reserved for each of wy / wx
-    int c_pad;                  // smem floats reserved for each of xs / xu
+    int4* plan_geo;             // [n] {y0, xa, wh, nxc}; nxc == 0: empty window
+    float* plan_cnt;            // [n] max(gh*gw, 1)
+    int* done;                  // [n] completed slices
+    float* wts;                 // [n][wstride]: wy[ext_y] | wx padded to chunks [ext_x]
+    int ext_y, wstride;
+    uint32_t* items;            // [<= n * max ns] (slice << 24) | box
+    float* pooled;              // [n][pooled_ld] raw pooled vectors (workspace), rows in output order
+    int pooled_ld;
 };
 
 struct AxisSample {
@@ -131,317 +138,29 @@ __device__ __forceinline__ float axis_weight(float start, float size, int grid, 
     return acc;
 }
 
-// Reduce N per-lane partial sums to N channel totals; afterwards every lane of group (lane >> (5 - log2 N))
-// holds the total of channel (lane >> (5 - log2 N)).
-template <int N>
-__device__ __forceinline__ float butterfly(float (&v)[N], int lane) {
-    int o = 16;
-#pragma unroll
-    for (int n = N; n > 1; n >>= 1, o >>= 1) {
-        const bool up = lane & o;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-            const float send = up ? v[i] : v[i + n / 2];
-            const float keep = up ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(kFull, send, o);
-        }
-    }
-    float r = v[0];
-    for (; o > 0; o >>= 1) r += __shfl_xor_sync(kFull, r, o);
-    return r;
-}
-
-template <int N> struct Log2 { static constexpr int v = 1 + Log2<N / 2>::v; };
-template <> struct Log2<1> { static constexpr int v = 0; };
-
-// Accumulate sum_p w_p * v[c, p] for every channel into acc_s[c].  R window positions per lane (chunks of 32*R),
-// CU channels per warp step, HWC = H*W when known at compile time (0: run-time stride).
-template <int R, int CU, int HWC>
-__device__ __forceinline__ void pool_window(const float* __restrict__ img, int C, int hw_rt, int W, int y0, int x0,
-                                            int wh, int ww, const float* wy, const float* wx, float* acc_s) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int HW = HWC ? HWC : hw_rt;
-    const int P = wh * ww;
-    const float inv_ww = 1.0f / (float)ww;
-    constexpr int kStep = kWarps * CU;
-    for (int base = 0; base < P; base += 32 * R) {
-        int off[R];
-        float wt[R];
-#pragma unroll
-        for (int t = 0; t < R; ++t) {
-            const int q = base + lane + 32 * t;
-            if (q < P) {
-                int y = (int)(((float)q + 0.5f) * inv_ww);
-                if (y * ww > q) --y;
-                else if ((y + 1) * ww <= q) ++y;
-                const int x = q - y * ww;
-                off[t] = (y0 + y) * W + (x0 + x);
-                wt[t] = wy[y] * wx[x];
-            } else {
-                off[t] = y0 * W + x0;
-                wt[t] = 0.f;
-            }
-        }
-        auto load = [&](float (&v)[CU][R], int c0) {
-            const float* __restrict__ b = img + (size_t)c0 * HW;
-            if (c0 + CU <= C) {
-#pragma unroll
-                for (int t = 0; t < R; ++t) {
-                    const float* __restrict__ pt = b + off[t];
-#pragma unroll
-                    for (int u = 0; u < CU; ++u) v[u][t] = ldg_f32(pt + u * HW);
-                }
-            } else {                                     // C % CU != 0: clamp (results of the extra channels are dropped)
-#pragma unroll
-                for (int t = 0; t < R; ++t)
-#pragma unroll
-                    for (int u = 0; u < CU; ++u) v[u][t] = ldg_f32(b + min(u, C - 1 - c0) * HW + off[t]);
-            }
-        };
-        auto consume = [&](float (&v)[CU][R], int c0) {
-            float a[CU];
-#pragma unroll
-            for (int u = 0; u < CU; ++u) {
-                float s = 0.f;
-#pragma unroll
-                for (int t = 0; t < R; ++t) s = fmaf(wt[t], v[u][t], s);
-                a[u] = s;
-            }
-            const float tot = butterfly<CU>(a, lane);
-            const int c = c0 + (lane >> (5 - Log2<CU>::v));
-            if ((lane & (32 / CU - 1)) == 0 && c < C) acc_s[c] = (base == 0) ? tot : acc_s[c] + tot;
-        };
-#if OODB200_FMAP_DOUBLE_BUFFER
-        float va[CU][R], vb[CU][R];
-        int c0 = warp * CU;
-        if (c0 < C) load(va, c0);
-        while (c0 < C) {                                 // ping-pong: next group's loads fly under this group's math
-            int cn = c0 + kStep;
-            if (cn < C) load(vb, cn);
-            consume(va, c0);
-            c0 = cn;
-            if (c0 >= C) break;
-            cn = c0 + kStep;
-            if (cn < C) load(va, cn);
-            consume(vb, c0);
-            c0 = cn;
-        }
-#else
-        for (int c0 = warp * CU; c0 < C; c0 += kStep) {
-            float va[CU][R];
-            load(va, c0);
-            consume(va, c0);
-        }
-#endif
-    }
-}
-
-template <int HWC>
-__device__ __forceinline__ void pool_dispatch(const float* img, int C, int hw, int W, int y0, int x0, int wh, int ww,
-                                              const float* wy, const float* wx, float* acc_s) {
-    const int P = wh * ww;
-    if (P <= 32) pool_window<1, 8, HWC>(img, C, hw, W, y0, x0, wh, ww, wy, wx, acc_s);
-    else if (P <= 64) pool_window<2, 4, HWC>(img, C, hw, W, y0, x0, wh, ww, wy, wx, acc_s);
-    else if (P <= 128) pool_window<4, 2, HWC>(img, C, hw, W, y0, x0, wh, ww, wy, wx, acc_s);
-    else pool_window<8, 2, HWC>(img, C, hw, W, y0, x0, wh, ww, wy, wx, acc_s);
-}
-
-__global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) fmap_kernel(const FmapParams p) {
-    extern __shared__ __align__(16) float smem[];
-    float* wy = smem;
-    float* wx = wy + p.ext_pad;
-    float* xs = wx + p.ext_pad;          // pooled -> normalised vector
-    float* xu = xs + p.c_pad;            // unit vector for cosine
-    __shared__ float s_red[kWarps];
-    __shared__ int s_win[4];
-    __shared__ float s_wmin[OODB200_N_METRICS][kWarps];
-    __shared__ int s_warg[OODB200_N_METRICS][kWarps];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // heaviest stride first (largest-processing-time-first keeps the tail short)
-    int i = blockIdx.x, box;
-    const int n2 = p.counts[2], n1 = p.counts[1], n0 = p.counts[0];
-    if (i < n2) box = p.lists[2 * p.n + i];
-    else if ((i -= n2) < n1) box = p.lists[p.n + i];
-    else if ((i -= n1) < n0) box = p.lists[i];
-    else return;                                      // boxes with an invalid stride were answered by the plan kernel
-    const int s = p.stride_idx[box];
-    const int img = p.img_idx[box];
-    const int out = p.out_index[box];
-    const int C = p.C[s], H = p.H[s], W = p.W[s];
-
-    // ---- ROI geometry (predict.py:64-70 -> roi_align, aligned=False) ----
-    const float sc = p.scale[s];
-    const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)box);
-    const float sw = __fmul_rn(bx.x, sc), sh = __fmul_rn(bx.y, sc);
-    const float ew = __fmul_rn(bx.z, sc), eh = __fmul_rn(bx.w, sc);
-    const float rw = fmaxf(__fsub_rn(ew, sw), 1.0f), rh = fmaxf(__fsub_rn(eh, sh), 1.0f);
-    const int gw = (int)ceilf(rw), gh = (int)ceilf(rh);
-    const float count = (float)max(gh * gw, 1);
-
-    if (tid == 0) {
-        s_win[0] = INT_MAX; s_win[1] = -1; s_win[2] = INT_MAX; s_win[3] = -1;
-    }
-    __syncthreads();
-    for (int k = tid; k < gh + gw; k += kThreads) {
-        const bool isy = k < gh;
-        const AxisSample a = isy ? axis_sample(sh, rh, gh, H, k) : axis_sample(sw, rw, gw, W, k - gh);
-        if (a.valid) {
-            atomicMin(&s_win[isy ? 0 : 2], a.low);
-            atomicMax(&s_win[isy ? 1 : 3], a.high);
-        }
-    }
-    __syncthreads();
-    const int y0 = s_win[0], x0 = s_win[2];
-    const int wh = s_win[1] - y0 + 1, ww = s_win[3] - x0 + 1;
-    const bool empty = (s_win[1] < 0) || (s_win[3] < 0);
-
-    if (!empty) {
-        for (int r = tid; r < wh + ww; r += kThreads) {
-            if (r < wh) wy[r] = axis_weight(sh, rh, gh, H, y0 + r);
-            else wx[r - wh] = axis_weight(sw, rw, gw, W, x0 + (r - wh));
-        }
-    }
-    __syncthreads();
-
-    // ---- gather + pool ----
-    if (empty) {
-        for (int c = tid; c < C; c += kThreads) xs[c] = 0.f;
-    } else {
-        const float* img_base = p.map_ptrs[img * 3 + s];
-        const int HW = H * W;
-        switch (HW) {                                 // map sizes of 320/640/1280-pixel inputs: immediate channel offsets
-            case 400: pool_dispatch<400>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs); break;
-            case 1600: pool_dispatch<1600>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs); break;
-            case 6400: pool_dispatch<6400>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs); break;
-            case 25600: pool_dispatch<25600>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs); break;
-            default: pool_dispatch<0>(img_base, C, HW, W, y0, x0, wh, ww, wy, wx, xs); break;
-        }
-    }
-    __syncthreads();
-    // ---- average (roi_align.py:192-196) and, for K2, the squared norm in the same sweep ----
-    float ss = 0.f;
-    for (int c = tid; c < C; c += kThreads) {
-        const float v = empty ? 0.f : __fdiv_rn(xs[c], count);
-        xs[c] = v;
-        ss = fmaf(v, v, ss);
-        if (p.pooled) p.pooled[(size_t)out * p.pooled_ld + c] = v;
-    }
-    if (p.cent == nullptr) return;                    // K1 only
-
-    // ---- K2: normalise (ood_utils.py:2409 -> sklearn normalize) ----
-    if (p.normalize) {
-        ss = block_sum<kWarps>(ss, s_red);
-        float nrm = sqrtf(ss);
-        if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;      // _handle_zeros_in_scale
-        for (int c = tid; c < C; c += kThreads) xs[c] = __fdiv_rn(xs[c], nrm);
-    }
-    __syncthreads();
-    const bool want_l1 = p.metric_mask & (1 << OODB200_METRIC_L1);
-    const bool want_l2 = p.metric_mask & (1 << OODB200_METRIC_L2);
-    const bool want_cos = p.metric_mask & (1 << OODB200_METRIC_COS);
-    if (want_cos) {                                   // cosine_distances re-normalises X (pairwise.py:1171-1182)
-        float s2 = 0.f;
-        for (int c = tid; c < C; c += kThreads) s2 = fmaf(xs[c], xs[c], s2);
-        s2 = block_sum<kWarps>(s2, s_red);
-        float n2v = sqrtf(s2);
-        if (n2v < 10.f * FLT_EPSILON) n2v = 1.f;
-        for (int c = tid; c < C; c += kThreads) xu[c] = __fdiv_rn(xs[c], n2v);
-        __syncthreads();
-    }
-
-    // ---- distances to the centroids of (class, stride); warps stride over centroids ----
-    const int cls = p.cls_used[box];
-    const bool cls_ok = cls >= 0 && cls < p.nc;
-    const int K = cls_ok ? p.cent_k[s * p.nc + cls] : 0;
-    float best[OODB200_N_METRICS] = {FLT_MAX, FLT_MAX, FLT_MAX};
-    int barg[OODB200_N_METRICS] = {-1, -1, -1};
-    if (K > 0) {
-        const int64_t off = p.cent_off[s * p.nc + cls];
-        const bool vec = (C % 4 == 0) && (off % 4 == 0);
-        for (int k = warp; k < K; k += kWarps) {
-            const float* __restrict__ ck = p.cent + off + (int64_t)k * C;
-            const float* __restrict__ cu = want_cos ? p.cent_unit + off + (int64_t)k * C : nullptr;
-            float a1 = 0.f, a2 = 0.f, ac = 0.f;
-            if (vec) {
-                for (int d = lane * 4; d < C; d += 128) {
-                    const float4 x4 = *reinterpret_cast<const float4*>(xs + d);
-                    if (want_l1 || want_l2) {
-                        const float4 c4 = __ldg(reinterpret_cast<const float4*>(ck + d));
-                        const float d0 = x4.x - c4.x, d1 = x4.y - c4.y, d2 = x4.z - c4.z, d3 = x4.w - c4.w;
-                        a1 += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
-                        a2 = fmaf(d0, d0, a2); a2 = fmaf(d1, d1, a2); a2 = fmaf(d2, d2, a2); a2 = fmaf(d3, d3, a2);
-                    }
-                    if (want_cos) {
-                        const float4 u4 = *reinterpret_cast<const float4*>(xu + d);
-                        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cu + d));
-                        ac = fmaf(u4.x, c4.x, ac); ac = fmaf(u4.y, c4.y, ac); ac = fmaf(u4.z, c4.z, ac); ac = fmaf(u4.w, c4.w, ac);
-                    }
-                }
-            } else {
-                for (int d = lane; d < C; d += 32) {
-                    const float x = xs[d];
-                    if (want_l1 || want_l2) {
-                        const float df = x - __ldg(ck + d);
-                        a1 += fabsf(df);
-                        a2 = fmaf(df, df, a2);
-                    }
-                    if (want_cos) ac = fmaf(xu[d], __ldg(cu + d), ac);
-                }
-            }
-            if (want_l1) {
-                a1 = warp_sum(a1);
-                if (a1 < best[0]) { best[0] = a1; barg[0] = k; }
-            }
-            if (want_l2) {
-                a2 = sqrtf(fmaxf(warp_sum(a2), 0.f));
-                if (a2 < best[1]) { best[1] = a2; barg[1] = k; }
-            }
-            if (want_cos) {
-                ac = fminf(fmaxf(1.0f - warp_sum(ac), 0.f), 2.f);
-                if (ac < best[2]) { best[2] = ac; barg[2] = k; }
-            }
-        }
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int m = 0; m < OODB200_N_METRICS; ++m) { s_wmin[m][warp] = best[m]; s_warg[m][warp] = barg[m]; }
-    }
-    __syncthreads();
-    if (tid < OODB200_N_METRICS && (p.metric_mask >> tid & 1)) {
-        const int m = tid;
-        float d = 1000.f;                             // ood_utils.py:2159-2164
-        int a = -1;
-        if (K > 0) {
-            d = FLT_MAX;
-            for (int w = 0; w < kWarps; ++w) {        // first minimum: smaller distance, then smaller index
-                const int wa = s_warg[m][w];
-                if (wa >= 0 && (s_wmin[m][w] < d || (s_wmin[m][w] == d && wa < a))) { d = s_wmin[m][w]; a = wa; }
-            }
-        }
-        const double t = cls_ok ? p.thr[(size_t)m * 3 * p.nc + s * p.nc + cls] : nan("");
-        const size_t o = (size_t)m * p.n + out;
-        p.dist[o] = d;
-        p.argmin[o] = a;
-        p.decision[o] = (t == t && (double)d < t) ? 1 : 0;   // NaN threshold = "no threshold" -> OoD (:2173-2180)
-    }
-}
-
-// One CTA per image: quirk Q1 (ood_utils.py:2152-2154) and the per-stride box lists (image-major inside a stride).
-__global__ void __launch_bounds__(128) plan_kernel(const FmapParams p) {
+// ---------------------------------------------------------------------------------------------- plan
+// One CTA per image: quirk Q1 (ood_utils.py:2152-2154), per-box geometry + weights, and the work list.
+__global__ void __launch_bounds__(kPlanThreads) plan_kernel(const FmapParams p) {
     const int img = blockIdx.x;
     const int b0 = p.img_start[img], m = p.img_start[img + 1] - b0;
-    __shared__ int s_cnt[4], s_base[4];
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_cnt[4], s_item0[3];
+    if (tid < 4) s_cnt[tid] = 0;
     __syncthreads();
-    for (int b = threadIdx.x; b < m; b += blockDim.x) {
+    for (int b = tid; b < m; b += kPlanThreads) {
         const int s = p.stride_idx[b0 + b];
         atomicAdd(&s_cnt[(s >= 0 && s <= 2) ? s : 3], 1);
     }
     __syncthreads();
-    if (threadIdx.x < 3) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&p.counts[threadIdx.x], s_cnt[threadIdx.x]) : 0;
+    if (tid == 0) {                                   // reserve this image's range of the work list (heaviest stride first)
+        const int tot = s_cnt[2] * p.ns[2] + s_cnt[1] * p.ns[1] + s_cnt[0] * p.ns[0];
+        const int base = tot ? atomicAdd(&p.counters[0], tot) : 0;
+        s_item0[2] = base;
+        s_item0[1] = base + s_cnt[2] * p.ns[2];
+        s_item0[0] = s_item0[1] + s_cnt[1] * p.ns[1];
+    }
     __syncthreads();
-    for (int b = threadIdx.x; b < m; b += blockDim.x) {
+    for (int b = tid; b < m; b += kPlanThreads) {
         const int s = p.stride_idx[b0 + b];
         const bool ok = s >= 0 && s <= 2;
         int j = 0;                                    // rank among earlier boxes of the same kind (m <= 300)
@@ -459,7 +178,9 @@ __global__ void __launch_bounds__(128) plan_kernel(const FmapParams p) {
         p.cls_used[b0 + b] = cls_u;
         p.out_index[b0 + b] = out;
         if (ok) {
-            p.lists[s * p.n + s_base[s] + j] = b0 + b;
+            const int nb = s_cnt[s];
+            for (int sl = 0; sl < p.ns[s]; ++sl)      // slice-major inside (image, stride)
+                p.items[s_item0[s] + sl * nb + j] = ((uint32_t)sl << 24) | (uint32_t)(b0 + b);
         } else if (p.cent) {                          // never pooled by the reference either: answered here
             for (int k = 0; k < OODB200_N_METRICS; ++k)
                 if (p.metric_mask >> k & 1) {
@@ -470,9 +191,53 @@ __global__ void __launch_bounds__(128) plan_kernel(const FmapParams p) {
                 }
         }
     }
+    // ---- ROI geometry (predict.py:64-70 -> roi_align, aligned=False), one warp per box ----
+    for (int b = warp; b < m; b += kPlanThreads / 32) {
+        const int box = b0 + b;
+        const int s = p.stride_idx[box];
+        if (s < 0 || s > 2) continue;
+        const int H = p.H[s], W = p.W[s];
+        const float sc = p.scale[s];
+        const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)box);
+        const float sw = __fmul_rn(bx.x, sc), sh = __fmul_rn(bx.y, sc);
+        const float ew = __fmul_rn(bx.z, sc), eh = __fmul_rn(bx.w, sc);
+        const float rw = fmaxf(__fsub_rn(ew, sw), 1.0f), rh = fmaxf(__fsub_rn(eh, sh), 1.0f);
+        const int gw = (int)ceilf(rw), gh = (int)ceilf(rh);
+        int ylo = INT_MAX, yhi = -1, xlo = INT_MAX, xhi = -1;
+        for (int k = lane; k < gh; k += 32) {
+            const AxisSample a = axis_sample(sh, rh, gh, H, k);
+            if (a.valid) { ylo = min(ylo, a.low); yhi = max(yhi, a.high); }
+        }
+        for (int k = lane; k < gw; k += 32) {
+            const AxisSample a = axis_sample(sw, rw, gw, W, k);
+            if (a.valid) { xlo = min(xlo, a.low); xhi = max(xhi, a.high); }
+        }
+        ylo = __reduce_min_sync(kFull, ylo); yhi = __reduce_max_sync(kFull, yhi);
+        xlo = __reduce_min_sync(kFull, xlo); xhi = __reduce_max_sync(kFull, xhi);
+        const bool empty = yhi < 0 || xhi < 0;
+        int wh = 0, nxc = 0, xa = 0;
+        if (!empty) {
+            wh = yhi - ylo + 1;
+            const int ww = xhi - xlo + 1;
+            xa = xlo & ~3;
+            nxc = ((xlo + ww + 3) >> 2) - (xa >> 2);
+            float* __restrict__ wy = p.wts + (size_t)box * p.wstride;
+            float* __restrict__ wx = wy + p.ext_y;
+            for (int r = lane; r < wh; r += 32) wy[r] = axis_weight(sh, rh, gh, H, ylo + r);
+            for (int i = lane; i < 4 * nxc; i += 32) {
+                const int x = xa + i;
+                wx[i] = (x >= xlo && x <= xhi) ? axis_weight(sw, rw, gw, W, x) : 0.f;
+            }
+        }
+        if (lane == 0) {
+            p.plan_geo[box] = make_int4(empty ? 0 : ylo, xa, wh, nxc);
+            p.plan_cnt[box] = (float)max(gh * gw, 1);
+            p.done[box] = 0;
+        }
+    }
 }
 
-// standalone Q1 plan (same arithmetic as plan_kernel, without the lists)
+// standalone Q1 plan (same arithmetic as plan_kernel, without the work list)
 __global__ void q1_plan_kernel(const int32_t* __restrict__ img_start, const int32_t* __restrict__ stride_idx,
                                const int32_t* __restrict__ cls, int32_t* __restrict__ cls_used,
                                int32_t* __restrict__ out_index) {
@@ -501,59 +266,449 @@ __global__ void q1_plan_kernel(const int32_t* __restrict__ img_start, const int3
     }
 }
 
-struct WorkspaceLayout {
-    size_t counts, lists, cls_used, out_index, total;
+// ---------------------------------------------------------------------------------------------- gather + pool
+template <int N> struct Log2 { static constexpr int v = 1 + Log2<N / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
+
+// Segmented transposing butterfly: the 32 lanes are 32/G segments of G = 1<<LG lanes; v[u] holds this lane's partial
+// sum of request u.  Afterwards every lane holds the segment total of request u = (lane & (G-1)) >> (LG - log2 CU).
+template <int LG, int CU>
+__device__ __forceinline__ float seg_butterfly(float (&v)[CU], int lane) {
+    static_assert(Log2<CU>::v <= LG, "CU requests need log2(CU) butterfly levels inside a segment");
+    int o = 1 << (LG - 1);
+#pragma unroll
+    for (int n = CU; n > 1; n >>= 1, o >>= 1) {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, o);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (; o > 0; o >>= 1) r += __shfl_xor_sync(kFull, r, o);
+    return r;
+}
+
+// Pool channels [c_lo, c_hi) of one window.  G = 1<<LG lanes cover the window's chunks (T chunk slots per lane),
+// 32/G channels share one request, CU requests are in flight.
+template <int LG, int T, int CU, bool ACC = false>
+__device__ __forceinline__ void pool_slice(const float* __restrict__ img, int C, int HW, int W, int4 geo,
+                                           const float* __restrict__ wy, const float* __restrict__ wx, float count,
+                                           int c_lo, int c_hi, float* __restrict__ out0, float* __restrict__ out1) {
+    constexpr int G = 1 << LG, CPR = 32 >> LG, STEP = CU * CPR;
+    const int lane = threadIdx.x & 31, l = lane & (G - 1), sub = lane >> LG;
+    const int y0 = geo.x, xa = geo.y, nxc = geo.w, nch = geo.z * geo.w;
+    float4 w[T];
+    int off[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const int q = l + G * t;
+        if (q < nch) {
+            const int r = q / nxc, xc = q - r * nxc;
+            const float a = __ldg(wy + r);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(wx) + xc);
+            w[t] = make_float4(a * b.x, a * b.y, a * b.z, a * b.w);
+            off[t] = (y0 + r) * W + xa + 4 * xc;
+        } else {
+            w[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            off[t] = y0 * W + xa;
+        }
+    }
+    const int u_mine = l >> (LG - Log2<CU>::v);
+    const bool holder = (l & ((1 << (LG - Log2<CU>::v)) - 1)) == 0;
+    for (int cb = c_lo; cb < c_hi; cb += STEP) {
+        float4 v[CU][T];
+#pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            const int c = min(cb + u * CPR + sub, C - 1);            // partial last step: clamp, result dropped
+            const float* __restrict__ pc = img + (size_t)c * HW;
+#pragma unroll
+            for (int t = 0; t < T; ++t) v[u][t] = __ldg(reinterpret_cast<const float4*>(pc + off[t]));
+        }
+        float a[CU];
+#pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            float s = 0.f;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                s = fmaf(w[t].x, v[u][t].x, s); s = fmaf(w[t].y, v[u][t].y, s);
+                s = fmaf(w[t].z, v[u][t].z, s); s = fmaf(w[t].w, v[u][t].w, s);
+            }
+            a[u] = s;
+        }
+        const float tot = seg_butterfly<LG, CU>(a, lane);
+        const int c = cb + u_mine * CPR + sub;
+        if (holder && c < c_hi) {
+            float val = __fdiv_rn(tot, count);                        // average over the sample grid (roi_align.py:192-196)
+            if (ACC) val += out0[c];                                  // later pass of a tiled window (same lane, same channel)
+            out0[c] = val;
+            if (out1) out1[c] = val;
+        }
+    }
+}
+
+// Maps whose rows are not 16-byte aligned (W % 4 != 0, odd base pointer): plain scalar gather, lanes over the window.
+__device__ __noinline__ void pool_scalar(const float* __restrict__ img, int HW, int W, int y0, int xa, int wh, int nxc,
+                                         const float* __restrict__ wy, const float* __restrict__ wx, float count,
+                                         int c_lo, int c_hi, float* __restrict__ out0, float* __restrict__ out1) {
+    const int lane = threadIdx.x & 31;
+    const int ww = 4 * nxc, P = wh * ww;
+    for (int c = c_lo; c < c_hi; ++c) {
+        const float* __restrict__ pc = img + (size_t)c * HW;
+        float s = 0.f;
+        for (int q = lane; q < P; q += 32) {
+            const int r = q / ww, x = q - r * ww;
+            const float wgt = __ldg(wy + r) * __ldg(wx + x);
+            if (wgt != 0.f) s = fmaf(wgt, __ldg(pc + (y0 + r) * W + xa + x), s);   // padding columns may lie outside the row
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+            const float val = __fdiv_rn(s, count);
+            out0[c] = val;
+            if (out1) out1[c] = val;
+        }
+    }
+}
+
+__device__ __forceinline__ void pool_dispatch(const float* img, int C, int HW, int W, int4 geo, const float* wy,
+                                              const float* wx, float count, int c_lo, int c_hi, float* out0, float* out1) {
+    const int nch = geo.z * geo.w;
+    if (nch <= 4) pool_slice<2, 1, 4>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+    else if (nch <= 8) pool_slice<3, 1, 8>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+    else if (nch <= 16) pool_slice<4, 1, 8>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+    else if (nch <= 32) pool_slice<5, 1, 8>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+    else if (nch <= 64) pool_slice<5, 2, 8>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+    else if (nch <= 128) pool_slice<5, 4, 4>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+    else if (nch <= 256) pool_slice<5, 8, 1>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+    else {
+        // very large windows (> 1024 elements per channel): tiles of <= 256 chunks, accumulated in the output row
+        const int cols = min(geo.w, 256);
+        const int rows = max(256 / cols, 1);
+        bool first = true;
+        for (int r0 = 0; r0 < geo.z; r0 += rows)
+            for (int x0 = 0; x0 < geo.w; x0 += cols) {
+                const int4 g2 = make_int4(geo.x + r0, geo.y + 4 * x0, min(rows, geo.z - r0), min(cols, geo.w - x0));
+                if (first) pool_slice<5, 8, 1, false>(img, C, HW, W, g2, wy + r0, wx + 4 * x0, count, c_lo, c_hi, out0, out1);
+                else pool_slice<5, 8, 1, true>(img, C, HW, W, g2, wy + r0, wx + 4 * x0, count, c_lo, c_hi, out0, out1);
+                first = false;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- distance phase
+struct Best {
+    float d[OODB200_N_METRICS];
+    int a[OODB200_N_METRICS];
 };
 
-static WorkspaceLayout layout_of(int n) {
+__device__ __forceinline__ void write_result(const FmapParams& p, int s, int cls, bool cls_ok, int K, int out, const Best& b) {
+    const int lane = threadIdx.x & 31;
+    if (lane < OODB200_N_METRICS && (p.metric_mask >> lane & 1)) {
+        const int m = lane;
+        const float bd = m == 0 ? b.d[0] : (m == 1 ? b.d[1] : b.d[2]);
+        const int ba = m == 0 ? b.a[0] : (m == 1 ? b.a[1] : b.a[2]);
+        const float d = K > 0 ? bd : 1000.f;                         // no cluster: ood_utils.py:2159-2164
+        const double t = cls_ok ? p.thr[(size_t)m * 3 * p.nc + s * p.nc + cls] : nan("");
+        const size_t o = (size_t)m * p.n + out;
+        p.dist[o] = d;
+        p.argmin[o] = K > 0 ? ba : -1;
+        p.decision[o] = (t == t && (double)d < t) ? 1 : 0;           // NaN threshold = "no threshold" -> OoD (:2173-2180)
+    }
+}
+
+// Vector in registers: NJ float4 per lane (C <= 128 * NJ, C % 4 == 0, 16-byte aligned centroid slices).
+template <int NJ>
+__device__ __forceinline__ void finalize_vec(const FmapParams& p, int box) {
+    const int lane = threadIdx.x & 31;
+    const int s = p.stride_idx[box], C = p.C[s], out = p.out_index[box];
+    const float* __restrict__ row = p.pooled + (size_t)out * p.pooled_ld;
+    float4 x[NJ];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int d = lane * 4 + 128 * j;
+        x[j] = d < C ? __ldcg(reinterpret_cast<const float4*>(row + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ss = fmaf(x[j].x, x[j].x, ss); ss = fmaf(x[j].y, x[j].y, ss);
+        ss = fmaf(x[j].z, x[j].z, ss); ss = fmaf(x[j].w, x[j].w, ss);
+    }
+    if (p.normalize) {                                // ood_utils.py:2409 -> sklearn normalize
+        float nrm = sqrtf(warp_sum(ss));
+        if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;      // _handle_zeros_in_scale
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            x[j].x = __fdiv_rn(x[j].x, nrm); x[j].y = __fdiv_rn(x[j].y, nrm);
+            x[j].z = __fdiv_rn(x[j].z, nrm); x[j].w = __fdiv_rn(x[j].w, nrm);
+        }
+    }
+    const bool want_l1 = p.metric_mask & (1 << OODB200_METRIC_L1);
+    const bool want_l2 = p.metric_mask & (1 << OODB200_METRIC_L2);
+    const bool want_cos = p.metric_mask & (1 << OODB200_METRIC_COS);
+    float n2v = 1.f;
+    if (want_cos) {                                   // cosine_distances re-normalises X (pairwise.py:1171-1182)
+        float s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            s2 = fmaf(x[j].x, x[j].x, s2); s2 = fmaf(x[j].y, x[j].y, s2);
+            s2 = fmaf(x[j].z, x[j].z, s2); s2 = fmaf(x[j].w, x[j].w, s2);
+        }
+        n2v = sqrtf(warp_sum(s2));
+        if (n2v < 10.f * FLT_EPSILON) n2v = 1.f;
+    }
+    const int cls = p.cls_used[box];
+    const bool cls_ok = cls >= 0 && cls < p.nc;
+    const int K = cls_ok ? p.cent_k[s * p.nc + cls] : 0;
+    Best b = {{FLT_MAX, FLT_MAX, FLT_MAX}, {-1, -1, -1}};
+    if (K > 0) {
+        const int64_t off = p.cent_off[s * p.nc + cls];
+        for (int k = 0; k < K; ++k) {
+            const float* __restrict__ ck = p.cent + off + (int64_t)k * C;
+            const float* __restrict__ cu = p.cent_unit + off + (int64_t)k * C;
+            float a1 = 0.f, a2 = 0.f, ac = 0.f;
+            if (want_l1 || want_l2) {
+                float4 c4[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int d = lane * 4 + 128 * j;
+                    c4[j] = d < C ? __ldg(reinterpret_cast<const float4*>(ck + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const float d0 = x[j].x - c4[j].x, d1 = x[j].y - c4[j].y, d2 = x[j].z - c4[j].z, d3 = x[j].w - c4[j].w;
+                    a1 += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+                    a2 = fmaf(d0, d0, a2); a2 = fmaf(d1, d1, a2); a2 = fmaf(d2, d2, a2); a2 = fmaf(d3, d3, a2);
+                }
+            }
+            if (want_cos) {
+                float4 c4[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int d = lane * 4 + 128 * j;
+                    c4[j] = d < C ? __ldg(reinterpret_cast<const float4*>(cu + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    ac = fmaf(x[j].x, c4[j].x, ac); ac = fmaf(x[j].y, c4[j].y, ac);
+                    ac = fmaf(x[j].z, c4[j].z, ac); ac = fmaf(x[j].w, c4[j].w, ac);
+                }
+            }
+            if (want_l1) { a1 = warp_sum(a1); if (a1 < b.d[0]) { b.d[0] = a1; b.a[0] = k; } }
+            if (want_l2) { a2 = sqrtf(fmaxf(warp_sum(a2), 0.f)); if (a2 < b.d[1]) { b.d[1] = a2; b.a[1] = k; } }
+            if (want_cos) {                           // X / ||X|| applied to the sum (same value to float32 rounding)
+                ac = fminf(fmaxf(1.0f - __fdiv_rn(warp_sum(ac), n2v), 0.f), 2.f);
+                if (ac < b.d[2]) { b.d[2] = ac; b.a[2] = k; }
+            }
+        }
+    }
+    write_result(p, s, cls, cls_ok, K, out, b);               // lane m reports metric m (all lanes hold the same totals)
+}
+
+// Any C / alignment: the vector is re-read from the (L1-resident) pooled row for every centroid.
+__device__ __noinline__ Best finalize_generic(const float* __restrict__ row, int C, int normalize, int metric_mask,
+                                              const float* __restrict__ cent, const float* __restrict__ cent_unit, int K) {
+    const int lane = threadIdx.x & 31;
+    float nrm = 1.f, n2v = 1.f;
+    if (normalize) {
+        float ss = 0.f;
+        for (int d = lane; d < C; d += 32) { const float v = __ldcg(row + d); ss = fmaf(v, v, ss); }
+        nrm = sqrtf(warp_sum(ss));
+        if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;
+    }
+    const bool want_l1 = metric_mask & (1 << OODB200_METRIC_L1);
+    const bool want_l2 = metric_mask & (1 << OODB200_METRIC_L2);
+    const bool want_cos = metric_mask & (1 << OODB200_METRIC_COS);
+    auto xn = [&](int d) { const float v = __ldcg(row + d); return normalize ? __fdiv_rn(v, nrm) : v; };
+    if (want_cos) {
+        float s2 = 0.f;
+        for (int d = lane; d < C; d += 32) { const float v = xn(d); s2 = fmaf(v, v, s2); }
+        n2v = sqrtf(warp_sum(s2));
+        if (n2v < 10.f * FLT_EPSILON) n2v = 1.f;
+    }
+    Best b = {{FLT_MAX, FLT_MAX, FLT_MAX}, {-1, -1, -1}};
+    for (int k = 0; k < K; ++k) {
+        const float* __restrict__ ck = cent + (int64_t)k * C;
+        const float* __restrict__ cu = cent_unit + (int64_t)k * C;
+        float a1 = 0.f, a2 = 0.f, ac = 0.f;
+        for (int d = lane; d < C; d += 32) {
+            const float x = xn(d);
+            if (want_l1 || want_l2) {
+                const float df = x - __ldg(ck + d);
+                a1 += fabsf(df);
+                a2 = fmaf(df, df, a2);
+            }
+            if (want_cos) ac = fmaf(x, __ldg(cu + d), ac);
+        }
+        if (want_l1) { a1 = warp_sum(a1); if (a1 < b.d[0]) { b.d[0] = a1; b.a[0] = k; } }
+        if (want_l2) { a2 = sqrtf(fmaxf(warp_sum(a2), 0.f)); if (a2 < b.d[1]) { b.d[1] = a2; b.a[1] = k; } }
+        if (want_cos) {
+            ac = fminf(fmaxf(1.0f - __fdiv_rn(warp_sum(ac), n2v), 0.f), 2.f);
+            if (ac < b.d[2]) { b.d[2] = ac; b.a[2] = k; }
+        }
+    }
+    return b;
+}
+
+__device__ __forceinline__ void finalize(const FmapParams& p, int box) {
+    const int s = p.stride_idx[box], C = p.C[s];
+    const int cls = p.cls_used[box];
+    bool vec = (C % 4 == 0) && C <= 1024;
+    if (vec && cls >= 0 && cls < p.nc) vec = (p.cent_off[s * p.nc + cls] % 4 == 0);
+    if (!vec) {
+        const bool cls_ok = cls >= 0 && cls < p.nc;
+        const int K = cls_ok ? p.cent_k[s * p.nc + cls] : 0;
+        const int64_t off = K > 0 ? p.cent_off[s * p.nc + cls] : 0;
+        const int out = p.out_index[box];
+        const Best b = finalize_generic(p.pooled + (size_t)out * p.pooled_ld, C, p.normalize, p.metric_mask, p.cent + off,
+                                        p.cent_unit + off, K);
+        write_result(p, s, cls, cls_ok, K, out, b);
+        return;
+    }
+    switch ((C + 127) / 128) {
+        case 1: finalize_vec<1>(p, box); break;
+        case 2: finalize_vec<2>(p, box); break;
+        case 3: finalize_vec<3>(p, box); break;
+        case 4: finalize_vec<4>(p, box); break;
+        case 5: finalize_vec<5>(p, box); break;
+        case 6: finalize_vec<6>(p, box); break;
+        case 7: finalize_vec<7>(p, box); break;
+        default: finalize_vec<8>(p, box); break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- main kernel
+__global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kernel(const FmapParams p) {
+    const int lane = threadIdx.x & 31;
+    const int n_items = p.counters[0];
+    auto fetch = [&]() {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&p.counters[1], 1);
+        return __shfl_sync(kFull, i, 0);
+    };
+    int it = fetch();
+    while (it < n_items) {
+        const uint32_t word = p.items[it];
+        const int nxt = fetch();                       // next item's index travels under this item's loads
+        const int box = (int)(word & 0xFFFFFFu), sl = (int)(word >> 24);
+        const int s = p.stride_idx[box];
+        const int C = p.C[s], W = p.W[s], HW = p.H[s] * W;
+        const int4 geo = p.plan_geo[box];
+        const int out = p.out_index[box];
+        const int c_lo = sl * kSliceChannels, c_hi = min(C, c_lo + kSliceChannels);
+        float* __restrict__ out0 = p.pooled + (size_t)out * p.pooled_ld;
+        float* __restrict__ out1 = p.pooled_user ? p.pooled_user + (size_t)out * p.pooled_user_ld : nullptr;
+        if (geo.w == 0) {                              // no sample inside the map (Q5): all-zero vector
+            for (int c = c_lo + lane; c < c_hi; c += 32) { out0[c] = 0.f; if (out1) out1[c] = 0.f; }
+        } else {
+            const float* __restrict__ img = p.map_ptrs[p.img_idx[box] * 3 + s];
+            const float* __restrict__ wy = p.wts + (size_t)box * p.wstride;
+            const float* __restrict__ wx = wy + p.ext_y;
+            const float count = p.plan_cnt[box];
+            const bool vec = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (HW % 4 == 0);
+            if (vec) pool_dispatch(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+            else pool_scalar(img, HW, W, geo.x, geo.y, geo.z, geo.w, wy, wx, count, c_lo, c_hi, out0, out1);
+        }
+        if (p.cent) {                                  // last slice of the box -> distance phase
+            __threadfence();
+            int last = 0;
+            if (lane == 0) last = (atomicAdd(&p.done[box], 1) == p.ns[s] - 1);
+            last = __shfl_sync(kFull, last, 0);
+            if (last) {
+                __threadfence();
+                finalize(p, box);
+            }
+        }
+        it = nxt;
+    }
+}
+
+struct WorkspaceLayout {
+    size_t counters, cls_used, out_index, plan_geo, plan_cnt, done, wts, items, pooled, total;
+    int ext_y, wstride, pooled_ld, max_ns;
+};
+
+static WorkspaceLayout layout_of(int n, const int32_t* map_chw) {
     WorkspaceLayout L;
+    int hmax = 1, wmax = 1, cmax = 1;
+    for (int s = 0; s < 3; ++s) {
+        cmax = max(cmax, map_chw[3 * s]);
+        hmax = max(hmax, map_chw[3 * s + 1]);
+        wmax = max(wmax, map_chw[3 * s + 2]);
+    }
+    L.ext_y = (hmax + 3) & ~3;
+    L.wstride = L.ext_y + ((wmax + 3) & ~3) + 4;
+    L.pooled_ld = (cmax + 3) & ~3;
+    L.max_ns = (cmax + kSliceChannels - 1) / kSliceChannels;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;
-    L.counts = o; o = up(o + 16);
-    L.lists = o; o = up(o + sizeof(int) * 3 * (size_t)n);
-    L.cls_used = o; o = up(o + sizeof(int) * (size_t)n);
-    L.out_index = o; o = up(o + sizeof(int) * (size_t)n);
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    L.counters = o; o = up(o + 16);
+    L.cls_used = o; o = up(o + 4 * nn);
+    L.out_index = o; o = up(o + 4 * nn);
+    L.plan_geo = o; o = up(o + 16 * nn);
+    L.plan_cnt = o; o = up(o + 4 * nn);
+    L.done = o; o = up(o + 4 * nn);
+    L.wts = o; o = up(o + 4 * nn * L.wstride);
+    L.items = o; o = up(o + 4 * nn * L.max_ns);
+    L.pooled = o; o = up(o + 4 * nn * L.pooled_ld);
     L.total = o;
     return L;
 }
 
+static int g_sm_count = 0, g_items_per_sm = 0;
+
 static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale, int32_t* cls_used_out,
                        int32_t* out_index_out, void* workspace, int64_t workspace_bytes, void* stream, const char* what) {
-    int ext = 1, cmax = 1;
     for (int s = 0; s < 3; ++s) {
         p.C[s] = map_chw[3 * s];
         p.H[s] = map_chw[3 * s + 1];
         p.W[s] = map_chw[3 * s + 2];
         p.scale[s] = scale[s];
         OODB200_REQUIRE(p.C[s] > 0 && p.H[s] > 0 && p.W[s] > 0, "%s: map %d has non-positive shape", what, s);
-        ext = max(ext, max(p.H[s], p.W[s]));
-        cmax = max(cmax, p.C[s]);
+        p.ns[s] = (p.C[s] + kSliceChannels - 1) / kSliceChannels;
+        OODB200_REQUIRE(p.ns[s] <= kMaxSlices, "%s: map %d has too many channels (%d)", what, s, p.C[s]);
+        OODB200_REQUIRE((long long)p.H[s] * p.W[s] < (1LL << 30), "%s: map %d too large", what, s);
     }
-    p.ext_pad = (ext + 3) & ~3;
-    p.c_pad = (cmax + 3) & ~3;
-    const size_t smem = sizeof(float) * (2 * (size_t)p.ext_pad + 2 * (size_t)p.c_pad);
-    OODB200_REQUIRE(smem <= 200 * 1024, "%s: maps too large for the shared-memory layout (%zu B)", what, smem);
+    OODB200_REQUIRE(p.n < (1 << 24), "%s: at most %d boxes per call", what, (1 << 24) - 1);
     if (p.n == 0) return OODB200_OK;
-    const WorkspaceLayout L = layout_of(p.n);
+    const WorkspaceLayout L = layout_of(p.n, map_chw);
     OODB200_REQUIRE(workspace && workspace_bytes >= (int64_t)L.total, "%s: workspace too small (%lld < %zu bytes)", what,
                     (long long)workspace_bytes, L.total);
     OODB200_REQUIRE(((uintptr_t)workspace & 255) == 0, "%s: workspace must be 256-byte aligned", what);
     char* ws = (char*)workspace;
-    p.counts = (int*)(ws + L.counts);
-    p.lists = (int*)(ws + L.lists);
+    p.counters = (int*)(ws + L.counters);
     p.cls_used = cls_used_out ? cls_used_out : (int32_t*)(ws + L.cls_used);
     p.out_index = out_index_out ? out_index_out : (int32_t*)(ws + L.out_index);
+    p.plan_geo = (int4*)(ws + L.plan_geo);
+    p.plan_cnt = (float*)(ws + L.plan_cnt);
+    p.done = (int*)(ws + L.done);
+    p.wts = (float*)(ws + L.wts);
+    p.ext_y = L.ext_y;
+    p.wstride = L.wstride;
+    p.items = (uint32_t*)(ws + L.items);
+    p.pooled = (float*)(ws + L.pooled);
+    p.pooled_ld = L.pooled_ld;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(p.counts, 0, 16, st);
+    cudaError_t e = cudaMemsetAsync(p.counters, 0, 16, st);
     if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
-    plan_kernel<<<p.n_img, 128, 0, st>>>(p);
+    plan_kernel<<<p.n_img, kPlanThreads, 0, st>>>(p);
     int rc = check_launch(what);
     if (rc) return rc;
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(fmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
+            g_sm_count = 148;
     }
-    fmap_kernel<<<p.n, kThreads, smem, st>>>(p);
+    if (g_items_per_sm == 0 &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_items_per_sm, items_kernel, kThreads, 0) != cudaSuccess || g_items_per_sm <= 0))
+        g_items_per_sm = OODB200_FMAP_MIN_BLOCKS;
+    const int per_sm = g_items_per_sm;
+    long long max_items = (long long)p.n * L.max_ns;
+    long long grid = (long long)g_sm_count * per_sm;                 // persistent: every resident warp pulls from the queue
+    if (grid * kWarps > max_items) grid = (max_items + kWarps - 1) / kWarps;
+    items_kernel<<<(int)grid, kThreads, 0, st>>>(p);
     return check_launch(what);
 }
 
@@ -562,9 +717,9 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
 using namespace oodb200;
 
 extern "C" int64_t oodb200_fmap_workspace_bytes(int n, const int32_t* map_chw, int need_pooled) {
-    (void)map_chw; (void)need_pooled;
-    if (n <= 0) return 256;
-    return (int64_t)layout_of(n).total;
+    (void)need_pooled;
+    if (!map_chw) return -1;
+    return (int64_t)layout_of(n, map_chw).total;
 }
 
 extern "C" int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
@@ -577,7 +732,7 @@ extern "C" int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t*
     OODB200_REQUIRE(map_ptrs && boxes && img_idx && stride_idx && img_start && out, "roi_pool: null pointer");
     FmapParams p = {};
     p.map_ptrs = map_ptrs; p.boxes = boxes; p.img_idx = img_idx; p.stride_idx = stride_idx; p.img_start = img_start;
-    p.n = n; p.n_img = n_img; p.pooled = out; p.pooled_ld = out_ld;
+    p.n = n; p.n_img = n_img; p.pooled_user = out; p.pooled_user_ld = out_ld;
     return launch_fmap(p, map_chw, scale, nullptr, nullptr, workspace, workspace_bytes, stream, "roi_pool");
 }
 
@@ -602,8 +757,8 @@ extern "C" int oodb200_fmap_score_f32(const float* const* map_ptrs, const int32_
     p.map_ptrs = map_ptrs; p.boxes = boxes; p.img_idx = img_idx; p.stride_idx = stride_idx;
     p.cls = cls; p.img_start = img_start; p.compat_q1 = compat_q1; p.n = n; p.n_img = n_img;
     p.metric_mask = metric_mask; p.normalize = normalize;
-    p.cent = cent; p.cent_unit = cent_unit; p.cent_off = cent_off; p.cent_k = cent_k; p.nc = nc; p.thr = thr;
-    p.dist = dist; p.argmin = argmin; p.decision = decision; p.pooled = pooled; p.pooled_ld = pooled_ld;
+    p.cent = cent; p.cent_unit = cent_unit ? cent_unit : cent; p.cent_off = cent_off; p.cent_k = cent_k; p.nc = nc; p.thr = thr;
+    p.dist = dist; p.argmin = argmin; p.decision = decision; p.pooled_user = pooled; p.pooled_user_ld = pooled_ld;
     return launch_fmap(p, map_chw, scale, cls_used_out, out_index_out, workspace, workspace_bytes, stream, "fmap_score");
 }
 
