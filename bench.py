@@ -296,6 +296,15 @@ def run_ours(args, wl):
     else:
         n_all = float(n)
     value = n_all * args.steps / (total_ms * 1e-3)
+    if args.quick:
+        clk.__exit__()
+        if rank == 0:
+            alg, upper, _ = algorithmic_bytes(det, wl, wl.k)
+            print(json.dumps({"value": value, "ms_per_step": total_ms / args.steps, "fmap_ms": fmap_ms,
+                              "frac": alg / (fmap_ms * 1e-3) / 1e9 / _peaks()[0], "quick": True}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end: host (pinned) inputs -> decisions on the host, every step
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -370,6 +379,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C4", "C5"])
+    ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the e2e and cpu_baseline legs (tuning sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     from ood_in_object_detection_b200 import synth

@@ -35,7 +35,17 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kPlanThreads = 128;
-constexpr int kSliceChannels = 32;          // channels per work item
+#ifndef OODB200_FMAP_SLICE
+#define OODB200_FMAP_SLICE 64
+#endif
+#ifndef OODB200_FMAP_CU
+#define OODB200_FMAP_CU 8                   // channel requests in flight per warp (x T chunk slots)
+#endif
+#ifndef OODB200_FMAP_STATIC_PCT
+#define OODB200_FMAP_STATIC_PCT 75          // share of the work list handed out round-robin, the rest through the queue
+#endif
+constexpr int kSliceChannels = OODB200_FMAP_SLICE;   // channels per work item (multiple of 32)
+constexpr int kCU = OODB200_FMAP_CU;
 constexpr int kMaxSlices = 255;
 #ifndef OODB200_FMAP_MIN_BLOCKS
 #define OODB200_FMAP_MIN_BLOCKS 2
@@ -70,12 +80,11 @@ struct FmapParams {
     int* counters;              // [0] items emitted by the plan, [1] queue head
     int32_t* cls_used;          // [n]
     int32_t* out_index;         // [n]
-    int4* plan_geo;             // [n] {y0, xa, wh, nxc}; nxc == 0: empty window
-    float* plan_cnt;            // [n] max(gh*gw, 1)
     int* done;                  // [n] completed slices
     float* wts;                 // [n][wstride]: wy[ext_y] | wx padded to chunks [ext_x]
     int ext_y, wstride;
-    uint32_t* items;            // [<= n * max ns] (slice << 24) | box
+    int2* ipos;                 // [n] {index of the box's slice-0 item, item stride between its slices}
+    int4* items;                // [<= n * max ns][2] self-contained item records (see write_item)
     float* pooled;              // [n][pooled_ld] raw pooled vectors (workspace), rows in output order
     int pooled_ld;
 };
@@ -139,11 +148,11 @@ __device__ __forceinline__ float axis_weight(float start, float size, int grid, 
 }
 
 // ---------------------------------------------------------------------------------------------- plan
-// One CTA per image: quirk Q1 (ood_utils.py:2152-2154), per-box geometry + weights, and the work list.
+// plan_kernel (one CTA per image): quirk Q1 (ood_utils.py:2152-2154) and the position of every box in the work list.
 __global__ void __launch_bounds__(kPlanThreads) plan_kernel(const FmapParams p) {
     const int img = blockIdx.x;
     const int b0 = p.img_start[img], m = p.img_start[img + 1] - b0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     __shared__ int s_cnt[4], s_item0[3];
     if (tid < 4) s_cnt[tid] = 0;
     __syncthreads();
@@ -177,10 +186,8 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(const FmapParams p) 
         }
         p.cls_used[b0 + b] = cls_u;
         p.out_index[b0 + b] = out;
-        if (ok) {
-            const int nb = s_cnt[s];
-            for (int sl = 0; sl < p.ns[s]; ++sl)      // slice-major inside (image, stride)
-                p.items[s_item0[s] + sl * nb + j] = ((uint32_t)sl << 24) | (uint32_t)(b0 + b);
+        if (ok) {                                     // slice-major inside (image, stride): item(sl) = pos0 + sl * nb
+            p.ipos[b0 + b] = make_int2(s_item0[s] + j, s_cnt[s]);
         } else if (p.cent) {                          // never pooled by the reference either: answered here
             for (int k = 0; k < OODB200_N_METRICS; ++k)
                 if (p.metric_mask >> k & 1) {
@@ -191,49 +198,60 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(const FmapParams p) 
                 }
         }
     }
-    // ---- ROI geometry (predict.py:64-70 -> roi_align, aligned=False), one warp per box ----
-    for (int b = warp; b < m; b += kPlanThreads / 32) {
-        const int box = b0 + b;
-        const int s = p.stride_idx[box];
-        if (s < 0 || s > 2) continue;
-        const int H = p.H[s], W = p.W[s];
-        const float sc = p.scale[s];
-        const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)box);
-        const float sw = __fmul_rn(bx.x, sc), sh = __fmul_rn(bx.y, sc);
-        const float ew = __fmul_rn(bx.z, sc), eh = __fmul_rn(bx.w, sc);
-        const float rw = fmaxf(__fsub_rn(ew, sw), 1.0f), rh = fmaxf(__fsub_rn(eh, sh), 1.0f);
-        const int gw = (int)ceilf(rw), gh = (int)ceilf(rh);
-        int ylo = INT_MAX, yhi = -1, xlo = INT_MAX, xhi = -1;
-        for (int k = lane; k < gh; k += 32) {
-            const AxisSample a = axis_sample(sh, rh, gh, H, k);
-            if (a.valid) { ylo = min(ylo, a.low); yhi = max(yhi, a.high); }
+}
+
+// geo_kernel (one warp per box): ROI geometry (predict.py:64-70 -> roi_align, aligned=False), separable weights, and the
+// box's self-contained item records.
+__global__ void __launch_bounds__(kThreads) geo_kernel(const FmapParams p) {
+    const int lane = threadIdx.x & 31;
+    const int box = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (box >= p.n) return;
+    const int s = p.stride_idx[box];
+    if (s < 0 || s > 2) return;
+    const int H = p.H[s], W = p.W[s];
+    const float sc = p.scale[s];
+    const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)box);
+    const float sw = __fmul_rn(bx.x, sc), sh = __fmul_rn(bx.y, sc);
+    const float ew = __fmul_rn(bx.z, sc), eh = __fmul_rn(bx.w, sc);
+    const float rw = fmaxf(__fsub_rn(ew, sw), 1.0f), rh = fmaxf(__fsub_rn(eh, sh), 1.0f);
+    const int gw = (int)ceilf(rw), gh = (int)ceilf(rh);
+    int ylo = INT_MAX, yhi = -1, xlo = INT_MAX, xhi = -1;
+    for (int k = lane; k < gh; k += 32) {
+        const AxisSample a = axis_sample(sh, rh, gh, H, k);
+        if (a.valid) { ylo = min(ylo, a.low); yhi = max(yhi, a.high); }
+    }
+    for (int k = lane; k < gw; k += 32) {
+        const AxisSample a = axis_sample(sw, rw, gw, W, k);
+        if (a.valid) { xlo = min(xlo, a.low); xhi = max(xhi, a.high); }
+    }
+    ylo = __reduce_min_sync(kFull, ylo); yhi = __reduce_max_sync(kFull, yhi);
+    xlo = __reduce_min_sync(kFull, xlo); xhi = __reduce_max_sync(kFull, xhi);
+    const bool empty = yhi < 0 || xhi < 0;
+    int wh = 0, nxc = 0, xa = 0;
+    if (!empty) {
+        wh = yhi - ylo + 1;
+        const int ww = xhi - xlo + 1;
+        xa = xlo & ~3;
+        nxc = ((xlo + ww + 3) >> 2) - (xa >> 2);
+        float* __restrict__ wy = p.wts + (size_t)box * p.wstride;
+        float* __restrict__ wx = wy + p.ext_y;
+        for (int r = lane; r < wh; r += 32) wy[r] = axis_weight(sh, rh, gh, H, ylo + r);
+        for (int i = lane; i < 4 * nxc; i += 32) {
+            const int x = xa + i;
+            wx[i] = (x >= xlo && x <= xhi) ? axis_weight(sw, rw, gw, W, x) : 0.f;
         }
-        for (int k = lane; k < gw; k += 32) {
-            const AxisSample a = axis_sample(sw, rw, gw, W, k);
-            if (a.valid) { xlo = min(xlo, a.low); xhi = max(xhi, a.high); }
-        }
-        ylo = __reduce_min_sync(kFull, ylo); yhi = __reduce_max_sync(kFull, yhi);
-        xlo = __reduce_min_sync(kFull, xlo); xhi = __reduce_max_sync(kFull, xhi);
-        const bool empty = yhi < 0 || xhi < 0;
-        int wh = 0, nxc = 0, xa = 0;
-        if (!empty) {
-            wh = yhi - ylo + 1;
-            const int ww = xhi - xlo + 1;
-            xa = xlo & ~3;
-            nxc = ((xlo + ww + 3) >> 2) - (xa >> 2);
-            float* __restrict__ wy = p.wts + (size_t)box * p.wstride;
-            float* __restrict__ wx = wy + p.ext_y;
-            for (int r = lane; r < wh; r += 32) wy[r] = axis_weight(sh, rh, gh, H, ylo + r);
-            for (int i = lane; i < 4 * nxc; i += 32) {
-                const int x = xa + i;
-                wx[i] = (x >= xlo && x <= xhi) ? axis_weight(sw, rw, gw, W, x) : 0.f;
-            }
-        }
-        if (lane == 0) {
-            p.plan_geo[box] = make_int4(empty ? 0 : ylo, xa, wh, nxc);
-            p.plan_cnt[box] = (float)max(gh * gw, 1);
-            p.done[box] = 0;
-        }
+    } else {
+        ylo = 0;
+    }
+    if (lane == 0) p.done[box] = 0;
+    const int2 ip = p.ipos[box];
+    const unsigned long long img = (unsigned long long)p.map_ptrs[p.img_idx[box] * 3 + s];
+    const int out = p.out_index[box];
+    const float count = (float)max(gh * gw, 1);
+    for (int sl = lane; sl < p.ns[s]; sl += 32) {     // record: everything an item warp needs except the weights
+        int4* rec = p.items + 2 * (size_t)(ip.x + sl * ip.y);
+        rec[0] = make_int4((int)(((uint32_t)sl << 24) | (uint32_t)box), ylo | (xa << 16), wh | (nxc << 16), out);
+        rec[1] = make_int4((int)(img & 0xffffffffu), (int)(img >> 32), __float_as_int(count), s);
     }
 }
 
@@ -376,12 +394,13 @@ __device__ __noinline__ void pool_scalar(const float* __restrict__ img, int HW, 
 __device__ __forceinline__ void pool_dispatch(const float* img, int C, int HW, int W, int4 geo, const float* wy,
                                               const float* wx, float count, int c_lo, int c_hi, float* out0, float* out1) {
     const int nch = geo.z * geo.w;
+    constexpr int CU1 = kCU, CU2 = kCU >= 8 ? 8 : kCU, CU4 = kCU >= 8 ? 4 : kCU / 2;
     if (nch <= 4) pool_slice<2, 1, 4>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
     else if (nch <= 8) pool_slice<3, 1, 8>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
-    else if (nch <= 16) pool_slice<4, 1, 8>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
-    else if (nch <= 32) pool_slice<5, 1, 8>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
-    else if (nch <= 64) pool_slice<5, 2, 8>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
-    else if (nch <= 128) pool_slice<5, 4, 4>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+    else if (nch <= 16) pool_slice<4, 1, CU1>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+    else if (nch <= 32) pool_slice<5, 1, CU1>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+    else if (nch <= 64) pool_slice<5, 2, CU2>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+    else if (nch <= 128) pool_slice<5, 4, CU4>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
     else if (nch <= 256) pool_slice<5, 8, 1>(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
     else {
         // very large windows (> 1024 elements per channel): tiles of <= 256 chunks, accumulated in the output row
@@ -463,42 +482,65 @@ __device__ __forceinline__ void finalize_vec(const FmapParams& p, int box) {
     Best b = {{FLT_MAX, FLT_MAX, FLT_MAX}, {-1, -1, -1}};
     if (K > 0) {
         const int64_t off = p.cent_off[s * p.nc + cls];
-        for (int k = 0; k < K; ++k) {
-            const float* __restrict__ ck = p.cent + off + (int64_t)k * C;
-            const float* __restrict__ cu = p.cent_unit + off + (int64_t)k * C;
-            float a1 = 0.f, a2 = 0.f, ac = 0.f;
+        constexpr int U = NJ <= 4 ? 2 : 1;            // centroid rows in flight (L2 latency, not bandwidth, bounds this loop)
+        for (int k = 0; k < K; k += U) {
+            float a1[U], a2[U], ac[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) a1[u] = a2[u] = ac[u] = 0.f;
             if (want_l1 || want_l2) {
-                float4 c4[NJ];
+                float4 c4[U][NJ];
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    const int d = lane * 4 + 128 * j;
-                    c4[j] = d < C ? __ldg(reinterpret_cast<const float4*>(ck + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < U; ++u) {
+                    const float* __restrict__ ck = p.cent + off + (int64_t)min(k + u, K - 1) * C;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int d = lane * 4 + 128 * j;
+                        c4[u][j] = d < C ? __ldg(reinterpret_cast<const float4*>(ck + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    const float d0 = x[j].x - c4[j].x, d1 = x[j].y - c4[j].y, d2 = x[j].z - c4[j].z, d3 = x[j].w - c4[j].w;
-                    a1 += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
-                    a2 = fmaf(d0, d0, a2); a2 = fmaf(d1, d1, a2); a2 = fmaf(d2, d2, a2); a2 = fmaf(d3, d3, a2);
-                }
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const float d0 = x[j].x - c4[u][j].x, d1 = x[j].y - c4[u][j].y, d2 = x[j].z - c4[u][j].z, d3 = x[j].w - c4[u][j].w;
+                        a1[u] += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+                        a2[u] = fmaf(d0, d0, a2[u]); a2[u] = fmaf(d1, d1, a2[u]); a2[u] = fmaf(d2, d2, a2[u]); a2[u] = fmaf(d3, d3, a2[u]);
+                    }
             }
             if (want_cos) {
-                float4 c4[NJ];
+                float4 c4[U][NJ];
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    const int d = lane * 4 + 128 * j;
-                    c4[j] = d < C ? __ldg(reinterpret_cast<const float4*>(cu + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < U; ++u) {
+                    const float* __restrict__ cu = p.cent_unit + off + (int64_t)min(k + u, K - 1) * C;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int d = lane * 4 + 128 * j;
+                        c4[u][j] = d < C ? __ldg(reinterpret_cast<const float4*>(cu + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    ac = fmaf(x[j].x, c4[j].x, ac); ac = fmaf(x[j].y, c4[j].y, ac);
-                    ac = fmaf(x[j].z, c4[j].z, ac); ac = fmaf(x[j].w, c4[j].w, ac);
-                }
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        ac[u] = fmaf(x[j].x, c4[u][j].x, ac[u]); ac[u] = fmaf(x[j].y, c4[u][j].y, ac[u]);
+                        ac[u] = fmaf(x[j].z, c4[u][j].z, ac[u]); ac[u] = fmaf(x[j].w, c4[u][j].w, ac[u]);
+                    }
             }
-            if (want_l1) { a1 = warp_sum(a1); if (a1 < b.d[0]) { b.d[0] = a1; b.a[0] = k; } }
-            if (want_l2) { a2 = sqrtf(fmaxf(warp_sum(a2), 0.f)); if (a2 < b.d[1]) { b.d[1] = a2; b.a[1] = k; } }
-            if (want_cos) {                           // X / ||X|| applied to the sum (same value to float32 rounding)
-                ac = fminf(fmaxf(1.0f - __fdiv_rn(warp_sum(ac), n2v), 0.f), 2.f);
-                if (ac < b.d[2]) { b.d[2] = ac; b.a[2] = k; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (want_l1) a1[u] = warp_sum(a1[u]);
+                if (want_l2) a2[u] = warp_sum(a2[u]);
+                if (want_cos) ac[u] = warp_sum(ac[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (k + u >= K) break;
+                if (want_l1 && a1[u] < b.d[0]) { b.d[0] = a1[u]; b.a[0] = k + u; }
+                if (want_l2) { const float v = sqrtf(fmaxf(a2[u], 0.f)); if (v < b.d[1]) { b.d[1] = v; b.a[1] = k + u; } }
+                if (want_cos) {                       // X / ||X|| applied to the sum (same value to float32 rounding)
+                    const float v = fminf(fmaxf(1.0f - __fdiv_rn(ac[u], n2v), 0.f), 2.f);
+                    if (v < b.d[2]) { b.d[2] = v; b.a[2] = k + u; }
+                }
             }
         }
     }
@@ -565,66 +607,82 @@ __device__ __forceinline__ void finalize(const FmapParams& p, int box) {
         write_result(p, s, cls, cls_ok, K, out, b);
         return;
     }
-    switch ((C + 127) / 128) {
-        case 1: finalize_vec<1>(p, box); break;
-        case 2: finalize_vec<2>(p, box); break;
-        case 3: finalize_vec<3>(p, box); break;
-        case 4: finalize_vec<4>(p, box); break;
-        case 5: finalize_vec<5>(p, box); break;
-        case 6: finalize_vec<6>(p, box); break;
-        case 7: finalize_vec<7>(p, box); break;
-        default: finalize_vec<8>(p, box); break;
-    }
+    if (C <= 256) finalize_vec<2>(p, box);             // few instantiations: the kernel must stay inside the instruction cache
+    else if (C <= 512) finalize_vec<4>(p, box);
+    else finalize_vec<8>(p, box);
 }
 
 // ---------------------------------------------------------------------------------------------- main kernel
+// release-add on the box's completion counter: orders the pooled-row stores of this warp (made visible to lane 0 by the
+// preceding __syncwarp) before the increment, without the L1 invalidation a full __threadfence() carries.
+__device__ __forceinline__ int atomic_add_release(int* addr, int v) {
+    int old;
+    asm volatile("atom.release.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
+    return old;
+}
+
 __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kernel(const FmapParams p) {
     const int lane = threadIdx.x & 31;
     const int n_items = p.counters[0];
-    auto fetch = [&]() {
-        int i = 0;
-        if (lane == 0) i = atomicAdd(&p.counters[1], 1);
-        return __shfl_sync(kFull, i, 0);
+    // Scheduling: the first kStaticPct % of the work list is handed out round-robin (no atomics: same-address atomics
+    // serialise in L2 and their latency under contention is of the order of an item), the tail through an atomic queue
+    // so that the last items balance.  The next item's index and record are requested while the current one runs.
+    const int warp_g = blockIdx.x * kWarps + (threadIdx.x >> 5), n_warps = gridDim.x * kWarps;
+    const int n_static = (int)((long long)n_items * OODB200_FMAP_STATIC_PCT / 100);
+    int q_reg = 0;                                     // lane 0: result of the most recent queue fetch
+    bool q_pending = false;
+    auto next_index = [&](int cur) {                   // warp-uniform
+        int nx = cur + n_warps;
+        if (cur < n_static && nx < n_static) return nx;
+        if (!q_pending) {                              // first dynamic fetch for this warp: blocking
+            if (lane == 0) q_reg = atomicAdd(&p.counters[1], 1);
+        }
+        nx = n_static + __shfl_sync(kFull, q_reg, 0);
+        if (lane == 0) q_reg = atomicAdd(&p.counters[1], 1);       // the one after, in flight during the next item
+        q_pending = true;
+        return nx;
     };
-    int it = fetch();
+    int it = warp_g < n_static ? warp_g : n_items;
+    if (it >= n_items) it = next_index(n_static);      // more warps than static items: go to the queue
+    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;
+    if (it < n_items) { r0 = __ldg(p.items + 2 * (size_t)it); r1 = __ldg(p.items + 2 * (size_t)it + 1); }
     while (it < n_items) {
-        const uint32_t word = p.items[it];
-        const int nxt = fetch();                       // next item's index travels under this item's loads
-        const int box = (int)(word & 0xFFFFFFu), sl = (int)(word >> 24);
-        const int s = p.stride_idx[box];
+        const int nit = next_index(it);
+        int4 n0 = make_int4(0, 0, 0, 0), n1 = n0;
+        if (nit < n_items) { n0 = __ldg(p.items + 2 * (size_t)nit); n1 = __ldg(p.items + 2 * (size_t)nit + 1); }
+
+        const int box = r0.x & 0xFFFFFF, sl = (int)((uint32_t)r0.x >> 24);
+        const int s = r1.w;
         const int C = p.C[s], W = p.W[s], HW = p.H[s] * W;
-        const int4 geo = p.plan_geo[box];
-        const int out = p.out_index[box];
+        const int4 geo = make_int4(r0.y & 0xFFFF, (int)((uint32_t)r0.y >> 16), r0.z & 0xFFFF, (int)((uint32_t)r0.z >> 16));
+        const int out = r0.w;
         const int c_lo = sl * kSliceChannels, c_hi = min(C, c_lo + kSliceChannels);
         float* __restrict__ out0 = p.pooled + (size_t)out * p.pooled_ld;
         float* __restrict__ out1 = p.pooled_user ? p.pooled_user + (size_t)out * p.pooled_user_ld : nullptr;
         if (geo.w == 0) {                              // no sample inside the map (Q5): all-zero vector
             for (int c = c_lo + lane; c < c_hi; c += 32) { out0[c] = 0.f; if (out1) out1[c] = 0.f; }
         } else {
-            const float* __restrict__ img = p.map_ptrs[p.img_idx[box] * 3 + s];
+            const float* __restrict__ img = reinterpret_cast<const float*>(((unsigned long long)(uint32_t)r1.y << 32) | (uint32_t)r1.x);
             const float* __restrict__ wy = p.wts + (size_t)box * p.wstride;
             const float* __restrict__ wx = wy + p.ext_y;
-            const float count = p.plan_cnt[box];
+            const float count = __int_as_float(r1.z);
             const bool vec = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (HW % 4 == 0);
             if (vec) pool_dispatch(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
             else pool_scalar(img, HW, W, geo.x, geo.y, geo.z, geo.w, wy, wx, count, c_lo, c_hi, out0, out1);
         }
         if (p.cent) {                                  // last slice of the box -> distance phase
-            __threadfence();
+            __syncwarp();
             int last = 0;
-            if (lane == 0) last = (atomicAdd(&p.done[box], 1) == p.ns[s] - 1);
+            if (lane == 0) last = (atomic_add_release(&p.done[box], 1) == p.ns[s] - 1);
             last = __shfl_sync(kFull, last, 0);
-            if (last) {
-                __threadfence();
-                finalize(p, box);
-            }
+            if (last) finalize(p, box);                // reads the completed row with ld.global.cg (L2), see finalize_*
         }
-        it = nxt;
+        r0 = n0; r1 = n1; it = nit;
     }
 }
 
 struct WorkspaceLayout {
-    size_t counters, cls_used, out_index, plan_geo, plan_cnt, done, wts, items, pooled, total;
+    size_t counters, cls_used, out_index, ipos, done, wts, items, pooled, total;
     int ext_y, wstride, pooled_ld, max_ns;
 };
 
@@ -646,11 +704,10 @@ static WorkspaceLayout layout_of(int n, const int32_t* map_chw) {
     L.counters = o; o = up(o + 16);
     L.cls_used = o; o = up(o + 4 * nn);
     L.out_index = o; o = up(o + 4 * nn);
-    L.plan_geo = o; o = up(o + 16 * nn);
-    L.plan_cnt = o; o = up(o + 4 * nn);
+    L.ipos = o; o = up(o + 8 * nn);
     L.done = o; o = up(o + 4 * nn);
     L.wts = o; o = up(o + 4 * nn * L.wstride);
-    L.items = o; o = up(o + 4 * nn * L.max_ns);
+    L.items = o; o = up(o + 32 * nn * L.max_ns);
     L.pooled = o; o = up(o + 4 * nn * L.pooled_ld);
     L.total = o;
     return L;
@@ -680,13 +737,12 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     p.counters = (int*)(ws + L.counters);
     p.cls_used = cls_used_out ? cls_used_out : (int32_t*)(ws + L.cls_used);
     p.out_index = out_index_out ? out_index_out : (int32_t*)(ws + L.out_index);
-    p.plan_geo = (int4*)(ws + L.plan_geo);
-    p.plan_cnt = (float*)(ws + L.plan_cnt);
+    p.ipos = (int2*)(ws + L.ipos);
     p.done = (int*)(ws + L.done);
     p.wts = (float*)(ws + L.wts);
     p.ext_y = L.ext_y;
     p.wstride = L.wstride;
-    p.items = (uint32_t*)(ws + L.items);
+    p.items = (int4*)(ws + L.items);
     p.pooled = (float*)(ws + L.pooled);
     p.pooled_ld = L.pooled_ld;
     cudaStream_t st = (cudaStream_t)stream;
@@ -694,6 +750,9 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
     plan_kernel<<<p.n_img, kPlanThreads, 0, st>>>(p);
     int rc = check_launch(what);
+    if (rc) return rc;
+    geo_kernel<<<(p.n + kWarps - 1) / kWarps, kThreads, 0, st>>>(p);
+    rc = check_launch(what);
     if (rc) return rc;
     if (g_sm_count == 0) {
         int dev = 0;

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Build tuning variants of liboodb200.so (macro sweeps) into ood_in_object_detection_b200/variants/.
+# usage: scripts/build_variants.sh name1:"-DX=1 -DY=2" name2:"..."
+set -e
+cd "$(dirname "$0")/.."
+D=ood_in_object_detection_b200; mkdir -p $D/variants
+for spec in "$@"; do
+  name="${spec%%:*}"; flags="${spec#*:}"
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -O3 --shared -cudart shared $flags \
+    $D/csrc/fmap_score.cu $D/csrc/logit_score.cu $D/csrc/fit_kernels.cu $D/csrc/kmeans.cu -o $D/variants/$name.so &
+done
+wait
+ls -la $D/variants
