@@ -4,26 +4,26 @@
 // with output 1x1, adaptive sampling grid, aligned=False) and the per-box loop of
 // /root/reference/ood_utils.py:2038-2180 (+ :2404-2409 normalize, :2422-2430 pairwise distance + min).
 //
-// Two launches per batch (plus a 16-byte memset of the counters):
-//  plan_kernel   one CTA per image.  (a) quirk-Q1 class / output slot of every box.  (b) one warp per box: ROI
-//                geometry, window, and the separable RoIAlign weights.  With a 1x1 output bin
+// Launches per batch: memset(16 B) -> plan_kernel -> geo_kernel -> items_kernel -> score_kernel.
+//  plan_kernel   one warp per image: quirk-Q1 class / output slot of every box (ballot prefix ranks) and the position of
+//                every box's work items in the item list.
+//  geo_kernel    one warp per box: ROI geometry and the separable RoIAlign weights.  With a 1x1 output bin
 //                    sum_{iy,ix} bilinear(y_iy, x_ix) = sum_r sum_c wy[r] wx[c] v[r,c]
 //                because both the bilinear weights and the "sample outside [-1,H]x[-1,W] contributes 0" mask are
 //                products of a y-term and an x-term.  Sample coordinates use the float32 operation order of the
 //                reference kernel (no FMA contraction).  Every window element is then read ONCE, not ~4 times.
-//                (c) the work list: a box is cut into channel slices of `cs` channels (item = box x slice,
-//                a few KB of window data), items of one (image, stride) are laid out slice-major so that the
-//                overlapping windows of one image are gathered at the same time (L1 / L2 hits).
-//  items_kernel  persistent grid, ONE WARP per work item pulled from an atomic queue: no block barriers, no tail of
-//                big boxes.  A window is addressed in 16-byte chunks (NCHW rows are 16-byte aligned for the usual map
-//                widths): lane = chunk, one LDG.128 per lane per channel, 8 channels in flight, 4 FMAs per load
-//                against the lane's fixed weight vector, and ONE transposing butterfly per 8 channels instead of 8
-//                warp reductions.  Small windows put 2/4/8 channels into one 32-lane request.  The warp that completes
-//                the last slice of a box (per-box counter) runs the distance phase: L2 norm, then L1 / L2 / cosine
-//                against the K centroids of (class, stride) in one sweep over the L2-resident table (128-bit loads,
-//                vector in registers), first-minimum arg-min and the float64 threshold compare.
-// Results do not depend on the order in which items are executed: each pooled element is produced by exactly one warp
-// in a fixed order, and the distance phase reads a completed vector.
+//                Emits self-contained item records: item = (box, slice of kSliceChannels channels).
+//  items_kernel  persistent grid, ONE WARP per work item (round-robin, atomic queue for the tail): no block barriers,
+//                no tail of big boxes.  A window is addressed in 16-byte chunks (NCHW rows are 16-byte aligned for the
+//                usual map widths): lane = chunk, one LDG.128 per lane per channel, 8 channels in flight, 4 FMAs per load
+//                against the lane's fixed weight vector, and ONE transposing butterfly per 8 channels instead of 8 warp
+//                reductions.  Small windows put 2/4/8 channels into one 32-lane request.
+//  score_kernel  one warp per box: L2 norm, then L1 / L2 / cosine against the K centroids of (class, stride) in one
+//                sweep over the L2-resident table (128-bit loads, vector in registers, several rows in flight),
+//                first-minimum arg-min and the float64 threshold compare.
+// Every pooled element is produced by exactly one warp in a fixed order: results do not depend on scheduling.
+// What bounds the gather on B200 (scripts/micro/*.cu): an L2 miss always moves a whole 128-byte line
+// from HBM while an NCHW window row is 8..52 bytes, so the HBM traffic of this kernel is the set of LINES the windows touch.
 #include "common.cuh"
 
 #include <float.h>
@@ -34,7 +34,10 @@ namespace oodb200 {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kPlanThreads = 128;
+constexpr int kMaxSlices = 255;
+#ifndef OODB200_FMAP_MIN_BLOCKS
+#define OODB200_FMAP_MIN_BLOCKS 2
+#endif
 #ifndef OODB200_FMAP_SLICE
 #define OODB200_FMAP_SLICE 64
 #endif
@@ -46,10 +49,6 @@ constexpr int kPlanThreads = 128;
 #endif
 constexpr int kSliceChannels = OODB200_FMAP_SLICE;   // channels per work item (multiple of 32)
 constexpr int kCU = OODB200_FMAP_CU;
-constexpr int kMaxSlices = 255;
-#ifndef OODB200_FMAP_MIN_BLOCKS
-#define OODB200_FMAP_MIN_BLOCKS 2
-#endif
 
 struct FmapParams {
     const float* const* map_ptrs;
@@ -77,14 +76,13 @@ struct FmapParams {
     float* pooled_user;         // optional caller buffer [n, pooled_user_ld], rows in output order
     int pooled_user_ld;
     // workspace
-    int* counters;              // [0] items emitted by the plan, [1] queue head
+    int* counters;              // [0] items emitted by the plan, [1] item queue head
     int32_t* cls_used;          // [n]
     int32_t* out_index;         // [n]
-    int* done;                  // [n] completed slices
+    int2* ipos;                 // [n] {index of the box's slice-0 item, item stride between its slices}
     float* wts;                 // [n][wstride]: wy[ext_y] | wx padded to chunks [ext_x]
     int ext_y, wstride;
-    int2* ipos;                 // [n] {index of the box's slice-0 item, item stride between its slices}
-    int4* items;                // [<= n * max ns][2] self-contained item records (see write_item)
+    int4* items;                // [<= n * max ns][2] self-contained item records
     float* pooled;              // [n][pooled_ld] raw pooled vectors (workspace), rows in output order
     int pooled_ld;
 };
@@ -148,37 +146,45 @@ __device__ __forceinline__ float axis_weight(float start, float size, int grid, 
 }
 
 // ---------------------------------------------------------------------------------------------- plan
-// plan_kernel (one CTA per image): quirk Q1 (ood_utils.py:2152-2154) and the position of every box in the work list.
-__global__ void __launch_bounds__(kPlanThreads) plan_kernel(const FmapParams p) {
-    const int img = blockIdx.x;
+// plan_kernel (one warp per image): quirk Q1 (ood_utils.py:2152-2154: the class of the box with the same IN-STRIDE index,
+// stride-major output) and the position of every box in the work list.  Ranks come from ballot prefixes over chunks of
+// 32 boxes; category 3 = "stride outside {0,1,2}" (never pooled by the reference either: answered here).
+__global__ void __launch_bounds__(32) plan_kernel(const FmapParams p) {
+    const int img = blockIdx.x, lane = threadIdx.x;
     const int b0 = p.img_start[img], m = p.img_start[img + 1] - b0;
-    const int tid = threadIdx.x;
-    __shared__ int s_cnt[4], s_item0[3];
-    if (tid < 4) s_cnt[tid] = 0;
-    __syncthreads();
-    for (int b = tid; b < m; b += kPlanThreads) {
-        const int s = p.stride_idx[b0 + b];
-        atomicAdd(&s_cnt[(s >= 0 && s <= 2) ? s : 3], 1);
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt[4] = {0, 0, 0, 0};
+    for (int c0 = 0; c0 < m; c0 += 32) {
+        const int b = c0 + lane;
+        const int s = b < m ? p.stride_idx[b0 + b] : -2;
+        const int cat = b < m ? ((s >= 0 && s <= 2) ? s : 3) : 4;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) cnt[t] += __popc(__ballot_sync(kFull, cat == t));
     }
-    __syncthreads();
-    if (tid == 0) {                                   // reserve this image's range of the work list (heaviest stride first)
-        const int tot = s_cnt[2] * p.ns[2] + s_cnt[1] * p.ns[1] + s_cnt[0] * p.ns[0];
-        const int base = tot ? atomicAdd(&p.counters[0], tot) : 0;
-        s_item0[2] = base;
-        s_item0[1] = base + s_cnt[2] * p.ns[2];
-        s_item0[0] = s_item0[1] + s_cnt[1] * p.ns[1];
-    }
-    __syncthreads();
-    for (int b = tid; b < m; b += kPlanThreads) {
-        const int s = p.stride_idx[b0 + b];
-        const bool ok = s >= 0 && s <= 2;
-        int j = 0;                                    // rank among earlier boxes of the same kind (m <= 300)
-        for (int e = 0; e < b; ++e) {
-            const int se = p.stride_idx[b0 + e];
-            j += ok ? (se == s) : !(se >= 0 && se <= 2);
+    // this image's range of the work list, heaviest stride (most channels) first; items of one stride are slice-major
+    const int tot = cnt[2] * p.ns[2] + cnt[1] * p.ns[1] + cnt[0] * p.ns[0];
+    int base = 0;
+    if (lane == 0 && tot) base = atomicAdd(&p.counters[0], tot);
+    base = __shfl_sync(kFull, base, 0);
+    int item0[3];
+    item0[2] = base;
+    item0[1] = base + cnt[2] * p.ns[2];
+    item0[0] = item0[1] + cnt[1] * p.ns[1];
+    int run[4] = {0, 0, 0, 0};
+    for (int c0 = 0; c0 < m; c0 += 32) {
+        const int b = c0 + lane;
+        const int s = b < m ? p.stride_idx[b0 + b] : -2;
+        const int cat = b < m ? ((s >= 0 && s <= 2) ? s : 3) : 4;
+        int j = 0, before = 0, nb = 0, it0 = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const unsigned mk = __ballot_sync(kFull, cat == t);
+            if (cat == t) { j = run[t] + __popc(mk & lt); nb = cnt[t]; if (t < 3) it0 = item0[t]; }
+            if (t < cat) before += cnt[t];
+            run[t] += __popc(mk);
         }
-        int before = 0;
-        for (int t = 0; t < (ok ? s : 3); ++t) before += s_cnt[t];
+        if (b >= m) continue;
+        const bool ok = cat < 3;
         int cls_u = p.cls ? p.cls[b0 + b] : 0, out = b0 + b;
         if (p.compat_q1) {
             cls_u = ok ? p.cls[b0 + j] : -1;
@@ -186,9 +192,9 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(const FmapParams p) 
         }
         p.cls_used[b0 + b] = cls_u;
         p.out_index[b0 + b] = out;
-        if (ok) {                                     // slice-major inside (image, stride): item(sl) = pos0 + sl * nb
-            p.ipos[b0 + b] = make_int2(s_item0[s] + j, s_cnt[s]);
-        } else if (p.cent) {                          // never pooled by the reference either: answered here
+        if (ok) {
+            p.ipos[b0 + b] = make_int2(it0 + j, nb);  // item(sl) = pos0 + sl * nb
+        } else if (p.cent) {
             for (int k = 0; k < OODB200_N_METRICS; ++k)
                 if (p.metric_mask >> k & 1) {
                     const size_t o = (size_t)k * p.n + out;
@@ -200,17 +206,22 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(const FmapParams p) 
     }
 }
 
-// geo_kernel (one warp per box): ROI geometry (predict.py:64-70 -> roi_align, aligned=False), separable weights, and the
-// box's self-contained item records.
+// geo_kernel (one warp per box): ROI geometry (predict.py:64-70 -> roi_align, aligned=False), separable weights, and
+// the box's self-contained item records.
 __global__ void __launch_bounds__(kThreads) geo_kernel(const FmapParams p) {
     const int lane = threadIdx.x & 31;
     const int box = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (box >= p.n) return;
+    // independent loads first: one round trip instead of a chain
     const int s = p.stride_idx[box];
+    const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)box);
+    const int2 ip = p.ipos[box];
+    const int out = p.out_index[box];
+    const int im = p.img_idx[box];
     if (s < 0 || s > 2) return;
+    const unsigned long long img = (unsigned long long)p.map_ptrs[im * 3 + s];
     const int H = p.H[s], W = p.W[s];
     const float sc = p.scale[s];
-    const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)box);
     const float sw = __fmul_rn(bx.x, sc), sh = __fmul_rn(bx.y, sc);
     const float ew = __fmul_rn(bx.z, sc), eh = __fmul_rn(bx.w, sc);
     const float rw = fmaxf(__fsub_rn(ew, sw), 1.0f), rh = fmaxf(__fsub_rn(eh, sh), 1.0f);
@@ -243,10 +254,6 @@ __global__ void __launch_bounds__(kThreads) geo_kernel(const FmapParams p) {
     } else {
         ylo = 0;
     }
-    if (lane == 0) p.done[box] = 0;
-    const int2 ip = p.ipos[box];
-    const unsigned long long img = (unsigned long long)p.map_ptrs[p.img_idx[box] * 3 + s];
-    const int out = p.out_index[box];
     const float count = (float)max(gh * gw, 1);
     for (int sl = lane; sl < p.ns[s]; sl += 32) {     // record: everything an item warp needs except the weights
         int4* rec = p.items + 2 * (size_t)(ip.x + sl * ip.y);
@@ -482,7 +489,7 @@ __device__ __forceinline__ void finalize_vec(const FmapParams& p, int box) {
     Best b = {{FLT_MAX, FLT_MAX, FLT_MAX}, {-1, -1, -1}};
     if (K > 0) {
         const int64_t off = p.cent_off[s * p.nc + cls];
-        constexpr int U = NJ <= 4 ? 2 : 1;            // centroid rows in flight (L2 latency, not bandwidth, bounds this loop)
+        constexpr int U = NJ <= 2 ? 4 : (NJ <= 4 ? 2 : 1);   // centroid rows in flight (L2 latency bounds this loop)
         for (int k = 0; k < K; k += U) {
             float a1[U], a2[U], ac[U];
 #pragma unroll
@@ -612,15 +619,7 @@ __device__ __forceinline__ void finalize(const FmapParams& p, int box) {
     else finalize_vec<8>(p, box);
 }
 
-// ---------------------------------------------------------------------------------------------- main kernel
-// release-add on the box's completion counter: orders the pooled-row stores of this warp (made visible to lane 0 by the
-// preceding __syncwarp) before the increment, without the L1 invalidation a full __threadfence() carries.
-__device__ __forceinline__ int atomic_add_release(int* addr, int v) {
-    int old;
-    asm volatile("atom.release.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
-    return old;
-}
-
+// ---------------------------------------------------------------------------------------------- gather kernel
 __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kernel(const FmapParams p) {
     const int lane = threadIdx.x & 31;
     const int n_items = p.counters[0];
@@ -643,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kerne
         return nx;
     };
     int it = warp_g < n_static ? warp_g : n_items;
-    if (it >= n_items) it = next_index(n_static);      // more warps than static items: go to the queue
+    if (it >= n_items && n_items > 0) it = next_index(n_static);   // more warps than static items: go to the queue
     int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;
     if (it < n_items) { r0 = __ldg(p.items + 2 * (size_t)it); r1 = __ldg(p.items + 2 * (size_t)it + 1); }
     while (it < n_items) {
@@ -670,19 +669,21 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kerne
             if (vec) pool_dispatch(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
             else pool_scalar(img, HW, W, geo.x, geo.y, geo.z, geo.w, wy, wx, count, c_lo, c_hi, out0, out1);
         }
-        if (p.cent) {                                  // last slice of the box -> distance phase
-            __syncwarp();
-            int last = 0;
-            if (lane == 0) last = (atomic_add_release(&p.done[box], 1) == p.ns[s] - 1);
-            last = __shfl_sync(kFull, last, 0);
-            if (last) finalize(p, box);                // reads the completed row with ld.global.cg (L2), see finalize_*
-        }
         r0 = n0; r1 = n1; it = nit;
     }
 }
 
+// ---------------------------------------------------------------------------------------------- score kernel
+__global__ void __launch_bounds__(kThreads) score_kernel(const FmapParams p) {
+    const int box = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (box >= p.n) return;
+    const int s = p.stride_idx[box];
+    if (s < 0 || s > 2) return;                        // answered by the plan kernel
+    finalize(p, box);
+}
+
 struct WorkspaceLayout {
-    size_t counters, cls_used, out_index, ipos, done, wts, items, pooled, total;
+    size_t counters, cls_used, out_index, ipos, wts, items, pooled, total;
     int ext_y, wstride, pooled_ld, max_ns;
 };
 
@@ -705,7 +706,6 @@ static WorkspaceLayout layout_of(int n, const int32_t* map_chw) {
     L.cls_used = o; o = up(o + 4 * nn);
     L.out_index = o; o = up(o + 4 * nn);
     L.ipos = o; o = up(o + 8 * nn);
-    L.done = o; o = up(o + 4 * nn);
     L.wts = o; o = up(o + 4 * nn * L.wstride);
     L.items = o; o = up(o + 32 * nn * L.max_ns);
     L.pooled = o; o = up(o + 4 * nn * L.pooled_ld);
@@ -725,7 +725,7 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
         OODB200_REQUIRE(p.C[s] > 0 && p.H[s] > 0 && p.W[s] > 0, "%s: map %d has non-positive shape", what, s);
         p.ns[s] = (p.C[s] + kSliceChannels - 1) / kSliceChannels;
         OODB200_REQUIRE(p.ns[s] <= kMaxSlices, "%s: map %d has too many channels (%d)", what, s, p.C[s]);
-        OODB200_REQUIRE((long long)p.H[s] * p.W[s] < (1LL << 30), "%s: map %d too large", what, s);
+        OODB200_REQUIRE((long long)p.H[s] * p.W[s] < (1LL << 30) && p.H[s] < 65536 && p.W[s] < 65536, "%s: map %d too large", what, s);
     }
     OODB200_REQUIRE(p.n < (1 << 24), "%s: at most %d boxes per call", what, (1 << 24) - 1);
     if (p.n == 0) return OODB200_OK;
@@ -738,7 +738,6 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     p.cls_used = cls_used_out ? cls_used_out : (int32_t*)(ws + L.cls_used);
     p.out_index = out_index_out ? out_index_out : (int32_t*)(ws + L.out_index);
     p.ipos = (int2*)(ws + L.ipos);
-    p.done = (int*)(ws + L.done);
     p.wts = (float*)(ws + L.wts);
     p.ext_y = L.ext_y;
     p.wstride = L.wstride;
@@ -748,7 +747,7 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(p.counters, 0, 16, st);
     if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
-    plan_kernel<<<p.n_img, kPlanThreads, 0, st>>>(p);
+    plan_kernel<<<p.n_img, 32, 0, st>>>(p);
     int rc = check_launch(what);
     if (rc) return rc;
     geo_kernel<<<(p.n + kWarps - 1) / kWarps, kThreads, 0, st>>>(p);
@@ -763,20 +762,25 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     if (g_items_per_sm == 0 &&
         (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_items_per_sm, items_kernel, kThreads, 0) != cudaSuccess || g_items_per_sm <= 0))
         g_items_per_sm = OODB200_FMAP_MIN_BLOCKS;
-    const int per_sm = g_items_per_sm;
     long long max_items = (long long)p.n * L.max_ns;
-    long long grid = (long long)g_sm_count * per_sm;                 // persistent: every resident warp pulls from the queue
+    long long grid = (long long)g_sm_count * g_items_per_sm;          // persistent: every resident warp pulls from the queue
     if (grid * kWarps > max_items) grid = (max_items + kWarps - 1) / kWarps;
     items_kernel<<<(int)grid, kThreads, 0, st>>>(p);
-    return check_launch(what);
+    rc = check_launch(what);
+    if (rc) return rc;
+    if (p.cent) {
+        score_kernel<<<(p.n + kWarps - 1) / kWarps, kThreads, 0, st>>>(p);
+        rc = check_launch(what);
+    }
+    return rc;
 }
 
 }  // namespace oodb200
 
 using namespace oodb200;
 
-extern "C" int64_t oodb200_fmap_workspace_bytes(int n, const int32_t* map_chw, int need_pooled) {
-    (void)need_pooled;
+extern "C" int64_t oodb200_fmap_workspace_bytes(int n, int n_img, const int32_t* map_chw) {
+    (void)n_img;
     if (!map_chw) return -1;
     return (int64_t)layout_of(n, map_chw).total;
 }

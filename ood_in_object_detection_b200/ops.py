@@ -207,7 +207,7 @@ _workspaces = {}
 def _workspace(batch: DetectionBatch, need_pooled: bool) -> torch.Tensor:
     """Scratch for the pooling kernels (grown on demand, one per device; kernels on one stream reuse it in order)."""
     lib = _lib.load()
-    need = int(lib.oodb200_fmap_workspace_bytes(batch.n, batch.map_chw.ctypes.data_as(C.c_void_p), int(need_pooled)))
+    need = int(lib.oodb200_fmap_workspace_bytes(batch.n, batch.n_img, batch.map_chw.ctypes.data_as(C.c_void_p)))
     dev = batch.boxes.device
     ws = _workspaces.get(dev)
     if ws is None or ws.numel() < need:
