@@ -68,8 +68,7 @@ const char* oodb200_last_error(void);
  *              are contiguous); img_start [n_img+1] int32 prefix of boxes per image
  *   out        [n, out_ld] float32; row i gets C_{stride_idx[i]} values (rest untouched)
  * A box whose stride_idx is outside {0,1,2} is skipped (the reference never pools it either).
- * Maps that are 16-byte aligned with W_s % 4 == 0 (every torch-allocated YOLO map) are either streamed plane by plane
- * into shared memory (TMA bulk copies; dense groups of boxes) or gathered with 128-bit loads (sparse groups); anything
+ * Maps that are 16-byte aligned with W_s % 4 == 0 (every torch-allocated YOLO map) take the 128-bit gather; anything
  * else falls back to a scalar gather with the same results.  At most 2^24 - 1 boxes per call.
  */
 int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
@@ -78,10 +77,11 @@ int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t* map_chw, c
                          float* out, int out_ld, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Scratch the two pooling entry points need (device memory, 256-byte aligned, owned by the caller; its
- * contents need not be preserved between calls): Q1 plan, per-box window geometry, RoIAlign weights and lane tables,
- * the unit / item work lists and the pooled vectors [n, round4(Cmax)].  map_chw as in roi_pool (host).
+ * contents need not be preserved between calls): Q1 plan, per-box window geometry and RoIAlign weights,
+ * the item work list, the (stride, class) ordering of the score kernel and the pooled vectors [n, round4(Cmax)].
+ * map_chw as in roi_pool (host); nc = number of classes of the centroid table (0 for roi_pool).
  * Returns -1 when map_chw is NULL. */
-int64_t oodb200_fmap_workspace_bytes(int n, int n_img, const int32_t* map_chw);
+int64_t oodb200_fmap_workspace_bytes(int n, int nc, const int32_t* map_chw);
 
 /* ---- K1+K2 fused: pool -> L2-normalise -> distance to the class/stride centroids -> min ->
  *      threshold.  Replaces the per-image/per-stride/per-box loop of

@@ -76,7 +76,10 @@ struct FmapParams {
     float* pooled_user;         // optional caller buffer [n, pooled_user_ld], rows in output order
     int pooled_user_ld;
     // workspace
-    int* counters;              // [0] items emitted by the plan, [1] item queue head
+    int* counters;              // [0] items emitted by the plan, [1] item queue head, [2] boxes with a valid stride
+    int* hist;                  // [3*nc + 1] boxes per (stride, class used) key; last = class outside [0, nc)
+    int* cursor;                // [3*nc + 1] scatter cursors of the counting sort
+    int32_t* sorted;            // [n] valid boxes grouped by key: the score kernel's order (centroid slices hit in L1)
     int32_t* cls_used;          // [n]
     int32_t* out_index;         // [n]
     int2* ipos;                 // [n] {index of the box's slice-0 item, item stride between its slices}
@@ -166,6 +169,7 @@ __global__ void __launch_bounds__(32) plan_kernel(const FmapParams p) {
     int base = 0;
     if (lane == 0 && tot) base = atomicAdd(&p.counters[0], tot);
     base = __shfl_sync(kFull, base, 0);
+    if (lane == 0 && p.cent && cnt[0] + cnt[1] + cnt[2]) atomicAdd(&p.counters[2], cnt[0] + cnt[1] + cnt[2]);
     int item0[3];
     item0[2] = base;
     item0[1] = base + cnt[2] * p.ns[2];
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(32) plan_kernel(const FmapParams p) {
         p.out_index[b0 + b] = out;
         if (ok) {
             p.ipos[b0 + b] = make_int2(it0 + j, nb);  // item(sl) = pos0 + sl * nb
+            if (p.cent) atomicAdd(&p.hist[(cls_u >= 0 && cls_u < p.nc) ? cat * p.nc + cls_u : 3 * p.nc], 1);
         } else if (p.cent) {
             for (int k = 0; k < OODB200_N_METRICS; ++k)
                 if (p.metric_mask >> k & 1) {
@@ -253,6 +258,14 @@ __global__ void __launch_bounds__(kThreads) geo_kernel(const FmapParams p) {
         }
     } else {
         ylo = 0;
+    }
+    if (p.cent) {                                     // counting sort by (stride, class used): position = prefix + ticket
+        const int cu = p.cls_used[box];
+        const int key = (cu >= 0 && cu < p.nc) ? s * p.nc + cu : 3 * p.nc;
+        int before = 0;
+        for (int i = lane; i < key; i += 32) before += p.hist[i];
+        before = __reduce_add_sync(kFull, before);
+        if (lane == 0) p.sorted[before + atomicAdd(&p.cursor[key], 1)] = box;
     }
     const float count = (float)max(gh * gw, 1);
     for (int sl = lane; sl < p.ns[s]; sl += 32) {     // record: everything an item warp needs except the weights
@@ -446,112 +459,101 @@ __device__ __forceinline__ void write_result(const FmapParams& p, int s, int cls
 }
 
 // Vector in registers: NJ float4 per lane (C <= 128 * NJ, C % 4 == 0, 16-byte aligned centroid slices).
-template <int NJ>
-__device__ __forceinline__ void finalize_vec(const FmapParams& p, int box) {
-    const int lane = threadIdx.x & 31;
-    const int s = p.stride_idx[box], C = p.C[s], out = p.out_index[box];
+// Vector path (C % 4 == 0, 16-byte aligned centroid slice).  The normalised vector sits in a warp-private shared-memory
+// row; the warp is 4 groups of 8 lanes and every group sweeps ONE centroid row with independent 128-bit loads, so four
+// rows (x two tables) are in flight per warp and a row total needs a 3-level reduction instead of 5.  L2 latency, not
+// bandwidth, bounds this phase: the point is requests in flight.
+__device__ __forceinline__ void finalize_rows(const FmapParams& p, int box, int s, int C, int cls, int out, float* xs) {
+    const int lane = threadIdx.x & 31, g = lane >> 3, j = lane & 7;
     const float* __restrict__ row = p.pooled + (size_t)out * p.pooled_ld;
-    float4 x[NJ];
+    const bool cls_ok = cls >= 0 && cls < p.nc;
+    const int K = cls_ok ? p.cent_k[s * p.nc + cls] : 0;
+    const int64_t off = K > 0 ? p.cent_off[s * p.nc + cls] : 0;
     float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const int d = lane * 4 + 128 * j;
-        x[j] = d < C ? __ldcg(reinterpret_cast<const float4*>(row + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ss = fmaf(x[j].x, x[j].x, ss); ss = fmaf(x[j].y, x[j].y, ss);
-        ss = fmaf(x[j].z, x[j].z, ss); ss = fmaf(x[j].w, x[j].w, ss);
-    }
-    if (p.normalize) {                                // ood_utils.py:2409 -> sklearn normalize
-        float nrm = sqrtf(warp_sum(ss));
-        if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;      // _handle_zeros_in_scale
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            x[j].x = __fdiv_rn(x[j].x, nrm); x[j].y = __fdiv_rn(x[j].y, nrm);
-            x[j].z = __fdiv_rn(x[j].z, nrm); x[j].w = __fdiv_rn(x[j].w, nrm);
-        }
+    for (int d = lane * 4; d < C; d += 128) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(row + d));
+        *reinterpret_cast<float4*>(xs + d) = v;
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
     }
     const bool want_l1 = p.metric_mask & (1 << OODB200_METRIC_L1);
     const bool want_l2 = p.metric_mask & (1 << OODB200_METRIC_L2);
     const bool want_cos = p.metric_mask & (1 << OODB200_METRIC_COS);
     float n2v = 1.f;
-    if (want_cos) {                                   // cosine_distances re-normalises X (pairwise.py:1171-1182)
+    if (p.normalize || want_cos) {
+        float nrm = 1.f;
+        if (p.normalize) {                             // ood_utils.py:2409 -> sklearn normalize
+            nrm = sqrtf(warp_sum(ss));
+            if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;   // _handle_zeros_in_scale
+        }
         float s2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            s2 = fmaf(x[j].x, x[j].x, s2); s2 = fmaf(x[j].y, x[j].y, s2);
-            s2 = fmaf(x[j].z, x[j].z, s2); s2 = fmaf(x[j].w, x[j].w, s2);
+        for (int d = lane * 4; d < C; d += 128) {      // each lane re-reads what it wrote
+            float4 v = *reinterpret_cast<float4*>(xs + d);
+            if (p.normalize) {
+                v.x = __fdiv_rn(v.x, nrm); v.y = __fdiv_rn(v.y, nrm); v.z = __fdiv_rn(v.z, nrm); v.w = __fdiv_rn(v.w, nrm);
+                *reinterpret_cast<float4*>(xs + d) = v;
+            }
+            s2 = fmaf(v.x, v.x, s2); s2 = fmaf(v.y, v.y, s2); s2 = fmaf(v.z, v.z, s2); s2 = fmaf(v.w, v.w, s2);
         }
-        n2v = sqrtf(warp_sum(s2));
-        if (n2v < 10.f * FLT_EPSILON) n2v = 1.f;
+        if (want_cos) {                                // cosine_distances re-normalises X (pairwise.py:1171-1182)
+            n2v = sqrtf(warp_sum(s2));
+            if (n2v < 10.f * FLT_EPSILON) n2v = 1.f;
+        }
     }
-    const int cls = p.cls_used[box];
-    const bool cls_ok = cls >= 0 && cls < p.nc;
-    const int K = cls_ok ? p.cent_k[s * p.nc + cls] : 0;
-    Best b = {{FLT_MAX, FLT_MAX, FLT_MAX}, {-1, -1, -1}};
-    if (K > 0) {
-        const int64_t off = p.cent_off[s * p.nc + cls];
-        constexpr int U = NJ <= 2 ? 4 : (NJ <= 4 ? 2 : 1);   // centroid rows in flight (L2 latency bounds this loop)
-        for (int k = 0; k < K; k += U) {
-            float a1[U], a2[U], ac[U];
+    __syncwarp();
+    Best b = {{FLT_MAX, FLT_MAX, FLT_MAX}, {INT_MAX, INT_MAX, INT_MAX}};
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        const int k = k0 + g;
+        const bool have = k < K;
+        const float* __restrict__ ck = p.cent + off + (int64_t)(have ? k : K - 1) * C;
+        const float* __restrict__ cu = p.cent_unit + off + (int64_t)(have ? k : K - 1) * C;
+        float a1 = 0.f, a2 = 0.f, ac = 0.f;
+        for (int d0 = j * 4; d0 < C; d0 += 128) {      // batches of 4 x 128-bit loads per table, issued before any use
+            float4 c[4], u[4];
 #pragma unroll
-            for (int u = 0; u < U; ++u) a1[u] = a2[u] = ac[u] = 0.f;
-            if (want_l1 || want_l2) {
-                float4 c4[U][NJ];
+            for (int i = 0; i < 4; ++i) {
+                const int d = min(d0 + 32 * i, C - 4);
+                if (want_l1 || want_l2) c[i] = __ldg(reinterpret_cast<const float4*>(ck + d));
+                if (want_cos) u[i] = __ldg(reinterpret_cast<const float4*>(cu + d));
+            }
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float* __restrict__ ck = p.cent + off + (int64_t)min(k + u, K - 1) * C;
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        const int d = lane * 4 + 128 * j;
-                        c4[u][j] = d < C ? __ldg(reinterpret_cast<const float4*>(ck + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+            for (int i = 0; i < 4; ++i) {
+                const int d = d0 + 32 * i;
+                if (d >= C) break;
+                const float4 x = *reinterpret_cast<const float4*>(xs + d);
+                if (want_l1 || want_l2) {
+                    const float e0 = x.x - c[i].x, e1 = x.y - c[i].y, e2 = x.z - c[i].z, e3 = x.w - c[i].w;
+                    a1 += (fabsf(e0) + fabsf(e1)) + (fabsf(e2) + fabsf(e3));
+                    a2 = fmaf(e0, e0, a2); a2 = fmaf(e1, e1, a2); a2 = fmaf(e2, e2, a2); a2 = fmaf(e3, e3, a2);
                 }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        const float d0 = x[j].x - c4[u][j].x, d1 = x[j].y - c4[u][j].y, d2 = x[j].z - c4[u][j].z, d3 = x[j].w - c4[u][j].w;
-                        a1[u] += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
-                        a2[u] = fmaf(d0, d0, a2[u]); a2[u] = fmaf(d1, d1, a2[u]); a2[u] = fmaf(d2, d2, a2[u]); a2[u] = fmaf(d3, d3, a2[u]);
-                    }
-            }
-            if (want_cos) {
-                float4 c4[U][NJ];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float* __restrict__ cu = p.cent_unit + off + (int64_t)min(k + u, K - 1) * C;
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        const int d = lane * 4 + 128 * j;
-                        c4[u][j] = d < C ? __ldg(reinterpret_cast<const float4*>(cu + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        ac[u] = fmaf(x[j].x, c4[u][j].x, ac[u]); ac[u] = fmaf(x[j].y, c4[u][j].y, ac[u]);
-                        ac[u] = fmaf(x[j].z, c4[u][j].z, ac[u]); ac[u] = fmaf(x[j].w, c4[u][j].w, ac[u]);
-                    }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (want_l1) a1[u] = warp_sum(a1[u]);
-                if (want_l2) a2[u] = warp_sum(a2[u]);
-                if (want_cos) ac[u] = warp_sum(ac[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (k + u >= K) break;
-                if (want_l1 && a1[u] < b.d[0]) { b.d[0] = a1[u]; b.a[0] = k + u; }
-                if (want_l2) { const float v = sqrtf(fmaxf(a2[u], 0.f)); if (v < b.d[1]) { b.d[1] = v; b.a[1] = k + u; } }
-                if (want_cos) {                       // X / ||X|| applied to the sum (same value to float32 rounding)
-                    const float v = fminf(fmaxf(1.0f - __fdiv_rn(ac[u], n2v), 0.f), 2.f);
-                    if (v < b.d[2]) { b.d[2] = v; b.a[2] = k + u; }
+                if (want_cos) {
+                    ac = fmaf(x.x, u[i].x, ac); ac = fmaf(x.y, u[i].y, ac); ac = fmaf(x.z, u[i].z, ac); ac = fmaf(x.w, u[i].w, ac);
                 }
             }
         }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {              // totals of the group's row
+            if (want_l1) a1 += __shfl_xor_sync(kFull, a1, o);
+            if (want_l2) a2 += __shfl_xor_sync(kFull, a2, o);
+            if (want_cos) ac += __shfl_xor_sync(kFull, ac, o);
+        }
+        if (have) {
+            if (want_l1 && a1 < b.d[0]) { b.d[0] = a1; b.a[0] = k; }
+            if (want_l2) { const float v = sqrtf(fmaxf(a2, 0.f)); if (v < b.d[1]) { b.d[1] = v; b.a[1] = k; } }
+            if (want_cos) {                            // X / ||X|| applied to the sum (same value to float32 rounding)
+                const float v = fminf(fmaxf(1.0f - __fdiv_rn(ac, n2v), 0.f), 2.f);
+                if (v < b.d[2]) { b.d[2] = v; b.a[2] = k; }
+            }
+        }
     }
-    write_result(p, s, cls, cls_ok, K, out, b);               // lane m reports metric m (all lanes hold the same totals)
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1)                  // first minimum over the 4 groups: smaller distance, then smaller index
+#pragma unroll
+        for (int m = 0; m < OODB200_N_METRICS; ++m) {
+            const float od = __shfl_xor_sync(kFull, b.d[m], o);
+            const int oa = __shfl_xor_sync(kFull, b.a[m], o);
+            if (od < b.d[m] || (od == b.d[m] && oa < b.a[m])) { b.d[m] = od; b.a[m] = oa; }
+        }
+    write_result(p, s, cls, cls_ok, K, out, b);       // lane m reports metric m (all lanes hold the same result)
 }
 
 // Any C / alignment: the vector is re-read from the (L1-resident) pooled row for every centroid.
@@ -599,24 +601,20 @@ __device__ __noinline__ Best finalize_generic(const float* __restrict__ row, int
     return b;
 }
 
-__device__ __forceinline__ void finalize(const FmapParams& p, int box) {
-    const int s = p.stride_idx[box], C = p.C[s];
+__device__ __forceinline__ void finalize(const FmapParams& p, int box, float* xs) {
+    const int s = p.stride_idx[box];
     const int cls = p.cls_used[box];
-    bool vec = (C % 4 == 0) && C <= 1024;
+    const int out = p.out_index[box];
+    const int C = p.C[s];
+    bool vec = (C % 4 == 0);
     if (vec && cls >= 0 && cls < p.nc) vec = (p.cent_off[s * p.nc + cls] % 4 == 0);
-    if (!vec) {
-        const bool cls_ok = cls >= 0 && cls < p.nc;
-        const int K = cls_ok ? p.cent_k[s * p.nc + cls] : 0;
-        const int64_t off = K > 0 ? p.cent_off[s * p.nc + cls] : 0;
-        const int out = p.out_index[box];
-        const Best b = finalize_generic(p.pooled + (size_t)out * p.pooled_ld, C, p.normalize, p.metric_mask, p.cent + off,
-                                        p.cent_unit + off, K);
-        write_result(p, s, cls, cls_ok, K, out, b);
-        return;
-    }
-    if (C <= 256) finalize_vec<2>(p, box);             // few instantiations: the kernel must stay inside the instruction cache
-    else if (C <= 512) finalize_vec<4>(p, box);
-    else finalize_vec<8>(p, box);
+    if (vec) { finalize_rows(p, box, s, C, cls, out, xs); return; }
+    const bool cls_ok = cls >= 0 && cls < p.nc;
+    const int K = cls_ok ? p.cent_k[s * p.nc + cls] : 0;
+    const int64_t off = K > 0 ? p.cent_off[s * p.nc + cls] : 0;
+    const Best b = finalize_generic(p.pooled + (size_t)out * p.pooled_ld, C, p.normalize, p.metric_mask, p.cent + off,
+                                    p.cent_unit + off, K);
+    write_result(p, s, cls, cls_ok, K, out, b);
 }
 
 // ---------------------------------------------------------------------------------------------- gather kernel
@@ -675,19 +673,19 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kerne
 
 // ---------------------------------------------------------------------------------------------- score kernel
 __global__ void __launch_bounds__(kThreads) score_kernel(const FmapParams p) {
-    const int box = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (box >= p.n) return;
-    const int s = p.stride_idx[box];
-    if (s < 0 || s > 2) return;                        // answered by the plan kernel
-    finalize(p, box);
+    extern __shared__ __align__(16) float s_x[];       // [kWarps][pooled_ld]
+    const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (w >= p.counters[2]) return;                    // boxes with an invalid stride were answered by the plan kernel
+    finalize(p, p.sorted[w], s_x + (size_t)(threadIdx.x >> 5) * p.pooled_ld);
 }
 
 struct WorkspaceLayout {
-    size_t counters, cls_used, out_index, ipos, wts, items, pooled, total;
+    size_t counters, hist, cursor, sorted, cls_used, out_index, ipos, wts, items, pooled, total;
+    size_t zero_bytes;
     int ext_y, wstride, pooled_ld, max_ns;
 };
 
-static WorkspaceLayout layout_of(int n, const int32_t* map_chw) {
+static WorkspaceLayout layout_of(int n, int nc, const int32_t* map_chw) {
     WorkspaceLayout L;
     int hmax = 1, wmax = 1, cmax = 1;
     for (int s = 0; s < 3; ++s) {
@@ -702,7 +700,13 @@ static WorkspaceLayout layout_of(int n, const int32_t* map_chw) {
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;
     const size_t nn = (size_t)(n > 0 ? n : 1);
-    L.counters = o; o = up(o + 16);
+    const size_t nk = 3 * (size_t)(nc > 0 ? nc : 1) + 1;
+    L.counters = o; o += 16;                          // counters, hist and cursor are zeroed by one memset
+    L.hist = o; o += 4 * nk;
+    L.cursor = o; o += 4 * nk;
+    L.zero_bytes = o;
+    o = up(o);
+    L.sorted = o; o = up(o + 4 * nn);
     L.cls_used = o; o = up(o + 4 * nn);
     L.out_index = o; o = up(o + 4 * nn);
     L.ipos = o; o = up(o + 8 * nn);
@@ -729,12 +733,15 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     }
     OODB200_REQUIRE(p.n < (1 << 24), "%s: at most %d boxes per call", what, (1 << 24) - 1);
     if (p.n == 0) return OODB200_OK;
-    const WorkspaceLayout L = layout_of(p.n, map_chw);
+    const WorkspaceLayout L = layout_of(p.n, p.cent ? p.nc : 0, map_chw);
     OODB200_REQUIRE(workspace && workspace_bytes >= (int64_t)L.total, "%s: workspace too small (%lld < %zu bytes)", what,
                     (long long)workspace_bytes, L.total);
     OODB200_REQUIRE(((uintptr_t)workspace & 255) == 0, "%s: workspace must be 256-byte aligned", what);
     char* ws = (char*)workspace;
     p.counters = (int*)(ws + L.counters);
+    p.hist = (int*)(ws + L.hist);
+    p.cursor = (int*)(ws + L.cursor);
+    p.sorted = (int32_t*)(ws + L.sorted);
     p.cls_used = cls_used_out ? cls_used_out : (int32_t*)(ws + L.cls_used);
     p.out_index = out_index_out ? out_index_out : (int32_t*)(ws + L.out_index);
     p.ipos = (int2*)(ws + L.ipos);
@@ -745,7 +752,7 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     p.pooled = (float*)(ws + L.pooled);
     p.pooled_ld = L.pooled_ld;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(p.counters, 0, 16, st);
+    cudaError_t e = cudaMemsetAsync(p.counters, 0, L.zero_bytes, st);
     if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
     plan_kernel<<<p.n_img, 32, 0, st>>>(p);
     int rc = check_launch(what);
@@ -769,7 +776,13 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     rc = check_launch(what);
     if (rc) return rc;
     if (p.cent) {
-        score_kernel<<<(p.n + kWarps - 1) / kWarps, kThreads, 0, st>>>(p);
+        const size_t smem = sizeof(float) * (size_t)kWarps * L.pooled_ld;
+        OODB200_REQUIRE(smem <= 200 * 1024, "%s: too many channels for the score kernel (%d)", what, L.pooled_ld);
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+        }
+        score_kernel<<<(p.n + kWarps - 1) / kWarps, kThreads, smem, st>>>(p);
         rc = check_launch(what);
     }
     return rc;
@@ -779,10 +792,9 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
 
 using namespace oodb200;
 
-extern "C" int64_t oodb200_fmap_workspace_bytes(int n, int n_img, const int32_t* map_chw) {
-    (void)n_img;
-    if (!map_chw) return -1;
-    return (int64_t)layout_of(n, map_chw).total;
+extern "C" int64_t oodb200_fmap_workspace_bytes(int n, int nc, const int32_t* map_chw) {
+    if (!map_chw || nc < 0) return -1;
+    return (int64_t)layout_of(n, nc, map_chw).total;
 }
 
 extern "C" int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,

@@ -204,10 +204,10 @@ def q1_plan(batch: DetectionBatch, cls_used: Optional[torch.Tensor] = None, out_
 _workspaces = {}
 
 
-def _workspace(batch: DetectionBatch, need_pooled: bool) -> torch.Tensor:
+def _workspace(batch: DetectionBatch, nc: int) -> torch.Tensor:
     """Scratch for the pooling kernels (grown on demand, one per device; kernels on one stream reuse it in order)."""
     lib = _lib.load()
-    need = int(lib.oodb200_fmap_workspace_bytes(batch.n, batch.n_img, batch.map_chw.ctypes.data_as(C.c_void_p)))
+    need = int(lib.oodb200_fmap_workspace_bytes(batch.n, int(nc), batch.map_chw.ctypes.data_as(C.c_void_p)))
     dev = batch.boxes.device
     ws = _workspaces.get(dev)
     if ws is None or ws.numel() < need:
@@ -222,7 +222,7 @@ def roi_pool(batch: DetectionBatch, out: Optional[torch.Tensor] = None) -> torch
     cmax = int(batch.map_chw.reshape(3, 3)[:, 0].max())
     if out is None:
         out = torch.zeros((batch.n, cmax), dtype=torch.float32, device=batch.boxes.device)
-    ws = _workspace(batch, False)
+    ws = _workspace(batch, 0)
     _lib.check(lib.oodb200_roi_pool_f32(
         _ptr(batch.map_ptrs), batch.map_chw.ctypes.data_as(C.c_void_p), batch.scale.ctypes.data_as(C.c_void_p),
         batch.n_img, _ptr(batch.boxes), _ptr(batch.img_idx), _ptr(batch.stride_idx), _ptr(batch.img_start), batch.n,
@@ -259,7 +259,7 @@ def fmap_score(batch: DetectionBatch, table: CentroidTable, metric_mask: int, no
     if out is None:
         cmax = int(batch.map_chw.reshape(3, 3)[:, 0].max())
         out = alloc_fmap_scores(n, batch.boxes.device, cmax, want_pooled, want_plan)
-    ws = _workspace(batch, out.pooled is None)
+    ws = _workspace(batch, table.nc)
     _lib.check(lib.oodb200_fmap_score_f32(
         _ptr(batch.map_ptrs), batch.map_chw.ctypes.data_as(C.c_void_p), batch.scale.ctypes.data_as(C.c_void_p),
         batch.n_img, _ptr(batch.boxes), _ptr(batch.img_idx), _ptr(batch.stride_idx), _ptr(batch.cls),
