@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the OoD-scoring hot path on B200 (contract: see the task prompt / DESIGN.md §5).
+"""bench.py -- throughput of the OoD-scoring hot path on B200 (contract: task prompt / DESIGN.md section 5).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2] [--workload score|fit]
 
-One "step" = one fused scoring pass over one synthetic batch of the BASELINE.json configuration
-(default configs[1] = C2: YOLOv8s 640x640, batch 64, FMap L1 + cosine against K=10 centroids per
-(class, stride), Energy / MSP / max-logit scored in the same pass).  N > 1: one process per GPU
-(torchrun), image batches sharded, no collective on the scoring path (weak scaling: 64 images per GPU).
-
-Printed JSON (rank 0, one line): `value` = detections scored per second with inputs resident in HBM
-(CUDA events, max over ranks); `e2e` = the same through the public class API with HOST inputs
-(H2D + kernels + D2H of the decisions inside the timed region); `roofline` for the dominant kernel
-(fmap_score) from algorithmic bytes / its own CUDA-event time; `cpu_baseline` = the
-reference's per-box CPU path (oracle/cpu_path.py, a loop-for-loop port using the same torchvision /
-sklearn calls) timed on a bounded sample on this box's host cores.
+workload score (default, BASELINE.json configs[1] = C2: YOLOv8s 640x640, batch 64, FMap L1 + cosine against K=10
+centroids per (class, stride), MSP / Energy / max-logit in the same step):
+  step    = one scoring pass over one synthetic batch = plan + geo + gather + score + logit kernels, replayed as a CUDA
+            graph.  N > 1: one process per GPU (torchrun), image batches sharded, NO collective on the scoring path
+            (weak scaling: 64 images per GPU).
+  value   = detections scored per second with inputs resident in HBM (CUDA events, max over ranks, L2 flushed between
+            timed iterations).
+  e2e     = the same through the public class API (ood_utils.compute_ood_decisions_fused: the reference's method
+            classes) with pinned HOST inputs: feature maps + detections H2D, decisions D2H inside the timed region.
+  roofline for the dominant kernel (items_kernel, the window gather): algorithmic bytes (union of
+            window cells per image/stride + 37 B/box + used centroid slices) / CUDA-event time of the fused-path
+            launches; `traffic` = dram bytes of the same launches from the committed ncu capture (profiles/).
+  fit     = sub-measurement: segmented k-means (K=16, D=576, 20 classes) on --fit-n vectors sharded over the ranks, one
+            all-reduce per Lloyd iteration + exact percentile thresholds (strong scaling), vectors x iterations / s.
+  cpu_baseline = the reference's per-box CPU path (oracle/cpu_path.py: loop-for-loop port, same torchvision / sklearn
+            calls) on a bounded sample of the same batch, on this box's host cores.
+workload fit: the C3 fit (4 M vectors) as the main line.
+--impl reference: the CPU port alone, same metric / config, bounded sample per step (rank 0 only).
 """
 from __future__ import annotations
 
@@ -33,9 +40,13 @@ if ROOT not in sys.path:
 
 METRIC = "detections OoD-scored/sec"
 UNIT = "detections/s"
+FIT_METRIC = "k-means fit vectors/sec"
+FIT_UNIT = "vector-iterations/s"
 FMAP_METRICS = ("l1", "cosine")
 LOGIT_METHODS = ("MSP", "Energy", "MaxLogit")
 CPU_SAMPLE_IMAGES = 6
+FIT_D, FIT_K, FIT_CLASSES = 576, 16, 20
+KERNELS_PER_STEP = 5            # plan_kernel, geo_kernel, items_kernel, score_kernel, logit_kernel (+ one small memset)
 
 
 # ----------------------------------------------------------------------------------------- helpers
@@ -66,12 +77,12 @@ class ClockSampler:
                 pass
             self._stop.wait(0.1)
 
-    def __enter__(self):
+    def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
         return self
 
-    def __exit__(self, *a):
+    def stop(self):
         self._stop.set()
         self._t.join(timeout=6)
 
@@ -86,7 +97,7 @@ class ClockSampler:
 
 
 def algorithmic_bytes(det, wl, k, n_tables=1):
-    """SURVEY.md §8d: sum over images/strides of 4*C_s*|union of window cells| + 37 B/box + centroid slices once."""
+    """SURVEY.md section 8d: sum over images/strides of 4*C_s*|union of window cells| + 37 B/box + centroid slices once."""
     total = 0
     upper = 0
     used = set()
@@ -113,6 +124,14 @@ def algorithmic_bytes(det, wl, k, n_tables=1):
     return int(total), int(upper), n
 
 
+def _traffic(key, field):
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            return json.load(f).get(key, {}).get(field)
+    return None
+
+
 # ------------------------------------------------------------------------------------ workload setup
 def device_maps(wl, seed, device):
     import torch
@@ -134,9 +153,7 @@ def fit_tables(ops, wl, maps, seed, device):
     rng = np.random.default_rng(seed)
     tr = synth.detections(seed, wl.batch, wl.img, wl.nc, 300, fixed=True)
     tb = ops.make_batch(maps, tr["boxes"], tr["strides"], tr["cls"], wl.img, device)
-    pooled = ops.roi_pool(tb)
-    pooled = pooled / pooled.norm(dim=1, keepdim=True).clamp_min(1e-12)
-    pooled = pooled.cpu().numpy()
+    pooled = ops.normalize_rows(ops.roi_pool(tb)).cpu().numpy()   # rows are zero beyond C_s: the norm is the stride's own
     cls = np.concatenate(tr["cls"]).astype(int)
     st = np.concatenate(tr["strides"]).astype(int)
     clusters = [[np.empty(0)] * 3 for _ in range(wl.nc)]
@@ -171,6 +188,27 @@ def fit_tables(ops, wl, maps, seed, device):
     return clusters, thr, table, lthr
 
 
+def fit_data(n_total, world, rank, device, seed=77):
+    """C3-shaped fit set: FIT_CLASSES segments of unit-norm vectors, a mixture of FIT_K well-separated Gaussians per class
+    (strict convergence in a few Lloyd iterations).  Rank r generates exactly the rows kmeans.shard_rows gives it."""
+    import torch
+    from ood_in_object_detection_b200 import kmeans
+    per = n_total // FIT_CLASSES
+    sizes = [per] * FIT_CLASSES
+    shard = kmeans.shard_rows(sizes, world, rank)
+    parts = []
+    for c, (a, cnt) in enumerate(shard):
+        g = torch.Generator(device=device)
+        g.manual_seed(seed * 1000 + c)
+        centers = torch.randn((FIT_K, FIT_D), device=device, generator=g) * 6.0 / FIT_D ** 0.5 + 1.0 / FIT_D ** 0.5
+        g2 = torch.Generator(device=device)
+        g2.manual_seed(seed * 100000 + c * 64 + rank)
+        lab = torch.randint(0, FIT_K, (cnt,), device=device, generator=g2)
+        x = centers[lab] + torch.randn((cnt, FIT_D), device=device, generator=g2) / FIT_D ** 0.5
+        parts.append(x / x.norm(dim=1, keepdim=True))
+    return torch.cat(parts).contiguous(), sizes, [cnt for _, cnt in shard]
+
+
 # ------------------------------------------------------------------------------------- CPU reference
 def cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, images):
     """One pass of the reference's CPU path (port) over `images` (indices); returns (#boxes, seconds)."""
@@ -190,6 +228,23 @@ def cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, images):
     return sum(len(det["boxes"][i]) for i in images), dt
 
 
+def cpu_fit_baseline(n=40000):
+    """sklearn KMeans(K=16, random_state=10) -- the call behind cluster_utils.py:62-73 -- on one bounded segment."""
+    import torch
+    from sklearn.cluster import KMeans
+    rng = np.random.default_rng(5)
+    centers = rng.standard_normal((FIT_K, FIT_D)).astype(np.float32) * 6.0 / FIT_D ** 0.5 + 1.0 / FIT_D ** 0.5
+    x = centers[rng.integers(0, FIT_K, n)] + rng.standard_normal((n, FIT_D)).astype(np.float32) / FIT_D ** 0.5
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    t0 = time.perf_counter()
+    km = KMeans(n_clusters=FIT_K, random_state=10).fit(x)
+    dt = time.perf_counter() - t0
+    return {"value": n * km.n_iter_ / dt, "unit": FIT_UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"sklearn KMeans(n_clusters={FIT_K}, random_state=10).fit on one segment of {n} x {FIT_D} vectors "
+                      f"({km.n_iter_} Lloyd iterations, {dt:.2f} s incl. k-means++ seeding)",
+            "e2e_vectors_per_s": n / dt}
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's CPU implementation of the path (loop-for-loop port, same third-party
     calls) on this box's host cores; rank 0 only."""
@@ -197,6 +252,16 @@ def run_reference(args, wl):
         return
     import torch
     from ood_in_object_detection_b200 import synth
+    if args.workload == "fit":
+        vals = [cpu_fit_baseline() for _ in range(max(args.steps, 1))]
+        v = float(np.mean([x["value"] for x in vals]))
+        cb = dict(vals[-1], value=v)
+        print(json.dumps({"impl": "reference", "metric": FIT_METRIC, "value": v, "unit": FIT_UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "C3 k-means fit (bounded CPU sample)", "dim": FIT_D, "k": FIT_K},
+                          "cpu_baseline": cb, "e2e": {"value": v, "unit": FIT_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     n_img = CPU_SAMPLE_IMAGES
     det = synth.detections(2000, n_img, wl.img, wl.nc, wl.lam, fixed=wl.fixed_boxes)
     maps = [torch.from_numpy(m) for m in synth.feature_maps(1000, n_img, wl.channels, wl.map_hw)]
@@ -225,11 +290,61 @@ def run_reference(args, wl):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ------------------------------------------------------------------------------------------ fit arm
+def run_fit(device, world, rank, n_total, reps, warm):
+    """Segmented k-means fit + thresholds; returns a dict (rank-0 meaningful).  The Lloyd loop and the seeding are timed
+    inside kmeans_fit (device synchronised on both sides); the end-to-end figure is the wall clock around the whole fit
+    (seeding has host decisions), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from ood_in_object_detection_b200 import kmeans, ops, select
+    x, gsizes, lsizes = fit_data(n_total, world, rank, device)
+    group = dist.group.WORLD if world > 1 else None
+    best = None
+    for it in range(warm + reps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            r = kmeans.kmeans_fit_sharded(x, lsizes, gsizes, FIT_K, world, rank, group, random_state=10)
+        else:
+            r = kmeans.kmeans_fit_predict_single(x, gsizes, FIT_K, random_state=10)
+        means, counts = kmeans.member_means(x, lsizes, r.labels, FIT_K, group=group)
+        off = np.concatenate([[0], np.cumsum(lsizes)]).tolist()
+        d, _ = ops.vec_score(x, off, means.reshape(-1, FIT_D).contiguous(), None, [g * FIT_K for g in range(FIT_CLASSES)],
+                             [FIT_K] * FIT_CLASSES, 1 << ops.METRIC_SLOT["l2"], normalize=False)
+        ranks = [select.lower_index(n, 95.0) for n in gsizes]
+        thr, _, _ = select.segment_select(d[ops.METRIC_SLOT["l2"]].contiguous(), off, ranks, group=group)
+        torch.cuda.synchronize()
+        total = time.perf_counter() - t0
+        t = torch.tensor([total, r.seconds["lloyd"], r.seconds["init"]], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cur = dict(total=float(t[0]), lloyd=float(t[1]), init=float(t[2]), iters=int(r.seconds["lloyd_iters"]),
+                   n_iter=[int(v) for v in r.n_iter], strict=all(r.strict), thr0=thr[0])
+        if it >= warm and (best is None or cur["total"] < best["total"]):
+            best = cur
+    peak, _ = _peaks()
+    it_bytes = 4.0 * n_total * FIT_D + 4.0 * n_total + 2 * 4.0 * FIT_CLASSES * FIT_K * FIT_D
+    lloyd_per_iter = best["lloyd"] / max(best["iters"], 1)
+    return {"metric": FIT_METRIC, "value": n_total * best["iters"] / best["lloyd"], "unit": FIT_UNIT,
+            "n_vectors": n_total, "dim": FIT_D, "k": FIT_K, "segments": FIT_CLASSES, "lloyd_iterations": best["iters"],
+            "lloyd_ms_per_iteration": 1e3 * lloyd_per_iter, "seed_ms": 1e3 * best["init"], "fit_ms": 1e3 * best["total"],
+            "e2e_vectors_per_s": n_total / best["total"], "strict_convergence": best["strict"], "scaling": "strong",
+            "collective": "1 all-reduce per Lloyd iteration + 1 per radix pass" if world > 1 else "none (1 GPU)",
+            "roofline": {"bound": "hbm", "kernel": "kmeans_step_kernel (+reduce/update, host loop)", "unit": "GB/s",
+                         "achieved": it_bytes / world / lloyd_per_iter / 1e9, "peak": peak,
+                         "frac": it_bytes / world / lloyd_per_iter / 1e9 / peak, "algorithmic_bytes_per_iteration": it_bytes,
+                         "traffic": _traffic("C3", "kmeans_step_dram_bytes_per_launch")}}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
-    from ood_in_object_detection_b200 import ops, synth
+    from ood_in_object_detection_b200 import ood_utils, ops, synth
+    from ood_in_object_detection_b200.results import Results, batch_shape
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -238,6 +353,27 @@ def run_ours(args, wl):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    clk = ClockSampler(local).start()
+
+    if args.workload == "fit":
+        fit = run_fit(device, world, rank, args.fit_n or 4_000_000, max(args.steps, 1), max(args.warmup, 1))
+        clk.stop()
+        if rank == 0:
+            cb = cpu_fit_baseline()
+            out = {"metric": FIT_METRIC, "value": fit["value"], "unit": FIT_UNIT, "n_gpus": world, "steps": args.steps,
+                   "warmup": args.warmup, "ms_per_step": fit["fit_ms"], "higher_is_better": True, "scaling": "strong",
+                   "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                   "config": {"workload": f"C3 k-means fit N={fit['n_vectors']} D={FIT_D} K={FIT_K} x {FIT_CLASSES} classes",
+                              "sharding": f"rows of every segment over {world} rank(s)"},
+                   "roofline": fit["roofline"], "cpu_baseline": cb, "fit": fit,
+                   "e2e": {"value": fit["e2e_vectors_per_s"], "unit": "vectors/s (seed + Lloyd + member means + scores + thresholds)",
+                           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                           "note": "activations are produced on the device by the pooling kernel; nothing crosses PCIe"},
+                   "gpu_launches": 3 * fit["lloyd_iterations"] * args.steps, "clocks": clk.summary()}
+            print(json.dumps(out))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     maps = device_maps(wl, 1000 + rank, device)
     det = synth.detections(2000 + rank, wl.batch, wl.img, wl.nc, wl.lam, fixed=wl.fixed_boxes)
@@ -255,37 +391,43 @@ def run_ours(args, wl):
                            sigmoid_mismatch=torch.zeros(1, dtype=torch.int32, device=device))
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
 
-    def step(ev=None):
-        if ev:
-            ev[0].record()
-        ops.fmap_score(batch, table, fmask, True, compat_q1=True, out=fout)     # memset + plan_kernel + items_kernel
-        if ev:
-            ev[1].record()
-        ops.logit_score(logits, batch.cls, lmask, thr=lthr_d, out=lout)
-    launches_per_step = 3                                                       # plan, items, logit
+    def fused():
+        ops.fmap_score(batch, table, fmask, True, compat_q1=True, out=fout)     # memset + plan + geo + items + score
 
-    for _ in range(args.warmup):
+    def logit():
+        ops.logit_score(logits, batch.cls, lmask, thr=lthr_d, out=lout)
+
+    for _ in range(max(args.warmup, 3)):                                        # also sizes the workspace before capture
         flush.zero_()
-        step()
+        fused()
+        logit()
+    torch.cuda.synchronize()
+    g_fused, g_logit = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()           # the step = two graph launches
+    with torch.cuda.graph(g_fused):
+        fused()
+    with torch.cuda.graph(g_logit):
+        logit()
+    for _ in range(2):
+        g_fused.replay()
+        g_logit.replay()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     E = lambda: torch.cuda.Event(enable_timing=True)
-    evs = [(E(), E(), E(), E()) for _ in range(args.steps)]
-    clk = ClockSampler(local)
-    clk.__enter__()                                                      # sampled over the timed steps and the e2e loop
-    if True:
-        torch.cuda.synchronize()
-        t_wall = time.perf_counter()
-        for a, b, c, d in evs:
-            flush.zero_()                                                # L2 flush between timed iterations
-            a.record()
-            step((b, c))
-            d.record()
-        torch.cuda.synchronize()
-        t_wall = time.perf_counter() - t_wall
-    total_ms = sum(a.elapsed_time(d) for a, b, c, d in evs)
-    fmap_ms = sum(b.elapsed_time(c) for a, b, c, d in evs) / max(args.steps, 1)
+    evs = [(E(), E(), E()) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter()
+    for a, b, c in evs:
+        flush.zero_()                                                # L2 flush between timed iterations
+        a.record()
+        g_fused.replay()
+        b.record()
+        g_logit.replay()
+        c.record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall
+    total_ms = sum(a.elapsed_time(c) for a, b, c in evs)
+    fmap_ms = sum(a.elapsed_time(b) for a, b, c in evs) / max(args.steps, 1)
     if world > 1:
         dist.barrier()
         t = torch.tensor([total_ms, float(n)], dtype=torch.float64, device=device)
@@ -297,7 +439,7 @@ def run_ours(args, wl):
         n_all = float(n)
     value = n_all * args.steps / (total_ms * 1e-3)
     if args.quick:
-        clk.__exit__()
+        clk.stop()
         if rank == 0:
             alg, upper, _ = algorithmic_bytes(det, wl, wl.k)
             print(json.dumps({"value": value, "ms_per_step": total_ms / args.steps, "fmap_ms": fmap_ms,
@@ -306,67 +448,91 @@ def run_ours(args, wl):
             dist.destroy_process_group()
         return
 
-    # ---- end to end: host (pinned) inputs -> decisions on the host, every step
+    # ---- end to end through the class surface: host (pinned) inputs -> decisions on the host, every step
+    KW = dict(agg_method="mean", cluster_method=f"KMeans_{wl.k}", cluster_optimization_metric="silhouette",
+              ind_info_creation_option="valid_preds_one_stride", which_internal_activations="ftmaps_and_strides",
+              iou_threshold_for_matching=0.5, min_conf_threshold_train=0.15, min_conf_threshold_test=0.15)
+    LKW = dict(per_class=True, per_stride=False, iou_threshold_for_matching=0.5, min_conf_threshold_train=0.15,
+               min_conf_threshold_test=0.15, use_values_before_sigmoid=True)
+    m_l1, m_cos = ood_utils.L1DistanceOneClusterPerStride(**KW), ood_utils.CosineDistanceOneClusterPerStride(**KW)
+    m_l1.clusters = m_cos.clusters = clusters
+    m_l1.thresholds, m_cos.thresholds = thr[0], thr[2]
+    m_msp, m_en, m_ml = ood_utils.MSP(**LKW), ood_utils.Energy(temper=1, **LKW), ood_utils.MaxLogit(**LKW)
+    m_msp.thresholds, m_en.thresholds, m_ml.thresholds = lthr[0].tolist(), lthr[1].tolist(), lthr[4].tolist()
+    methods = [m_l1, m_cos, m_msp, m_en, m_ml]
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_maps = [m.cpu().pin_memory() for m in maps]
-    h_boxes, h_str, h_cls = [pin(b) for b in det["boxes"]], [pin(s) for s in det["strides"]], [pin(c) for c in det["cls"]]
-    h_logits = pin(np.concatenate(det["logits"]))
-    h2d = sum(m.numel() * 4 for m in h_maps) + sum(b.numel() * 4 for b in h_boxes + h_str + h_cls) + h_logits.numel() * 4
+    shape = batch_shape(wl.batch, wl.img, wl.img)
+    res_f, res_l = [], []
+    for i in range(wl.batch):
+        b6 = np.concatenate([det["boxes"][i], det["conf"][i][:, None], det["cls"][i][:, None]], 1).astype(np.float32)
+        res_f.append(Results(orig_img=shape, boxes=pin(b6), extra_item=([hm[i] for hm in h_maps], pin(det["strides"][i]))))
+        res_l.append(Results(orig_img=shape, boxes=pin(b6), extra_item=pin(det["logits"][i])))
+    h2d = sum(m.numel() * 4 for m in h_maps) + sum(r.boxes.data.numel() * 4 + r.extra_item[1].numel() * 4 for r in res_f) \
+        + len(LOGIT_METHODS) * sum(r.extra_item.numel() * 4 + r.boxes.data.shape[0] * 4 for r in res_l)
+    import logging
+    log = logging.getLogger("bench")
+    log.setLevel(logging.ERROR)
     e2e_steps = max(2, min(args.steps, 5))
 
     def e2e_step():
-        b = ops.make_batch(h_maps, h_boxes, h_str, h_cls, wl.img, device)
-        z = h_logits.to(device, non_blocking=True)
-        fr = ops.fmap_score(b, table, fmask, True, compat_q1=True)
-        lr = ops.logit_score(z, b.cls, lmask, thr=lthr_d)
-        return fr.decision.cpu(), lr.decision.cpu()
-    e2e_step()
+        return ood_utils.compute_ood_decisions_fused(methods, res_f, log, logits_results=res_l)
+    dec = e2e_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        fd, ld = e2e_step()
+        dec = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    d2h = fd.numel() + ld.numel()
+    d2h = sum(sum(len(v) for v in d) for d in dec.values())
+    # the class surface and the resident path agree
+    same = np.array_equal(np.array([v for im in dec[m_cos.name] for v in im], np.uint8), fout.decision[2].cpu().numpy())
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     e2e_value = n_all * e2e_steps / e2e_s
-    clk.__exit__()
+
+    fit = None
+    if args.fit_n != 0:
+        del h_maps, res_f, res_l
+        torch.cuda.empty_cache()
+        fit = run_fit(device, world, rank, args.fit_n or 2_000_000, 2, 1)
+    clk.stop()
 
     if rank == 0:
         alg, upper, _ = algorithmic_bytes(det, wl, wl.k)
         peak, how = _peaks()
         achieved = alg / (fmap_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get(args.config, {}).get("fmap_dram_bytes_per_launch")
         maps_cpu = [m[:CPU_SAMPLE_IMAGES].cpu() for m in maps]
         cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, [0])        # warm the imports / thread pools
         cpu_n, cpu_t = cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, list(range(CPU_SAMPLE_IMAGES)))
-        clocks = clk.summary()
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "images_per_gpu": wl.batch, "boxes_per_gpu": n, "fmap_metrics": FMAP_METRICS,
                        "logit_methods": LOGIT_METHODS, "k_per_class_stride": wl.k, "nc": wl.nc,
-                       "l2_flush": "512 MiB memset between timed iterations", "sharding": f"batch x{world}, no collective"},
-            "roofline": {"bound": "hbm", "kernel": "plan_kernel+items_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg,
-                         "upper_bound_bytes": upper, "kernel_ms": fmap_ms, "peak_source": how},
+                       "l2_flush": "512 MiB memset between timed iterations", "sharding": f"batch x{world}, no collective",
+                       "launch": "CUDA graph replay (fused path, logit path)"},
+            "roofline": {"bound": "hbm", "kernel": "items_kernel (window gather) within plan+geo+items+score", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": _traffic(args.config, "fmap_dram_bytes_per_launch"), "algorithmic_bytes": alg,
+                         "upper_bound_bytes": upper, "kernel_ms": fmap_ms, "peak_source": how,
+                         "note": "HBM moves whole 128-byte lines; NCHW window rows are 8..52 B (DESIGN.md section 4)"},
             "cpu_baseline": {"value": cpu_n / cpu_t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{CPU_SAMPLE_IMAGES} of {wl.batch} images ({cpu_n} boxes), L1+cosine FMap and "
                                        f"MSP+Energy logits through oracle/cpu_path.py (per-box sklearn/torchvision calls)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "note": "host pinned feature maps + detections -> decisions on host"},
-            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "wall_s_timed_region": t_wall,
+                    "steps": e2e_steps, "api": "ood_utils.compute_ood_decisions_fused([L1, Cosine, MSP, Energy, MaxLogit], results)",
+                    "matches_resident_path": bool(same),
+                    "note": "host pinned feature maps + detections -> per-image decision lists on the host"},
+            "gpu_launches": KERNELS_PER_STEP * args.steps, "clocks": clk.summary(), "wall_s_timed_region": t_wall,
         }
+        if fit is not None:
+            out["fit"] = fit
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -379,7 +545,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C4", "C5"])
-    ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the e2e and cpu_baseline legs (tuning sweeps)")
+    ap.add_argument("--workload", default="score", choices=["score", "fit"])
+    ap.add_argument("--fit-n", type=int, default=None, help="vectors of the k-means sub-measurement (0: skip; default 2 M, "
+                    "4 M for --workload fit)")
+    ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the e2e, fit and cpu_baseline legs (tuning sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     from ood_in_object_detection_b200 import synth

@@ -185,6 +185,230 @@ __global__ void __launch_bounds__(kKmThreads) kmeans_step_kernel(const KmParams 
     }
 }
 
+// ---- fast path for K <= 16: register tiling.
+// A warp takes R = 4 rows at a time (x in registers: R * NJ float4 per lane), so every centroid value read from shared
+// memory feeds 4 rows (the one-row kernel above is bound by shared-memory bandwidth: 1 LDS.128 per 4 FMAs).  The
+// R * 8 partial dots of a group of 8 centroids are reduced with ONE transposing butterfly (31 shuffles for 32 totals).
+// Partial sums live in REGISTERS: thread t owns columns t, t + 256, ... of every centroid; the label of a row is
+// warp-uniform, so `switch (label)` picks the accumulator without divergence and rows are added in row order
+// (bit-reproducible block partials, same order as the one-row kernel).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+
+constexpr int kFastR = 4;
+constexpr int kFastRows = kKmWarps * kFastR;          // rows per chunk
+
+template <int N>
+__device__ __forceinline__ float transpose_reduce(float (&v)[N], int lane) {   // lane l ends with the total of v[l], N == 32
+    int o = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1, o >>= 1) {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFullMask, send, o);
+        }
+    }
+    return v[0];
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(kKmThreads, 1) kmeans_step_fast_kernel(const KmParams p) {
+    extern __shared__ __align__(128) float smem[];
+    constexpr int NC = (NJ * 128 + kKmThreads - 1) / kKmThreads;      // columns per thread
+    const int D = p.dim, K = p.k;                                     // D % 4 == 0 (row pitch = D), K <= 16
+    float* s_stage = smem;                                            // [2][kFastRows][D]: TMA landing zone, double buffered
+    float* s_cent = s_stage + (size_t)2 * kFastRows * D;              // [16][D]
+    float* s_csn = s_cent + (size_t)16 * D;                           // [16]
+    __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ int s_lab[kFastRows];
+    __shared__ unsigned s_mask[16];
+    __shared__ int s_changed;
+    static_assert(kFastRows == 32, "one ballot covers the chunk");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    const int g = p.block_seg[b];
+    if (p.active && !p.active[g]) return;
+    const int Kg = p.seg_k[g];
+    const int64_t r0 = p.block_row0[b], r1 = p.block_row1[b];
+    const int n_chunks = (int)((r1 - r0 + kFastRows - 1) / kFastRows);
+    auto issue = [&](int c) {                                         // thread 0: one bulk copy = the chunk's rows (contiguous)
+        const int64_t ra = r0 + (int64_t)c * kFastRows;
+        const uint32_t bytes = (uint32_t)(min((int64_t)kFastRows, r1 - ra) * D * 4);
+        mbar_expect_tx(&s_full[c & 1], bytes);
+        bulk_g2s(s_stage + (size_t)(c & 1) * kFastRows * D, p.x + ra * D, bytes, &s_full[c & 1]);
+    };
+    if (tid == 0) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_changed = 0;
+        issue(0);
+        if (n_chunks > 1) issue(1);
+    }
+    const float* __restrict__ cg = p.cent + (size_t)g * K * D;
+    for (int i = tid; i < 16 * D; i += kKmThreads) {
+        const int k = i / D, d = i - k * D;
+        s_cent[i] = k < Kg ? __ldg(cg + (size_t)k * D + d) : 0.f;
+    }
+    __syncthreads();
+    for (int k = warp; k < 16; k += kKmWarps) {                       // ||c||^2 (row_norms(centers, squared=True))
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) s = fmaf(s_cent[k * D + d], s_cent[k * D + d], s);
+        s = warp_sum(s);
+        if (lane == 0) s_csn[k] = s;
+    }
+    float acc[16][NC];
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[k][c] = 0.f;
+    float cnt = 0.f;                                                  // thread k (< 16) counts the members of cluster k
+    __syncthreads();
+    for (int c = 0; c < n_chunks; ++c) {
+        const float* __restrict__ st = s_stage + (size_t)(c & 1) * kFastRows * D;
+        const int64_t rw = r0 + (int64_t)c * kFastRows + warp * kFastR;
+        mbar_wait(&s_full[c & 1], (uint32_t)(c >> 1) & 1u);
+        float4 xv[kFastR][NJ];
+#pragma unroll
+        for (int r = 0; r < kFastR; ++r)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int d = lane * 4 + 128 * j;
+                xv[r][j] = (rw + r < r1 && d < D) ? *reinterpret_cast<const float4*>(st + (size_t)(warp * kFastR + r) * D + d)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        float best = FLT_MAX;                                         // lane l: row l >> 3 of this warp
+        int barg = 0;
+        if (p.update == 2) {                                          // sums of the GIVEN labels (member means)
+            const int64_t rr = rw + (lane >> 3);
+            barg = rr < r1 ? p.labels[rr] : 0;
+            if (barg < 0 || barg >= Kg) barg = 0;
+        } else {
+            for (int kg = 0; kg < Kg; kg += 8) {
+                float dot[kFastR * 8];
+#pragma unroll
+                for (int i = 0; i < kFastR * 8; ++i) dot[i] = 0.f;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int d = lane * 4 + 128 * j;
+                    if (d < D) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float4 c4 = *reinterpret_cast<const float4*>(s_cent + (size_t)(kg + u) * D + d);
+#pragma unroll
+                            for (int r = 0; r < kFastR; ++r) {
+                                float s = dot[r * 8 + u];
+                                s = fmaf(xv[r][j].x, c4.x, s); s = fmaf(xv[r][j].y, c4.y, s);
+                                s = fmaf(xv[r][j].z, c4.z, s); s = fmaf(xv[r][j].w, c4.w, s);
+                                dot[r * 8 + u] = s;
+                            }
+                        }
+                    }
+                }
+                const float tot = transpose_reduce<kFastR * 8>(dot, lane);   // lane l: row l >> 3, centroid kg + (l & 7)
+                const int kk = kg + (lane & 7);
+                float pd = kk < Kg ? fmaf(-2.0f, tot, s_csn[kk]) : FLT_MAX;  // gemm(alpha=-2, beta=1) on ||c||^2
+                int pk = kk < Kg ? kk : INT_MAX;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {                            // first minimum over the 8 centroids of the group
+                    const float od = __shfl_xor_sync(kFullMask, pd, o);
+                    const int ok = __shfl_xor_sync(kFullMask, pk, o);
+                    if (od < pd || (od == pd && ok < pk)) { pd = od; pk = ok; }
+                }
+                if (pd < best) { best = pd; barg = pk; }                     // strict <: earlier group wins ties
+            }
+        }
+        if ((lane & 7) == 0) {
+            const int r = lane >> 3;
+            const int64_t rr = rw + r;
+            if (rr < r1) {
+                s_lab[warp * kFastR + r] = barg;
+                if (p.labels[rr] != barg) atomicAdd(&s_changed, 1);
+                p.labels[rr] = barg;
+            } else {
+                s_lab[warp * kFastR + r] = -1;
+            }
+        }
+        __syncthreads();
+        if (p.update) {
+            // Register accumulation, cluster by cluster: the rows of the chunk that carry label k come from a ballot
+            // (warp 0), are visited in row order (bit-reproducible block partial), and k is a compile-time index of
+            // the accumulator array -- no label-dependent branch, no shared-memory read-modify-write.
+            if (warp == 0) {
+                const int l = s_lab[lane];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const unsigned m = __ballot_sync(kFullMask, l == k);
+                    if (lane == k) s_mask[k] = m;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                unsigned m = s_mask[k];
+                if (tid == k) cnt += (float)__popc(m);
+                while (m) {                                           // 4 rows per trip: their loads overlap, the adds stay in row order
+                    int w[4];
+                    float v[4][NC];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        w[q] = m ? __ffs(m) - 1 : -1;
+                        m &= m - 1;                                   // 0 & anything stays 0
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            const int d = tid + cc * kKmThreads;
+                            v[q][cc] = (w[q] >= 0 && d < D) ? st[(size_t)w[q] * D + d] : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc)
+                            if (w[q] >= 0) acc[k][cc] += v[q][cc];
+                }
+            }
+            __syncthreads();                                          // the buffer is free again
+        }
+        if (tid == 0 && c + 2 < n_chunks) issue(c + 2);
+    }
+    __syncthreads();
+    if (tid == 0 && s_changed) atomicAdd(&p.n_changed[g], s_changed);
+    if (p.update) {
+        float* __restrict__ ps = p.psums + (size_t)b * K * D;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < K)
+#pragma unroll
+                for (int cc = 0; cc < NC; ++cc) {
+                    const int d = tid + cc * kKmThreads;
+                    if (d < D) ps[(size_t)k * D + d] = acc[k][cc];
+                }
+        if (tid < K) p.pcounts[(size_t)b * K + tid] = cnt;
+    }
+}
+
 // out[grp, e] = sum over blocks b in [first[grp], first[grp+1]) of in[b, e], sequentially in b
 __global__ void kmeans_reduce_kernel(const float* __restrict__ in, const int32_t* __restrict__ first, int n_groups,
                                      int64_t elems, float* __restrict__ out) {
@@ -328,6 +552,22 @@ extern "C" int oodb200_kmeans_step_f32(const float* x, int dim, int n_seg, int k
                   n_changed, update};
     const int nj = (dim + 127) / 128;
     cudaStream_t st = (cudaStream_t)stream;
+    if (k <= 16 && nj <= 6 && dim % 4 == 0 && ((uintptr_t)x & 15) == 0) {   // TMA-fed register-tiled fast path
+        const size_t fsmem = sizeof(float) * ((size_t)16 * dim + (size_t)2 * kFastRows * dim + 16);
+#define OODB200_KMF_LAUNCH(NJ)                                                                                        \
+    case NJ: {                                                                                                         \
+        cudaError_t e = cudaFuncSetAttribute(kmeans_step_fast_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)fsmem);                                                              \
+        if (e != cudaSuccess) { set_error("kmeans_step: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }        \
+        kmeans_step_fast_kernel<NJ><<<n_blocks, kKmThreads, fsmem, st>>>(p);                                           \
+    } break;
+        switch (nj) {
+            OODB200_KMF_LAUNCH(1) OODB200_KMF_LAUNCH(2) OODB200_KMF_LAUNCH(3) OODB200_KMF_LAUNCH(4)
+            OODB200_KMF_LAUNCH(5) OODB200_KMF_LAUNCH(6)
+        }
+#undef OODB200_KMF_LAUNCH
+        return check_launch("kmeans_step");
+    }
 #define OODB200_KM_LAUNCH(NJ)                                                                                          \
     case NJ: {                                                                                                         \
         if (smem > 48 * 1024) {                                                                                        \

@@ -1486,6 +1486,48 @@ class TripleFusionMethod(_FusionBase):
         return _split_lists(out.cpu().numpy(), counts, int)
 
 
+# ------------------------------------------------------------------------------------------------ fused multi-method pass
+def compute_ood_decisions_fused(methods: Sequence[OODMethod], results, logger, logits_results=None) -> Dict[str, List[List[int]]]:
+    """Decisions of several methods on the same detections with the feature maps uploaded / gathered ONCE.
+
+    Extension of the reference surface (which scores one method per detector pass, ood_evaluation.py:183-278):
+    every `DistanceMethod` in `methods` that shares its `.clusters` object with the others is scored in the same fused
+    launch (metric mask), the logit methods in one logit launch.  `results` carry `(ftmaps, strides)` extra items,
+    `logits_results` (default: `results`) the raw class logits.  Returns {method.name or 'name#i': decisions}, each
+    exactly what `method.compute_ood_decision_on_results` returns."""
+    out: Dict[str, List[List[int]]] = {}
+    dist_m = [m for m in methods if isinstance(m, DistanceMethod)]
+    logit_m = [m for m in methods if isinstance(m, LogitsMethod)]
+    key = lambda m, i: m.name if m.name not in out else f"{m.name}#{i}"
+    if dist_m:
+        lead = dist_m[0]
+        share = [m for m in dist_m if m.clusters is lead.clusters and m.which_internal_activations == 'ftmaps_and_strides'
+                 and m.reference_compat == lead.reference_compat and m.normalize_activations == lead.normalize_activations]
+        if len(share) > 1 and len(results):
+            dev = ops.default_device()
+            hw = _img_hw(results[0])
+            batch = ops.make_batch([list(r.extra_item[0]) for r in results], [r.boxes.xyxy for r in results],
+                                   [r.extra_item[1] for r in results], [r.boxes.cls for r in results], hw[1], dev)
+            dims = [int(c) for c in batch.map_chw.reshape(3, 3)[:, 0]]
+            table = ops.pack_centroids(lead.clusters, {m._metric_slot: m.thresholds for m in share}, dims, dev)
+            mask = 0
+            for m in share:
+                mask |= 1 << m._metric_slot
+            res = ops.fmap_score(batch, table, mask, normalize=lead.normalize_activations, compat_q1=lead.reference_compat)
+            dec = res.decision.cpu().numpy()
+            for i, m in enumerate(share):
+                out[key(m, i)] = _split_lists(dec[m._metric_slot], batch.counts, int)
+        else:
+            share = []
+        for i, m in enumerate(dist_m):
+            if m not in share:
+                out[key(m, i)] = m.compute_ood_decision_on_results(results, logger)
+    lres = results if logits_results is None else logits_results
+    for i, m in enumerate(logit_m):
+        out[key(m, i)] = m.compute_ood_decision_on_results(lres, logger)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ detector hook-up
 def configure_extra_output_of_the_model(model, ood_method):
     """Tell the (reference-patched ultralytics) detector which extra item to attach to its Results
