@@ -400,9 +400,13 @@ class LogitsMethod(OODMethod):
         counts = [int(len(res.boxes.cls)) for res in results]
         if sum(counts) == 0:
             return dev, counts, None, None
-        logits = torch.cat([_to_device_f32(res.extra_item, dev).reshape(len(res.boxes.cls), -1)
-                            for res, m in zip(results, counts) if m])
-        cls = torch.cat([res.boxes.cls.to(dev) for res, m in zip(results, counts) if m]).to(torch.int32)
+        rows = [(res.extra_item, res.boxes.cls) for res, m in zip(results, counts) if m]
+        if all(isinstance(z, torch.Tensor) and not z.is_cuda and not c.is_cuda for z, c in rows):   # host inputs: one copy each
+            logits = torch.cat([z.reshape(len(c), -1) for z, c in rows]).to(torch.float32).to(dev, non_blocking=True)
+            cls = torch.cat([c.reshape(-1) for _, c in rows]).to(torch.int32).to(dev, non_blocking=True)
+        else:
+            logits = torch.cat([_to_device_f32(z, dev).reshape(len(c), -1) for z, c in rows])
+            cls = torch.cat([c.to(dev) for _, c in rows]).to(torch.int32)
         return dev, counts, logits, cls
 
     def _launch(self, logits: Tensor, cls: Tensor, with_tables: bool):

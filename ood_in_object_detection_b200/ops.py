@@ -85,22 +85,44 @@ def make_batch(maps, boxes: Sequence, strides: Sequence, cls: Sequence, img_w: i
         assert len(maps) == n_img, "maps must be 3 batched tensors or one list of 3 CHW tensors per image"
         ptrs = np.empty((n_img, 3), dtype=np.int64)
         chw = None
-        for i, per_img in enumerate(maps):
-            ts = [_dev(m, device, torch.float32) for m in per_img]
-            assert len(ts) == 3 and all(t.dim() == 3 for t in ts), "each image needs 3 CHW maps"
-            shp = [tuple(t.shape) for t in ts]
+        for per_img in maps:
+            assert len(per_img) == 3 and all(isinstance(t, torch.Tensor) and t.dim() == 3 for t in per_img), \
+                "each image needs 3 CHW maps"
+            shp = [tuple(t.shape) for t in per_img]
             assert chw is None or shp == chw, "all images must share the map shapes"
             chw = shp
-            ptrs[i] = [t.data_ptr() for t in ts]
-            keep.extend(ts)
         if chw is None:
             chw = [(1, 1, 1)] * 3
+        for s in range(3):
+            col = [per_img[s] for per_img in maps]
+            nbytes = int(np.prod(chw[s])) * 4
+            batched = None
+            if col and not col[0].is_cuda and col[0].dtype == torch.float32 and all(
+                    t.is_contiguous() and t.dtype == torch.float32 and t.data_ptr() == col[0].data_ptr() + i * nbytes
+                    for i, t in enumerate(col)):
+                # host maps that are consecutive views of one batched tensor (what the detector hook hands out): ONE copy
+                batched = torch.as_strided(col[0], (len(col),) + chw[s], (int(np.prod(chw[s])),) + tuple(col[0].stride()))
+                dev_b = batched.to(device, non_blocking=True)
+                ptrs[:, s] = dev_b.data_ptr() + np.arange(n_img, dtype=np.int64) * nbytes
+                keep.append(dev_b)
+            else:
+                ts = [_dev(t, device, torch.float32) for t in col]
+                ptrs[:, s] = [t.data_ptr() for t in ts]
+                keep.extend(ts)
     counts = [int(len(b)) for b in boxes]
     n = sum(counts)
+    def _flat(seq, dtype, width=None):
+        """per-image sequences -> one device tensor; host inputs are concatenated on the host and copied ONCE"""
+        ts = [t if isinstance(t, torch.Tensor) else torch.as_tensor(np.asarray(t)) for t in seq]
+        shape = (-1, width) if width else (-1,)
+        if all(not t.is_cuda for t in ts):
+            return torch.cat([t.reshape(shape) for t in ts]).to(dtype).contiguous().to(device, non_blocking=True)
+        return torch.cat([t.to(device).reshape(shape) for t in ts]).to(dtype).contiguous()
+
     if n:
-        bx = torch.cat([_dev(b, device, torch.float32).reshape(-1, 4) for b in boxes])
-        st = torch.cat([_dev(s, device).reshape(-1) for s in strides]).to(torch.int32)
-        cl = torch.cat([_dev(c, device).reshape(-1) for c in cls]).to(torch.int32)
+        bx = _flat(boxes, torch.float32, 4)
+        st = _flat(strides, torch.int32)
+        cl = _flat(cls, torch.int32)
     else:
         bx = torch.zeros((0, 4), dtype=torch.float32, device=device)
         st = torch.zeros(0, dtype=torch.int32, device=device)
