@@ -57,10 +57,18 @@ class CudaBackend:
                                                          _stream()), "oodb200_sqdist_cand_f32")
         return out, pot
 
+    def _partials(self, n_blocks, k, dim, device):
+        """Block-partial buffers, reused across the Lloyd iterations of a fit (144 MB at C3/2: not worth re-allocating)."""
+        key = (n_blocks, k, dim, str(device))
+        if getattr(self, "_pkey", None) != key:
+            self._pbuf = (torch.empty((n_blocks, k, dim), dtype=torch.float32, device=device),
+                          torch.empty((n_blocks, k), dtype=torch.float32, device=device))
+            self._pkey = key
+        return self._pbuf
+
     def step(self, x, k, seg_k, cent, blocks, active, labels, n_changed, update):
         n_blocks = blocks.n_blocks
-        psums = torch.empty((n_blocks, k, x.shape[1]), dtype=torch.float32, device=x.device) if update else None
-        pcounts = torch.empty((n_blocks, k), dtype=torch.float32, device=x.device) if update else None
+        psums, pcounts = self._partials(n_blocks, k, x.shape[1], x.device) if update else (None, None)
         self._lib.check(self.lib.oodb200_kmeans_step_f32(
             _ptr(x), x.shape[1], int(seg_k.shape[0]), k, _ptr(seg_k), _ptr(cent), _ptr(blocks.seg), _ptr(blocks.row0),
             _ptr(blocks.row1), n_blocks, _ptr(active), _ptr(labels), _ptr(psums), _ptr(pcounts), _ptr(n_changed),
