@@ -97,9 +97,11 @@ def make_batch(maps, boxes: Sequence, strides: Sequence, cls: Sequence, img_w: i
             col = [per_img[s] for per_img in maps]
             nbytes = int(np.prod(chw[s])) * 4
             batched = None
+            st0 = col[0].untyped_storage() if col else None
             if col and not col[0].is_cuda and col[0].dtype == torch.float32 and all(
                     t.is_contiguous() and t.dtype == torch.float32 and t.data_ptr() == col[0].data_ptr() + i * nbytes
-                    for i, t in enumerate(col)):
+                    and t.untyped_storage().data_ptr() == st0.data_ptr() for i, t in enumerate(col)) \
+                    and col[0].data_ptr() - st0.data_ptr() + len(col) * nbytes <= st0.nbytes():
                 # host maps that are consecutive views of one batched tensor (what the detector hook hands out): ONE copy
                 batched = torch.as_strided(col[0], (len(col),) + chw[s], (int(np.prod(chw[s])),) + tuple(col[0].stride()))
                 dev_b = batched.to(device, non_blocking=True)

@@ -91,6 +91,30 @@ def test_kmeans_labels_match_sklearn_and_reference(dev, golden):
         np.testing.assert_allclose(res.centers[i, :min(8, len(s))].cpu().numpy(), km.cluster_centers_, rtol=1e-4, atol=1e-5)
 
 
+def test_kmeans_c3_shape_fast_path(dev):
+    """D = 576, K = 16 (the TMA-fed register-tiled step kernel, 5 x 128 columns, ragged last chunk) vs sklearn."""
+    from sklearn.cluster import KMeans
+    from threadpoolctl import threadpool_limits
+    from ood_in_object_detection_b200 import kmeans, synth
+    segs = [synth.blob_vectors(40 + i, n, 576, 16, 8.0)[0] for i, n in enumerate((2500, 1037))]
+    sizes = [len(s) for s in segs]
+    x = torch.from_numpy(np.concatenate(segs)).to(dev)
+    res = kmeans.kmeans_fit_predict_single(x, sizes, 16)
+    lab = res.labels.cpu().numpy()
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    for i, s in enumerate(segs):
+        with threadpool_limits(1):
+            km = KMeans(n_clusters=16, random_state=10).fit(s)
+        assert np.array_equal(lab[off[i]:off[i + 1]], km.labels_), i
+        np.testing.assert_allclose(res.centers[i].cpu().numpy(), km.cluster_centers_, rtol=1e-4, atol=1e-5)
+    means, counts = kmeans.member_means(x, sizes, res.labels, 16)         # update == 2 mode of the same kernel
+    for i, s in enumerate(segs):
+        for j in range(16):
+            m = lab[off[i]:off[i + 1]] == j
+            assert counts[i, j].item() == m.sum()
+            np.testing.assert_allclose(means[i, j].cpu().numpy(), s[m].mean(0), rtol=1e-5, atol=1e-6)
+
+
 def test_kmeans_realistic_overlap_agreement(dev):
     """Unstructured data: labels are compared through agreement / inertia (sklearn itself is not reproducible across
     thread counts there), not bit for bit."""

@@ -154,6 +154,38 @@ def test_pre_pooled_and_box_order_modes(ou, golden):
     assert np.array_equal(a["decision"], b["decision"])
 
 
+def test_fused_multi_method_helper(ou, golden):
+    """compute_ood_decisions_fused (maps uploaded once, metrics in one launch) == each method on its own; host inputs."""
+    g = golden("golden_small_kmeans5.npz")
+    nc, img = int(g["nc"]), int(g["img"])
+    images, maps = scoring_case(g)
+    boxes, cls, strides = [im["boxes"] for im in images], [im["cls"] for im in images], [im["strides"] for im in images]
+    test = _results(maps, boxes, cls, strides, img, device="cpu")         # per-image views of one host tensor: one H2D copy
+    shared = unpack_nested(g, "l2_clusters", nc)
+    methods = []
+    for tag, klass in _classes(ou):
+        m = klass(**dict(DIST_KW, cluster_method="KMeans_5"))
+        m.clusters = shared
+        m.thresholds = unpack_nested(g, f"{tag}_thr", nc, as_threshold=True)
+        methods.append(m)
+    rng = np.random.default_rng(0)
+    from ood_in_object_detection_b200.results import Results, batch_shape
+    lres = [Results(orig_img=batch_shape(len(boxes), img, img), boxes=r.boxes,
+                    extra_item=torch.from_numpy(rng.normal(size=(len(b), nc)).astype(np.float32))) for r, b in zip(test, boxes)]
+    msp = ou.MSP(**LOGIT_KW)
+    msp.thresholds = [0.2] * nc
+    out = ou.compute_ood_decisions_fused(methods + [msp], test, LOG, logits_results=lres)
+    assert set(out) == {"L1DistancePerStride", "L2DistancePerStride", "CosineDistancePerStride", "MSP"}
+    for m in methods:
+        assert out[m.name] == m.compute_ood_decision_on_results(test, LOG), m.name
+    assert out["MSP"] == msp.compute_ood_decision_on_results(lres, LOG)
+    own = ou.L2DistanceOneClusterPerStride(**dict(DIST_KW, cluster_method="KMeans_5"))   # different clusters object: own pass
+    own.clusters = [list(row) for row in shared]
+    own.thresholds = methods[1].thresholds
+    out2 = ou.compute_ood_decisions_fused([methods[0], own], test, LOG)
+    assert out2["L2DistancePerStride"] == out["L2DistancePerStride"] and out2["L1DistancePerStride"] == out["L1DistancePerStride"]
+
+
 def test_extractor_helper_matches_reference(ou, golden):
     g = golden("golden_roi_edges.npz")
     img = int(g["img"])

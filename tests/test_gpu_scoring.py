@@ -175,6 +175,11 @@ def test_fused_scoring_vs_oracle_at_config_shapes(ops, cfg, batch, lam, k):
     maps = synth.feature_maps(99, batch, wl.channels, wl.map_hw)
     det = synth.detections(100, batch, wl.img, wl.nc, lam)
     det["boxes"][0][0] = [0, 0, wl.img, wl.img]                               # full-image box on its stride
+    for j in range(3):                                                        # whole-image / wide boxes forced onto EVERY stride:
+        det["boxes"][0][1 + j] = [3, 5, wl.img - 2, wl.img - 7]               # windows of > 256 16-byte chunks (tiled path)
+        det["strides"][0][1 + j] = j
+    det["boxes"][0][4] = [0, 10, wl.img, 40]                                  # one very wide, flat window on the finest map
+    det["strides"][0][4] = 0
     rng = np.random.default_rng(5)
     clusters = [[np.abs(rng.standard_normal((k, c))).astype(np.float32) / np.sqrt(c) * 1.3 for c in wl.channels]
                 for _ in range(wl.nc)]
