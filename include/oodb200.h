@@ -211,6 +211,35 @@ int oodb200_sqdist_cand_f32(const float* x, int dim, const int64_t* seg_off, int
                             const float* cand, int n_cand, const float* closest, float* out_d, double* pot,
                             void* stream);
 
+/* ---- K4b: k-means++ seeding on the device (sklearn `_kmeans_plusplus`, sklearn/cluster/_kmeans.py:180-278, behind
+ * /root/reference/cluster_utils.py:62-73), every segment in lock-step, no host round trip per centre.
+ * seed_sqdist: like sqdist_cand with n_cand <= 4, but the potentials are bit-reproducible: every block writes a
+ *   float64 partial to pot_part [n_seg, oodb200_seed_grid(max_seg_rows), 4] and pots [n_seg, n_cand] receives their
+ *   fixed-order sum (the caller adds the ranks).
+ * seed_scan: cand_id[g, t] = min(searchsorted(cumsum_f32(closest of segment g in global row order),
+ *   uniform[g, t] * pot[g]), n_g - 1) -- the cumsum is the sequential float32 sum numpy computes.  Segment g is the
+ *   concatenation of n_pieces pieces closest_all[piece_off[g, r] .. + piece_cnt[g, r]) (one piece per rank).
+ *   chunk_sum: scratch [n_seg, max_chunks] floats, max_chunks >= 32 * ceil(max segment rows / 4096).
+ *   seg_trials [n_seg] (<= n_trials; remaining slots repeat candidate 0), seg_on [n_seg] (0 = skip) may be NULL.
+ * seed_gather: vec[g, j, :] = x[seg_off[g] + cand_id[g, j] - shard_first[g]] when this rank owns that row, else 0.
+ * seed_pick: best = first minimum of float32(pots[g, :trials]); closest[r] = newd[best, r] for the rows of g;
+ *   pot[g] = float32(pots[g, best]); cent_out[g * cent_stride + d] = cand_vec[g, best, d].
+ */
+int oodb200_seed_grid(int64_t max_seg_rows);
+int oodb200_seed_sqdist_f32(const float* x, int dim, const int64_t* seg_off, int n_seg, int64_t max_seg_rows,
+                            const float* cand, int n_cand, const float* closest, float* out_d, double* pot_part,
+                            double* pots, void* stream);
+int oodb200_seed_scan_f32(const float* closest_all, const int64_t* piece_off, const int64_t* piece_cnt, int n_seg,
+                          int n_pieces, const double* uniform, const float* pot, const int32_t* seg_trials,
+                          const int32_t* seg_on, int n_trials, float* chunk_sum, int64_t max_chunks, int64_t* cand_id,
+                          void* stream);
+int oodb200_seed_gather_f32(const float* x, int dim, const int64_t* cand_id, int n_seg, int n_cand,
+                            const int64_t* seg_off, const int64_t* shard_first, float* vec, void* stream);
+int oodb200_seed_pick_f32(const double* pots, const int32_t* seg_trials, const int32_t* seg_on, int n_seg, int n_cand,
+                          const int64_t* seg_off, int64_t max_seg_rows, const float* newd, const float* cand_vec, int dim,
+                          float* closest, float* pot, float* cent_out, int64_t cent_stride, int32_t* best_out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,487 @@
+// K4b: k-means++ seeding on the device, every (class, stride) segment in lock-step, sm_100a.
+//
+// Replaces the per-centre loop of sklearn's `_kmeans_plusplus` (sklearn/cluster/_kmeans.py:180-278), which
+// `KMeans(n_clusters=k, random_state=10).fit_predict(X)` (/root/reference/cluster_utils.py:62-73) runs once per
+// (class, stride).  Per new centre:
+//
+//   seed_scan      `np.searchsorted(np.cumsum(closest_dist_sq), rand_vals)` (:252-257).  np.cumsum on float32 is a
+//                  sequential float32 sum, so the scan is a single dependent FADD chain per segment (one CTA per
+//                  segment: all threads stage 4096 values into shared memory, double buffered, one thread runs the
+//                  chain at 4 cycles per value and records the running sum at the end of every 128-value chunk).
+//                  The search is a binary search over the chunk sums followed by a re-scan of ONE chunk from its
+//                  exact start value, which reproduces the sequential sums bit for bit.  rand_vals = u * pot is
+//                  float64 (u ~ RandomState.uniform drawn on the host up front: the stream does not depend on the
+//                  data); `cum[i] >= v` with cum float32 and v float64 is the same as `cum[i] >= float32_roundup(v)`.
+//   sqdist_cand4   `_euclidean_distances(X[candidate_ids], X, squared=True)` + `np.minimum(closest, .)` (:260-265):
+//                  float64 expansion cast to float32 (like `_euclidean_distances_upcast`), 4 rows per warp in
+//                  registers so every candidate value read from shared memory feeds 4 rows, ONE transposing
+//                  butterfly per 4 rows, per-block float64 partial potentials (no atomics: bit-reproducible).
+//   seed_pots      fixed-order sum of the block partials -> candidate potentials [n_seg, n_cand] (:268).
+//   seed_pick      best candidate = first minimum of the float32 potentials (:271-276); the new closest distances,
+//                  the new centre, the new potential.
+// Segments are described in GLOBAL row order by `pieces` so that N ranks run the identical scan on an all-gathered
+// copy of the closest distances (rank-major = row order).
+#include "common.cuh"
+
+#include <float.h>
+
+namespace oodb200 {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kScanThreads = 128;
+constexpr int kScanBatch = 4096;       // values staged per buffer
+constexpr int kScanChunk = 128;        // running sum recorded every kScanChunk values
+constexpr int kMaxPieces = 16;         // ranks
+
+struct ScanParams {
+    const float* closest_all;          // all-gathered closest distances
+    const int64_t* piece_off;          // [n_seg, n_pieces] element offset of the piece in closest_all
+    const int64_t* piece_cnt;          // [n_seg, n_pieces] rows of the piece
+    int n_pieces;
+    const double* uniform;             // [n_seg, n_trials] u in [0, 1)
+    const float* pot;                  // [n_seg] current potential (float32)
+    const int32_t* seg_trials;         // [n_seg] trials used by the segment (<= n_trials)
+    const int32_t* seg_on;             // [n_seg] 0 -> segment skipped this round
+    int n_trials;
+    float* chunk_sum;                  // [n_seg, max_chunks] scratch
+    int64_t max_chunks;
+    int64_t* cand_id;                  // [n_seg, n_trials] global row index within the segment
+};
+
+__global__ void __launch_bounds__(kScanThreads) seed_scan_kernel(const ScanParams p) {
+    __shared__ __align__(16) float s_buf[2][kScanBatch];
+    __shared__ int64_t s_start[kMaxPieces + 1];        // global index of the first row of every piece
+    __shared__ int64_t s_off[kMaxPieces];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (p.seg_on && !p.seg_on[g]) return;
+    if (tid == 0) {
+        int64_t acc = 0;
+        for (int r = 0; r < p.n_pieces; ++r) {
+            s_start[r] = acc;
+            s_off[r] = p.piece_off[(size_t)g * p.n_pieces + r];
+            acc += p.piece_cnt[(size_t)g * p.n_pieces + r];
+        }
+        s_start[p.n_pieces] = acc;
+    }
+    __syncthreads();
+    const int np = p.n_pieces;
+    const int64_t n = s_start[np];
+    if (n == 0) return;
+    auto value = [&](int64_t i) -> float {             // closest distance of global row i of this segment
+        int r = 0;
+        while (r + 1 < np && i >= s_start[r + 1]) ++r;
+        return __ldg(p.closest_all + s_off[r] + (i - s_start[r]));
+    };
+    auto stage = [&](int64_t i0, int b) {
+        for (int j = tid; j < kScanBatch; j += kScanThreads) {
+            const int64_t i = i0 + j;
+            s_buf[b][j] = i < n ? value(i) : 0.f;
+        }
+    };
+    float* __restrict__ cs = p.chunk_sum + (size_t)g * p.max_chunks;
+    const int64_t n_batches = (n + kScanBatch - 1) / kScanBatch;
+    stage(0, 0);
+    __syncthreads();
+    float run = 0.f;                                   // thread 0: the sequential float32 sum
+    for (int64_t b = 0; b < n_batches; ++b) {
+        const int cur = (int)(b & 1);
+        if (tid == 0) {
+            const int64_t i0 = b * kScanBatch;
+            const int valid = (int)min((int64_t)kScanBatch, n - i0);
+            const int n_chunks = (valid + kScanChunk - 1) / kScanChunk;
+            const float4* __restrict__ v4 = reinterpret_cast<const float4*>(s_buf[cur]);
+            for (int c = 0; c < n_chunks; ++c) {       // padding values are +0.0f: x + 0 == x for x >= 0
+#pragma unroll 8
+                for (int q = 0; q < kScanChunk / 4; ++q) {
+                    const float4 v = v4[c * (kScanChunk / 4) + q];
+                    run = __fadd_rn(run, v.x);
+                    run = __fadd_rn(run, v.y);
+                    run = __fadd_rn(run, v.z);
+                    run = __fadd_rn(run, v.w);
+                }
+                cs[b * (kScanBatch / kScanChunk) + c] = run;
+            }
+        } else if (b + 1 < n_batches) {
+            // threads 1.. stage the next batch meanwhile (thread 0's share is picked up by striding over tid >= 1)
+            const int64_t i0 = (b + 1) * kScanBatch;
+            for (int j = tid - 1; j < kScanBatch; j += kScanThreads - 1) {
+                const int64_t i = i0 + j;
+                s_buf[cur ^ 1][j] = i < n ? value(i) : 0.f;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- searchsorted(cumsum, u * pot), side='left', then clip to n - 1
+    const int64_t n_chunks_tot = (n + kScanChunk - 1) / kScanChunk;
+    const int trials = p.seg_trials ? p.seg_trials[g] : p.n_trials;
+    if (tid < p.n_trials) {
+        int64_t id = 0;
+        if (tid < trials) {
+            const double v = p.uniform[(size_t)g * p.n_trials + tid] * (double)p.pot[g];
+            const float thr = __double2float_ru(v);    // cum >= v  <=>  cum >= thr for float32 cum
+            int64_t lo = 0, hi = n_chunks_tot;         // first chunk whose end sum reaches thr
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (cs[mid] >= thr) hi = mid; else lo = mid + 1;
+            }
+            if (lo >= n_chunks_tot) {
+                id = n - 1;                            // beyond the total: np.clip(ids, None, n - 1)
+            } else {
+                float s = lo > 0 ? cs[lo - 1] : 0.f;
+                const int64_t i0 = lo * kScanChunk, i1 = min(n, i0 + kScanChunk);
+                id = i1 - 1;
+                for (int64_t i = i0; i < i1; ++i) {
+                    s = __fadd_rn(s, value(i));
+                    if (s >= thr) { id = i; break; }
+                }
+            }
+        }
+        p.cand_id[(size_t)g * p.n_trials + tid] = id;
+    }
+    __syncthreads();
+    if (tid == 0 && trials < p.n_trials) {             // padding slots repeat the first candidate (ignored by pick)
+        const int64_t id0 = p.cand_id[(size_t)g * p.n_trials];
+        for (int t = trials; t < p.n_trials; ++t) p.cand_id[(size_t)g * p.n_trials + t] = id0;
+    }
+}
+
+// ---- candidate distances, 4 rows per warp -----------------------------------------------------------------------
+struct Cand4Params {
+    const float* x;
+    int dim;
+    const int64_t* seg_off;            // [n_seg + 1] local row offsets
+    int n_seg;
+    const float* cand;                 // [n_seg, n_cand, dim]
+    int n_cand;                        // <= 4
+    const float* closest;              // [n_rows] or null
+    float* out_d;                      // [n_cand, n_rows]
+    double* pot_part;                  // [n_seg, gridDim.x, 4]
+};
+
+__device__ __forceinline__ double shfl_xor_f64(double v, int o) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(kFull, lo, o);
+    hi = __shfl_xor_sync(kFull, hi, o);
+    return __hiloint2double(hi, lo);
+}
+
+__device__ __forceinline__ double transpose_reduce_f64(double (&v)[32], int lane) {   // lane l ends with the total of v[l]
+    int o = 16;
+#pragma unroll
+    for (int n = 32; n > 1; n >>= 1, o >>= 1) {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const double send = up ? v[i] : v[i + n / 2];
+            const double keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + shfl_xor_f64(send, o);
+        }
+    }
+    return v[0];
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(256, 1) sqdist_cand4_kernel(const Cand4Params p) {
+    extern __shared__ __align__(16) double s_y[];              // [4][dim] candidates in float64, then 4 norms
+    const int g = blockIdx.y;
+    const int D = p.dim, NC = p.n_cand;
+    double* s_yy = s_y + (size_t)4 * D;
+    __shared__ double s_pot[8][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = p.seg_off[g], r1 = p.seg_off[g + 1];
+    const int64_t n_rows = p.seg_off[p.n_seg];
+    for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) {
+        const int j = i / D, d = i - j * D;
+        s_y[i] = j < NC ? (double)p.cand[((size_t)g * NC + j) * D + d] : 0.0;
+    }
+    __syncthreads();
+    if (warp < 4) {
+        double s = 0.0;
+        for (int d = lane; d < D; d += 32) s += s_y[warp * D + d] * s_y[warp * D + d];
+        for (int o = 16; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
+        if (lane == 0) s_yy[warp] = s;
+    }
+    __syncthreads();
+    const int q = lane & 7, rr = lane >> 3;                    // after the butterfly: lane = row rr, quantity q
+    double pot = 0.0;
+    for (int64_t base = r0 + ((int64_t)blockIdx.x * 8 + warp) * 4; base < r1; base += (int64_t)gridDim.x * 32) {
+        float4 xv[4][NJ];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int d = lane * 4 + 128 * j;
+                xv[r][j] = (base + r < r1 && d < D) ? __ldg(reinterpret_cast<const float4*>(p.x + (base + r) * D + d))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        double acc[32];                                        // [row][8]: 4 candidate dots, ||x||^2, 3 unused
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int d = lane * 4 + 128 * j;
+            if (d < D) {
+                double2 y01[4], y23[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    y01[c] = *reinterpret_cast<const double2*>(s_y + (size_t)c * D + d);
+                    y23[c] = *reinterpret_cast<const double2*>(s_y + (size_t)c * D + d + 2);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const double a = (double)xv[r][j].x, b = (double)xv[r][j].y, c2 = (double)xv[r][j].z,
+                                 e = (double)xv[r][j].w;
+                    double xx = acc[r * 8 + 4];
+                    xx += a * a; xx += b * b; xx += c2 * c2; xx += e * e;
+                    acc[r * 8 + 4] = xx;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        double s = acc[r * 8 + c];
+                        s += a * y01[c].x; s += b * y01[c].y; s += c2 * y23[c].x; s += e * y23[c].y;
+                        acc[r * 8 + c] = s;
+                    }
+                }
+            }
+        }
+        const double tot = transpose_reduce_f64(acc, lane);    // lane: row rr, quantity q
+        int xlo = __double2loint(tot), xhi = __double2hiint(tot);
+        xlo = __shfl_sync(kFull, xlo, (lane & ~7) | 4);
+        xhi = __shfl_sync(kFull, xhi, (lane & ~7) | 4);
+        const double xnorm = __hiloint2double(xhi, xlo);
+        const int64_t r = base + rr;
+        if (q < NC && r < r1) {
+            const float cl = p.closest ? p.closest[r] : FLT_MAX;
+            float d32 = (float)(-2.0 * tot + s_yy[q] + xnorm);
+            d32 = fminf(fmaxf(d32, 0.f), cl);
+            p.out_d[(size_t)q * n_rows + r] = d32;
+            pot += (double)d32;
+        }
+    }
+    // block partial in a fixed order: rows of a lane group, then warps
+    pot += shfl_xor_f64(pot, 8);
+    pot += shfl_xor_f64(pot, 16);
+    if (lane < 4) s_pot[warp][lane] = pot;
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_pot[w][threadIdx.x];
+        p.pot_part[((size_t)g * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = t;
+    }
+}
+
+// generic shapes (dim % 4 != 0, unaligned x): one row per warp, same arithmetic and the same partial layout
+__global__ void __launch_bounds__(256) sqdist_cand1_kernel(const Cand4Params p) {
+    extern __shared__ __align__(16) double s_y[];
+    const int g = blockIdx.y;
+    const int D = p.dim, NC = p.n_cand;
+    double* s_yy = s_y + (size_t)4 * D;
+    __shared__ double s_pot[8][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = p.seg_off[g], r1 = p.seg_off[g + 1];
+    const int64_t n_rows = p.seg_off[p.n_seg];
+    for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) {
+        const int j = i / D, d = i - j * D;
+        s_y[i] = j < NC ? (double)p.cand[((size_t)g * NC + j) * D + d] : 0.0;
+    }
+    __syncthreads();
+    if (warp < 4) {
+        double s = 0.0;
+        for (int d = lane; d < D; d += 32) s += s_y[warp * D + d] * s_y[warp * D + d];
+        for (int o = 16; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
+        if (lane == 0) s_yy[warp] = s;
+    }
+    __syncthreads();
+    double pot[4] = {0, 0, 0, 0};
+    for (int64_t r = r0 + (int64_t)blockIdx.x * 8 + warp; r < r1; r += (int64_t)gridDim.x * 8) {
+        const float* __restrict__ xr = p.x + r * D;
+        double xx = 0.0, dot[4] = {0, 0, 0, 0};
+        for (int d = lane; d < D; d += 32) {
+            const double v = (double)__ldg(xr + d);
+            xx += v * v;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dot[j] += v * s_y[j * D + d];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            xx += shfl_xor_f64(xx, o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dot[j] += shfl_xor_f64(dot[j], o);
+        }
+        if (lane == 0) {
+            const float cl = p.closest ? p.closest[r] : FLT_MAX;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < NC) {
+                    float d32 = (float)(-2.0 * dot[j] + s_yy[j] + xx);
+                    d32 = fminf(fmaxf(d32, 0.f), cl);
+                    p.out_d[(size_t)j * n_rows + r] = d32;
+                    pot[j] += (double)d32;
+                }
+        }
+    }
+    if (lane == 0)
+        for (int j = 0; j < 4; ++j) s_pot[warp][j] = pot[j];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_pot[w][threadIdx.x];
+        p.pot_part[((size_t)g * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = t;
+    }
+}
+
+// pots[g, j] = sum_b pot_part[g, b, j] in increasing b
+__global__ void seed_pots_kernel(const double* __restrict__ part, int n_blocks, int n_cand, double* __restrict__ pots) {
+    const int g = blockIdx.x, j = threadIdx.x;
+    if (j >= n_cand) return;
+    double t = 0.0;
+    for (int b = 0; b < n_blocks; ++b) t += part[((size_t)g * n_blocks + b) * 4 + j];
+    pots[(size_t)g * n_cand + j] = t;
+}
+
+struct PickParams {
+    const double* pots;                // [n_seg, n_cand] (summed over ranks)
+    const int32_t* seg_trials;
+    const int32_t* seg_on;
+    int n_seg, n_cand;
+    const int64_t* seg_off;            // local rows
+    const float* newd;                 // [n_cand, n_rows]
+    const float* cand_vec;             // [n_seg, n_cand, dim]
+    int dim;
+    float* closest;                    // [n_rows] updated in place
+    float* pot;                        // [n_seg]
+    float* cent_out;                   // centre slot of this round: cent + c * dim, segment stride cent_stride
+    int64_t cent_stride;
+    int32_t* best_out;                 // [n_seg]
+};
+
+__device__ __forceinline__ int pick_best(const PickParams& p, int g) {
+    const int t = p.seg_trials ? p.seg_trials[g] : p.n_cand;
+    int best = 0;
+    float bp = (float)p.pots[(size_t)g * p.n_cand];
+    for (int j = 1; j < t; ++j) {                      // np.argmin over float32 potentials: first minimum
+        const float v = (float)p.pots[(size_t)g * p.n_cand + j];
+        if (v < bp) { bp = v; best = j; }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(256) seed_pick_kernel(const PickParams p) {
+    const int g = blockIdx.y;
+    if (p.seg_on && !p.seg_on[g]) return;
+    const int best = pick_best(p, g);
+    const int64_t r0 = p.seg_off[g], r1 = p.seg_off[g + 1];
+    const int64_t n_rows = p.seg_off[p.n_seg];
+    const float* __restrict__ src = p.newd + (size_t)best * n_rows;
+    for (int64_t r = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += (int64_t)gridDim.x * blockDim.x)
+        p.closest[r] = src[r];
+    if (blockIdx.x == 0) {
+        for (int d = threadIdx.x; d < p.dim; d += blockDim.x)
+            p.cent_out[(size_t)g * p.cent_stride + d] = p.cand_vec[((size_t)g * p.n_cand + best) * p.dim + d];
+        if (threadIdx.x == 0) {
+            p.pot[g] = (float)p.pots[(size_t)g * p.n_cand + best];
+            if (p.best_out) p.best_out[g] = best;
+        }
+    }
+}
+
+// vec[g, j, :] = x[local row of global id] if this rank owns the row, else 0 (ranks are summed afterwards)
+__global__ void seed_gather_kernel(const float* __restrict__ x, int dim, const int64_t* __restrict__ cand_id, int n_cand,
+                                   const int64_t* __restrict__ seg_off, const int64_t* __restrict__ shard_first,
+                                   float* __restrict__ vec) {
+    const int g = blockIdx.x, j = blockIdx.y;
+    const int64_t id = cand_id[(size_t)g * n_cand + j] - shard_first[g];
+    const int64_t cnt = seg_off[g + 1] - seg_off[g];
+    const bool mine = id >= 0 && id < cnt;
+    float* __restrict__ o = vec + ((size_t)g * n_cand + j) * dim;
+    const float* __restrict__ s = x + (size_t)(seg_off[g] + (mine ? id : 0)) * dim;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) o[d] = mine ? s[d] : 0.f;
+}
+
+}  // namespace oodb200
+
+using namespace oodb200;
+
+extern "C" int oodb200_seed_grid(int64_t max_seg_rows) {
+    long long gx = (max_seg_rows + 127) / 128;
+    if (gx > 148 * 4) gx = 148 * 4;
+    if (gx < 1) gx = 1;
+    return (int)gx;
+}
+
+extern "C" int oodb200_seed_sqdist_f32(const float* x, int dim, const int64_t* seg_off, int n_seg, int64_t max_seg_rows,
+                                       const float* cand, int n_cand, const float* closest, float* out_d,
+                                       double* pot_part, double* pots, void* stream) {
+    OODB200_REQUIRE(dim > 0 && n_seg >= 0 && n_cand >= 1 && n_cand <= 4, "seed_sqdist: bad size (n_cand <= 4)");
+    if (n_seg == 0) return OODB200_OK;
+    OODB200_REQUIRE(x && seg_off && cand && out_d && pot_part && pots, "seed_sqdist: null pointer");
+    OODB200_REQUIRE(n_seg <= 65535, "seed_sqdist: too many segments");
+    const size_t smem = sizeof(double) * ((size_t)4 * dim + 4);
+    OODB200_REQUIRE(smem <= 200 * 1024, "seed_sqdist: dim too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = oodb200_seed_grid(max_seg_rows);
+    Cand4Params p = {x, dim, seg_off, n_seg, cand, n_cand, closest, out_d, pot_part};
+    const int nj = (dim + 127) / 128;
+    const dim3 grid((unsigned)gx, (unsigned)n_seg);
+    cudaError_t e = cudaSuccess;
+    if (dim % 4 == 0 && nj <= 6 && ((uintptr_t)x & 15) == 0) {
+#define OODB200_C4_LAUNCH(NJ)                                                                                        \
+    case NJ:                                                                                                         \
+        if (smem > 48 * 1024)                                                                                        \
+            e = cudaFuncSetAttribute(sqdist_cand4_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) sqdist_cand4_kernel<NJ><<<grid, 256, smem, st>>>(p);                                   \
+        break;
+        switch (nj) {
+            OODB200_C4_LAUNCH(1) OODB200_C4_LAUNCH(2) OODB200_C4_LAUNCH(3) OODB200_C4_LAUNCH(4)
+            OODB200_C4_LAUNCH(5) OODB200_C4_LAUNCH(6)
+        }
+#undef OODB200_C4_LAUNCH
+    } else {
+        if (smem > 48 * 1024)
+            e = cudaFuncSetAttribute(sqdist_cand1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) sqdist_cand1_kernel<<<grid, 256, smem, st>>>(p);
+    }
+    if (e != cudaSuccess) { set_error("seed_sqdist: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+    int rc = check_launch("seed_sqdist");
+    if (rc) return rc;
+    seed_pots_kernel<<<n_seg, 32, 0, st>>>(pot_part, gx, n_cand, pots);
+    return check_launch("seed_pots");
+}
+
+extern "C" int oodb200_seed_scan_f32(const float* closest_all, const int64_t* piece_off, const int64_t* piece_cnt,
+                                     int n_seg, int n_pieces, const double* uniform, const float* pot,
+                                     const int32_t* seg_trials, const int32_t* seg_on, int n_trials, float* chunk_sum,
+                                     int64_t max_chunks, int64_t* cand_id, void* stream) {
+    OODB200_REQUIRE(n_seg >= 0 && n_pieces >= 1 && n_pieces <= kMaxPieces, "seed_scan: 1..%d pieces per segment", kMaxPieces);
+    OODB200_REQUIRE(n_trials >= 1 && n_trials <= 32, "seed_scan: 1..32 trials");
+    if (n_seg == 0) return OODB200_OK;
+    OODB200_REQUIRE(closest_all && piece_off && piece_cnt && uniform && pot && chunk_sum && cand_id, "seed_scan: null pointer");
+    ScanParams p = {closest_all, piece_off, piece_cnt, n_pieces, uniform, pot, seg_trials, seg_on, n_trials, chunk_sum,
+                    max_chunks, cand_id};
+    seed_scan_kernel<<<n_seg, kScanThreads, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("seed_scan");
+}
+
+extern "C" int oodb200_seed_gather_f32(const float* x, int dim, const int64_t* cand_id, int n_seg, int n_cand,
+                                       const int64_t* seg_off, const int64_t* shard_first, float* vec, void* stream) {
+    OODB200_REQUIRE(dim > 0 && n_seg >= 0 && n_cand >= 1 && n_cand <= 65535, "seed_gather: bad size");
+    if (n_seg == 0) return OODB200_OK;
+    OODB200_REQUIRE(x && cand_id && seg_off && shard_first && vec, "seed_gather: null pointer");
+    seed_gather_kernel<<<dim3((unsigned)n_seg, (unsigned)n_cand), 128, 0, (cudaStream_t)stream>>>(x, dim, cand_id, n_cand, seg_off,
+                                                                                                   shard_first, vec);
+    return check_launch("seed_gather");
+}
+
+extern "C" int oodb200_seed_pick_f32(const double* pots, const int32_t* seg_trials, const int32_t* seg_on, int n_seg,
+                                     int n_cand, const int64_t* seg_off, int64_t max_seg_rows, const float* newd,
+                                     const float* cand_vec, int dim, float* closest, float* pot, float* cent_out,
+                                     int64_t cent_stride, int32_t* best_out, void* stream) {
+    OODB200_REQUIRE(n_seg >= 0 && n_cand >= 1 && dim > 0, "seed_pick: bad size");
+    if (n_seg == 0) return OODB200_OK;
+    OODB200_REQUIRE(pots && seg_off && newd && cand_vec && closest && pot && cent_out, "seed_pick: null pointer");
+    PickParams p = {pots, seg_trials, seg_on, n_seg, n_cand, seg_off, newd, cand_vec, dim, closest, pot, cent_out, cent_stride,
+                    best_out};
+    long long gx = (max_seg_rows + 1023) / 1024;
+    if (gx > 64) gx = 64;
+    if (gx < 1) gx = 1;
+    seed_pick_kernel<<<dim3((unsigned)gx, (unsigned)n_seg), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("seed_pick");
+}

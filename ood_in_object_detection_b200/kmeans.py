@@ -27,6 +27,7 @@ import torch
 
 BLOCK_ROWS = 512          # rows per CTA partial
 SUPER_BLOCKS = 32         # block partials per super-block (unit of ownership for reduce="ordered")
+DEVICE_SEEDING_MIN_ROWS = 1 << 16   # seeding="auto": below this the host loop costs nothing and tracks sklearn's BLAS
 
 
 def _ptr(t):
@@ -56,6 +57,50 @@ class CudaBackend:
                                                          _ptr(cand), n_cand, _ptr(closest), _ptr(out), _ptr(pot),
                                                          _stream()), "oodb200_sqdist_cand_f32")
         return out, pot
+
+    # ---- device seeding (csrc/seed.cu) ----
+    supports_device_seeding = True
+
+    def seed_sqdist(self, x, seg_off_d, max_seg_rows, cand, closest):
+        """-> (min(closest, d) [n_cand, n_local], potentials [n_seg, n_cand] float64, bit-reproducible)"""
+        n_seg, n_cand = cand.shape[0], cand.shape[1]
+        gx = int(self.lib.oodb200_seed_grid(int(max_seg_rows)))
+        out = torch.empty((n_cand, x.shape[0]), dtype=torch.float32, device=x.device)
+        part = torch.empty((n_seg, gx, 4), dtype=torch.float64, device=x.device)
+        pots = torch.empty((n_seg, n_cand), dtype=torch.float64, device=x.device)
+        self._lib.check(self.lib.oodb200_seed_sqdist_f32(_ptr(x), x.shape[1], _ptr(seg_off_d), n_seg, int(max_seg_rows),
+                                                         _ptr(cand), n_cand, _ptr(closest), _ptr(out), _ptr(part),
+                                                         _ptr(pots), _stream()), "oodb200_seed_sqdist_f32")
+        return out, pots
+
+    def seed_scan(self, closest_all, piece_off, piece_cnt, uniform, pot, seg_trials, seg_on, max_seg_rows_global, cand_id):
+        n_seg, n_pieces = piece_off.shape
+        n_trials = uniform.shape[1]
+        max_chunks = 32 * ((int(max_seg_rows_global) + 4095) // 4096) + 32
+        key = (n_seg, max_chunks, str(closest_all.device))
+        if getattr(self, "_skey", None) != key:
+            self._sbuf = torch.empty((n_seg, max_chunks), dtype=torch.float32, device=closest_all.device)
+            self._skey = key
+        self._lib.check(self.lib.oodb200_seed_scan_f32(_ptr(closest_all), _ptr(piece_off), _ptr(piece_cnt), n_seg, n_pieces,
+                                                       _ptr(uniform), _ptr(pot), _ptr(seg_trials), _ptr(seg_on), n_trials,
+                                                       _ptr(self._sbuf), max_chunks, _ptr(cand_id), _stream()),
+                        "oodb200_seed_scan_f32")
+
+    def seed_gather(self, x, cand_id, seg_off_d, shard_first):
+        n_seg, n_cand = cand_id.shape
+        vec = torch.empty((n_seg, n_cand, x.shape[1]), dtype=torch.float32, device=x.device)
+        self._lib.check(self.lib.oodb200_seed_gather_f32(_ptr(x), x.shape[1], _ptr(cand_id), n_seg, n_cand, _ptr(seg_off_d),
+                                                         _ptr(shard_first), _ptr(vec), _stream()), "oodb200_seed_gather_f32")
+        return vec
+
+    def seed_pick(self, pots, seg_trials, seg_on, seg_off_d, max_seg_rows, newd, vec, closest, pot, cent, c):
+        n_seg, n_cand = pots.shape
+        k, dim = cent.shape[1], cent.shape[2]
+        out = C.c_void_p(cent.data_ptr() + 4 * c * dim)
+        self._lib.check(self.lib.oodb200_seed_pick_f32(_ptr(pots), _ptr(seg_trials), _ptr(seg_on), n_seg, n_cand,
+                                                       _ptr(seg_off_d), int(max_seg_rows), _ptr(newd), _ptr(vec), dim,
+                                                       _ptr(closest), _ptr(pot), out, k * dim, None, _stream()),
+                        "oodb200_seed_pick_f32")
 
     def _partials(self, n_blocks, k, dim, device):
         """Block-partial buffers, reused across the Lloyd iterations of a fit (144 MB at C3/2: not worth re-allocating)."""
@@ -162,9 +207,17 @@ def _sklearn_first_center(rs: np.random.RandomState, n: int) -> int:
 
 def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table: BlockTable, local_off: Sequence[int],
                shard: Sequence[tuple], random_state: int = 10, max_iter: int = 300, tol: float = 1e-4,
-               backend=None, group=None, reduce: str = "allreduce") -> KMeansResult:
+               backend=None, group=None, reduce: str = "allreduce", seeding: str = "auto") -> KMeansResult:
     """x_local: this rank's rows [n_local, dim] (segment-major, each segment's shard contiguous), float32.
-    global_sizes: rows per segment over all ranks.  Returns labels for the local rows and the global centres."""
+    global_sizes: rows per segment over all ranks.  Returns labels for the local rows and the global centres.
+
+    seeding: "device" -- the whole k-means++ loop runs on the device (csrc/seed.cu): exact sequential float32 cumsum +
+             searchsorted, float64 candidate distances, potentials = correctly rounded float32 of the exact sum;
+             "host"   -- the scalar decisions run in numpy with sklearn's own expressions (the potentials come from the
+             host BLAS `closest @ ones`, like sklearn on this machine), O(N) host work per centre;
+             "auto"   -- "device" from DEVICE_SEEDING_MIN_ROWS total rows on, else "host".
+    The two differ only in the last bit of a potential, which moves a draw to a neighbouring row with probability
+    ~ n * 2^-24 per draw (sklearn itself depends on the BLAS summation order there)."""
     import time
     import torch.distributed as dist
     distributed = group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
@@ -208,6 +261,95 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
 
     # ---- k-means++ seeding, all segments in lock-step (sklearn _kmeans_plusplus, _kmeans.py:180-278) ----
     t0 = time.perf_counter()
+    if seeding == "auto":
+        seeding = "device" if (getattr(backend, "supports_device_seeding", False)
+                               and sum(int(n) for n in global_sizes) >= DEVICE_SEEDING_MIN_ROWS) else "host"
+    if seeding not in ("device", "host"):
+        raise ValueError(f"seeding must be 'auto', 'device' or 'host', not {seeding!r}")
+    if seeding == "device":
+        cent = _seed_on_device(x, global_sizes, local_off, shard, seg_k_host, k, random_state, backend, group,
+                               distributed, world)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+    else:
+        cent = _seed_on_host(x, global_sizes, local_off, shard, seg_k_host, k, random_state, backend, group,
+                             distributed, world, seg_off_d)
+    timing["init"] = time.perf_counter() - t0
+    timing["seeding"] = seeding
+
+    # ---- Lloyd iterations (sklearn _kmeans_single_lloyd, _kmeans.py:630-758) ----
+    t0 = time.perf_counter()
+    labels = torch.full((x.shape[0],), -1, dtype=torch.int32, device=dev)
+    active = torch.tensor([1 if global_sizes[g] > 0 else 0 for g in range(n_seg)], dtype=torch.int32, device=dev)
+    active_h = active.cpu().numpy().astype(bool)
+    need_final = np.zeros(n_seg, dtype=bool)
+    n_iter = [0] * n_seg
+    strict = [False] * n_seg
+    n_empty_tot = [0] * n_seg
+    seg_first = _seg_first_local(table, n_seg, dev)
+    counts = torch.zeros((n_seg, k), dtype=torch.float32, device=dev)
+    lloyd_iters = 0
+    for it in range(max_iter):
+        n_changed = torch.zeros(n_seg, dtype=torch.int32, device=dev)
+        psums, pcounts = backend.step(x, k, seg_k, cent, table, active, labels, n_changed, True)
+        if reduce == "ordered":
+            sums, cnts = _ordered_reduce(backend, psums, pcounts, table, n_seg, world, group)
+        else:
+            sums = backend.reduce(psums, seg_first, n_seg) if table.n_blocks else torch.zeros_like(cent)
+            cnts = backend.reduce(pcounts, seg_first, n_seg) if table.n_blocks else torch.zeros_like(counts)
+            if distributed:
+                flat = torch.cat([sums.reshape(-1), cnts.reshape(-1), n_changed.to(torch.float32)])
+                allreduce(flat)                                            # the one collective of the iteration
+                sums = flat[:sums.numel()].reshape(sums.shape)
+                cnts = flat[sums.numel():sums.numel() + cnts.numel()].reshape(cnts.shape)
+                n_changed = flat[sums.numel() + cnts.numel():].to(torch.int32)
+        if reduce == "ordered" and distributed:
+            allreduce(n_changed)
+        new_cent, shift, n_empty = backend.update(sums, cnts, cent, seg_k, active)
+        flags = torch.stack([n_changed.to(torch.float64), shift.to(torch.float64), n_empty.to(torch.float64)]).cpu().numpy()
+        cent = new_cent
+        am = active.to(torch.bool)
+        counts = torch.where(am[:, None], cnts, counts)
+        lloyd_iters += 1
+        for g in range(n_seg):
+            if not active_h[g]:
+                continue
+            n_iter[g] = it + 1
+            n_empty_tot[g] += int(flags[2, g])
+            if flags[0, g] == 0:
+                strict[g] = True
+                active_h[g] = False
+            elif flags[1, g] <= tol_abs[g]:
+                active_h[g] = False
+                need_final[g] = True
+        active = torch.from_numpy(active_h.astype(np.int32)).to(dev)
+        if not active_h.any():
+            break
+    need_final |= active_h                                                  # max_iter reached without convergence
+    if need_final.any():                                                    # E-step with the final centres (:742-754)
+        fin = torch.from_numpy(need_final.astype(np.int32)).to(dev)
+        dummy = torch.zeros(n_seg, dtype=torch.int32, device=dev)
+        backend.step(x, k, seg_k, cent, table, fin, labels, dummy, False)
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    timing["lloyd"] = time.perf_counter() - t0
+    timing["lloyd_iters"] = lloyd_iters
+    return KMeansResult(labels=labels, centers=cent + mean[:, None, :], counts=counts, n_iter=n_iter, strict=strict,
+                        n_empty=n_empty_tot, seconds=timing)
+
+
+def _seed_on_host(x, global_sizes, local_off, shard, seg_k_host, k, random_state, backend, group, distributed, world,
+                  seg_off_d):
+    """k-means++ with the scalar decisions in numpy (sklearn's own expressions, host BLAS potentials)."""
+    import torch.distributed as dist
+    dev = x.device
+    n_seg, dim = len(global_sizes), int(x.shape[1])
+
+    def allreduce(t, op=None):
+        if distributed:
+            dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=group)
+        return t
+
     # sklearn: n_local_trials = 2 + int(log(n_clusters)) with the segment's OWN n_clusters = min(k, n)
     trials = [2 + int(np.log(kk)) if kk > 1 else 1 for kk in seg_k_host]
     n_trials = max(trials + [1])
@@ -305,67 +447,92 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
         if x.shape[0]:
             sel = newd[best_d[seg_of_row], torch.arange(x.shape[0], device=dev)]
             closest = torch.where(take[seg_of_row], sel, closest).contiguous()
-    timing["init"] = time.perf_counter() - t0
+    return cent
 
-    # ---- Lloyd iterations (sklearn _kmeans_single_lloyd, _kmeans.py:630-758) ----
-    t0 = time.perf_counter()
-    labels = torch.full((x.shape[0],), -1, dtype=torch.int32, device=dev)
-    active = torch.tensor([1 if global_sizes[g] > 0 else 0 for g in range(n_seg)], dtype=torch.int32, device=dev)
-    active_h = active.cpu().numpy().astype(bool)
-    need_final = np.zeros(n_seg, dtype=bool)
-    n_iter = [0] * n_seg
-    strict = [False] * n_seg
-    n_empty_tot = [0] * n_seg
-    seg_first = _seg_first_local(table, n_seg, dev)
-    counts = torch.zeros((n_seg, k), dtype=torch.float32, device=dev)
-    lloyd_iters = 0
-    for it in range(max_iter):
-        n_changed = torch.zeros(n_seg, dtype=torch.int32, device=dev)
-        psums, pcounts = backend.step(x, k, seg_k, cent, table, active, labels, n_changed, True)
-        if reduce == "ordered":
-            sums, cnts = _ordered_reduce(backend, psums, pcounts, table, n_seg, world, group)
+
+
+def _sklearn_uniform_stream(global_sizes, seg_k_host, k, random_state):
+    """The RandomState draws of `_kmeans_plusplus` do not depend on the data: first centre = rs.choice(n, p=uniform)
+    (_kmeans.py:234), then `rs.uniform(size=n_local_trials)` per further centre (:252).  -> (first [n_seg],
+    uniform [k, n_seg, n_trials] float64, trials [n_seg])."""
+    n_seg = len(global_sizes)
+    trials = [2 + int(np.log(kk)) if kk > 1 else 1 for kk in seg_k_host]
+    n_trials = max(trials + [1])
+    first = np.zeros(n_seg, dtype=np.int64)
+    uni = np.zeros((k, n_seg, n_trials), dtype=np.float64)
+    for g in range(n_seg):
+        if global_sizes[g] <= 0:
+            continue
+        rs = np.random.RandomState(random_state)
+        first[g] = _sklearn_first_center(rs, int(global_sizes[g]))
+        for c in range(1, seg_k_host[g]):
+            uni[c, g, :trials[g]] = rs.uniform(size=trials[g])
+    return first, uni, trials
+
+
+def _seed_on_device(x, global_sizes, local_off, shard, seg_k_host, k, random_state, backend, group, distributed, world):
+    """k-means++ without a host round trip per centre: scan + search, gather, distance pass, pick are stream-ordered
+    kernels (csrc/seed.cu); N > 1 adds an all-gather of the closest distances (the scan is global and sequential, every
+    rank runs it redundantly on the same bits) and all-reduces of the candidate vectors and potentials."""
+    import torch.distributed as dist
+    dev = x.device
+    n_seg, dim = len(global_sizes), int(x.shape[1])
+    first, uni, trials = _sklearn_uniform_stream(global_sizes, seg_k_host, k, random_state)
+    n_trials = uni.shape[2]
+    i64 = lambda a: torch.tensor(np.asarray(a), dtype=torch.int64, device=dev)
+    i32 = lambda a: torch.tensor(np.asarray(a), dtype=torch.int32, device=dev)
+    seg_off_d = i64(list(local_off))
+    shard_first = i64([a for a, _ in shard])
+    uni_d = torch.from_numpy(uni).to(dev)
+    trials_d = i32(trials)
+    one_d = i32([1] * n_seg)
+    seg_on = i32([[1 if (global_sizes[g] > 0 and c < seg_k_host[g]) else 0 for g in range(n_seg)] for c in range(k)])
+    local_sizes = [local_off[g + 1] - local_off[g] for g in range(n_seg)]
+    max_rows = max(local_sizes + [0])
+    max_rows_global = max([int(n) for n in global_sizes] + [0])
+    n_local = int(x.shape[0])
+    if distributed:
+        meta = torch.tensor([n_local] + local_sizes, dtype=torch.int64, device=dev)
+        metas = [torch.empty_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta, group=group)
+        metas = [m.cpu().numpy() for m in metas]
+        max_local = max(int(m[0]) for m in metas)
+        piece_off = i64([[r * max_local + int(metas[r][1:1 + g].sum()) for r in range(world)] for g in range(n_seg)])
+        piece_cnt = i64([[int(metas[r][1 + g]) for r in range(world)] for g in range(n_seg)])
+        gathered = torch.zeros((world, max_local), dtype=torch.float32, device=dev)
+    else:
+        piece_off = i64([[local_off[g]] for g in range(n_seg)])
+        piece_cnt = i64([[local_sizes[g]] for g in range(n_seg)])
+
+    def allreduce(t):
+        if distributed:
+            dist.all_reduce(t, group=group)
+        return t
+
+    cent = torch.zeros((n_seg, k, dim), dtype=torch.float32, device=dev)
+    closest = torch.zeros(n_local, dtype=torch.float32, device=dev)
+    pot = torch.zeros(n_seg, dtype=torch.float32, device=dev)
+    cand_id = i64(first.reshape(n_seg, 1))
+    vec = allreduce(backend.seed_gather(x, cand_id, seg_off_d, shard_first))
+    newd, pots = backend.seed_sqdist(x, seg_off_d, max_rows, vec, None)
+    allreduce(pots)
+    backend.seed_pick(pots, one_d, seg_on[0], seg_off_d, max_rows, newd, vec, closest, pot, cent, 0)
+    cand_id = torch.zeros((n_seg, n_trials), dtype=torch.int64, device=dev)
+    for c in range(1, k):
+        if distributed:
+            pad = torch.zeros(max_local, dtype=torch.float32, device=dev)
+            pad[:n_local] = closest
+            dist.all_gather_into_tensor(gathered, pad, group=group) if dev.type == "cuda" else \
+                dist.all_gather(list(gathered.unbind(0)), pad, group=group)
+            closest_all = gathered
         else:
-            sums = backend.reduce(psums, seg_first, n_seg) if table.n_blocks else torch.zeros_like(cent)
-            cnts = backend.reduce(pcounts, seg_first, n_seg) if table.n_blocks else torch.zeros_like(counts)
-            if distributed:
-                flat = torch.cat([sums.reshape(-1), cnts.reshape(-1), n_changed.to(torch.float32)])
-                allreduce(flat)                                            # the one collective of the iteration
-                sums = flat[:sums.numel()].reshape(sums.shape)
-                cnts = flat[sums.numel():sums.numel() + cnts.numel()].reshape(cnts.shape)
-                n_changed = flat[sums.numel() + cnts.numel():].to(torch.int32)
-        if reduce == "ordered" and distributed:
-            allreduce(n_changed)
-        new_cent, shift, n_empty = backend.update(sums, cnts, cent, seg_k, active)
-        flags = torch.stack([n_changed.to(torch.float64), shift.to(torch.float64), n_empty.to(torch.float64)]).cpu().numpy()
-        cent = new_cent
-        am = active.to(torch.bool)
-        counts = torch.where(am[:, None], cnts, counts)
-        lloyd_iters += 1
-        for g in range(n_seg):
-            if not active_h[g]:
-                continue
-            n_iter[g] = it + 1
-            n_empty_tot[g] += int(flags[2, g])
-            if flags[0, g] == 0:
-                strict[g] = True
-                active_h[g] = False
-            elif flags[1, g] <= tol_abs[g]:
-                active_h[g] = False
-                need_final[g] = True
-        active = torch.from_numpy(active_h.astype(np.int32)).to(dev)
-        if not active_h.any():
-            break
-    need_final |= active_h                                                  # max_iter reached without convergence
-    if need_final.any():                                                    # E-step with the final centres (:742-754)
-        fin = torch.from_numpy(need_final.astype(np.int32)).to(dev)
-        dummy = torch.zeros(n_seg, dtype=torch.int32, device=dev)
-        backend.step(x, k, seg_k, cent, table, fin, labels, dummy, False)
-    if dev.type == "cuda":
-        torch.cuda.synchronize()
-    timing["lloyd"] = time.perf_counter() - t0
-    timing["lloyd_iters"] = lloyd_iters
-    return KMeansResult(labels=labels, centers=cent + mean[:, None, :], counts=counts, n_iter=n_iter, strict=strict,
-                        n_empty=n_empty_tot, seconds=timing)
+            closest_all = closest
+        backend.seed_scan(closest_all, piece_off, piece_cnt, uni_d[c], pot, trials_d, seg_on[c], max_rows_global, cand_id)
+        vec = allreduce(backend.seed_gather(x, cand_id, seg_off_d, shard_first))
+        newd, pots = backend.seed_sqdist(x, seg_off_d, max_rows, vec, closest)
+        allreduce(pots)
+        backend.seed_pick(pots, trials_d, seg_on[c], seg_off_d, max_rows, newd, vec, closest, pot, cent, c)
+    return cent
 
 
 def _seg_first_local(table: BlockTable, n_seg: int, dev) -> torch.Tensor:

@@ -37,6 +37,50 @@ class NumpyBackend:
             pot[g] = d.astype(np.float64).sum(0)
         return torch.from_numpy(out), torch.from_numpy(pot)
 
+    # ---- device seeding stand-ins (csrc/seed.cu) ----
+    supports_device_seeding = True
+
+    def seed_sqdist(self, x, seg_off_d, max_seg_rows, cand, closest):
+        out, pot = self.sqdist_cand(x, seg_off_d, max_seg_rows, cand, closest)
+        return out, pot
+
+    def seed_scan(self, closest_all, piece_off, piece_cnt, uniform, pot, seg_trials, seg_on, max_seg_rows_global, cand_id):
+        flat = closest_all.numpy().reshape(-1)
+        po, pc = piece_off.numpy(), piece_cnt.numpy()
+        u, pt, tr, on, out = uniform.numpy(), pot.numpy(), seg_trials.numpy(), seg_on.numpy(), cand_id.numpy()
+        for g in range(po.shape[0]):
+            if not on[g]:
+                continue
+            cd = np.concatenate([flat[po[g, r]:po[g, r] + pc[g, r]] for r in range(po.shape[1])])
+            if not cd.size:
+                continue
+            vals = u[g, :tr[g]] * pt[g]                                    # float64 * float32 -> float64
+            ids = np.searchsorted(np.cumsum(cd.astype(np.float32)), vals)
+            np.clip(ids, None, cd.size - 1, out=ids)
+            out[g, :tr[g]] = ids
+            out[g, tr[g]:] = ids[0]
+
+    def seed_gather(self, x, cand_id, seg_off_d, shard_first):
+        xs, ids, off, sf = x.numpy(), cand_id.numpy(), seg_off_d.numpy(), shard_first.numpy()
+        vec = np.zeros(ids.shape + (xs.shape[1],), np.float32)
+        for g in range(ids.shape[0]):
+            for j in range(ids.shape[1]):
+                i = ids[g, j] - sf[g]
+                if 0 <= i < off[g + 1] - off[g]:
+                    vec[g, j] = xs[off[g] + i]
+        return torch.from_numpy(vec)
+
+    def seed_pick(self, pots, seg_trials, seg_on, seg_off_d, max_seg_rows, newd, vec, closest, pot, cent, c):
+        ps, tr, on, off = pots.numpy(), seg_trials.numpy(), seg_on.numpy(), seg_off_d.numpy()
+        nd, cl, pt = newd.numpy(), closest.numpy(), pot.numpy()
+        for g in range(ps.shape[0]):
+            if not on[g]:
+                continue
+            best = int(np.argmin(ps[g, :tr[g]].astype(np.float32)))
+            cl[off[g]:off[g + 1]] = nd[best, off[g]:off[g + 1]]
+            pt[g] = np.float32(ps[g, best])
+            cent[g, c] = vec[g, best]
+
     # Lloyd assignment + per-block partial sums (kmeans.cu::kmeans_step_kernel)
     def step(self, x, k, seg_k, cent, blocks, active, labels, n_changed, update):
         xs, dim = x.numpy(), x.shape[1]

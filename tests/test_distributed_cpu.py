@@ -147,3 +147,15 @@ def test_block_table_is_rank_count_invariant():
         tabs = [kmeans.build_blocks(SIZES, world, r, torch.device("cpu"))[0] for r in range(world)]
         assert sum(t.n_super_local for t in tabs) == tabs[0].n_super_global
         assert sum(t.n_blocks for t in tabs) == kmeans.build_blocks(SIZES, 1, 0, torch.device("cpu"))[0].n_blocks
+
+
+def test_device_seeding_control_flow_matches_host_seeding():
+    """seeding="device" (scan + search, gather, distance pass, pick as backend steps; uniforms drawn up front) picks
+    the same seeds as the host loop written with sklearn's expressions, hence identical labels."""
+    be = NumpyBackend()
+    x = torch.from_numpy(np.concatenate(_data()))
+    a = kmeans.kmeans_fit_predict_single(x, SIZES, K, backend=be, seeding="device")
+    b = kmeans.kmeans_fit_predict_single(x, SIZES, K, backend=be, seeding="host")
+    assert a.seconds["seeding"] == "device" and b.seconds["seeding"] == "host"
+    assert np.array_equal(a.labels.numpy(), b.labels.numpy())
+    assert np.allclose(a.centers.numpy(), b.centers.numpy(), rtol=0, atol=1e-6)

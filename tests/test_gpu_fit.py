@@ -132,3 +132,99 @@ def test_kmeans_realistic_overlap_agreement(dev):
     c = res.centers[0].cpu().numpy()
     inertia = ((x - c[lab]) ** 2).sum()
     assert agree > 0.9 and inertia <= km.inertia_ * 1.01
+
+
+def test_seed_scan_is_numpy_cumsum_searchsorted(dev):
+    """The device scan + search == np.searchsorted(np.cumsum(float32), u * pot) bit for bit, segments split into
+    several pieces (ranks), ragged sizes around the 128-value chunk and 4096-value batch boundaries."""
+    from ood_in_object_detection_b200 import kmeans
+    be = kmeans.CudaBackend(dev)
+    rng = np.random.default_rng(11)
+    sizes = [1, 127, 128, 129, 4095, 4096, 4097, 50001, 0, 200000]
+    n_pieces, n_trials = 3, 4
+    segs = [(rng.random(n) ** 4).astype(np.float32) for n in sizes]
+    for s in segs[3:5]:
+        s[::3] = 0.0                                                  # runs of equal cumulative sums
+    # piece layout: piece r of every segment lives in row r of a padded [n_pieces, max_local] buffer
+    cuts = [[(n * r) // n_pieces for r in range(n_pieces + 1)] for n in sizes]
+    local = [sum(c[r + 1] - c[r] for c in cuts) for r in range(n_pieces)]
+    max_local = max(local)
+    buf = np.zeros((n_pieces, max_local), np.float32)
+    piece_off = np.zeros((len(sizes), n_pieces), np.int64)
+    piece_cnt = np.zeros((len(sizes), n_pieces), np.int64)
+    fill = [0] * n_pieces
+    for g, (s, c) in enumerate(zip(segs, cuts)):
+        for r in range(n_pieces):
+            cnt = c[r + 1] - c[r]
+            buf[r, fill[r]:fill[r] + cnt] = s[c[r]:c[r + 1]]
+            piece_off[g, r], piece_cnt[g, r] = r * max_local + fill[r], cnt
+            fill[r] += cnt
+    uni = rng.random((len(sizes), n_trials))
+    uni[1, 0], uni[2, 1] = 0.0, 0.999999999                            # ends of the range
+    trials = np.array([4, 4, 3, 4, 4, 2, 4, 4, 4, 4], np.int32)
+    pot = np.array([np.float32(s.astype(np.float64).sum()) for s in segs], np.float32)
+    pot[7] *= np.float32(1.01)                                         # targets beyond the total -> clipped to n - 1
+    on = np.ones(len(sizes), np.int32)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    cand = torch.full((len(sizes), n_trials), -7, dtype=torch.int64, device=dev)
+    be.seed_scan(t(buf), t(piece_off), t(piece_cnt), t(uni), t(pot), t(trials), t(on), max(sizes), cand)
+    got = cand.cpu().numpy()
+    for g, s in enumerate(segs):
+        if not len(s):
+            continue
+        ids = np.searchsorted(np.cumsum(s), uni[g, :trials[g]] * pot[g])
+        np.clip(ids, None, len(s) - 1, out=ids)
+        assert np.array_equal(got[g, :trials[g]], ids), (g, got[g], ids)
+        assert (got[g, trials[g]:] == ids[0]).all()
+
+
+def test_seed_sqdist_matches_float64_expansion(dev):
+    """Candidate distances: float32(float64 expansion) exactly like sklearn's `_euclidean_distances_upcast`, min
+    against `closest`, bit-reproducible potentials; D = 576 (4 rows per warp) and an odd D (one row per warp)."""
+    from ood_in_object_detection_b200 import kmeans
+    be = kmeans.CudaBackend(dev)
+    rng = np.random.default_rng(12)
+    for dim, sizes in ((576, [3001, 0, 517]), (50, [999, 130])):
+        n = sum(sizes)
+        x = (rng.standard_normal((n, dim)) * 0.3).astype(np.float32)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        cand = (rng.standard_normal((len(sizes), 3, dim)) * 0.3).astype(np.float32)
+        closest = (rng.random(n) * dim * 0.2).astype(np.float32)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        out, pots = be.seed_sqdist(t(x), t(off), max(sizes), t(cand), t(closest))
+        out2, pots2 = be.seed_sqdist(t(x), t(off), max(sizes), t(cand), t(closest))
+        assert torch.equal(pots, pots2) and torch.equal(out, out2)
+        out, pots = out.cpu().numpy(), pots.cpu().numpy()
+        xs = x.astype(np.float64)
+        for g in range(len(sizes)):
+            a, b = off[g], off[g + 1]
+            if a == b:
+                continue
+            y = cand[g].astype(np.float64)
+            ref = (-2.0 * xs[a:b] @ y.T + (y * y).sum(1)[None] + (xs[a:b] ** 2).sum(1)[:, None])
+            ref32 = np.minimum(np.maximum(ref.astype(np.float32), 0), closest[a:b, None])
+            # the float64 sums differ from numpy's in the last bits only: after the cast to float32 at most 1 ulp
+            np.testing.assert_allclose(out[:, a:b].T, ref32, rtol=2e-7, atol=1e-7)
+            assert (out[:, a:b].T != ref32).mean() < 0.01
+            np.testing.assert_allclose(pots[g], ref32.astype(np.float64).sum(0), rtol=1e-6)
+
+
+def test_device_seeding_equals_host_seeding(dev, golden):
+    """seeding="device" picks the seeds of the host loop (sklearn's expressions), hence the same labels: golden call
+    sites of the reference, ragged multi-segment data, and the C3 shape."""
+    from ood_in_object_detection_b200 import kmeans, synth
+    g = golden("golden_kmeans.npz")
+    for tag in "abc":
+        x, k = g[f"{tag}_x"], int(g[f"{tag}_k"])
+        res = kmeans.kmeans_fit_predict_single(torch.from_numpy(x).to(dev), [len(x)], min(k, len(x)), seeding="device")
+        assert res.seconds["seeding"] == "device"
+        assert np.array_equal(res.labels.cpu().numpy(), g[f"{tag}_labels"]), tag
+    for dim, kk, spec in ((48, 8, ((1, 3000), (2, 700), (3, 5), (4, 20000), (5, 0))), (576, 16, ((40, 2500), (41, 1037)))):
+        segs = [synth.blob_vectors(s, n, dim, kk, 7.5)[0] if n else np.zeros((0, dim), np.float32) for s, n in spec]
+        sizes = [len(s) for s in segs]
+        x = torch.from_numpy(np.concatenate(segs)).to(dev)
+        a = kmeans.kmeans_fit_predict_single(x, sizes, kk, seeding="device")
+        b = kmeans.kmeans_fit_predict_single(x, sizes, kk, seeding="host")
+        assert torch.equal(a.labels, b.labels)
+        assert a.n_iter == b.n_iter
+        torch.testing.assert_close(a.centers, b.centers, rtol=0, atol=1e-6)
