@@ -180,17 +180,65 @@ __device__ __forceinline__ double transpose_reduce_f64(double (&v)[32], int lane
     return v[0];
 }
 
+__device__ __forceinline__ uint32_t sd_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sd_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sd_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sd_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sd_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sd_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(sd_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void sd_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(sd_smem_u32(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+
+constexpr int kC4Rows = 32;                                     // rows per TMA chunk: 8 warps x 4 rows
+
+// One CTA owns a contiguous range of 32-row chunks of its segment.  The rows arrive by 1-D TMA bulk copies into a
+// double-buffered landing zone (one copy = one chunk = 72 KB at D = 576), so 72-144 KB are in flight per SM while the
+// warps convert and multiply the previous chunk from shared memory; registers only hold the 32 float64 accumulators.
 template <int NJ>
 __global__ void __launch_bounds__(256, 1) sqdist_cand4_kernel(const Cand4Params p) {
-    extern __shared__ __align__(16) double s_y[];              // [4][dim] candidates in float64, then 4 norms
+    extern __shared__ __align__(128) unsigned char s_raw[];
     const int g = blockIdx.y;
     const int D = p.dim, NC = p.n_cand;
+    float* s_stage = reinterpret_cast<float*>(s_raw);                              // [2][32][D]
+    double* s_y = reinterpret_cast<double*>(s_raw + sizeof(float) * 2 * kC4Rows * D);   // [4][D]
     double* s_yy = s_y + (size_t)4 * D;
+    __shared__ __align__(8) uint64_t s_full[2];
     __shared__ double s_pot[8][4];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t r0 = p.seg_off[g], r1 = p.seg_off[g + 1];
     const int64_t n_rows = p.seg_off[p.n_seg];
-    for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) {
+    const int64_t seg_chunks = (r1 - r0 + kC4Rows - 1) / kC4Rows;
+    const int64_t per_block = (seg_chunks + gridDim.x - 1) / gridDim.x;
+    const int64_t c_first = (int64_t)blockIdx.x * per_block;
+    const int n_chunks = (int)max((int64_t)0, min(per_block, seg_chunks - c_first));
+    const int64_t b0 = r0 + c_first * kC4Rows;                                     // first row of this block
+    auto issue = [&](int c) {
+        const int64_t ra = b0 + (int64_t)c * kC4Rows;
+        const uint32_t bytes = (uint32_t)(min((int64_t)kC4Rows, r1 - ra) * D * 4);
+        sd_mbar_expect_tx(&s_full[c & 1], bytes);
+        sd_bulk_g2s(s_stage + (size_t)(c & 1) * kC4Rows * D, p.x + ra * D, bytes, &s_full[c & 1]);
+    };
+    if (tid == 0) {
+        sd_mbar_init(&s_full[0], 1);
+        sd_mbar_init(&s_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (n_chunks > 0) issue(0);
+        if (n_chunks > 1) issue(1);
+    }
+    for (int i = tid; i < 4 * D; i += blockDim.x) {
         const int j = i / D, d = i - j * D;
         s_y[i] = j < NC ? (double)p.cand[((size_t)g * NC + j) * D + d] : 0.0;
     }
@@ -204,16 +252,10 @@ __global__ void __launch_bounds__(256, 1) sqdist_cand4_kernel(const Cand4Params 
     __syncthreads();
     const int q = lane & 7, rr = lane >> 3;                    // after the butterfly: lane = row rr, quantity q
     double pot = 0.0;
-    for (int64_t base = r0 + ((int64_t)blockIdx.x * 8 + warp) * 4; base < r1; base += (int64_t)gridDim.x * 32) {
-        float4 xv[4][NJ];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int d = lane * 4 + 128 * j;
-                xv[r][j] = (base + r < r1 && d < D) ? __ldg(reinterpret_cast<const float4*>(p.x + (base + r) * D + d))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+    for (int c = 0; c < n_chunks; ++c) {
+        const float* __restrict__ st = s_stage + (size_t)(c & 1) * kC4Rows * D + (size_t)warp * 4 * D;
+        const int64_t base = b0 + (int64_t)c * kC4Rows + warp * 4;
+        sd_mbar_wait(&s_full[c & 1], (uint32_t)(c >> 1) & 1u);
         double acc[32];                                        // [row][8]: 4 candidate dots, ||x||^2, 3 unused
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = 0.0;
@@ -223,22 +265,23 @@ __global__ void __launch_bounds__(256, 1) sqdist_cand4_kernel(const Cand4Params 
             if (d < D) {
                 double2 y01[4], y23[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    y01[c] = *reinterpret_cast<const double2*>(s_y + (size_t)c * D + d);
-                    y23[c] = *reinterpret_cast<const double2*>(s_y + (size_t)c * D + d + 2);
+                for (int cc = 0; cc < 4; ++cc) {
+                    y01[cc] = *reinterpret_cast<const double2*>(s_y + (size_t)cc * D + d);
+                    y23[cc] = *reinterpret_cast<const double2*>(s_y + (size_t)cc * D + d + 2);
                 }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const double a = (double)xv[r][j].x, b = (double)xv[r][j].y, c2 = (double)xv[r][j].z,
-                                 e = (double)xv[r][j].w;
+                    // rows past the end of the segment were not copied: stale data, results discarded below
+                    const float4 xv = *reinterpret_cast<const float4*>(st + (size_t)r * D + d);
+                    const double a = (double)xv.x, b = (double)xv.y, c2 = (double)xv.z, e = (double)xv.w;
                     double xx = acc[r * 8 + 4];
                     xx += a * a; xx += b * b; xx += c2 * c2; xx += e * e;
                     acc[r * 8 + 4] = xx;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        double s = acc[r * 8 + c];
-                        s += a * y01[c].x; s += b * y01[c].y; s += c2 * y23[c].x; s += e * y23[c].y;
-                        acc[r * 8 + c] = s;
+                    for (int cc = 0; cc < 4; ++cc) {
+                        double s = acc[r * 8 + cc];
+                        s += a * y01[cc].x; s += b * y01[cc].y; s += c2 * y23[cc].x; s += e * y23[cc].y;
+                        acc[r * 8 + cc] = s;
                     }
                 }
             }
@@ -256,6 +299,8 @@ __global__ void __launch_bounds__(256, 1) sqdist_cand4_kernel(const Cand4Params 
             p.out_d[(size_t)q * n_rows + r] = d32;
             pot += (double)d32;
         }
+        __syncthreads();                                       // the buffer is free again
+        if (tid == 0 && c + 2 < n_chunks) issue(c + 2);
     }
     // block partial in a fixed order: rows of a lane group, then warps
     pot += shfl_xor_f64(pot, 8);
@@ -401,8 +446,8 @@ __global__ void seed_gather_kernel(const float* __restrict__ x, int dim, const i
 using namespace oodb200;
 
 extern "C" int oodb200_seed_grid(int64_t max_seg_rows) {
-    long long gx = (max_seg_rows + 127) / 128;
-    if (gx > 148 * 4) gx = 148 * 4;
+    long long gx = (max_seg_rows + 255) / 256;
+    if (gx > 148) gx = 148;
     if (gx < 1) gx = 1;
     return (int)gx;
 }
@@ -422,12 +467,12 @@ extern "C" int oodb200_seed_sqdist_f32(const float* x, int dim, const int64_t* s
     const int nj = (dim + 127) / 128;
     const dim3 grid((unsigned)gx, (unsigned)n_seg);
     cudaError_t e = cudaSuccess;
-    if (dim % 4 == 0 && nj <= 6 && ((uintptr_t)x & 15) == 0) {
-#define OODB200_C4_LAUNCH(NJ)                                                                                        \
-    case NJ:                                                                                                         \
-        if (smem > 48 * 1024)                                                                                        \
-            e = cudaFuncSetAttribute(sqdist_cand4_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) sqdist_cand4_kernel<NJ><<<grid, 256, smem, st>>>(p);                                   \
+    const size_t fsmem = sizeof(float) * 2 * kC4Rows * (size_t)dim + smem;
+    if (dim % 4 == 0 && nj <= 6 && ((uintptr_t)x & 15) == 0 && fsmem <= 220 * 1024) {
+#define OODB200_C4_LAUNCH(NJ)                                                                                         \
+    case NJ:                                                                                                          \
+        e = cudaFuncSetAttribute(sqdist_cand4_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);   \
+        if (e == cudaSuccess) sqdist_cand4_kernel<NJ><<<grid, 256, fsmem, st>>>(p);                                   \
         break;
         switch (nj) {
             OODB200_C4_LAUNCH(1) OODB200_C4_LAUNCH(2) OODB200_C4_LAUNCH(3) OODB200_C4_LAUNCH(4)
