@@ -211,6 +211,17 @@ int oodb200_sqdist_cand_f32(const float* x, int dim, const int64_t* seg_off, int
                             const float* cand, int n_cand, const float* closest, float* out_d, double* pot,
                             void* stream);
 
+/* ---- K4 on the tensor pipe: same contract as kmeans_step (update 0 or 1) for k <= 16, dim % 32 == 0,
+ * 128 <= dim <= 576: the x.c cross-term runs on tcgen05 (kind::tf32, split-float hi/lo pieces = float32-level
+ * accuracy), rows arrive once by TMA and stay resident for the partial sums (csrc/kmeans_tc.cu).
+ * kmeans_tc_workspace_bytes: scratch the call needs (0 = shape not supported, use kmeans_step). */
+int64_t oodb200_kmeans_tc_workspace_bytes(int n_seg, int k, int dim);
+int oodb200_kmeans_step_tc_f32(const float* x, int64_t n_rows, int dim, int n_seg, int k, const int32_t* seg_k,
+                               const float* cent, const int32_t* block_seg, const int64_t* block_row0,
+                               const int64_t* block_row1, int n_blocks, const int32_t* active, int32_t* labels,
+                               float* psums, float* pcounts, int32_t* n_changed, int update, void* workspace,
+                               void* stream);
+
 /* ---- K4b: k-means++ seeding on the device (sklearn `_kmeans_plusplus`, sklearn/cluster/_kmeans.py:180-278, behind
  * /root/reference/cluster_utils.py:62-73), every segment in lock-step, no host round trip per centre.
  * seed_sqdist: like sqdist_cand with n_cand <= 4, but the potentials are bit-reproducible: every block writes a

@@ -19,6 +19,7 @@ All tensor arithmetic on N rows happens in the CUDA kernels; torch is used for m
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -46,6 +47,8 @@ class CudaBackend:
         self._lib = _lib
         self.lib = _lib.load()
         self.device = device
+        # OODB200_KMEANS_TC=0 keeps the Lloyd step on the FP32 kernel (A/B runs); default: tcgen05 where the shape fits
+        self.tensor_core = os.environ.get("OODB200_KMEANS_TC", "1") != "0"
 
     def sqdist_cand(self, x, seg_off_d, max_seg_rows, cand, closest):
         n_seg, n_cand = cand.shape[0], cand.shape[1]
@@ -114,6 +117,19 @@ class CudaBackend:
     def step(self, x, k, seg_k, cent, blocks, active, labels, n_changed, update):
         n_blocks = blocks.n_blocks
         psums, pcounts = self._partials(n_blocks, k, x.shape[1], x.device) if update else (None, None)
+        n_seg = int(seg_k.shape[0])
+        ws_bytes = int(self.lib.oodb200_kmeans_tc_workspace_bytes(n_seg, k, x.shape[1])) if self.tensor_core else 0
+        if ws_bytes and update in (0, 1, True, False) and n_blocks and x.data_ptr() % 16 == 0:
+            # tcgen05 path (csrc/kmeans_tc.cu): cross-term on the tensor pipe, rows read once by TMA
+            key = (ws_bytes, str(x.device))
+            if getattr(self, "_wkey", None) != key:
+                self._wbuf = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+                self._wkey = key
+            self._lib.check(self.lib.oodb200_kmeans_step_tc_f32(
+                _ptr(x), int(x.shape[0]), x.shape[1], n_seg, k, _ptr(seg_k), _ptr(cent), _ptr(blocks.seg), _ptr(blocks.row0),
+                _ptr(blocks.row1), n_blocks, _ptr(active), _ptr(labels), _ptr(psums), _ptr(pcounts), _ptr(n_changed),
+                int(update), _ptr(self._wbuf), _stream()), "oodb200_kmeans_step_tc_f32")
+            return psums, pcounts
         self._lib.check(self.lib.oodb200_kmeans_step_f32(
             _ptr(x), x.shape[1], int(seg_k.shape[0]), k, _ptr(seg_k), _ptr(cent), _ptr(blocks.seg), _ptr(blocks.row0),
             _ptr(blocks.row1), n_blocks, _ptr(active), _ptr(labels), _ptr(psums), _ptr(pcounts), _ptr(n_changed),
