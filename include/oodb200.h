@@ -212,8 +212,8 @@ int oodb200_sqdist_cand_f32(const float* x, int dim, const int64_t* seg_off, int
                             void* stream);
 
 /* ---- K4 on the tensor pipe: same contract as kmeans_step (update 0 or 1) for k <= 16, dim % 32 == 0,
- * 128 <= dim <= 576: the x.c cross-term runs on tcgen05 (kind::tf32, split-float hi/lo pieces = float32-level
- * accuracy), rows arrive once by TMA and stay resident for the partial sums (csrc/kmeans_tc.cu).
+ * 128 <= dim <= 640: the x.c cross-term runs on tcgen05 (kind::tf32, split-float hi/lo pieces = float32-level
+ * accuracy) on 128-row tiles streamed by TMA; the partial sums re-read the tile from L2 (csrc/kmeans_tc.cu).
  * kmeans_tc_workspace_bytes: scratch the call needs (0 = shape not supported, use kmeans_step). */
 int64_t oodb200_kmeans_tc_workspace_bytes(int n_seg, int k, int dim);
 int oodb200_kmeans_step_tc_f32(const float* x, int64_t n_rows, int dim, int n_seg, int k, const int32_t* seg_k,

@@ -1,29 +1,32 @@
-// K4 on the tensor pipe: Lloyd assignment with tcgen05 (kind::tf32, split-float "3xTF32") + register partial sums,
-// one pass over X, sm_100a.
+// K4 on the tensor pipe: Lloyd assignment with tcgen05 (kind::tf32, split-float "3xTF32") + register partial sums, sm_100a.
 //
 // Same contract as kmeans_step_fast_kernel (kmeans.cu): replaces sklearn's `lloyd_iter_chunked_dense` behind
 // `KMeans(n_clusters=k, random_state=10).fit_predict(X)` (/root/reference/cluster_utils.py:62-73).  The FP32 kernel
 // needs 2*K*D FFMA-flops per row (18.4 kflop at K = 16, D = 576) and runs at ~20 % of the HBM roofline because the
-// FMA pipe, not memory, bounds it.  Here the x.c cross-term is a [32 rows x D] x [D x 16] contraction on the tensor
-// core, and the CUDA cores only split, compare and accumulate:
+// FMA pipe, not memory, bounds it.  Here the x.c cross-term is a [128 rows x D] x [D x 16] contraction on the tensor
+// core, and the CUDA cores only split, compare and accumulate.  One CTA per block of rows, 128-row tiles:
 //
-//   warp 8 (1 thread)   TMA producer: 2-D tensor-map copies (box 32 rows x 32 floats, SWIZZLE_128B) of a 32-row
-//                       half-tile into a RESIDENT image of the rows [D/32 k-blocks][2 halves][32 rows][128 B];
-//                       two halves ping-pong, so one half streams in while the other is assigned and accumulated.
-//   warps 6-7           split: x_lo = tf32(x - trunc_tf32(x)) per k-block into a 2-stage ring (generic -> async proxy
-//                       fence).  The raw float32 tile is itself the "hi" operand: kind::tf32 ignores the low 13 bits.
-//   warp 9 (1 thread)   MMA issuer: per k-block 4 k-steps x {x_raw.c_hi, x_raw.c_lo, x_lo.c_hi}, M = 128 (rows 0-31 are
-//                       the half-tile, the rest of the M range reads whatever follows and is never looked at), N = 16,
-//                       accumulator in TMEM (16 columns per half); tcgen05.commit frees the ring stage / publishes the tile.
-//   warp 0              epilogue: tcgen05.ld (lane = row), d_k = ||c_k||^2 - 2 x.c_k, first-minimum label, changed count,
-//                       per-cluster row masks by ballot.
-//   warps 1-5           M-step: thread = one 16-byte column chunk; for every cluster (compile-time index) the rows of its
-//                       mask are added from the resident tile in row order into REGISTER accumulators -> block partials
-//                       are bit-reproducible and identical in order to the FP32 kernel's.
+//   warp 9 (1 thread)   TMA producer: 2-D tensor-map copies (box 128 rows x 32 floats = one k-block, SWIZZLE_128B) into a
+//                       3-stage ring.
+//   warps 0-3           split: x_lo = tf32(x - trunc_tf32(x)) of the stage into the lo ring (generic -> async proxy
+//                       fence).  The raw float32 stage is itself the "hi" operand: kind::tf32 ignores the low 13 bits.
+//                       After the last k-block the same warps are the epilogue: tcgen05.ld (lane = row, warp = lane
+//                       quadrant), d_k = ||c_k||^2 - 2 x.c_k, first-minimum label, changed count, per-cluster row masks.
+//   warp 10 (1 thread)  MMA issuer: per k-block 4 k-steps x { x_raw.[c_hi | c_lo] (N = 32), x_lo.c_hi (N = 16) }, M = 128,
+//                       accumulators in TMEM (2 x 32 columns, double buffered across tiles); tcgen05.commit frees the
+//                       ring stage / publishes the tile.
+//   warps 4-8           M-step of the PREVIOUS tile, overlapped with the streaming of the next one: thread = one 16-byte
+//                       column chunk; the rows are re-read from L2 (coalesced LDG.128, 16 in flight per thread; the tile
+//                       was fetched microseconds ago) and added to the cluster's slot of a thread-private [16][D]
+//                       shared-memory accumulator (the label is a run-time index), rows in increasing order -> block
+//                       partials are bit-reproducible and identical in order to the FP32 kernel's.
 // Centroids are pre-split once per iteration (kmeans_tc_prep_kernel) into the exact shared-memory image (hi and lo,
-// K-major SWIZZLE_128B, 16 rows per k-block) and arrive with ONE bulk copy per CTA.
+// K-major SWIZZLE_128B, 32 rows per k-block) and arrive with ONE bulk copy per CTA.
 // Accuracy: x = x_hi + x_lo and c = c_hi + c_lo with 11-bit pieces; the dropped x_lo.c_lo term and the rounding of the
 // lo pieces are ~2^-22 relative per product, i.e. float32-level, accumulated in FP32 in TMEM.
+// History (profiles/r1_summary.md): a resident-tile variant (32-row half-tiles kept in shared memory for the M-step,
+// M = 64) was correct but slower than the FP32 kernel: ~50 cycles per tcgen05.mma regardless of N, so only 128 useful
+// rows per instruction amortise the issue cost, and a 2-stage lo ring made every k-block a ~550-cycle handshake.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -33,11 +36,12 @@
 
 namespace oodb200 {
 
-constexpr int kTcRows = 32;            // rows per half-tile
+constexpr int kTcRows = 128;           // rows per tile = MMA M
 constexpr int kTcThreads = 352;
-constexpr int kTcMaxKb = 18;           // D <= 576
-constexpr int kWEpi = 0, kNEpi = 2, kWAcc0 = 2, kNAcc = 5, kWSplit0 = 7, kNSplit = 2, kWTma = 9, kWMma = 10;
-constexpr int kTcCols = 64;            // TMEM columns: 2 halves x (16 hi + 16 lo)
+constexpr int kTcMaxKb = 20;           // D <= 640 (one 16-byte column chunk per M-step thread)
+constexpr int kTcStages = 3;           // ring depth: 3 x (16 KB raw + 16 KB lo)
+constexpr int kNSplit = 4, kWAcc0 = 4, kNAcc = 5, kWTma = 9, kWMma = 10;
+constexpr int kTcCols = 64;            // TMEM columns: 2 tiles x (16 hi + 16 lo)
 
 struct TcParams {
     int dim, kb;                       // kb = dim / 32
@@ -54,7 +58,8 @@ struct TcParams {
     float* pcounts;
     int32_t* n_changed;
     int update;
-    int debug;                         // tuning only (OODB200_TC_DEBUG): 1 no split work, 2 no MMA, 4 no accumulation, 8 one k-block of MMA per half
+    int debug;                         // tuning only (OODB200_TC_DEBUG): 1 no split work, 2 no MMA, 4 no accumulation
+    const float* x;
 };
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,10 +109,9 @@ __device__ __forceinline__ uint32_t tf32_rna(float v) {
 __device__ __forceinline__ uint64_t tc_desc(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: D = F32, A = B = TF32, K-major both, M = 64 (rows 0-15 -> TMEM lanes 0-15, rows 16-31 -> lanes
-// 32-47: the "half subpartition" accumulator layout of cta_group::1), N = 32 (c_hi | c_lo) or 16 (c_hi)
-constexpr uint32_t kTcIdescN32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((64u >> 4) << 24);
-constexpr uint32_t kTcIdescN16 = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((64u >> 4) << 24);
+// instruction descriptor: D = F32, A = B = TF32, K-major both, M = 128 (row i -> TMEM lane i), N = 32 (c_hi | c_lo) or 16 (c_hi)
+constexpr uint32_t kTcIdescN32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kTcIdescN16 = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -122,9 +126,10 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 
 __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     extern __shared__ unsigned char tc_dyn[];
-    __shared__ __align__(8) uint64_t s_full[2][kTcMaxKb];
-    __shared__ __align__(8) uint64_t s_xfree[2], s_lofull[2], s_lofree[2], s_accfull[2], s_labready[2], s_bfull;
-    __shared__ unsigned s_mask[2][kNEpi][16];               // [half][epilogue warp][cluster]: 16 rows each
+    __shared__ __align__(8) uint64_t s_afull[kTcStages], s_lofull[kTcStages], s_sfree[kTcStages];
+    __shared__ __align__(8) uint64_t s_accfull[2], s_labready[2], s_mdone[2], s_bfull;
+    __shared__ unsigned s_mask[2][4][16];                   // [tile parity][32-row group][cluster] (counts)
+    __shared__ __align__(16) unsigned char s_lab[2][kTcRows];             // label of every row of the tile, 255 = past the block
     __shared__ float s_csn[16];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -134,24 +139,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
     const int D = p.dim, KB = p.kb;
     const int Kg = p.seg_k[g];
     const int64_t r0 = p.block_row0[b], r1 = p.block_row1[b];
-    const int n_half = (int)((r1 - r0 + kTcRows - 1) / kTcRows);
-    const uint32_t x_base = (tc_smem_u32(tc_dyn) + 1023u) & ~1023u;          // [KB][2][32 rows][128 B]
-    const uint32_t lo_base = x_base + (uint32_t)KB * 8192u;                    // [2][32 rows][128 B]
-    const uint32_t b_base = lo_base + 8192u;                                    // [KB][32 rows: c_hi, c_lo][128 B]
+    const int n_tiles = (int)((r1 - r0 + kTcRows - 1) / kTcRows);
+    const uint32_t x_base = (tc_smem_u32(tc_dyn) + 1023u) & ~1023u;          // [stage][128 rows][128 B]
+    const uint32_t lo_base = x_base + kTcStages * 16384u;                      // [stage][128 rows][128 B]
+    const uint32_t b_base = lo_base + kTcStages * 16384u;                      // [KB][32 rows: c_hi, c_lo][128 B]
+    const uint32_t acc_base = b_base + (uint32_t)KB * 4096u;                    // [16][D] float32 partial sums
 
     if (tid == 0) {
-        for (int h = 0; h < 2; ++h) {
-            for (int kb = 0; kb < KB; ++kb) tc_mbar_init(&s_full[h][kb], 1);
-            tc_mbar_init(&s_xfree[h], kNAcc);
-            tc_mbar_init(&s_lofull[h], kNSplit);
-            tc_mbar_init(&s_lofree[h], 1);
-            tc_mbar_init(&s_accfull[h], 1);
-            tc_mbar_init(&s_labready[h], kNEpi);
+        for (int s = 0; s < kTcStages; ++s) {
+            tc_mbar_init(&s_afull[s], 1);
+            tc_mbar_init(&s_lofull[s], kNSplit);
+            tc_mbar_init(&s_sfree[s], 1);
+        }
+        for (int e = 0; e < 2; ++e) {
+            tc_mbar_init(&s_accfull[e], 1);
+            tc_mbar_init(&s_labready[e], kNSplit);
+            tc_mbar_init(&s_mdone[e], kNAcc);
         }
         tc_mbar_init(&s_bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kWEpi) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "r"(kTcCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -166,13 +174,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
             const uint32_t b_bytes = (uint32_t)KB * 4096u;
             tc_mbar_expect_tx(&s_bfull, b_bytes);
             tc_bulk_g2s(b_base, p.bimg + (size_t)g * KB * 1024, b_bytes, &s_bfull);
-            for (int i = 0; i < n_half; ++i) {
-                const int h = i & 1, j = i >> 1;
-                if (j >= 1) tc_mbar_wait(&s_xfree[h], (uint32_t)(j - 1) & 1u);
-                const int row = (int)(r0 + (int64_t)i * kTcRows);
-                for (int kb = 0; kb < KB; ++kb) {
-                    tc_mbar_expect_tx(&s_full[h][kb], 4096u);
-                    tc_tma_2d(x_base + (uint32_t)kb * 8192u + (uint32_t)h * 4096u, &tmap, kb * 32, row, &s_full[h][kb]);
+            uint32_t n = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int row = (int)(r0 + (int64_t)t * kTcRows);
+                for (int kb = 0; kb < KB; ++kb, ++n) {
+                    const uint32_t s = n % kTcStages, u = n / kTcStages;
+                    if (u >= 1) tc_mbar_wait(&s_sfree[s], (u - 1) & 1u);
+                    tc_mbar_expect_tx(&s_afull[s], 16384u);
+                    tc_tma_2d(x_base + s * 16384u, &tmap, kb * 32, row, &s_afull[s]);
                 }
             }
         }
@@ -180,18 +189,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
         if (lane == 0) {
             tc_mbar_wait(&s_bfull, 0);
             uint32_t n = 0;
-            for (int i = 0; i < n_half; ++i) {
-                const int h = i & 1, j = i >> 1;
-                const uint32_t acc = tmem + (uint32_t)h * 32u;
+            for (int t = 0; t < n_tiles; ++t) {
+                const uint32_t acc = tmem + (uint32_t)(t & 1) * 32u;
                 for (int kb = 0; kb < KB; ++kb, ++n) {
-                    const uint32_t s = n & 1u, u = n >> 1;
-                    tc_mbar_wait(&s_full[h][kb], (uint32_t)j & 1u);
+                    const uint32_t s = n % kTcStages, u = n / kTcStages;
+                    tc_mbar_wait(&s_afull[s], u & 1u);
                     tc_mbar_wait(&s_lofull[s], u & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_raw = x_base + (uint32_t)kb * 8192u + (uint32_t)h * 4096u;
-                    const uint32_t a_lo = lo_base + s * 4096u;
+                    const uint32_t a_raw = x_base + s * 16384u, a_lo = lo_base + s * 16384u;
                     const uint32_t b_img = b_base + (uint32_t)kb * 4096u;       // rows 0-15 c_hi, rows 16-31 c_lo
-                    if (!(p.debug & 2) && !((p.debug & 8) && kb > 0))
+                    if (!(p.debug & 2))
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {                            // UMMA_K = 8 floats = 32 B inside the 128 B row
                         const uint64_t dar = tc_desc(a_raw + k4 * 32), dal = tc_desc(a_lo + k4 * 32);
@@ -199,54 +206,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
                         tc_mma(acc, dar, db, kTcIdescN32, (kb | k4) != 0);      // cols 0-15 += x.c_hi, cols 16-31 += x.c_lo
                         tc_mma(acc, dal, db, kTcIdescN16, 1u);                  // cols 0-15 += x_lo.c_hi
                     }
-                    tc_commit(&s_lofree[s]);
-                    if (kb == KB - 1) tc_commit(&s_accfull[h]);
+                    tc_commit(&s_sfree[s]);
+                    if (kb == KB - 1) tc_commit(&s_accfull[t & 1]);
                 }
             }
         }
-    } else if (warp >= kWSplit0 && warp < kWSplit0 + kNSplit) {
-        const int w2 = warp - kWSplit0;
+    } else if (warp < kNSplit) {                                                // split, then epilogue of rows 32*warp ..
+        int changed = 0;
         uint32_t n = 0;
-        for (int i = 0; i < n_half; ++i) {
-            const int h = i & 1, j = i >> 1;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int e = t & 1, j = t >> 1;
             for (int kb = 0; kb < KB; ++kb, ++n) {
-                const uint32_t s = n & 1u, u = n >> 1;
-                tc_mbar_wait(&s_full[h][kb], (uint32_t)j & 1u);
-                if (u >= 1) tc_mbar_wait(&s_lofree[s], (u - 1) & 1u);
-                const uint32_t src = x_base + (uint32_t)kb * 8192u + (uint32_t)h * 4096u;
-                const uint32_t dst = lo_base + s * 4096u;
-                float4 v[4];
+                const uint32_t s = n % kTcStages, u = n / kTcStages;
+                tc_mbar_wait(&s_afull[s], u & 1u);      // the producer reloaded stage s only after the MMAs that read lo[s] committed
                 if (p.debug & 1) { __syncwarp(); if (lane == 0) tc_mbar_arrive(&s_lofull[s]); continue; }
+                const uint32_t src = x_base + s * 16384u + (uint32_t)warp * 4096u;
+                const uint32_t dst = lo_base + s * 16384u + (uint32_t)warp * 4096u;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t off = (uint32_t)(w2 * 128 + q * 32 + lane) * 16u;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w) : "r"(src + off));
-                }
+                for (int half = 0; half < 2; ++half) {
+                    float4 v[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t off = (uint32_t)(w2 * 128 + q * 32 + lane) * 16u;
-                    uint32_t o[4];
-                    const float e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float hi = __uint_as_float(__float_as_uint(e[c]) & 0xffffe000u);   // what kind::tf32 reads
-                        o[c] = tf32_rna(e[c] - hi);
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t off = (uint32_t)((half * 4 + q) * 32 + lane) * 16u;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w) : "r"(src + off));
                     }
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t off = (uint32_t)((half * 4 + q) * 32 + lane) * 16u;
+                        uint32_t o[4];
+                        const float el[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float hi = __uint_as_float(__float_as_uint(el[c]) & 0xffffe000u);   // what kind::tf32 reads
+                            o[c] = tf32_rna(el[c] - hi);
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(&s_lofull[s]);
             }
-        }
-    } else if (warp < kWEpi + kNEpi) {                                          // warp w: rows 16w .. 16w+15 = TMEM lanes 32w + (0..15)
-        int changed = 0;
-        for (int i = 0; i < n_half; ++i) {
-            const int h = i & 1, j = i >> 1;
-            tc_mbar_wait(&s_accfull[h], (uint32_t)j & 1u);
+            // ---- epilogue of tile t: TMEM lanes 32*warp .. +31 = rows of this warp
+            tc_mbar_wait(&s_accfull[e], (uint32_t)j & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t d[16], e[16];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)h * 32u;
+            uint32_t d[16], f[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)e * 32u;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]),
@@ -254,90 +259,106 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
                 : "r"(taddr));
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7]), "=r"(e[8]),
-                  "=r"(e[9]), "=r"(e[10]), "=r"(e[11]), "=r"(e[12]), "=r"(e[13]), "=r"(e[14]), "=r"(e[15])
+                : "=r"(f[0]), "=r"(f[1]), "=r"(f[2]), "=r"(f[3]), "=r"(f[4]), "=r"(f[5]), "=r"(f[6]), "=r"(f[7]), "=r"(f[8]),
+                  "=r"(f[9]), "=r"(f[10]), "=r"(f[11]), "=r"(f[12]), "=r"(f[13]), "=r"(f[14]), "=r"(f[15])
                 : "r"(taddr + 16u));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             float best = FLT_MAX;
             int lab = 0;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const float dot = __uint_as_float(d[k]) + __uint_as_float(e[k]);                    // x.c_hi + x_lo.c_hi, then + x.c_lo
+                const float dot = __uint_as_float(d[k]) + __uint_as_float(f[k]);                    // (x.c_hi + x_lo.c_hi) + x.c_lo
                 const float pd = k < Kg ? fmaf(-2.0f, dot, s_csn[k]) : FLT_MAX;                      // gemm(alpha=-2, beta=1) on ||c||^2
                 if (pd < best) { best = pd; lab = k; }                                              // strict <: first minimum
             }
-            const int64_t row = r0 + (int64_t)i * kTcRows + warp * 16 + lane;
-            const bool valid = lane < 16 && row < r1;
+            const int64_t row = r0 + (int64_t)t * kTcRows + warp * 32 + lane;
+            const bool valid = row < r1;
             if (valid) {
                 if (p.labels[row] != lab) ++changed;
                 p.labels[row] = lab;
             }
+            if (j >= 1) tc_mbar_wait(&s_mdone[e], (uint32_t)(j - 1) & 1u);      // the M-step of tile t-2 has consumed these masks
+            s_lab[e][warp * 32 + lane] = valid ? (unsigned char)lab : (unsigned char)255;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const unsigned m = __ballot_sync(0xffffffffu, valid && lab == k);
-                if (lane == k) s_mask[h][warp][k] = m;
+                if (lane == k) s_mask[e][warp][k] = m;
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) tc_mbar_arrive(&s_labready[h]);
+            if (lane == 0) tc_mbar_arrive(&s_labready[e]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
         if (lane == 0 && changed) atomicAdd(&p.n_changed[g], changed);
-    } else {                                                                    // warps 2-6: M-step
-        const int t = tid - kWAcc0 * 32;                                        // 0..159: one 16-byte column chunk each
-        const bool have = t < D / 4;
-        const int kbc = t >> 3, cc = t & 7;
-        float4 acc[16];
+    } else {                                                                    // warps 4-8: M-step of the finished tile
+        const int c = tid - kWAcc0 * 32;                                        // 0..159: one 16-byte column chunk each
+        const bool have = c < D / 4;
+        // per-cluster sums of this thread's 4 columns live in shared memory (dynamic label index), private to the thread
+        float4* __restrict__ accp = reinterpret_cast<float4*>(tc_dyn + (acc_base - tc_smem_u32(tc_dyn))) + c;
+        const int row_f4 = D / 4;
+        if (have)
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < 16; ++k) accp[k * row_f4] = make_float4(0.f, 0.f, 0.f, 0.f);
         float cnt = 0.f;
-        for (int i = 0; i < n_half; ++i) {
-            const int h = i & 1, j = i >> 1;
-            tc_mbar_wait(&s_labready[h], (uint32_t)j & 1u);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int e = t & 1, j = t >> 1;
+            tc_mbar_wait(&s_labready[e], (uint32_t)j & 1u);
             if (p.update && !(p.debug & 4)) {
-                if (have) tc_mbar_wait(&s_full[h][kbc], (uint32_t)j & 1u);     // completed long ago: acquires the TMA writes
-                const uint32_t rowbase = x_base + (uint32_t)kbc * 8192u + (uint32_t)h * 4096u;
+                const float* __restrict__ xt = p.x + (size_t)(r0 + (int64_t)t * kTcRows) * D + c * 4;
+                if (c < 16) {
+                    unsigned tot = 0;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    unsigned m = s_mask[h][0][k] | (s_mask[h][1][k] << 16);
-                    if (t == k) cnt += (float)__popc(m);
-                    if (have) {
-                        while (m) {                                             // rows of cluster k in row order, two loads in flight
-                            const int ra = __ffs(m) - 1;
-                            m &= m - 1;
-                            const int rb = m ? __ffs(m) - 1 : -1;
-                            m &= m - 1;                                         // 0 & anything stays 0
-                            float4 va, vb = make_float4(0.f, 0.f, 0.f, 0.f);
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(va.x), "=f"(va.y), "=f"(va.z), "=f"(va.w)
-                                         : "r"(rowbase + (uint32_t)ra * 128u + (uint32_t)((cc ^ (ra & 7)) << 4)));
-                            if (rb >= 0)
-                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                             : "=f"(vb.x), "=f"(vb.y), "=f"(vb.z), "=f"(vb.w)
-                                             : "r"(rowbase + (uint32_t)rb * 128u + (uint32_t)((cc ^ (rb & 7)) << 4)));
-                            acc[k].x += va.x; acc[k].y += va.y; acc[k].z += va.z; acc[k].w += va.w;
-                            if (rb >= 0) { acc[k].x += vb.x; acc[k].y += vb.y; acc[k].z += vb.z; acc[k].w += vb.w; }
+                    for (int w = 0; w < 4; ++w) tot += __popc(s_mask[e][w][c]);
+                    cnt += (float)tot;
+                }
+                // 16 rows in flight per thread (coalesced LDG.128 from L2: the tile was fetched microseconds ago), then a
+                // read-modify-write of the cluster's slot, rows in increasing order -> same sums as the FP32 kernel
+                auto load16 = [&](int i0, float4 (&v)[16], unsigned (&lws)[4]) {
+                    const uint4 lw = *reinterpret_cast<const uint4*>(&s_lab[e][i0]);
+                    lws[0] = lw.x; lws[1] = lw.y; lws[2] = lw.z; lws[3] = lw.w;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const unsigned l = (lws[q >> 2] >> ((q & 3) * 8)) & 255u;
+                        v[q] = (l < 16u && have) ? __ldcg(reinterpret_cast<const float4*>(xt + (size_t)(i0 + q) * D))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                };
+                auto add16 = [&](const float4 (&v)[16], const unsigned (&lws)[4]) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const unsigned l = (lws[q >> 2] >> ((q & 3) * 8)) & 255u;
+                        if (l < 16u && have) {
+                            float4 a = accp[l * row_f4];
+                            a.x += v[q].x; a.y += v[q].y; a.z += v[q].z; a.w += v[q].w;
+                            accp[l * row_f4] = a;
                         }
                     }
+                };
+                float4 va[16], vb[16];
+                unsigned la[4], lb[4];
+                load16(0, va, la);
+#pragma unroll 1
+                for (int i0 = 0; i0 < kTcRows; i0 += 32) {                     // the next 16 rows are in flight while 16 are added
+                    load16(i0 + 16, vb, lb);
+                    add16(va, la);
+                    if (i0 + 32 < kTcRows) load16(i0 + 32, va, la);
+                    add16(vb, lb);
                 }
             }
             __syncwarp();
-            if (lane == 0) tc_mbar_arrive(&s_xfree[h]);
+            if (lane == 0) tc_mbar_arrive(&s_mdone[e]);
         }
         if (p.update) {
             float* __restrict__ ps = p.psums + (size_t)b * p.k * D;
-            if (have) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (k < p.k) *reinterpret_cast<float4*>(ps + (size_t)k * D + t * 4) = acc[k];
-            }
-            if (t < p.k) p.pcounts[(size_t)b * p.k + t] = cnt;
+            if (have)
+                for (int k = 0; k < p.k; ++k) *reinterpret_cast<float4*>(ps + (size_t)k * D + c * 4) = accp[k * row_f4];
+            if (c < p.k) p.pcounts[(size_t)b * p.k + c] = cnt;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == kWEpi) {
+    if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcCols) : "memory");
     }
@@ -390,7 +411,7 @@ static TcEncodeFn tc_encode_fn() {
     return fn;
 }
 
-static size_t tc_smem_bytes(int dim) { return (size_t)(dim / 32) * (8192 + 4096) + 8192 + 1024; }
+static size_t tc_smem_bytes(int dim) { return (size_t)(dim / 32) * 4096 + (size_t)kTcStages * 32768 + (size_t)64 * dim + 1024; }
 
 }  // namespace oodb200
 
@@ -407,7 +428,7 @@ extern "C" int oodb200_kmeans_step_tc_f32(const float* x, int64_t n_rows, int di
                                           float* psums, float* pcounts, int32_t* n_changed, int update, void* workspace,
                                           void* stream) {
     OODB200_REQUIRE(oodb200_kmeans_tc_workspace_bytes(n_seg > 0 ? n_seg : 1, k, dim) > 0,
-                    "kmeans_step_tc: needs k <= 16 and dim %% 32 == 0, 128 <= dim <= 576 (k = %d, dim = %d)", k, dim);
+                    "kmeans_step_tc: needs k <= 16 and dim %% 32 == 0, 128 <= dim <= 640 (k = %d, dim = %d)", k, dim);
     OODB200_REQUIRE(update == 0 || update == 1, "kmeans_step_tc: update must be 0 or 1");
     OODB200_REQUIRE(n_rows > 0 && n_rows < INT_MAX && n_blocks >= 0, "kmeans_step_tc: bad size");
     if (n_blocks == 0) return OODB200_OK;
@@ -421,7 +442,7 @@ extern "C" int oodb200_kmeans_step_tc_f32(const float* x, int64_t n_rows, int di
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n_rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)dim * 4};
-    const cuuint32_t box[2] = {32, (cuuint32_t)kTcRows};
+    const cuuint32_t box[2] = {32, (cuuint32_t)kTcRows};   // one k-block of a 128-row tile
     const cuuint32_t estride[2] = {1, 1};
     CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstride, box, estride,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -438,7 +459,7 @@ extern "C" int oodb200_kmeans_step_tc_f32(const float* x, int64_t n_rows, int di
     if (e != cudaSuccess) { set_error("kmeans_step_tc: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
     const char* dbg = getenv("OODB200_TC_DEBUG");
     TcParams p = {dim, KB, k, seg_k, bimg, csn, block_seg, block_row0, block_row1, active, labels, psums, pcounts, n_changed, update,
-                  dbg ? atoi(dbg) : 0};
+                  dbg ? atoi(dbg) : 0, x};
     kmeans_step_tc_kernel<<<n_blocks, kTcThreads, smem, st>>>(tmap, p);
     return check_launch("kmeans_step_tc");
 }

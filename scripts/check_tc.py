@@ -20,7 +20,7 @@ def run(be, x, sizes, k, cent, update=1):
 
 ok = True
 for dim, k, spec in ((576, 16, ((1, 5000), (2, 777), (3, 33), (4, 0), (5, 1500))), (128, 5, ((6, 2000), (7, 1029))),
-                     (256, 16, ((8, 4100),))):
+                     (256, 16, ((8, 4100),)), (640, 12, ((9, 1300), (10, 64)))):
     segs = [synth.blob_vectors(s, n, dim, k, 3.0)[0] if n else np.zeros((0, dim), np.float32) for s, n in spec]
     sizes = [len(s) for s in segs]
     x = torch.from_numpy(np.concatenate(segs)).to(dev)

@@ -4,7 +4,7 @@ import torch
 from ood_in_object_detection_b200 import kmeans
 dev = torch.device("cuda:0")
 be = kmeans.CudaBackend(dev)
-n_seg, per, dim, k = 20, 200000, 576, 16
+n_seg, per, dim, k = 20, int(sys.argv[1]) if len(sys.argv) > 1 else 200000, 576, 16
 x = torch.randn(n_seg * per, dim, device=dev) * 0.05
 sizes = [per] * n_seg
 cent = torch.randn(n_seg, k, dim, device=dev) * 0.05
@@ -12,13 +12,7 @@ table, _, _ = kmeans.build_blocks(sizes, 1, 0, dev)
 seg_k = torch.full((n_seg,), k, dtype=torch.int32, device=dev)
 labels = torch.full((x.shape[0],), -1, dtype=torch.int32, device=dev)
 chg = torch.zeros(n_seg, dtype=torch.int32, device=dev)
-for dbg in (0, 3, 4):
-    os.environ["OODB200_TC_DEBUG"] = str(dbg)
-    be.step(x, k, seg_k, cent, table, None, labels, chg, 1); torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(3):
-        be.step(x, k, seg_k, cent, table, None, labels, chg, 1)
-    b.record(); torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 3
-    print(f"debug={dbg:2d} (1 nosplit, 2 nomma, 4 noacc, 8 mma kb0 only): {ms:.3f} ms  {x.numel() * 4 / ms / 1e6:.0f} GB/s")
+for _ in range(2):
+    be.step(x, k, seg_k, cent, table, None, labels, chg, 1)
+torch.cuda.synchronize()
+print("ok")
