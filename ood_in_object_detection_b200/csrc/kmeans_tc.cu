@@ -7,7 +7,7 @@
 // core, and the CUDA cores only split, compare and accumulate.  One CTA per block of rows, 128-row tiles:
 //
 //   warp 9 (1 thread)   TMA producer: 2-D tensor-map copies (box 128 rows x 32 floats = one k-block, SWIZZLE_128B) into a
-//                       3-stage ring.
+//                       ring (5 stages at D = 576).
 //   warps 0-3           split: x_lo = tf32(x - trunc_tf32(x)) of the stage into the lo ring (generic -> async proxy
 //                       fence).  The raw float32 stage is itself the "hi" operand: kind::tf32 ignores the low 13 bits.
 //                       After the last k-block the same warps are the epilogue: tcgen05.ld (lane = row, warp = lane
@@ -39,7 +39,8 @@ namespace oodb200 {
 constexpr int kTcRows = 128;           // rows per tile = MMA M
 constexpr int kTcThreads = 352;
 constexpr int kTcMaxKb = 20;           // D <= 640 (one 16-byte column chunk per M-step thread)
-constexpr int kTcStages = 3;           // ring depth: 3 x (16 KB raw + 16 KB lo)
+constexpr int kTcMaxXs = 6;            // raw ring: up to 6 x 16 KB (as many as shared memory allows: HBM latency)
+constexpr int kTcMaxLs = 4;             // lo ring: up to 4 x 16 KB
 constexpr int kNSplit = 4, kWAcc0 = 4, kNAcc = 5, kWTma = 9, kWMma = 10;
 constexpr int kTcCols = 64;            // TMEM columns: 2 tiles x (16 hi + 16 lo)
 
@@ -95,9 +96,9 @@ __device__ __forceinline__ void tc_bulk_g2s(uint32_t dst, const void* src, uint3
                  "r"(bytes), "r"(tc_smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-                 "l"(map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1)
+__device__ __forceinline__ void tc_tma_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+                 "l"(map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ uint32_t tf32_rna(float v) {
@@ -105,9 +106,11 @@ __device__ __forceinline__ uint32_t tf32_rna(float v) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return r;
 }
-// shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups of 1024 B (SBO), LBO = 1 (unused), version 1
+// shared-memory matrix descriptor, K-major, SWIZZLE_32B: a row is ONE k-step (8 floats = 32 B), 8-row groups of 256 B
+// (SBO), LBO = 1 (unused), version 1.  With 128-byte rows every tcgen05.mma fetched the whole 128-byte row of all M rows
+// to use 32 bytes of it (~170 cycles per instruction at N <= 32); 32-byte rows make the operand fetch 4x smaller.
 __device__ __forceinline__ uint64_t tc_desc(uint32_t addr) {
-    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
 }
 // instruction descriptor: D = F32, A = B = TF32, K-major both, M = 128 (row i -> TMEM lane i), N = 32 (c_hi | c_lo) or 16 (c_hi)
 constexpr uint32_t kTcIdescN32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
@@ -120,13 +123,22 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t da, uint64_t db
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a CONVERGED warp.  The single-thread instructions (TMA, tcgen05.mma, tcgen05.commit) take their operands
+// from uniform registers: under `if (lane == 0)` the compiler wraps every one of them in an ELECT / BRA.U.ANY loop
+// (~40 issue slots per MMA, measured); with warp-uniform control flow + elect they are issued directly.
+__device__ __forceinline__ bool tc_elect() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
 
+template <int XS_, int LS_>
 __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     extern __shared__ unsigned char tc_dyn[];
-    __shared__ __align__(8) uint64_t s_afull[kTcStages], s_lofull[kTcStages], s_sfree[kTcStages];
+    __shared__ __align__(8) uint64_t s_afull[kTcMaxXs], s_done[kTcMaxXs], s_lofull[kTcMaxLs];   // s_done[n % XS]: the MMAs of k-block n have completed
     __shared__ __align__(8) uint64_t s_accfull[2], s_labready[2], s_mdone[2], s_bfull;
     __shared__ unsigned s_mask[2][4][16];                   // [tile parity][32-row group][cluster] (counts)
     __shared__ __align__(16) unsigned char s_lab[2][kTcRows];             // label of every row of the tile, 255 = past the block
@@ -140,17 +152,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
     const int Kg = p.seg_k[g];
     const int64_t r0 = p.block_row0[b], r1 = p.block_row1[b];
     const int n_tiles = (int)((r1 - r0 + kTcRows - 1) / kTcRows);
-    const uint32_t x_base = (tc_smem_u32(tc_dyn) + 1023u) & ~1023u;          // [stage][128 rows][128 B]
-    const uint32_t lo_base = x_base + kTcStages * 16384u;                      // [stage][128 rows][128 B]
-    const uint32_t b_base = lo_base + kTcStages * 16384u;                      // [KB][32 rows: c_hi, c_lo][128 B]
+    constexpr uint32_t XS = XS_, LS = LS_;                  // raw ring / lo ring depth
+    const uint32_t x_base = (tc_smem_u32(tc_dyn) + 1023u) & ~1023u;          // [XS][4 k-steps][128 rows][32 B]
+    const uint32_t lo_base = x_base + XS * 16384u;                             // [LS][4 k-steps][128 rows][32 B]
+    const uint32_t b_base = lo_base + LS * 16384u;                    // [KB][4 k-steps][32 rows: c_hi, c_lo][32 B]
     const uint32_t acc_base = b_base + (uint32_t)KB * 4096u;                    // [16][D] float32 partial sums
 
     if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) {
+        for (int s = 0; s < kTcMaxXs; ++s) {
             tc_mbar_init(&s_afull[s], 1);
-            tc_mbar_init(&s_lofull[s], kNSplit);
-            tc_mbar_init(&s_sfree[s], 1);
+            tc_mbar_init(&s_done[s], 1);
         }
+        for (int s = 0; s < kTcMaxLs; ++s) tc_mbar_init(&s_lofull[s], kNSplit);
         for (int e = 0; e < 2; ++e) {
             tc_mbar_init(&s_accfull[e], 1);
             tc_mbar_init(&s_labready[e], kNSplit);
@@ -169,45 +182,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
-    if (warp == kWTma) {
-        if (lane == 0) {
-            const uint32_t b_bytes = (uint32_t)KB * 4096u;
+    if (warp == kWTma) {                                                        // whole warp in the loop, one elected lane issues
+        const uint32_t b_bytes = (uint32_t)KB * 4096u;
+        if (tc_elect()) {
             tc_mbar_expect_tx(&s_bfull, b_bytes);
             tc_bulk_g2s(b_base, p.bimg + (size_t)g * KB * 1024, b_bytes, &s_bfull);
-            uint32_t n = 0;
-            for (int t = 0; t < n_tiles; ++t) {
-                const int row = (int)(r0 + (int64_t)t * kTcRows);
-                for (int kb = 0; kb < KB; ++kb, ++n) {
-                    const uint32_t s = n % kTcStages, u = n / kTcStages;
-                    if (u >= 1) tc_mbar_wait(&s_sfree[s], (u - 1) & 1u);
+        }
+        uint64_t pol_last;                                                      // the tile is read again by the M-step: keep it in L2
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+        uint32_t n = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int row = (int)(r0 + (int64_t)t * kTcRows);
+            for (int kb = 0; kb < KB; ++kb, ++n) {
+                const uint32_t s = n % XS, u = n / XS;
+                if (u >= 1) tc_mbar_wait(&s_done[s], (u - 1) & 1u);           // MMAs of k-block n - XS done: the stage is free
+                if (tc_elect()) {
                     tc_mbar_expect_tx(&s_afull[s], 16384u);
-                    tc_tma_2d(x_base + s * 16384u, &tmap, kb * 32, row, &s_afull[s]);
+                    tc_tma_3d(x_base + s * 16384u, &tmap, 0, row, kb * 4, &s_afull[s], pol_last);
                 }
             }
         }
+        __syncwarp();
     } else if (warp == kWMma) {
-        if (lane == 0) {
+        {
             tc_mbar_wait(&s_bfull, 0);
             uint32_t n = 0;
             for (int t = 0; t < n_tiles; ++t) {
                 const uint32_t acc = tmem + (uint32_t)(t & 1) * 32u;
                 for (int kb = 0; kb < KB; ++kb, ++n) {
-                    const uint32_t s = n % kTcStages, u = n / kTcStages;
-                    tc_mbar_wait(&s_afull[s], u & 1u);
-                    tc_mbar_wait(&s_lofull[s], u & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_raw = x_base + s * 16384u, a_lo = lo_base + s * 16384u;
+                    const uint32_t s = n % XS, u = n / XS, sl = n % LS, ul = n / LS;
+                    const uint32_t a_raw = x_base + s * 16384u, a_lo = lo_base + sl * 16384u;
                     const uint32_t b_img = b_base + (uint32_t)kb * 4096u;       // rows 0-15 c_hi, rows 16-31 c_lo
-                    if (!(p.debug & 2))
+                    tc_mbar_wait(&s_afull[s], u & 1u);                          // the raw products do not wait for the split
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (!(p.debug & 2) && tc_elect())
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {                            // UMMA_K = 8 floats = 32 B inside the 128 B row
-                        const uint64_t dar = tc_desc(a_raw + k4 * 32), dal = tc_desc(a_lo + k4 * 32);
-                        const uint64_t db = tc_desc(b_img + k4 * 32);
-                        tc_mma(acc, dar, db, kTcIdescN32, (kb | k4) != 0);      // cols 0-15 += x.c_hi, cols 16-31 += x.c_lo
-                        tc_mma(acc, dal, db, kTcIdescN16, 1u);                  // cols 0-15 += x_lo.c_hi
+                    for (int k4 = 0; k4 < 4; ++k4)                              // UMMA_K = 8 floats: k-step k4 = the stage's k4-th [128 rows][32 B] block
+                        tc_mma(acc, tc_desc(a_raw + k4 * 4096), tc_desc(b_img + k4 * 1024), kTcIdescN32, (kb | k4) != 0);   // cols 0-15 += x.c_hi, 16-31 += x.c_lo
+                    tc_mbar_wait(&s_lofull[sl], ul & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (tc_elect()) {
+                        if (!(p.debug & 2))
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tc_mma(acc, tc_desc(a_lo + k4 * 4096), tc_desc(b_img + k4 * 1024), kTcIdescN16, 1u);           // cols 0-15 += x_lo.c_hi
+                        tc_commit(&s_done[s]);                                  // ONE commit per k-block frees the raw and the lo stage
+                        if (kb == KB - 1) tc_commit(&s_accfull[t & 1]);
                     }
-                    tc_commit(&s_sfree[s]);
-                    if (kb == KB - 1) tc_commit(&s_accfull[t & 1]);
+                    __syncwarp();
                 }
             }
         }
@@ -217,11 +239,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
         for (int t = 0; t < n_tiles; ++t) {
             const int e = t & 1, j = t >> 1;
             for (int kb = 0; kb < KB; ++kb, ++n) {
-                const uint32_t s = n % kTcStages, u = n / kTcStages;
-                tc_mbar_wait(&s_afull[s], u & 1u);      // the producer reloaded stage s only after the MMAs that read lo[s] committed
-                if (p.debug & 1) { __syncwarp(); if (lane == 0) tc_mbar_arrive(&s_lofull[s]); continue; }
+                const uint32_t s = n % XS, u = n / XS, sl = n % LS, ul = n / LS;
+                tc_mbar_wait(&s_afull[s], u & 1u);
+                if (n >= LS) tc_mbar_wait(&s_done[(n - LS) % XS], ((n - LS) / XS) & 1u);   // MMAs that read lo[sl] are done
+                if (p.debug & 1) { __syncwarp(); if (lane == 0) tc_mbar_arrive(&s_lofull[sl]); continue; }
                 const uint32_t src = x_base + s * 16384u + (uint32_t)warp * 4096u;
-                const uint32_t dst = lo_base + s * 16384u + (uint32_t)warp * 4096u;
+                const uint32_t dst = lo_base + sl * 16384u + (uint32_t)warp * 4096u;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     float4 v[4];
@@ -238,14 +261,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const float hi = __uint_as_float(__float_as_uint(el[c]) & 0xffffe000u);   // what kind::tf32 reads
-                            o[c] = tf32_rna(el[c] - hi);
+                            // round-to-nearest (ties away) to 10 mantissa bits = cvt.rna.tf32 without the conversion pipe
+                            o[c] = (__float_as_uint(el[c] - hi) + 0x1000u) & 0xffffe000u;
                         }
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
                 __syncwarp();
-                if (lane == 0) tc_mbar_arrive(&s_lofull[s]);
+                if (lane == 0) tc_mbar_arrive(&s_lofull[sl]);
             }
             // ---- epilogue of tile t: TMEM lanes 32*warp .. +31 = rows of this warp
             tc_mbar_wait(&s_accfull[e], (uint32_t)j & 1u);
@@ -301,6 +325,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
 #pragma unroll
             for (int k = 0; k < 16; ++k) accp[k * row_f4] = make_float4(0.f, 0.f, 0.f, 0.f);
         float cnt = 0.f;
+        uint64_t pol_first;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
         for (int t = 0; t < n_tiles; ++t) {
             const int e = t & 1, j = t >> 1;
             tc_mbar_wait(&s_labready[e], (uint32_t)j & 1u);
@@ -320,8 +346,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
                         const unsigned l = (lws[q >> 2] >> ((q & 3) * 8)) & 255u;
-                        v[q] = (l < 16u && have) ? __ldcg(reinterpret_cast<const float4*>(xt + (size_t)(i0 + q) * D))
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (l < 16u && have)                                    // last use of the line: first to leave L2
+                            asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                                         : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w)
+                                         : "l"(xt + (size_t)(i0 + q) * D), "l"(pol_first));
                     }
                 };
                 auto add16 = [&](const float4 (&v)[16], const unsigned (&lws)[4]) {
@@ -380,10 +409,12 @@ __global__ void __launch_bounds__(256) kmeans_tc_prep_kernel(const float* __rest
         const uint32_t hi = tf32_rna(c);
         const uint32_t lo = tf32_rna(c - __uint_as_float(hi));
         const int kb = d >> 5, kc = d & 31;
-        // k-block image: 32 rows x 128 B (rows 0-15 hi pieces, rows 16-31 lo pieces), 8-row groups of 1024 B, in floats
-        const int off = kb * 1024 + (n >> 3) * 256 + (n & 7) * 32 + (((kc >> 2) ^ (n & 7)) << 2) + (kc & 3);
+        // k-block image: 4 k-steps x [32 rows (0-15 hi pieces, 16-31 lo pieces)][32 B], 8-row groups of 256 B,
+        // 32-byte swizzle (16-byte chunk index ^ bit 2 of the row); offsets in floats
+        const int k4 = kc >> 3, ch = (kc >> 2) & 1;
+        const int off = kb * 1024 + k4 * 256 + (n >> 3) * 64 + (n & 7) * 8 + ((ch ^ ((n >> 2) & 1)) << 2) + (kc & 3);
         img[off] = hi;
-        img[off + 512] = lo;
+        img[off + 128] = lo;                                       // rows 16-31 of the same k-step block
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int kk = warp; kk < 16; kk += 8) {
@@ -411,7 +442,21 @@ static TcEncodeFn tc_encode_fn() {
     return fn;
 }
 
-static size_t tc_smem_bytes(int dim) { return (size_t)(dim / 32) * 4096 + (size_t)kTcStages * 32768 + (size_t)64 * dim + 1024; }
+static int tc_lo_stages() {
+    const char* e = getenv("OODB200_TC_LS");
+    const int v = e ? atoi(e) : 2;
+    return v < 2 ? 2 : (v > 3 ? 3 : v);
+}
+static int tc_x_stages(int dim) {          // as many raw stages as fit next to the lo ring, the centroid image and the sums
+    const long fixed = (long)(dim / 32) * 4096 + (long)tc_lo_stages() * 16384 + 64L * dim + 1024 + 1024;
+    long xs = (232448 - fixed) / 16384;
+    const char* e = getenv("OODB200_TC_XS");
+    if (e && atoi(e) >= 2 && atoi(e) < xs) xs = atoi(e);
+    return (int)(xs > 5 ? 5 : xs);       // the lo ring is never deeper than the raw ring (s_done indexing)
+}
+static size_t tc_smem_bytes(int dim) {
+    return (size_t)(dim / 32) * 4096 + (size_t)(tc_x_stages(dim) + tc_lo_stages()) * 16384 + (size_t)64 * dim + 1024;
+}
 
 }  // namespace oodb200
 
@@ -440,12 +485,14 @@ extern "C" int oodb200_kmeans_step_tc_f32(const float* x, int64_t n_rows, int di
     OODB200_REQUIRE(enc != nullptr, "kmeans_step_tc: cuTensorMapEncodeTiled is not available from this driver");
     const int KB = dim / 32;
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n_rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)dim * 4};
-    const cuuint32_t box[2] = {32, (cuuint32_t)kTcRows};   // one k-block of a 128-row tile
-    const cuuint32_t estride[2] = {1, 1};
-    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstride, box, estride,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    // X [n_rows, dim] seen as (8 floats of a k-step, row, k-step): one copy = the 4 k-steps of a k-block of a 128-row
+    // tile, landing as [k-step][row][32 B] with the 32-byte swizzle the MMA descriptors name
+    const cuuint64_t gdim[3] = {8, (cuuint64_t)n_rows, (cuuint64_t)dim / 8};
+    const cuuint64_t gstride[2] = {(cuuint64_t)dim * 4, 32};
+    const cuuint32_t box[3] = {8, (cuuint32_t)kTcRows, 4};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), gdim, gstride, box, estride,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("kmeans_step_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return OODB200_ERR_CUDA; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -454,12 +501,20 @@ extern "C" int oodb200_kmeans_step_tc_f32(const float* x, int64_t n_rows, int di
     kmeans_tc_prep_kernel<<<n_seg, 256, 0, st>>>(cent, seg_k, active, k, dim, bimg, csn);
     int rc = check_launch("kmeans_tc_prep");
     if (rc) return rc;
-    const size_t smem = tc_smem_bytes(dim);
-    cudaError_t e = cudaFuncSetAttribute(kmeans_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("kmeans_step_tc: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
     const char* dbg = getenv("OODB200_TC_DEBUG");
     TcParams p = {dim, KB, k, seg_k, bimg, csn, block_seg, block_row0, block_row1, active, labels, psums, pcounts, n_changed, update,
                   dbg ? atoi(dbg) : 0, x};
-    kmeans_step_tc_kernel<<<n_blocks, kTcThreads, smem, st>>>(tmap, p);
+    const size_t smem = tc_smem_bytes(dim);
+    const int xs = tc_x_stages(dim), ls = tc_lo_stages();
+    cudaError_t e = cudaErrorInvalidValue;
+#define OODB200_TC_LAUNCH(XS, LS)                                                                                          \
+    if (xs == XS && ls == LS) {                                                                                            \
+        e = cudaFuncSetAttribute(kmeans_step_tc_kernel<XS, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (e == cudaSuccess) kmeans_step_tc_kernel<XS, LS><<<n_blocks, kTcThreads, smem, st>>>(tmap, p);                  \
+    }
+    OODB200_TC_LAUNCH(3, 2) OODB200_TC_LAUNCH(4, 2) OODB200_TC_LAUNCH(5, 2)
+    OODB200_TC_LAUNCH(3, 3) OODB200_TC_LAUNCH(4, 3) OODB200_TC_LAUNCH(5, 3)
+#undef OODB200_TC_LAUNCH
+    if (e != cudaSuccess) { set_error("kmeans_step_tc: %s (xs %d, ls %d)", cudaGetErrorString(e), xs, ls); return OODB200_ERR_CUDA; }
     return check_launch("kmeans_step_tc");
 }

@@ -12,8 +12,10 @@ table, _, _ = kmeans.build_blocks(sizes, 1, 0, dev)
 seg_k = torch.full((n_seg,), k, dtype=torch.int32, device=dev)
 labels = torch.full((x.shape[0],), -1, dtype=torch.int32, device=dev)
 chg = torch.zeros(n_seg, dtype=torch.int32, device=dev)
-for dbg in (0, 3, 4):
+import itertools
+for (xs, ls), dbg in itertools.product(((5, 2),), (0, 3, 4)):
     os.environ["OODB200_TC_DEBUG"] = str(dbg)
+    os.environ["OODB200_TC_XS"], os.environ["OODB200_TC_LS"] = str(xs), str(ls)
     be.step(x, k, seg_k, cent, table, None, labels, chg, 1); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -21,4 +23,4 @@ for dbg in (0, 3, 4):
         be.step(x, k, seg_k, cent, table, None, labels, chg, 1)
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 3
-    print(f"debug={dbg:2d} (1 nosplit, 2 nomma, 4 noacc, 8 mma kb0 only): {ms:.3f} ms  {x.numel() * 4 / ms / 1e6:.0f} GB/s")
+    print(f"xs={xs} ls={ls} debug={dbg:2d} (1 nosplit, 2 nomma, 4 noacc): {ms:.3f} ms  {x.numel() * 4 / ms / 1e6:.0f} GB/s")

@@ -228,3 +228,46 @@ def test_device_seeding_equals_host_seeding(dev, golden):
         assert torch.equal(a.labels, b.labels)
         assert a.n_iter == b.n_iter
         torch.testing.assert_close(a.centers, b.centers, rtol=0, atol=1e-6)
+
+
+def test_tcgen05_step_equals_fp32_step(dev):
+    """The tensor-core Lloyd step (csrc/kmeans_tc.cu: tcgen05 kind::tf32 with split-float operands, M-step from L2) vs
+    the FP32 step kernel on the same centres: identical labels and changed counts, bit-identical block partial sums
+    and counts (same row order), for ragged segments, an empty one, short last tiles, K < 16 and the D range."""
+    from ood_in_object_detection_b200 import kmeans, synth
+    tc, fp = kmeans.CudaBackend(dev), kmeans.CudaBackend(dev)
+    tc.tensor_core, fp.tensor_core = True, False
+    assert tc.lib.oodb200_kmeans_tc_workspace_bytes(3, 16, 576) > 0
+    assert tc.lib.oodb200_kmeans_tc_workspace_bytes(3, 17, 576) == 0 and tc.lib.oodb200_kmeans_tc_workspace_bytes(3, 16, 100) == 0
+    for dim, k, spec in ((576, 16, ((1, 5000), (2, 777), (3, 33), (4, 0), (5, 1500))), (128, 5, ((6, 2000), (7, 1029))),
+                         (640, 12, ((9, 1300), (10, 64)))):
+        segs = [synth.blob_vectors(s, n, dim, k, 3.0)[0] if n else np.zeros((0, dim), np.float32) for s, n in spec]
+        sizes = [len(s) for s in segs]
+        x = torch.from_numpy(np.concatenate(segs)).to(dev)
+        rng = np.random.default_rng(dim)
+        cent = np.stack([s[rng.integers(0, len(s), k)] if len(s) else np.zeros((k, dim), np.float32) for s in segs])
+        cent = torch.from_numpy(cent + 0.01 * rng.standard_normal(cent.shape).astype(np.float32)).to(dev)
+        table, _, _ = kmeans.build_blocks(sizes, 1, 0, dev)
+        seg_k = torch.tensor([min(k, n) for n in sizes], dtype=torch.int32, device=dev)
+        out = []
+        for be in (fp, tc):
+            for update in (1, 0):
+                labels = torch.full((x.shape[0],), -1, dtype=torch.int32, device=dev)
+                chg = torch.zeros(len(sizes), dtype=torch.int32, device=dev)
+                ps, pc = be.step(x, k, seg_k, cent, table, None, labels, chg, update)
+                torch.cuda.synchronize()
+                out.append((labels, chg, None if ps is None else ps.clone(), None if pc is None else pc.clone()))
+        (l_fp, c_fp, ps_fp, pc_fp), (l_fp0, _, _, _), (l_tc, c_tc, ps_tc, pc_tc), (l_tc0, _, _, _) = out
+        assert torch.equal(l_fp, l_tc) and torch.equal(l_fp0, l_tc0) and torch.equal(l_tc, l_tc0), dim
+        assert torch.equal(c_fp, c_tc)
+        assert torch.equal(pc_fp, pc_tc) and torch.equal(ps_fp, ps_tc), dim
+        # labels are the nearest centre in float64 (up to float32 ties)
+        off = np.concatenate([[0], np.cumsum(sizes)])
+        for g, s in enumerate(segs):
+            if not len(s):
+                continue
+            kg = min(k, len(s))
+            d = ((s[:, None, :].astype(np.float64) - cent[g, :kg].cpu().numpy()[None].astype(np.float64)) ** 2).sum(-1)
+            lab = l_tc[off[g]:off[g + 1]].cpu().numpy()
+            best = d.min(1)
+            assert np.all(d[np.arange(len(s)), lab] <= best * (1 + 1e-5) + 1e-7)
