@@ -318,10 +318,11 @@ def run_fit(device, world, rank, n_total, reps, warm):
         thr, _, _ = select.segment_select(d[ops.METRIC_SLOT["l2"]].contiguous(), off, ranks, group=group)
         torch.cuda.synchronize()
         total = time.perf_counter() - t0
-        t = torch.tensor([total, r.seconds["lloyd"], r.seconds["init"]], dtype=torch.float64, device=device)
+        t = torch.tensor([total, r.seconds["lloyd"], r.seconds["init"], r.seconds["center"]], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        cur = dict(total=float(t[0]), lloyd=float(t[1]), init=float(t[2]), iters=int(r.seconds["lloyd_iters"]),
+        cur = dict(total=float(t[0]), lloyd=float(t[1]), init=float(t[2]), center=float(t[3]), seeding=r.seconds.get("seeding"),
+                   iters=int(r.seconds["lloyd_iters"]),
                    n_iter=[int(v) for v in r.n_iter], strict=all(r.strict), thr0=thr[0])
         if it >= warm and (best is None or cur["total"] < best["total"]):
             best = cur
@@ -330,10 +331,14 @@ def run_fit(device, world, rank, n_total, reps, warm):
     lloyd_per_iter = best["lloyd"] / max(best["iters"], 1)
     return {"metric": FIT_METRIC, "value": n_total * best["iters"] / best["lloyd"], "unit": FIT_UNIT,
             "n_vectors": n_total, "dim": FIT_D, "k": FIT_K, "segments": FIT_CLASSES, "lloyd_iterations": best["iters"],
-            "lloyd_ms_per_iteration": 1e3 * lloyd_per_iter, "seed_ms": 1e3 * best["init"], "fit_ms": 1e3 * best["total"],
+            "lloyd_ms_per_iteration": 1e3 * lloyd_per_iter, "seed_ms": 1e3 * best["init"], "seeding": best["seeding"],
+            "center_ms": 1e3 * best["center"],
+            "means_scores_thresholds_ms": 1e3 * (best["total"] - best["init"] - best["lloyd"] - best["center"]),
+            "fit_ms": 1e3 * best["total"],
             "e2e_vectors_per_s": n_total / best["total"], "strict_convergence": best["strict"], "scaling": "strong",
             "collective": "1 all-reduce per Lloyd iteration + 1 per radix pass" if world > 1 else "none (1 GPU)",
-            "roofline": {"bound": "hbm", "kernel": "kmeans_step_kernel (+reduce/update, host loop)", "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "kmeans_step_tc_kernel (tcgen05 assignment + partial sums; + reduce/update, host loop)",
+                         "unit": "GB/s",
                          "achieved": it_bytes / world / lloyd_per_iter / 1e9, "peak": peak,
                          "frac": it_bytes / world / lloyd_per_iter / 1e9 / peak, "algorithmic_bytes_per_iteration": it_bytes,
                          "traffic": _traffic("C3", "kmeans_step_dram_bytes_per_launch")}}

@@ -211,6 +211,17 @@ int oodb200_sqdist_cand_f32(const float* x, int dim, const int64_t* seg_off, int
                             const float* cand, int n_cand, const float* closest, float* out_d, double* pot,
                             void* stream);
 
+/* Mean-centring of every segment and the variance behind sklearn's tolerance (KMeans.fit `X -= X.mean(axis=0)`,
+ * `_tolerance`; sklearn/cluster/_kmeans.py:283-293, 1487-1497), float64 accumulation, fixed combination order.
+ * segment_colsum: sums[g, d] = sum_r x[r, d] over the rows of segment g (the caller divides by the global size).
+ * segment_center: out[r, d] = x[r, d] - mean[g, d]; sq[g] = sum of out^2 over the segment.
+ * scratch: oodb200_segment_scratch_doubles(n_seg, dim) doubles. */
+int64_t oodb200_segment_scratch_doubles(int n_seg, int dim);
+int oodb200_segment_colsum_f64(const float* x, int dim, const int64_t* seg_off, int n_seg, double* scratch, double* sums,
+                               void* stream);
+int oodb200_segment_center_f32(const float* x, int dim, const int64_t* seg_off, int n_seg, const float* mean, float* out,
+                               double* scratch, double* sq, void* stream);
+
 /* ---- K4 on the tensor pipe: same contract as kmeans_step (update 0 or 1) for k <= 16, dim % 32 == 0,
  * 128 <= dim <= 640: the x.c cross-term runs on tcgen05 (kind::tf32, split-float hi/lo pieces = float32-level
  * accuracy) on 128-row tiles streamed by TMA; the partial sums re-read the tile from L2 (csrc/kmeans_tc.cu).

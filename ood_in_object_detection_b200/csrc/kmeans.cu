@@ -529,6 +529,121 @@ __global__ void __launch_bounds__(256) sqdist_cand_kernel(const CandParams p) {
     }
 }
 
+// ---- mean-centring of every segment (KMeans.fit: `X -= X.mean(axis=0)`, sklearn/cluster/_kmeans.py:1487-1497) and the
+// variance behind sklearn's tolerance (`_tolerance`, :283-293).  Two streaming passes, float64 accumulation, block
+// partials combined in block order -> bit-reproducible.
+constexpr int kCsThreads = 160;
+constexpr int kCsBlocks = 64;                  // row blocks per segment
+
+// partial[g, b, d] = sum over the rows of block b of segment g of x[r, d] (float64)
+template <bool VEC4>
+__global__ void __launch_bounds__(kCsThreads) seg_colsum_kernel(const float* __restrict__ x, int dim, const int64_t* __restrict__ seg_off,
+                                                                double* __restrict__ partial) {
+    const int g = blockIdx.y, b = blockIdx.x;
+    const int64_t s0 = seg_off[g], s1 = seg_off[g + 1];
+    const int64_t per = (s1 - s0 + kCsBlocks - 1) / kCsBlocks;
+    const int64_t r0 = min(s1, s0 + per * b), r1 = min(s1, r0 + per);
+    double* __restrict__ out = partial + ((size_t)g * kCsBlocks + b) * dim;
+    if (VEC4) {
+        for (int c = threadIdx.x; c < dim / 4; c += kCsThreads) {
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            const float* __restrict__ col = x + c * 4;
+            int64_t r = r0;
+            for (; r + 8 <= r1; r += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = __ldg(reinterpret_cast<const float4*>(col + (r + q) * dim));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { a0 += v[q].x; a1 += v[q].y; a2 += v[q].z; a3 += v[q].w; }
+            }
+            for (; r < r1; ++r) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(col + r * dim));
+                a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+            }
+            out[c * 4] = a0; out[c * 4 + 1] = a1; out[c * 4 + 2] = a2; out[c * 4 + 3] = a3;
+        }
+    } else {
+        for (int c = threadIdx.x; c < dim; c += kCsThreads) {
+            double a = 0;
+            for (int64_t r = r0; r < r1; ++r) a += __ldg(x + r * dim + c);
+            out[c] = a;
+        }
+    }
+}
+
+// sums[g, d] = sum_b partial[g, b, d] in increasing b
+__global__ void seg_colsum_reduce_kernel(const double* __restrict__ partial, int dim, double* __restrict__ sums) {
+    const int g = blockIdx.y;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= dim) return;
+    double t = 0;
+    for (int b = 0; b < kCsBlocks; ++b) t += partial[((size_t)g * kCsBlocks + b) * dim + d];
+    sums[(size_t)g * dim + d] = t;
+}
+
+// out[r, d] = x[r, d] - mean[g, d];  sq_partial[g, b] = sum over the block of out^2 (float64)
+template <bool VEC4>
+__global__ void __launch_bounds__(kCsThreads) seg_center_kernel(const float* __restrict__ x, int dim, const int64_t* __restrict__ seg_off,
+                                                                const float* __restrict__ mean, float* __restrict__ out,
+                                                                double* __restrict__ sq_partial) {
+    __shared__ double s_red[kCsThreads];
+    const int g = blockIdx.y, b = blockIdx.x;
+    const int64_t s0 = seg_off[g], s1 = seg_off[g + 1];
+    const int64_t per = (s1 - s0 + kCsBlocks - 1) / kCsBlocks;
+    const int64_t r0 = min(s1, s0 + per * b), r1 = min(s1, r0 + per);
+    const float* __restrict__ mg = mean + (size_t)g * dim;
+    double sq = 0;
+    if (VEC4) {
+        for (int c = threadIdx.x; c < dim / 4; c += kCsThreads) {
+            const float4 m = *reinterpret_cast<const float4*>(mg + c * 4);
+            int64_t r = r0;
+            for (; r + 4 <= r1; r += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float4*>(x + (r + q) * dim + c * 4));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    v[q].x -= m.x; v[q].y -= m.y; v[q].z -= m.z; v[q].w -= m.w;
+                    sq += (double)v[q].x * v[q].x; sq += (double)v[q].y * v[q].y;
+                    sq += (double)v[q].z * v[q].z; sq += (double)v[q].w * v[q].w;
+                    *reinterpret_cast<float4*>(out + (r + q) * dim + c * 4) = v[q];
+                }
+            }
+            for (; r < r1; ++r) {
+                float4 v = __ldg(reinterpret_cast<const float4*>(x + r * dim + c * 4));
+                v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
+                sq += (double)v.x * v.x; sq += (double)v.y * v.y; sq += (double)v.z * v.z; sq += (double)v.w * v.w;
+                *reinterpret_cast<float4*>(out + r * dim + c * 4) = v;
+            }
+        }
+    } else {
+        for (int c = threadIdx.x; c < dim; c += kCsThreads) {
+            const float m = mg[c];
+            for (int64_t r = r0; r < r1; ++r) {
+                const float v = __ldg(x + r * dim + c) - m;
+                sq += (double)v * v;
+                out[r * dim + c] = v;
+            }
+        }
+    }
+    s_red[threadIdx.x] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < kCsThreads; ++i) t += s_red[i];
+        sq_partial[(size_t)g * kCsBlocks + b] = t;
+    }
+}
+
+__global__ void seg_sq_reduce_kernel(const double* __restrict__ sq_partial, double* __restrict__ sq) {
+    const int g = blockIdx.x;
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int b = 0; b < kCsBlocks; ++b) t += sq_partial[(size_t)g * kCsBlocks + b];
+        sq[g] = t;
+    }
+}
+
 }  // namespace oodb200
 
 using namespace oodb200;
@@ -628,4 +743,38 @@ extern "C" int oodb200_sqdist_cand_f32(const float* x, int dim, const int64_t* s
     if (gx < 1) gx = 1;
     sqdist_cand_kernel<<<dim3((unsigned)gx, (unsigned)n_seg), 256, smem, (cudaStream_t)stream>>>(p);
     return check_launch("sqdist_cand");
+}
+
+extern "C" int64_t oodb200_segment_scratch_doubles(int n_seg, int dim) { return (int64_t)n_seg * kCsBlocks * (dim > 1 ? dim : 1); }
+
+extern "C" int oodb200_segment_colsum_f64(const float* x, int dim, const int64_t* seg_off, int n_seg, double* scratch,
+                                          double* sums, void* stream) {
+    OODB200_REQUIRE(dim > 0 && n_seg >= 0 && n_seg <= 65535, "segment_colsum: bad size");
+    if (n_seg == 0) return OODB200_OK;
+    OODB200_REQUIRE(x && seg_off && scratch && sums, "segment_colsum: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(kCsBlocks, (unsigned)n_seg);
+    if (dim % 4 == 0 && ((uintptr_t)x & 15) == 0) seg_colsum_kernel<true><<<grid, kCsThreads, 0, st>>>(x, dim, seg_off, scratch);
+    else seg_colsum_kernel<false><<<grid, kCsThreads, 0, st>>>(x, dim, seg_off, scratch);
+    int rc = check_launch("segment_colsum");
+    if (rc) return rc;
+    seg_colsum_reduce_kernel<<<dim3((unsigned)((dim + 127) / 128), (unsigned)n_seg), 128, 0, st>>>(scratch, dim, sums);
+    return check_launch("segment_colsum_reduce");
+}
+
+extern "C" int oodb200_segment_center_f32(const float* x, int dim, const int64_t* seg_off, int n_seg, const float* mean,
+                                          float* out, double* scratch, double* sq, void* stream) {
+    OODB200_REQUIRE(dim > 0 && n_seg >= 0 && n_seg <= 65535, "segment_center: bad size");
+    if (n_seg == 0) return OODB200_OK;
+    OODB200_REQUIRE(x && seg_off && mean && out && scratch && sq, "segment_center: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(kCsBlocks, (unsigned)n_seg);
+    if (dim % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)mean & 15) == 0)
+        seg_center_kernel<true><<<grid, kCsThreads, 0, st>>>(x, dim, seg_off, mean, out, scratch);
+    else
+        seg_center_kernel<false><<<grid, kCsThreads, 0, st>>>(x, dim, seg_off, mean, out, scratch);
+    int rc = check_launch("segment_center");
+    if (rc) return rc;
+    seg_sq_reduce_kernel<<<n_seg, 32, 0, st>>>(scratch, sq);
+    return check_launch("segment_sq_reduce");
 }

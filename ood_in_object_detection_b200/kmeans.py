@@ -61,6 +61,24 @@ class CudaBackend:
                                                          _stream()), "oodb200_sqdist_cand_f32")
         return out, pot
 
+    # ---- mean-centring (csrc/kmeans.cu) ----
+    def colsum(self, x, seg_off_d, n_seg):
+        dim = x.shape[1]
+        scratch = torch.empty(int(self.lib.oodb200_segment_scratch_doubles(n_seg, dim)), dtype=torch.float64, device=x.device)
+        sums = torch.zeros((n_seg, dim), dtype=torch.float64, device=x.device)
+        self._lib.check(self.lib.oodb200_segment_colsum_f64(_ptr(x), dim, _ptr(seg_off_d), n_seg, _ptr(scratch), _ptr(sums),
+                                                            _stream()), "oodb200_segment_colsum_f64")
+        return sums
+
+    def center(self, x, seg_off_d, n_seg, mean):
+        dim = x.shape[1]
+        scratch = torch.empty(int(self.lib.oodb200_segment_scratch_doubles(n_seg, dim)), dtype=torch.float64, device=x.device)
+        out = torch.empty_like(x)
+        sq = torch.zeros(n_seg, dtype=torch.float64, device=x.device)
+        self._lib.check(self.lib.oodb200_segment_center_f32(_ptr(x), dim, _ptr(seg_off_d), n_seg, _ptr(mean), _ptr(out),
+                                                            _ptr(scratch), _ptr(sq), _stream()), "oodb200_segment_center_f32")
+        return out, sq
+
     # ---- device seeding (csrc/seed.cu) ----
     supports_device_seeding = True
 
@@ -217,8 +235,17 @@ class KMeansResult:
 
 
 def _sklearn_first_center(rs: np.random.RandomState, n: int) -> int:
-    w = np.ones(n, dtype=np.float32)
-    return int(rs.choice(n, p=w / w.sum()))           # _kmeans.py:234
+    """`random_state.choice(n_samples, p=sample_weight / sample_weight.sum())` (_kmeans.py:234) with unit float32 weights.
+    RandomState.choice(p=...) is `cdf = p.cumsum(); cdf /= cdf[-1]; cdf.searchsorted(random_sample(), side='right')` on
+    the float64 copy of p; restated here without choice()'s O(n) validation passes (same stream consumption, same
+    arithmetic; tests/test_host_logic.py holds it to rs.choice)."""
+    if n >= 1 << 24:                                   # float32 ones no longer sum exactly: take numpy's own path
+        w = np.ones(n, dtype=np.float32)
+        return int(rs.choice(n, p=w / w.sum()))
+    pv = np.float64(np.float32(1.0) / np.float32(n))
+    cdf = np.cumsum(np.full(n, pv, dtype=np.float64))
+    cdf /= cdf[-1]
+    return int(cdf.searchsorted(rs.random_sample(), side="right"))
 
 
 def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table: BlockTable, local_off: Sequence[int],
@@ -254,21 +281,11 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
         return t
 
     # ---- mean-centre every segment (KMeans.fit: X -= X.mean(axis=0)) and the sklearn tolerance ----
-    mean = torch.zeros((n_seg, dim), dtype=torch.float64, device=dev)
-    for g in range(n_seg):
-        a, b = local_off[g], local_off[g + 1]
-        if b > a:
-            mean[g] = x_local[a:b].sum(dim=0, dtype=torch.float64)
-    allreduce(mean)
+    x_local = x_local.contiguous()
+    mean = allreduce(backend.colsum(x_local, seg_off_d, n_seg))            # float64 column sums, one streaming pass
     gs = torch.tensor([max(int(n), 1) for n in global_sizes], dtype=torch.float64, device=dev)
-    mean = (mean / gs[:, None]).to(torch.float32)
-    x = torch.empty_like(x_local)
-    var = torch.zeros(n_seg, dtype=torch.float64, device=dev)
-    for g in range(n_seg):
-        a, b = local_off[g], local_off[g + 1]
-        if b > a:
-            x[a:b] = x_local[a:b] - mean[g]
-            var[g] = (x[a:b].to(torch.float64) ** 2).sum()
+    mean = (mean / gs[:, None]).to(torch.float32).contiguous()
+    x, var = backend.center(x_local, seg_off_d, n_seg, mean)                # x - mean and sum of squares, second pass
     allreduce(var)
     tol_abs = (var / gs / dim * tol).cpu().numpy()                         # mean over features of the variance
     if distributed:
@@ -476,13 +493,19 @@ def _sklearn_uniform_stream(global_sizes, seg_k_host, k, random_state):
     n_trials = max(trials + [1])
     first = np.zeros(n_seg, dtype=np.int64)
     uni = np.zeros((k, n_seg, n_trials), dtype=np.float64)
+    memo = {}                                          # every segment restarts RandomState(random_state): (n, k) decides
     for g in range(n_seg):
         if global_sizes[g] <= 0:
             continue
-        rs = np.random.RandomState(random_state)
-        first[g] = _sklearn_first_center(rs, int(global_sizes[g]))
-        for c in range(1, seg_k_host[g]):
-            uni[c, g, :trials[g]] = rs.uniform(size=trials[g])
+        key = (int(global_sizes[g]), int(seg_k_host[g]))
+        if key not in memo:
+            rs = np.random.RandomState(random_state)
+            f = _sklearn_first_center(rs, key[0])
+            u = np.zeros((k, n_trials), dtype=np.float64)
+            for c in range(1, key[1]):
+                u[c, :trials[g]] = rs.uniform(size=trials[g])
+            memo[key] = (f, u)
+        first[g], uni[:, g, :] = memo[key]
     return first, uni, trials
 
 

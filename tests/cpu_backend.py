@@ -37,6 +37,23 @@ class NumpyBackend:
             pot[g] = d.astype(np.float64).sum(0)
         return torch.from_numpy(out), torch.from_numpy(pot)
 
+    # ---- mean-centring stand-ins (kmeans.cu::seg_colsum_kernel / seg_center_kernel) ----
+    def colsum(self, x, seg_off_d, n_seg):
+        xs, off = x.numpy(), seg_off_d.numpy()
+        out = np.zeros((n_seg, xs.shape[1]), np.float64)
+        for g in range(n_seg):
+            out[g] = xs[off[g]:off[g + 1]].sum(0, dtype=np.float64)
+        return torch.from_numpy(out)
+
+    def center(self, x, seg_off_d, n_seg, mean):
+        xs, off, m = x.numpy(), seg_off_d.numpy(), mean.numpy()
+        out = np.empty_like(xs)
+        sq = np.zeros(n_seg, np.float64)
+        for g in range(n_seg):
+            out[off[g]:off[g + 1]] = xs[off[g]:off[g + 1]] - m[g]
+            sq[g] = (out[off[g]:off[g + 1]].astype(np.float64) ** 2).sum()
+        return torch.from_numpy(out), torch.from_numpy(sq)
+
     # ---- device seeding stand-ins (csrc/seed.cu) ----
     supports_device_seeding = True
 

@@ -90,3 +90,16 @@ def test_fusion_state_plumbing():
     ou.configure_extra_output_of_the_model(_M, m)
     assert _M.model.which_layers_to_extract == "convolutional_layers" and _M.model.extraction_mode == "ftmaps_and_strides"
     assert _M.model.model[-1].output_values_before_sigmoid is False
+
+
+def test_first_centre_draw_is_randomstate_choice():
+    """kmeans._sklearn_first_center restates RandomState.choice(n, p=uniform float32 weights) without its O(n) checks:
+    same index and same stream position for every n (sklearn _kmeans.py:234)."""
+    from ood_in_object_detection_b200 import kmeans
+    for n in (1, 2, 3, 7, 100, 4097, 200000, 1234567):
+        for seed in (10, 0, 123):
+            a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+            w = np.ones(n, dtype=np.float32)
+            ref = int(a.choice(n, p=w / w.sum()))
+            assert kmeans._sklearn_first_center(b, n) == ref, (n, seed)
+            assert a.uniform() == b.uniform()
