@@ -90,21 +90,33 @@ __global__ void __launch_bounds__(kScanThreads) seed_scan_kernel(const ScanParam
             const int valid = (int)min((int64_t)kScanBatch, n - i0);
             const int n_chunks = (valid + kScanChunk - 1) / kScanChunk;
             const float4* __restrict__ v4 = reinterpret_cast<const float4*>(s_buf[cur]);
-            for (int c = 0; c < n_chunks; ++c) {       // padding values are +0.0f: x + 0 == x for x >= 0
-#pragma unroll 8
-                for (int q = 0; q < kScanChunk / 4; ++q) {
-                    const float4 v = v4[c * (kScanChunk / 4) + q];
-                    run = __fadd_rn(run, v.x);
-                    run = __fadd_rn(run, v.y);
-                    run = __fadd_rn(run, v.z);
-                    run = __fadd_rn(run, v.w);
+            // the FADD chain (4 cycles per value) must never wait for shared memory: 8 float4 are loaded one group ahead
+            float4 nxt[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) nxt[q] = v4[q];
+            const int n_groups = n_chunks * (kScanChunk / 32);                 // padding values are +0.0f: x + 0 == x for x >= 0
+            for (int gq = 0; gq < n_groups; ++gq) {
+                float4 curv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) curv[q] = nxt[q];
+                if (gq + 1 < n_groups) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) nxt[q] = v4[(gq + 1) * 8 + q];
                 }
-                cs[b * (kScanBatch / kScanChunk) + c] = run;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    run = __fadd_rn(run, curv[q].x);
+                    run = __fadd_rn(run, curv[q].y);
+                    run = __fadd_rn(run, curv[q].z);
+                    run = __fadd_rn(run, curv[q].w);
+                }
+                if ((gq & 3) == 3) cs[b * (kScanBatch / kScanChunk) + (gq >> 2)] = run;
             }
-        } else if (b + 1 < n_batches) {
-            // threads 1.. stage the next batch meanwhile (thread 0's share is picked up by striding over tid >= 1)
+        } else if (tid >= 32 && b + 1 < n_batches) {
+            // warps 1.. stage the next batch meanwhile; the other lanes of warp 0 stay idle: a divergent warp would
+            // interleave their global loads with the FADD chain of lane 0
             const int64_t i0 = (b + 1) * kScanBatch;
-            for (int j = tid - 1; j < kScanBatch; j += kScanThreads - 1) {
+            for (int j = tid - 32; j < kScanBatch; j += kScanThreads - 32) {
                 const int64_t i = i0 + j;
                 s_buf[cur ^ 1][j] = i < n ? value(i) : 0.f;
             }
