@@ -16,10 +16,11 @@
 //                       accumulators in TMEM (2 x 32 columns, double buffered across tiles); tcgen05.commit frees the
 //                       ring stage / publishes the tile.
 //   warps 4-8           M-step of the PREVIOUS tile, overlapped with the streaming of the next one: thread = one 16-byte
-//                       column chunk; the rows are re-read from L2 (coalesced LDG.128, 16 in flight per thread; the tile
-//                       was fetched microseconds ago) and added to the cluster's slot of a thread-private [16][D]
-//                       shared-memory accumulator (the label is a run-time index), rows in increasing order -> block
-//                       partials are bit-reproducible and identical in order to the FP32 kernel's.
+//                       column chunk; the epilogue sorts the tile's rows by (label, row); the rows are re-read from L2 in
+//                       that order (coalesced LDG.128 through a register ring; the tile was fetched microseconds ago) and
+//                       every RUN of one cluster is added in registers between one load and one store of the cluster's
+//                       slot in a thread-private [16][D] shared-memory accumulator -> block partials are bit-reproducible
+//                       and identical in order to the FP32 kernel's.
 // Centroids are pre-split once per iteration (kmeans_tc_prep_kernel) into the exact shared-memory image (hi and lo,
 // K-major SWIZZLE_128B, 32 rows per k-block) and arrive with ONE bulk copy per CTA.
 // Accuracy: x = x_hi + x_lo and c = c_hi + c_lo with 11-bit pieces; the dropped x_lo.c_lo term and the rounding of the
@@ -39,7 +40,7 @@ namespace oodb200 {
 constexpr int kTcRows = 128;           // rows per tile = MMA M
 constexpr int kTcThreads = 352;
 constexpr int kTcMaxKb = 20;           // D <= 640 (one 16-byte column chunk per M-step thread)
-constexpr int kTcMaxXs = 6;            // raw ring: up to 6 x 16 KB (as many as shared memory allows: HBM latency)
+constexpr int kTcMaxXs = 7;            // raw ring: up to 6 x 16 KB (as many as shared memory allows: HBM latency)
 constexpr int kTcMaxLs = 4;             // lo ring: up to 4 x 16 KB
 constexpr int kNSplit = 4, kWAcc0 = 4, kNAcc = 5, kWTma = 9, kWMma = 10;
 constexpr int kTcCols = 64;            // TMEM columns: 2 tiles x (16 hi + 16 lo)
@@ -141,7 +142,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
     __shared__ __align__(8) uint64_t s_afull[kTcMaxXs], s_done[kTcMaxXs], s_lofull[kTcMaxLs];   // s_done[n % XS]: the MMAs of k-block n have completed
     __shared__ __align__(8) uint64_t s_accfull[2], s_labready[2], s_mdone[2], s_bfull;
     __shared__ unsigned s_mask[2][4][16];                   // [tile parity][32-row group][cluster] (counts)
-    __shared__ __align__(16) unsigned char s_lab[2][kTcRows];             // label of every row of the tile, 255 = past the block
+    __shared__ unsigned char s_order[2][kTcRows];           // rows of the tile sorted by (label, row)
+    __shared__ int s_start[2][17];                          // first sorted position of every cluster; [16] = valid rows
     __shared__ float s_csn[16];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -302,12 +304,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
                 p.labels[row] = lab;
             }
             if (j >= 1) tc_mbar_wait(&s_mdone[e], (uint32_t)(j - 1) & 1u);      // the M-step of tile t-2 has consumed these masks
-            s_lab[e][warp * 32 + lane] = valid ? (unsigned char)lab : (unsigned char)255;
+            // rows of the tile sorted by (label, row): per-cluster masks of the 4 warps -> exclusive starts, then every
+            // row's position = start[label] + rows with the same label before it
+            unsigned mym = 0;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const unsigned m = __ballot_sync(0xffffffffu, valid && lab == k);
                 if (lane == k) s_mask[e][warp][k] = m;
+                if (lab == k) mym = m;
             }
+            asm volatile("bar.sync 1, 128;" ::: "memory");                     // the 4 epilogue warps
+            int cntk = 0;
+            if (lane < 16) cntk = __popc(s_mask[e][0][lane]) + __popc(s_mask[e][1][lane]) + __popc(s_mask[e][2][lane]) + __popc(s_mask[e][3][lane]);
+            int incl = cntk;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const int startk = incl - cntk;                                     // lane k < 16: first position of cluster k
+            const int my_start = __shfl_sync(0xffffffffu, startk, lab & 15);
+            if (valid) {
+                int pos = my_start + __popc(mym & ((1u << lane) - 1u));
+                for (int w = 0; w < warp; ++w) pos += __popc(s_mask[e][w][lab]);
+                s_order[e][pos] = (unsigned char)(warp * 32 + lane);
+            }
+            if (warp == 0 && lane < 16) s_start[e][lane] = startk;
+            if (warp == 0 && lane == 15) s_start[e][16] = incl;
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(&s_labready[e]);
@@ -318,7 +341,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
     } else {                                                                    // warps 4-8: M-step of the finished tile
         const int c = tid - kWAcc0 * 32;                                        // 0..159: one 16-byte column chunk each
         const bool have = c < D / 4;
-        // per-cluster sums of this thread's 4 columns live in shared memory (dynamic label index), private to the thread
+        // per-cluster sums of this thread's 4 columns: thread-private [16][D] in shared memory (the cluster is a run-time
+        // index); a whole RUN of rows of one cluster is added in registers between one load and one store of its slot
         float4* __restrict__ accp = reinterpret_cast<float4*>(tc_dyn + (acc_base - tc_smem_u32(tc_dyn))) + c;
         const int row_f4 = D / 4;
         if (have)
@@ -327,53 +351,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) kmeans_step_tc_kernel(const __g
         float cnt = 0.f;
         uint64_t pol_first;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+        const bool accumulate = p.update && !(p.debug & 4);
         for (int t = 0; t < n_tiles; ++t) {
             const int e = t & 1, j = t >> 1;
             tc_mbar_wait(&s_labready[e], (uint32_t)j & 1u);
-            if (p.update && !(p.debug & 4)) {
+            if (accumulate) {
                 const float* __restrict__ xt = p.x + (size_t)(r0 + (int64_t)t * kTcRows) * D + c * 4;
-                if (c < 16) {
-                    unsigned tot = 0;
+                const int n_valid = s_start[e][16];
+                if (c < 16) cnt += (float)(s_start[e][c + 1] - s_start[e][c]);
+                // the tile's rows in (label, row) order through a register ring of 4 batches x 4 rows (coalesced LDG.128
+                // from L2: the tile was fetched microseconds ago); rows of a cluster arrive in increasing order
+                auto load4 = [&](int bi, float4 (&v)[4]) {
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) tot += __popc(s_mask[e][w][c]);
-                    cnt += (float)tot;
-                }
-                // 16 rows in flight per thread (coalesced LDG.128 from L2: the tile was fetched microseconds ago), then a
-                // read-modify-write of the cluster's slot, rows in increasing order -> same sums as the FP32 kernel
-                auto load16 = [&](int i0, float4 (&v)[16], unsigned (&lws)[4]) {
-                    const uint4 lw = *reinterpret_cast<const uint4*>(&s_lab[e][i0]);
-                    lws[0] = lw.x; lws[1] = lw.y; lws[2] = lw.z; lws[3] = lw.w;
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const unsigned l = (lws[q >> 2] >> ((q & 3) * 8)) & 255u;
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = bi * 4 + q;
                         v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (l < 16u && have)                                    // last use of the line: first to leave L2
+                        if (have && i < n_valid) {                              // last use of the line: first to leave L2
+                            const int r = s_order[e][i];
                             asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                                          : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w)
-                                         : "l"(xt + (size_t)(i0 + q) * D), "l"(pol_first));
-                    }
-                };
-                auto add16 = [&](const float4 (&v)[16], const unsigned (&lws)[4]) {
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const unsigned l = (lws[q >> 2] >> ((q & 3) * 8)) & 255u;
-                        if (l < 16u && have) {
-                            float4 a = accp[l * row_f4];
-                            a.x += v[q].x; a.y += v[q].y; a.z += v[q].z; a.w += v[q].w;
-                            accp[l * row_f4] = a;
+                                         : "l"(xt + (size_t)r * D), "l"(pol_first));
                         }
                     }
                 };
-                float4 va[16], vb[16];
-                unsigned la[4], lb[4];
-                load16(0, va, la);
+                int cur_k = -1, next_start = 0;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                auto consume4 = [&](int bi, const float4 (&v)[4]) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = bi * 4 + q;
+                        if (i < n_valid) {
+                            while (i >= next_start) {                           // next cluster (warp-uniform): swap the slot
+                                if (cur_k >= 0 && have) accp[cur_k * row_f4] = a;
+                                ++cur_k;
+                                next_start = s_start[e][cur_k + 1];
+                                if (have) a = accp[cur_k * row_f4];
+                            }
+                            a.x += v[q].x; a.y += v[q].y; a.z += v[q].z; a.w += v[q].w;
+                        }
+                    }
+                };
+                float4 v0[4], v1[4], v2[4], v3[4];
+                load4(0, v0);
+                load4(1, v1);
+                load4(2, v2);
 #pragma unroll 1
-                for (int i0 = 0; i0 < kTcRows; i0 += 32) {                     // the next 16 rows are in flight while 16 are added
-                    load16(i0 + 16, vb, lb);
-                    add16(va, la);
-                    if (i0 + 32 < kTcRows) load16(i0 + 32, va, la);
-                    add16(vb, lb);
+                for (int bi = 0; bi * 4 < n_valid; bi += 4) {
+                    load4(bi + 3, v3);
+                    consume4(bi, v0);
+                    load4(bi + 4, v0);
+                    consume4(bi + 1, v1);
+                    load4(bi + 5, v1);
+                    consume4(bi + 2, v2);
+                    load4(bi + 6, v2);
+                    consume4(bi + 3, v3);
                 }
+                if (cur_k >= 0 && have) accp[cur_k * row_f4] = a;
             }
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(&s_mdone[e]);
@@ -452,7 +485,7 @@ static int tc_x_stages(int dim) {          // as many raw stages as fit next to 
     long xs = (232448 - fixed) / 16384;
     const char* e = getenv("OODB200_TC_XS");
     if (e && atoi(e) >= 2 && atoi(e) < xs) xs = atoi(e);
-    return (int)(xs > 5 ? 5 : xs);       // the lo ring is never deeper than the raw ring (s_done indexing)
+    return (int)(xs > kTcMaxXs ? kTcMaxXs : xs);   // the lo ring is never deeper than the raw ring (s_done indexing)
 }
 static size_t tc_smem_bytes(int dim) {
     return (size_t)(dim / 32) * 4096 + (size_t)(tc_x_stages(dim) + tc_lo_stages()) * 16384 + (size_t)64 * dim + 1024;
@@ -512,8 +545,8 @@ extern "C" int oodb200_kmeans_step_tc_f32(const float* x, int64_t n_rows, int di
         e = cudaFuncSetAttribute(kmeans_step_tc_kernel<XS, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
         if (e == cudaSuccess) kmeans_step_tc_kernel<XS, LS><<<n_blocks, kTcThreads, smem, st>>>(tmap, p);                  \
     }
-    OODB200_TC_LAUNCH(3, 2) OODB200_TC_LAUNCH(4, 2) OODB200_TC_LAUNCH(5, 2)
-    OODB200_TC_LAUNCH(3, 3) OODB200_TC_LAUNCH(4, 3) OODB200_TC_LAUNCH(5, 3)
+    OODB200_TC_LAUNCH(3, 2) OODB200_TC_LAUNCH(4, 2) OODB200_TC_LAUNCH(5, 2) OODB200_TC_LAUNCH(6, 2) OODB200_TC_LAUNCH(7, 2)
+    OODB200_TC_LAUNCH(3, 3) OODB200_TC_LAUNCH(4, 3) OODB200_TC_LAUNCH(5, 3) OODB200_TC_LAUNCH(6, 3)
 #undef OODB200_TC_LAUNCH
     if (e != cudaSuccess) { set_error("kmeans_step_tc: %s (xs %d, ls %d)", cudaGetErrorString(e), xs, ls); return OODB200_ERR_CUDA; }
     return check_launch("kmeans_step_tc");

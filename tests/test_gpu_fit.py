@@ -239,6 +239,7 @@ def test_tcgen05_step_equals_fp32_step(dev):
     tc.tensor_core, fp.tensor_core = True, False
     assert tc.lib.oodb200_kmeans_tc_workspace_bytes(3, 16, 576) > 0
     assert tc.lib.oodb200_kmeans_tc_workspace_bytes(3, 17, 576) == 0 and tc.lib.oodb200_kmeans_tc_workspace_bytes(3, 16, 100) == 0
+    n_exact = 0
     for dim, k, spec in ((576, 16, ((1, 5000), (2, 777), (3, 33), (4, 0), (5, 1500))), (128, 5, ((6, 2000), (7, 1029))),
                          (640, 12, ((9, 1300), (10, 64)))):
         segs = [synth.blob_vectors(s, n, dim, k, 3.0)[0] if n else np.zeros((0, dim), np.float32) for s, n in spec]
@@ -258,9 +259,15 @@ def test_tcgen05_step_equals_fp32_step(dev):
                 torch.cuda.synchronize()
                 out.append((labels, chg, None if ps is None else ps.clone(), None if pc is None else pc.clone()))
         (l_fp, c_fp, ps_fp, pc_fp), (l_fp0, _, _, _), (l_tc, c_tc, ps_tc, pc_tc), (l_tc0, _, _, _) = out
-        assert torch.equal(l_fp, l_tc) and torch.equal(l_fp0, l_tc0) and torch.equal(l_tc, l_tc0), dim
-        assert torch.equal(c_fp, c_tc)
-        assert torch.equal(pc_fp, pc_tc) and torch.equal(ps_fp, ps_tc), dim
+        assert torch.equal(l_fp, l_fp0) and torch.equal(l_tc, l_tc0), dim
+        differ = (l_fp != l_tc)
+        # the two kernels round the cross-term differently (FP32 FMA chain vs split-float tensor-core products): a label
+        # may differ only on a float32 tie (checked against float64 below); with identical labels everything is bit-equal
+        assert differ.float().mean().item() <= 1e-3, dim
+        if not differ.any():
+            n_exact += 1
+            assert torch.equal(c_fp, c_tc)
+            assert torch.equal(pc_fp, pc_tc) and torch.equal(ps_fp, ps_tc), dim
         # labels are the nearest centre in float64 (up to float32 ties)
         off = np.concatenate([[0], np.cumsum(sizes)])
         for g, s in enumerate(segs):
@@ -271,3 +278,6 @@ def test_tcgen05_step_equals_fp32_step(dev):
             lab = l_tc[off[g]:off[g + 1]].cpu().numpy()
             best = d.min(1)
             assert np.all(d[np.arange(len(s)), lab] <= best * (1 + 1e-5) + 1e-7)
+            lab_fp = l_fp[off[g]:off[g + 1]].cpu().numpy()
+            assert np.all(d[np.arange(len(s)), lab_fp] <= best * (1 + 1e-5) + 1e-7)
+    assert n_exact >= 2                                                  # the bit-equality claim was actually exercised
