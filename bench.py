@@ -341,7 +341,7 @@ def run_fit(device, world, rank, n_total, reps, warm):
                          "unit": "GB/s",
                          "achieved": it_bytes / world / lloyd_per_iter / 1e9, "peak": peak,
                          "frac": it_bytes / world / lloyd_per_iter / 1e9 / peak, "algorithmic_bytes_per_iteration": it_bytes,
-                         "traffic": _traffic("C3", "kmeans_step_dram_bytes_per_launch")}}
+                         "traffic": (_traffic("C3", "kmeans_step_dram_bytes_per_vector") or 0) * n_total / world or None}}
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -374,7 +374,9 @@ def run_ours(args, wl):
                    "e2e": {"value": fit["e2e_vectors_per_s"], "unit": "vectors/s (seed + Lloyd + member means + scores + thresholds)",
                            "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                            "note": "activations are produced on the device by the pooling kernel; nothing crosses PCIe"},
-                   "gpu_launches": 3 * fit["lloyd_iterations"] * args.steps, "clocks": clk.summary()}
+                   # per Lloyd iteration: centroid prep, tcgen05 step, 2 x reduce, update; per seeded centre: scan, gather, distance
+                   # pass, potentials, pick; plus centring (4), member means (3), scores (1), 3 radix passes
+                   "gpu_launches": (5 * fit["lloyd_iterations"] + 5 * FIT_K + 11) * args.steps, "clocks": clk.summary()}
             print(json.dumps(out))
         if world > 1:
             dist.destroy_process_group()

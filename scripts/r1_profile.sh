@@ -1,0 +1,13 @@
+#!/bin/bash
+# Round-1 measurement pass on one B200: tests, bench lines, ncu launch lists and full captures (outputs in gpurun_out/).
+set -x
+O=gpurun_out
+python -m pytest tests -x -q -m gpu > $O/r1_pytest_gpu.log 2>&1; tail -2 $O/r1_pytest_gpu.log
+python bench.py --steps 50 --warmup 5 > $O/r1_bench_c2.json 2> $O/r1_bench_c2.err; tail -c 600 $O/r1_bench_c2.json
+python bench.py --workload fit --steps 3 --warmup 1 > $O/r1_bench_fit.json 2> $O/r1_bench_fit.err; tail -c 900 $O/r1_bench_fit.json
+python bench.py --impl reference --steps 1 --warmup 0 > $O/r1_bench_ref.json 2> $O/r1_bench_ref.err; tail -c 400 $O/r1_bench_ref.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r1_launches.csv python bench.py --steps 3 --warmup 3 --fit-n 0 > $O/ncu_l.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/r1_launches_fit.csv python bench.py --workload fit --steps 1 --warmup 1 > $O/ncu_lf.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name regex:'items_kernel|score_kernel' --launch-skip 6 --launch-count 2 -o $O/r1_fmap -f python bench.py --steps 3 --warmup 3 --fit-n 0 --quick > $O/ncu_f1.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name regex:'kmeans_step_tc|sqdist_cand4|seed_scan' --launch-skip 3 --launch-count 3 -o $O/r1_fit -f python bench.py --workload fit --steps 1 --warmup 1 > $O/ncu_f2.log 2>&1
+ls -la $O/*.ncu-rep
