@@ -281,3 +281,79 @@ def test_tcgen05_step_equals_fp32_step(dev):
             lab_fp = l_fp[off[g]:off[g + 1]].cpu().numpy()
             assert np.all(d[np.arange(len(s)), lab_fp] <= best * (1 + 1e-5) + 1e-7)
     assert n_exact >= 2                                                  # the bit-equality claim was actually exercised
+
+
+def test_segment_centring_kernels(dev):
+    """seg_colsum / seg_center: float64 column sums, x - mean and the sum of squares per segment (KMeans.fit centring and
+    `_tolerance`), ragged and empty segments, vector and scalar paths; bit-reproducible."""
+    from ood_in_object_detection_b200 import kmeans
+    be = kmeans.CudaBackend(dev)
+    rng = np.random.default_rng(21)
+    for dim, sizes in ((576, [3001, 0, 517, 64]), (50, [999, 1, 130])):
+        x = (rng.standard_normal((sum(sizes), dim)) * 0.3 + 0.5).astype(np.float32)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        sums = be.colsum(t(x), t(off), len(sizes))
+        assert torch.equal(sums, be.colsum(t(x), t(off), len(sizes)))
+        mean = np.zeros((len(sizes), dim), np.float32)
+        for g, n in enumerate(sizes):
+            ref = x[off[g]:off[g + 1]].sum(0, dtype=np.float64)
+            np.testing.assert_allclose(sums[g].cpu().numpy(), ref, rtol=1e-12, atol=1e-9)
+            mean[g] = (ref / max(n, 1)).astype(np.float32)
+        out, sq = be.center(t(x), t(off), len(sizes), t(mean))
+        for g in range(len(sizes)):
+            ref = x[off[g]:off[g + 1]] - mean[g]
+            assert np.array_equal(out[off[g]:off[g + 1]].cpu().numpy(), ref)
+            np.testing.assert_allclose(sq[g].item(), (ref.astype(np.float64) ** 2).sum(), rtol=1e-12, atol=1e-12)
+
+
+def test_c3_full_size_fit_properties(dev):
+    """BASELINE config C3 at full size (4 M x 576 vectors, 20 classes x K = 16) through size-independent properties:
+    every label is the nearest final centre (float64 check on a sample), the centres are the means of their members,
+    the counts add up, the fit converged strictly (one more assignment changes nothing), and the tensor-core step and
+    the FP32 step agree on the final assignment."""
+    from ood_in_object_detection_b200 import kmeans
+    if torch.cuda.get_device_properties(dev).total_memory < 60e9:
+        pytest.skip("needs ~25 GB of device memory")
+    n_seg, per, dim, k = 20, 200_000, 576, 16
+    g = torch.Generator(device=dev).manual_seed(77)
+    x = torch.empty((n_seg * per, dim), dtype=torch.float32, device=dev)
+    for s in range(n_seg):
+        centres = torch.randn((k, dim), generator=g, device=dev) * (8.0 / dim ** 0.5) + 1.0
+        lab = torch.randint(0, k, (per,), generator=g, device=dev)
+        blk = centres[lab] + torch.randn((per, dim), generator=g, device=dev) / dim ** 0.5
+        x[s * per:(s + 1) * per] = blk / blk.norm(dim=1, keepdim=True)
+        del blk
+    sizes = [per] * n_seg
+    res = kmeans.kmeans_fit_predict_single(x, sizes, k)
+    assert res.seconds["seeding"] == "device"
+    lab = res.labels
+    assert int(lab.min()) >= 0 and int(lab.max()) < k
+    assert all(res.strict), "well-separated mixtures converge strictly"
+    cnt = torch.stack([torch.bincount(lab[s * per:(s + 1) * per].long(), minlength=k) for s in range(n_seg)])
+    assert torch.equal(cnt.float(), res.counts) and int(cnt.sum()) == n_seg * per
+    # nearest centre (float64) on a sample of rows of every segment
+    idx = torch.randint(0, per, (2000,), generator=g, device=dev)
+    for s in range(n_seg):
+        rows = x[s * per + idx].double()
+        d = ((rows[:, None, :] - res.centers[s].double()[None]) ** 2).sum(-1)
+        mine = d.gather(1, lab[s * per + idx].long()[:, None])[:, 0]
+        assert bool((mine <= d.min(1).values * (1 + 1e-6) + 1e-9).all()), s
+    # centres are the member means (float64 reference) for two segments
+    for s in (0, n_seg - 1):
+        seg, sl = x[s * per:(s + 1) * per], lab[s * per:(s + 1) * per].long()
+        ref = torch.zeros((k, dim), dtype=torch.float64, device=dev).index_add_(0, sl, seg.double()) / cnt[s][:, None].double()
+        torch.testing.assert_close(res.centers[s].double(), ref, rtol=1e-5, atol=1e-6)
+    # idempotence of the assignment with the final centres, on both step kernels
+    table, _, _ = kmeans.build_blocks(sizes, 1, 0, dev)
+    seg_k = torch.full((n_seg,), k, dtype=torch.int32, device=dev)
+    xm = torch.stack([x[s * per:(s + 1) * per].mean(0, dtype=torch.float64) for s in range(n_seg)]).float()
+    for tc in (True, False):
+        be = kmeans.CudaBackend(dev)
+        be.tensor_core = tc
+        xc, _ = be.center(x, torch.arange(n_seg + 1, device=dev, dtype=torch.int64) * per, n_seg, xm)
+        l2 = lab.clone()
+        chg = torch.zeros(n_seg, dtype=torch.int32, device=dev)
+        be.step(xc, k, seg_k, (res.centers - xm[:, None, :]).contiguous(), table, None, l2, chg, 0)
+        assert int(chg.sum()) == 0 and torch.equal(l2, lab), tc
+        del xc
