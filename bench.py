@@ -312,8 +312,8 @@ def run_fit(device, world, rank, n_total, reps, warm):
             r = kmeans.kmeans_fit_predict_single(x, gsizes, FIT_K, random_state=10)
         means, counts = kmeans.member_means(x, lsizes, r.labels, FIT_K, group=group)
         off = np.concatenate([[0], np.cumsum(lsizes)]).tolist()
-        d, _ = ops.vec_score(x, off, means.reshape(-1, FIT_D).contiguous(), None, [g * FIT_K for g in range(FIT_CLASSES)],
-                             [FIT_K] * FIT_CLASSES, 1 << ops.METRIC_SLOT["l2"], normalize=False)
+        d, _ = ops.vec_score_one(x, off, means.reshape(-1, FIT_D).contiguous(), None, [g * FIT_K for g in range(FIT_CLASSES)],
+                                 [FIT_K] * FIT_CLASSES, ops.METRIC_SLOT["l2"], normalize=False)     # tcgen05 cross-term (K2b)
         ranks = [select.lower_index(n, 95.0) for n in gsizes]
         thr, _, _ = select.segment_select(d[ops.METRIC_SLOT["l2"]].contiguous(), off, ranks, group=group)
         torch.cuda.synchronize()

@@ -211,6 +211,21 @@ int oodb200_sqdist_cand_f32(const float* x, int dim, const int64_t* seg_off, int
                             const float* cand, int n_cand, const float* closest, float* out_d, double* pot,
                             void* stream);
 
+/* ---- K2b: K2 standalone on the tensor pipe for up to 64 centroids per segment (BASELINE config C5: K = 64): the x.c
+ * cross-term of 'l2' / 'cosine' runs on tcgen05 (kind::tf32, split-float operands), combined like sklearn
+ * (`euclidean_distances`: XX - 2 X.Y^T + YY in float64, cast to float32, sqrt; `cosine_distances`: 1 - cos, clipped).
+ * Replaces `pairwise_distances(cluster, activations, metric).min(axis=0)` (/root/reference/ood_utils.py:2422-2430).
+ *   x [n_rows, dim] float32 contiguous, ALREADY normalised (normalize_rows) when the method normalises; metric =
+ *   OODB200_METRIC_L2 or OODB200_METRIC_COS (for cosine pass the unit-norm centroid rows as `cent`);
+ *   blocks: block b = rows [block_row0[b], block_row1[b]) of segment block_seg[b], at most 512 rows, never straddling
+ *   segments; dist / argmin / decision / thr laid out like vec_score ([3][n_rows], [3][n_seg]); only slot `metric` is written.
+ *   workspace: oodb200_vec_score_tc_workspace_bytes (0 = shape not supported), 256-byte aligned. */
+int64_t oodb200_vec_score_tc_workspace_bytes(int n_seg, int64_t n_rows, int dim);
+int oodb200_vec_score_tc_f32(const float* x, int64_t n_rows, int dim, int n_seg, int metric, const float* cent,
+                             const int64_t* cent_row_off, const int32_t* cent_k, int max_k, const int32_t* block_seg,
+                             const int64_t* block_row0, const int64_t* block_row1, int n_blocks, float* dist,
+                             int32_t* argmin, const double* thr, uint8_t* decision, void* workspace, void* stream);
+
 /* Mean-centring of every segment and the variance behind sklearn's tolerance (KMeans.fit `X -= X.mean(axis=0)`,
  * `_tolerance`; sklearn/cluster/_kmeans.py:283-293, 1487-1497), float64 accumulation, fixed combination order.
  * segment_colsum: sums[g, d] = sum_r x[r, d] over the rows of segment g (the caller divides by the global size).

@@ -40,6 +40,8 @@ SIGNATURES = {
     "oodb200_kmeans_reduce_f32": [_P, _P, _I, _L, _P, _P],
     "oodb200_kmeans_update_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "oodb200_sqdist_cand_f32": [_P, _I, _P, _I, _L, _P, _I, _P, _P, _P, _P],
+    "oodb200_vec_score_tc_workspace_bytes": [_I, _L, _I],
+    "oodb200_vec_score_tc_f32": [_P, _L, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     "oodb200_segment_scratch_doubles": [_I, _I],
     "oodb200_segment_colsum_f64": [_P, _I, _P, _I, _P, _P, _P],
     "oodb200_segment_center_f32": [_P, _I, _P, _I, _P, _P, _P, _P, _P],
@@ -53,7 +55,7 @@ SIGNATURES = {
 }
 _RESTYPE = {"oodb200_last_error": C.c_char_p, "oodb200_fmap_workspace_bytes": C.c_int64,
             "oodb200_kmeans_smem_bytes": C.c_int64, "oodb200_kmeans_tc_workspace_bytes": C.c_int64,
-            "oodb200_segment_scratch_doubles": C.c_int64}
+            "oodb200_segment_scratch_doubles": C.c_int64, "oodb200_vec_score_tc_workspace_bytes": C.c_int64}
 
 _lib = None
 

@@ -459,6 +459,253 @@ __global__ void __launch_bounds__(256) kmeans_tc_prep_kernel(const float* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// K2b: nearest-centroid distance of already pooled vectors on the tensor pipe, K <= 64 (BASELINE config C5: K = 64 clusters
+// per class).  Replaces `pairwise_distances(cluster, activations, metric).min(axis=0)` (/root/reference/ood_utils.py:2422-2430)
+// for 'l2' (sklearn `euclidean_distances`: XX - 2 X.Y^T + YY combined in float64, cast to float32, sqrt) and 'cosine'.
+// Same pipeline as the Lloyd step (128-row tiles, 32-byte-swizzle operands, split-float x), but the centroid image of
+// K = 64 (hi | lo = 128 rows x D) does not fit shared memory: its k-block travels with the rows' k-block through the
+// same ring stage (it is L2 resident), N = 128 for the raw products and 64 for the lo products, 2 x 128 TMEM columns.
+constexpr int kVtThreads = 192;        // warps 0-3 split + epilogue, warp 4 TMA, warp 5 MMA
+constexpr int kVtStages = 4, kVtLo = 2;
+constexpr int kVtCols = 256;
+constexpr uint32_t kVtIdescN128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kVtIdescN64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct VtParams {
+    int dim, kb, n_seg, metric;        // metric: OODB200_METRIC_L2 or OODB200_METRIC_COS
+    int64_t n_rows;
+    const int32_t* cent_k;
+    const float* bimg;                 // [n_seg][kb][4 k-steps][128 rows: 64 hi, 64 lo][8 floats], swizzled
+    const double* cc;                  // [n_seg][64] ||c||^2 (l2)
+    const double* xx;                  // [n_rows] ||x||^2
+    const int32_t* block_seg;
+    const int64_t* block_row0;
+    const int64_t* block_row1;
+    float* dist;                       // [3][n_rows]
+    int32_t* argmin;
+    const double* thr;                 // [3][n_seg] or null
+    uint8_t* decision;
+};
+
+__global__ void __launch_bounds__(kVtThreads, 1) vec_score_tc_kernel(const __grid_constant__ CUtensorMap tmap, const VtParams p) {
+    extern __shared__ unsigned char tc_dyn[];
+    __shared__ __align__(8) uint64_t s_afull[kVtStages], s_done[kVtStages], s_lofull[kVtLo], s_accfull[2];
+    __shared__ uint32_t s_tmem;
+    constexpr uint32_t XS = kVtStages, LS = kVtLo;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    const int g = p.block_seg[b];
+    const int KB = p.kb;
+    const int Kg = p.cent_k[g];
+    const int64_t r0 = p.block_row0[b], r1 = p.block_row1[b];
+    const int n_tiles = (int)((r1 - r0 + kTcRows - 1) / kTcRows);
+    const uint32_t x_base = (tc_smem_u32(tc_dyn) + 1023u) & ~1023u;          // [XS][4 k-steps][128 rows][32 B]
+    const uint32_t b_base = x_base + XS * 16384u;                              // [XS][4 k-steps][128 rows: c_hi, c_lo][32 B]
+    const uint32_t lo_base = b_base + XS * 16384u;                             // [LS][4 k-steps][128 rows][32 B]
+    if (tid == 0) {
+        for (int s = 0; s < kVtStages; ++s) { tc_mbar_init(&s_afull[s], 1); tc_mbar_init(&s_done[s], 1); }
+        for (int s = 0; s < kVtLo; ++s) tc_mbar_init(&s_lofull[s], 4);
+        tc_mbar_init(&s_accfull[0], 1);
+        tc_mbar_init(&s_accfull[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "r"(kVtCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const bool work = Kg > 0;                                                   // a segment without centroids: 1000 / -1 below
+
+    if (warp == 4) {                                                            // TMA producer
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        uint32_t n = 0;
+        for (int t = 0; work && t < n_tiles; ++t) {
+            const int row = (int)(r0 + (int64_t)t * kTcRows);
+            for (int kb = 0; kb < KB; ++kb, ++n) {
+                const uint32_t s = n % XS, u = n / XS;
+                if (u >= 1) tc_mbar_wait(&s_done[s], (u - 1) & 1u);
+                if (tc_elect()) {
+                    tc_mbar_expect_tx(&s_afull[s], 32768u);
+                    tc_tma_3d(x_base + s * 16384u, &tmap, 0, row, kb * 4, &s_afull[s], pol);
+                    tc_bulk_g2s(b_base + s * 16384u, p.bimg + ((size_t)g * KB + kb) * 4096, 16384u, &s_afull[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {                                                     // MMA issuer
+        uint32_t n = 0;
+        for (int t = 0; work && t < n_tiles; ++t) {
+            const uint32_t acc = tmem + (uint32_t)(t & 1) * 128u;
+            for (int kb = 0; kb < KB; ++kb, ++n) {
+                const uint32_t s = n % XS, u = n / XS, sl = n % LS, ul = n / LS;
+                const uint32_t a_raw = x_base + s * 16384u, a_lo = lo_base + sl * 16384u, b_img = b_base + s * 16384u;
+                tc_mbar_wait(&s_afull[s], u & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tc_elect())
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)                              // cols 0-63 += x.c_hi, cols 64-127 += x.c_lo
+                        tc_mma(acc, tc_desc(a_raw + k4 * 4096), tc_desc(b_img + k4 * 4096), kVtIdescN128, (kb | k4) != 0);
+                tc_mbar_wait(&s_lofull[sl], ul & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tc_elect()) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)                              // cols 0-63 += x_lo.c_hi
+                        tc_mma(acc, tc_desc(a_lo + k4 * 4096), tc_desc(b_img + k4 * 4096), kVtIdescN64, 1u);
+                    tc_commit(&s_done[s]);
+                    if (kb == KB - 1) tc_commit(&s_accfull[t & 1]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {                                                                    // warps 0-3: split, then epilogue of rows 32*warp ..
+        uint32_t n = 0;
+        const int slot = p.metric;
+        const double thr = p.thr ? p.thr[(size_t)slot * p.n_seg + g] : 0.0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int e = t & 1, j = t >> 1;
+            for (int kb = 0; work && kb < KB; ++kb, ++n) {
+                const uint32_t s = n % XS, u = n / XS, sl = n % LS;
+                tc_mbar_wait(&s_afull[s], u & 1u);
+                if (n >= LS) tc_mbar_wait(&s_done[(n - LS) % XS], ((n - LS) / XS) & 1u);
+                const uint32_t src = x_base + s * 16384u + (uint32_t)warp * 4096u;
+                const uint32_t dst = lo_base + sl * 16384u + (uint32_t)warp * 4096u;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float4 v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t off = (uint32_t)((half * 4 + q) * 32 + lane) * 16u;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w) : "r"(src + off));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t off = (uint32_t)((half * 4 + q) * 32 + lane) * 16u;
+                        uint32_t o[4];
+                        const float el[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float hi = __uint_as_float(__float_as_uint(el[c]) & 0xffffe000u);
+                            o[c] = (__float_as_uint(el[c] - hi) + 0x1000u) & 0xffffe000u;
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(&s_lofull[sl]);
+            }
+            // ---- epilogue: lane = row
+            const int64_t row = r0 + (int64_t)t * kTcRows + warp * 32 + lane;
+            const bool valid = row < r1;
+            float best = FLT_MAX;
+            int barg = -1;
+            if (work) {
+                tc_mbar_wait(&s_accfull[e], (uint32_t)j & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const double xx = valid ? p.xx[row] : 1.0;
+                const float inv_norm = (float)(1.0 / sqrt(xx > 0.0 ? xx : 1.0));
+#pragma unroll 1
+                for (int c16 = 0; c16 < 4; ++c16) {
+                    uint32_t d[16], f[16];
+                    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)e * 128u + (uint32_t)c16 * 16u;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]),
+                          "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+                        : "r"(taddr));
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(f[0]), "=r"(f[1]), "=r"(f[2]), "=r"(f[3]), "=r"(f[4]), "=r"(f[5]), "=r"(f[6]), "=r"(f[7]), "=r"(f[8]),
+                          "=r"(f[9]), "=r"(f[10]), "=r"(f[11]), "=r"(f[12]), "=r"(f[13]), "=r"(f[14]), "=r"(f[15])
+                        : "r"(taddr + 64u));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int k = c16 * 16 + i;
+                        if (k < Kg) {
+                            const float dot = __uint_as_float(d[i]) + __uint_as_float(f[i]);
+                            float val;
+                            if (p.metric == OODB200_METRIC_L2)                  // XX - 2 X.Y + YY in float64, cast, clamp (sklearn)
+                                val = fmaxf((float)(xx - 2.0 * (double)dot + p.cc[(size_t)g * 64 + k]), 0.f);
+                            else                                                // 1 - cos, clipped to [0, 2] (sklearn cosine_distances)
+                                val = fminf(fmaxf(1.0f - dot * inv_norm, 0.f), 2.f);
+                            if (val < best) { best = val; barg = k; }           // strict <: first minimum
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+            if (valid) {
+                const size_t o = (size_t)slot * p.n_rows + row;
+                const float dv = work ? (p.metric == OODB200_METRIC_L2 ? sqrtf(best) : best) : 1000.f;   // no cluster: ood_utils.py:2159-2164
+                p.dist[o] = dv;
+                p.argmin[o] = barg;
+                if (p.decision) p.decision[o] = (thr == thr && (double)dv < thr) ? 1 : 0;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kVtCols) : "memory");
+    }
+}
+
+// centroids of every segment -> streamed image [kb][4 k-steps][128 rows: 64 hi pieces, 64 lo pieces][8 floats] + ||c||^2
+__global__ void __launch_bounds__(256) vec_score_tc_prep_kernel(const float* __restrict__ cent, const int64_t* __restrict__ cent_row_off,
+                                                                const int32_t* __restrict__ cent_k, int dim, float* __restrict__ bimg,
+                                                                double* __restrict__ cc) {
+    const int g = blockIdx.x;
+    const int Kg = cent_k[g], KB = dim / 32;
+    const float* __restrict__ cg = cent + (size_t)cent_row_off[g] * dim;
+    uint32_t* __restrict__ img = reinterpret_cast<uint32_t*>(bimg) + (size_t)g * KB * 4096;
+    for (int idx = threadIdx.x; idx < 64 * dim; idx += blockDim.x) {
+        const int n = idx / dim, d = idx - n * dim;
+        const float c = n < Kg ? cg[(size_t)n * dim + d] : 0.f;
+        const uint32_t hi = tf32_rna(c);
+        const uint32_t lo = tf32_rna(c - __uint_as_float(hi));
+        const int kb = d >> 5, kc = d & 31, k4 = kc >> 3, ch = (kc >> 2) & 1;
+        const int off = kb * 4096 + k4 * 1024 + (n >> 3) * 64 + (n & 7) * 8 + ((ch ^ ((n >> 2) & 1)) << 2) + (kc & 3);
+        img[off] = hi;
+        img[off + 512] = lo;                                       // rows 64-127 of the same k-step block
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int kk = warp; kk < 64; kk += 8) {
+        double s = 0.0;
+        if (kk < Kg)
+            for (int d = lane; d < dim; d += 32) s += (double)cg[(size_t)kk * dim + d] * (double)cg[(size_t)kk * dim + d];
+        for (int o = 16; o > 0; o >>= 1) {
+            int lo = __double2loint(s), hi = __double2hiint(s);
+            lo = __shfl_xor_sync(0xffffffffu, lo, o);
+            hi = __shfl_xor_sync(0xffffffffu, hi, o);
+            s += __hiloint2double(hi, lo);
+        }
+        if (lane == 0) cc[(size_t)g * 64 + kk] = s;
+    }
+}
+
+// xx[r] = sum_d x[r, d]^2 in float64, one warp per row
+__global__ void __launch_bounds__(256) row_sqnorm_kernel(const float* __restrict__ x, int dim, int64_t n_rows, double* __restrict__ xx) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_rows; r += (int64_t)gridDim.x * 8) {
+        double s = 0.0;
+        for (int d = lane; d < dim; d += 32) { const double v = (double)__ldg(x + r * dim + d); s += v * v; }
+        for (int o = 16; o > 0; o >>= 1) {
+            int lo = __double2loint(s), hi = __double2hiint(s);
+            lo = __shfl_xor_sync(0xffffffffu, lo, o);
+            hi = __shfl_xor_sync(0xffffffffu, hi, o);
+            s += __hiloint2double(hi, lo);
+        }
+        if (lane == 0) xx[r] = s;
+    }
+}
+
 typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -550,4 +797,55 @@ extern "C" int oodb200_kmeans_step_tc_f32(const float* x, int64_t n_rows, int di
 #undef OODB200_TC_LAUNCH
     if (e != cudaSuccess) { set_error("kmeans_step_tc: %s (xs %d, ls %d)", cudaGetErrorString(e), xs, ls); return OODB200_ERR_CUDA; }
     return check_launch("kmeans_step_tc");
+}
+
+extern "C" int64_t oodb200_vec_score_tc_workspace_bytes(int n_seg, int64_t n_rows, int dim) {
+    if (dim < 128 || dim % 32 != 0 || dim > 2048 || n_seg < 1 || n_rows < 0) return 0;
+    return (int64_t)n_seg * ((int64_t)(dim / 32) * 16384 + 64 * 8) + n_rows * 8 + 256;
+}
+
+extern "C" int oodb200_vec_score_tc_f32(const float* x, int64_t n_rows, int dim, int n_seg, int metric, const float* cent,
+                                        const int64_t* cent_row_off, const int32_t* cent_k, int max_k, const int32_t* block_seg,
+                                        const int64_t* block_row0, const int64_t* block_row1, int n_blocks, float* dist,
+                                        int32_t* argmin, const double* thr, uint8_t* decision, void* workspace, void* stream) {
+    OODB200_REQUIRE(oodb200_vec_score_tc_workspace_bytes(n_seg > 0 ? n_seg : 1, n_rows, dim) > 0,
+                    "vec_score_tc: needs dim %% 32 == 0, 128 <= dim <= 2048 (dim = %d)", dim);
+    OODB200_REQUIRE(metric == OODB200_METRIC_L2 || metric == OODB200_METRIC_COS, "vec_score_tc: metric must be l2 or cosine");
+    OODB200_REQUIRE(max_k >= 0 && max_k <= 64, "vec_score_tc: at most 64 centroids per segment (max_k = %d)", max_k);
+    OODB200_REQUIRE(n_rows >= 0 && n_rows < INT_MAX && n_blocks >= 0, "vec_score_tc: bad size");
+    if (n_blocks == 0 || n_rows == 0) return OODB200_OK;
+    OODB200_REQUIRE(x && cent && cent_row_off && cent_k && block_seg && block_row0 && block_row1 && dist && argmin && workspace,
+                    "vec_score_tc: null pointer");
+    OODB200_REQUIRE(!decision || thr, "vec_score_tc: decision needs thresholds");
+    OODB200_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)workspace & 255) == 0, "vec_score_tc: x must be 16-byte, workspace 256-byte aligned");
+    TcEncodeFn enc = tc_encode_fn();
+    OODB200_REQUIRE(enc != nullptr, "vec_score_tc: cuTensorMapEncodeTiled is not available from this driver");
+    const int KB = dim / 32;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {8, (cuuint64_t)n_rows, (cuuint64_t)dim / 8};
+    const cuuint64_t gstride[2] = {(cuuint64_t)dim * 4, 32};
+    const cuuint32_t box[3] = {8, (cuuint32_t)kTcRows, 4};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), gdim, gstride, box, estride,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("vec_score_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return OODB200_ERR_CUDA; }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* bimg = reinterpret_cast<float*>(workspace);
+    double* cc = reinterpret_cast<double*>(bimg + (size_t)n_seg * KB * 4096);
+    double* xx = cc + (size_t)n_seg * 64;
+    vec_score_tc_prep_kernel<<<n_seg, 256, 0, st>>>(cent, cent_row_off, cent_k, dim, bimg, cc);
+    int rc = check_launch("vec_score_tc_prep");
+    if (rc) return rc;
+    long long gx = (n_rows + 7) / 8;
+    if (gx > 148LL * 16) gx = 148LL * 16;
+    row_sqnorm_kernel<<<(int)gx, 256, 0, st>>>(x, dim, n_rows, xx);
+    rc = check_launch("row_sqnorm");
+    if (rc) return rc;
+    const size_t smem = (size_t)(2 * kVtStages + kVtLo) * 16384 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(vec_score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("vec_score_tc: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+    VtParams p = {dim, KB, n_seg, metric, n_rows, cent_k, bimg, cc, xx, block_seg, block_row0, block_row1, dist, argmin, thr, decision};
+    vec_score_tc_kernel<<<n_blocks, kVtThreads, smem, st>>>(tmap, p);
+    return check_launch("vec_score_tc");
 }

@@ -187,8 +187,24 @@ class BlockTable:
     super_owner_counts: List[int]  # super-blocks per rank
 
 
+_BLOCK_CACHE: dict = {}
+
+
 def build_blocks(global_sizes: Sequence[int], world: int, rank: int, device) -> tuple:
-    """Row sharding + block tables.  Rank r owns a contiguous range of super-blocks of every segment."""
+    """Row sharding + block tables.  Rank r owns a contiguous range of super-blocks of every segment.
+    The tables only depend on (sizes, world, rank): the last few are kept (a C3 table has 7.8 k blocks built in Python)."""
+    key = (tuple(int(n) for n in global_sizes), int(world), int(rank), str(device))
+    hit = _BLOCK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    out = _build_blocks(global_sizes, world, rank, device)
+    if len(_BLOCK_CACHE) >= 8:
+        _BLOCK_CACHE.pop(next(iter(_BLOCK_CACHE)))
+    _BLOCK_CACHE[key] = out
+    return out
+
+
+def _build_blocks(global_sizes: Sequence[int], world: int, rank: int, device) -> tuple:
     seg_l, r0_l, r1_l, sfirst = [], [], [], [0]
     local_sizes, local_off = [], [0]
     super_seg_first = [0]

@@ -815,8 +815,8 @@ class DistanceMethod(OODMethod):
             thr = np.full((3, nc), np.nan)
             if self.thresholds is not None:
                 thr[m] = ops.pack_thresholds({m: self.thresholds}, nc)[m].reshape(3, nc)[s]
-            d, _, de = ops.vec_score(x, seg_off, cent, unit, row_off, kk, 1 << m, normalize=self.normalize_activations,
-                                     thr=torch.from_numpy(thr).to(dev))
+            d, _, de = ops.vec_score_one(x, seg_off, cent, unit, row_off, kk, m, normalize=self.normalize_activations,
+                                         thr=torch.from_numpy(thr).to(dev))
             o = out_pos[order]
             dist[o], dec[o], cls_used[o], stride_of[o] = d[m].cpu().numpy(), de[m].cpu().numpy(), cl, s
         return counts, dist, dec, cls_used, stride_of
@@ -1121,7 +1121,7 @@ class DistanceMethod(OODMethod):
             cent = torch.from_numpy(cent_np).to(dev)
             unit = torch.from_numpy(ops._unit_rows(cent_np)).to(dev) if self.metric == 'cosine' else None
             seg_off = np.concatenate([[0], np.cumsum(sizes)]).tolist()
-            d, _ = ops.vec_score(x, seg_off, cent, unit, row_off, kk, 1 << m, normalize=False)
+            d, _ = ops.vec_score_one(x, seg_off, cent, unit, row_off, kk, m, normalize=False)
             d = d[m] if self.activations_on_device else d[m].cpu().numpy()
             for i, c in enumerate(classes):
                 scores[c][s] = d[seg_off[i]:seg_off[i + 1]]

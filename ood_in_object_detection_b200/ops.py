@@ -376,6 +376,72 @@ def vec_score(x: torch.Tensor, seg_off: Sequence[int], cent: torch.Tensor, cent_
     return dist, arg
 
 
+def vec_score_tc(x: torch.Tensor, seg_off: Sequence[int], cent: torch.Tensor, cent_row_off: Sequence[int],
+                 cent_k: Sequence[int], metric: str, thr: Optional[torch.Tensor] = None, out=None):
+    """K2b: like vec_score for ONE of 'l2' / 'cosine' with up to 64 centroids per segment, the x.c cross-term on the
+    tensor cores (csrc/kmeans_tc.cu::vec_score_tc_kernel).  x [n, D] float32 contiguous on the device, already
+    normalised when the method normalises (ops.normalize_rows); for 'cosine' pass the unit-norm centroid rows.
+    -> (dist [3, n], argmin [3, n][, decision [3, n]]) with only the metric's slot written (others: NaN / -1 / 0)."""
+    from . import kmeans
+    lib = _lib.load()
+    dev = x.device
+    slot = METRIC_SLOT[metric]
+    if metric not in ("l2", "cosine"):
+        raise ValueError("vec_score_tc: metric must be 'l2' or 'cosine'")
+    for name, ten in (("x", x), ("cent", cent)):
+        if ten.dtype != torch.float32 or ten.device != dev:
+            raise TypeError(f"vec_score_tc: {name} must be a float32 tensor on {dev}")
+    x, cent = x.contiguous(), cent.contiguous()
+    n, dim = int(x.shape[0]), int(x.shape[1])
+    n_seg = len(seg_off) - 1
+    ws_bytes = int(lib.oodb200_vec_score_tc_workspace_bytes(max(n_seg, 1), n, dim))
+    if not ws_bytes:
+        raise ValueError(f"vec_score_tc: dim must be a multiple of 32 in [128, 2048], got {dim}")
+    if out is None:
+        dist = torch.full((3, n), float("nan"), dtype=torch.float32, device=dev)
+        arg = torch.full((3, n), -1, dtype=torch.int32, device=dev)
+    else:
+        dist, arg = out
+    dec = None
+    if thr is not None:
+        if thr.dtype != torch.float64 or tuple(thr.shape) != (3, n_seg) or thr.device != dev:
+            raise TypeError("vec_score_tc: thr must be a float64 [3, n_seg] tensor on the device of x")
+        thr = thr.contiguous()
+        dec = torch.zeros((3, n), dtype=torch.uint8, device=dev)
+    sizes = [int(seg_off[g + 1] - seg_off[g]) for g in range(n_seg)]
+    table, _, _ = kmeans.build_blocks(sizes, 1, 0, dev)
+    t = lambda a, dt: torch.tensor(list(a), dtype=dt, device=dev)
+    crow_d, ck_d = t(cent_row_off, torch.int64), t(cent_k, torch.int32)
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = (ws.data_ptr() + 255) & ~255
+    _lib.check(lib.oodb200_vec_score_tc_f32(_ptr(x), n, dim, n_seg, slot, _ptr(cent), _ptr(crow_d), _ptr(ck_d),
+                                            int(max(list(cent_k) + [0])), _ptr(table.seg), _ptr(table.row0), _ptr(table.row1),
+                                            table.n_blocks, _ptr(dist), _ptr(arg), _ptr(thr), _ptr(dec), C.c_void_p(ws_ptr),
+                                            _stream()), "oodb200_vec_score_tc_f32")
+    if thr is not None:
+        return dist, arg, dec
+    return dist, arg
+
+
+TC_SCORE_MIN_ROWS = 4096      # below this the FP32 kernel's single launch wins over prep + norms + tensor-core launch
+
+
+def vec_score_one(x: torch.Tensor, seg_off: Sequence[int], cent: torch.Tensor, cent_unit: Optional[torch.Tensor],
+                  cent_row_off: Sequence[int], cent_k: Sequence[int], slot: int, normalize: bool = True,
+                  thr: Optional[torch.Tensor] = None):
+    """One metric of K2 on pooled vectors: 'l2' / 'cosine' go to the tensor-core kernel (vec_score_tc) when the shape
+    fits (D % 32 == 0, 128 <= D <= 2048, <= 64 centroids per segment, >= TC_SCORE_MIN_ROWS rows; OODB200_VEC_TC=0
+    disables), everything else to the FP32 kernel.  Same return value as vec_score."""
+    import os
+    name = {v: k for k, v in METRIC_SLOT.items()}[slot]
+    n, dim = int(x.shape[0]), int(x.shape[1])
+    if (name in ("l2", "cosine") and n >= TC_SCORE_MIN_ROWS and dim % 32 == 0 and 128 <= dim <= 2048
+            and max(list(cent_k) + [0]) <= 64 and os.environ.get("OODB200_VEC_TC", "1") != "0"):
+        xs = normalize_rows(x) if normalize else x
+        return vec_score_tc(xs, seg_off, cent_unit if name == "cosine" else cent, cent_row_off, cent_k, name, thr=thr)
+    return vec_score(x, seg_off, cent, cent_unit, cent_row_off, cent_k, 1 << slot, normalize=normalize, thr=thr)
+
+
 def dist_indness(dist: torch.Tensor, slot: torch.Tensor, thr: torch.Tensor, dmin: torch.Tensor, dmax: torch.Tensor,
                  clip: bool = True) -> torch.Tensor:
     """Intended `DistanceMethod.compute_indness` (ood_utils.py:1599-1604) for n distances; slot [n] int32 indexes the

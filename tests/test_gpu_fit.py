@@ -357,3 +357,56 @@ def test_c3_full_size_fit_properties(dev):
         be.step(xc, k, seg_k, (res.centers - xm[:, None, :]).contiguous(), table, None, l2, chg, 0)
         assert int(chg.sum()) == 0 and torch.equal(l2, lab), tc
         del xc
+
+
+def test_tcgen05_vector_scoring_c5_shapes(dev):
+    """K2b (tcgen05 cross-term, K = 64 clusters per class: BASELINE config C5) vs the float64 statement of sklearn's
+    `euclidean_distances` / `cosine_distances` and vs the FP32 vec_score kernel: distances within the 1e-3 tier the
+    north star grants the tensor-core path (measured ~1e-6), arg-min equal except float32 ties, decisions equal away
+    from the threshold.  YOLOv8x channel counts (320 / 640), ragged segments, K < 64, a segment without centroids."""
+    from ood_in_object_detection_b200 import ops
+    rng = np.random.default_rng(64)
+    for dim, spec in ((640, ((300, 64), (80, 64), (0, 64), (1500, 37), (513, 0), (129, 1))), (320, ((700, 64), (33, 5)))):
+        sizes, ks = [n for n, _ in spec], [k for _, k in spec]
+        n = sum(sizes)
+        x = np.abs(rng.standard_normal((n, dim))).astype(np.float32)
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        cent = np.abs(rng.standard_normal((sum(ks), dim))).astype(np.float32)
+        cent = (0.7 * cent / np.linalg.norm(cent, axis=1, keepdims=True)).astype(np.float32)
+        cunit = (cent / np.maximum(np.linalg.norm(cent, axis=1, keepdims=True), 1e-12)).astype(np.float32)
+        off = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+        crow = np.concatenate([[0], np.cumsum(ks)])[:-1].tolist()
+        xd, cd, cud = torch.from_numpy(x).to(dev), torch.from_numpy(cent).to(dev), torch.from_numpy(cunit).to(dev)
+        d_fp, a_fp = ops.vec_score(xd, off, cd, cud, crow, ks, 0b110, normalize=False)
+        for metric, cmat in (("l2", cd), ("cosine", cud)):
+            slot = ops.METRIC_SLOT[metric]
+            # thresholds: the median distance of every segment
+            ref_d, ref_a = np.full(n, 1000.0), np.full(n, -1)
+            for g, (a, b) in enumerate(zip(off[:-1], off[1:])):
+                if ks[g] == 0 or a == b:
+                    continue
+                xs, cs = x[a:b].astype(np.float64), cent[crow[g]:crow[g] + ks[g]].astype(np.float64)
+                if metric == "l2":
+                    dm = np.sqrt(np.maximum(((xs ** 2).sum(1)[:, None] - 2 * xs @ cs.T + (cs ** 2).sum(1)[None]).astype(np.float32), 0))
+                else:
+                    cu = cunit[crow[g]:crow[g] + ks[g]].astype(np.float64)
+                    dm = np.clip(1.0 - (xs / np.linalg.norm(xs, axis=1, keepdims=True)) @ cu.T, 0, 2)
+                ref_d[a:b], ref_a[a:b] = dm.min(1), dm.argmin(1)
+            thr = np.full((3, len(sizes)), np.nan)
+            for g, (a, b) in enumerate(zip(off[:-1], off[1:])):
+                if b > a and ks[g]:
+                    thr[slot, g] = np.median(ref_d[a:b])
+            dist, arg, dec = ops.vec_score_tc(xd, off, cmat, crow, ks, metric, thr=torch.from_numpy(thr).to(dev))
+            torch.cuda.synchronize()
+            got, ga = dist[slot].cpu().numpy(), arg[slot].cpu().numpy()
+            np.testing.assert_allclose(got, ref_d, rtol=1e-3, atol=1e-6)          # the tier of the tensor-core path
+            np.testing.assert_allclose(got, ref_d, rtol=2e-5, atol=2e-6)          # what split-float operands actually give
+            np.testing.assert_allclose(got, d_fp[slot].cpu().numpy(), rtol=2e-5, atol=2e-6)
+            diff = ga != ref_a
+            assert diff.mean() <= 2e-3
+            for g, (a, b) in enumerate(zip(off[:-1], off[1:])):
+                if ks[g] == 0:
+                    assert (got[a:b] == 1000).all() and (ga[a:b] == -1).all() and (dec[slot, a:b] == 0).all()
+                elif b > a:
+                    near = np.abs(ref_d[a:b] - thr[slot, g]) <= 1e-4 * abs(thr[slot, g])
+                    assert np.array_equal(dec[slot, a:b].cpu().numpy()[~near], (ref_d[a:b] < thr[slot, g]).astype(np.uint8)[~near])
