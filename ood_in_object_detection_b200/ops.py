@@ -229,14 +229,16 @@ _workspaces = {}
 
 
 def _workspace(batch: DetectionBatch, nc: int) -> torch.Tensor:
-    """Scratch for the pooling kernels (grown on demand, one per device; kernels on one stream reuse it in order)."""
+    """Scratch for the pooling kernels, grown on demand: one per (device, stream) -- kernels on one stream reuse it in
+    order, passes issued on different streams (sub-batches side by side) must not share work lists."""
     lib = _lib.load()
     need = int(lib.oodb200_fmap_workspace_bytes(batch.n, int(nc), batch.map_chw.ctypes.data_as(C.c_void_p)))
     dev = batch.boxes.device
-    ws = _workspaces.get(dev)
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
-        _workspaces[dev] = ws
+        _workspaces[key] = ws
     return ws
 
 
