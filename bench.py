@@ -46,7 +46,7 @@ FMAP_METRICS = ("l1", "cosine")
 LOGIT_METHODS = ("MSP", "Energy", "MaxLogit")
 CPU_SAMPLE_IMAGES = 6
 FIT_D, FIT_K, FIT_CLASSES = 576, 16, 20
-KERNELS_PER_STEP = 5            # plan_kernel, geo_kernel, items_kernel, score_kernel, logit_kernel (+ one small memset)
+KERNELS_PER_STEP = 4            # plan_geo_kernel, items_kernel, score_kernel, logit_kernel (+ one small memset)
 
 
 # ----------------------------------------------------------------------------------------- helpers
@@ -488,7 +488,7 @@ def run_ours(args, wl):
         res_f.append(Results(orig_img=shape, boxes=pin(b6), extra_item=([hm[i] for hm in h_maps], pin(det["strides"][i]))))
         res_l.append(Results(orig_img=shape, boxes=pin(b6), extra_item=pin(det["logits"][i])))
     h2d = sum(m.numel() * 4 for m in h_maps) + sum(r.boxes.data.numel() * 4 + r.extra_item[1].numel() * 4 for r in res_f) \
-        + len(LOGIT_METHODS) * sum(r.extra_item.numel() * 4 + r.boxes.data.shape[0] * 4 for r in res_l)
+        + sum(r.extra_item.numel() * 4 + r.boxes.data.shape[0] * 4 for r in res_l)      # logits + classes, uploaded once
     import logging
     log = logging.getLogger("bench")
     log.setLevel(logging.ERROR)

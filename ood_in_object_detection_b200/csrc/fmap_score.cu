@@ -4,10 +4,10 @@
 // with output 1x1, adaptive sampling grid, aligned=False) and the per-box loop of
 // /root/reference/ood_utils.py:2038-2180 (+ :2404-2409 normalize, :2422-2430 pairwise distance + min).
 //
-// Launches per batch: memset(16 B) -> plan_kernel -> geo_kernel -> items_kernel -> score_kernel.
-//  plan_kernel   one warp per image: quirk-Q1 class / output slot of every box (ballot prefix ranks) and the position of
-//                every box's work items in the item list.
-//  geo_kernel    one warp per box: ROI geometry and the separable RoIAlign weights.  With a 1x1 output bin
+// Launches per batch: memset(counters) -> plan_geo_kernel -> items_kernel -> score_kernel.
+//  plan_geo_kernel  one CTA per image.  Warp 0: quirk-Q1 class / output slot of every box (ballot prefix ranks) and the
+//                position of every box's work items in the item list.  Then one warp per box: ROI geometry and the
+//                separable RoIAlign weights.  With a 1x1 output bin
 //                    sum_{iy,ix} bilinear(y_iy, x_ix) = sum_r sum_c wy[r] wx[c] v[r,c]
 //                because both the bilinear weights and the "sample outside [-1,H]x[-1,W] contributes 0" mask are
 //                products of a y-term and an x-term.  Sample coordinates use the float32 operation order of the
@@ -17,19 +17,25 @@
 //                no tail of big boxes.  A window is addressed in 16-byte chunks (NCHW rows are 16-byte aligned for the
 //                usual map widths): lane = chunk, one LDG.128 per lane per channel, 8 channels in flight, 4 FMAs per load
 //                against the lane's fixed weight vector, and ONE transposing butterfly per 8 channels instead of 8 warp
-//                reductions.  Small windows put 2/4/8 channels into one 32-lane request.
-//  score_kernel  one warp per box: L2 norm, then L1 / L2 / cosine against the K centroids of (class, stride) in one
-//                sweep over the L2-resident table (128-bit loads, vector in registers, several rows in flight),
-//                first-minimum arg-min and the float64 threshold compare.
+//                reductions.  Small windows put 2/4/8 channels into one 32-lane request.  Its prologue groups the boxes
+//                by (stride, class) for the score kernel (counting sort on the plan's histogram).
+//  score_kernel  CTAs per (stride, class) group: the group's K centroid rows are staged once into shared memory by
+//                bulk-async copies; one warp per box: vector in registers, L2 norm, then L1 / L2 / cosine against the K
+//                rows in one sweep, first-minimum arg-min and the float64 threshold compare.
 // Every pooled element is produced by exactly one warp in a fixed order: results do not depend on scheduling.
 // What bounds the gather on B200 (scripts/micro/*.cu): an L2 miss always moves a whole 128-byte line
 // from HBM while an NCHW window row is 8..52 bytes, so the HBM traffic of this kernel is the set of LINES the windows touch.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
 
 namespace oodb200 {
+
+namespace cg = cooperative_groups;
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -127,14 +133,14 @@ __device__ __forceinline__ float axis_weight(float start, float size, int grid, 
     if (row > 0) {
         float f = ((float)(row - 1) - start) * inv - 0.5f;
         if (f > (float)grid) f = (float)grid;
-        int v = (int)floorf(f) - 2;
+        int v = (int)floorf(f) - 1;                  // one sample of slack for the rounding of f
         lo = v < 0 ? 0 : v;
     }
     if (row < extent - 1) {
         float f = ((float)(row + 1) - start) * inv - 0.5f;
         if (f < -4.f) f = -4.f;
         if (f > (float)grid) f = (float)grid;
-        int v = (int)ceilf(f) + 2;
+        int v = (int)ceilf(f) + 1;
         hi = v > grid - 1 ? grid - 1 : v;
     }
     float acc = 0.f;
@@ -148,83 +154,26 @@ __device__ __forceinline__ float axis_weight(float start, float size, int grid, 
     return acc;
 }
 
-// ---------------------------------------------------------------------------------------------- plan
-// plan_kernel (one warp per image): quirk Q1 (ood_utils.py:2152-2154: the class of the box with the same IN-STRIDE index,
-// stride-major output) and the position of every box in the work list.  Ranks come from ballot prefixes over chunks of
-// 32 boxes; category 3 = "stride outside {0,1,2}" (never pooled by the reference either: answered here).
-__global__ void __launch_bounds__(32) plan_kernel(const FmapParams p) {
-    const int img = blockIdx.x, lane = threadIdx.x;
-    const int b0 = p.img_start[img], m = p.img_start[img + 1] - b0;
-    const unsigned lt = (1u << lane) - 1u;
-    int cnt[4] = {0, 0, 0, 0};
-    for (int c0 = 0; c0 < m; c0 += 32) {
-        const int b = c0 + lane;
-        const int s = b < m ? p.stride_idx[b0 + b] : -2;
-        const int cat = b < m ? ((s >= 0 && s <= 2) ? s : 3) : 4;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) cnt[t] += __popc(__ballot_sync(kFull, cat == t));
-    }
-    // this image's range of the work list, heaviest stride (most channels) first; items of one stride are slice-major
-    const int tot = cnt[2] * p.ns[2] + cnt[1] * p.ns[1] + cnt[0] * p.ns[0];
-    int base = 0;
-    if (lane == 0 && tot) base = atomicAdd(&p.counters[0], tot);
-    base = __shfl_sync(kFull, base, 0);
-    if (lane == 0 && p.cent && cnt[0] + cnt[1] + cnt[2]) atomicAdd(&p.counters[2], cnt[0] + cnt[1] + cnt[2]);
-    int item0[3];
-    item0[2] = base;
-    item0[1] = base + cnt[2] * p.ns[2];
-    item0[0] = item0[1] + cnt[1] * p.ns[1];
-    int run[4] = {0, 0, 0, 0};
-    for (int c0 = 0; c0 < m; c0 += 32) {
-        const int b = c0 + lane;
-        const int s = b < m ? p.stride_idx[b0 + b] : -2;
-        const int cat = b < m ? ((s >= 0 && s <= 2) ? s : 3) : 4;
-        int j = 0, before = 0, nb = 0, it0 = 0;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const unsigned mk = __ballot_sync(kFull, cat == t);
-            if (cat == t) { j = run[t] + __popc(mk & lt); nb = cnt[t]; if (t < 3) it0 = item0[t]; }
-            if (t < cat) before += cnt[t];
-            run[t] += __popc(mk);
-        }
-        if (b >= m) continue;
-        const bool ok = cat < 3;
-        int cls_u = p.cls ? p.cls[b0 + b] : 0, out = b0 + b;
-        if (p.compat_q1) {
-            cls_u = ok ? p.cls[b0 + j] : -1;
-            out = b0 + before + j;
-        }
-        p.cls_used[b0 + b] = cls_u;
-        p.out_index[b0 + b] = out;
-        if (ok) {
-            p.ipos[b0 + b] = make_int2(it0 + j, nb);  // item(sl) = pos0 + sl * nb
-            if (p.cent) atomicAdd(&p.hist[(cls_u >= 0 && cls_u < p.nc) ? cat * p.nc + cls_u : 3 * p.nc], 1);
-        } else if (p.cent) {
-            for (int k = 0; k < OODB200_N_METRICS; ++k)
-                if (p.metric_mask >> k & 1) {
-                    const size_t o = (size_t)k * p.n + out;
-                    p.dist[o] = nanf("");
-                    p.argmin[o] = -1;
-                    p.decision[o] = 0;
-                }
-        }
-    }
-}
+// ---------------------------------------------------------------------------------------------- plan + geometry
+// plan_geo_kernel, one thread-block CLUSTER per image (1-8 CTAs, chosen from the mean number of boxes per image).
+//  warp 0 of CTA 0: quirk Q1 (ood_utils.py:2152-2154: the class of the box with the same IN-STRIDE index, stride-major
+//  output) and the position of every box in the work list.  Ranks come from ballot prefixes over chunks of 32 boxes;
+//  category 3 = "stride outside {0,1,2}" (never pooled by the reference either: answered here).  Results go to global
+//  memory (the later kernels read them) and, for the first kPgCap boxes of the image, to CTA 0's shared memory, which the
+//  other CTAs of the cluster read through distributed shared memory after the cluster barrier.
+//  all warps of the cluster, one box per warp at a time: ROI geometry (predict.py:64-70 -> roi_align, aligned=False), the
+//  separable weights and the box's self-contained item records.  The first box's inputs are requested before the plan
+//  finishes.
+constexpr int kPgThreads = 1024, kPgWarps = kPgThreads / 32, kPgCap = 1024;
 
-// geo_kernel (one warp per box): ROI geometry (predict.py:64-70 -> roi_align, aligned=False), separable weights, and
-// the box's self-contained item records.
-__global__ void __launch_bounds__(kThreads) geo_kernel(const FmapParams p) {
+struct BoxGeo {
+    int ylo, xa, wh, nxc;
+    float count;
+};
+
+// ROI geometry + separable weights of one box (one warp); writes the weights, returns what the item records need.
+__device__ __forceinline__ BoxGeo geo_compute(const FmapParams& p, int box, int s, float4 bx) {
     const int lane = threadIdx.x & 31;
-    const int box = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (box >= p.n) return;
-    // independent loads first: one round trip instead of a chain
-    const int s = p.stride_idx[box];
-    const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)box);
-    const int2 ip = p.ipos[box];
-    const int out = p.out_index[box];
-    const int im = p.img_idx[box];
-    if (s < 0 || s > 2) return;
-    const unsigned long long img = (unsigned long long)p.map_ptrs[im * 3 + s];
     const int H = p.H[s], W = p.W[s];
     const float sc = p.scale[s];
     const float sw = __fmul_rn(bx.x, sc), sh = __fmul_rn(bx.y, sc);
@@ -242,40 +191,169 @@ __global__ void __launch_bounds__(kThreads) geo_kernel(const FmapParams p) {
     }
     ylo = __reduce_min_sync(kFull, ylo); yhi = __reduce_max_sync(kFull, yhi);
     xlo = __reduce_min_sync(kFull, xlo); xhi = __reduce_max_sync(kFull, xhi);
-    const bool empty = yhi < 0 || xhi < 0;
-    int wh = 0, nxc = 0, xa = 0;
-    if (!empty) {
-        wh = yhi - ylo + 1;
+    BoxGeo g = {0, 0, 0, 0, (float)max(gh * gw, 1)};
+    if (yhi >= 0 && xhi >= 0) {
+        g.ylo = ylo;
+        g.wh = yhi - ylo + 1;
         const int ww = xhi - xlo + 1;
-        xa = xlo & ~3;
-        nxc = ((xlo + ww + 3) >> 2) - (xa >> 2);
+        g.xa = xlo & ~3;
+        g.nxc = ((xlo + ww + 3) >> 2) - (g.xa >> 2);
         float* __restrict__ wy = p.wts + (size_t)box * p.wstride;
         float* __restrict__ wx = wy + p.ext_y;
-        for (int r = lane; r < wh; r += 32) wy[r] = axis_weight(sh, rh, gh, H, ylo + r);
-        for (int i = lane; i < 4 * nxc; i += 32) {
-            const int x = xa + i;
-            wx[i] = (x >= xlo && x <= xhi) ? axis_weight(sw, rw, gw, W, x) : 0.f;
+        for (int t = lane; t < g.wh + 4 * g.nxc; t += 32) {   // rows and columns share one pass over the lanes
+            if (t < g.wh) {
+                wy[t] = axis_weight(sh, rh, gh, H, ylo + t);
+            } else {
+                const int i = t - g.wh, x = g.xa + i;
+                wx[i] = (x >= xlo && x <= xhi) ? axis_weight(sw, rw, gw, W, x) : 0.f;
+            }
         }
-    } else {
-        ylo = 0;
     }
-    if (p.cent) {                                     // counting sort by (stride, class used): position = prefix + ticket
-        const int cu = p.cls_used[box];
-        const int key = (cu >= 0 && cu < p.nc) ? s * p.nc + cu : 3 * p.nc;
-        int before = 0;
-        for (int i = lane; i < key; i += 32) before += p.hist[i];
-        before = __reduce_add_sync(kFull, before);
-        if (lane == 0) p.sorted[before + atomicAdd(&p.cursor[key], 1)] = box;
-    }
-    const float count = (float)max(gh * gw, 1);
-    for (int sl = lane; sl < p.ns[s]; sl += 32) {     // record: everything an item warp needs except the weights
-        int4* rec = p.items + 2 * (size_t)(ip.x + sl * ip.y);
-        rec[0] = make_int4((int)(((uint32_t)sl << 24) | (uint32_t)box), ylo | (xa << 16), wh | (nxc << 16), out);
-        rec[1] = make_int4((int)(img & 0xffffffffu), (int)(img >> 32), __float_as_int(count), s);
+    return g;
+}
+
+// record: everything an item warp needs except the weights; item(sl) = pos + sl * nbs
+__device__ __forceinline__ void geo_emit(const FmapParams& p, int box, int s, unsigned long long mapp, const BoxGeo& g,
+                                         int pos, int nbs, int out) {
+    const int lane = threadIdx.x & 31;
+    for (int sl = lane; sl < p.ns[s]; sl += 32) {
+        int4* rec = p.items + 2 * (size_t)(pos + sl * nbs);
+        rec[0] = make_int4((int)(((uint32_t)sl << 24) | (uint32_t)box), g.ylo | (g.xa << 16), g.wh | (g.nxc << 16), out);
+        rec[1] = make_int4((int)(mapp & 0xffffffffu), (int)(mapp >> 32), __float_as_int(g.count), s);
     }
 }
 
-// standalone Q1 plan (same arithmetic as plan_kernel, without the work list)
+__global__ void __launch_bounds__(kPgThreads) plan_geo_kernel(const FmapParams p) {
+    __shared__ int s_out[kPgCap], s_pos[kPgCap], s_cls[kPgCap];
+    __shared__ signed char s_cat[kPgCap + 32];
+    __shared__ int s_meta[8];                          // boxes per category [0..3], base of the image's item range [4]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int G = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int img = blockIdx.x / G, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b0 = p.img_start[img], m = p.img_start[img + 1] - b0;
+    const bool planner = rank == 0 && warp == 0;
+    const int stride_b = G * kPgWarps;
+    int b = rank * kPgWarps + warp;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = -1;
+    unsigned long long mapp = 0;
+    auto fetch = [&](int bb, float4& fbx, int& fs, unsigned long long& fmap) {
+        fs = p.stride_idx[b0 + bb];
+        fbx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)(b0 + bb));
+        const int im = p.img_idx[b0 + bb];
+        fmap = (fs >= 0 && fs <= 2) ? (unsigned long long)p.map_ptrs[im * 3 + fs] : 0ull;
+    };
+    if (!planner && b < m) fetch(b, bx, s, mapp);
+    if (planner) {
+        const unsigned lt = (1u << lane) - 1u;
+        int cnt[4] = {0, 0, 0, 0};
+        for (int c0 = 0; c0 < m; c0 += 128) {          // 4 chunks of 32 boxes per trip; the raw classes ride along
+            int st[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int bb = c0 + 32 * i + lane;
+                st[i] = bb < m ? p.stride_idx[b0 + bb] : -2;
+                if (bb < m && bb < kPgCap && p.cls) s_cls[bb] = p.cls[b0 + bb];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int bb = c0 + 32 * i + lane;
+                const int cat = bb < m ? ((st[i] >= 0 && st[i] <= 2) ? st[i] : 3) : 4;
+                if (bb < kPgCap) s_cat[bb] = (signed char)cat;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) cnt[t] += __popc(__ballot_sync(kFull, cat == t));
+            }
+        }
+        // this image's range of the work list, heaviest stride (most channels) first; items of one stride are slice-major
+        const int tot = cnt[2] * p.ns[2] + cnt[1] * p.ns[1] + cnt[0] * p.ns[0];
+        int base = 0;
+        if (lane == 0 && tot) base = atomicAdd(&p.counters[0], tot);       // awaited only where `base` is used
+        if (lane == 0 && p.cent && cnt[0] + cnt[1] + cnt[2]) atomicAdd(&p.counters[2], cnt[0] + cnt[1] + cnt[2]);
+        if (lane < 4) s_meta[lane] = cnt[lane];
+        __syncwarp();
+        int item0[3];                                  // relative to base
+        item0[2] = 0;
+        item0[1] = cnt[2] * p.ns[2];
+        item0[0] = item0[1] + cnt[1] * p.ns[1];
+        int run[4] = {0, 0, 0, 0};
+        for (int c0 = 0; c0 < m; c0 += 32) {
+            const int bb = c0 + lane;
+            int cat;
+            if (bb < kPgCap) {
+                cat = s_cat[bb];
+            } else {
+                const int st = bb < m ? p.stride_idx[b0 + bb] : -2;
+                cat = bb < m ? ((st >= 0 && st <= 2) ? st : 3) : 4;
+            }
+            int j = 0, before = 0, nb = 0, it0 = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const unsigned mk = __ballot_sync(kFull, cat == t);
+                if (cat == t) { j = run[t] + __popc(mk & lt); nb = cnt[t]; if (t < 3) it0 = item0[t]; }
+                if (t < cat) before += cnt[t];
+                run[t] += __popc(mk);
+            }
+            if (bb >= m) continue;
+            const bool ok = cat < 3;
+            int cls_u = p.cls ? (bb < kPgCap ? s_cls[bb] : p.cls[b0 + bb]) : 0, out = b0 + bb;
+            if (p.compat_q1) {
+                cls_u = ok ? (j < kPgCap ? s_cls[j] : p.cls[b0 + j]) : -1;
+                out = b0 + before + j;
+            }
+            p.cls_used[b0 + bb] = cls_u;
+            p.out_index[b0 + bb] = out;
+            if (bb < kPgCap) { s_out[bb] = out; s_pos[bb] = it0 + j; }
+            if (ok) {
+                if (bb >= kPgCap) p.ipos[b0 + bb] = make_int2(__shfl_sync(__activemask(), base, 0) + it0 + j, nb);
+                if (p.cent) atomicAdd(&p.hist[(cls_u >= 0 && cls_u < p.nc) ? cat * p.nc + cls_u : 3 * p.nc], 1);
+            } else if (p.cent) {
+                for (int k = 0; k < OODB200_N_METRICS; ++k)
+                    if (p.metric_mask >> k & 1) {
+                        const size_t o = (size_t)k * p.n + out;
+                        p.dist[o] = nanf("");
+                        p.argmin[o] = -1;
+                        p.decision[o] = 0;
+                    }
+            }
+        }
+        if (lane == 0) s_meta[4] = base;
+    }
+    // The geometry of a warp's first box does not depend on the plan: it overlaps the planner's chain of round trips.
+    // The planner arrives at the cluster barrier first and computes its own box between arrive and wait.
+    BoxGeo g = {0, 0, 0, 0, 1.f};
+    if (!planner && b < m && s >= 0 && s <= 2) g = geo_compute(p, b0 + b, s, bx);
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (planner && b < m) {
+        fetch(b, bx, s, mapp);
+        if (s >= 0 && s <= 2) g = geo_compute(p, b0 + b, s, bx);
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // the plan's global writes are visible too
+    const int* __restrict__ r_out = cluster.map_shared_rank(s_out, 0);
+    const int* __restrict__ r_pos = cluster.map_shared_rank(s_pos, 0);
+    const int* __restrict__ r_meta = cluster.map_shared_rank(s_meta, 0);
+    const int base = r_meta[4];
+    bool have_geo = true;
+    while (b < m) {
+        const int nb_ = b + stride_b;
+        float4 nbx = make_float4(0.f, 0.f, 0.f, 0.f);
+        int nst = -1;
+        unsigned long long nmap = 0;
+        if (nb_ < m) fetch(nb_, nbx, nst, nmap);
+        if (s >= 0 && s <= 2) {
+            const int box = b0 + b;
+            if (!have_geo) g = geo_compute(p, box, s, bx);
+            int pos, out;
+            if (b < kPgCap) { pos = base + r_pos[b]; out = r_out[b]; }
+            else { pos = p.ipos[box].x; out = p.out_index[box]; }
+            geo_emit(p, box, s, mapp, g, pos, r_meta[s], out);
+        }
+        have_geo = false;
+        b = nb_; bx = nbx; s = nst; mapp = nmap;
+    }
+    cluster.sync();                                    // CTA 0's shared memory stays alive until every reader is done
+}
+
+// standalone Q1 plan (same arithmetic as the plan phase of plan_geo_kernel, without the work list)
 __global__ void q1_plan_kernel(const int32_t* __restrict__ img_start, const int32_t* __restrict__ stride_idx,
                                const int32_t* __restrict__ cls, int32_t* __restrict__ cls_used,
                                int32_t* __restrict__ out_index) {
@@ -463,7 +541,7 @@ __device__ __forceinline__ void write_result(const FmapParams& p, int s, int cls
 // row; the warp is 4 groups of 8 lanes and every group sweeps ONE centroid row with independent 128-bit loads, so four
 // rows (x two tables) are in flight per warp and a row total needs a 3-level reduction instead of 5.  L2 latency, not
 // bandwidth, bounds this phase: the point is requests in flight.
-__device__ __forceinline__ void finalize_rows(const FmapParams& p, int box, int s, int C, int cls, int out, float* xs) {
+__device__ __forceinline__ void finalize_rows(const FmapParams& p, int s, int C, int cls, int out, float* xs) {
     const int lane = threadIdx.x & 31, g = lane >> 3, j = lane & 7;
     const float* __restrict__ row = p.pooled + (size_t)out * p.pooled_ld;
     const bool cls_ok = cls >= 0 && cls < p.nc;
@@ -601,14 +679,11 @@ __device__ __noinline__ Best finalize_generic(const float* __restrict__ row, int
     return b;
 }
 
-__device__ __forceinline__ void finalize(const FmapParams& p, int box, float* xs) {
-    const int s = p.stride_idx[box];
-    const int cls = p.cls_used[box];
-    const int out = p.out_index[box];
+__device__ __forceinline__ void finalize(const FmapParams& p, int s, int cls, int out, float* xs) {
     const int C = p.C[s];
-    bool vec = (C % 4 == 0);
+    bool vec = (C % 4 == 0) && (((uintptr_t)p.cent | (uintptr_t)p.cent_unit) & 15) == 0;
     if (vec && cls >= 0 && cls < p.nc) vec = (p.cent_off[s * p.nc + cls] % 4 == 0);
-    if (vec) { finalize_rows(p, box, s, C, cls, out, xs); return; }
+    if (vec) { finalize_rows(p, s, C, cls, out, xs); return; }
     const bool cls_ok = cls >= 0 && cls < p.nc;
     const int K = cls_ok ? p.cent_k[s * p.nc + cls] : 0;
     const int64_t off = K > 0 ? p.cent_off[s * p.nc + cls] : 0;
@@ -618,13 +693,29 @@ __device__ __forceinline__ void finalize(const FmapParams& p, int box, float* xs
 }
 
 // ---------------------------------------------------------------------------------------------- gather kernel
-__global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kernel(const FmapParams p) {
+__global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kernel(const __grid_constant__ FmapParams p) {
     const int lane = threadIdx.x & 31;
     const int n_items = p.counters[0];
     // Scheduling: the first kStaticPct % of the work list is handed out round-robin (no atomics: same-address atomics
     // serialise in L2 and their latency under contention is of the order of an item), the tail through an atomic queue
     // so that the last items balance.  The next item's index and record are requested while the current one runs.
     const int warp_g = blockIdx.x * kWarps + (threadIdx.x >> 5), n_warps = gridDim.x * kWarps;
+    if (p.cent) {
+        // Counting sort of the boxes by (stride, class used) for the score kernel: position = prefix of the plan's
+        // histogram + an atomic ticket.  Done here because the histogram is complete only after the plan kernel; the
+        // order inside a group is arbitrary (every box is scored independently).  The list holds OUTPUT slots.
+        for (int box = warp_g; box < p.n; box += n_warps) {
+            const int s = p.stride_idx[box];
+            if (s < 0 || s > 2) continue;
+            const int cu = p.cls_used[box];
+            const int out = p.out_index[box];
+            const int key = (cu >= 0 && cu < p.nc) ? s * p.nc + cu : 3 * p.nc;
+            int before = 0;
+            for (int i = lane; i < key; i += 32) before += p.hist[i];
+            before = __reduce_add_sync(kFull, before);
+            if (lane == 0) p.sorted[before + atomicAdd(&p.cursor[key], 1)] = out;
+        }
+    }
     const int n_static = (int)((long long)n_items * OODB200_FMAP_STATIC_PCT / 100);
     int q_reg = 0;                                     // lane 0: result of the most recent queue fetch
     bool q_pending = false;
@@ -672,11 +763,233 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kerne
 }
 
 // ---------------------------------------------------------------------------------------------- score kernel
-__global__ void __launch_bounds__(kThreads) score_kernel(const FmapParams p) {
-    extern __shared__ __align__(16) float s_x[];       // [kWarps][pooled_ld]
-    const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (w >= p.counters[2]) return;                    // boxes with an invalid stride were answered by the plan kernel
-    finalize(p, p.sorted[w], s_x + (size_t)(threadIdx.x >> 5) * p.pooled_ld);
+// score_kernel: one CTA per unit = kUnitBoxes consecutive boxes of one (stride, class) group, one box per warp.
+// The group's K centroid rows (and their unit-norm twins for cosine) are staged ONCE per CTA into shared memory with
+// bulk-async copies (one mbarrier), while every warp already loads and normalises its first pooled vector into
+// registers; the K rows are then swept from shared memory (128-bit, conflict-free), 4 rows per reduction round.  A warp's
+// dependent global round trips are: histogram -> list entry -> pooled row (the centroid copy runs beside them).
+// Groups whose tables do not fit the shared-memory budget, or whose slices are not 16-byte aligned, are swept from
+// global memory (finalize) by the same CTAs.
+constexpr int kUnitBoxes = kWarps;                     // boxes per score CTA: one per warp
+
+__device__ __forceinline__ uint32_t fs_smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar) {   // phase 0; a protocol error traps instead of hanging
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(fs_smem_u32(bar)), "r"(0u) : "memory");
+        if (!ok && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+// One box against the K staged rows.  NJ = float4 per lane (C <= 128 * NJ, only the last one can be partial), MASK = the
+// requested metrics: no run-time flag or bound check inside the sweep.
+template <int NJ, int MASK>
+__device__ __forceinline__ void score_box_smem(const FmapParams& p, int s, int C, int cls, int K, int out,
+                                               const float* __restrict__ sc, const float* __restrict__ su, uint64_t* bar) {
+    constexpr bool L1 = MASK & (1 << OODB200_METRIC_L1), L2 = MASK & (1 << OODB200_METRIC_L2);
+    constexpr bool COS = MASK & (1 << OODB200_METRIC_COS), L12 = L1 || L2;
+    constexpr int NM = (L1 ? 1 : 0) + (L2 ? 1 : 0) + (COS ? 1 : 0);
+    const int lane = threadIdx.x & 31;
+    const float* __restrict__ row = p.pooled + (size_t)out * p.pooled_ld;
+    const bool last_ok = (NJ - 1) * 128 + lane * 4 < C;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 x[NJ];
+#pragma unroll
+    for (int t = 0; t < NJ; ++t)
+        x[t] = (t < NJ - 1 || last_ok) ? __ldcg(reinterpret_cast<const float4*>(row + t * 128 + lane * 4)) : zero;
+    float ss = 0.f;
+#pragma unroll
+    for (int t = 0; t < NJ; ++t) {
+        ss = fmaf(x[t].x, x[t].x, ss); ss = fmaf(x[t].y, x[t].y, ss);
+        ss = fmaf(x[t].z, x[t].z, ss); ss = fmaf(x[t].w, x[t].w, ss);
+    }
+    float n2v = 1.f;
+    if (p.normalize) {                                 // ood_utils.py:2409 -> sklearn normalize
+        float nrm = sqrtf(warp_sum(ss));
+        if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;       // _handle_zeros_in_scale
+        ss = 0.f;
+#pragma unroll
+        for (int t = 0; t < NJ; ++t) {
+            x[t].x = __fdiv_rn(x[t].x, nrm); x[t].y = __fdiv_rn(x[t].y, nrm);
+            x[t].z = __fdiv_rn(x[t].z, nrm); x[t].w = __fdiv_rn(x[t].w, nrm);
+            if (COS) {
+                ss = fmaf(x[t].x, x[t].x, ss); ss = fmaf(x[t].y, x[t].y, ss);
+                ss = fmaf(x[t].z, x[t].z, ss); ss = fmaf(x[t].w, x[t].w, ss);
+            }
+        }
+    }
+    if (COS) {                                         // cosine_distances re-normalises X (pairwise.py:1171-1182)
+        n2v = sqrtf(warp_sum(ss));
+        if (n2v < 10.f * FLT_EPSILON) n2v = 1.f;
+    }
+    mbar_wait_bounded(bar);                            // the centroid tables have landed
+    Best b = {{FLT_MAX, FLT_MAX, FLT_MAX}, {-1, -1, -1}};
+    auto batch = [&](int k0, int nr) {                 // rows k0 .. k0 + nr - 1 (nr <= 4): 4 x NM independent reductions
+        float acc[4][NM];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float a1 = 0.f, a2 = 0.f, ac = 0.f;
+            const int k = k0 + (r < nr ? r : 0);       // short batch: repeat row k0, result dropped
+            const float* __restrict__ ck = sc + (size_t)k * C + lane * 4;
+            const float* __restrict__ cu = su + (size_t)k * C + lane * 4;
+#pragma unroll
+            for (int t = 0; t < NJ; ++t) {
+                const bool ld = t < NJ - 1 || last_ok;
+                if (L12) {
+                    const float4 c = ld ? *reinterpret_cast<const float4*>(ck + t * 128) : zero;
+                    const float e0 = x[t].x - c.x, e1 = x[t].y - c.y, e2 = x[t].z - c.z, e3 = x[t].w - c.w;
+                    if (L1) a1 += (fabsf(e0) + fabsf(e1)) + (fabsf(e2) + fabsf(e3));
+                    if (L2) { a2 = fmaf(e0, e0, a2); a2 = fmaf(e1, e1, a2); a2 = fmaf(e2, e2, a2); a2 = fmaf(e3, e3, a2); }
+                }
+                if (COS) {
+                    const float4 u = ld ? *reinterpret_cast<const float4*>(cu + t * 128) : zero;
+                    ac = fmaf(x[t].x, u.x, ac); ac = fmaf(x[t].y, u.y, ac); ac = fmaf(x[t].z, u.z, ac); ac = fmaf(x[t].w, u.w, ac);
+                }
+            }
+            int i = 0;
+            if (L1) acc[r][i++] = a1;
+            if (L2) acc[r][i++] = a2;
+            if (COS) acc[r][i++] = ac;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < NM; ++i) acc[r][i] += __shfl_xor_sync(kFull, acc[r][i], o);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {                  // rows in increasing order, strict '<': first minimum
+            if (r < nr) {
+                const int k = k0 + r;
+                int i = 0;
+                if (L1) { const float v = acc[r][i++]; if (v < b.d[0]) { b.d[0] = v; b.a[0] = k; } }
+                if (L2) { const float v = sqrtf(fmaxf(acc[r][i++], 0.f)); if (v < b.d[1]) { b.d[1] = v; b.a[1] = k; } }
+                if (COS) {                             // X / ||X|| applied to the sum (same value to float32 rounding)
+                    const float v = fminf(fmaxf(1.0f - __fdiv_rn(acc[r][i++], n2v), 0.f), 2.f);
+                    if (v < b.d[2]) { b.d[2] = v; b.a[2] = k; }
+                }
+            }
+        }
+    };
+    int k0 = 0;
+    for (; k0 + 4 <= K; k0 += 4) batch(k0, 4);
+    if (k0 < K) batch(k0, K - k0);
+    write_result(p, s, cls, true, K, out, b);         // lane m reports metric m (all lanes hold the same result)
+}
+
+// Groups that cannot be staged: sweep from global memory, warp-private vector in shared memory (kept out of line: the
+// staged path stays small in the instruction cache).
+__device__ __noinline__ void score_unit_global(const FmapParams& p, int s, int cls, int out, float* xs) {
+    finalize(p, s, cls, out, xs);
+}
+
+template <int MASK>
+__global__ void __launch_bounds__(kThreads, 3) score_kernel(const __grid_constant__ FmapParams p, int smem_bytes) {
+    extern __shared__ __align__(128) float s_dyn[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_unit[4];                          // key, chunk, start, boxes of the group
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fs_smem_u32(&s_bar)), "r"(1) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        // unit u = blockIdx.x -> (group key, chunk of kUnitBoxes boxes inside the group): blocked prefix over the histogram
+        const int nkeys = 3 * p.nc + 1, q = (nkeys + 31) >> 5;
+        int ub = 0, bb = 0;
+        for (int i = 0; i < q; ++i) {
+            const int k = lane * q + i;
+            if (k < nkeys) { const int h = p.hist[k]; ub += (h + kUnitBoxes - 1) / kUnitBoxes; bb += h; }
+        }
+        int ue = ub, be = bb;                          // inclusive scans over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tu = __shfl_up_sync(kFull, ue, o), tb = __shfl_up_sync(kFull, be, o);
+            if (lane >= o) { ue += tu; be += tb; }
+        }
+        const int u = blockIdx.x;
+        if (lane == 0) s_unit[0] = -1;                 // beyond the last unit
+        __syncwarp();
+        if (u >= ue - ub && u < ue) {                  // exactly one lane owns the unit
+            int uacc = ue - ub, bacc = be - bb;
+            for (int i = 0; i < q; ++i) {
+                const int k = lane * q + i;
+                const int h = k < nkeys ? p.hist[k] : 0;
+                const int nu = (h + kUnitBoxes - 1) / kUnitBoxes;
+                if (u < uacc + nu) { s_unit[0] = k; s_unit[1] = u - uacc; s_unit[2] = bacc; s_unit[3] = h; break; }
+                uacc += nu; bacc += h;
+            }
+        }
+    }
+    __syncthreads();
+    const int key = s_unit[0];
+    if (key < 0) return;
+    const int chunk = s_unit[1], start = s_unit[2], m = s_unit[3];
+    const int bi = chunk * kUnitBoxes + warp;          // this warp's box inside the group
+    const bool have = bi < m;
+    const int out = have ? p.sorted[start + bi] : 0;
+    const bool cls_ok = key < 3 * p.nc;
+    const int s = cls_ok ? key / p.nc : 0;
+    const int cls = cls_ok ? key - s * p.nc : -1;
+    if (!cls_ok) {                                     // class outside [0, nc): no clusters, no threshold
+        const Best b = {{FLT_MAX, FLT_MAX, FLT_MAX}, {-1, -1, -1}};
+        if (have) write_result(p, 0, -1, false, 0, out, b);
+        return;
+    }
+    const int C = p.C[s];
+    const int K = p.cent_k[key];
+    const int64_t off = K > 0 ? p.cent_off[key] : 0;
+    constexpr bool L12 = MASK & ((1 << OODB200_METRIC_L1) | (1 << OODB200_METRIC_L2));
+    constexpr bool COS = MASK & (1 << OODB200_METRIC_COS);
+    const size_t tab = (size_t)K * C * sizeof(float);
+    const size_t need = tab * ((L12 ? 1 : 0) + (COS ? 1 : 0));
+    const int nj = (C + 127) >> 7;
+    const bool staged = K > 0 && C % 4 == 0 && nj <= 8 && need <= (size_t)smem_bytes && tab < (1u << 20) &&
+                        off % 4 == 0 && ((((uintptr_t)p.cent) | ((uintptr_t)p.cent_unit)) & 15) == 0;
+    if (!staged) {
+        if (have) score_unit_global(p, s, cls, out, s_dyn + (size_t)warp * p.pooled_ld);
+        return;
+    }
+    float* sc = s_dyn;
+    float* su = L12 ? s_dyn + (size_t)K * C : s_dyn;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem_u32(&s_bar)), "r"((uint32_t)need) : "memory");
+        if (L12)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fs_smem_u32(sc)),
+                         "l"(p.cent + off), "r"((uint32_t)tab), "r"(fs_smem_u32(&s_bar)) : "memory");
+        if (COS)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fs_smem_u32(su)),
+                         "l"(p.cent_unit + off), "r"((uint32_t)tab), "r"(fs_smem_u32(&s_bar)) : "memory");
+    }
+    if (!have) {                                       // a warp without a box must not leave while the copy is in flight
+        mbar_wait_bounded(&s_bar);
+        return;
+    }
+    switch (nj) {
+        case 1: score_box_smem<1, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
+        case 2: score_box_smem<2, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
+        case 3: score_box_smem<3, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
+        case 4: score_box_smem<4, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
+        case 5: score_box_smem<5, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
+        case 6: score_box_smem<6, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
+        default: score_box_smem<8, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
+    }
+}
+
+typedef void (*ScoreKernel)(const FmapParams, int);
+static ScoreKernel score_kernel_for(int mask) {
+    switch (mask) {
+        case 1: return score_kernel<1>;
+        case 2: return score_kernel<2>;
+        case 3: return score_kernel<3>;
+        case 4: return score_kernel<4>;
+        case 5: return score_kernel<5>;
+        case 6: return score_kernel<6>;
+        default: return score_kernel<7>;
+    }
 }
 
 struct WorkspaceLayout {
@@ -754,12 +1067,27 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(p.counters, 0, L.zero_bytes, st);
     if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
-    plan_kernel<<<p.n_img, 32, 0, st>>>(p);
-    int rc = check_launch(what);
-    if (rc) return rc;
-    geo_kernel<<<(p.n + kWarps - 1) / kWarps, kThreads, 0, st>>>(p);
-    rc = check_launch(what);
-    if (rc) return rc;
+    int rc;
+    {
+        int G = 1;                                                 // CTAs per image: one warp per box in one round if possible
+        while (G < 8 && (long long)G * kPgWarps * p.n_img < p.n) G *= 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(p.n_img * G), 1, 1);
+        cfg.blockDim = dim3(kPgThreads, 1, 1);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)G;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, plan_geo_kernel, p);
+        if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+        rc = check_launch(what);
+        if (rc) return rc;
+    }
     if (g_sm_count == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -776,13 +1104,28 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     rc = check_launch(what);
     if (rc) return rc;
     if (p.cent) {
-        const size_t smem = sizeof(float) * (size_t)kWarps * L.pooled_ld;
-        OODB200_REQUIRE(smem <= 200 * 1024, "%s: too many channels for the score kernel (%d)", what, L.pooled_ld);
-        if (smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+        // shared memory per score CTA: the centroid tables of one (stride, class) group when they fit this budget
+        // (OODB200_SCORE_SMEM_KB, default 72 KB = 3 CTAs per SM), at least the warp-private vectors of the global sweep
+        static int budget_kb = 0;
+        if (budget_kb == 0) {
+            const char* env = getenv("OODB200_SCORE_SMEM_KB");
+            budget_kb = env ? atoi(env) : 72;
+            if (budget_kb < 16) budget_kb = 16;
+            if (budget_kb > 200) budget_kb = 200;
         }
-        score_kernel<<<(p.n + kWarps - 1) / kWarps, kThreads, smem, st>>>(p);
+        size_t smem = sizeof(float) * (size_t)kWarps * L.pooled_ld;
+        OODB200_REQUIRE(smem <= 200 * 1024, "%s: too many channels for the score kernel (%d)", what, L.pooled_ld);
+        if (smem < (size_t)budget_kb * 1024) smem = (size_t)budget_kb * 1024;
+        const ScoreKernel kern = score_kernel_for(p.metric_mask);
+        static size_t attr_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (smem > 48 * 1024 && smem > attr_set[p.metric_mask & 7]) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+            attr_set[p.metric_mask & 7] = smem;
+        }
+        const int nkeys = 3 * p.nc + 1;
+        const int units = (p.n + kUnitBoxes - 1) / kUnitBoxes + nkeys;   // >= sum over groups of ceil(m / kUnitBoxes)
+        kern<<<units, kThreads, smem, st>>>(p, (int)smem);
         rc = check_launch(what);
     }
     return rc;

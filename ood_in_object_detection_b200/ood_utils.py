@@ -69,9 +69,17 @@ def _to_device_f32(a, device) -> torch.Tensor:
 
 
 def _split_lists(flat: np.ndarray, counts: Sequence[int], cast) -> List[list]:
+    """flat per-box values -> per-image python lists of `cast` (int / float) values, like the reference returns."""
+    flat = np.asarray(flat)
+    if cast is int:
+        vals = flat.astype(np.int64, copy=False).tolist()
+    elif cast is float:
+        vals = flat.astype(np.float64, copy=False).tolist()
+    else:
+        vals = [cast(v) for v in flat]
     out, pos = [], 0
     for m in counts:
-        out.append([cast(v) for v in flat[pos:pos + m]])
+        out.append(vals[pos:pos + m])
         pos += m
     return out
 
@@ -393,7 +401,7 @@ class LogitsMethod(OODMethod):
             row[c] = float(v) if not (isinstance(v, (list, tuple)) and len(v) == 0) else 0.0
         tab = np.zeros((ops.N_LOGIT, nc), dtype=np.float64)
         tab[self._slot] = row
-        return torch.from_numpy(tab).to(device)
+        return ops.h2d(tab, device)
 
     def _gather(self, results):
         dev = ops.default_device()
@@ -402,8 +410,8 @@ class LogitsMethod(OODMethod):
             return dev, counts, None, None
         rows = [(res.extra_item, res.boxes.cls) for res, m in zip(results, counts) if m]
         if all(isinstance(z, torch.Tensor) and not z.is_cuda and not c.is_cuda for z, c in rows):   # host inputs: one copy each
-            logits = torch.cat([z.reshape(len(c), -1) for z, c in rows]).to(torch.float32).to(dev, non_blocking=True)
-            cls = torch.cat([c.reshape(-1) for _, c in rows]).to(torch.int32).to(dev, non_blocking=True)
+            logits = ops.h2d(torch.cat([z.reshape(len(c), -1) for z, c in rows]), dev, torch.float32)
+            cls = ops.h2d(torch.cat([c.reshape(-1) for _, c in rows]), dev, torch.int32)
         else:
             logits = torch.cat([_to_device_f32(z, dev).reshape(len(c), -1) for z, c in rows])
             cls = torch.cat([c.to(dev) for _, c in rows]).to(torch.int32)
@@ -1503,33 +1511,89 @@ def compute_ood_decisions_fused(methods: Sequence[OODMethod], results, logger, l
     dist_m = [m for m in methods if isinstance(m, DistanceMethod)]
     logit_m = [m for m in methods if isinstance(m, LogitsMethod)]
     key = lambda m, i: m.name if m.name not in out else f"{m.name}#{i}"
+    # Order of work: (1) queue the upload of the feature maps, (2) flatten the detections / logits and launch every kernel
+    # while that copy runs, (3) read all decisions back, (4) build the python lists.  Nothing waits on the device before (3).
+    pending = []                                       # (result key, device tensor row, counts)
+    share = []
     if dist_m:
         lead = dist_m[0]
         share = [m for m in dist_m if m.clusters is lead.clusters and m.which_internal_activations == 'ftmaps_and_strides'
                  and m.reference_compat == lead.reference_compat and m.normalize_activations == lead.normalize_activations]
         if len(share) > 1 and len(results):
             dev = ops.default_device()
+            staged = ops.stage_maps([list(r.extra_item[0]) for r in results], len(results), dev)
             hw = _img_hw(results[0])
-            batch = ops.make_batch([list(r.extra_item[0]) for r in results], [r.boxes.xyxy for r in results],
-                                   [r.extra_item[1] for r in results], [r.boxes.cls for r in results], hw[1], dev)
+            batch = ops.make_batch(staged, [r.boxes.xyxy for r in results], [r.extra_item[1] for r in results],
+                                   [r.boxes.cls for r in results], hw[1], dev)
             dims = [int(c) for c in batch.map_chw.reshape(3, 3)[:, 0]]
-            table = ops.pack_centroids(lead.clusters, {m._metric_slot: m.thresholds for m in share}, dims, dev)
+            table = ops.pack_centroids_cached(lead.clusters, {m._metric_slot: m.thresholds for m in share}, dims, dev)
             mask = 0
             for m in share:
                 mask |= 1 << m._metric_slot
             res = ops.fmap_score(batch, table, mask, normalize=lead.normalize_activations, compat_q1=lead.reference_compat)
-            dec = res.decision.cpu().numpy()
             for i, m in enumerate(share):
-                out[key(m, i)] = _split_lists(dec[m._metric_slot], batch.counts, int)
+                k = key(m, i)
+                out[k] = None                          # keeps the reference's order of keys
+                pending.append((k, res.decision, m._metric_slot, batch.counts))
         else:
             share = []
-        for i, m in enumerate(dist_m):
-            if m not in share:
-                out[key(m, i)] = m.compute_ood_decision_on_results(results, logger)
     lres = results if logits_results is None else logits_results
-    for i, m in enumerate(logit_m):
-        out[key(m, i)] = m.compute_ood_decision_on_results(lres, logger)
+    # logit methods that read the same kind of logits: ONE upload, ONE K3 launch (method mask), one read-back
+    slots = [m._slot for m in logit_m]
+    fusable = len(logit_m) > 1 and len(set(slots)) == len(slots) and all(s >= 0 for s in slots) \
+        and len({m.use_values_before_sigmoid for m in logit_m}) == 1
+    lres_out = None
+    if fusable:
+        lead_l = logit_m[0]
+        dev, counts, logits, cls = lead_l._gather(lres)
+        if logits is not None:
+            nc = int(logits.shape[1])
+            rows = lambda attr: [(m._slot, getattr(m, attr)) for m in logit_m if getattr(m, attr) is not None]
+            thr = _logit_table(rows('thresholds'), nc, dev)
+            with_ind = all(m.min_score is not None and m.max_score is not None for m in logit_m)
+            smin = _logit_table(rows('min_score'), nc, dev) if with_ind else None
+            smax = _logit_table(rows('max_score'), nc, dev) if with_ind else None
+            te, to, mask = 1.0, 1000.0, 0
+            for m in logit_m:
+                mte, mto = m._temperatures()
+                te = mte if m._slot == ops.LOGIT_SLOT['Energy'] else te
+                to = mto if m._slot == ops.LOGIT_SLOT['ODIN'] else to
+                mask |= 1 << m._slot
+            lres_out = ops.logit_score(logits, cls, mask, t_energy=te, t_odin=to, thr=thr, smin=smin, smax=smax,
+                                       clip=CUSTOM_HYP.fusion.CLIP_FUSION_SCORES)
+    # (3) + (4)
+    host = {}
+    for k, dec, row, counts_k in pending:
+        if id(dec) not in host:
+            host[id(dec)] = dec.cpu().numpy()
+        out[k] = _split_lists(host[id(dec)][row], counts_k, int)
+    for i, m in enumerate(dist_m):
+        if m not in share:
+            out[key(m, i)] = m.compute_ood_decision_on_results(results, logger)
+    if fusable:
+        if lres_out is None:
+            for i, m in enumerate(logit_m):
+                out[key(m, i)] = [[] for _ in counts]
+        else:
+            for m in logit_m:
+                m._post_launch_checks(lres_out)
+            dec = lres_out.decision.cpu().numpy()
+            for i, m in enumerate(logit_m):
+                out[key(m, i)] = _split_lists(dec[m._slot], counts, int)
+    else:
+        for i, m in enumerate(logit_m):
+            out[key(m, i)] = m.compute_ood_decision_on_results(lres, logger)
     return out
+
+
+def _logit_table(rows, nc: int, device) -> Tensor:
+    """[(slot, per-class python list)] -> float64 [N_LOGIT, nc] device table (LogitsMethod._table for several methods)."""
+    tab = np.zeros((ops.N_LOGIT, nc), dtype=np.float64)
+    for slot, values in rows:
+        for c in range(min(nc, len(values))):
+            v = values[c]
+            tab[slot, c] = float(v) if not (isinstance(v, (list, tuple)) and len(v) == 0) else 0.0
+    return ops.h2d(tab, device)
 
 
 # ------------------------------------------------------------------------------------------------ detector hook-up

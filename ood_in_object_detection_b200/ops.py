@@ -35,13 +35,30 @@ def default_device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _dev(t, device, dtype=None) -> torch.Tensor:
+def h2d(t, device, dtype=None) -> torch.Tensor:
+    """Host array / tensor -> device through PINNED staging.  A copy from pageable memory makes the host wait for
+    everything queued on the stream before it (the 100s of MB of feature maps of the same batch): staged through torch's
+    caching pinned allocator the call returns at once and the host keeps preparing the next launch under that copy."""
     if not isinstance(t, torch.Tensor):
         t = torch.as_tensor(np.asarray(t))
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
+    if t.is_cuda:
+        return t.to(device).contiguous()
+    if not t.is_pinned() or not t.is_contiguous():
+        stage = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        stage.copy_(t)
+        t = stage
+    return t.to(device, non_blocking=True)
+
+
+def _dev(t, device, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t))
     if t.device != device:
-        t = t.to(device, non_blocking=True)
+        return h2d(t, device, dtype)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
     return t.contiguous()
 
 
@@ -66,12 +83,20 @@ class DetectionBatch:
         return int(self.boxes.shape[0])
 
 
-def make_batch(maps, boxes: Sequence, strides: Sequence, cls: Sequence, img_w: int, device=None) -> DetectionBatch:
-    """maps: either 3 batched tensors [B,C_s,H_s,W_s] or a per-image list of 3 CHW tensors.
-    boxes/strides/cls: per-image sequences ([M_i,4], [M_i], [M_i]); strides in {0,1,2}.
-    img_w: width of the network input (`res.orig_img.shape[2]`, predict.py:68)."""
+@dataclass
+class StagedMaps:
+    """Feature maps of a batch on the device (or on their way: the copies are queued on the current stream)."""
+    ptrs: np.ndarray           # int64 [n_img, 3] device addresses of the CHW maps
+    chw: list                  # 3 x (C_s, H_s, W_s)
+    n_img: int
+    keepalive: tuple
+
+
+def stage_maps(maps, n_img: int, device=None) -> StagedMaps:
+    """Queue the upload of the feature maps (the bulk of a host batch) BEFORE any other host-side preparation, so that
+    the detections are flattened and the launches prepared while the DMA engine works.
+    maps: either 3 batched tensors [B,C_s,H_s,W_s] or a per-image list of 3 CHW tensors."""
     device = device or default_device()
-    n_img = len(boxes)
     keep = []
     if len(maps) == 3 and all(isinstance(m, torch.Tensor) and m.dim() == 4 for m in maps):
         mt = [_dev(m, device, torch.float32) for m in maps]
@@ -111,6 +136,18 @@ def make_batch(maps, boxes: Sequence, strides: Sequence, cls: Sequence, img_w: i
                 ts = [_dev(t, device, torch.float32) for t in col]
                 ptrs[:, s] = [t.data_ptr() for t in ts]
                 keep.extend(ts)
+    return StagedMaps(ptrs=ptrs, chw=[tuple(int(v) for v in c) for c in chw], n_img=n_img, keepalive=tuple(keep))
+
+
+def make_batch(maps, boxes: Sequence, strides: Sequence, cls: Sequence, img_w: int, device=None) -> DetectionBatch:
+    """maps: either 3 batched tensors [B,C_s,H_s,W_s], a per-image list of 3 CHW tensors, or `stage_maps(...)` of those.
+    boxes/strides/cls: per-image sequences ([M_i,4], [M_i], [M_i]); strides in {0,1,2}.
+    img_w: width of the network input (`res.orig_img.shape[2]`, predict.py:68)."""
+    device = device or default_device()
+    n_img = len(boxes)
+    staged = maps if isinstance(maps, StagedMaps) else stage_maps(maps, n_img, device)
+    assert staged.n_img == n_img, "one set of maps per image"
+    ptrs, chw, keep = staged.ptrs, staged.chw, staged.keepalive
     counts = [int(len(b)) for b in boxes]
     n = sum(counts)
     def _flat(seq, dtype, width=None):
@@ -118,7 +155,7 @@ def make_batch(maps, boxes: Sequence, strides: Sequence, cls: Sequence, img_w: i
         ts = [t if isinstance(t, torch.Tensor) else torch.as_tensor(np.asarray(t)) for t in seq]
         shape = (-1, width) if width else (-1,)
         if all(not t.is_cuda for t in ts):
-            return torch.cat([t.reshape(shape) for t in ts]).to(dtype).contiguous().to(device, non_blocking=True)
+            return h2d(torch.cat([t.reshape(shape) for t in ts]), device, dtype)
         return torch.cat([t.to(device).reshape(shape) for t in ts]).to(dtype).contiguous()
 
     if n:
@@ -133,11 +170,11 @@ def make_batch(maps, boxes: Sequence, strides: Sequence, cls: Sequence, img_w: i
     np.cumsum(counts, out=start[1:])
     img_idx = np.repeat(np.arange(n_img, dtype=np.int32), counts)
     return DetectionBatch(
-        map_ptrs=torch.from_numpy(ptrs.reshape(-1)).to(device, non_blocking=True),
+        map_ptrs=h2d(ptrs.reshape(-1), device),
         map_chw=np.asarray(chw, dtype=np.int32).reshape(9),
         scale=np.asarray([np.float32(c[2] / img_w) for c in chw], dtype=np.float32),
-        n_img=n_img, boxes=bx, img_idx=torch.from_numpy(img_idx).to(device, non_blocking=True),
-        stride_idx=st, cls=cl, img_start=torch.from_numpy(start).to(device, non_blocking=True),
+        n_img=n_img, boxes=bx, img_idx=h2d(img_idx, device),
+        stride_idx=st, cls=cl, img_start=h2d(start, device),
         counts=counts, keepalive=tuple(keep))
 
 
@@ -179,6 +216,43 @@ def pack_thresholds(thresholds_by_metric: dict, nc: int) -> np.ndarray:
     return thr.reshape(3, 3 * nc)
 
 
+_table_cache: dict = {}
+
+
+def _table_key(clusters, thresholds_by_metric: dict, dims, device):
+    """Identity of a (clusters, thresholds) pair: buffer address, shape and two probe values of every centroid array, the
+    threshold values themselves.  Cheap next to packing + uploading the tables for every batch."""
+    ck = []
+    for per_cls in clusters:
+        for a in per_cls:
+            if isinstance(a, np.ndarray) and a.size:
+                ck.append((a.ctypes.data, a.shape, a.dtype.str, float(a.flat[0]), float(a.flat[-1])))
+            else:
+                ck.append(np.size(a))
+    tk = []
+    for slot in sorted(thresholds_by_metric):
+        th = thresholds_by_metric[slot]
+        tk.append((slot, None if th is None else tuple(tuple(tuple(np.ravel(np.asarray(v, dtype=np.float64)).tolist()) for v in per) for per in th)))
+    return (tuple(ck), tuple(tk), tuple(int(d) for d in dims), str(device))
+
+
+def pack_centroids_cached(clusters, thresholds_by_metric: dict, dims: Sequence[int], device=None) -> "CentroidTable":
+    """`pack_centroids` memoised on the content fingerprint of its inputs (scoring calls it once per batch with the same
+    fitted tables); holds the 4 most recent tables."""
+    device = device or default_device()
+    try:
+        key = _table_key(clusters, thresholds_by_metric, dims, device)
+    except (TypeError, ValueError):
+        return pack_centroids(clusters, thresholds_by_metric, dims, device)
+    hit = _table_cache.get(key)
+    if hit is None:
+        hit = pack_centroids(clusters, thresholds_by_metric, dims, device)
+        if len(_table_cache) >= 4:
+            _table_cache.pop(next(iter(_table_cache)))
+        _table_cache[key] = hit
+    return hit
+
+
 def pack_centroids(clusters, thresholds_by_metric: dict, dims: Sequence[int], device=None) -> CentroidTable:
     """clusters[cls][stride] = ndarray [K, C_s] or empty; thresholds_by_metric = {metric_slot: thresholds[cls][stride]}
     with python floats or falsy entries ([] / 0 / 0.0 -> "no threshold", ood_utils.py:2173)."""
@@ -210,7 +284,7 @@ def pack_centroids(clusters, thresholds_by_metric: dict, dims: Sequence[int], de
     flat = np.concatenate(chunks) if chunks else np.zeros(4, np.float32)
     flat_u = np.concatenate(units) if units else np.zeros(4, np.float32)
     thr = pack_thresholds(thresholds_by_metric, nc)
-    t = lambda a: torch.from_numpy(a).to(device, non_blocking=True)
+    t = lambda a: h2d(a, device)
     return CentroidTable(cent=t(flat), cent_unit=t(flat_u), cent_off=t(off.reshape(-1)), cent_k=t(kk.reshape(-1)),
                          thr=t(thr), nc=nc, k_host=kk)
 

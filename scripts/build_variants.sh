@@ -4,10 +4,11 @@
 set -e
 cd "$(dirname "$0")/.."
 D=ood_in_object_detection_b200; mkdir -p $D/variants
+SRC=$(python -c "from ood_in_object_detection_b200 import build as b; print(' '.join('$D/csrc/' + s for s in b.SOURCES))")
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -O3 --shared -cudart shared $flags \
-    $D/csrc/fmap_score.cu $D/csrc/logit_score.cu $D/csrc/fit_kernels.cu $D/csrc/kmeans.cu -o $D/variants/$name.so &
+    $SRC -o $D/variants/$name.so &
 done
 wait
 ls -la $D/variants

@@ -179,6 +179,21 @@ def test_fused_multi_method_helper(ou, golden):
     for m in methods:
         assert out[m.name] == m.compute_ood_decision_on_results(test, LOG), m.name
     assert out["MSP"] == msp.compute_ood_decision_on_results(lres, LOG)
+    # several logit methods: one upload + one launch with the method mask == each method on its own
+    en, ml = ou.Energy(temper=2, **LOGIT_KW), ou.MaxLogit(**LOGIT_KW)
+    en.thresholds = list(np.linspace(3.0, 9.0, nc))
+    ml.thresholds = list(np.linspace(1.2, 2.6, nc))
+    out3 = ou.compute_ood_decisions_fused([methods[0], methods[2], msp, en, ml], test, LOG, logits_results=lres)
+    assert out3[methods[0].name] == out[methods[0].name] and out3[methods[2].name] == out[methods[2].name]
+    for m in (msp, en, ml):
+        alone = m.compute_ood_decision_on_results(lres, LOG)
+        assert out3[m.name] == alone, m.name
+        assert 0 < sum(map(sum, alone)) < sum(map(len, alone)), m.name       # thresholds that actually split the boxes
+    out4 = ou.compute_ood_decisions_fused([methods[0], methods[2]], test, LOG)        # second call: cached tables
+    assert out4[methods[0].name] == out[methods[0].name] and out4[methods[2].name] == out[methods[2].name]
+    methods[2].thresholds = [[t * 0.5 if t else t for t in per] for per in methods[2].thresholds]   # new thresholds: no stale hit
+    out5 = ou.compute_ood_decisions_fused([methods[0], methods[2]], test, LOG)
+    assert out5[methods[2].name] == methods[2].compute_ood_decision_on_results(test, LOG)
     own = ou.L2DistanceOneClusterPerStride(**dict(DIST_KW, cluster_method="KMeans_5"))   # different clusters object: own pass
     own.clusters = [list(row) for row in shared]
     own.thresholds = methods[1].thresholds
