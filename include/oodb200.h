@@ -277,6 +277,17 @@ int oodb200_seed_pick_f32(const double* pots, const int32_t* seg_trials, const i
                           float* closest, float* pot, float* cent_out, int64_t cent_stride, int32_t* best_out,
                           void* stream);
 
+/* ---- K7: per-cluster distance sums for the silhouette score of the k-search
+ * (/root/reference/cluster_utils.py:203-302; :277 `silhouette_score(feature_maps_one_run, cluster_labels, metric=metric)`
+ * -> sklearn `silhouette_samples`: pairwise_distances_chunked + `_silhouette_reduce`).
+ *   x [n, ld] float32 rows of ONE (class, stride) segment (first `d` columns used; for cosine the rows must already be
+ *   unit-norm like sklearn `normalize` leaves them); labels int32 [n] in [0, kc)
+ *   sums float64 [n, kc]:  sums[i][c] = sum_{j : labels[j] == c} dist(x_i, x_j), dist(i, i) = 0
+ *   metric = OODB200_METRIC_L1 (cityblock) / _L2 (euclidean) / _COS (1 - x.y clipped to [0, 2])
+ */
+int oodb200_pair_cluster_sums_f32(const float* x, int n, int d, int64_t ld, const int32_t* labels, int kc, int metric,
+                                  double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,7 @@ import numpy as np
 import torch
 from torch import Tensor
 
+from . import cluster_utils as _cluster_utils
 from . import kmeans as _kmeans
 from . import ops
 from . import select as _select
@@ -1004,7 +1005,8 @@ class DistanceMethod(OODMethod):
     def generate_clusters(self, ind_tensors, logger: Logger, group=None):
         """clusters[cls][stride] = [K, C_s] float32 centroids (np.empty(0) when there are <= MIN_SAMPLES vectors).
         'one': mean of the normalised vectors; 'KMeans_<k>': k-means labels (sklearn-compatible seeding + Lloyd, K4,
-        all classes of a stride in the same launches) then per-label member means; 'all': every vector.
+        all classes of a stride in the same launches) then per-label member means; 'KMeans': the number of clusters of
+        every segment searched over 2..14 by silhouette / Calinski-Harabasz score (K7); 'all': every vector.
         `group`: process group when ind_tensors holds this rank's row shard of every segment (k-means only)."""
         t1 = time.perf_counter()
         if not (self.per_class and self.per_stride):
@@ -1013,8 +1015,10 @@ class DistanceMethod(OODMethod):
             raise NotImplementedError("agg_method='median' is not available on the GPU path")
         method = self.cluster_method
         k = kmeans_k(method)
-        if method not in ('one', 'all') and k is None:
+        if method not in ('one', 'all', 'KMeans') and k is None:
             raise NotImplementedError(f"cluster_method '{method}' is a CPU-library clusterer outside the GPU hot path")
+        if method == 'KMeans' and group is not None:
+            raise NotImplementedError("the searched 'KMeans' runs on one GPU per (class, stride) segment; shard the classes instead")
         if k is not None and k < 2:
             raise ValueError("The number of clusters must be greater than 1")
         dev = ops.default_device()
@@ -1035,6 +1039,14 @@ class DistanceMethod(OODMethod):
                 continue
             if method == 'one':
                 means, counts = _kmeans.member_means(x, sizes, None, 1, group=group)
+            elif method == 'KMeans':
+                # number of clusters searched per segment (cluster_utils.py:75-80, :203-356): labels of the best k
+                off = np.concatenate([[0], np.cumsum(sizes)])
+                labels = [_cluster_utils.search_number_of_clusters(x[off[i]:off[i + 1]], self.metric,
+                                                                   self.cluster_optimization_metric, logger)[0]
+                          for i in range(len(classes))]
+                kmax = max(CUSTOM_HYP.clusters.RANGE_OF_CLUSTERS)
+                means, counts = _kmeans.member_means(x, sizes, torch.cat(labels), kmax, group=None)
             else:
                 gsizes = self._global_sizes(sizes, dev, group)
                 world, rank = (torch.distributed.get_world_size(group), torch.distributed.get_rank(group)) if group is not None else (1, 0)

@@ -540,3 +540,52 @@ def normalize_rows(x: torch.Tensor) -> torch.Tensor:
     _lib.check(lib.oodb200_normalize_rows_f32(_ptr(x), int(x.stride(0)), int(x.shape[1]), int(x.shape[0]), _ptr(out),
                                               int(out.stride(0)), _stream()), "oodb200_normalize_rows_f32")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ k-search scores (K7)
+def pair_cluster_sums(x: torch.Tensor, labels: torch.Tensor, kc: int, metric: str) -> torch.Tensor:
+    """sums[i][c] = sum of dist(x_i, x_j) over the rows j with labels[j] == c (float64 [n, kc]); x float32 [n, D] rows of
+    one segment (unit-norm rows for 'cosine'), labels int32 in [0, kc)."""
+    lib = _lib.load()
+    if x.dtype != torch.float32 or not x.is_cuda or labels.dtype != torch.int32 or not labels.is_cuda:
+        raise TypeError("pair_cluster_sums: float32 rows and int32 labels on the device expected")
+    x = x.contiguous()
+    n, d = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty((n, int(kc)), dtype=torch.float64, device=x.device)
+    _lib.check(lib.oodb200_pair_cluster_sums_f32(_ptr(x), n, d, int(x.stride(0)), _ptr(labels.contiguous()), int(kc),
+                                                 METRIC_SLOT[metric], _ptr(out), _stream()), "oodb200_pair_cluster_sums_f32")
+    return out
+
+
+def silhouette_score(x: torch.Tensor, labels: torch.Tensor, metric: str) -> float:
+    """sklearn.metrics.silhouette_score(X, labels, metric='l1' | 'l2' | 'cosine') (cluster_utils.py:277): mean over the
+    samples of (b - a) / max(a, b), a = mean distance to the other members of the own cluster, b = smallest mean distance
+    to another cluster; members of one-sample clusters count 0.  The pair distances are summed per cluster on the GPU
+    (K7), the n x n matrix is never stored."""
+    uniq, enc = torch.unique(labels, return_inverse=True)
+    kc, n = int(uniq.numel()), int(labels.numel())
+    if not 1 < kc < n:
+        raise ValueError(f"Number of labels is {kc}. Valid values are 2 to n_samples - 1 (inclusive)")
+    enc32 = enc.to(torch.int32)
+    xs = normalize_rows(x) if metric == "cosine" else x
+    sums = pair_cluster_sums(xs, enc32, kc, metric)
+    freq = torch.bincount(enc, minlength=kc).to(torch.float64)
+    rows = torch.arange(n, device=x.device)
+    intra = sums[rows, enc] / (freq - 1.0)[enc]
+    sums[rows, enc] = float("inf")
+    inter = (sums / freq).min(dim=1).values
+    sil = torch.nan_to_num((inter - intra) / torch.maximum(intra, inter), nan=0.0)
+    return float(sil.mean())
+
+
+def calinski_harabasz_score(x: torch.Tensor, labels: torch.Tensor) -> float:
+    """sklearn.metrics.calinski_harabasz_score (cluster_utils.py:280): between- over within-cluster dispersion."""
+    uniq, enc = torch.unique(labels, return_inverse=True)
+    k, n = int(uniq.numel()), int(labels.numel())
+    x64 = x.to(torch.float64)
+    freq = torch.bincount(enc, minlength=k).to(torch.float64)
+    sums = torch.zeros((k, x.shape[1]), dtype=torch.float64, device=x.device).index_add_(0, enc, x64)
+    means = sums / freq[:, None]
+    extra = float((freq * ((means - x64.mean(0)) ** 2).sum(1)).sum())
+    intra = float(((x64 - means[enc]) ** 2).sum())
+    return 1.0 if intra == 0.0 else extra * (n - k) / (intra * (k - 1.0))

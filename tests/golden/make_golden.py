@@ -374,10 +374,36 @@ def golden_matching(ref):
     print("golden_matching", {k: store[k].tolist() for k in store if k.startswith("valid_") and k.endswith("0.5")})
 
 
+def golden_ksearch(ref):
+    """Silhouette / Calinski-Harabasz search of the number of k-means clusters through the reference's own functions
+    (cluster_utils.py:75-80 params, :203-302 scores per k, :160-186 best k + refit): per-k scores and final labels."""
+    from sklearn.cluster import KMeans
+    cu = ref.cluster_utils
+    store = {}
+    cases = {"a": (600, 24, 5, 7.0, "l2", "silhouette"), "b": (420, 16, 3, 8.0, "cosine", "silhouette"),
+             "c": (500, 12, 4, 7.0, "l1", "silhouette"), "d": (450, 16, 6, 8.0, "l2", "calinski_harabasz"),
+             "e": (9, 8, 2, 8.0, "l2", "silhouette")}        # e: fewer samples than most k -> default scores
+    for tag, (n, dim, k_true, sep, metric, perf) in cases.items():
+        x, _ = synth.blob_vectors(300 + n, n, dim, k_true, sep)
+        params = {"n_clusters": list(range(2, 15)), "random_state": [10]}
+        scores, configs = cu.compute_score_for_all_possible_configurations(x, KMeans, params, "n_clusters", perf, metric, LOG)
+        lab = cu.find_optimal_number_of_clusters_one_class_one_stride_and_return_labels(x, "KMeans", metric, perf, "", LOG)
+        store[f"{tag}_x"] = x
+        store[f"{tag}_scores"] = np.asarray(scores, np.float64)
+        store[f"{tag}_ks"] = np.asarray([c["n_clusters"] for c in configs], np.int32)
+        store[f"{tag}_labels"] = np.asarray(lab, np.int32)
+        store[f"{tag}_metric"], store[f"{tag}_perf"] = np.array(metric), np.array(perf)
+        print("ksearch", tag, "best k", int(store[f"{tag}_ks"][int(np.argmax(scores))]), np.round(scores, 4).tolist())
+    np.savez_compressed(os.path.join(OUT, "golden_ksearch.npz"), **store)
+
+
 def main():
     ref = ref_shim.load()
     if "--only-matching" in sys.argv:
         return golden_matching(ref)
+    if "--only-ksearch" in sys.argv:
+        return golden_ksearch(ref)
+    golden_ksearch(ref)
     golden_matching(ref)
     golden_roi_edges(ref)
     golden_quirks(ref)

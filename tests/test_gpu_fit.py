@@ -410,3 +410,78 @@ def test_tcgen05_vector_scoring_c5_shapes(dev):
                 elif b > a:
                     near = np.abs(ref_d[a:b] - thr[slot, g]) <= 1e-4 * abs(thr[slot, g])
                     assert np.array_equal(dec[slot, a:b].cpu().numpy()[~near], (ref_d[a:b] < thr[slot, g]).astype(np.uint8)[~near])
+
+
+def test_pair_cluster_sums_match_the_oracle(dev):
+    """K7 against the dense pairwise matrix of the oracle: every (row, cluster) sum, all three metrics, ragged sizes
+    (n not a multiple of the 64-row tile, D not a multiple of 4 or 16), one split over column tiles."""
+    from oracle import distance as D, silhouette as S
+    from ood_in_object_detection_b200 import ops
+    rng = np.random.default_rng(5)
+    for n, dim, kc in ((1, 8, 1), (70, 24, 3), (333, 50, 7), (900, 37, 14)):
+        x = np.abs(rng.standard_normal((n, dim))).astype(np.float32) + 0.05
+        lab = rng.integers(0, kc, size=n).astype(np.int32)
+        for metric in ("l1", "l2", "cosine"):
+            d = S.pairwise_full(x, metric).astype(np.float64)
+            want = np.stack([d[:, lab == c].sum(1) for c in range(kc)], 1)
+            xs = torch.from_numpy(D.normalize_rows(x) if metric == "cosine" else x).to(dev)
+            got = ops.pair_cluster_sums(xs, torch.from_numpy(lab).to(dev), kc, metric).cpu().numpy()
+            np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6 * n if metric == "cosine" else 1e-9)
+
+
+def test_silhouette_score_matches_sklearn(dev, golden):
+    """ops.silhouette_score / calinski_harabasz_score == sklearn on the reference's final labels (1e-5, stated), also with a
+    one-sample cluster (scores 0 for its member) and labels that are not 0..k-1."""
+    from sklearn.metrics import calinski_harabasz_score, silhouette_score
+    from ood_in_object_detection_b200 import ops
+    g = golden("golden_ksearch.npz")
+    for tag in "abcd":
+        x, lab, metric = g[f"{tag}_x"], g[f"{tag}_labels"].copy(), str(g[f"{tag}_metric"])
+        for variant in range(3):
+            if variant == 1:
+                lab = lab * 3 + 2                                   # sparse label values
+            if variant == 2:
+                lab[0] = lab.max() + 5                              # a cluster of one sample
+            xd, ld = torch.from_numpy(x).to(dev), torch.from_numpy(lab.astype(np.int32)).to(dev)
+            for m in ("l1", "l2", "cosine") if variant == 0 else (metric,):
+                assert abs(ops.silhouette_score(xd, ld, m) - silhouette_score(x, lab, metric=m)) < 1e-5, (tag, variant, m)
+            assert np.isclose(ops.calinski_harabasz_score(xd, ld), calinski_harabasz_score(x, lab), rtol=1e-5)
+
+
+def test_k_search_matches_the_reference(dev, golden):
+    """`cluster_method='KMeans'` (cluster_utils.py:75-80, :160-186, :203-356): per-k scores within 1e-4 of the reference's
+    (k-means labels are bit-exact on these separated sets, so only the arithmetic of the score differs), same best k,
+    identical final labels; through the mirror of the reference's function and through DistanceMethod.generate_clusters."""
+    import logging
+    from ood_in_object_detection_b200 import cluster_utils, ood_utils
+    log = logging.getLogger("t")
+    log.setLevel(logging.CRITICAL)
+    g = golden("golden_ksearch.npz")
+    for tag in "abcde":
+        x, metric, perf = g[f"{tag}_x"], str(g[f"{tag}_metric"]), str(g[f"{tag}_perf"])
+        ref_scores, ref_labels = g[f"{tag}_scores"], g[f"{tag}_labels"]
+        labels, scores, ks = cluster_utils.search_number_of_clusters(torch.from_numpy(x).to(dev), metric, perf, log)
+        assert ks == g[f"{tag}_ks"].tolist()
+        assert int(np.argmax(scores)) == int(np.argmax(ref_scores)), (tag, scores, ref_scores.tolist())
+        np.testing.assert_allclose(scores, ref_scores, rtol=1e-4, atol=1e-4)
+        assert np.array_equal(labels.cpu().numpy(), ref_labels), tag
+        lab2 = cluster_utils.find_optimal_number_of_clusters_one_class_one_stride_and_return_labels(x, "KMeans", metric, perf, "", log)
+        assert np.array_equal(lab2, ref_labels)
+    # the class surface: centroids = member means of the searched labels (ood_utils.py:2359-2366)
+    KW = dict(agg_method="mean", cluster_method="KMeans", cluster_optimization_metric="silhouette",
+              ind_info_creation_option="valid_preds_one_stride", which_internal_activations="ftmaps_and_strides",
+              iou_threshold_for_matching=0.5, min_conf_threshold_train=0.15, min_conf_threshold_test=0.15)
+    m = ood_utils.L2DistanceOneClusterPerStride(**KW)
+    acts = [[np.empty(0) for _ in range(3)] for _ in range(2)]
+    place = {(0, 0): "a", (0, 1): "b", (1, 1): "d", (1, 2): "c"}         # segments of one stride share their dimension
+    for (c, s), tag in place.items():
+        acts[c][s] = g[f"{tag}_x"][:, :, None, None]
+    clusters = m.generate_clusters(acts, log)
+    from oracle import distance as D
+    xn, lab = D.normalize_rows(g["a_x"]), g["a_labels"]                  # 'a' was searched with l2 / silhouette: same labels
+    want = np.stack([xn[lab == j].mean(0) for j in sorted(set(lab.tolist()))])
+    np.testing.assert_allclose(clusters[0][0], want, rtol=1e-5, atol=1e-6)
+    for (c, s), tag in place.items():
+        k_true = {"a": 5, "b": 3, "c": 4, "d": 6}[tag]
+        assert clusters[c][s].shape == (k_true, g[f"{tag}_x"].shape[1]), (tag, clusters[c][s].shape)
+    assert len(clusters[0][2]) == 0 and len(clusters[1][0]) == 0

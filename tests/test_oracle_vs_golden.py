@@ -212,3 +212,21 @@ def test_cpu_port_matches_golden(golden):
     for tag, temper in (("MSP", 1.0), ("Energy", 1.0), ("ODIN", 1000.0), ("Sigmoid", 1.0)):
         dec = cpu_path.logit_decisions(limg, tag, gl[f"{tag}_thr"].tolist(), temper)
         assert np.array_equal(np.concatenate([np.asarray(d, np.int8) for d in dec]), gl[f"{tag}_decisions"])
+
+
+def test_silhouette_and_k_search(golden):
+    """oracle/silhouette.py against sklearn (the dependency it restates) and against the per-k scores and final labels the
+    reference's own k-search produced (cluster_utils.py:203-356; tests/golden/make_golden.py::golden_ksearch)."""
+    from sklearn.metrics import calinski_harabasz_score, silhouette_score
+    from oracle import silhouette as S
+    g = golden("golden_ksearch.npz")
+    for tag in "abcde":
+        x, metric, perf = g[f"{tag}_x"], str(g[f"{tag}_metric"]), str(g[f"{tag}_perf"])
+        ref_scores, ref_labels = g[f"{tag}_scores"], g[f"{tag}_labels"]
+        assert g[f"{tag}_ks"].tolist() == S.RANGE_OF_CLUSTERS
+        if len(set(ref_labels.tolist())) > 1:
+            assert abs(S.silhouette_score(x, ref_labels, metric) - silhouette_score(x, ref_labels, metric=metric)) < 1e-6
+            assert np.isclose(S.calinski_harabasz_score(x, ref_labels), calinski_harabasz_score(x, ref_labels), rtol=1e-6)
+        scores, labels = S.k_search(x, metric, perf)
+        np.testing.assert_allclose(scores, ref_scores, rtol=2e-6, atol=2e-6)
+        assert np.array_equal(labels, ref_labels), tag
