@@ -116,6 +116,24 @@ int oodb200_fmap_score_f32(const float* const* map_ptrs, const int32_t* map_chw,
                            float* pooled, int pooled_ld, int32_t* cls_used_out, int32_t* out_index_out,
                            void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- K1 / K1+K2 on CHANNELS-LAST maps (what a detector run in torch.channels_last hands out): same arguments and
+ * results as oodb200_roi_pool_f32 / oodb200_fmap_score_f32, but map_ptrs[i*3+s] points at a [H_s, W_s, C_s] array
+ * (element (c, y, x) at [(y * W_s + x) * C_s + c]).  A window cell is then C_s contiguous floats: every fetched
+ * 128-byte line is used in full and pooling needs no cross-lane reduction. */
+int oodb200_roi_pool_nhwc_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
+                         const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
+                         const int32_t* img_start, int n,
+                         float* out, int out_ld, void* workspace, int64_t workspace_bytes, void* stream);
+int oodb200_fmap_score_nhwc_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
+                           const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
+                           const int32_t* cls, const int32_t* img_start, int compat_q1, int n,
+                           int metric_mask, int normalize,
+                           const float* cent, const float* cent_unit, const int64_t* cent_off, const int32_t* cent_k,
+                           int nc, const double* thr,
+                           float* dist, int32_t* argmin, uint8_t* decision,
+                           float* pooled, int pooled_ld, int32_t* cls_used_out, int32_t* out_index_out,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- Q1 plan (standalone; oodb200_fmap_score_f32 does the same internally when img_start != NULL):
  * the reference looks the class up with the in-stride index and emits decisions
  * stride-major (/root/reference/ood_utils.py:2152-2154).  For box b of an image

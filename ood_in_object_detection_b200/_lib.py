@@ -28,6 +28,9 @@ SIGNATURES = {
     "oodb200_fmap_score_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P,
                                _P, _I, _P, _P, _P, _L, _P],
     "oodb200_q1_plan_i32": [_P, _P, _P, _I, _P, _P, _P],
+    "oodb200_roi_pool_nhwc_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _L, _P],
+    "oodb200_fmap_score_nhwc_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P,
+                                    _P, _I, _P, _P, _P, _L, _P],
     "oodb200_logit_score_f32": [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "oodb200_fuse_u8": [_P, _P, _P, _I, _I, _P, _P],
     "oodb200_fuse_score_f32": [_P, _P, _I, _P, _P],

@@ -55,12 +55,15 @@ constexpr int kMaxSlices = 255;
 #endif
 constexpr int kSliceChannels = OODB200_FMAP_SLICE;   // channels per work item (multiple of 32)
 constexpr int kCU = OODB200_FMAP_CU;
+constexpr int kSliceNhwc = 128;                      // channels-last: one 128-bit load per lane covers a slice of one cell
 
 struct FmapParams {
     const float* const* map_ptrs;
     int C[3], H[3], W[3];
     float scale[3];
     int ns[3];                  // slices per box, per stride
+    int nhwc;                   // maps are channels-last: element (c, y, x) of a map at [(y * W + x) * C + c]
+    int slice;                  // channels per work item: kSliceChannels (NCHW) / kSliceNhwc (channels-last)
     const float* boxes;
     const int32_t* img_idx;
     const int32_t* stride_idx;
@@ -692,8 +695,80 @@ __device__ __forceinline__ void finalize(const FmapParams& p, int s, int cls, in
     write_result(p, s, cls, cls_ok, K, out, b);
 }
 
+// ---------------------------------------------------------------------------------------------- channels-last pooling
+// Channels-last maps (what a detector run in torch.channels_last hands out): the C values of a cell are contiguous, so
+// one warp request = 128 channels of one cell = 512 contiguous bytes, every fetched line is used in full and the pooled
+// channels never leave their lane: no cross-lane reduction at all.  Lanes first build the (offset, weight) pair of up to 32
+// cells of the window in parallel; the cells are then visited with shuffles, 8 loads in flight, zero-weight padding
+// columns skipped without touching memory.  Accumulation runs cell by cell in row-major order (fixed order).
+__device__ __forceinline__ void pool_nhwc(const float* __restrict__ img, int C, int W, int4 geo,
+                                          const float* __restrict__ wy, const float* __restrict__ wx, float count,
+                                          int c_lo, int c_hi, float* __restrict__ out0, float* __restrict__ out1) {
+    const int lane = threadIdx.x & 31;
+    const int y0 = geo.x, xa = geo.y, wh = geo.z, wc = 4 * geo.w, ncell = wh * wc;
+    const int c = c_lo + lane * 4;
+    const bool vec = (C % 4 == 0) && (((uintptr_t)img & 15) == 0);
+    if (vec) {
+        const bool mine = c < c_hi;                    // c_hi - c_lo is a multiple of 4 here
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q0 = 0; q0 < ncell; q0 += 32) {
+            const int q = q0 + lane;
+            float wq = 0.f;
+            int oq = 0;
+            if (q < ncell) {
+                const int r = q / wc, x = q - r * wc;
+                wq = __ldg(wy + r) * __ldg(wx + x);
+                oq = ((y0 + r) * W + xa + x) * C;
+            }
+            const unsigned live = __ballot_sync(kFull, wq != 0.f);
+            unsigned todo = live;
+            while (todo) {                             // warp-uniform: 8 cells per round
+                float4 v[8];
+                float w8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = todo ? __ffs(todo) - 1 : 0;
+                    const bool on = todo != 0;
+                    todo &= todo - 1;
+                    const int off = __shfl_sync(kFull, oq, j);
+                    w8[u] = on ? __shfl_sync(kFull, wq, j) : 0.f;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (on && mine) v[u] = __ldg(reinterpret_cast<const float4*>(img + (size_t)off + c));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    acc.x = fmaf(w8[u], v[u].x, acc.x); acc.y = fmaf(w8[u], v[u].y, acc.y);
+                    acc.z = fmaf(w8[u], v[u].z, acc.z); acc.w = fmaf(w8[u], v[u].w, acc.w);
+                }
+            }
+        }
+        if (mine) {
+            const float4 val = make_float4(__fdiv_rn(acc.x, count), __fdiv_rn(acc.y, count), __fdiv_rn(acc.z, count),
+                                           __fdiv_rn(acc.w, count));   // average over the sample grid (roi_align.py:192-196)
+            *reinterpret_cast<float4*>(out0 + c) = val;
+            if (out1) { out1[c] = val.x; out1[c + 1] = val.y; out1[c + 2] = val.z; out1[c + 3] = val.w; }
+        }
+    } else {                                           // any C / alignment: lanes over channels, scalar loads
+        for (int cc = c_lo + lane; cc < c_hi; cc += 32) {
+            float acc = 0.f;
+            for (int r = 0; r < wh; ++r)
+                for (int x = 0; x < wc; ++x) {
+                    const float w = __ldg(wy + r) * __ldg(wx + x);
+                    if (w != 0.f) acc = fmaf(w, __ldg(img + ((size_t)(y0 + r) * W + xa + x) * C + cc), acc);
+                }
+            const float val = __fdiv_rn(acc, count);
+            out0[cc] = val;
+            if (out1) out1[cc] = val;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- gather kernel
-__global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kernel(const __grid_constant__ FmapParams p) {
+#ifndef OODB200_FMAP_NHWC_BLOCKS
+#define OODB200_FMAP_NHWC_BLOCKS 3
+#endif
+template <bool NHWC>
+__global__ void __launch_bounds__(kThreads, NHWC ? OODB200_FMAP_NHWC_BLOCKS : OODB200_FMAP_MIN_BLOCKS) items_kernel(const __grid_constant__ FmapParams p) {
     const int lane = threadIdx.x & 31;
     const int n_items = p.counters[0];
     // Scheduling: the first kStaticPct % of the work list is handed out round-robin (no atomics: same-address atomics
@@ -744,7 +819,8 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kerne
         const int C = p.C[s], W = p.W[s], HW = p.H[s] * W;
         const int4 geo = make_int4(r0.y & 0xFFFF, (int)((uint32_t)r0.y >> 16), r0.z & 0xFFFF, (int)((uint32_t)r0.z >> 16));
         const int out = r0.w;
-        const int c_lo = sl * kSliceChannels, c_hi = min(C, c_lo + kSliceChannels);
+        constexpr int kSl = NHWC ? kSliceNhwc : kSliceChannels;
+        const int c_lo = sl * kSl, c_hi = min(C, c_lo + kSl);
         float* __restrict__ out0 = p.pooled + (size_t)out * p.pooled_ld;
         float* __restrict__ out1 = p.pooled_user ? p.pooled_user + (size_t)out * p.pooled_user_ld : nullptr;
         if (geo.w == 0) {                              // no sample inside the map (Q5): all-zero vector
@@ -754,9 +830,13 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kerne
             const float* __restrict__ wy = p.wts + (size_t)box * p.wstride;
             const float* __restrict__ wx = wy + p.ext_y;
             const float count = __int_as_float(r1.z);
-            const bool vec = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (HW % 4 == 0);
-            if (vec) pool_dispatch(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
-            else pool_scalar(img, HW, W, geo.x, geo.y, geo.z, geo.w, wy, wx, count, c_lo, c_hi, out0, out1);
+            if (NHWC) {
+                pool_nhwc(img, C, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+            } else {
+                const bool vec = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (HW % 4 == 0);
+                if (vec) pool_dispatch(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+                else pool_scalar(img, HW, W, geo.x, geo.y, geo.z, geo.w, wy, wx, count, c_lo, c_hi, out0, out1);
+            }
         }
         r0 = n0; r1 = n1; it = nit;
     }
@@ -1030,7 +1110,7 @@ static WorkspaceLayout layout_of(int n, int nc, const int32_t* map_chw) {
     return L;
 }
 
-static int g_sm_count = 0, g_items_per_sm = 0;
+static int g_sm_count = 0, g_items_per_sm = 0, g_items_per_sm_nhwc = 0;
 
 static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale, int32_t* cls_used_out,
                        int32_t* out_index_out, void* workspace, int64_t workspace_bytes, void* stream, const char* what) {
@@ -1040,9 +1120,11 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
         p.W[s] = map_chw[3 * s + 2];
         p.scale[s] = scale[s];
         OODB200_REQUIRE(p.C[s] > 0 && p.H[s] > 0 && p.W[s] > 0, "%s: map %d has non-positive shape", what, s);
-        p.ns[s] = (p.C[s] + kSliceChannels - 1) / kSliceChannels;
+        p.slice = p.nhwc ? kSliceNhwc : kSliceChannels;
+        p.ns[s] = (p.C[s] + p.slice - 1) / p.slice;
         OODB200_REQUIRE(p.ns[s] <= kMaxSlices, "%s: map %d has too many channels (%d)", what, s, p.C[s]);
         OODB200_REQUIRE((long long)p.H[s] * p.W[s] < (1LL << 30) && p.H[s] < 65536 && p.W[s] < 65536, "%s: map %d too large", what, s);
+        OODB200_REQUIRE(!p.nhwc || (long long)p.H[s] * p.W[s] * p.C[s] < (1LL << 31), "%s: channels-last map %d too large", what, s);
     }
     OODB200_REQUIRE(p.n < (1 << 24), "%s: at most %d boxes per call", what, (1 << 24) - 1);
     if (p.n == 0) return OODB200_OK;
@@ -1095,12 +1177,16 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
             g_sm_count = 148;
     }
     if (g_items_per_sm == 0 &&
-        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_items_per_sm, items_kernel, kThreads, 0) != cudaSuccess || g_items_per_sm <= 0))
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_items_per_sm, items_kernel<false>, kThreads, 0) != cudaSuccess || g_items_per_sm <= 0))
         g_items_per_sm = OODB200_FMAP_MIN_BLOCKS;
+    if (g_items_per_sm_nhwc == 0 &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_items_per_sm_nhwc, items_kernel<true>, kThreads, 0) != cudaSuccess || g_items_per_sm_nhwc <= 0))
+        g_items_per_sm_nhwc = OODB200_FMAP_MIN_BLOCKS;
     long long max_items = (long long)p.n * L.max_ns;
-    long long grid = (long long)g_sm_count * g_items_per_sm;          // persistent: every resident warp pulls from the queue
+    long long grid = (long long)g_sm_count * (p.nhwc ? g_items_per_sm_nhwc : g_items_per_sm);   // persistent: every resident warp pulls from the queue
     if (grid * kWarps > max_items) grid = (max_items + kWarps - 1) / kWarps;
-    items_kernel<<<(int)grid, kThreads, 0, st>>>(p);
+    if (p.nhwc) items_kernel<true><<<(int)grid, kThreads, 0, st>>>(p);
+    else items_kernel<false><<<(int)grid, kThreads, 0, st>>>(p);
     rc = check_launch(what);
     if (rc) return rc;
     if (p.cent) {
@@ -1140,29 +1226,45 @@ extern "C" int64_t oodb200_fmap_workspace_bytes(int n, int nc, const int32_t* ma
     return (int64_t)layout_of(n, nc, map_chw).total;
 }
 
-extern "C" int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
-                                    const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
-                                    const int32_t* img_start, int n,
-                                    float* out, int out_ld, void* workspace, int64_t workspace_bytes, void* stream) {
+static int roi_pool_impl(int nhwc, const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
+                         const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
+                         const int32_t* img_start, int n,
+                         float* out, int out_ld, void* workspace, int64_t workspace_bytes, void* stream) {
     OODB200_REQUIRE(n >= 0 && n_img >= 0, "roi_pool: negative size");
     OODB200_REQUIRE(map_chw && scale, "roi_pool: map_chw/scale must be host arrays");
     if (n == 0) return OODB200_OK;
     OODB200_REQUIRE(map_ptrs && boxes && img_idx && stride_idx && img_start && out, "roi_pool: null pointer");
     FmapParams p = {};
     p.map_ptrs = map_ptrs; p.boxes = boxes; p.img_idx = img_idx; p.stride_idx = stride_idx; p.img_start = img_start;
-    p.n = n; p.n_img = n_img; p.pooled_user = out; p.pooled_user_ld = out_ld;
+    p.n = n; p.n_img = n_img; p.pooled_user = out; p.pooled_user_ld = out_ld; p.nhwc = nhwc;
     return launch_fmap(p, map_chw, scale, nullptr, nullptr, workspace, workspace_bytes, stream, "roi_pool");
 }
 
-extern "C" int oodb200_fmap_score_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
-                                      const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
-                                      const int32_t* cls, const int32_t* img_start, int compat_q1, int n,
-                                      int metric_mask, int normalize,
-                                      const float* cent, const float* cent_unit, const int64_t* cent_off,
-                                      const int32_t* cent_k, int nc, const double* thr,
-                                      float* dist, int32_t* argmin, uint8_t* decision,
-                                      float* pooled, int pooled_ld, int32_t* cls_used_out, int32_t* out_index_out,
-                                      void* workspace, int64_t workspace_bytes, void* stream) {
+extern "C" int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
+                                    const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
+                                    const int32_t* img_start, int n,
+                                    float* out, int out_ld, void* workspace, int64_t workspace_bytes, void* stream) {
+    return roi_pool_impl(0, map_ptrs, map_chw, scale, n_img, boxes, img_idx, stride_idx, img_start, n, out, out_ld, workspace,
+                         workspace_bytes, stream);
+}
+
+extern "C" int oodb200_roi_pool_nhwc_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
+                                         const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
+                                         const int32_t* img_start, int n,
+                                         float* out, int out_ld, void* workspace, int64_t workspace_bytes, void* stream) {
+    return roi_pool_impl(1, map_ptrs, map_chw, scale, n_img, boxes, img_idx, stride_idx, img_start, n, out, out_ld, workspace,
+                         workspace_bytes, stream);
+}
+
+static int fmap_score_impl(int nhwc, const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
+                           const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
+                           const int32_t* cls, const int32_t* img_start, int compat_q1, int n,
+                           int metric_mask, int normalize,
+                           const float* cent, const float* cent_unit, const int64_t* cent_off,
+                           const int32_t* cent_k, int nc, const double* thr,
+                           float* dist, int32_t* argmin, uint8_t* decision,
+                           float* pooled, int pooled_ld, int32_t* cls_used_out, int32_t* out_index_out,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
     OODB200_REQUIRE(n >= 0 && n_img >= 0 && nc > 0, "fmap_score: bad size");
     OODB200_REQUIRE(map_chw && scale, "fmap_score: map_chw/scale must be host arrays");
     OODB200_REQUIRE(metric_mask > 0 && metric_mask < (1 << OODB200_N_METRICS), "fmap_score: metric_mask %d", metric_mask);
@@ -1177,8 +1279,24 @@ extern "C" int oodb200_fmap_score_f32(const float* const* map_ptrs, const int32_
     p.metric_mask = metric_mask; p.normalize = normalize;
     p.cent = cent; p.cent_unit = cent_unit ? cent_unit : cent; p.cent_off = cent_off; p.cent_k = cent_k; p.nc = nc; p.thr = thr;
     p.dist = dist; p.argmin = argmin; p.decision = decision; p.pooled_user = pooled; p.pooled_user_ld = pooled_ld;
+    p.nhwc = nhwc;
     return launch_fmap(p, map_chw, scale, cls_used_out, out_index_out, workspace, workspace_bytes, stream, "fmap_score");
 }
+
+#define OODB200_FMAP_SCORE_ARGS                                                                                       \
+    const float *const *map_ptrs, const int32_t *map_chw, const float *scale, int n_img, const float *boxes,          \
+        const int32_t *img_idx, const int32_t *stride_idx, const int32_t *cls, const int32_t *img_start, int compat_q1, \
+        int n, int metric_mask, int normalize, const float *cent, const float *cent_unit, const int64_t *cent_off,    \
+        const int32_t *cent_k, int nc, const double *thr, float *dist, int32_t *argmin, uint8_t *decision,            \
+        float *pooled, int pooled_ld, int32_t *cls_used_out, int32_t *out_index_out, void *workspace,                 \
+        int64_t workspace_bytes, void *stream
+#define OODB200_FMAP_SCORE_PASS                                                                                        \
+    map_ptrs, map_chw, scale, n_img, boxes, img_idx, stride_idx, cls, img_start, compat_q1, n, metric_mask, normalize, \
+        cent, cent_unit, cent_off, cent_k, nc, thr, dist, argmin, decision, pooled, pooled_ld, cls_used_out,           \
+        out_index_out, workspace, workspace_bytes, stream
+
+extern "C" int oodb200_fmap_score_f32(OODB200_FMAP_SCORE_ARGS) { return fmap_score_impl(0, OODB200_FMAP_SCORE_PASS); }
+extern "C" int oodb200_fmap_score_nhwc_f32(OODB200_FMAP_SCORE_ARGS) { return fmap_score_impl(1, OODB200_FMAP_SCORE_PASS); }
 
 extern "C" int oodb200_q1_plan_i32(const int32_t* img_start, const int32_t* stride_idx, const int32_t* cls, int n_img,
                                    int32_t* cls_used, int32_t* out_index, void* stream) {

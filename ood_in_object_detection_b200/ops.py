@@ -77,6 +77,7 @@ class DetectionBatch:
     img_start: torch.Tensor         # [n_img+1] i32
     counts: List[int]               # host copy of boxes per image
     keepalive: tuple = ()           # tensors whose storage map_ptrs points into
+    nhwc: bool = False              # the maps are channels-last ([H, W, C] per image): the *_nhwc entry points read them
 
     @property
     def n(self) -> int:
@@ -90,6 +91,21 @@ class StagedMaps:
     chw: list                  # 3 x (C_s, H_s, W_s)
     n_img: int
     keepalive: tuple
+    nhwc: bool = False         # channels-last maps: element (c, y, x) at [(y * W + x) * C + c]
+
+
+def _is_channels_last(t: torch.Tensor) -> bool:
+    """4-D [B,C,H,W] or 3-D [C,H,W] tensor whose memory is [.., H, W, C] (torch.channels_last and its per-image slices);
+    a map with C == 1 or H == W == 1 is both layouts at once and counts as the default one."""
+    if t.dim() == 4:
+        c, h, w = t.shape[1:]
+        st = t.stride()[1:]
+    else:
+        c, h, w = t.shape
+        st = t.stride()
+    if c == 1 or h * w == 1:
+        return False
+    return tuple(st) == (1, w * c, c)
 
 
 def stage_maps(maps, n_img: int, device=None) -> StagedMaps:
@@ -98,8 +114,15 @@ def stage_maps(maps, n_img: int, device=None) -> StagedMaps:
     maps: either 3 batched tensors [B,C_s,H_s,W_s] or a per-image list of 3 CHW tensors."""
     device = device or default_device()
     keep = []
+    nhwc = False
     if len(maps) == 3 and all(isinstance(m, torch.Tensor) and m.dim() == 4 for m in maps):
-        mt = [_dev(m, device, torch.float32) for m in maps]
+        nhwc = all(_is_channels_last(m) for m in maps)
+        if nhwc:                                       # keep the channels-last memory: no re-layout, the kernels read it as is
+            mt = [m if (m.device == device and m.dtype == torch.float32) else
+                  m.to(device=device, dtype=torch.float32, non_blocking=True, memory_format=torch.preserve_format) for m in maps]
+            assert all(_is_channels_last(m) for m in mt)
+        else:
+            mt = [_dev(m, device, torch.float32) for m in maps]
         assert all(m.shape[0] == n_img for m in mt), "batched maps must have one slice per image"
         chw = [tuple(m.shape[1:]) for m in mt]
         ptrs = np.empty((n_img, 3), dtype=np.int64)
@@ -118,9 +141,18 @@ def stage_maps(maps, n_img: int, device=None) -> StagedMaps:
             chw = shp
         if chw is None:
             chw = [(1, 1, 1)] * 3
+        flat_maps = [t for per_img in maps for t in per_img]
+        nhwc = bool(flat_maps) and all(_is_channels_last(t) for t in flat_maps)
         for s in range(3):
             col = [per_img[s] for per_img in maps]
             nbytes = int(np.prod(chw[s])) * 4
+            if nhwc:                                   # per-image channels-last views: moved as they are, one by one
+                ts = [t if (t.device == device and t.dtype == torch.float32) else
+                      t.to(device=device, dtype=torch.float32, non_blocking=True, memory_format=torch.preserve_format) for t in col]
+                assert all(_is_channels_last(t) for t in ts), "channels-last maps must keep their layout on the device"
+                ptrs[:, s] = [t.data_ptr() for t in ts]
+                keep.extend(ts)
+                continue
             batched = None
             st0 = col[0].untyped_storage() if col else None
             if col and not col[0].is_cuda and col[0].dtype == torch.float32 and all(
@@ -136,7 +168,7 @@ def stage_maps(maps, n_img: int, device=None) -> StagedMaps:
                 ts = [_dev(t, device, torch.float32) for t in col]
                 ptrs[:, s] = [t.data_ptr() for t in ts]
                 keep.extend(ts)
-    return StagedMaps(ptrs=ptrs, chw=[tuple(int(v) for v in c) for c in chw], n_img=n_img, keepalive=tuple(keep))
+    return StagedMaps(ptrs=ptrs, chw=[tuple(int(v) for v in c) for c in chw], n_img=n_img, keepalive=tuple(keep), nhwc=nhwc)
 
 
 def make_batch(maps, boxes: Sequence, strides: Sequence, cls: Sequence, img_w: int, device=None) -> DetectionBatch:
@@ -175,7 +207,7 @@ def make_batch(maps, boxes: Sequence, strides: Sequence, cls: Sequence, img_w: i
         scale=np.asarray([np.float32(c[2] / img_w) for c in chw], dtype=np.float32),
         n_img=n_img, boxes=bx, img_idx=h2d(img_idx, device),
         stride_idx=st, cls=cl, img_start=h2d(start, device),
-        counts=counts, keepalive=tuple(keep))
+        counts=counts, keepalive=tuple(keep), nhwc=staged.nhwc)
 
 
 @dataclass
@@ -323,10 +355,11 @@ def roi_pool(batch: DetectionBatch, out: Optional[torch.Tensor] = None) -> torch
     if out is None:
         out = torch.zeros((batch.n, cmax), dtype=torch.float32, device=batch.boxes.device)
     ws = _workspace(batch, 0)
-    _lib.check(lib.oodb200_roi_pool_f32(
+    fn, name = (lib.oodb200_roi_pool_nhwc_f32, "oodb200_roi_pool_nhwc_f32") if batch.nhwc else (lib.oodb200_roi_pool_f32, "oodb200_roi_pool_f32")
+    _lib.check(fn(
         _ptr(batch.map_ptrs), batch.map_chw.ctypes.data_as(C.c_void_p), batch.scale.ctypes.data_as(C.c_void_p),
         batch.n_img, _ptr(batch.boxes), _ptr(batch.img_idx), _ptr(batch.stride_idx), _ptr(batch.img_start), batch.n,
-        _ptr(out), int(out.stride(0)), _ptr(ws), int(ws.numel()), _stream()), "oodb200_roi_pool_f32")
+        _ptr(out), int(out.stride(0)), _ptr(ws), int(ws.numel()), _stream()), name)
     return out
 
 
@@ -360,7 +393,8 @@ def fmap_score(batch: DetectionBatch, table: CentroidTable, metric_mask: int, no
         cmax = int(batch.map_chw.reshape(3, 3)[:, 0].max())
         out = alloc_fmap_scores(n, batch.boxes.device, cmax, want_pooled, want_plan)
     ws = _workspace(batch, table.nc)
-    _lib.check(lib.oodb200_fmap_score_f32(
+    fn, name = (lib.oodb200_fmap_score_nhwc_f32, "oodb200_fmap_score_nhwc_f32") if batch.nhwc else (lib.oodb200_fmap_score_f32, "oodb200_fmap_score_f32")
+    _lib.check(fn(
         _ptr(batch.map_ptrs), batch.map_chw.ctypes.data_as(C.c_void_p), batch.scale.ctypes.data_as(C.c_void_p),
         batch.n_img, _ptr(batch.boxes), _ptr(batch.img_idx), _ptr(batch.stride_idx), _ptr(batch.cls),
         _ptr(batch.img_start), int(bool(compat_q1)), n, int(metric_mask), int(bool(normalize)),
@@ -368,7 +402,7 @@ def fmap_score(batch: DetectionBatch, table: CentroidTable, metric_mask: int, no
         _ptr(out.dist), _ptr(out.argmin), _ptr(out.decision),
         _ptr(out.pooled), int(out.pooled.stride(0)) if out.pooled is not None else 0,
         _ptr(out.cls_used), _ptr(out.out_index), _ptr(ws), int(ws.numel()), _stream()),
-        "oodb200_fmap_score_f32")
+        name)
     return out
 
 

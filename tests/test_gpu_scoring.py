@@ -221,3 +221,57 @@ def test_empty_batch_and_invalid_args(ops):
     assert ops.fmap_score(batch, table, 0b010).dist.shape == (3, 0)
     with pytest.raises(RuntimeError, match="metric_mask"):
         ops.fmap_score(batch, table, 0)
+
+
+def _channels_last(m: np.ndarray) -> torch.Tensor:
+    """[B, C, H, W] array -> tensor with the same values and shape whose memory is [B, H, W, C]."""
+    return torch.from_numpy(np.ascontiguousarray(m)).contiguous(memory_format=torch.channels_last)
+
+
+def test_channels_last_maps_give_the_reference_results(ops, golden):
+    """The *_nhwc entry points (maps as torch.channels_last hands them out): pooled vectors within 1e-5 of the reference
+    extractor on the edge boxes; fused decisions / arg-min / order identical to the default-layout pass on the golden
+    batches, distances within 1e-5; batched tensors, per-image views and host tensors all keep their layout."""
+    g = golden("golden_roi_edges.npz")
+    n, img = g["n_boxes"], int(g["img"])
+    boxes, strides = split(g["boxes"], n), split(g["strides"], n)
+    cls = [np.zeros(len(b), np.float32) for b in boxes]
+    maps_cl = [_channels_last(g[f"map{s}"]) for s in range(3)]
+    batch = ops.make_batch(maps_cl, boxes, strides, cls, img)
+    assert batch.nhwc
+    pooled = ops.roi_pool(batch).cpu().numpy()
+    start = np.concatenate([[0], np.cumsum(n)])
+    for i in range(3):
+        for s in range(3):
+            idx, exp = g[f"all0_idx_{i}_{s}"].astype(int), g[f"all0_feat_{i}_{s}"]
+            got = pooled[start[i] + idx][:, :exp.shape[1]]
+            scale = np.abs(exp).max(axis=1, keepdims=True) + 1e-30
+            assert np.all(np.abs(got - exp) <= RTOL * scale), (i, s)
+    for name in ("golden_c1_one.npz", "golden_small_kmeans5.npz"):
+        g = golden(name)
+        images, maps = scoring_case(g)
+        nc, img = int(g["nc"]), int(g["img"])
+        dims = [int(c) for c in g["channels"]]
+        clusters = unpack_nested(g, "l2_clusters", nc)
+        thr = {ops.METRIC_SLOT[m]: unpack_nested(g, f"{t}_thr", nc, as_threshold=True)
+               for t, m in (("l1", "l1"), ("l2", "l2"), ("cos", "cosine"))}
+        table = ops.pack_centroids(clusters, thr, dims)
+        ref = ops.fmap_score(_batch_from_images(ops, images, img), table, 0b111, True, compat_q1=True, want_plan=True)
+        args = ([torch.from_numpy(im["boxes"]) for im in images], [torch.from_numpy(im["strides"]) for im in images],
+                [torch.from_numpy(im["cls"]) for im in images], img)
+        batched = [_channels_last(m) for m in maps]                               # host, batched
+        per_image = [[m[i] for m in batched] for i in range(len(images))]         # host, per-image views
+        on_device = [m.cuda() for m in batched]                                   # device, batched
+        for maps_in in (batched, per_image, on_device):
+            b = ops.make_batch(maps_in, *args)
+            assert b.nhwc
+            res = ops.fmap_score(b, table, 0b111, True, compat_q1=True, want_plan=True)
+            assert torch.equal(res.out_index, ref.out_index) and torch.equal(res.cls_used, ref.cls_used)
+            d, dr = res.dist.cpu().numpy(), ref.dist.cpu().numpy()
+            np.testing.assert_allclose(d, dr, rtol=RTOL, atol=5e-7)
+            assert (res.argmin != ref.argmin).sum().item() == 0
+            for slot, tag in ((0, "l1"), (1, "l2"), (2, "cos")):
+                thr_flat = np.array([thr[slot][c][s] if thr[slot][c][s] != [] else np.nan
+                                     for c, s in zip(g[f"{tag}_cls_used"], g[f"{tag}_stride_of"])], np.float64)
+                near = np.abs(g[f"{tag}_dist"] - thr_flat) <= RTOL * np.abs(thr_flat)
+                assert np.array_equal(res.decision[slot].cpu().numpy()[~near], g[f"{tag}_decisions"][~near]), (name, tag)
