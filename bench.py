@@ -389,7 +389,12 @@ def run_ours(args, wl):
     lmask = sum(1 << ops.LOGIT_SLOT[m] for m in LOGIT_METHODS)
     lthr_d = torch.from_numpy(lthr).to(device)
 
+    maps_cl = [m.contiguous(memory_format=torch.channels_last) for m in maps]    # same values, [B, H, W, C] memory
+    if args.layout == "nhwc":
+        maps, maps_cl = maps_cl, maps
     batch = ops.make_batch(maps, det["boxes"], det["strides"], det["cls"], wl.img, device)
+    batch_alt = ops.make_batch(maps_cl, det["boxes"], det["strides"], det["cls"], wl.img, device)
+    assert batch.nhwc == (args.layout == "nhwc") and batch_alt.nhwc != batch.nhwc
     logits = torch.from_numpy(np.concatenate(det["logits"])).to(device)
     n = batch.n
     fout = ops.alloc_fmap_scores(n, device)
@@ -401,12 +406,18 @@ def run_ours(args, wl):
     def fused():
         ops.fmap_score(batch, table, fmask, True, compat_q1=True, out=fout)     # memset + plan + geo + items + score
 
+    fout_alt = ops.alloc_fmap_scores(n, device)
+
+    def fused_alt():                                                             # the same pass on the other map layout
+        ops.fmap_score(batch_alt, table, fmask, True, compat_q1=True, out=fout_alt)
+
     def logit():
         ops.logit_score(logits, batch.cls, lmask, thr=lthr_d, out=lout)
 
     for _ in range(max(args.warmup, 3)):                                        # also sizes the workspace before capture
         flush.zero_()
         fused()
+        fused_alt()
         logit()
     torch.cuda.synchronize()
     # the step = ONE graph: the fused FMap path on the capture stream, the (independent) logit methods on a forked branch
@@ -421,9 +432,13 @@ def run_ours(args, wl):
         cur.wait_stream(side)
     with torch.cuda.graph(g_fused):                                             # the fused path alone: roofline timing
         fused()
+    g_alt = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_alt):
+        fused_alt()
     for _ in range(2):
         g_step.replay()
         g_fused.replay()
+        g_alt.replay()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -447,6 +462,17 @@ def run_ours(args, wl):
         b.record()
     torch.cuda.synchronize()
     fmap_ms = sum(a.elapsed_time(b) for a, b in evf) / max(args.steps, 1)
+    eva = [(E(), E()) for _ in range(args.steps)]                    # the fused path on the other map layout (reported beside)
+    for a, b in eva:
+        flush.zero_()
+        a.record()
+        g_alt.replay()
+        b.record()
+    torch.cuda.synchronize()
+    alt_ms = sum(a.elapsed_time(b) for a, b in eva) / max(args.steps, 1)
+    alt_name = "nchw" if args.layout == "nhwc" else "channels_last"
+    slots = [ops.METRIC_SLOT[m] for m in FMAP_METRICS]                # only the requested metric slots are written
+    alt_same = int((fout.decision[slots] != fout_alt.decision[slots]).sum()) + int((fout.argmin[slots] != fout_alt.argmin[slots]).sum())
     if world > 1:
         dist.barrier()
         t = torch.tensor([total_ms, float(n)], dtype=torch.float64, device=device)
@@ -462,7 +488,9 @@ def run_ours(args, wl):
         if rank == 0:
             alg, upper, _ = algorithmic_bytes(det, wl, wl.k)
             print(json.dumps({"value": value, "ms_per_step": total_ms / args.steps, "fmap_ms": fmap_ms,
-                              "frac": alg / (fmap_ms * 1e-3) / 1e9 / _peaks()[0], "quick": True}))
+                              "frac": alg / (fmap_ms * 1e-3) / 1e9 / _peaks()[0], alt_name + "_fmap_ms": alt_ms,
+                              alt_name + "_frac": alg / (alt_ms * 1e-3) / 1e9 / _peaks()[0],
+                              "decisions_or_argmin_differing": alt_same, "quick": True}))
         if world > 1:
             dist.destroy_process_group()
         return
@@ -532,14 +560,19 @@ def run_ours(args, wl):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl.name, "images_per_gpu": wl.batch, "boxes_per_gpu": n, "fmap_metrics": FMAP_METRICS,
+            "config": {"workload": wl.name, "map_layout": args.layout, "images_per_gpu": wl.batch, "boxes_per_gpu": n, "fmap_metrics": FMAP_METRICS,
                        "logit_methods": LOGIT_METHODS, "k_per_class_stride": wl.k, "nc": wl.nc,
                        "l2_flush": "512 MiB memset between timed iterations", "sharding": f"batch x{world}, no collective",
                        "launch": "one CUDA graph per step: fused FMap path + logit methods on a forked branch"},
-            "roofline": {"bound": "hbm", "kernel": "items_kernel (window gather) within plan+geo+items+score", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "items_kernel (window gather) within plan_geo+items+score", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": _traffic(args.config, "fmap_dram_bytes_per_launch"), "algorithmic_bytes": alg,
-                         "upper_bound_bytes": upper, "kernel_ms": fmap_ms, "peak_source": how,
+                         "traffic": _traffic(args.config, "fmap_dram_bytes_per_launch") if args.layout == "nchw" else None,
+                         "algorithmic_bytes": alg,
+                         "upper_bound_bytes": upper, "kernel_ms": fmap_ms, "peak_source": how, "layout": args.layout,
+                         "other_layout": {"layout": alt_name, "kernel_ms": alt_ms, "achieved": alg / (alt_ms * 1e-3) / 1e9,
+                                          "frac": alg / (alt_ms * 1e-3) / 1e9 / peak, "decisions_or_argmin_differing": alt_same,
+                                          "note": "the same fused pass over the same values with the maps in the other memory "
+                                                  "layout (channels_last = what a detector run in torch.channels_last hands over)"},
                          "note": "HBM moves whole 128-byte lines; NCHW window rows are 8..52 B (DESIGN.md section 4)"},
             "cpu_baseline": {"value": cpu_n / cpu_t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{CPU_SAMPLE_IMAGES} of {wl.batch} images ({cpu_n} boxes), L1+cosine FMap and "
@@ -565,6 +598,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C4", "C5"])
     ap.add_argument("--workload", default="score", choices=["score", "fit"])
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"],
+                    help="memory layout of the synthetic feature maps: nchw = what the reference's hooks hand over (default), "
+                         "nhwc = torch.channels_last; the other layout is timed beside it (roofline.other_layout)")
     ap.add_argument("--fit-n", type=int, default=None, help="vectors of the k-means sub-measurement (0: skip; default 2 M, "
                     "4 M for --workload fit)")
     ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the e2e, fit and cpu_baseline legs (tuning sweeps)")

@@ -48,14 +48,14 @@ constexpr int kMaxSlices = 255;
 #define OODB200_FMAP_SLICE 64
 #endif
 #ifndef OODB200_FMAP_CU
-#define OODB200_FMAP_CU 8                   // channel requests in flight per warp (x T chunk slots)
+#define OODB200_FMAP_CU 16                  // channel requests in flight per warp for windows of <= 32 chunks (8 beyond)
 #endif
 #ifndef OODB200_FMAP_STATIC_PCT
 #define OODB200_FMAP_STATIC_PCT 75          // share of the work list handed out round-robin, the rest through the queue
 #endif
 constexpr int kSliceChannels = OODB200_FMAP_SLICE;   // channels per work item (multiple of 32)
 constexpr int kCU = OODB200_FMAP_CU;
-constexpr int kSliceNhwc = 128;                      // channels-last: one 128-bit load per lane covers a slice of one cell
+constexpr int kSliceNhwc = 32;                       // channels-last: a slice of one cell = one 128-byte line = 8 lanes x 128 bits
 
 struct FmapParams {
     const float* const* map_ptrs;
@@ -172,6 +172,7 @@ constexpr int kPgThreads = 1024, kPgWarps = kPgThreads / 32, kPgCap = 1024;
 struct BoxGeo {
     int ylo, xa, wh, nxc;
     float count;
+    int xoff, ww;                // first live column relative to xa, number of live columns (channels-last path)
 };
 
 // ROI geometry + separable weights of one box (one warp); writes the weights, returns what the item records need.
@@ -194,12 +195,14 @@ __device__ __forceinline__ BoxGeo geo_compute(const FmapParams& p, int box, int 
     }
     ylo = __reduce_min_sync(kFull, ylo); yhi = __reduce_max_sync(kFull, yhi);
     xlo = __reduce_min_sync(kFull, xlo); xhi = __reduce_max_sync(kFull, xhi);
-    BoxGeo g = {0, 0, 0, 0, (float)max(gh * gw, 1)};
+    BoxGeo g = {0, 0, 0, 0, (float)max(gh * gw, 1), 0, 0};
     if (yhi >= 0 && xhi >= 0) {
         g.ylo = ylo;
         g.wh = yhi - ylo + 1;
         const int ww = xhi - xlo + 1;
         g.xa = xlo & ~3;
+        g.xoff = xlo - g.xa;
+        g.ww = ww;
         g.nxc = ((xlo + ww + 3) >> 2) - (g.xa >> 2);
         float* __restrict__ wy = p.wts + (size_t)box * p.wstride;
         float* __restrict__ wx = wy + p.ext_y;
@@ -222,7 +225,7 @@ __device__ __forceinline__ void geo_emit(const FmapParams& p, int box, int s, un
     for (int sl = lane; sl < p.ns[s]; sl += 32) {
         int4* rec = p.items + 2 * (size_t)(pos + sl * nbs);
         rec[0] = make_int4((int)(((uint32_t)sl << 24) | (uint32_t)box), g.ylo | (g.xa << 16), g.wh | (g.nxc << 16), out);
-        rec[1] = make_int4((int)(mapp & 0xffffffffu), (int)(mapp >> 32), __float_as_int(g.count), s);
+        rec[1] = make_int4((int)(mapp & 0xffffffffu), (int)(mapp >> 32), __float_as_int(g.count), s | (g.xoff << 2) | (g.ww << 4));
     }
 }
 
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(kPgThreads) plan_geo_kernel(const FmapParams p
     }
     // The geometry of a warp's first box does not depend on the plan: it overlaps the planner's chain of round trips.
     // The planner arrives at the cluster barrier first and computes its own box between arrive and wait.
-    BoxGeo g = {0, 0, 0, 0, 1.f};
+    BoxGeo g = {0, 0, 0, 0, 1.f, 0, 0};
     if (!planner && b < m && s >= 0 && s <= 2) g = geo_compute(p, b0 + b, s, bx);
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     if (planner && b < m) {
@@ -696,101 +699,119 @@ __device__ __forceinline__ void finalize(const FmapParams& p, int s, int cls, in
 }
 
 // ---------------------------------------------------------------------------------------------- channels-last pooling
-// Channels-last maps (what a detector run in torch.channels_last hands out): the C values of a cell are contiguous, so
-// one warp request = 128 channels of one cell = 512 contiguous bytes, every fetched line is used in full and the pooled
-// channels never leave their lane: no cross-lane reduction at all.  Lanes first build the (offset, weight) pair of up to 32
-// cells of the window in parallel; the cells are then visited with shuffles, 8 loads in flight, zero-weight padding
-// columns skipped without touching memory.  Accumulation runs cell by cell in row-major order (fixed order).
-__device__ __forceinline__ void pool_nhwc(const float* __restrict__ img, int C, int W, int4 geo,
-                                          const float* __restrict__ wy, const float* __restrict__ wx, float count,
-                                          int c_lo, int c_hi, float* __restrict__ out0, float* __restrict__ out1) {
+// Channels-last maps (what a detector run in torch.channels_last hands out): the C values of a cell are contiguous.  A
+// work item is a slice of 32 channels = ONE 128-byte line per cell: 8 lanes x 128 bits cover it, so a warp request fetches
+// 4 cells, every fetched line is used in full, and a pooled channel stays in its lane (the 4 cell groups are added with
+// two shuffles at the very end).  Lanes first build the (offset, weight) pairs of 32 cells of the window in parallel; the
+// cells are then visited with shuffles, 8 requests (32 cells) in flight.  Accumulation order is fixed (cell order).
+struct NhwcItem {
+    const float* img;
+    int box, c_lo, s, out, y0, x0, wh, ww, xoff;
+    float count;
+};
+
+__device__ __forceinline__ NhwcItem nhwc_decode(int4 r0, int4 r1) {
+    NhwcItem it;
+    it.img = reinterpret_cast<const float*>(((unsigned long long)(uint32_t)r1.y << 32) | (uint32_t)r1.x);
+    it.box = r0.x & 0xFFFFFF;
+    it.c_lo = (int)((uint32_t)r0.x >> 24) * kSliceNhwc;
+    it.s = r1.w & 3;
+    it.xoff = (r1.w >> 2) & 3;
+    it.ww = r1.w >> 4;
+    it.out = r0.w;
+    it.y0 = r0.y & 0xFFFF;
+    it.x0 = (int)((uint32_t)r0.y >> 16) + it.xoff;     // first live column
+    it.wh = r0.z & 0xFFFF;
+    it.count = __int_as_float(r1.z);
+    return it;
+}
+
+// (element offset, weight) of cell q0 + lane of the item's window (0 weight beyond the window)
+__device__ __forceinline__ void nhwc_cells(const FmapParams& p, const NhwcItem& it, int q0, float& wq, int& oq) {
+    const int q = q0 + (threadIdx.x & 31);
+    wq = 0.f;
+    oq = 0;
+    if (q < it.wh * it.ww) {
+        const float* __restrict__ wy = p.wts + (size_t)it.box * p.wstride;
+        const int r = q / it.ww, x = q - r * it.ww;
+        wq = __ldg(wy + r) * __ldg(wy + p.ext_y + it.xoff + x);
+        oq = ((it.y0 + r) * p.W[it.s] + it.x0 + x) * p.C[it.s];
+    }
+}
+
+// 32 cells: 8 requests of 4 cells (lane group g takes cell 4u + g), rounds beyond the window cost nothing
+__device__ __forceinline__ void nhwc_issue(const float* __restrict__ src, bool mine, int left, float wq, int oq,
+                                           float4 (&v)[8], float (&w8)[8]) {
+    const int g = (threadIdx.x & 31) >> 3;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        w8[u] = 0.f;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (4 * u < left) {                            // warp-uniform
+            const int j = 4 * u + g;
+            const int off = __shfl_sync(kFull, oq, j);
+            w8[u] = __shfl_sync(kFull, wq, j);
+            if (w8[u] != 0.f && mine) v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)off));
+        }
+    }
+}
+__device__ __forceinline__ void nhwc_consume(int left, const float4 (&v)[8], const float (&w8)[8], float4& acc) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        if (4 * u < left) {
+            acc.x = fmaf(w8[u], v[u].x, acc.x); acc.y = fmaf(w8[u], v[u].y, acc.y);
+            acc.z = fmaf(w8[u], v[u].z, acc.z); acc.w = fmaf(w8[u], v[u].w, acc.w);
+        }
+}
+
+// any C / alignment: lanes over channels, scalar loads
+__device__ __noinline__ void pool_nhwc_scalar(const FmapParams& p, const NhwcItem& it, float* __restrict__ out0,
+                                              float* __restrict__ out1) {
     const int lane = threadIdx.x & 31;
-    const int y0 = geo.x, xa = geo.y, wh = geo.z, wc = 4 * geo.w, ncell = wh * wc;
-    const int c = c_lo + lane * 4;
-    const bool vec = (C % 4 == 0) && (((uintptr_t)img & 15) == 0);
-    if (vec) {
-        const bool mine = c < c_hi;                    // c_hi - c_lo is a multiple of 4 here
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q0 = 0; q0 < ncell; q0 += 32) {
-            const int q = q0 + lane;
-            float wq = 0.f;
-            int oq = 0;
-            if (q < ncell) {
-                const int r = q / wc, x = q - r * wc;
-                wq = __ldg(wy + r) * __ldg(wx + x);
-                oq = ((y0 + r) * W + xa + x) * C;
+    const int C = p.C[it.s], W = p.W[it.s];
+    const float* __restrict__ wy = p.wts + (size_t)it.box * p.wstride;
+    const float* __restrict__ wx = wy + p.ext_y + it.xoff;
+    for (int cc = it.c_lo + lane; cc < min(C, it.c_lo + kSliceNhwc); cc += 32) {
+        float acc = 0.f;
+        for (int r = 0; r < it.wh; ++r)
+            for (int x = 0; x < it.ww; ++x) {
+                const float w = __ldg(wy + r) * __ldg(wx + x);
+                if (w != 0.f) acc = fmaf(w, __ldg(it.img + ((size_t)(it.y0 + r) * W + it.x0 + x) * C + cc), acc);
             }
-            const unsigned live = __ballot_sync(kFull, wq != 0.f);
-            unsigned todo = live;
-            while (todo) {                             // warp-uniform: 8 cells per round
-                float4 v[8];
-                float w8[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = todo ? __ffs(todo) - 1 : 0;
-                    const bool on = todo != 0;
-                    todo &= todo - 1;
-                    const int off = __shfl_sync(kFull, oq, j);
-                    w8[u] = on ? __shfl_sync(kFull, wq, j) : 0.f;
-                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (on && mine) v[u] = __ldg(reinterpret_cast<const float4*>(img + (size_t)off + c));
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    acc.x = fmaf(w8[u], v[u].x, acc.x); acc.y = fmaf(w8[u], v[u].y, acc.y);
-                    acc.z = fmaf(w8[u], v[u].z, acc.z); acc.w = fmaf(w8[u], v[u].w, acc.w);
-                }
-            }
-        }
-        if (mine) {
-            const float4 val = make_float4(__fdiv_rn(acc.x, count), __fdiv_rn(acc.y, count), __fdiv_rn(acc.z, count),
-                                           __fdiv_rn(acc.w, count));   // average over the sample grid (roi_align.py:192-196)
-            *reinterpret_cast<float4*>(out0 + c) = val;
-            if (out1) { out1[c] = val.x; out1[c + 1] = val.y; out1[c + 2] = val.z; out1[c + 3] = val.w; }
-        }
-    } else {                                           // any C / alignment: lanes over channels, scalar loads
-        for (int cc = c_lo + lane; cc < c_hi; cc += 32) {
-            float acc = 0.f;
-            for (int r = 0; r < wh; ++r)
-                for (int x = 0; x < wc; ++x) {
-                    const float w = __ldg(wy + r) * __ldg(wx + x);
-                    if (w != 0.f) acc = fmaf(w, __ldg(img + ((size_t)(y0 + r) * W + xa + x) * C + cc), acc);
-                }
-            const float val = __fdiv_rn(acc, count);
-            out0[cc] = val;
-            if (out1) out1[cc] = val;
-        }
+        const float val = __fdiv_rn(acc, it.count);
+        out0[cc] = val;
+        if (out1) out1[cc] = val;
     }
 }
 
 // ---------------------------------------------------------------------------------------------- gather kernel
-#ifndef OODB200_FMAP_NHWC_BLOCKS
-#define OODB200_FMAP_NHWC_BLOCKS 3
-#endif
-template <bool NHWC>
-__global__ void __launch_bounds__(kThreads, NHWC ? OODB200_FMAP_NHWC_BLOCKS : OODB200_FMAP_MIN_BLOCKS) items_kernel(const __grid_constant__ FmapParams p) {
+// Counting sort of the boxes by (stride, class used) for the score kernel: position = prefix of the plan's histogram + an
+// atomic ticket.  Runs in the gather kernels' prologue because the histogram is complete only after the plan kernel; the
+// order inside a group is arbitrary (every box is scored independently).  The list holds OUTPUT slots.
+__device__ __forceinline__ void sort_boxes_by_key(const FmapParams& p, int warp_g, int n_warps) {
+    if (!p.cent) return;
+    const int lane = threadIdx.x & 31;
+    for (int box = warp_g; box < p.n; box += n_warps) {
+        const int s = p.stride_idx[box];
+        if (s < 0 || s > 2) continue;
+        const int cu = p.cls_used[box];
+        const int out = p.out_index[box];
+        const int key = (cu >= 0 && cu < p.nc) ? s * p.nc + cu : 3 * p.nc;
+        int before = 0;
+        for (int i = lane; i < key; i += 32) before += p.hist[i];
+        before = __reduce_add_sync(kFull, before);
+        if (lane == 0) p.sorted[before + atomicAdd(&p.cursor[key], 1)] = out;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kernel(const __grid_constant__ FmapParams p) {
     const int lane = threadIdx.x & 31;
     const int n_items = p.counters[0];
     // Scheduling: the first kStaticPct % of the work list is handed out round-robin (no atomics: same-address atomics
     // serialise in L2 and their latency under contention is of the order of an item), the tail through an atomic queue
     // so that the last items balance.  The next item's index and record are requested while the current one runs.
     const int warp_g = blockIdx.x * kWarps + (threadIdx.x >> 5), n_warps = gridDim.x * kWarps;
-    if (p.cent) {
-        // Counting sort of the boxes by (stride, class used) for the score kernel: position = prefix of the plan's
-        // histogram + an atomic ticket.  Done here because the histogram is complete only after the plan kernel; the
-        // order inside a group is arbitrary (every box is scored independently).  The list holds OUTPUT slots.
-        for (int box = warp_g; box < p.n; box += n_warps) {
-            const int s = p.stride_idx[box];
-            if (s < 0 || s > 2) continue;
-            const int cu = p.cls_used[box];
-            const int out = p.out_index[box];
-            const int key = (cu >= 0 && cu < p.nc) ? s * p.nc + cu : 3 * p.nc;
-            int before = 0;
-            for (int i = lane; i < key; i += 32) before += p.hist[i];
-            before = __reduce_add_sync(kFull, before);
-            if (lane == 0) p.sorted[before + atomicAdd(&p.cursor[key], 1)] = out;
-        }
-    }
+    sort_boxes_by_key(p, warp_g, n_warps);
     const int n_static = (int)((long long)n_items * OODB200_FMAP_STATIC_PCT / 100);
     int q_reg = 0;                                     // lane 0: result of the most recent queue fetch
     bool q_pending = false;
@@ -815,12 +836,11 @@ __global__ void __launch_bounds__(kThreads, NHWC ? OODB200_FMAP_NHWC_BLOCKS : OO
         if (nit < n_items) { n0 = __ldg(p.items + 2 * (size_t)nit); n1 = __ldg(p.items + 2 * (size_t)nit + 1); }
 
         const int box = r0.x & 0xFFFFFF, sl = (int)((uint32_t)r0.x >> 24);
-        const int s = r1.w;
+        const int s = r1.w & 3;
         const int C = p.C[s], W = p.W[s], HW = p.H[s] * W;
         const int4 geo = make_int4(r0.y & 0xFFFF, (int)((uint32_t)r0.y >> 16), r0.z & 0xFFFF, (int)((uint32_t)r0.z >> 16));
         const int out = r0.w;
-        constexpr int kSl = NHWC ? kSliceNhwc : kSliceChannels;
-        const int c_lo = sl * kSl, c_hi = min(C, c_lo + kSl);
+        const int c_lo = sl * kSliceChannels, c_hi = min(C, c_lo + kSliceChannels);
         float* __restrict__ out0 = p.pooled + (size_t)out * p.pooled_ld;
         float* __restrict__ out1 = p.pooled_user ? p.pooled_user + (size_t)out * p.pooled_user_ld : nullptr;
         if (geo.w == 0) {                              // no sample inside the map (Q5): all-zero vector
@@ -830,13 +850,80 @@ __global__ void __launch_bounds__(kThreads, NHWC ? OODB200_FMAP_NHWC_BLOCKS : OO
             const float* __restrict__ wy = p.wts + (size_t)box * p.wstride;
             const float* __restrict__ wx = wy + p.ext_y;
             const float count = __int_as_float(r1.z);
-            if (NHWC) {
-                pool_nhwc(img, C, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
-            } else {
-                const bool vec = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (HW % 4 == 0);
-                if (vec) pool_dispatch(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
-                else pool_scalar(img, HW, W, geo.x, geo.y, geo.z, geo.w, wy, wx, count, c_lo, c_hi, out0, out1);
+            const bool vec = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (HW % 4 == 0);
+            if (vec) pool_dispatch(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
+            else pool_scalar(img, HW, W, geo.x, geo.y, geo.z, geo.w, wy, wx, count, c_lo, c_hi, out0, out1);
+        }
+        r0 = n0; r1 = n1; it = nit;
+    }
+}
+
+// Channels-last gather: the same work list and scheduling as items_kernel (record of the next item requested while the
+// current one runs).  Measured and not kept: building the next item's (offset, weight) pairs under the current item's
+// cell loads with records fetched two items ahead -- 85 us (16 warps/SM) / 98 us (24 warps/SM, spills) against 78 us
+// for this loop: the deeper look-ahead takes work out of the balancing queue early.
+#ifndef OODB200_FMAP_NHWC_BLOCKS
+#define OODB200_FMAP_NHWC_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kThreads, OODB200_FMAP_NHWC_BLOCKS) items_nhwc_kernel(const __grid_constant__ FmapParams p) {
+    const int lane = threadIdx.x & 31, g = lane >> 3, l = lane & 7;
+    const int n_items = p.counters[0];
+    const int warp_g = blockIdx.x * kWarps + (threadIdx.x >> 5), n_warps = gridDim.x * kWarps;
+    sort_boxes_by_key(p, warp_g, n_warps);
+    const int n_static = (int)((long long)n_items * OODB200_FMAP_STATIC_PCT / 100);
+    int q_reg = 0;
+    bool q_pending = false;
+    auto next_index = [&](int cur) {                   // warp-uniform (see items_kernel)
+        int nx = cur + n_warps;
+        if (cur < n_static && nx < n_static) return nx;
+        if (!q_pending) {
+            if (lane == 0) q_reg = atomicAdd(&p.counters[1], 1);
+        }
+        nx = n_static + __shfl_sync(kFull, q_reg, 0);
+        if (lane == 0) q_reg = atomicAdd(&p.counters[1], 1);
+        q_pending = true;
+        return nx;
+    };
+    int it = warp_g < n_static ? warp_g : n_items;
+    if (it >= n_items && n_items > 0) it = next_index(n_static);
+    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;
+    if (it < n_items) { r0 = __ldg(p.items + 2 * (size_t)it); r1 = __ldg(p.items + 2 * (size_t)it + 1); }
+    while (it < n_items) {
+        const int nit = next_index(it);
+        int4 n0 = make_int4(0, 0, 0, 0), n1 = n0;
+        if (nit < n_items) { n0 = __ldg(p.items + 2 * (size_t)nit); n1 = __ldg(p.items + 2 * (size_t)nit + 1); }
+        const NhwcItem a = nhwc_decode(r0, r1);
+        const int C = p.C[a.s];
+        const int ncell = a.wh * a.ww;                 // 0: no sample inside the map (Q5) -> all-zero vector
+        float* __restrict__ out0 = p.pooled + (size_t)a.out * p.pooled_ld;
+        float* __restrict__ out1 = p.pooled_user ? p.pooled_user + (size_t)a.out * p.pooled_user_ld : nullptr;
+        if ((C % 4 == 0) && (((uintptr_t)a.img & 15) == 0)) {
+            const int c = a.c_lo + l * 4;
+            const bool mine = c < C;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q0 = 0; q0 < ncell; q0 += 32) {
+                float wq;
+                int oq;
+                nhwc_cells(p, a, q0, wq, oq);
+                const int left = min(32, ncell - q0);
+                float4 v[8];
+                float w8[8];
+                nhwc_issue(a.img + c, mine, left, wq, oq, v, w8);
+                nhwc_consume(left, v, w8, acc);
             }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {        // the four cell groups
+                acc.x += __shfl_xor_sync(kFull, acc.x, o); acc.y += __shfl_xor_sync(kFull, acc.y, o);
+                acc.z += __shfl_xor_sync(kFull, acc.z, o); acc.w += __shfl_xor_sync(kFull, acc.w, o);
+            }
+            if (mine && g == 0) {
+                const float4 val = make_float4(__fdiv_rn(acc.x, a.count), __fdiv_rn(acc.y, a.count), __fdiv_rn(acc.z, a.count),
+                                               __fdiv_rn(acc.w, a.count));    // average over the sample grid (roi_align.py:192-196)
+                *reinterpret_cast<float4*>(out0 + c) = val;
+                if (out1) { out1[c] = val.x; out1[c + 1] = val.y; out1[c + 2] = val.z; out1[c + 3] = val.w; }
+            }
+        } else {
+            pool_nhwc_scalar(p, a, out0, out1);
         }
         r0 = n0; r1 = n1; it = nit;
     }
@@ -1089,7 +1176,7 @@ static WorkspaceLayout layout_of(int n, int nc, const int32_t* map_chw) {
     L.ext_y = (hmax + 3) & ~3;
     L.wstride = L.ext_y + ((wmax + 3) & ~3) + 4;
     L.pooled_ld = (cmax + 3) & ~3;
-    L.max_ns = (cmax + kSliceChannels - 1) / kSliceChannels;
+    L.max_ns = (cmax + kSliceNhwc - 1) / kSliceNhwc;  // the finer of the two slicings (kSliceNhwc <= kSliceChannels)
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;
     const size_t nn = (size_t)(n > 0 ? n : 1);
@@ -1177,16 +1264,16 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
             g_sm_count = 148;
     }
     if (g_items_per_sm == 0 &&
-        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_items_per_sm, items_kernel<false>, kThreads, 0) != cudaSuccess || g_items_per_sm <= 0))
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_items_per_sm, items_kernel, kThreads, 0) != cudaSuccess || g_items_per_sm <= 0))
         g_items_per_sm = OODB200_FMAP_MIN_BLOCKS;
     if (g_items_per_sm_nhwc == 0 &&
-        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_items_per_sm_nhwc, items_kernel<true>, kThreads, 0) != cudaSuccess || g_items_per_sm_nhwc <= 0))
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_items_per_sm_nhwc, items_nhwc_kernel, kThreads, 0) != cudaSuccess || g_items_per_sm_nhwc <= 0))
         g_items_per_sm_nhwc = OODB200_FMAP_MIN_BLOCKS;
     long long max_items = (long long)p.n * L.max_ns;
     long long grid = (long long)g_sm_count * (p.nhwc ? g_items_per_sm_nhwc : g_items_per_sm);   // persistent: every resident warp pulls from the queue
     if (grid * kWarps > max_items) grid = (max_items + kWarps - 1) / kWarps;
-    if (p.nhwc) items_kernel<true><<<(int)grid, kThreads, 0, st>>>(p);
-    else items_kernel<false><<<(int)grid, kThreads, 0, st>>>(p);
+    if (p.nhwc) items_nhwc_kernel<<<(int)grid, kThreads, 0, st>>>(p);
+    else items_kernel<<<(int)grid, kThreads, 0, st>>>(p);
     rc = check_launch(what);
     if (rc) return rc;
     if (p.cent) {
