@@ -284,7 +284,7 @@ class OODMethod(ABC):
             raise NotImplementedError("assign ood_utils.compute_metrics (the evaluation harness' metric function) first; "
                                       "metric computation is outside the GPU hot path (INTEGRATION.md)")
         if self.enhanced_unk_localization:
-            raise NotImplementedError("enhanced unknown localisation (EUL) is outside the rebuilt hot path (SURVEY.md §8f)")
+            raise NotImplementedError("enhanced unknown localisation: only the proposal ranking (rank_unknown_proposals, SURVEY.md §8f rank 4) is rebuilt; the saliency / region-proposal stage around it is CPU image processing outside the hot path")
         logger.warning(f"Using a confidence threshold of {self.min_conf_threshold_test} for tests")
         assert hasattr(dataloader.dataset, "number_of_classes"), \
             "The dataset does not have the attribute number_of_classes to know the number of classes known in the dataset"
@@ -370,7 +370,7 @@ class OODMethod(ABC):
         return thresholds
 
     def compute_extra_possible_unkwnown_bboxes_and_decision(self, *args, **kwargs):
-        raise NotImplementedError("enhanced unknown localisation (EUL) is outside the rebuilt hot path (SURVEY.md §8f)")
+        raise NotImplementedError("enhanced unknown localisation: only the proposal ranking (rank_unknown_proposals, SURVEY.md §8f rank 4) is rebuilt; the saliency / region-proposal stage around it is CPU image processing outside the hot path")
 
 
 # ------------------------------------------------------------------------------------------------ logits family
@@ -701,6 +701,52 @@ class DistanceMethod(OODMethod):
             table.thr = torch.from_numpy(thr).to(device)
             self._packed = (key, table, thr)
         return table
+
+    # -- enhanced unknown localisation: ranking of the unknown proposals (ood_utils.py:1031-1084)
+    def rank_unknown_proposals(self, feature_map, proposals, selected_stride: int, operation: Optional[str] = None):
+        """Rank of every unknown-object proposal of one image: RoIAlign (1x1, spatial_scale 1, aligned=False) of the
+        proposals on the (padded) feature map of the selected stride, the transformed vector's distance to the nearest
+        centroid of EVERY known class that has clusters on that stride, folded over the classes with
+        CUSTOM_HYP.unk.rank.RANK_BOXES_OPERATION ('mean' / 'max' / 'sum' / 'min' (x100, or as is with the index of the
+        closest class when USE_OOD_THR_TO_REMOVE_PROPS) / 'geometric_mean' / 'entropy').
+        feature_map: [C, H, W] tensor; proposals: [P, 4] xyxy in feature-map cells.  Pooling (K1) and the
+        [classes, P] distance matrix (K2, one launch, one segment per class) run on the GPU; the fold over <= NC values
+        per proposal is the reference's own numpy / scipy expression.
+        -> ranks [P] (and, for 'min' with USE_OOD_THR_TO_REMOVE_PROPS, the index of the closest class among the classes
+        with clusters, as `(ranks, idx_of_closest_cluster)`)."""
+        if self._clusters is None:
+            raise RuntimeError(f"{self.name}: `.clusters` is not set (fit or load the clusters first)")
+        op = operation or CUSTOM_HYP.unk.rank.RANK_BOXES_OPERATION
+        dev = ops.default_device()
+        fm = feature_map if isinstance(feature_map, torch.Tensor) else torch.as_tensor(np.asarray(feature_map))
+        assert fm.dim() == 3, "feature_map must be [C, H, W]"
+        boxes = torch.as_tensor(_np(proposals), dtype=torch.float32).reshape(-1, 4)
+        n_prop, dim = int(boxes.shape[0]), int(fm.shape[0])
+        if n_prop == 0:
+            return np.zeros(0, dtype=np.float32)
+        s = int(selected_stride)
+        dummy = torch.zeros((1, 1, 1), dtype=torch.float32, device=dev)
+        maps = [dummy, dummy, dummy]
+        maps[s] = fm
+        # spatial_scale = 1: the "image" is the feature map itself
+        batch = ops.make_batch([maps], [boxes], [torch.full((n_prop,), float(s))], [torch.zeros(n_prop)], int(fm.shape[2]), dev)
+        pooled = ops.roi_pool(batch)[:, :dim].contiguous()
+        classes = [c for c, per_cls in enumerate(self._clusters) if s < len(per_cls) and len(per_cls[s]) > 0]
+        if not classes:
+            raise ValueError(f"no class has clusters on stride {s}")
+        # one segment per class over the same vectors; the transformation is applied per class (ood_utils.py:1047-1052)
+        xr = self._transform_device(pooled.repeat(len(classes), 1), classes, [n_prop] * len(classes), s).contiguous()
+        d_eff = int(xr.shape[1])
+        cents = [np.ascontiguousarray(_np(self._clusters[c][s]), dtype=np.float32).reshape(-1, d_eff) for c in classes]
+        ks = [int(c.shape[0]) for c in cents]
+        cent = np.concatenate(cents)
+        row_off = np.concatenate([[0], np.cumsum(ks)])[:-1].tolist()
+        cent_d = ops.h2d(cent, dev)
+        unit_d = ops.h2d(ops._unit_rows(cent), dev) if self.metric == 'cosine' else None
+        seg_off = [i * n_prop for i in range(len(classes) + 1)]
+        dist, _ = ops.vec_score(xr, seg_off, cent_d, unit_d, row_off, ks, 1 << self._metric_slot, normalize=False)
+        d = dist[self._metric_slot].reshape(len(classes), n_prop).cpu().numpy()
+        return fold_proposal_distances(d, op, CUSTOM_HYP.unk.rank.USE_OOD_THR_TO_REMOVE_PROPS)
 
     # -- scoring primitives with the reference's numpy-in / numpy-out contracts
     def compute_scores(self, activations, cluster) -> np.ndarray:
@@ -1171,10 +1217,10 @@ class DistanceMethod(OODMethod):
         return scores
 
     def compute_scores_from_activations_for_unk_proposals(self, activations, logger):
-        raise NotImplementedError("enhanced unknown localisation (EUL) is outside the rebuilt hot path (SURVEY.md §8f)")
+        raise NotImplementedError("enhanced unknown localisation: only the proposal ranking (rank_unknown_proposals, SURVEY.md §8f rank 4) is rebuilt; the saliency / region-proposal stage around it is CPU image processing outside the hot path")
 
     def generate_unk_prop_thr(self, scores, tpr) -> None:
-        raise NotImplementedError("enhanced unknown localisation (EUL) is outside the rebuilt hot path (SURVEY.md §8f)")
+        raise NotImplementedError("enhanced unknown localisation: only the proposal ranking (rank_unknown_proposals, SURVEY.md §8f rank 4) is rebuilt; the saliency / region-proposal stage around it is CPU image processing outside the hot path")
 
 
 class _PairwiseDistanceClustersPerClassPerStride(DistanceMethod):
@@ -1508,6 +1554,28 @@ class TripleFusionMethod(_FusionBase):
         t = lambda a: torch.from_numpy(a).to(dev)
         out = ops.fuse_decisions(t(d1), t(d2), 'majority_voting', t(d3))
         return _split_lists(out.cpu().numpy(), counts, int)
+
+
+def fold_proposal_distances(distances_per_proposal: np.ndarray, operation: str, use_ood_thr_to_remove_props: bool = False):
+    """[classes, P] distances -> [P] ranks, the reference's expressions (ood_utils.py:1057-1084)."""
+    d = np.asarray(distances_per_proposal)
+    if operation == 'mean':
+        return d.mean(axis=0)
+    if operation == 'max':
+        return d.max(axis=0)
+    if operation == 'sum':
+        return d.sum(axis=0)
+    if operation == 'min':
+        if use_ood_thr_to_remove_props:
+            return d.min(axis=0), np.argsort(d, axis=0)[0]
+        return d.min(axis=0) * 100                       # "to compensate the low values"
+    if operation == 'geometric_mean':
+        from scipy.stats import gmean
+        return gmean(d, axis=0)
+    if operation == 'entropy':
+        from scipy.stats import entropy
+        return entropy(d / d.sum(axis=0), axis=0)
+    raise NotImplementedError("This operation is not implemented yet")
 
 
 # ------------------------------------------------------------------------------------------------ fused multi-method pass

@@ -28,5 +28,7 @@ Modules
     decide        decide-on-results loops (incl. quirks Q1, Q2, Q4), fusion rules
     fit           cluster generation ('one', 'all', KMeans_<k>), scores, thresholds
     kmeans        sklearn KMeans (k-means++ init + Lloyd) restated in numpy
+    silhouette    sklearn silhouette / Calinski-Harabasz scores and the reference's search of the number of clusters
+    eul           ranking of unknown-object proposals against the clusters of every class
     cpu_path      loop-for-loop port of the reference's per-box CPU path (timing)
 """

@@ -397,13 +397,59 @@ def golden_ksearch(ref):
     np.savez_compressed(os.path.join(OUT, "golden_ksearch.npz"), **store)
 
 
+def golden_eul_rank(ref):
+    """Ranking of unknown proposals: the statements of ood_utils.py:1031-1084 executed with the reference's own objects
+    (torchvision roi_align on the padded map with spatial_scale 1, `activations_transformation`, `compute_distance` of the
+    reference's method classes, the numpy / scipy fold).  The block sits inside a 500-line method that needs the whole
+    EUL pipeline (saliency maps, skimage region proposals), so it cannot be called in isolation."""
+    import torchvision.ops as t_ops
+    from scipy.stats import entropy, gmean
+    ou = ref.ood_utils
+    rng = np.random.default_rng(77)
+    store = {}
+    C, H, W, nc, P = 24, 22, 26, 6, 9
+    fm = np.abs(rng.standard_normal((C, H, W))).astype(F32)
+    x1, y1 = rng.uniform(-1, W - 3, P), rng.uniform(-1, H - 3, P)
+    props = np.stack([x1, y1, x1 + rng.uniform(0.3, 9, P), y1 + rng.uniform(0.3, 9, P)], 1).astype(F32)
+    clusters = [[np.empty(0)] * 3 for _ in range(nc)]
+    for c in range(nc):
+        if c != 2:                                           # class 2 has no clusters on this stride
+            k = int(rng.integers(1, 5))
+            v = np.abs(rng.standard_normal((k, C))).astype(F32)
+            clusters[c][1] = (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(F32)
+    store["fm"], store["props"], store["stride"], store["nc"] = fm, props, np.int32(1), np.int32(nc)
+    _pack_nested("clusters", clusters, store)
+    feats = t_ops.roi_align(input=torch.from_numpy(fm).unsqueeze(0), boxes=[torch.from_numpy(props).float()],
+                            output_size=(1, 1), spatial_scale=1.0, aligned=False)
+    for tag, klass in (("l1", ou.L1DistanceOneClusterPerStride), ("l2", ou.L2DistanceOneClusterPerStride),
+                       ("cos", ou.CosineDistanceOneClusterPerStride)):
+        m = klass(**ref_shim.DIST_KW)
+        m.clusters = clusters
+        dpp = []
+        for idx_cls, cluster in enumerate(m.clusters):
+            if len(cluster[1]) > 0:
+                dpp.append(m.compute_distance(cluster[1], m.activations_transformation(feats, cls_idx=idx_cls, stride_idx=1)))
+        dpp = np.array(dpp)
+        store[f"{tag}_matrix"] = dpp.astype(np.float64)
+        store[f"{tag}_mean"], store[f"{tag}_max"], store[f"{tag}_sum"] = dpp.mean(axis=0), dpp.max(axis=0), dpp.sum(axis=0)
+        store[f"{tag}_min"] = dpp.min(axis=0) * 100
+        store[f"{tag}_minthr"], store[f"{tag}_closest"] = dpp.min(axis=0), np.argsort(dpp, axis=0)[0]
+        store[f"{tag}_geometric_mean"] = gmean(dpp, axis=0)
+        store[f"{tag}_entropy"] = entropy(dpp / dpp.sum(axis=0), axis=0)
+    np.savez_compressed(os.path.join(OUT, "golden_eul_rank.npz"), **store)
+    print("golden_eul_rank", store["l2_matrix"].shape, np.round(store["l2_entropy"], 4).tolist())
+
+
 def main():
     ref = ref_shim.load()
+    if "--only-eul" in sys.argv:
+        return golden_eul_rank(ref)
     if "--only-matching" in sys.argv:
         return golden_matching(ref)
     if "--only-ksearch" in sys.argv:
         return golden_ksearch(ref)
     golden_ksearch(ref)
+    golden_eul_rank(ref)
     golden_matching(ref)
     golden_roi_edges(ref)
     golden_quirks(ref)

@@ -377,3 +377,33 @@ def test_kmeans_fit_through_the_class(ou, golden):
         lab = cluster_utils.find_optimal_number_of_clusters_one_class_one_stride_and_return_labels(
             g[f"{tag}_x"], f"KMeans_{int(g[f'{tag}_k'])}", "l2", "silhouette", "", LOG)
         assert np.array_equal(lab, g[f"{tag}_labels"]), tag
+
+
+def test_unknown_proposal_ranking(ou, golden):
+    """DistanceMethod.rank_unknown_proposals == ood_utils.py:1031-1084 run with the reference's objects: every fold of the
+    [classes, proposals] distance matrix within 1e-5, the closest class exact; channels-last map gives the same ranks."""
+    from ood_in_object_detection_b200.custom_hyperparams import CUSTOM_HYP
+    g = golden("golden_eul_rank.npz")
+    nc, s = int(g["nc"]), int(g["stride"])
+    clusters = unpack_nested(g, "clusters", nc)
+    fm = torch.from_numpy(g["fm"])
+    for tag, klass in _classes(ou):
+        m = klass(**DIST_KW)
+        m.clusters = clusters
+        for op in ("mean", "max", "sum", "min", "geometric_mean", "entropy"):
+            got = m.rank_unknown_proposals(fm, g["props"], s, operation=op)
+            np.testing.assert_allclose(got, g[f"{tag}_{op}"], rtol=1e-5, atol=1e-6 if tag == "cos" else 0, err_msg=f"{tag} {op}")
+        assert CUSTOM_HYP.unk.rank.RANK_BOXES_OPERATION == "entropy"
+        np.testing.assert_allclose(m.rank_unknown_proposals(fm.cuda(), torch.from_numpy(g["props"]), s), g[f"{tag}_entropy"],
+                                   rtol=1e-5, atol=1e-6)
+        CUSTOM_HYP.unk.rank.USE_OOD_THR_TO_REMOVE_PROPS = True
+        try:
+            mn, closest = m.rank_unknown_proposals(fm, g["props"], s, operation="min")
+        finally:
+            CUSTOM_HYP.unk.rank.USE_OOD_THR_TO_REMOVE_PROPS = False
+        assert np.array_equal(closest, g[f"{tag}_closest"])
+        np.testing.assert_allclose(mn, g[f"{tag}_minthr"], rtol=1e-5, atol=1e-6 if tag == "cos" else 0)
+        cl = fm[None].contiguous(memory_format=torch.channels_last)[0]          # same values, [H, W, C] memory
+        np.testing.assert_allclose(m.rank_unknown_proposals(cl, g["props"], s, operation="sum"), g[f"{tag}_sum"],
+                                   rtol=1e-5, atol=1e-6)
+    assert len(m.rank_unknown_proposals(fm, np.zeros((0, 4), np.float32), s)) == 0

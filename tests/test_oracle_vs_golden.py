@@ -230,3 +230,19 @@ def test_silhouette_and_k_search(golden):
         scores, labels = S.k_search(x, metric, perf)
         np.testing.assert_allclose(scores, ref_scores, rtol=2e-6, atol=2e-6)
         assert np.array_equal(labels, ref_labels), tag
+
+
+def test_eul_proposal_ranking(golden):
+    """oracle/eul.py against the distances and folds produced with the reference's own method objects
+    (ood_utils.py:1031-1084; tests/golden/make_golden.py::golden_eul_rank)."""
+    from oracle import eul
+    from tests.helpers import unpack_nested
+    g = golden("golden_eul_rank.npz")
+    clusters = unpack_nested(g, "clusters", int(g["nc"]))
+    for tag, metric in (("l1", "l1"), ("l2", "l2"), ("cos", "cosine")):
+        d = eul.distance_matrix(g["fm"], g["props"], clusters, int(g["stride"]), metric)
+        np.testing.assert_allclose(d, g[f"{tag}_matrix"], rtol=1e-5, atol=5e-7 if metric == "cosine" else 0)
+        for op in ("mean", "max", "sum", "min", "geometric_mean", "entropy"):
+            np.testing.assert_allclose(eul.fold(g[f"{tag}_matrix"], op), g[f"{tag}_{op}"], rtol=1e-6)
+        mn, closest = eul.fold(g[f"{tag}_matrix"], "min", True)
+        assert np.array_equal(closest, g[f"{tag}_closest"]) and np.allclose(mn, g[f"{tag}_minthr"])
