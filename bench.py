@@ -252,6 +252,16 @@ def run_reference(args, wl):
         return
     import torch
     from ood_in_object_detection_b200 import synth
+    # all the host threads the box has: torchrun exports OMP_NUM_THREADS=1 to its workers, which would pin the reference
+    # arm to one thread whenever it is launched the way the N > 1 runs are
+    ncpu = os.cpu_count() or 1
+    if torch.get_num_threads() < ncpu:
+        torch.set_num_threads(ncpu)
+    try:
+        import threadpoolctl
+        _limits = threadpoolctl.threadpool_limits(limits=ncpu)      # BLAS / OpenMP pools of numpy, scipy, sklearn
+    except Exception:                                               # the pools keep their environment defaults
+        _limits = None
     if args.workload == "fit":
         vals = [cpu_fit_baseline() for _ in range(max(args.steps, 1))]
         v = float(np.mean([x["value"] for x in vals]))
@@ -271,7 +281,7 @@ def run_reference(args, wl):
     thr = {m: [[1.0] * 3 for _ in range(wl.nc)] for m in range(3)}
     lthr = np.zeros((5, wl.nc))
     imgs = list(range(n_img))
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 1)):                # imports and thread pools are not part of the metric
         cpu_reference_pass(det, maps, wl, clusters, thr, lthr, imgs[:1])
     tot_n, tot_t = 0, 0.0
     for _ in range(args.steps):
