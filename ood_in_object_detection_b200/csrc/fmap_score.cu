@@ -935,27 +935,45 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_NHWC_BLOCKS) items_nhwc
 // bulk-async copies (one mbarrier), while every warp already loads and normalises its first pooled vector into
 // registers; the K rows are then swept from shared memory (128-bit, conflict-free), 4 rows per reduction round.  A warp's
 // dependent global round trips are: histogram -> list entry -> pooled row (the centroid copy runs beside them).
-// Groups whose tables do not fit the shared-memory budget, or whose slices are not 16-byte aligned, are swept from
-// global memory (finalize) by the same CTAs.
+// Tables larger than the shared-memory budget are staged in chunks of rows (the running best stays in registers); groups
+// whose slices are not 16-byte aligned are swept from global memory (finalize) by the same CTAs.
 constexpr int kUnitBoxes = kWarps;                     // boxes per score CTA: one per warp
 
 __device__ __forceinline__ uint32_t fs_smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar) {   // phase 0; a protocol error traps instead of hanging
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {   // a protocol error traps instead of hanging
     uint32_t ok = 0;
     const long long t0 = clock64();
     while (!ok) {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(fs_smem_u32(bar)), "r"(0u) : "memory");
+                     : "=r"(ok) : "r"(fs_smem_u32(bar)), "r"(parity) : "memory");
         if (!ok && clock64() - t0 > 4000000000LL) __trap();
     }
 }
 
-// One box against the K staged rows.  NJ = float4 per lane (C <= 128 * NJ, only the last one can be partial), MASK = the
+// Rows [kb, kb + rc) of the group's centroid tables -> shared memory (one elected thread; completes on `bar`).
+template <int MASK>
+__device__ __forceinline__ void stage_rows(const FmapParams& p, int64_t off, int C, int kb, int rc, int RC, float* s_dyn, uint64_t* bar) {
+    constexpr bool L12 = MASK & ((1 << OODB200_METRIC_L1) | (1 << OODB200_METRIC_L2));
+    constexpr bool COS = MASK & (1 << OODB200_METRIC_COS);
+    const uint32_t tab = (uint32_t)((size_t)rc * C * sizeof(float));
+    float* sc = s_dyn;
+    float* su = L12 ? s_dyn + (size_t)RC * C : s_dyn;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem_u32(bar)), "r"(tab * ((L12 ? 1u : 0u) + (COS ? 1u : 0u))) : "memory");
+    if (L12)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fs_smem_u32(sc)),
+                     "l"(p.cent + off + (int64_t)kb * C), "r"(tab), "r"(fs_smem_u32(bar)) : "memory");
+    if (COS)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fs_smem_u32(su)),
+                     "l"(p.cent_unit + off + (int64_t)kb * C), "r"(tab), "r"(fs_smem_u32(bar)) : "memory");
+}
+
+// One box against the K rows of its group, staged RC rows at a time (one chunk when the tables fit the shared-memory
+// budget; the running best lives in registers across chunks).  NJ = float4 per lane (C <= 128 * NJ, only the last one can be partial), MASK = the
 // requested metrics: no run-time flag or bound check inside the sweep.
 template <int NJ, int MASK>
-__device__ __forceinline__ void score_box_smem(const FmapParams& p, int s, int C, int cls, int K, int out,
-                                               const float* __restrict__ sc, const float* __restrict__ su, uint64_t* bar) {
+__device__ __forceinline__ void score_box_smem(const FmapParams& p, int s, int C, int cls, int K, int out, bool have,
+                                               int64_t off, int RC, float* s_dyn, uint64_t* bar) {
     constexpr bool L1 = MASK & (1 << OODB200_METRIC_L1), L2 = MASK & (1 << OODB200_METRIC_L2);
     constexpr bool COS = MASK & (1 << OODB200_METRIC_COS), L12 = L1 || L2;
     constexpr int NM = (L1 ? 1 : 0) + (L2 ? 1 : 0) + (COS ? 1 : 0);
@@ -963,10 +981,12 @@ __device__ __forceinline__ void score_box_smem(const FmapParams& p, int s, int C
     const float* __restrict__ row = p.pooled + (size_t)out * p.pooled_ld;
     const bool last_ok = (NJ - 1) * 128 + lane * 4 < C;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* __restrict__ sc = s_dyn;
+    const float* __restrict__ su = L12 ? s_dyn + (size_t)RC * C : s_dyn;
     float4 x[NJ];
 #pragma unroll
     for (int t = 0; t < NJ; ++t)
-        x[t] = (t < NJ - 1 || last_ok) ? __ldcg(reinterpret_cast<const float4*>(row + t * 128 + lane * 4)) : zero;
+        x[t] = (have && (t < NJ - 1 || last_ok)) ? __ldcg(reinterpret_cast<const float4*>(row + t * 128 + lane * 4)) : zero;
     float ss = 0.f;
 #pragma unroll
     for (int t = 0; t < NJ; ++t) {
@@ -992,9 +1012,9 @@ __device__ __forceinline__ void score_box_smem(const FmapParams& p, int s, int C
         n2v = sqrtf(warp_sum(ss));
         if (n2v < 10.f * FLT_EPSILON) n2v = 1.f;
     }
-    mbar_wait_bounded(bar);                            // the centroid tables have landed
     Best b = {{FLT_MAX, FLT_MAX, FLT_MAX}, {-1, -1, -1}};
-    auto batch = [&](int k0, int nr) {                 // rows k0 .. k0 + nr - 1 (nr <= 4): 4 x NM independent reductions
+    int kb = 0;                                        // first row of the staged chunk
+    auto batch = [&](int k0, int nr) {                 // staged rows k0 .. k0 + nr - 1 (nr <= 4): 4 x NM independent reductions
         float acc[4][NM];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -1030,7 +1050,7 @@ __device__ __forceinline__ void score_box_smem(const FmapParams& p, int s, int C
 #pragma unroll
         for (int r = 0; r < 4; ++r) {                  // rows in increasing order, strict '<': first minimum
             if (r < nr) {
-                const int k = k0 + r;
+                const int k = kb + k0 + r;
                 int i = 0;
                 if (L1) { const float v = acc[r][i++]; if (v < b.d[0]) { b.d[0] = v; b.a[0] = k; } }
                 if (L2) { const float v = sqrtf(fmaxf(acc[r][i++], 0.f)); if (v < b.d[1]) { b.d[1] = v; b.a[1] = k; } }
@@ -1041,10 +1061,22 @@ __device__ __forceinline__ void score_box_smem(const FmapParams& p, int s, int C
             }
         }
     };
-    int k0 = 0;
-    for (; k0 + 4 <= K; k0 += 4) batch(k0, 4);
-    if (k0 < K) batch(k0, K - k0);
-    write_result(p, s, cls, true, K, out, b);         // lane m reports metric m (all lanes hold the same result)
+    uint32_t phase = 0;
+    for (; kb < K; kb += RC) {
+        const int rc = min(RC, K - kb);
+        if (kb > 0) {
+            __syncthreads();                           // every warp is done with the previous chunk
+            if (threadIdx.x == 0) stage_rows<MASK>(p, off, C, kb, rc, RC, s_dyn, bar);
+        }
+        mbar_wait_bounded(bar, phase);                 // the chunk has landed
+        phase ^= 1u;
+        if (have) {
+            int k0 = 0;
+            for (; k0 + 4 <= rc; k0 += 4) batch(k0, 4);
+            if (k0 < rc) batch(k0, rc - k0);
+        }
+    }
+    if (have) write_result(p, s, cls, true, K, out, b);   // lane m reports metric m (all lanes hold the same result)
 }
 
 // Groups that cannot be staged: sweep from global memory, warp-private vector in shared memory (kept out of line: the
@@ -1111,38 +1143,25 @@ __global__ void __launch_bounds__(kThreads, 3) score_kernel(const __grid_constan
     const int64_t off = K > 0 ? p.cent_off[key] : 0;
     constexpr bool L12 = MASK & ((1 << OODB200_METRIC_L1) | (1 << OODB200_METRIC_L2));
     constexpr bool COS = MASK & (1 << OODB200_METRIC_COS);
-    const size_t tab = (size_t)K * C * sizeof(float);
-    const size_t need = tab * ((L12 ? 1 : 0) + (COS ? 1 : 0));
+    const int ntab = (L12 ? 1 : 0) + (COS ? 1 : 0);
+    const int rows_fit = (int)((size_t)smem_bytes / ((size_t)C * sizeof(float) * ntab));
+    const int RC = min(K, min(rows_fit, (int)((1u << 19) / ((size_t)C * sizeof(float)))));   // rows per staged chunk
     const int nj = (C + 127) >> 7;
-    const bool staged = K > 0 && C % 4 == 0 && nj <= 8 && need <= (size_t)smem_bytes && tab < (1u << 20) &&
+    const bool staged = K > 0 && C % 4 == 0 && nj <= 8 && RC >= 1 &&
                         off % 4 == 0 && ((((uintptr_t)p.cent) | ((uintptr_t)p.cent_unit)) & 15) == 0;
     if (!staged) {
         if (have) score_unit_global(p, s, cls, out, s_dyn + (size_t)warp * p.pooled_ld);
         return;
     }
-    float* sc = s_dyn;
-    float* su = L12 ? s_dyn + (size_t)K * C : s_dyn;
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem_u32(&s_bar)), "r"((uint32_t)need) : "memory");
-        if (L12)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fs_smem_u32(sc)),
-                         "l"(p.cent + off), "r"((uint32_t)tab), "r"(fs_smem_u32(&s_bar)) : "memory");
-        if (COS)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fs_smem_u32(su)),
-                         "l"(p.cent_unit + off), "r"((uint32_t)tab), "r"(fs_smem_u32(&s_bar)) : "memory");
-    }
-    if (!have) {                                       // a warp without a box must not leave while the copy is in flight
-        mbar_wait_bounded(&s_bar);
-        return;
-    }
-    switch (nj) {
-        case 1: score_box_smem<1, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
-        case 2: score_box_smem<2, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
-        case 3: score_box_smem<3, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
-        case 4: score_box_smem<4, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
-        case 5: score_box_smem<5, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
-        case 6: score_box_smem<6, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
-        default: score_box_smem<8, MASK>(p, s, C, cls, K, out, sc, su, &s_bar); break;
+    if (threadIdx.x == 0) stage_rows<MASK>(p, off, C, 0, RC, RC, s_dyn, &s_bar);
+    switch (nj) {                                      // block-uniform: every warp runs the same chunk loop (barriers inside)
+        case 1: score_box_smem<1, MASK>(p, s, C, cls, K, out, have, off, RC, s_dyn, &s_bar); break;
+        case 2: score_box_smem<2, MASK>(p, s, C, cls, K, out, have, off, RC, s_dyn, &s_bar); break;
+        case 3: score_box_smem<3, MASK>(p, s, C, cls, K, out, have, off, RC, s_dyn, &s_bar); break;
+        case 4: score_box_smem<4, MASK>(p, s, C, cls, K, out, have, off, RC, s_dyn, &s_bar); break;
+        case 5: score_box_smem<5, MASK>(p, s, C, cls, K, out, have, off, RC, s_dyn, &s_bar); break;
+        case 6: score_box_smem<6, MASK>(p, s, C, cls, K, out, have, off, RC, s_dyn, &s_bar); break;
+        default: score_box_smem<8, MASK>(p, s, C, cls, K, out, have, off, RC, s_dyn, &s_bar); break;
     }
 }
 

@@ -166,7 +166,7 @@ def test_logits_and_fusion(ops, golden):
     assert np.array_equal(ops.fuse_scores(f32(f["s1"]), f32(f["s2"])).cpu().numpy(), f["fuse_score"])
 
 
-@pytest.mark.parametrize("cfg,batch,lam,k", [("C2", 4, 50, 10), ("C5", 1, 120, 16)])
+@pytest.mark.parametrize("cfg,batch,lam,k", [("C2", 4, 50, 10), ("C5", 1, 120, 16), ("C5", 1, 60, 64)])
 def test_fused_scoring_vs_oracle_at_config_shapes(ops, cfg, batch, lam, k):
     """Real YOLOv8s / YOLOv8x map shapes (incl. 160x160 maps and windows > 256 cells), random centroids."""
     from oracle import decide
