@@ -55,7 +55,13 @@ constexpr int kMaxSlices = 255;
 #endif
 constexpr int kSliceChannels = OODB200_FMAP_SLICE;   // channels per work item (multiple of 32)
 constexpr int kCU = OODB200_FMAP_CU;
-constexpr int kSliceNhwc = 32;                       // channels-last: a slice of one cell = one 128-byte line = 8 lanes x 128 bits
+#ifndef OODB200_NHWC_SLICE
+#define OODB200_NHWC_SLICE 32
+#endif
+constexpr int kSliceNhwc = OODB200_NHWC_SLICE;       // channels-last: channels per work item (32 = one 128-byte line per cell)
+constexpr int kNhwcLanes = kSliceNhwc / 4;           // lanes per cell (128 bits each)
+constexpr int kNhwcCells = 32 / kNhwcLanes;          // cells per warp request
+static_assert(kSliceNhwc == 32 || kSliceNhwc == 64 || kSliceNhwc == 128, "channels-last slice: 32, 64 or 128 channels");
 
 struct FmapParams {
     const float* const* map_ptrs;
@@ -739,26 +745,27 @@ __device__ __forceinline__ void nhwc_cells(const FmapParams& p, const NhwcItem& 
     }
 }
 
-// 32 cells: 8 requests of 4 cells (lane group g takes cell 4u + g), rounds beyond the window cost nothing
-__device__ __forceinline__ void nhwc_issue(const float* __restrict__ src, bool mine, int left, float wq, int oq,
+// 8 requests of kNhwcCells cells starting at cell `first` of the 32 built by the lanes (lane group g takes cell
+// first + kNhwcCells * u + g); rounds beyond the window cost nothing
+__device__ __forceinline__ void nhwc_issue(const float* __restrict__ src, bool mine, int first, int left, float wq, int oq,
                                            float4 (&v)[8], float (&w8)[8]) {
-    const int g = (threadIdx.x & 31) >> 3;
+    const int g = (threadIdx.x & 31) / kNhwcLanes;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         w8[u] = 0.f;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (4 * u < left) {                            // warp-uniform
-            const int j = 4 * u + g;
+        if (first + kNhwcCells * u < left) {           // warp-uniform
+            const int j = (first + kNhwcCells * u + g) & 31;
             const int off = __shfl_sync(kFull, oq, j);
             w8[u] = __shfl_sync(kFull, wq, j);
-            if (w8[u] != 0.f && mine) v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)off));
+            if (first + kNhwcCells * u + g < left && w8[u] != 0.f && mine) v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)off));
         }
     }
 }
-__device__ __forceinline__ void nhwc_consume(int left, const float4 (&v)[8], const float (&w8)[8], float4& acc) {
+__device__ __forceinline__ void nhwc_consume(int first, int left, const float4 (&v)[8], const float (&w8)[8], float4& acc) {
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-        if (4 * u < left) {
+        if (first + kNhwcCells * u < left) {
             acc.x = fmaf(w8[u], v[u].x, acc.x); acc.y = fmaf(w8[u], v[u].y, acc.y);
             acc.z = fmaf(w8[u], v[u].z, acc.z); acc.w = fmaf(w8[u], v[u].w, acc.w);
         }
@@ -866,7 +873,7 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kerne
 #define OODB200_FMAP_NHWC_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(kThreads, OODB200_FMAP_NHWC_BLOCKS) items_nhwc_kernel(const __grid_constant__ FmapParams p) {
-    const int lane = threadIdx.x & 31, g = lane >> 3, l = lane & 7;
+    const int lane = threadIdx.x & 31, g = lane / kNhwcLanes, l = lane % kNhwcLanes;
     const int n_items = p.counters[0];
     const int warp_g = blockIdx.x * kWarps + (threadIdx.x >> 5), n_warps = gridDim.x * kWarps;
     sort_boxes_by_key(p, warp_g, n_warps);
@@ -906,13 +913,15 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_NHWC_BLOCKS) items_nhwc
                 int oq;
                 nhwc_cells(p, a, q0, wq, oq);
                 const int left = min(32, ncell - q0);
-                float4 v[8];
-                float w8[8];
-                nhwc_issue(a.img + c, mine, left, wq, oq, v, w8);
-                nhwc_consume(left, v, w8, acc);
+                for (int first = 0; first < left; first += 8 * kNhwcCells) {
+                    float4 v[8];
+                    float w8[8];
+                    nhwc_issue(a.img + c, mine, first, left, wq, oq, v, w8);
+                    nhwc_consume(first, left, v, w8, acc);
+                }
             }
 #pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {        // the four cell groups
+            for (int o = kNhwcLanes; o <= 16; o <<= 1) {   // the cell groups
                 acc.x += __shfl_xor_sync(kFull, acc.x, o); acc.y += __shfl_xor_sync(kFull, acc.y, o);
                 acc.z += __shfl_xor_sync(kFull, acc.z, o); acc.w += __shfl_xor_sync(kFull, acc.w, o);
             }
@@ -1195,7 +1204,8 @@ static WorkspaceLayout layout_of(int n, int nc, const int32_t* map_chw) {
     L.ext_y = (hmax + 3) & ~3;
     L.wstride = L.ext_y + ((wmax + 3) & ~3) + 4;
     L.pooled_ld = (cmax + 3) & ~3;
-    L.max_ns = (cmax + kSliceNhwc - 1) / kSliceNhwc;  // the finer of the two slicings (kSliceNhwc <= kSliceChannels)
+    constexpr int kFine = kSliceNhwc < kSliceChannels ? kSliceNhwc : kSliceChannels;   // the finer of the two slicings
+    L.max_ns = (cmax + kFine - 1) / kFine;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;
     const size_t nn = (size_t)(n > 0 ? n : 1);
