@@ -59,23 +59,47 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe: the nvidia-smi query, read through
+    NVML in-process when pynvml is there)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
 
+    def _nvml(self):
+        """In-process NVML handle (no nvidia-smi process per sample: starting one every 100 ms perturbs the host-side
+        legs of the measurement); None when pynvml is unavailable."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            return None
+
     def _run(self):
+        nv = self._nvml()
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if nv is not None:
+                    pynvml, h = nv
+                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    try:
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    flag = lambda bit: "Active" if r & bit else "Not Active"
+                    # NVML bit masks: sw power cap 0x4, hw slowdown 0x8, sw thermal 0x20, hw thermal 0x40
+                    self.rows.append([str(sm), str(mx), flag(0x8), flag(0x40), flag(0x20), flag(0x4)])
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05 if nv is not None else 0.1)
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)

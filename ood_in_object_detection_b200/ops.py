@@ -35,21 +35,59 @@ def default_device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+class _PinnedRing:
+    """Reusable pinned staging buffers, one ring per size class.  torch's caching pinned allocator hands a block out again
+    only after the copy that read it has completed; a caller that queues several batches without synchronising would get
+    a FRESH cudaHostAlloc (~0.5 ms) for every small upload.  A slot is reused after its own copy event has completed
+    (waited on only if the ring has wrapped around while that copy is still in flight)."""
+    SLOTS = 32
+
+    def __init__(self):
+        self.rings = {}
+
+    def stage(self, t: torch.Tensor, device) -> torch.Tensor:
+        nbytes = max(int(t.numel()) * t.element_size(), 1)
+        size = 1 << max(nbytes - 1, 255).bit_length()
+        ring = self.rings.get(size)
+        if ring is None:
+            ring = self.rings[size] = {"next": 0, "slots": []}
+        if len(ring["slots"]) < self.SLOTS:
+            ring["slots"].append([torch.empty(size, dtype=torch.uint8, pin_memory=True), None])
+            slot = ring["slots"][-1]
+        else:
+            slot = ring["slots"][ring["next"]]
+            ring["next"] = (ring["next"] + 1) % self.SLOTS
+            if slot[1] is not None:
+                slot[1].synchronize()
+        stage = slot[0][:nbytes].view(t.dtype).reshape(t.shape)
+        stage.copy_(t)
+        out = torch.empty(t.shape, dtype=t.dtype, device=device)
+        out.copy_(stage, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        slot[1] = ev
+        return out
+
+
+_pinned = _PinnedRing()
+_STAGE_MAX_BYTES = 8 << 20          # larger host tensors are pinned (or not) by their owner
+
+
 def h2d(t, device, dtype=None) -> torch.Tensor:
     """Host array / tensor -> device through PINNED staging.  A copy from pageable memory makes the host wait for
-    everything queued on the stream before it (the 100s of MB of feature maps of the same batch): staged through torch's
-    caching pinned allocator the call returns at once and the host keeps preparing the next launch under that copy."""
+    everything queued on the stream before it (the 100s of MB of feature maps of the same batch): staged through a ring
+    of reusable pinned buffers the call returns at once and the host keeps preparing the next launch under that copy."""
     if not isinstance(t, torch.Tensor):
         t = torch.as_tensor(np.asarray(t))
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     if t.is_cuda:
         return t.to(device).contiguous()
-    if not t.is_pinned() or not t.is_contiguous():
-        stage = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        stage.copy_(t)
-        t = stage
-    return t.to(device, non_blocking=True)
+    if t.is_pinned() and t.is_contiguous():
+        return t.to(device, non_blocking=True)
+    if t.numel() * t.element_size() <= _STAGE_MAX_BYTES and t.numel() > 0:
+        return _pinned.stage(t.contiguous(), device)
+    return t.contiguous().to(device, non_blocking=True)
 
 
 def _dev(t, device, dtype=None) -> torch.Tensor:
