@@ -173,7 +173,10 @@ __device__ __forceinline__ float axis_weight(float start, float size, int grid, 
 //  all warps of the cluster, one box per warp at a time: ROI geometry (predict.py:64-70 -> roi_align, aligned=False), the
 //  separable weights and the box's self-contained item records.  The first box's inputs are requested before the plan
 //  finishes.
-constexpr int kPgThreads = 1024, kPgWarps = kPgThreads / 32, kPgCap = 1024;
+#ifndef OODB200_PG_THREADS
+#define OODB200_PG_THREADS 1024
+#endif
+constexpr int kPgThreads = OODB200_PG_THREADS, kPgWarps = kPgThreads / 32, kPgCap = 1024;
 
 struct BoxGeo {
     int ylo, xa, wh, nxc;
@@ -1269,6 +1272,9 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     {
         int G = 1;                                                 // CTAs per image: one warp per box in one round if possible
         while (G < 8 && (long long)G * kPgWarps * p.n_img < p.n) G *= 2;
+        static int g_force = -1;                                   // OODB200_PLAN_CLUSTER: tuning override (1, 2, 4 or 8)
+        if (g_force < 0) { const char* env = getenv("OODB200_PLAN_CLUSTER"); g_force = env ? atoi(env) : 0; }
+        if (g_force == 1 || g_force == 2 || g_force == 4 || g_force == 8) G = g_force;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(p.n_img * G), 1, 1);
         cfg.blockDim = dim3(kPgThreads, 1, 1);
