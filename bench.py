@@ -580,7 +580,9 @@ def run_ours(args, wl):
     if args.fit_n != 0:
         del h_maps, res_f, res_l
         torch.cuda.empty_cache()
-        fit = run_fit(device, world, rank, args.fit_n or 2_000_000, 2, 1)
+        # default size: 2 M vectors, and at least one 16 384-row super-block of every segment per rank (the fit shards whole
+        # super-blocks: with fewer of them than ranks some ranks would own nothing)
+        fit = run_fit(device, world, rank, args.fit_n or max(2_000_000, FIT_CLASSES * 16384 * world), 2, 1)
     clk.stop()
 
     if rank == 0:

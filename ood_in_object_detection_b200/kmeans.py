@@ -31,8 +31,20 @@ SUPER_BLOCKS = 32         # block partials per super-block (unit of ownership fo
 DEVICE_SEEDING_MIN_ROWS = 1 << 16   # seeding="auto": below this the host loop costs nothing and tracks sklearn's BLAS
 
 
+_empty_stub = {}
+
+
 def _ptr(t):
-    return C.c_void_p(0 if t is None else t.data_ptr())
+    """Device address for the C ABI.  An EMPTY tensor (a rank that owns no row of a sharded fit) has a null data pointer,
+    which the entry points reject: it is passed as the address of a small stub buffer that is never dereferenced."""
+    if t is None:
+        return C.c_void_p(0)
+    if t.numel() == 0 and t.is_cuda:
+        stub = _empty_stub.get(t.device)
+        if stub is None:
+            stub = _empty_stub[t.device] = torch.zeros(256, dtype=torch.uint8, device=t.device)
+        return C.c_void_p(stub.data_ptr())
+    return C.c_void_p(t.data_ptr())
 
 
 def _stream():

@@ -25,8 +25,20 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_empty_stub = {}
+
+
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
-    return C.c_void_p(0 if t is None else t.data_ptr())
+    """Device address for the C ABI.  An EMPTY tensor (a rank that owns no row of a sharded fit) has a null data pointer,
+    which the entry points reject: it is passed as the address of a small stub buffer that is never dereferenced."""
+    if t is None:
+        return C.c_void_p(0)
+    if t.numel() == 0 and t.is_cuda:
+        stub = _empty_stub.get(t.device)
+        if stub is None:
+            stub = _empty_stub[t.device] = torch.zeros(256, dtype=torch.uint8, device=t.device)
+        return C.c_void_p(stub.data_ptr())
+    return C.c_void_p(t.data_ptr())
 
 
 def default_device() -> torch.device:
