@@ -159,3 +159,38 @@ def test_device_seeding_control_flow_matches_host_seeding():
     assert a.seconds["seeding"] == "device" and b.seconds["seeding"] == "host"
     assert np.array_equal(a.labels.numpy(), b.labels.numpy())
     assert np.allclose(a.centers.numpy(), b.centers.numpy(), rtol=0, atol=1e-6)
+
+
+SMALL = [9000, 5000, 12]                   # one super-block per segment: with two ranks, rank 0 owns NO row at all
+
+
+def _worker_empty_rank(rank: int, world: int, port: int, outdir: str):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        be = NumpyBackend()
+        segs = [synth.blob_vectors(40 + i, n, DIM, K, 7.0)[0] for i, n in enumerate(SMALL)]
+        shard = kmeans.shard_rows(SMALL, world, rank)
+        local = [s[a:a + n] for s, (a, n) in zip(segs, shard)]
+        x = torch.from_numpy(np.concatenate(local).reshape(-1, DIM))
+        r = kmeans.kmeans_fit_sharded(x, [len(v) for v in local], SMALL, K, world, rank, group=dist.group.WORLD, backend=be)
+        means, counts = kmeans.member_means(x, [len(v) for v in local], r.labels, K, group=dist.group.WORLD, backend=be)
+        np.savez(os.path.join(outdir, f"rank{rank}.npz"), labels=r.labels.numpy(), centers=r.centers.numpy(),
+                 means=means.numpy(), counts=counts.numpy(), rows=np.array(x.shape[0]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_a_rank_without_rows_takes_part_in_the_fit():
+    """Fewer super-blocks per segment than ranks: rank 0 owns nothing, still joins every collective, and the result equals
+    the single-process fit (the case the 8-GPU bench hit with 2 M vectors)."""
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker_empty_rank, args=(2, _free_port(), d), nprocs=2, join=True)
+        out = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(2)]
+    assert int(out[0]["rows"]) == 0 and int(out[1]["rows"]) == sum(SMALL)
+    segs = [synth.blob_vectors(40 + i, n, DIM, K, 7.0)[0] for i, n in enumerate(SMALL)]
+    single = kmeans.kmeans_fit_predict_single(torch.from_numpy(np.concatenate(segs)), SMALL, K, backend=NumpyBackend())
+    assert len(out[0]["labels"]) == 0
+    assert np.array_equal(out[1]["labels"], single.labels.numpy())
+    assert np.array_equal(out[0]["centers"], out[1]["centers"]) and np.array_equal(out[0]["means"], out[1]["means"])
+    np.testing.assert_allclose(out[1]["centers"], single.centers.numpy(), rtol=1e-5, atol=1e-6)
