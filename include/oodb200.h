@@ -45,6 +45,9 @@ extern "C" {
 #define OODB200_LOGIT_SIGMOID 3
 #define OODB200_LOGIT_MAXLOGIT 4
 #define OODB200_N_LOGIT 5
+/* flag bit OR-ed into method_mask: the inputs are post-sigmoid probabilities, the Sigmoid slot returns logits[cls] as is
+ * (`use_values_before_sigmoid=False`, /root/reference/ood_utils.py:1438-1439) */
+#define OODB200_LOGIT_FLAG_POST_SIGMOID 0x100
 
 /* fusion strategies (reference: FusionMethod.fuse_ood_decisions :2906-2940,
  * TripleFusionMethod.fuse_ood_decisions :3282-3301) */
@@ -212,7 +215,8 @@ int oodb200_radix_hist_u32(const float* scores, const int64_t* seg_off, int n_se
  *   x [n_rows, dim] float32, already mean-centred per segment by the caller; cent [n_seg, k, dim]; seg_k [n_seg].
  * kmeans_reduce: out[grp] = sum of in[b] for b in [first[grp], first[grp+1]) in increasing b (fixed order).
  * kmeans_update: centres = sums * (1/count) (sklearn arithmetic), empty clusters keep the old centre and are
- *   counted in n_empty[g]; shift_sq[g] = sum_k ||new_k - old_k||^2.
+ *   counted in n_empty[g] (written, not accumulated); shift_sq[g] = sum_k ||new_k - old_k||^2.  An inactive segment
+ *   copies cent_old to cent_new (shift 0), so the caller may ping-pong two centre buffers.
  * sqdist_cand (k-means++ seeding): out_d[j, r] = min(closest[r], d(x_r, cand[g,j,:])) with d evaluated like
  *   sklearn's float64 expansion cast to float32; pot[g, j] += sum_r out_d[j, r] (float64).
  */
@@ -225,6 +229,18 @@ int oodb200_kmeans_reduce_f32(const float* in, const int32_t* first, int n_group
 int oodb200_kmeans_update_f32(const float* sums, const float* counts, const float* cent_old, const int32_t* seg_k,
                               const int32_t* active, int n_seg, int k, int dim, float* cent_new, float* shift_sq,
                               int32_t* n_empty, void* stream);
+
+/* ---- Lloyd convergence bookkeeping on the device: replaces the per-iteration host decisions of sklearn's
+ * `_kmeans_single_lloyd` (`_kmeans.py:712-740`, behind /root/reference/cluster_utils.py:62-73) so that the host does
+ * not read flags back every iteration.  For every ACTIVE segment: state[0][g] += 1 (iterations), state[3][g] +=
+ * n_empty[g], counts[g] = cnts[g]; no label changed -> state[1][g] = 1 (strict), active[g] = 0; else squared centre
+ * shift <= tol_abs[g] -> state[2][g] = 1 (final E-step needed), active[g] = 0.  any_active[0] = 1 iff a segment is
+ * still active.  n_changed: int32 (n_changed_i) or float32 (n_changed_f, when it rode through the all-reduce buffer).
+ *   shift [n_seg] f32, n_empty [n_seg] i32, tol_abs [n_seg] f64, cnts / counts [n_seg, k] f32, state [4, n_seg] i32
+ */
+int oodb200_kmeans_converge_f32(const int32_t* n_changed_i, const float* n_changed_f, const float* shift,
+                                const int32_t* n_empty, const double* tol_abs, const float* cnts, int n_seg, int k,
+                                int32_t* active, int32_t* state, float* counts, int32_t* any_active, void* stream);
 int oodb200_sqdist_cand_f32(const float* x, int dim, const int64_t* seg_off, int n_seg, int64_t max_seg_rows,
                             const float* cand, int n_cand, const float* closest, float* out_d, double* pot,
                             void* stream);

@@ -7,6 +7,8 @@
 #include "common.cuh"
 
 #include <float.h>
+#include <limits.h>
+#include <stdlib.h>
 
 namespace oodb200 {
 
@@ -126,6 +128,182 @@ __global__ void __launch_bounds__(kVecThreads) vec_score_kernel(const VecParams 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- fast path (one metric)
+// vec_score_fast_kernel<NJ, METRIC>: D % 4 == 0, D <= 128 * NJ, 16-byte aligned rows.  A CTA owns a contiguous range of
+// rows; per segment inside that range the segment's centroid rows (the unit-norm twins for cosine) are staged ONCE into
+// shared memory (chunks of RC rows when K rows do not fit), then every warp takes groups of 4 consecutive rows: the 4
+// rows live in registers (NJ float4 per lane and row), a centroid row is read once from shared memory (128-bit,
+// conflict-free) for all 4 rows, and the 4 x 8 partial sums of 8 centroid rows are reduced with ONE transposing
+// butterfly (31 shuffles for 32 totals instead of 160).  The per-lane accumulation order and the pairing tree of the
+// reduction are those of score_box_smem (csrc/fmap_score.cu): given the same pooled vector, fit-time and decision-time
+// distances are bit-identical (thresholds are compared with distances of the same arithmetic).
+constexpr int kVfRows = 4;                          // rows per warp and group
+constexpr int kVfK = 8;                             // centroid rows per butterfly
+
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+    // afterwards lane j holds the warp-wide total of value index j; the pairing tree is the xor butterfly 16, 8, 4, 2, 1
+    int o = 16;
+#pragma unroll
+    for (int n = 32; n > 1; n >>= 1, o >>= 1) {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+
+template <int NJ, int METRIC>
+__global__ void __launch_bounds__(kVecThreads, NJ <= 2 ? 2 : 1) vec_score_fast_kernel(const VecParams p, int rows_per_cta, int rc_max) {
+    extern __shared__ __align__(16) float s_cent[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.dim;
+    const float* __restrict__ table = METRIC == OODB200_METRIC_COS ? p.cent_unit : p.cent;
+    const int64_t cta0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t cta1 = cta0 + rows_per_cta < p.n_rows ? cta0 + rows_per_cta : p.n_rows;
+    const bool last_ok = (NJ - 1) * 128 + lane * 4 < D;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t r0 = cta0;
+    while (r0 < cta1) {                                              // block-uniform loop over the segments of the range
+        const int g = find_segment(p.seg_off, p.n_seg, r0);
+        const int64_t seg_end = __ldg(p.seg_off + g + 1);
+        const int64_t r1 = seg_end < cta1 ? seg_end : cta1;
+        const int K = p.cent_k[g];
+        const int64_t coff = p.cent_row_off[g] * (int64_t)D;
+        const int RC = K < rc_max ? K : rc_max;
+        for (int kb = 0; kb == 0 || kb < K; kb += (RC > 0 ? RC : 1)) {
+            const int rc = K - kb < RC ? K - kb : RC;
+            const bool first = kb == 0, final = kb + rc >= K;
+            __syncthreads();                                         // previous table no longer read
+            for (int i = threadIdx.x * 4; i < rc * D; i += kVecThreads * 4)
+                *reinterpret_cast<float4*>(s_cent + i) = __ldg(reinterpret_cast<const float4*>(table + coff + (int64_t)kb * D + i));
+            __syncthreads();
+            for (int64_t gr = r0 + (int64_t)warp * kVfRows; gr < r1; gr += (int64_t)kVecWarps * kVfRows) {
+                float4 x[kVfRows][NJ];
+                float n2v[kVfRows];
+#pragma unroll
+                for (int r = 0; r < kVfRows; ++r) {
+                    const int64_t row = gr + r < r1 ? gr + r : r1 - 1;        // short group: repeat the last row, result dropped
+                    const float* __restrict__ xr = p.x + row * p.ld + lane * 4;
+#pragma unroll
+                    for (int t = 0; t < NJ; ++t)
+                        x[r][t] = (t < NJ - 1 || last_ok) ? __ldg(reinterpret_cast<const float4*>(xr + t * 128)) : zero;
+                }
+#pragma unroll
+                for (int r = 0; r < kVfRows; ++r) {
+                    float ss = 0.f;
+#pragma unroll
+                    for (int t = 0; t < NJ; ++t) {
+                        ss = fmaf(x[r][t].x, x[r][t].x, ss); ss = fmaf(x[r][t].y, x[r][t].y, ss);
+                        ss = fmaf(x[r][t].z, x[r][t].z, ss); ss = fmaf(x[r][t].w, x[r][t].w, ss);
+                    }
+                    if (p.normalize) {                               // ood_utils.py:2409 -> sklearn normalize
+                        float nrm = sqrtf(warp_sum(ss));
+                        if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;     // _handle_zeros_in_scale
+                        ss = 0.f;
+#pragma unroll
+                        for (int t = 0; t < NJ; ++t) {
+                            x[r][t].x = __fdiv_rn(x[r][t].x, nrm); x[r][t].y = __fdiv_rn(x[r][t].y, nrm);
+                            x[r][t].z = __fdiv_rn(x[r][t].z, nrm); x[r][t].w = __fdiv_rn(x[r][t].w, nrm);
+                            if (METRIC == OODB200_METRIC_COS) {
+                                ss = fmaf(x[r][t].x, x[r][t].x, ss); ss = fmaf(x[r][t].y, x[r][t].y, ss);
+                                ss = fmaf(x[r][t].z, x[r][t].z, ss); ss = fmaf(x[r][t].w, x[r][t].w, ss);
+                            }
+                        }
+                    }
+                    n2v[r] = 1.f;
+                    if (METRIC == OODB200_METRIC_COS) {              // cosine_distances re-normalises X (pairwise.py:1171-1182)
+                        n2v[r] = sqrtf(warp_sum(ss));
+                        if (n2v[r] < 10.f * FLT_EPSILON) n2v[r] = 1.f;
+                    }
+                }
+                // lane j = r + 4 * kk receives the total of (row r, centroid row k0 + kk)
+                const int my_r = lane & 3, my_kk = lane >> 2;
+                const float my_n2v = my_r == 0 ? n2v[0] : (my_r == 1 ? n2v[1] : (my_r == 2 ? n2v[2] : n2v[3]));
+                float best = FLT_MAX;
+                int barg = INT_MAX;
+                for (int k0 = 0; k0 < rc; k0 += kVfK) {
+                    float acc[32];
+#pragma unroll
+                    for (int kk = 0; kk < kVfK; ++kk) {
+                        const int k = k0 + kk < rc ? k0 + kk : rc - 1;        // short batch: repeat the last row, result dropped
+                        const float* __restrict__ ck = s_cent + (size_t)k * D + lane * 4;
+                        float a[kVfRows] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int t = 0; t < NJ; ++t) {
+                            const float4 c = (t < NJ - 1 || last_ok) ? *reinterpret_cast<const float4*>(ck + t * 128) : zero;
+#pragma unroll
+                            for (int r = 0; r < kVfRows; ++r) {
+                                if (METRIC == OODB200_METRIC_COS) {
+                                    a[r] = fmaf(x[r][t].x, c.x, a[r]); a[r] = fmaf(x[r][t].y, c.y, a[r]);
+                                    a[r] = fmaf(x[r][t].z, c.z, a[r]); a[r] = fmaf(x[r][t].w, c.w, a[r]);
+                                } else {
+                                    const float e0 = x[r][t].x - c.x, e1 = x[r][t].y - c.y, e2 = x[r][t].z - c.z, e3 = x[r][t].w - c.w;
+                                    if (METRIC == OODB200_METRIC_L1) a[r] += (fabsf(e0) + fabsf(e1)) + (fabsf(e2) + fabsf(e3));
+                                    else { a[r] = fmaf(e0, e0, a[r]); a[r] = fmaf(e1, e1, a[r]); a[r] = fmaf(e2, e2, a[r]); a[r] = fmaf(e3, e3, a[r]); }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < kVfRows; ++r) acc[r + 4 * kk] = a[r];
+                    }
+                    const float tot = transpose_reduce32(acc, lane);
+                    if (k0 + my_kk < rc) {
+                        float v = tot;
+                        if (METRIC == OODB200_METRIC_L2) v = sqrtf(fmaxf(tot, 0.f));
+                        if (METRIC == OODB200_METRIC_COS) v = fminf(fmaxf(1.0f - __fdiv_rn(tot, my_n2v), 0.f), 2.f);
+                        if (v < best) { best = v; barg = kb + k0 + my_kk; }                    // increasing k per lane, strict '<'
+                    }
+                }
+                // first minimum over the 8 lanes of a row: smaller value, then smaller index
+#pragma unroll
+                for (int o = 4; o <= 16; o <<= 1) {
+                    const float od = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oa = __shfl_xor_sync(0xffffffffu, barg, o);
+                    if (od < best || (od == best && oa < barg)) { best = od; barg = oa; }
+                }
+                if (lane < kVfRows && gr + lane < r1) {
+                    const size_t o = (size_t)METRIC * p.n_rows + (size_t)(gr + lane);
+                    if (!first) {                                    // merge with the earlier chunks (kept un-finalised in the outputs)
+                        const float pd = p.dist[o];
+                        const int pa = p.argmin[o];
+                        if (pd <= best) { best = pd; barg = pa; }    // earlier rows win ties
+                    }
+                    if (final) {
+                        const float dv = K > 0 ? best : 1000.f;   // no cluster: ood_utils.py:2159-2164
+                        p.dist[o] = dv;
+                        p.argmin[o] = K > 0 ? barg : -1;
+                        if (p.decision) {                            // :2173-2180 (NaN = falsy threshold -> OoD)
+                            const double t = p.thr[(size_t)METRIC * p.n_seg + g];
+                            p.decision[o] = (t == t && (double)dv < t) ? 1 : 0;
+                        }
+                    } else {
+                        p.dist[o] = best;
+                        p.argmin[o] = barg;
+                    }
+                }
+            }
+            if (K == 0) break;
+        }
+        r0 = r1;
+    }
+}
+
+typedef void (*VecFastKernel)(const VecParams, int, int);
+template <int METRIC>
+static VecFastKernel vec_fast_for(int nj) {
+    switch (nj) {
+        case 1: return vec_score_fast_kernel<1, METRIC>;
+        case 2: return vec_score_fast_kernel<2, METRIC>;
+        case 3: return vec_score_fast_kernel<3, METRIC>;
+        case 4: return vec_score_fast_kernel<4, METRIC>;
+        default: return vec_score_fast_kernel<5, METRIC>;
+    }
+}
+
 // sklearn.preprocessing.normalize(x, axis=1) for float32 rows: one warp per row
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ x, int64_t ld, int dim, int64_t n_rows,
                                                              float* __restrict__ out, int64_t out_ld) {
@@ -219,6 +397,36 @@ extern "C" int oodb200_vec_score_f32(const float* x, int64_t ld, int dim, const 
     OODB200_REQUIRE(!decision || thr, "vec_score: decision output needs thresholds");
     VecParams p = {x, ld, dim, seg_off, n_seg, n_rows, metric_mask, normalize, cent, cent_unit, cent_row_off, cent_k,
                    dist, argmin, (dim + 3) & ~3, thr, decision};
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    static int use_fast = -1;                                       // OODB200_VEC_FAST=0: one-row-per-warp kernel (A/B runs)
+    if (use_fast < 0) { const char* env = getenv("OODB200_VEC_FAST"); use_fast = (env && atoi(env) == 0) ? 0 : 1; }
+    const bool aligned = dim % 4 == 0 && ld % 4 == 0 && (((uintptr_t)x | (uintptr_t)cent | (uintptr_t)(cent_unit ? cent_unit : cent)) & 15) == 0;
+    if (use_fast && aligned && dim <= 640) {
+        // one launch per requested metric: rows in registers, centroid rows staged in shared memory
+        const int nj = (dim + 127) / 128;
+        const size_t budget = (nj <= 2 ? 96 : 192) * 1024;          // 2 CTAs / 1 CTA per SM
+        int rc_max = (int)(budget / ((size_t)dim * sizeof(float)));
+        OODB200_REQUIRE(rc_max >= 1, "vec_score: dim %d too large", dim);
+        const size_t smem = (size_t)rc_max * dim * sizeof(float);
+        const int ctas = sms * (nj <= 2 ? 2 : 1);
+        long long per = (n_rows + ctas - 1) / ctas;
+        per = (per + kVecWarps * kVfRows - 1) / (kVecWarps * kVfRows) * (kVecWarps * kVfRows);
+        const int grid = (int)((n_rows + per - 1) / per);
+        for (int m = 0; m < OODB200_N_METRICS; ++m) {
+            if (!(metric_mask >> m & 1)) continue;
+            const VecFastKernel kern = m == OODB200_METRIC_L1 ? vec_fast_for<OODB200_METRIC_L1>(nj)
+                                     : (m == OODB200_METRIC_L2 ? vec_fast_for<OODB200_METRIC_L2>(nj) : vec_fast_for<OODB200_METRIC_COS>(nj));
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: cheap
+            if (e != cudaSuccess) { set_error("vec_score: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+            kern<<<grid, kVecThreads, smem, st>>>(p, (int)per, rc_max);
+            const int rc = check_launch("vec_score");
+            if (rc) return rc;
+        }
+        return OODB200_OK;
+    }
     const size_t smem = sizeof(float) * 2 * (size_t)p.d_pad * kVecWarps;
     OODB200_REQUIRE(smem <= 200 * 1024, "vec_score: dim %d too large", dim);
     if (smem > 48 * 1024) {
@@ -226,8 +434,8 @@ extern "C" int oodb200_vec_score_f32(const float* x, int64_t ld, int dim, const 
         if (e != cudaSuccess) { set_error("vec_score: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
     }
     long long grid = (n_rows + kVecWarps - 1) / kVecWarps;
-    if (grid > 148LL * 32) grid = 148LL * 32;
-    vec_score_kernel<<<(int)grid, kVecThreads, smem, (cudaStream_t)stream>>>(p);
+    if (grid > (long long)sms * 32) grid = (long long)sms * 32;
+    vec_score_kernel<<<(int)grid, kVecThreads, smem, st>>>(p);
     return check_launch("vec_score");
 }
 

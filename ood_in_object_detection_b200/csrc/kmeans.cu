@@ -421,17 +421,30 @@ __global__ void kmeans_reduce_kernel(const float* __restrict__ in, const int32_t
     }
 }
 
-// sklearn _average_centers + _center_shift (squared, summed per segment); empty clusters keep their old centre
+// sklearn _average_centers + _center_shift (squared, summed per segment); empty clusters keep their old centre.
+// An inactive (converged) segment copies its centres through, so that the caller can ping-pong two buffers.
 __global__ void kmeans_update_kernel(const float* __restrict__ sums, const float* __restrict__ counts,
                                      const float* __restrict__ cent_old, const int32_t* __restrict__ seg_k,
                                      const int32_t* __restrict__ active, int k, int dim, float* __restrict__ cent_new,
                                      float* __restrict__ shift_sq, int32_t* __restrict__ n_empty) {
     const int g = blockIdx.x;
-    if (active && !active[g]) return;
+    if (active && !active[g]) {
+        for (int i = threadIdx.x; i < k * dim; i += blockDim.x) cent_new[(size_t)g * k * dim + i] = cent_old[(size_t)g * k * dim + i];
+        if (threadIdx.x == 0) { shift_sq[g] = 0.f; n_empty[g] = 0; }
+        return;
+    }
     __shared__ float s_red[32];
     const int Kg = seg_k[g];
     float tot = 0.f;
-    for (int kk = 0; kk < Kg; ++kk) {
+    int empties = 0;
+    for (int kk = 0; kk < k; ++kk) {
+        if (kk >= Kg) {                                     // slots beyond the segment's own cluster count: carried through
+            for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+                const size_t i = ((size_t)g * k + kk) * dim + d;
+                cent_new[i] = cent_old[i];
+            }
+            continue;
+        }
         const float w = counts[(size_t)g * k + kk];
         const float alpha = w > 0.f ? (float)(1.0 / (double)w) : 0.f;
         float sh = 0.f;
@@ -450,10 +463,43 @@ __global__ void kmeans_update_kernel(const float* __restrict__ sums, const float
             float t = 0.f;
             for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
             tot += t;                                   // (sqrt(t))^2 in sklearn; equal up to one rounding
-            if (!(w > 0.f)) atomicAdd(&n_empty[g], 1);
+            if (!(w > 0.f)) ++empties;
         }
     }
-    if (threadIdx.x == 0) shift_sq[g] = tot;
+    if (threadIdx.x == 0) { shift_sq[g] = tot; n_empty[g] = empties; }
+}
+
+// Convergence bookkeeping of one Lloyd iteration on the device (sklearn _kmeans_single_lloyd, _kmeans.py:712-740): a
+// segment stops when no label changed (strict convergence) or when its squared centre shift is <= tol; state rows:
+// [0] iterations run, [1] strict, [2] needs the final E-step, [3] empty clusters seen.  The host only polls any_active.
+__global__ void kmeans_converge_kernel(const int32_t* __restrict__ n_changed_i, const float* __restrict__ n_changed_f,
+                                       const float* __restrict__ shift, const int32_t* __restrict__ n_empty,
+                                       const double* __restrict__ tol_abs, const float* __restrict__ cnts, int n_seg, int k,
+                                       int32_t* __restrict__ active, int32_t* __restrict__ state, float* __restrict__ counts,
+                                       int32_t* __restrict__ any_active) {
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    int any = 0;
+    for (int g = threadIdx.x; g < n_seg; g += blockDim.x) {
+        if (!active[g]) continue;
+        const bool changed = n_changed_i ? n_changed_i[g] != 0 : n_changed_f[g] != 0.f;
+        state[g] += 1;
+        state[3 * n_seg + g] += n_empty[g];
+        for (int j = 0; j < k; ++j) counts[(size_t)g * k + j] = cnts[(size_t)g * k + j];
+        if (!changed) {
+            state[n_seg + g] = 1;
+            active[g] = 0;
+        } else if ((double)shift[g] <= tol_abs[g]) {
+            state[2 * n_seg + g] = 1;
+            active[g] = 0;
+        } else {
+            any = 1;
+        }
+    }
+    if (any) atomicOr(&s_any, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) any_active[0] = s_any;
 }
 
 // d[j, r] = max(float32(||y_j||^2 - 2 x_r.y_j + ||x_r||^2 in float64), 0); newd = min(closest, d); pot[j] += sum newd
@@ -722,6 +768,18 @@ extern "C" int oodb200_kmeans_update_f32(const float* sums, const float* counts,
     kmeans_update_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(sums, counts, cent_old, seg_k, active, k, dim, cent_new,
                                                                    shift_sq, n_empty);
     return check_launch("kmeans_update");
+}
+
+extern "C" int oodb200_kmeans_converge_f32(const int32_t* n_changed_i, const float* n_changed_f, const float* shift,
+                                           const int32_t* n_empty, const double* tol_abs, const float* cnts, int n_seg, int k,
+                                           int32_t* active, int32_t* state, float* counts, int32_t* any_active, void* stream) {
+    OODB200_REQUIRE(n_seg >= 0 && k > 0, "kmeans_converge: bad size");
+    OODB200_REQUIRE(any_active, "kmeans_converge: null pointer");
+    OODB200_REQUIRE(n_seg == 0 || ((n_changed_i || n_changed_f) && shift && n_empty && tol_abs && cnts && active && state && counts),
+                    "kmeans_converge: null pointer");
+    kmeans_converge_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(n_changed_i, n_changed_f, shift, n_empty, tol_abs, cnts, n_seg, k,
+                                                                 active, state, counts, any_active);
+    return check_launch("kmeans_converge");
 }
 
 extern "C" int oodb200_sqdist_cand_f32(const float* x, int dim, const int64_t* seg_off, int n_seg, int64_t max_seg_rows,

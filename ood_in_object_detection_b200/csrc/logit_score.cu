@@ -89,7 +89,9 @@ __global__ void __launch_bounds__(kLogitThreads) logit_kernel(const LogitParams 
     sc[OODB200_LOGIT_MSP] = cls_ok ? __fdiv_rn(expf(zc - m), ss) : 0.f;                                  // :1394-1397
     sc[OODB200_LOGIT_ENERGY] = want_energy ? p.t_energy * (me + logf(se)) : 0.f;                          // :1409-1412
     sc[OODB200_LOGIT_ODIN] = (want_odin && cls_ok) ? __fdiv_rn(expf(__fdiv_rn(zc, p.t_odin) - mo), so) : 0.f;  // :1424-1427
-    sc[OODB200_LOGIT_SIGMOID] = cls_ok ? __fdiv_rn(1.0f, 1.0f + expf(-zc)) : 0.f;                          // :1436-1443
+    // :1436-1443; with OODB200_LOGIT_FLAG_POST_SIGMOID the inputs already went through the detector's sigmoid
+    // (use_values_before_sigmoid=False, :1438-1439): the score is the input value itself
+    sc[OODB200_LOGIT_SIGMOID] = !cls_ok ? 0.f : ((p.method_mask & OODB200_LOGIT_FLAG_POST_SIGMOID) ? zc : __fdiv_rn(1.0f, 1.0f + expf(-zc)));
     sc[OODB200_LOGIT_MAXLOGIT] = m;                                                                      // no reference (Q7)
     if ((p.method_mask >> OODB200_LOGIT_SIGMOID & 1) && p.sigmoid_mismatch && am != cls) atomicAdd(p.sigmoid_mismatch, 1);
 #pragma unroll
@@ -142,7 +144,9 @@ extern "C" int oodb200_logit_score_f32(const float* logits, const int32_t* cls, 
                                        const double* smax, int clip_indness, float* scores, float* indness,
                                        uint8_t* decision, int32_t* sigmoid_mismatch, void* stream) {
     OODB200_REQUIRE(n >= 0 && nc > 0, "logit_score: bad size");
-    OODB200_REQUIRE(method_mask > 0 && method_mask < (1 << OODB200_N_LOGIT), "logit_score: method_mask %d", method_mask);
+    OODB200_REQUIRE((method_mask & ((1 << OODB200_N_LOGIT) - 1)) != 0 &&
+                    (method_mask & ~(((1 << OODB200_N_LOGIT) - 1) | OODB200_LOGIT_FLAG_POST_SIGMOID)) == 0,
+                    "logit_score: method_mask %d", method_mask);
     OODB200_REQUIRE(t_energy != 0.f && t_odin != 0.f, "logit_score: zero temperature");
     if (n == 0) return OODB200_OK;
     OODB200_REQUIRE(logits && cls && scores, "logit_score: null pointer");

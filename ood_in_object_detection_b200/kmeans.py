@@ -27,7 +27,22 @@ import numpy as np
 import torch
 
 BLOCK_ROWS = 512          # rows per CTA partial
-SUPER_BLOCKS = 32         # block partials per super-block (unit of ownership for reduce="ordered")
+SUPER_BLOCKS = 8          # block partials per super-block (unit of ownership; 4096 rows: C3's 200 000-row segments split
+                          # into 49 units, so 8 ranks own 6-7 each)
+POLL_LAG = 2              # Lloyd iterations the device may run ahead of the host's convergence poll
+
+
+def range_index(seg: int, world: int, rank: int) -> int:
+    """Which of the `world` contiguous row ranges of segment `seg` the rank owns.  The assignment rotates with the
+    segment index: floor(n_super * r / world) gives some range indices one super-block more than others, and without
+    the rotation the same ranks would get the larger range of EVERY segment (C3 on 8 ranks: 2 x the rows of their
+    neighbours)."""
+    return (rank - seg) % world
+
+
+def ranks_in_row_order(seg: int, world: int) -> List[int]:
+    """Ranks owning the consecutive row ranges of segment `seg`, in row order."""
+    return [(seg + j) % world for j in range(world)]
 DEVICE_SEEDING_MIN_ROWS = 1 << 16   # seeding="auto": below this the host loop costs nothing and tracks sklearn's BLAS
 
 
@@ -173,15 +188,32 @@ class CudaBackend:
                         "oodb200_kmeans_reduce_f32")
         return out
 
-    def update(self, sums, counts, cent, seg_k, active):
+    def reduce_into(self, part, first, n_groups, out):
+        """kmeans_reduce into a caller-owned contiguous buffer (a slice of the all-reduce buffer: no concatenation)."""
+        elems = int(np.prod(part.shape[1:]))
+        self._lib.check(self.lib.oodb200_kmeans_reduce_f32(_ptr(part), _ptr(first), n_groups, elems, _ptr(out), _stream()),
+                        "oodb200_kmeans_reduce_f32")
+        return out
+
+    def update(self, sums, counts, cent, seg_k, active, out=None):
         n_seg, k, dim = cent.shape
-        new = cent.clone()
-        shift = torch.zeros(n_seg, dtype=torch.float32, device=cent.device)
-        n_empty = torch.zeros(n_seg, dtype=torch.int32, device=cent.device)
+        if out is None:
+            out = (torch.empty_like(cent), torch.empty(n_seg, dtype=torch.float32, device=cent.device),
+                   torch.empty(n_seg, dtype=torch.int32, device=cent.device))
+        new, shift, n_empty = out
         self._lib.check(self.lib.oodb200_kmeans_update_f32(_ptr(sums), _ptr(counts), _ptr(cent), _ptr(seg_k), _ptr(active),
                                                            n_seg, k, dim, _ptr(new), _ptr(shift), _ptr(n_empty), _stream()),
                         "oodb200_kmeans_update_f32")
         return new, shift, n_empty
+
+    def converge(self, n_changed, shift, n_empty, tol_abs, cnts, k, active, state, counts, any_active):
+        """Device-side convergence bookkeeping of one iteration (csrc/kmeans.cu::kmeans_converge_kernel)."""
+        n_seg = int(active.shape[0])
+        as_int = n_changed.dtype == torch.int32
+        self._lib.check(self.lib.oodb200_kmeans_converge_f32(
+            _ptr(n_changed) if as_int else None, None if as_int else _ptr(n_changed), _ptr(shift), _ptr(n_empty), _ptr(tol_abs),
+            _ptr(cnts), n_seg, k, _ptr(active), _ptr(state), _ptr(counts), _ptr(any_active), _stream()),
+            "oodb200_kmeans_converge_f32")
 
 
 @dataclass
@@ -197,26 +229,30 @@ class BlockTable:
     super_seg_first: torch.Tensor  # [n_seg+1] int32 over ALL super-blocks (global, rank-major = row order)
     n_super_global: int
     super_owner_counts: List[int]  # super-blocks per rank
+    rot: List[int] = field(default_factory=list)   # rotation key of every segment (range_index / ranks_in_row_order)
 
 
 _BLOCK_CACHE: dict = {}
 
 
-def build_blocks(global_sizes: Sequence[int], world: int, rank: int, device) -> tuple:
+def build_blocks(global_sizes: Sequence[int], world: int, rank: int, device, rot: Optional[Sequence[int]] = None) -> tuple:
     """Row sharding + block tables.  Rank r owns a contiguous range of super-blocks of every segment.
-    The tables only depend on (sizes, world, rank): the last few are kept (a C3 table has 7.8 k blocks built in Python)."""
-    key = (tuple(int(n) for n in global_sizes), int(world), int(rank), str(device))
+    rot[g]: rotation key of segment g (default: its index) -- callers that fit a SUBSET of their segments pass a stable id
+    (the class index) so that the rows a rank must hold do not depend on which other segments take part.
+    The tables only depend on (sizes, world, rank, rot): the last few are kept (a C3 table has 7.8 k blocks built in Python)."""
+    rot = list(range(len(global_sizes))) if rot is None else [int(v) for v in rot]
+    key = (tuple(int(n) for n in global_sizes), int(world), int(rank), str(device), tuple(rot))
     hit = _BLOCK_CACHE.get(key)
     if hit is not None:
         return hit
-    out = _build_blocks(global_sizes, world, rank, device)
+    out = _build_blocks(global_sizes, world, rank, device, rot)
     if len(_BLOCK_CACHE) >= 8:
         _BLOCK_CACHE.pop(next(iter(_BLOCK_CACHE)))
     _BLOCK_CACHE[key] = out
     return out
 
 
-def _build_blocks(global_sizes: Sequence[int], world: int, rank: int, device) -> tuple:
+def _build_blocks(global_sizes: Sequence[int], world: int, rank: int, device, rot) -> tuple:
     seg_l, r0_l, r1_l, sfirst = [], [], [], [0]
     local_sizes, local_off = [], [0]
     super_seg_first = [0]
@@ -224,11 +260,13 @@ def _build_blocks(global_sizes: Sequence[int], world: int, rank: int, device) ->
     shard = []                                           # per segment: (global start row, rows) owned by this rank
     for g, n in enumerate(global_sizes):
         n_super = (n + BLOCK_ROWS * SUPER_BLOCKS - 1) // (BLOCK_ROWS * SUPER_BLOCKS)
-        bounds = [(n_super * r) // world for r in range(world + 1)]       # super-blocks per rank, contiguous
+        bounds = [(n_super * r) // world for r in range(world + 1)]       # super-blocks per range, contiguous
         for r in range(world):
-            owner_counts[r] += bounds[r + 1] - bounds[r]
+            ri = range_index(rot[g], world, r)
+            owner_counts[r] += bounds[ri + 1] - bounds[ri]
         super_seg_first.append(super_seg_first[-1] + n_super)
-        s0, s1 = bounds[rank], bounds[rank + 1]
+        ri = range_index(rot[g], world, rank)
+        s0, s1 = bounds[ri], bounds[ri + 1]
         row_a = min(n, s0 * BLOCK_ROWS * SUPER_BLOCKS)
         row_b = min(n, s1 * BLOCK_ROWS * SUPER_BLOCKS)
         shard.append((row_a, row_b - row_a))
@@ -247,7 +285,7 @@ def _build_blocks(global_sizes: Sequence[int], world: int, rank: int, device) ->
     table = BlockTable(seg=t(seg_l, torch.int32), row0=t(r0_l, torch.int64), row1=t(r1_l, torch.int64),
                        n_blocks=len(seg_l), super_first=t(sfirst, torch.int32), n_super_local=len(sfirst) - 1,
                        super_seg_first=t(super_seg_first, torch.int32), n_super_global=super_seg_first[-1],
-                       super_owner_counts=owner_counts)
+                       super_owner_counts=owner_counts, rot=list(rot))
     return table, shard, local_off
 
 
@@ -291,7 +329,7 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
     ~ n * 2^-24 per draw (sklearn itself depends on the BLAS summation order there)."""
     import time
     import torch.distributed as dist
-    distributed = group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+    distributed = group is not None                    # explicit: a single-process fit inside an initialised job stays local
     world = dist.get_world_size(group) if distributed else 1
     rank = dist.get_rank(group) if distributed else 0
     dev = x_local.device
@@ -329,82 +367,108 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
         raise ValueError(f"seeding must be 'auto', 'device' or 'host', not {seeding!r}")
     if seeding == "device":
         cent = _seed_on_device(x, global_sizes, local_off, shard, seg_k_host, k, random_state, backend, group,
-                               distributed, world)
+                               distributed, world, table.rot)
         if dev.type == "cuda":
             torch.cuda.synchronize()
     else:
         cent = _seed_on_host(x, global_sizes, local_off, shard, seg_k_host, k, random_state, backend, group,
-                             distributed, world, seg_off_d)
+                             distributed, world, seg_off_d, table.rot)
     timing["init"] = time.perf_counter() - t0
     timing["seeding"] = seeding
 
     # ---- Lloyd iterations (sklearn _kmeans_single_lloyd, _kmeans.py:630-758) ----
+    # Everything an iteration decides stays on the device: the convergence kernel retires segments (active flags, iteration
+    # counts, strict / needs-final-E-step marks) and the host only polls ONE flag, POLL_LAG iterations behind the launches,
+    # so that the device never waits for the host loop.  Iterations issued after every segment has stopped are no-ops
+    # (inactive segments are skipped by the step, carried through by the update, ignored by the bookkeeping); with N > 1
+    # every rank sees the same all-reduced flags and therefore issues the same number of collectives.
     t0 = time.perf_counter()
+    cuda = dev.type == "cuda"
     labels = torch.full((x.shape[0],), -1, dtype=torch.int32, device=dev)
     active = torch.tensor([1 if global_sizes[g] > 0 else 0 for g in range(n_seg)], dtype=torch.int32, device=dev)
-    active_h = active.cpu().numpy().astype(bool)
-    need_final = np.zeros(n_seg, dtype=bool)
-    n_iter = [0] * n_seg
-    strict = [False] * n_seg
-    n_empty_tot = [0] * n_seg
+    state = torch.zeros((4, n_seg), dtype=torch.int32, device=dev)         # iterations, strict, needs final E-step, empties
+    any_active = torch.ones(1, dtype=torch.int32, device=dev)
+    tol_d = torch.from_numpy(np.ascontiguousarray(tol_abs, dtype=np.float64)).to(dev)
     seg_first = _seg_first_local(table, n_seg, dev)
     counts = torch.zeros((n_seg, k), dtype=torch.float32, device=dev)
-    lloyd_iters = 0
+    n_sum, n_cnt = n_seg * k * dim, n_seg * k
+    flat = torch.zeros(n_sum + n_cnt + n_seg, dtype=torch.float32, device=dev)   # sums | counts | changed labels: ONE all-reduce
+    sums_v, cnts_v = flat[:n_sum].view(n_seg, k, dim), flat[n_sum:n_sum + n_cnt].view(n_seg, k)
+    chg_f = flat[n_sum + n_cnt:]
+    n_changed = torch.zeros(n_seg, dtype=torch.int32, device=dev)
+    cent = cent.contiguous()
+    other = (torch.empty_like(cent), torch.empty(n_seg, dtype=torch.float32, device=dev),
+             torch.empty(n_seg, dtype=torch.int32, device=dev))
+    has_into = hasattr(backend, "reduce_into")
+    polls = []                                                              # (host flag, event) per issued iteration
+    flag_ring = torch.empty(POLL_LAG + 2, dtype=torch.int32).pin_memory() if cuda else None
+    issued = 0
     for it in range(max_iter):
-        n_changed = torch.zeros(n_seg, dtype=torch.int32, device=dev)
+        n_changed.zero_()
         psums, pcounts = backend.step(x, k, seg_k, cent, table, active, labels, n_changed, True)
         if reduce == "ordered":
             sums, cnts = _ordered_reduce(backend, psums, pcounts, table, n_seg, world, group)
+            chg = allreduce(n_changed) if distributed else n_changed
         else:
-            sums = backend.reduce(psums, seg_first, n_seg) if table.n_blocks else torch.zeros_like(cent)
-            cnts = backend.reduce(pcounts, seg_first, n_seg) if table.n_blocks else torch.zeros_like(counts)
+            if table.n_blocks and has_into:
+                backend.reduce_into(psums, seg_first, n_seg, sums_v)
+                backend.reduce_into(pcounts, seg_first, n_seg, cnts_v)
+            elif table.n_blocks:
+                sums_v.copy_(backend.reduce(psums, seg_first, n_seg))
+                cnts_v.copy_(backend.reduce(pcounts, seg_first, n_seg))
+            else:
+                flat.zero_()
+            sums, cnts, chg = sums_v, cnts_v, n_changed
             if distributed:
-                flat = torch.cat([sums.reshape(-1), cnts.reshape(-1), n_changed.to(torch.float32)])
-                allreduce(flat)                                            # the one collective of the iteration
-                sums = flat[:sums.numel()].reshape(sums.shape)
-                cnts = flat[sums.numel():sums.numel() + cnts.numel()].reshape(cnts.shape)
-                n_changed = flat[sums.numel() + cnts.numel():].to(torch.int32)
-        if reduce == "ordered" and distributed:
-            allreduce(n_changed)
-        new_cent, shift, n_empty = backend.update(sums, cnts, cent, seg_k, active)
-        flags = torch.stack([n_changed.to(torch.float64), shift.to(torch.float64), n_empty.to(torch.float64)]).cpu().numpy()
+                chg_f.copy_(n_changed)                                      # exact in float32 below 2^24 rows per segment
+                allreduce(flat)                                             # the one collective of the iteration
+                chg = chg_f
+        new_cent, shift, n_empty = backend.update(sums, cnts, cent, seg_k, active, out=other)
+        backend.converge(chg, shift, n_empty, tol_d, cnts, k, active, state, counts, any_active)
+        other = (cent, shift, n_empty)
         cent = new_cent
-        am = active.to(torch.bool)
-        counts = torch.where(am[:, None], cnts, counts)
-        lloyd_iters += 1
-        for g in range(n_seg):
-            if not active_h[g]:
-                continue
-            n_iter[g] = it + 1
-            n_empty_tot[g] += int(flags[2, g])
-            if flags[0, g] == 0:
-                strict[g] = True
-                active_h[g] = False
-            elif flags[1, g] <= tol_abs[g]:
-                active_h[g] = False
-                need_final[g] = True
-        active = torch.from_numpy(active_h.astype(np.int32)).to(dev)
-        if not active_h.any():
+        issued += 1
+        if cuda:
+            flag = flag_ring[it % (POLL_LAG + 2):it % (POLL_LAG + 2) + 1]     # consumed POLL_LAG iterations later: no reuse hazard
+            flag.copy_(any_active, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            polls.append((flag, ev))
+            if len(polls) > POLL_LAG:
+                f, e = polls[len(polls) - 1 - POLL_LAG]
+                e.synchronize()
+                if int(f[0]) == 0:
+                    break
+        elif int(any_active[0]) == 0:
             break
-    need_final |= active_h                                                  # max_iter reached without convergence
+    if cuda:
+        torch.cuda.synchronize()
+    st = state.cpu().numpy()
+    n_iter = [int(v) for v in st[0]]
+    strict = [bool(v) for v in st[1]]
+    n_empty_tot = [int(v) for v in st[3]]
+    need_final = st[2].astype(bool) | active.cpu().numpy().astype(bool)    # max_iter reached without convergence
+    lloyd_iters = max(n_iter + [0])
     if need_final.any():                                                    # E-step with the final centres (:742-754)
         fin = torch.from_numpy(need_final.astype(np.int32)).to(dev)
         dummy = torch.zeros(n_seg, dtype=torch.int32, device=dev)
         backend.step(x, k, seg_k, cent, table, fin, labels, dummy, False)
-    if dev.type == "cuda":
+    if cuda:
         torch.cuda.synchronize()
     timing["lloyd"] = time.perf_counter() - t0
     timing["lloyd_iters"] = lloyd_iters
-    return KMeansResult(labels=labels, centers=cent + mean[:, None, :], counts=counts, n_iter=n_iter, strict=strict,
+    timing["lloyd_issued"] = issued
+    return KMeansResult(labels=labels, centers=cent + mean[:, None, :], counts=counts.clone(), n_iter=n_iter, strict=strict,
                         n_empty=n_empty_tot, seconds=timing)
 
 
 def _seed_on_host(x, global_sizes, local_off, shard, seg_k_host, k, random_state, backend, group, distributed, world,
-                  seg_off_d):
+                  seg_off_d, rot=None):
     """k-means++ with the scalar decisions in numpy (sklearn's own expressions, host BLAS potentials)."""
     import torch.distributed as dist
     dev = x.device
     n_seg, dim = len(global_sizes), int(x.shape[1])
+    rot = list(range(n_seg)) if not rot else rot
 
     def allreduce(t, op=None):
         if distributed:
@@ -441,7 +505,7 @@ def _seed_on_host(x, global_sizes, local_off, shard, seg_k_host, k, random_state
         out = []
         for g in range(n_seg):
             parts = []
-            for r in range(world):
+            for r in ranks_in_row_order(rot[g], world):
                 o = int(metas[r][1:1 + g].sum())
                 parts.append(host[r][:, o:o + int(metas[r][1 + g])])
             out.append(np.concatenate(parts, axis=1))
@@ -537,13 +601,15 @@ def _sklearn_uniform_stream(global_sizes, seg_k_host, k, random_state):
     return first, uni, trials
 
 
-def _seed_on_device(x, global_sizes, local_off, shard, seg_k_host, k, random_state, backend, group, distributed, world):
+def _seed_on_device(x, global_sizes, local_off, shard, seg_k_host, k, random_state, backend, group, distributed, world,
+                    rot=None):
     """k-means++ without a host round trip per centre: scan + search, gather, distance pass, pick are stream-ordered
     kernels (csrc/seed.cu); N > 1 adds an all-gather of the closest distances (the scan is global and sequential, every
     rank runs it redundantly on the same bits) and all-reduces of the candidate vectors and potentials."""
     import torch.distributed as dist
     dev = x.device
     n_seg, dim = len(global_sizes), int(x.shape[1])
+    rot = list(range(n_seg)) if not rot else rot
     first, uni, trials = _sklearn_uniform_stream(global_sizes, seg_k_host, k, random_state)
     n_trials = uni.shape[2]
     i64 = lambda a: torch.tensor(np.asarray(a), dtype=torch.int64, device=dev)
@@ -564,8 +630,9 @@ def _seed_on_device(x, global_sizes, local_off, shard, seg_k_host, k, random_sta
         dist.all_gather(metas, meta, group=group)
         metas = [m.cpu().numpy() for m in metas]
         max_local = max(int(m[0]) for m in metas)
-        piece_off = i64([[r * max_local + int(metas[r][1:1 + g].sum()) for r in range(world)] for g in range(n_seg)])
-        piece_cnt = i64([[int(metas[r][1 + g]) for r in range(world)] for g in range(n_seg)])
+        # the pieces of a segment in ROW order (the owner of the j-th range rotates with the segment, ranks_in_row_order)
+        piece_off = i64([[r * max_local + int(metas[r][1:1 + g].sum()) for r in ranks_in_row_order(rot[g], world)] for g in range(n_seg)])
+        piece_cnt = i64([[int(metas[r][1 + g]) for r in ranks_in_row_order(rot[g], world)] for g in range(n_seg)])
         gathered = torch.zeros((world, max_local), dtype=torch.float32, device=dev)
     else:
         piece_off = i64([[local_off[g]] for g in range(n_seg)])
@@ -589,8 +656,12 @@ def _seed_on_device(x, global_sizes, local_off, shard, seg_k_host, k, random_sta
         if distributed:
             pad = torch.zeros(max_local, dtype=torch.float32, device=dev)
             pad[:n_local] = closest
-            dist.all_gather_into_tensor(gathered, pad, group=group) if dev.type == "cuda" else \
-                dist.all_gather(list(gathered.unbind(0)), pad, group=group)
+            if dist.get_backend(group) == "nccl":
+                dist.all_gather_into_tensor(gathered, pad, group=group)
+            else:                                                          # gloo (CPU tests, two ranks on one GPU)
+                parts = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad, group=group)
+                gathered.copy_(torch.stack(parts))
             closest_all = gathered
         else:
             closest_all = closest
@@ -631,7 +702,7 @@ def _ordered_reduce(backend, psums, pcounts, table: BlockTable, n_seg: int, worl
     per_rank_seg = _super_per_rank_seg(table, n_seg, world)
     rows, offs = [], [0] * world
     for g in range(n_seg):
-        for r in range(world):
+        for r in ranks_in_row_order(table.rot[g], world):
             c = per_rank_seg[r][g]
             rows.append(bufs[r][offs[r]:offs[r] + c])
             offs[r] += c
@@ -648,16 +719,17 @@ def _super_per_rank_seg(table: BlockTable, n_seg: int, world: int):
         n_super = int(first[g + 1] - first[g])
         bounds = [(n_super * r) // world for r in range(world + 1)]
         for r in range(world):
-            out[r][g] = bounds[r + 1] - bounds[r]
+            ri = range_index(table.rot[g], world, r)
+            out[r][g] = bounds[ri + 1] - bounds[ri]
     return out
 
 
 def kmeans_fit_sharded(x_local: torch.Tensor, local_sizes: Sequence[int], global_sizes: Sequence[int], k: int, world: int,
-                       rank: int, group=None, random_state: int = 10, **kw) -> KMeansResult:
+                       rank: int, group=None, random_state: int = 10, rot: Optional[Sequence[int]] = None, **kw) -> KMeansResult:
     """N > 1 entry: this rank holds `local_sizes[g]` rows of segment g (segment-major in x_local).  The block table
     only depends on the GLOBAL sizes, and build_blocks prescribes which rows each rank owns; the caller must have
     sharded accordingly (see shard_rows)."""
-    table, shard, local_off = build_blocks(global_sizes, world, rank, x_local.device)
+    table, shard, local_off = build_blocks(global_sizes, world, rank, x_local.device, rot)
     mine = [cnt for _, cnt in shard]
     if list(mine) != [int(v) for v in local_sizes]:
         raise ValueError(f"rank {rank}: row shard {list(local_sizes)} does not match the block table's {mine}; "
@@ -665,46 +737,91 @@ def kmeans_fit_sharded(x_local: torch.Tensor, local_sizes: Sequence[int], global
     return kmeans_fit(x_local, global_sizes, k, table, local_off, shard, random_state=random_state, group=group, **kw)
 
 
-def shard_rows(global_sizes: Sequence[int], world: int, rank: int) -> List[tuple]:
-    """(first row, row count) of every segment owned by `rank` (contiguous super-block ranges, build_blocks)."""
+def shard_rows(global_sizes: Sequence[int], world: int, rank: int, rot: Optional[Sequence[int]] = None) -> List[tuple]:
+    """(first row, row count) of every segment owned by `rank`: a contiguous range of whole super-blocks; which of the
+    `world` ranges of a segment a rank owns rotates with the segment index (range_index)."""
     out = []
-    for n in global_sizes:
+    for g, n in enumerate(global_sizes):
         n_super = (n + BLOCK_ROWS * SUPER_BLOCKS - 1) // (BLOCK_ROWS * SUPER_BLOCKS)
-        s0, s1 = (n_super * rank) // world, (n_super * (rank + 1)) // world
+        ri = range_index(g if rot is None else int(rot[g]), world, rank)
+        s0, s1 = (n_super * ri) // world, (n_super * (ri + 1)) // world
         a, b = min(n, s0 * BLOCK_ROWS * SUPER_BLOCKS), min(n, s1 * BLOCK_ROWS * SUPER_BLOCKS)
         out.append((a, b - a))
     return out
 
 
-def member_means(x: torch.Tensor, sizes: Sequence[int], labels: Optional[torch.Tensor], k: int, group=None, backend=None):
+def member_means(x: torch.Tensor, sizes: Sequence[int], labels: Optional[torch.Tensor], k: int, group=None, backend=None,
+                 reduce: str = "allreduce", global_sizes: Optional[Sequence[int]] = None, rot: Optional[Sequence[int]] = None):
     """Per segment, per label: mean of the member rows -- `np.mean(X[labels == j], axis=0)` of
     /root/reference/ood_utils.py:2359-2366 (labels=None: one cluster = the segment mean, :2306).
     Sums run through the k-means step kernel in its update==2 mode (block partials in row order + fixed-order
-    reduction); N > 1: one all-reduce of the sums and counts.  -> (means [n_seg, k, dim], counts [n_seg, k])."""
+    reduction); N > 1: one all-reduce of the sums and counts, or, with reduce="ordered" (needs the global sizes: the
+    local rows are the shard `shard_rows` prescribes), the rank-count-invariant reduction of `_ordered_reduce`, whose
+    result is bit-identical for 1 / 2 / 4 / 8 ranks.  -> (means [n_seg, k, dim], counts [n_seg, k])."""
     import torch.distributed as dist
     dev = x.device
     backend = backend or CudaBackend(dev)
     n_seg, dim = len(sizes), int(x.shape[1])
-    table, _, _ = build_blocks(sizes, 1, 0, dev)
+    ordered = reduce == "ordered"
+    if ordered:
+        world = dist.get_world_size(group) if group is not None else 1
+        rank = dist.get_rank(group) if group is not None else 0
+        gsz = list(sizes) if global_sizes is None else list(global_sizes)
+        table, shard, _ = build_blocks(gsz, world, rank, dev, rot)
+        if [cnt for _, cnt in shard] != [int(v) for v in sizes]:
+            raise ValueError("member_means(reduce='ordered'): the local rows must be the shard kmeans.shard_rows() prescribes")
+    else:
+        table, _, _ = build_blocks(sizes, 1, 0, dev)
     if labels is None:
         labels = torch.zeros(x.shape[0], dtype=torch.int32, device=dev)
     labels = labels.to(torch.int32).contiguous()
     seg_k = torch.full((n_seg,), k, dtype=torch.int32, device=dev)
     cent = torch.zeros((n_seg, k, dim), dtype=torch.float32, device=dev)
     dummy = torch.zeros(n_seg, dtype=torch.int32, device=dev)
-    if table.n_blocks:
-        psums, pcounts = backend.step(x.contiguous(), k, seg_k, cent, table, None, labels, dummy, 2)
-        first = _seg_first_local(table, n_seg, dev)
-        sums = backend.reduce(psums, first, n_seg)
-        cnts = backend.reduce(pcounts, first, n_seg)
+    if ordered:
+        if table.n_blocks:
+            psums, pcounts = backend.step(x.contiguous(), k, seg_k, cent, table, None, labels, dummy, 2)
+        else:
+            psums, pcounts = cent.new_zeros((0, k, dim)), cent.new_zeros((0, k))
+        sums, cnts = _ordered_reduce(backend, psums, pcounts, table, n_seg, world, group)
     else:
-        sums, cnts = cent, torch.zeros((n_seg, k), dtype=torch.float32, device=dev)
-    if group is not None:
-        flat = torch.cat([sums.reshape(-1), cnts.reshape(-1)])
-        dist.all_reduce(flat, group=group)
-        sums, cnts = flat[:sums.numel()].reshape(sums.shape), flat[sums.numel():].reshape(cnts.shape)
+        if table.n_blocks:
+            psums, pcounts = backend.step(x.contiguous(), k, seg_k, cent, table, None, labels, dummy, 2)
+            first = _seg_first_local(table, n_seg, dev)
+            sums = backend.reduce(psums, first, n_seg)
+            cnts = backend.reduce(pcounts, first, n_seg)
+        else:
+            sums, cnts = cent, torch.zeros((n_seg, k), dtype=torch.float32, device=dev)
+        if group is not None:
+            flat = torch.cat([sums.reshape(-1), cnts.reshape(-1)])
+            dist.all_reduce(flat, group=group)
+            sums, cnts = flat[:sums.numel()].reshape(sums.shape), flat[sums.numel():].reshape(cnts.shape)
     means = sums / cnts.clamp_min(1.0)[..., None]
     return means, cnts
+
+
+def member_medians(x: torch.Tensor, sizes: Sequence[int], labels: Optional[torch.Tensor], k: int):
+    """`agg_method='median'`: per segment, per label `np.median(X[labels == j], axis=0)` (/root/reference/ood_utils.py:
+    1481-1483, :2306, :2365).  One device sort per (segment, label) (torch.sort = CUB radix sort: memory plumbing, the
+    order statistic needs every member row); an even count averages the two middle rows in float32 like numpy does.
+    Not on the bandwidth-critical path (the paper's runs use 'mean').  -> (medians [n_seg, k, dim], counts [n_seg, k])."""
+    dev = x.device
+    n_seg, dim = len(sizes), int(x.shape[1])
+    med = torch.zeros((n_seg, k, dim), dtype=torch.float32, device=dev)
+    cnt = torch.zeros((n_seg, k), dtype=torch.float32, device=dev)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    for g in range(n_seg):
+        xs = x[off[g]:off[g + 1]]
+        lab = None if labels is None else labels[off[g]:off[g + 1]]
+        for j in range(k if labels is not None else 1):
+            rows = xs if lab is None else xs[lab == j]
+            m = int(rows.shape[0])
+            if m == 0:
+                continue
+            srt = torch.sort(rows, dim=0).values
+            med[g, j] = srt[m // 2] if m % 2 else (srt[m // 2 - 1] + srt[m // 2]) / 2
+            cnt[g, j] = m
+    return med, cnt
 
 
 def kmeans_fit_predict_single(x: torch.Tensor, sizes: Sequence[int], k: int, random_state: int = 10, **kw) -> KMeansResult:

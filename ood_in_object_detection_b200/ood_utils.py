@@ -60,6 +60,8 @@ def _rows_2d(a) -> Union[np.ndarray, torch.Tensor]:
     """[N, C, 1, 1] / [N, C] / [C, 1, 1]-list -> [N, D] view (numpy or torch, no copy when possible)."""
     if isinstance(a, (list, tuple)):
         a = np.stack([_np(v) for v in a], axis=0) if len(a) else np.empty((0, 0), np.float32)
+    if a.ndim == 1 and a.shape[0] == 0:                    # format_internal_activations stores np.empty(0) for "no rows"
+        return a.reshape(0, 0)
     return a.reshape(a.shape[0], -1) if a.ndim != 2 else a
 
 
@@ -388,6 +390,9 @@ class LogitsMethod(OODMethod):
         self.min_score = None
         self.max_score = None
 
+    def _method_mask(self) -> int:
+        return 1 << self._slot
+
     # temperatures of the K3 launch (Energy / ODIN override)
     def _temperatures(self) -> Tuple[float, float]:
         return 1.0, 1000.0
@@ -425,7 +430,7 @@ class LogitsMethod(OODMethod):
         thr = self._table(self.thresholds, nc, dev) if with_tables else None
         smin = self._table(self.min_score, nc, dev) if with_tables and self.min_score is not None else None
         smax = self._table(self.max_score, nc, dev) if with_tables and self.max_score is not None else None
-        out = ops.logit_score(logits, cls, 1 << self._slot, t_energy=te, t_odin=to, thr=thr, smin=smin, smax=smax,
+        out = ops.logit_score(logits, cls, self._method_mask(), t_energy=te, t_odin=to, thr=thr, smin=smin, smax=smax,
                               clip=CUSTOM_HYP.fusion.CLIP_FUSION_SCORES)
         return out
 
@@ -597,11 +602,9 @@ class Sigmoid(LogitsMethod):
     def __init__(self, **kwargs):
         super().__init__('MSP', **kwargs)
 
-    def _launch(self, logits, cls, with_tables):
-        if not self.use_values_before_sigmoid:
-            # the detector already applied the sigmoid: undo it so that K3's sigmoid reproduces the input value
-            logits = torch.logit(logits.clamp(1e-12, 1 - 1e-7))
-        return super()._launch(logits, cls, with_tables)
+    def _method_mask(self) -> int:
+        # the detector already applied the sigmoid: K3's Sigmoid slot then returns the input value itself
+        return (1 << self._slot) | (0 if self.use_values_before_sigmoid else ops.LOGIT_FLAG_POST_SIGMOID)
 
     def _post_launch_checks(self, out) -> None:
         assert int(out.sigmoid_mismatch.item()) == 0, "The max logit is not the one of the predicted class"
@@ -624,6 +627,7 @@ class DistanceMethod(OODMethod):
     metric: str
     normalize_activations: bool = True     # vanilla FMap methods L2-normalise the pooled vector (ood_utils.py:2409)
     activations_on_device: bool = False    # keep collected InD activations as CUDA tensors (large fits)
+    fit_reduce: str = "allreduce"          # sharded fit: "ordered" = rank-count-invariant reductions (identical bits for 1/2/4/8 ranks)
 
     def __init__(self, name: str, per_class: bool, per_stride: bool, cluster_method: str, metric: str,
                  cluster_optimization_metric: str, agg_method: str, ind_info_creation_option: str,
@@ -818,11 +822,37 @@ class DistanceMethod(OODMethod):
             out.append(per_stride)
         return out
 
-    def _vector_scores(self, results, want_decision: bool = True):
+    embeds_vectors: bool = False           # SDR methods: `_transform_device` maps the pooled vector to another space
+
+    def _pooled_per_stride(self, results):
+        """'ftmaps_and_strides' for the methods that cannot use the fused pass (SDR: a learned reducer sits between pooling
+        and scoring): pool every box on its stride (K1) and hand the vectors out in the per-image / per-stride form of
+        `_vectors_per_stride` (box indices in box order per stride, like predict.py:78-88)."""
+        dev = ops.default_device()
+        hw = _img_hw(results[0])
+        assert all(_img_hw(r) == hw for r in results), "all images of a batch must share the network input shape"
+        batch = ops.make_batch([list(res.extra_item[0]) for res in results], [res.boxes.xyxy for res in results],
+                               [res.extra_item[1] for res in results], [res.boxes.cls for res in results], hw[1], dev)
+        dims = [int(c) for c in batch.map_chw.reshape(3, 3)[:, 0]]
+        pooled = ops.roi_pool(batch) if batch.n else None
+        st_h = batch.stride_idx.cpu().numpy().astype(np.int64) if batch.n else np.zeros(0, np.int64)
+        start = np.concatenate([[0], np.cumsum(batch.counts)]).astype(np.int64)
+        out = []
+        for i in range(len(results)):
+            st = st_h[start[i]:start[i + 1]]
+            per_stride = []
+            for s in range(3):
+                idx = np.nonzero(st == s)[0]
+                v = pooled.index_select(0, torch.from_numpy(start[i] + idx).to(dev))[:, :dims[s]].contiguous() if len(idx) else None
+                per_stride.append((idx, v))
+            out.append(per_stride)
+        return out
+
+    def _vector_scores(self, results, want_decision: bool = True, per_img=None):
         """Distances / decisions for pre-extracted vectors, K2 standalone, one launch per stride.
         Returns (counts, dist [n] numpy, decision [n] numpy, cls_used [n], stride [n]) in the reference's output order."""
         dev = ops.default_device()
-        per_img = self._vectors_per_stride(results)
+        per_img = self._vectors_per_stride(results) if per_img is None else per_img
         counts = [int(len(res.boxes.cls)) for res in results]
         n = sum(sum(len(ix) for ix, _ in ps) for ps in per_img)
         dist = np.zeros(n, np.float32)
@@ -856,8 +886,22 @@ class DistanceMethod(OODMethod):
             order = np.argsort(cl_src, kind="stable")            # rows grouped by class = K2 segments
             x = torch.cat(srcs[s]).index_select(0, torch.from_numpy(order).to(dev))
             cl = cl_src[order]
-            dim = int(x.shape[1])
             seg_off = np.searchsorted(cl, np.arange(nc + 1)).tolist()
+            if self.embeds_vectors:
+                # the learned embedding of every (class used, stride) segment that has clusters; other rows score 1000
+                live = [c for c in range(nc) if seg_off[c + 1] > seg_off[c] and len(self._clusters[c][s]) > 0]
+                emb = None
+                if live:
+                    xin = torch.cat([x[seg_off[c]:seg_off[c + 1]] for c in live])
+                    part = self._transform_device(xin, live, [seg_off[c + 1] - seg_off[c] for c in live], s)
+                    emb = torch.zeros((x.shape[0], part.shape[1]), dtype=torch.float32, device=dev)
+                    pos = 0
+                    for c in live:
+                        m_c = seg_off[c + 1] - seg_off[c]
+                        emb[seg_off[c]:seg_off[c + 1]] = part[pos:pos + m_c]
+                        pos += m_c
+                x = emb if emb is not None else torch.zeros((x.shape[0], 4), dtype=torch.float32, device=dev)
+            dim = int(x.shape[1])
             cent_rows, row_off, kk = [], [], []
             for c in range(nc):
                 a = self._cluster_rows(c, s, dim)
@@ -898,6 +942,9 @@ class DistanceMethod(OODMethod):
         if len(results) == 0:
             return dict(counts=[], dist=np.zeros(0, np.float32), argmin=np.zeros(0, np.int32), decision=np.zeros(0, np.uint8),
                         cls_used=np.zeros(0, np.int64), stride=np.zeros(0, np.int64))
+        if self.which_internal_activations == 'ftmaps_and_strides' and self.embeds_vectors:
+            counts, dist, dec, cls_used, stride_of = self._vector_scores(results, per_img=self._pooled_per_stride(results))
+            return dict(counts=counts, dist=dist, argmin=None, decision=dec, cls_used=cls_used, stride=stride_of)
         if self.which_internal_activations == 'ftmaps_and_strides':
             batch, table, out = self._fused_scores(results)
             m = self._metric_slot
@@ -1031,16 +1078,28 @@ class DistanceMethod(OODMethod):
                     all_activations[c][s] = np.concatenate(fix, axis=0)
 
     # -- fit: segment packing shared by clusters / scores
-    def _stride_segments(self, tensors, s: int, min_len: int, device):
-        """Classes whose stride-s segment has more than `min_len` rows -> (classes, sizes, x [sum, D] device)."""
+    def _stride_segments(self, tensors, s: int, min_len: int, device, group=None):
+        """Classes whose stride-s segment has more than `min_len` rows -> (classes, sizes, x [sum, D] device).
+        Sharded fit (`group`): every class is listed on every rank, also with 0 local rows (a class without samples on
+        a stride, or a rank whose shard of it is empty); the row length is agreed on across the ranks so that a rank
+        without any row still takes part in the collectives with a [0, D] matrix."""
         classes, sizes, parts = [], [], []
         for c, per_cls in enumerate(tensors):
             a = per_cls[s] if s < len(per_cls) else []
             if len(a) > min_len:
                 classes.append(c)
                 sizes.append(int(len(a)))
-                parts.append(_to_device_f32(_rows_2d(a), device))
-        x = torch.cat(parts) if parts else None
+                if len(a):
+                    parts.append(_to_device_f32(_rows_2d(a), device))
+        dim = int(parts[0].shape[1]) if parts else 0
+        if group is not None:
+            t = torch.tensor([dim], dtype=torch.int64, device=device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=group)
+            dim = int(t.item())
+        if parts:
+            x = torch.cat(parts)
+        else:
+            x = torch.zeros((0, dim), dtype=torch.float32, device=device) if (classes and dim) else None
         return classes, sizes, x
 
     def _transform_device(self, x: Tensor, classes, sizes, stride_idx: int) -> Tensor:
@@ -1057,34 +1116,41 @@ class DistanceMethod(OODMethod):
         t1 = time.perf_counter()
         if not (self.per_class and self.per_stride):
             raise NotImplementedError("Not implemented yet")
-        if self._agg_name != 'mean':
-            raise NotImplementedError("agg_method='median' is not available on the GPU path")
+        median = self._agg_name == 'median'                # np.median over the members (ood_utils.py:1481-1483, :2306, :2365)
+        if median and group is not None:
+            raise NotImplementedError("agg_method='median' needs every member row of a cluster on one rank: fit it unsharded")
         method = self.cluster_method
         k = kmeans_k(method)
         if method not in ('one', 'all', 'KMeans') and k is None:
             raise NotImplementedError(f"cluster_method '{method}' is a CPU-library clusterer outside the GPU hot path")
-        if method == 'KMeans' and group is not None:
-            raise NotImplementedError("the searched 'KMeans' runs on one GPU per (class, stride) segment; shard the classes instead")
         if k is not None and k < 2:
             raise ValueError("The number of clusters must be greater than 1")
         dev = ops.default_device()
         clusters = [[np.empty(0) for _ in range(3)] for _ in range(len(ind_tensors))]
         min_samples = CUSTOM_HYP.clusters.MIN_SAMPLES
         for s in range(3):
-            classes, sizes, x = self._stride_segments(ind_tensors, s, min_samples if group is None else -1, dev)
+            classes, sizes, x = self._stride_segments(ind_tensors, s, min_samples if group is None else -1, dev, group)
             if group is not None:
                 classes, sizes, x = self._drop_small_global(classes, sizes, x, min_samples, group)
-            if not classes:
+            if not classes or x is None:
                 continue
             x = self._transform_device(x, classes, sizes, s)
+            if method == 'KMeans' and group is not None:
+                # the searched fit needs all pair distances of a segment on one GPU: the segments are dealt out to the ranks
+                self._searched_kmeans_sharded(x, classes, sizes, s, clusters, group, logger, median)
+                continue
             if method == 'all':
                 host = x.cpu().numpy()
                 off = np.concatenate([[0], np.cumsum(sizes)])
                 for i, c in enumerate(classes):
                     clusters[c][s] = host[off[i]:off[i + 1]].copy()
                 continue
+            gsizes = self._global_sizes(sizes, dev, group)
+            ordered = dict(reduce="ordered", global_sizes=gsizes, rot=classes) if (group is not None and self.fit_reduce == "ordered") else {}
+            agg = (lambda xx, ss, ll, kk, gg: _kmeans.member_medians(xx, ss, ll, kk)) if median else \
+                (lambda xx, ss, ll, kk, gg: _kmeans.member_means(xx, ss, ll, kk, group=gg, **(ordered if gg is not None else {})))
             if method == 'one':
-                means, counts = _kmeans.member_means(x, sizes, None, 1, group=group)
+                means, counts = agg(x, sizes, None, 1, group)
             elif method == 'KMeans':
                 # number of clusters searched per segment (cluster_utils.py:75-80, :203-356): labels of the best k
                 off = np.concatenate([[0], np.cumsum(sizes)])
@@ -1092,12 +1158,11 @@ class DistanceMethod(OODMethod):
                                                                    self.cluster_optimization_metric, logger)[0]
                           for i in range(len(classes))]
                 kmax = max(CUSTOM_HYP.clusters.RANGE_OF_CLUSTERS)
-                means, counts = _kmeans.member_means(x, sizes, torch.cat(labels), kmax, group=None)
+                means, counts = agg(x, sizes, torch.cat(labels), kmax, None)
             else:
-                gsizes = self._global_sizes(sizes, dev, group)
                 world, rank = (torch.distributed.get_world_size(group), torch.distributed.get_rank(group)) if group is not None else (1, 0)
-                res = self._kmeans_fit(x, sizes, gsizes, k, world, rank, group)
-                means, counts = _kmeans.member_means(x, sizes, res.labels, k, group=group)
+                res = self._kmeans_fit(x, sizes, gsizes, k, world, rank, group, classes)
+                means, counts = agg(x, sizes, res.labels, k, group)
             means, counts = means.cpu().numpy(), counts.cpu().numpy()
             for i, c in enumerate(classes):
                 present = counts[i] > 0                      # `sorted(set(labels))`: empty clusters have no centroid
@@ -1111,6 +1176,43 @@ class DistanceMethod(OODMethod):
         x_ = str(timedelta(seconds=time.perf_counter() - t1)).split(':')
         logger.info(f'Clusters generated in {x_[0]} Hours, {x_[1]} Minutes {x_[2]} Seconds')
         return clusters
+
+    def _searched_kmeans_sharded(self, x, classes, sizes, s, clusters, group, logger, median):
+        """cluster_method='KMeans' with row-sharded input: the rows of every segment are all-gathered (rank-major = the
+        row order of `kmeans.shard_rows`), segment i is searched and aggregated on rank i % world exactly like the
+        single-process fit, and the small per-segment centroid arrays are exchanged."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = x.device
+        t = torch.tensor(sizes, dtype=torch.int64, device=dev)
+        all_sizes = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(all_sizes, t, group=group)
+        all_sizes = [[int(v) for v in a.cpu()] for a in all_sizes]
+        max_local = max(sum(a) for a in all_sizes)
+        pad = torch.zeros((max_local, x.shape[1]), dtype=torch.float32, device=dev)
+        pad[:x.shape[0]] = x
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+        mine = {}
+        kmax = max(CUSTOM_HYP.clusters.RANGE_OF_CLUSTERS)
+        for i, c in enumerate(classes):
+            if i % world != rank:
+                continue
+            parts = []
+            for r in _kmeans.ranks_in_row_order(c, world):   # rows of class c in row order (rotation key = class index)
+                o = sum(all_sizes[r][:i])
+                parts.append(bufs[r][o:o + all_sizes[r][i]])
+            xi = torch.cat(parts).contiguous()
+            lab = _cluster_utils.search_number_of_clusters(xi, self.metric, self.cluster_optimization_metric, logger)[0]
+            fn = _kmeans.member_medians if median else _kmeans.member_means
+            means, counts = fn(xi, [int(xi.shape[0])], lab, kmax)
+            means, counts = means.cpu().numpy(), counts.cpu().numpy()
+            mine[c] = means[0][counts[0] > 0].copy()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        for part in gathered:
+            for c, arr in part.items():
+                clusters[c][s] = arr
 
     @staticmethod
     def _global_sizes(sizes, dev, group):
@@ -1131,10 +1233,13 @@ class DistanceMethod(OODMethod):
         parts = [x[off[i]:off[i + 1]] for i in keep]
         return [classes[i] for i in keep], [sizes[i] for i in keep], (torch.cat(parts) if parts else None)
 
-    def _kmeans_fit(self, x, sizes, gsizes, k, world, rank, group):
+    def _kmeans_fit(self, x, sizes, gsizes, k, world, rank, group, classes=None):
+        """Sharded fit: rank r must hold the rows `kmeans.shard_rows([n_c], world, r, rot=[c])` of class c (per stride):
+        the rotation key of a segment is its CLASS index, so the split does not depend on which classes are dropped."""
         if world == 1:
             return _kmeans.kmeans_fit_predict_single(x, sizes, k, random_state=10)
-        return _kmeans.kmeans_fit_sharded(x, sizes, gsizes, k, world, rank, group, random_state=10)
+        return _kmeans.kmeans_fit_sharded(x, sizes, gsizes, k, world, rank, group, random_state=10, rot=classes,
+                                          reduce=self.fit_reduce)
 
     def generate_one_cluster_per_class_and_stride(self, ind_tensors, clusters_per_class_and_stride, logger):
         """In-place form kept for API compatibility (ood_utils.py:2297-2314)."""
@@ -1247,74 +1352,100 @@ class CosineDistanceOneClusterPerStride(_PairwiseDistanceClustersPerClassPerStri
 
 
 class _DimensionalityReductionMethod(_PairwiseDistanceClustersPerClassPerStride):
-    """SDR methods (ood_utils.py:2433-2571): vectors are embedded by a trained per-(class, stride) reducer and scored
-    WITHOUT L2 normalisation.  Training the reducer (ivis / umap, CPU / TensorFlow libraries) is outside the hot path:
-    supply fitted reducers through `set_reducers` -- `reducers[cls][stride]` is a callable or an object with
-    `.transform(ndarray [n, C]) -> ndarray [n, d]`.  The scoring of the embedded vectors runs on the GPU (K2)."""
+    """SDR methods (ood_utils.py:2433-2571): the pooled vector is embedded by a trained reducer and scored WITHOUT L2
+    normalisation of the embedding.  Training the reducer (ivis / umap: CPU / TensorFlow libraries) is outside the hot
+    path: supply fitted reducers through `set_reducers` -- either one per stride (`reducers[stride]`, what the
+    reference trains, :2486-2492, :2526-2536) or one per (class, stride) (`reducers[cls][stride]`); a reducer is a
+    callable or an object with `.transform(ndarray [n, C]) -> ndarray [n, d]`.  Pooling (K1), the normalisation the
+    ivis methods apply BEFORE the embedding (:2542-2548) and the scoring of the embedded vectors (K2) run on the GPU;
+    the reducer itself runs wherever its library runs."""
 
-    normalize_activations = False
+    normalize_activations = False          # the embedded vectors are scored as they are
+    normalize_before_reduce = False        # ivis: sklearn normalize() of the pooled vector before the embedding
+    embeds_vectors = True
 
     def __init__(self, **kwargs):
         super().__init__(**kwargs)
         self.reducers = None
+        self.is_dimensionality_reduction_trained = False
 
     def set_reducers(self, reducers) -> None:
         self.reducers = reducers
+        self.is_dimensionality_reduction_trained = reducers is not None
 
     def train_dimensionality_reduction_module(self, activations, logger):
         raise NotImplementedError("training the SDR reducer (ivis / umap) is outside the GPU hot path; fit it with the "
                                   "reference tooling and pass it through set_reducers()")
 
-    def _reduce(self, a: np.ndarray, cls_idx: int, stride_idx: int) -> np.ndarray:
-        if self.reducers is None:
+    def generate_clusters(self, ind_tensors, logger: Logger, group=None):
+        if not self.is_dimensionality_reduction_trained:           # ood_utils.py:2450-2456
+            self.train_dimensionality_reduction_module(ind_tensors, logger)
+            self.is_dimensionality_reduction_trained = True
+        return super().generate_clusters(ind_tensors, logger, group=group)
+
+    def _reducer(self, cls_idx: int, stride_idx: int):
+        r = self.reducers
+        if r is None:
             raise RuntimeError(f"{self.name}: no reducers set (see set_reducers)")
-        r = self.reducers[cls_idx][stride_idx]
+        per_stride = len(r) == 3 and not isinstance(r[0], (list, tuple))
+        return r[stride_idx] if per_stride else r[cls_idx][stride_idx]
+
+    def _reduce(self, a: np.ndarray, cls_idx: int, stride_idx: int) -> np.ndarray:
+        r = self._reducer(cls_idx, stride_idx)
         out = r.transform(a) if hasattr(r, "transform") else r(a)
         return np.ascontiguousarray(out, dtype=np.float32)
 
     def activations_transformation(self, activations, cls_idx: int = None, stride_idx: int = None, **kwargs):
-        a = _np(_rows_2d(activations)).astype(np.float32)
-        return self._reduce(a, cls_idx, stride_idx)
+        a = _rows_2d(activations)
+        if self.normalize_before_reduce:
+            a = ops.normalize_rows(_to_device_f32(a, ops.default_device()))
+        return self._reduce(_np(a).astype(np.float32), cls_idx, stride_idx)
 
     def _transform_device(self, x, classes, sizes, stride_idx):
+        if self.normalize_before_reduce:
+            x = ops.normalize_rows(x)
         host = x.cpu().numpy()
         off = np.concatenate([[0], np.cumsum(sizes)])
         parts = [self._reduce(host[off[i]:off[i + 1]], c, stride_idx) for i, c in enumerate(classes)]
         return torch.from_numpy(np.concatenate(parts)).to(x.device)
 
     def _fused_scores(self, results):
-        raise NotImplementedError("SDR methods embed the pooled vector with a learned reducer between pooling and scoring; "
-                                  "use which_internal_activations='roi_aligned_ftmaps' style scoring via score_vectors()")
+        raise NotImplementedError("SDR methods embed the pooled vector between pooling and scoring: score_results() pools "
+                                  "(K1), embeds and scores (K2) instead of the fused pass")
 
     def score_vectors(self, vectors: np.ndarray, cls_idx: int, stride_idx: int) -> np.ndarray:
-        """Distances of already-pooled vectors of one (class, stride): reduce on the host, score on the GPU."""
+        """Distances of already-pooled vectors of one (class, stride): embed, then score on the GPU."""
         return self.compute_distance(self._clusters[cls_idx][stride_idx], self.activations_transformation(
             vectors, cls_idx=cls_idx, stride_idx=stride_idx))
 
 
 class UmapMethod(_DimensionalityReductionMethod):
+    """name / metric as in the reference (ood_utils.py:2476-2478)."""
     def __init__(self, **kwargs):
-        super().__init__(name='Umap', metric=kwargs.pop('metric', 'l2'), **kwargs)
+        kwargs.pop('metric', None)
+        super().__init__(name='CosineDistancePerStride', metric='cosine', **kwargs)
 
 
 class _IvisMethodPairwiseDistance(_DimensionalityReductionMethod):
+    normalize_before_reduce = True         # ood_utils.py:2542-2548
+
     def __init__(self, metric, name, **kwargs):
         super().__init__(name=name, metric=metric, **kwargs)
 
 
 class IvisMethodCosine(_IvisMethodPairwiseDistance):
     def __init__(self, **kwargs):
-        super().__init__('cosine', 'CosineIvis', **kwargs)
+        super().__init__('cosine', 'IvisCosineDistancePerStride', **kwargs)
 
 
 class IvisMethodL1(_IvisMethodPairwiseDistance):
     def __init__(self, **kwargs):
-        super().__init__('l1', 'L1Ivis', **kwargs)
+        super().__init__('manhattan', 'IvisL1DistancePerStride', **kwargs)
 
 
 class IvisMethodL2(_IvisMethodPairwiseDistance):
     def __init__(self, **kwargs):
-        super().__init__('l2', 'L2Ivis', **kwargs)
+        super().__init__('euclidean', 'IvisL2DistancePerStride', **kwargs)
 
 
 class ActivationsExtractor(DistanceMethod):
@@ -1638,7 +1769,7 @@ def compute_ood_decisions_fused(methods: Sequence[OODMethod], results, logger, l
                 mte, mto = m._temperatures()
                 te = mte if m._slot == ops.LOGIT_SLOT['Energy'] else te
                 to = mto if m._slot == ops.LOGIT_SLOT['ODIN'] else to
-                mask |= 1 << m._slot
+                mask |= m._method_mask()           # carries Sigmoid's post-sigmoid flag (use_values_before_sigmoid=False)
             lres_out = ops.logit_score(logits, cls, mask, t_energy=te, t_odin=to, thr=thr, smin=smin, smax=smax,
                                        clip=CUSTOM_HYP.fusion.CLIP_FUSION_SCORES)
     # (3) + (4)

@@ -19,6 +19,7 @@ METRIC_SLOT = {"l1": 0, "manhattan": 0, "cityblock": 0, "l2": 1, "euclidean": 1,
 LOGIT_SLOT = {"MSP": 0, "Energy": 1, "ODIN": 2, "Sigmoid": 3, "MaxLogit": 4}
 FUSE_SLOT = {"and": 0, "or": 1, "majority_voting": 2}
 N_LOGIT = 5
+LOGIT_FLAG_POST_SIGMOID = 0x100      # OR-ed into method_mask: Sigmoid slot = input value (inputs are post-sigmoid)
 
 
 def _stream() -> C.c_void_p:
@@ -588,15 +589,20 @@ TC_SCORE_MIN_ROWS = 4096      # below this the FP32 kernel's single launch wins 
 
 def vec_score_one(x: torch.Tensor, seg_off: Sequence[int], cent: torch.Tensor, cent_unit: Optional[torch.Tensor],
                   cent_row_off: Sequence[int], cent_k: Sequence[int], slot: int, normalize: bool = True,
-                  thr: Optional[torch.Tensor] = None):
-    """One metric of K2 on pooled vectors: 'l2' / 'cosine' go to the tensor-core kernel (vec_score_tc) when the shape
-    fits (D % 32 == 0, 128 <= D <= 2048, <= 64 centroids per segment, >= TC_SCORE_MIN_ROWS rows; OODB200_VEC_TC=0
-    disables), everything else to the FP32 kernel.  Same return value as vec_score."""
+                  thr: Optional[torch.Tensor] = None, tensor_core: Optional[bool] = None):
+    """One metric of K2 on pooled vectors.  Default: the FP32 kernel (csrc/fit_kernels.cu::vec_score_fast_kernel), whose
+    per-lane accumulation and reduction tree are those of the fused per-box scorer -- distances that feed a threshold
+    (fit) and distances compared with it (decisions) come from ONE arithmetic.  `tensor_core=True` (or
+    OODB200_VEC_TC=1 when the argument is None) sends 'l2' / 'cosine' to the tcgen05 kernel (vec_score_tc) when the
+    shape fits (D % 32 == 0, 128 <= D <= 2048, <= 64 centroids per segment, >= TC_SCORE_MIN_ROWS rows): the 1e-3 tier of
+    BASELINE.json, meant for the K = 64 dense-contraction case (C5).  Same return value as vec_score."""
     import os
     name = {v: k for k, v in METRIC_SLOT.items()}[slot]
     n, dim = int(x.shape[0]), int(x.shape[1])
-    if (name in ("l2", "cosine") and n >= TC_SCORE_MIN_ROWS and dim % 32 == 0 and 128 <= dim <= 2048
-            and max(list(cent_k) + [0]) <= 64 and os.environ.get("OODB200_VEC_TC", "1") != "0"):
+    if tensor_core is None:
+        tensor_core = os.environ.get("OODB200_VEC_TC", "0") == "1"
+    if (tensor_core and name in ("l2", "cosine") and n >= TC_SCORE_MIN_ROWS and dim % 32 == 0 and 128 <= dim <= 2048
+            and max(list(cent_k) + [0]) <= 64):
         xs = normalize_rows(x) if normalize else x
         return vec_score_tc(xs, seg_off, cent_unit if name == "cosine" else cent, cent_row_off, cent_k, name, thr=thr)
     return vec_score(x, seg_off, cent, cent_unit, cent_row_off, cent_k, 1 << slot, normalize=normalize, thr=thr)

@@ -52,7 +52,7 @@ def segment_select(scores: torch.Tensor, seg_off: Sequence[int], ranks: Sequence
     backend = backend or _CudaHist()
     dev = scores.device
     n_seg = len(seg_off) - 1
-    distributed = group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+    distributed = group is not None                    # explicit: a local selection inside an initialised job stays local
     scores = scores.contiguous()
     want = np.array([-1 if r is None else int(r) for r in ranks], dtype=np.int64)
     prefix = np.zeros(n_seg, dtype=np.uint32)

@@ -137,7 +137,26 @@ class NumpyBackend:
                 out[g] += p[b]
         return torch.from_numpy(out)
 
-    def update(self, sums, counts, cent, seg_k, active):
+    def converge(self, n_changed, shift, n_empty, tol_abs, cnts, k, active, state, counts, any_active):
+        """kmeans.cu::kmeans_converge_kernel: retire converged segments, count iterations (in place)."""
+        chg, sh, ne, tol = n_changed.numpy(), shift.numpy(), n_empty.numpy(), tol_abs.numpy()
+        act, st, cn, cs = active.numpy(), state.numpy(), counts.numpy(), cnts.numpy()
+        any_ = 0
+        for g in range(act.shape[0]):
+            if not act[g]:
+                continue
+            st[0, g] += 1
+            st[3, g] += ne[g]
+            cn[g] = cs[g]
+            if chg[g] == 0:
+                st[1, g], act[g] = 1, 0
+            elif float(sh[g]) <= tol[g]:
+                st[2, g], act[g] = 1, 0
+            else:
+                any_ = 1
+        any_active.numpy()[0] = any_
+
+    def update(self, sums, counts, cent, seg_k, active, out=None):
         s, c, old = sums.numpy(), counts.numpy(), cent.numpy()
         new = old.copy()
         n_seg, k, _ = old.shape

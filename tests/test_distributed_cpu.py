@@ -94,7 +94,7 @@ def test_sharded_kmeans_equals_single_process(two_rank_run, single_run):
     for mode in ("allreduce", "ordered"):
         parts = []
         for g, n in enumerate(SIZES):                       # re-assemble global row order from the two row shards
-            for r in range(2):
+            for r in kmeans.ranks_in_row_order(g, 2):
                 a, cnt = kmeans.shard_rows(SIZES, 2, r)[g]
                 loc_off = np.concatenate([[0], np.cumsum([c for _, c in kmeans.shard_rows(SIZES, 2, r)])])
                 parts.append(two_rank_run[r][f"labels_{mode}"][loc_off[g]:loc_off[g] + cnt])
@@ -139,7 +139,7 @@ def test_block_table_is_rank_count_invariant():
         owned = [kmeans.shard_rows(SIZES, world, r) for r in range(world)]
         for g, n in enumerate(SIZES):
             pos = 0
-            for r in range(world):                           # contiguous, ordered, complete cover of every segment
+            for r in kmeans.ranks_in_row_order(g, world):    # contiguous, ordered (rotating owner), complete cover of every segment
                 a, cnt = owned[r][g]
                 assert a == pos or cnt == 0
                 pos += cnt
@@ -161,7 +161,7 @@ def test_device_seeding_control_flow_matches_host_seeding():
     assert np.allclose(a.centers.numpy(), b.centers.numpy(), rtol=0, atol=1e-6)
 
 
-SMALL = [9000, 5000, 12]                   # one super-block per segment: with two ranks, rank 0 owns NO row at all
+SMALL = [3000, 0, 2500]                    # one super-block per live segment, both owned by rank 1 (rotating ownership): rank 0 owns NO row
 
 
 def _worker_empty_rank(rank: int, world: int, port: int, outdir: str):
@@ -169,7 +169,7 @@ def _worker_empty_rank(rank: int, world: int, port: int, outdir: str):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         be = NumpyBackend()
-        segs = [synth.blob_vectors(40 + i, n, DIM, K, 7.0)[0] for i, n in enumerate(SMALL)]
+        segs = [synth.blob_vectors(40 + i, n, DIM, K, 7.0)[0] if n else np.zeros((0, DIM), np.float32) for i, n in enumerate(SMALL)]
         shard = kmeans.shard_rows(SMALL, world, rank)
         local = [s[a:a + n] for s, (a, n) in zip(segs, shard)]
         x = torch.from_numpy(np.concatenate(local).reshape(-1, DIM))
@@ -188,7 +188,7 @@ def test_a_rank_without_rows_takes_part_in_the_fit():
         mp.spawn(_worker_empty_rank, args=(2, _free_port(), d), nprocs=2, join=True)
         out = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(2)]
     assert int(out[0]["rows"]) == 0 and int(out[1]["rows"]) == sum(SMALL)
-    segs = [synth.blob_vectors(40 + i, n, DIM, K, 7.0)[0] for i, n in enumerate(SMALL)]
+    segs = [synth.blob_vectors(40 + i, n, DIM, K, 7.0)[0] if n else np.zeros((0, DIM), np.float32) for i, n in enumerate(SMALL)]
     single = kmeans.kmeans_fit_predict_single(torch.from_numpy(np.concatenate(segs)), SMALL, K, backend=NumpyBackend())
     assert len(out[0]["labels"]) == 0
     assert np.array_equal(out[1]["labels"], single.labels.numpy())

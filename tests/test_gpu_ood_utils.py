@@ -304,6 +304,41 @@ def test_logits_methods(ou, golden):
     np.testing.assert_array_equal(ml.compute_scores(torch.from_numpy(g["logits"]), g["cls"]), g["logits"].max(1))
 
 
+def test_sigmoid_on_post_sigmoid_values_fused_and_per_method(ou, golden):
+    """`use_values_before_sigmoid=False` (ood_utils.py:1438-1439): the hooked values already went through the detector's
+    sigmoid, the Sigmoid score is the value itself.  The fused multi-method pass must decide exactly like the per-method
+    call for both flag values."""
+    g = golden("golden_logits.npz")
+    from ood_in_object_detection_b200.results import Results, batch_shape
+    n = g["n_boxes"]
+    cls = split(g["cls"], n)
+    for before in (True, False):
+        vals = g["logits"] if before else torch.sigmoid(torch.from_numpy(g["logits"])).numpy()
+        rows = split(vals, n)
+        results = []
+        for i in range(len(n)):
+            b6 = np.zeros((len(cls[i]), 6), np.float32)
+            b6[:, 5] = cls[i]
+            results.append(Results(orig_img=batch_shape(len(n), 640, 640), boxes=torch.from_numpy(b6),
+                                   extra_item=torch.from_numpy(np.ascontiguousarray(rows[i]))))
+        kw = dict(LOGIT_KW, use_values_before_sigmoid=before)
+        sg, msp = ou.Sigmoid(**kw), ou.MSP(**kw)
+        sc = sg.compute_scores(torch.from_numpy(vals), g["cls"])
+        want = torch.sigmoid(torch.from_numpy(g["logits"])).numpy()[np.arange(len(g["cls"])), g["cls"].astype(int)]
+        if before:
+            np.testing.assert_allclose(sc, want, rtol=RTOL)
+        else:
+            np.testing.assert_array_equal(sc, want)          # the reference returns the stored value (:1443)
+        sg.thresholds = [float(np.median(sc))] * int(g["nc"])
+        msp.thresholds = [0.5] * int(g["nc"])
+        fused = ou.compute_ood_decisions_fused([sg, msp], results, LOG)
+        assert list(fused) == ["MSP", "MSP#1"]                # Sigmoid's name is 'MSP' in the reference too
+        assert fused["MSP"] == sg.compute_ood_decision_on_results(results, LOG)
+        assert fused["MSP#1"] == msp.compute_ood_decision_on_results(results, LOG)
+        flat = np.array([v for d in fused["MSP"] for v in d])
+        assert 0 < flat.sum() < len(flat)
+
+
 def test_fusion_rules(ou, golden):
     g = golden("golden_fusion.npz")
     n = g["n"]
