@@ -162,9 +162,8 @@ def device_maps(wl, seed, device):
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     out = []
-    for c, hw in zip(wl.channels, wl.map_hw):
-        u = torch.randint(0, 65536, (wl.batch, c, hw, hw), device=device, generator=g).to(torch.float64) / 65536.0
-        out.append((7.0 * u ** 4 - 0.27).to(torch.float32).contiguous())
+    for c, hw in zip(wl.channels, wl.map_hw):          # x = silu(1.2 * randn), fp32 NCHW contiguous
+        out.append(torch.nn.functional.silu(1.2 * torch.randn((wl.batch, c, hw, hw), device=device, generator=g)).contiguous())
     return out
 
 
@@ -212,24 +211,55 @@ def fit_tables(ops, wl, maps, seed, device):
     return clusters, thr, table, lthr
 
 
-def fit_data(n_total, world, rank, device, seed=77):
-    """C3-shaped fit set: FIT_CLASSES segments of unit-norm vectors, a mixture of FIT_K well-separated Gaussians per class
-    (strict convergence in a few Lloyd iterations).  Rank r generates exactly the rows kmeans.shard_rows gives it."""
+FIT_VARIANTS = {
+    # "separated": mixture of FIT_K Gaussians, centre spread 6 sigma*sqrt(D): strict convergence in a few Lloyd iterations;
+    #              carries the bit-exact-labels claim.
+    # "realistic": normalize(silu(1.2 * (low-rank signal + noise))) -- a continuous 8-dimensional structure like pooled
+    #              post-SiLU activations, no separable blobs: sklearn needs 200-300 iterations on it, max_iter = 100 caps
+    #              every segment at 100 (50-100 iterations); carries the throughput number.
+    "separated": dict(sep=6.0, max_iter=300),
+    "realistic": dict(rank=8, noise=0.3, max_iter=100),
+}
+
+
+def fit_segment_rows(c, a, cnt, device, variant, seed=77):
+    """Rows [a, a + cnt) of class c of the C3-shaped fit set (unit-norm float32 vectors).  Generated per 4096-row unit from
+    a seed of (class, unit): the data set does not depend on how many ranks share it."""
+    import torch
+    from ood_in_object_detection_b200 import kmeans
+    unit = kmeans.BLOCK_ROWS * kmeans.SUPER_BLOCKS
+    cfg = FIT_VARIANTS[variant]
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 1000 + c)
+    if variant == "separated":
+        centers = torch.randn((FIT_K, FIT_D), device=device, generator=g) * cfg["sep"] / FIT_D ** 0.5 + 1.0 / FIT_D ** 0.5
+    else:
+        basis = torch.randn((cfg["rank"], FIT_D), device=device, generator=g) / cfg["rank"] ** 0.5
+    parts = []
+    u0, u1 = a // unit, ((a + cnt + unit - 1) // unit if cnt else a // unit)
+    for u in range(u0, u1):
+        g2 = torch.Generator(device=device)
+        g2.manual_seed((seed * 100000 + c) * 4096 + u)
+        if variant == "separated":
+            lab = torch.randint(0, FIT_K, (unit,), device=device, generator=g2)
+            xu = centers[lab] + torch.randn((unit, FIT_D), device=device, generator=g2) / FIT_D ** 0.5
+        else:
+            z = torch.randn((unit, cfg["rank"]), device=device, generator=g2)
+            xu = torch.nn.functional.silu(1.2 * (z @ basis + cfg["noise"] * torch.randn((unit, FIT_D), device=device, generator=g2)))
+        lo, hi = max(a, u * unit) - u * unit, min(a + cnt, (u + 1) * unit) - u * unit
+        parts.append(xu[lo:hi])
+    x = torch.cat(parts) if parts else torch.zeros((0, FIT_D), device=device)
+    return x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)
+
+
+def fit_data(n_total, world, rank, device, seed=77, variant="separated"):
+    """C3-shaped fit set: FIT_CLASSES segments.  Rank r generates exactly the rows kmeans.shard_rows gives it."""
     import torch
     from ood_in_object_detection_b200 import kmeans
     per = n_total // FIT_CLASSES
     sizes = [per] * FIT_CLASSES
     shard = kmeans.shard_rows(sizes, world, rank)
-    parts = []
-    for c, (a, cnt) in enumerate(shard):
-        g = torch.Generator(device=device)
-        g.manual_seed(seed * 1000 + c)
-        centers = torch.randn((FIT_K, FIT_D), device=device, generator=g) * 6.0 / FIT_D ** 0.5 + 1.0 / FIT_D ** 0.5
-        g2 = torch.Generator(device=device)
-        g2.manual_seed(seed * 100000 + c * 64 + rank)
-        lab = torch.randint(0, FIT_K, (cnt,), device=device, generator=g2)
-        x = centers[lab] + torch.randn((cnt, FIT_D), device=device, generator=g2) / FIT_D ** 0.5
-        parts.append(x / x.norm(dim=1, keepdim=True))
+    parts = [fit_segment_rows(c, a, cnt, device, variant, seed) for c, (a, cnt) in enumerate(shard)]
     return torch.cat(parts).contiguous(), sizes, [cnt for _, cnt in shard]
 
 
@@ -252,21 +282,54 @@ def cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, images):
     return sum(len(det["boxes"][i]) for i in images), dt
 
 
-def cpu_fit_baseline(n=40000):
-    """sklearn KMeans(K=16, random_state=10) -- the call behind cluster_utils.py:62-73 -- on one bounded segment."""
+def _best_label_agreement(a, b, k):
+    """Share of rows on which two clusterings agree after the best one-to-one relabelling (Hungarian on the contingency
+    table), and the adjusted Rand index."""
+    from scipy.optimize import linear_sum_assignment
+    from sklearn.metrics import adjusted_rand_score
+    tab = np.zeros((k, k), np.int64)
+    np.add.at(tab, (a, b), 1)
+    r, c = linear_sum_assignment(-tab)
+    return float(tab[r, c].sum() / len(a)), float(adjusted_rand_score(a, b))
+
+
+def cpu_fit_baseline(n=40000, variant="separated", device=None):
+    """sklearn KMeans(K=16, random_state=10) -- the call behind cluster_utils.py:62-73 -- on one bounded segment (class 0 of
+    the bench's fit set, first n rows).  With `device`: the same segment through the GPU fit as well, and its agreement /
+    ARI / inertia against sklearn next to sklearn's own 1-thread vs all-threads noise floor (its E-step BLAS summation
+    order depends on the thread count)."""
     import torch
     from sklearn.cluster import KMeans
-    rng = np.random.default_rng(5)
-    centers = rng.standard_normal((FIT_K, FIT_D)).astype(np.float32) * 6.0 / FIT_D ** 0.5 + 1.0 / FIT_D ** 0.5
-    x = centers[rng.integers(0, FIT_K, n)] + rng.standard_normal((n, FIT_D)).astype(np.float32) / FIT_D ** 0.5
-    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    max_iter = FIT_VARIANTS[variant]["max_iter"]
+    if device is not None:
+        x = fit_segment_rows(0, 0, n, device, variant).cpu().numpy()
+    else:                                                # reference arm on a box without touching the GPU
+        x = fit_segment_rows(0, 0, n, torch.device("cpu"), variant).numpy()
     t0 = time.perf_counter()
-    km = KMeans(n_clusters=FIT_K, random_state=10).fit(x)
+    km = KMeans(n_clusters=FIT_K, random_state=10, max_iter=max_iter).fit(x)
     dt = time.perf_counter() - t0
-    return {"value": n * km.n_iter_ / dt, "unit": FIT_UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"sklearn KMeans(n_clusters={FIT_K}, random_state=10).fit on one segment of {n} x {FIT_D} vectors "
-                      f"({km.n_iter_} Lloyd iterations, {dt:.2f} s incl. k-means++ seeding)",
-            "e2e_vectors_per_s": n / dt}
+    out = {"value": n * km.n_iter_ / dt, "unit": FIT_UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+           "sample": f"sklearn KMeans(n_clusters={FIT_K}, random_state=10, max_iter={max_iter}).fit (the call of "
+                     f"cluster_utils.py:62-73) on one '{variant}' segment of {n} x {FIT_D} vectors "
+                     f"({km.n_iter_} Lloyd iterations, {dt:.2f} s incl. k-means++ seeding)",
+           "e2e_vectors_per_s": n / dt, "variant": variant}
+    if device is not None:
+        import threadpoolctl
+        from ood_in_object_detection_b200 import kmeans
+        with threadpoolctl.threadpool_limits(limits=1):
+            km1 = KMeans(n_clusters=FIT_K, random_state=10, max_iter=max_iter).fit(x)
+        r = kmeans.kmeans_fit_predict_single(torch.from_numpy(x).to(device), [n], FIT_K, random_state=10, max_iter=max_iter)
+        lab = r.labels.cpu().numpy()
+        cent = r.centers.cpu().numpy()[0]
+        inertia = float(((x.astype(np.float64) - cent[lab].astype(np.float64)) ** 2).sum())
+        agree, ari = _best_label_agreement(lab, km.labels_, FIT_K)
+        agree0, ari0 = _best_label_agreement(km1.labels_, km.labels_, FIT_K)
+        out["parity"] = {"gpu_vs_sklearn": {"label_agreement": agree, "ari": ari, "inertia_ratio": inertia / float(km.inertia_),
+                                            "n_iter_gpu": int(r.n_iter[0]), "n_iter_sklearn": int(km.n_iter_)},
+                         "sklearn_1_thread_vs_all_threads": {"label_agreement": agree0, "ari": ari0,
+                                                            "inertia_ratio": float(km1.inertia_) / float(km.inertia_),
+                                                            "n_iter": [int(km1.n_iter_), int(km.n_iter_)]}}
+    return out
 
 
 def run_reference(args, wl):
@@ -287,13 +350,13 @@ def run_reference(args, wl):
     except Exception:                                               # the pools keep their environment defaults
         _limits = None
     if args.workload == "fit":
-        vals = [cpu_fit_baseline() for _ in range(max(args.steps, 1))]
+        vals = [cpu_fit_baseline(variant=args.fit_variant) for _ in range(max(min(args.steps, 3), 1))]
         v = float(np.mean([x["value"] for x in vals]))
         cb = dict(vals[-1], value=v)
         print(json.dumps({"impl": "reference", "metric": FIT_METRIC, "value": v, "unit": FIT_UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "C3 k-means fit (bounded CPU sample)", "dim": FIT_D, "k": FIT_K},
+                          "config": {"workload": f"C3 k-means fit ('{args.fit_variant}' set, bounded CPU sample)", "dim": FIT_D, "k": FIT_K},
                           "cpu_baseline": cb, "e2e": {"value": v, "unit": FIT_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     n_img = CPU_SAMPLE_IMAGES
@@ -325,14 +388,70 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------------------ fit arm
-def run_fit(device, world, rank, n_total, reps, warm):
+def _fit_once(x, gsizes, lsizes, world, rank, group, max_iter, reduce="allreduce"):
+    """seed + Lloyd + member means + fit scores + exact thresholds of the C3-shaped set (the fit stage of ood_utils)."""
+    from ood_in_object_detection_b200 import kmeans, ops, select
+    if world > 1:
+        r = kmeans.kmeans_fit_sharded(x, lsizes, gsizes, FIT_K, world, rank, group, random_state=10, max_iter=max_iter, reduce=reduce)
+    else:
+        r = kmeans.kmeans_fit_predict_single(x, gsizes, FIT_K, random_state=10, max_iter=max_iter, reduce=reduce)
+    kw = dict(reduce="ordered", global_sizes=gsizes) if reduce == "ordered" else {}
+    means, counts = kmeans.member_means(x, lsizes, r.labels, FIT_K, group=group, **kw)
+    off = np.concatenate([[0], np.cumsum(lsizes)]).tolist()
+    d, _ = ops.vec_score_one(x, off, means.reshape(-1, FIT_D).contiguous(), None, [g * FIT_K for g in range(FIT_CLASSES)],
+                             [FIT_K] * FIT_CLASSES, ops.METRIC_SLOT["l2"], normalize=False)      # FP32: the decision path's arithmetic
+    ranks = [select.lower_index(n, 95.0) for n in gsizes]
+    thr, _, _ = select.segment_select(d[ops.METRIC_SLOT["l2"]].contiguous(), off, ranks, group=group)
+    return r, means, thr
+
+
+def verify_against_single_gpu(device, world, rank, n_total, variant):
+    """SURVEY.md section 4 (iii) on hardware: the N-rank fit (reduce="ordered") against the same fit on ONE GPU (rank 0
+    holds the whole set): labels identical on every rank's rows, centres / member means / thresholds bit-equal."""
+    import torch
+    import torch.distributed as dist
+    from ood_in_object_detection_b200 import kmeans
+    max_iter = FIT_VARIANTS[variant]["max_iter"]
+    x, gsizes, lsizes = fit_data(n_total, world, rank, device, variant=variant)
+    group = dist.group.WORLD
+    r, means, thr = _fit_once(x, gsizes, lsizes, world, rank, group, max_iter, reduce="ordered")
+    del x
+    full = torch.empty(n_total, dtype=torch.int32, device=device)
+    same = torch.zeros(3, dtype=torch.int32, device=device)
+    if rank == 0:
+        x1, _, _ = fit_data(n_total, 1, 0, device, variant=variant)
+        r1, means1, thr1 = _fit_once(x1, gsizes, gsizes, 1, 0, None, max_iter, reduce="ordered")
+        del x1
+        full.copy_(r1.labels)
+        same[0] = int(torch.equal(r1.centers, r.centers))
+        same[1] = int(torch.equal(means1, means))
+        same[2] = int(all((a == b) or (a is None and b is None) for a, b in zip(thr, thr1)))
+        iters1 = [int(v) for v in r1.n_iter]
+    dist.broadcast(full, src=0)
+    dist.broadcast(same, src=0)
+    goff = np.concatenate([[0], np.cumsum(gsizes)])
+    shard = kmeans.shard_rows(gsizes, world, rank)
+    mine = torch.cat([full[int(goff[g]) + a:int(goff[g]) + a + cnt] for g, (a, cnt) in enumerate(shard)])
+    bad = (mine != r.labels).sum().to(torch.int64)
+    dist.all_reduce(bad)
+    torch.cuda.empty_cache()
+    out = {"labels_differing": int(bad), "centres_bit_equal": bool(same[0]), "member_means_bit_equal": bool(same[1]),
+           "thresholds_bit_equal": bool(same[2]), "reduce": "ordered", "variant": variant, "n_vectors": n_total,
+           "lloyd_iterations": max(int(v) for v in r.n_iter)}
+    if rank == 0:
+        out["lloyd_iterations_single_gpu"] = max(iters1)
+    out["matches"] = out["labels_differing"] == 0 and all(out[k] for k in ("centres_bit_equal", "member_means_bit_equal", "thresholds_bit_equal"))
+    return out
+
+
+def run_fit(device, world, rank, n_total, reps, warm, variant="realistic"):
     """Segmented k-means fit + thresholds; returns a dict (rank-0 meaningful).  The Lloyd loop and the seeding are timed
     inside kmeans_fit (device synchronised on both sides); the end-to-end figure is the wall clock around the whole fit
     (seeding has host decisions), max over ranks."""
     import torch
     import torch.distributed as dist
-    from ood_in_object_detection_b200 import kmeans, ops, select
-    x, gsizes, lsizes = fit_data(n_total, world, rank, device)
+    x, gsizes, lsizes = fit_data(n_total, world, rank, device, variant=variant)
+    max_iter = FIT_VARIANTS[variant]["max_iter"]
     group = dist.group.WORLD if world > 1 else None
     best = None
     for it in range(warm + reps):
@@ -340,41 +459,42 @@ def run_fit(device, world, rank, n_total, reps, warm):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        if world > 1:
-            r = kmeans.kmeans_fit_sharded(x, lsizes, gsizes, FIT_K, world, rank, group, random_state=10)
-        else:
-            r = kmeans.kmeans_fit_predict_single(x, gsizes, FIT_K, random_state=10)
-        means, counts = kmeans.member_means(x, lsizes, r.labels, FIT_K, group=group)
-        off = np.concatenate([[0], np.cumsum(lsizes)]).tolist()
-        d, _ = ops.vec_score_one(x, off, means.reshape(-1, FIT_D).contiguous(), None, [g * FIT_K for g in range(FIT_CLASSES)],
-                                 [FIT_K] * FIT_CLASSES, ops.METRIC_SLOT["l2"], normalize=False)     # tcgen05 cross-term (K2b)
-        ranks = [select.lower_index(n, 95.0) for n in gsizes]
-        thr, _, _ = select.segment_select(d[ops.METRIC_SLOT["l2"]].contiguous(), off, ranks, group=group)
+        r, means, thr = _fit_once(x, gsizes, lsizes, world, rank, group, max_iter)
         torch.cuda.synchronize()
         total = time.perf_counter() - t0
         t = torch.tensor([total, r.seconds["lloyd"], r.seconds["init"], r.seconds["center"]], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         cur = dict(total=float(t[0]), lloyd=float(t[1]), init=float(t[2]), center=float(t[3]), seeding=r.seconds.get("seeding"),
-                   iters=int(r.seconds["lloyd_iters"]),
+                   iters=int(r.seconds["lloyd_iters"]), issued=int(r.seconds.get("lloyd_issued", 0)),
                    n_iter=[int(v) for v in r.n_iter], strict=all(r.strict), thr0=thr[0])
         if it >= warm and (best is None or cur["total"] < best["total"]):
             best = cur
+    rows = torch.tensor([x.shape[0]], dtype=torch.int64, device=device)
+    rows_max = rows.clone()
+    if world > 1:
+        dist.all_reduce(rows_max, op=dist.ReduceOp.MAX)
+    del x
+    torch.cuda.empty_cache()
     peak, _ = _peaks()
     it_bytes = 4.0 * n_total * FIT_D + 4.0 * n_total + 2 * 4.0 * FIT_CLASSES * FIT_K * FIT_D
+    # vector-iterations actually computed: segments that converged early drop out of the later iterations
+    vec_iters = float(sum(n * i for n, i in zip(gsizes, best["n_iter"])))
     lloyd_per_iter = best["lloyd"] / max(best["iters"], 1)
-    return {"metric": FIT_METRIC, "value": n_total * best["iters"] / best["lloyd"], "unit": FIT_UNIT,
+    return {"metric": FIT_METRIC, "value": vec_iters / best["lloyd"], "unit": FIT_UNIT, "variant": variant,
             "n_vectors": n_total, "dim": FIT_D, "k": FIT_K, "segments": FIT_CLASSES, "lloyd_iterations": best["iters"],
+            "lloyd_iterations_per_segment": best["n_iter"], "lloyd_iterations_issued": best["issued"],
             "lloyd_ms_per_iteration": 1e3 * lloyd_per_iter, "seed_ms": 1e3 * best["init"], "seeding": best["seeding"],
             "center_ms": 1e3 * best["center"],
             "means_scores_thresholds_ms": 1e3 * (best["total"] - best["init"] - best["lloyd"] - best["center"]),
-            "fit_ms": 1e3 * best["total"],
+            "fit_ms": 1e3 * best["total"], "rows_on_fullest_rank": int(rows_max),
             "e2e_vectors_per_s": n_total / best["total"], "strict_convergence": best["strict"], "scaling": "strong",
             "collective": "1 all-reduce per Lloyd iteration + 1 per radix pass" if world > 1 else "none (1 GPU)",
             "roofline": {"bound": "hbm", "kernel": "kmeans_step_tc_kernel (tcgen05 assignment + partial sums; + reduce/update, host loop)",
                          "unit": "GB/s",
-                         "achieved": it_bytes / world / lloyd_per_iter / 1e9, "peak": peak,
-                         "frac": it_bytes / world / lloyd_per_iter / 1e9 / peak, "algorithmic_bytes_per_iteration": it_bytes,
+                         "achieved": it_bytes * (vec_iters / n_total / max(best["iters"], 1)) / world / lloyd_per_iter / 1e9, "peak": peak,
+                         "frac": it_bytes * (vec_iters / n_total / max(best["iters"], 1)) / world / lloyd_per_iter / 1e9 / peak,
+                         "algorithmic_bytes_per_iteration": it_bytes,
                          "traffic": (_traffic("C3", "kmeans_step_dram_bytes_per_vector") or 0) * n_total / world or None}}
 
 
@@ -395,14 +515,16 @@ def run_ours(args, wl):
     clk = ClockSampler(local).start()
 
     if args.workload == "fit":
-        fit = run_fit(device, world, rank, args.fit_n or 4_000_000, max(args.steps, 1), max(args.warmup, 1))
+        fit = run_fit(device, world, rank, args.fit_n or 4_000_000, max(min(args.steps, 5), 1), 1, variant=args.fit_variant)
+        if world > 1:
+            fit["matches_single_gpu"] = verify_against_single_gpu(device, world, rank, args.fit_n or 4_000_000, args.fit_variant)
         clk.stop()
         if rank == 0:
-            cb = cpu_fit_baseline()
+            cb = cpu_fit_baseline(variant=args.fit_variant, device=device)
             out = {"metric": FIT_METRIC, "value": fit["value"], "unit": FIT_UNIT, "n_gpus": world, "steps": args.steps,
                    "warmup": args.warmup, "ms_per_step": fit["fit_ms"], "higher_is_better": True, "scaling": "strong",
                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                   "config": {"workload": f"C3 k-means fit N={fit['n_vectors']} D={FIT_D} K={FIT_K} x {FIT_CLASSES} classes",
+                   "config": {"workload": f"C3 k-means fit N={fit['n_vectors']} D={FIT_D} K={FIT_K} x {FIT_CLASSES} classes, '{args.fit_variant}' set",
                               "sharding": f"rows of every segment over {world} rank(s)"},
                    "roofline": fit["roofline"], "cpu_baseline": cb, "fit": fit,
                    "e2e": {"value": fit["e2e_vectors_per_s"], "unit": "vectors/s (seed + Lloyd + member means + scores + thresholds)",
@@ -580,9 +702,16 @@ def run_ours(args, wl):
     if args.fit_n != 0:
         del h_maps, res_f, res_l
         torch.cuda.empty_cache()
-        # default size: 2 M vectors, and at least one 16 384-row super-block of every segment per rank (the fit shards whole
-        # super-blocks: with fewer of them than ranks some ranks would own nothing)
-        fit = run_fit(device, world, rank, args.fit_n or max(2_000_000, FIT_CLASSES * 16384 * world), 2, 1)
+        # BASELINE config 3 at its full size on every N (strong scaling: 4 M x 576, K = 16 x 20 classes): the 'realistic' set
+        # (tens of Lloyd iterations) carries the throughput and scaling figures, the 'separated' set the bit-exact-labels claim
+        n_fit = args.fit_n or 4_000_000
+        fit = run_fit(device, world, rank, n_fit, 2, 1, variant="realistic")
+        fit["separated"] = run_fit(device, world, rank, n_fit, 2, 1, variant="separated")
+        if world > 1:
+            fit["matches_single_gpu"] = verify_against_single_gpu(device, world, rank, n_fit, "separated")
+            fit["matches_single_gpu_realistic"] = verify_against_single_gpu(device, world, rank, n_fit, "realistic")
+        if rank == 0:
+            fit["cpu_baseline"] = cpu_fit_baseline(variant="realistic", device=device)
     clk.stop()
 
     if rank == 0:
@@ -637,8 +766,10 @@ def main():
     ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"],
                     help="memory layout of the synthetic feature maps: nchw = what the reference's hooks hand over (default), "
                          "nhwc = torch.channels_last; the other layout is timed beside it (roofline.other_layout)")
-    ap.add_argument("--fit-n", type=int, default=None, help="vectors of the k-means sub-measurement (0: skip; default 2 M, "
-                    "4 M for --workload fit)")
+    ap.add_argument("--fit-n", type=int, default=None, help="vectors of the k-means fit (0: skip the sub-measurement; default 4 M = "
+                    "BASELINE config 3, the same on every N)")
+    ap.add_argument("--fit-variant", default="realistic", choices=list(FIT_VARIANTS),
+                    help="--workload fit / --impl reference --workload fit: which C3 set (SURVEY.md section 8d)")
     ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the e2e, fit and cpu_baseline legs (tuning sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

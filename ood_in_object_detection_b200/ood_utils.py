@@ -1146,9 +1146,10 @@ class DistanceMethod(OODMethod):
                     clusters[c][s] = host[off[i]:off[i + 1]].copy()
                 continue
             gsizes = self._global_sizes(sizes, dev, group)
-            ordered = dict(reduce="ordered", global_sizes=gsizes, rot=classes) if (group is not None and self.fit_reduce == "ordered") else {}
+            # fit_reduce="ordered": the rank-count-invariant reduction, ALSO in a single process (same bits for 1/2/4/8 ranks)
+            ordered = dict(reduce="ordered", global_sizes=gsizes, rot=classes) if self.fit_reduce == "ordered" else {}
             agg = (lambda xx, ss, ll, kk, gg: _kmeans.member_medians(xx, ss, ll, kk)) if median else \
-                (lambda xx, ss, ll, kk, gg: _kmeans.member_means(xx, ss, ll, kk, group=gg, **(ordered if gg is not None else {})))
+                (lambda xx, ss, ll, kk, gg: _kmeans.member_means(xx, ss, ll, kk, group=gg, **(ordered if gg is group else {})))
             if method == 'one':
                 means, counts = agg(x, sizes, None, 1, group)
             elif method == 'KMeans':
@@ -1237,7 +1238,7 @@ class DistanceMethod(OODMethod):
         """Sharded fit: rank r must hold the rows `kmeans.shard_rows([n_c], world, r, rot=[c])` of class c (per stride):
         the rotation key of a segment is its CLASS index, so the split does not depend on which classes are dropped."""
         if world == 1:
-            return _kmeans.kmeans_fit_predict_single(x, sizes, k, random_state=10)
+            return _kmeans.kmeans_fit_predict_single(x, sizes, k, random_state=10, reduce=self.fit_reduce)
         return _kmeans.kmeans_fit_sharded(x, sizes, gsizes, k, world, rank, group, random_state=10, rot=classes,
                                           reduce=self.fit_reduce)
 

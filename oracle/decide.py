@@ -31,12 +31,14 @@ def _has_cluster(clusters, c, s):
 
 
 def distance_decisions(images, clusters, thresholds, metric, compat_q1=True, normalize=True,
-                       return_details=False):
+                       return_details=False, transform=None):
     """-> List[List[int]] (1 = InD, 0 = OoD), per image in the reference's (stride-major) order.
 
     compat_q1=False gives the evidently intended behaviour: class of the box being scored,
     decisions returned in box order.
     With return_details also returns per-image lists of (distance, argmin, cls_used, stride, box_idx).
+    transform(x [1, C], cls, stride) -> [1, d]: the `activations_transformation` of the SDR methods (:2501-2571, e.g.
+    normalise -> trained embedding for ivis :2542-2548); replaces the plain row normalisation (:2404-2409).
     """
     decisions, details = [], []
     for im in images:
@@ -54,7 +56,10 @@ def distance_decisions(images, clusters, thresholds, metric, compat_q1=True, nor
                     dist, arg = 1000, -1                                                       # :2159-2164
                 else:
                     x = v.reshape(1, -1)
-                    x = D.normalize_rows(x) if normalize else x.astype(F32)                    # :2169 -> :2409
+                    if transform is not None:
+                        x = np.asarray(transform(x, c, s), dtype=F32)                          # :2169 -> SDR override
+                    else:
+                        x = D.normalize_rows(x) if normalize else x.astype(F32)                # :2169 -> :2409
                     pw = D.pairwise(clusters[c][s], x, metric)
                     dist, arg = pw.min(axis=0)[0], int(pw.argmin(axis=0)[0])                   # :2166-2170
                 thr = thresholds[c][s] if c < len(thresholds) else []

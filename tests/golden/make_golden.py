@@ -440,14 +440,141 @@ def golden_eul_rank(ref):
     print("golden_eul_rank", store["l2_matrix"].shape, np.round(store["l2_entropy"], 4).tolist())
 
 
+def golden_c4(ref):
+    """BASELINE config 4 shapes (YOLOv8l maps 256/512/512 @ 80/40/20, K = 10 per (class, stride)) through the reference's own
+    classes: the vanilla Cosine method with `KMeans_10`, an SDR method (IvisMethodCosine: normalise -> 32-d embedding ->
+    un-normalised scoring, ood_utils.py:2501-2571; the trained ivis model is replaced by the fixed projection
+    tests/helpers.py::Projection, the rest is the reference's code), MSP, `fusion-MSP-Cosine_cl_stride` with and / or /
+    score (fuse_ood_decisions over the two methods' own outputs, :2942-2975), and the EUL ranking of 3 unknown proposals
+    per image against all classes (:1031-1084 statements, as in golden_eul_rank)."""
+    import torchvision.ops as t_ops
+    from scipy.stats import entropy
+    from tests.helpers import Projection
+    ou = ref.ood_utils
+    nc, img, k = 8, 640, 10
+    wl = synth.Workload("C4-shaped YOLOv8l K=10", "l", img, 4, nc, k, 50)
+    ch, hw, seed = wl.channels, wl.map_hw, 4400
+    train_maps = synth.feature_maps(seed, 3, ch, hw)
+    train_det = synth.detections(seed + 1, 3, img, nc, 300, fixed=True)
+    test_maps = synth.feature_maps(seed + 2, wl.batch, ch, hw)
+    test_det = synth.detections(seed + 3, wl.batch, img, nc, wl.lam)
+    acts = _collect_activations(ref, train_maps, train_det, img, nc)
+    results = _images(ref, test_maps, test_det, img)
+    store = dict(seed=seed, img=img, batch=wl.batch, nc=nc, k=k, channels=np.array(ch),
+                 n_boxes=np.array([len(b) for b in test_det["boxes"]]),
+                 boxes=_cat(test_det["boxes"], F32).reshape(-1, 4), cls=_cat(test_det["cls"], F32),
+                 strides=_cat(test_det["strides"], F32), conf=_cat(test_det["conf"], F32),
+                 logits=np.concatenate(test_det["logits"], 0),
+                 train_cls=_cat(train_det["cls"], F32), train_logits=np.concatenate(train_det["logits"], 0))
+    kw = dict(ref_shim.DIST_KW, cluster_method=f"KMeans_{k}")
+    cos = ou.CosineDistanceOneClusterPerStride(**kw)
+    ivis = ou.IvisMethodCosine(**kw)
+    ivis.ivis = [Projection(900 + s, ch[s], 32) for s in range(3)]
+    ivis.is_dimensionality_reduction_trained = True
+    for tag, m in (("cos", cos), ("ivis", ivis)):
+        m.clusters = m.generate_clusters(acts, LOG)
+        scores = m.compute_scores_from_activations(acts, LOG)
+        m.thresholds = m.generate_thresholds(scores, 0.95, LOG)
+        dec = m.compute_ood_decision_on_results(results, LOG)
+        dist, cls_used, stride_of, box_of = _ref_distances_q1(ref, m, results)
+        _pack_nested(f"{tag}_clusters", m.clusters, store)
+        _pack_nested(f"{tag}_thr", m.thresholds, store)
+        store[f"{tag}_decisions"] = _cat(dec, np.int8)
+        store[f"{tag}_dist"] = _cat(dist, np.float64)
+        store[f"{tag}_cls_used"] = _cat(cls_used, np.int32)
+        store[f"{tag}_stride_of"] = _cat(stride_of, np.int32)
+    # MSP on the same detections
+    boxes6 = [torch.from_numpy(np.concatenate([test_det["boxes"][i], test_det["conf"][i][:, None], test_det["cls"][i][:, None]], 1))
+              for i in range(wl.batch)]
+    results_l = ref_shim.make_results(ref, None, boxes6, logits=[torch.from_numpy(z) for z in test_det["logits"]],
+                                      batch_hw=(img, img), n_batch=wl.batch)
+    msp = ou.MSP(**ref_shim.LOGIT_KW)
+    tl, tc = store["train_logits"], store["train_cls"]
+    lacts = [torch.from_numpy(tl[tc == c]) if (tc == c).any() else torch.tensor([]) for c in range(nc)]
+    lscores = msp.compute_scores_from_activations(lacts, LOG)
+    msp.thresholds = msp.generate_thresholds(lscores, 0.95, LOG)
+    store["msp_thr"] = np.asarray(msp.thresholds, np.float64)
+    store["msp_min"], store["msp_max"] = np.asarray(msp.min_score, np.float64), np.asarray(msp.max_score, np.float64)
+    d_msp = msp.compute_ood_decision_on_results(results_l, LOG)
+    d_cos = cos.compute_ood_decision_on_results(results, LOG)
+    store["msp_decisions"] = _cat(d_msp, np.int8)
+    common = dict(iou_threshold_for_matching=0.5, min_conf_threshold_train=0.15, min_conf_threshold_test=0.15)
+    for strat in ("and", "or", "score"):
+        thr_pair = (msp.thresholds, cos.thresholds)
+        f = ou.FusionMethod(msp, cos, strat, fusion_method_name="fusion-MSP-Cosine_cl_stride", cluster_method=f"KMeans_{k}", **common)
+        f.thresholds = thr_pair                              # the constructor resets both methods' thresholds (OODMethod.__init__, :89)
+        if strat == "score":                                 # :2958-2975: INDness of both methods, summed, > 0 = InD
+            a = msp.compute_INDness_scores_on_results(results_l, LOG)
+            b = cos.compute_INDness_scores_on_results(results, LOG)
+            store["msp_indness"], store["cos_indness"] = _cat(a, np.float64), _cat(b, np.float64)
+        else:
+            a, b = d_msp, d_cos
+        store[f"fusion_{strat}"] = _cat(f.fuse_ood_decisions(a, b), np.int8)
+    # EUL: 3 unknown proposals per image on the stride-1 map, ranked against every class (cosine clusters above)
+    rng = np.random.default_rng(seed + 9)
+    W = hw[1]
+    x1, y1 = rng.uniform(-1, W - 4, (wl.batch, 3)), rng.uniform(-1, W - 4, (wl.batch, 3))
+    props = np.stack([x1, y1, x1 + rng.uniform(0.5, 12, (wl.batch, 3)), y1 + rng.uniform(0.5, 12, (wl.batch, 3))], -1).astype(F32)
+    store["eul_props"] = props
+    mats = []
+    for i in range(wl.batch):
+        feats = t_ops.roi_align(input=torch.from_numpy(test_maps[1][i]).unsqueeze(0), boxes=[torch.from_numpy(props[i]).float()],
+                                output_size=(1, 1), spatial_scale=1.0, aligned=False)
+        dpp = np.array([cos.compute_distance(cl[1], cos.activations_transformation(feats, cls_idx=c, stride_idx=1))
+                        for c, cl in enumerate(cos.clusters) if len(cl[1]) > 0])
+        mats.append(dpp.astype(np.float64))
+    store["eul_matrix"] = np.stack(mats)                      # [image, classes with clusters, proposal]
+    store["eul_entropy"] = np.stack([entropy(m / m.sum(axis=0), axis=0) for m in mats])
+    store["eul_min"] = np.stack([m.min(axis=0) * 100 for m in mats])
+    np.savez_compressed(os.path.join(OUT, "golden_c4.npz"), **store)
+    print("golden_c4 boxes", int(store["n_boxes"].sum()), "InD frac cos / ivis / msp",
+          float(store["cos_decisions"].mean()), float(store["ivis_decisions"].mean()), float(store["msp_decisions"].mean()),
+          "fusion and/or/score", [float(store[f"fusion_{s}"].mean()) for s in ("and", "or", "score")])
+
+
+def golden_bigfit(ref):
+    """Segments with >= 4096 rows through the reference's fit (generate_clusters with KMeans_5 -> member means,
+    compute_scores_from_activations, generate_thresholds) for L1 / L2 / Cosine: pins the fit-time scores at the sizes where
+    K2 used to switch to the tensor-core kernel.  The activations are regenerated from the seeds (synth.blob_vectors)."""
+    ou = ref.ood_utils
+    spec = {(0, 0): (71, 6000, 128), (1, 1): (72, 4500, 256), (1, 0): (73, 4096, 128), (2, 2): (74, 40, 160)}
+    acts = [[np.empty(0) for _ in range(3)] for _ in range(3)]
+    store = dict(spec=np.array([[c, s, sd, n, d] for (c, s), (sd, n, d) in spec.items()]))
+    for (c, s), (sd, n, d) in spec.items():
+        acts[c][s] = np.abs(synth.blob_vectors(sd, n, d, 5, 7.0, unit_norm=False)[0])[:, :, None, None]   # 5 separated blobs for KMeans_5
+    for tag, cls in (("l1", ou.L1DistanceOneClusterPerStride), ("l2", ou.L2DistanceOneClusterPerStride),
+                     ("cos", ou.CosineDistanceOneClusterPerStride)):
+        m = cls(**dict(ref_shim.DIST_KW, cluster_method="KMeans_5"))
+        m.clusters = m.generate_clusters(acts, LOG)
+        scores = m.compute_scores_from_activations(acts, LOG)
+        thr = m.generate_thresholds(scores, 0.95, LOG)
+        _pack_nested(f"{tag}_clusters", m.clusters, store)
+        _pack_nested(f"{tag}_scores", [[np.asarray(v, F32) for v in row] for row in scores], store)
+        _pack_nested(f"{tag}_thr", thr, store)
+        _pack_nested(f"{tag}_mindist", m.min_dist, store)
+        _pack_nested(f"{tag}_maxdist", m.max_dist, store)
+    np.savez_compressed(os.path.join(OUT, "golden_bigfit.npz"), **store)
+    print("golden_bigfit ok", {k: float(np.asarray(store[k])) for k in ("l2_thr_0_0", "cos_thr_1_1")})
+
+
 def main():
+    global OUT
+    if "--out" in sys.argv:                                  # regenerate into another directory (tests/test_live_reference.py)
+        OUT = sys.argv[sys.argv.index("--out") + 1]
+        os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
+    if "--only-c4" in sys.argv:
+        return golden_c4(ref)
+    if "--only-bigfit" in sys.argv:
+        return golden_bigfit(ref)
     if "--only-eul" in sys.argv:
         return golden_eul_rank(ref)
     if "--only-matching" in sys.argv:
         return golden_matching(ref)
     if "--only-ksearch" in sys.argv:
         return golden_ksearch(ref)
+    golden_c4(ref)
+    golden_bigfit(ref)
     golden_ksearch(ref)
     golden_eul_rank(ref)
     golden_matching(ref)

@@ -48,3 +48,16 @@ def train_case(g):
     maps = synth.feature_maps(seed, B, ch, hw)
     n = g["train_n_boxes"]
     return maps, split(g["train_boxes"], n), split(g["train_cls"], n), split(g["train_strides"], n)
+
+
+class Projection:
+    """Fixed stand-in for a TRAINED dimensionality reducer (ivis / umap model) of the SDR methods: tanh of a seeded random
+    projection to `d_out` dimensions.  Used on both sides of the C4 golden (the reference's IvisMethodCosine and ours)."""
+
+    def __init__(self, seed: int, d_in: int, d_out: int = 32):
+        rng = np.random.default_rng(seed)
+        self.w = (rng.standard_normal((d_in, d_out)) * (4.0 / np.sqrt(d_in))).astype(np.float64)
+
+    def transform(self, a) -> np.ndarray:
+        a = np.asarray(a, dtype=np.float64).reshape(len(a), -1)
+        return np.tanh(a @ self.w).astype(np.float32)

@@ -442,3 +442,103 @@ def test_unknown_proposal_ranking(ou, golden):
         np.testing.assert_allclose(m.rank_unknown_proposals(cl, g["props"], s, operation="sum"), g[f"{tag}_sum"],
                                    rtol=1e-5, atol=1e-6)
     assert len(m.rank_unknown_proposals(fm, np.zeros((0, 4), np.float32), s)) == 0
+
+
+def test_c4_shaped_methods_through_the_classes(ou, golden):
+    """BASELINE config 4 (YOLOv8l maps 256/512/512, K = 10) against golden_c4.npz, frozen from the reference's classes:
+    vanilla Cosine, the SDR path of IvisMethodCosine (pool -> normalise -> supplied 32-d reducer -> un-normalised
+    scoring, decided on Results), MSP, fusion-MSP-Cosine_cl_stride with and / or / score, EUL ranking of 3 proposals per
+    image against all classes."""
+    from ood_in_object_detection_b200.results import Results, batch_shape
+    from ood_in_object_detection_b200 import synth
+    from tests.helpers import Projection
+    g = golden("golden_c4.npz")
+    nc, img, B, k = int(g["nc"]), int(g["img"]), int(g["batch"]), int(g["k"])
+    ch = tuple(int(c) for c in g["channels"])
+    maps = synth.feature_maps(int(g["seed"]) + 2, B, ch, tuple(img // s for s in synth.STRIDES))
+    n = g["n_boxes"]
+    boxes, cls, strides, logit = split(g["boxes"], n), split(g["cls"], n), split(g["strides"], n), split(g["logits"], n)
+    results = _results(maps, boxes, cls, strides, img)
+    results_l = []
+    for i in range(B):
+        b6 = np.concatenate([boxes[i], np.full((len(boxes[i]), 1), 0.5, np.float32), cls[i][:, None]], 1).astype(np.float32)
+        results_l.append(Results(orig_img=batch_shape(B, img, img), boxes=torch.from_numpy(b6), extra_item=torch.from_numpy(logit[i])))
+    kw = dict(DIST_KW, cluster_method=f"KMeans_{k}")
+    cos, ivis = ou.CosineDistanceOneClusterPerStride(**kw), ou.IvisMethodCosine(**kw)
+    assert ivis.name == "IvisCosineDistancePerStride" and ivis.metric == "cosine"
+    ivis.set_reducers([Projection(900 + s, ch[s], 32) for s in range(3)])          # one reducer per stride, like the reference
+    flat = lambda d: np.array([v for im in d for v in im], np.int8)
+    dec = {}
+    for tag, m in (("cos", cos), ("ivis", ivis)):
+        m.clusters = unpack_nested(g, f"{tag}_clusters", nc)
+        m.thresholds = unpack_nested(g, f"{tag}_thr", nc, as_threshold=True)
+        r = m.score_results(results)
+        np.testing.assert_allclose(r["dist"], g[f"{tag}_dist"], rtol=RTOL, atol=5e-7)
+        assert np.array_equal(r["cls_used"], g[f"{tag}_cls_used"]) and np.array_equal(r["stride"], g[f"{tag}_stride_of"])
+        d = m.compute_ood_decision_on_results(results, LOG)
+        assert [len(v) for v in d] == [int(v) for v in n]
+        thr_box = np.array([m.thresholds[c][s] if m.thresholds[c][s] != [] else np.inf
+                            for c, s in zip(g[f"{tag}_cls_used"], g[f"{tag}_stride_of"])])
+        near = np.abs(g[f"{tag}_dist"] - thr_box) <= RTOL * thr_box
+        assert near.sum() <= 2 and np.array_equal(flat(d)[~near], g[f"{tag}_decisions"][~near]), tag
+        dec[tag] = (d, near)
+    msp = ou.MSP(**LOGIT_KW)
+    msp.thresholds, msp.min_score, msp.max_score = g["msp_thr"].tolist(), g["msp_min"].tolist(), g["msp_max"].tolist()
+    d_msp = msp.compute_ood_decision_on_results(results_l, LOG)
+    assert np.array_equal(flat(d_msp), g["msp_decisions"])
+    near = dec["cos"][1]
+    for strat in ("and", "or", "score"):
+        thr_pair = (msp.thresholds, cos.thresholds)
+        f = ou.FusionMethod(msp, cos, strat, fusion_method_name="fusion-MSP-Cosine_cl_stride", cluster_method=f"KMeans_{k}", **COMMON)
+        f.thresholds = thr_pair
+        out = f.compute_ood_decision_on_results(results_l, LOG, results2=results)
+        assert np.array_equal(flat(out)[~near], g[f"fusion_{strat}"][~near]), strat
+    ind = msp.compute_INDness_scores_on_results(results_l, LOG)
+    np.testing.assert_allclose(np.array([v for im in ind for v in im]), g["msp_indness"], atol=1e-4)
+    # EUL: 3 proposals per image on the stride-1 map against every class that has clusters there
+    for i in range(B):
+        fm = torch.from_numpy(maps[1][i]).cuda()
+        for op, key in (("entropy", "eul_entropy"), ("min", "eul_min")):
+            ranks = cos.rank_unknown_proposals(fm, g["eul_props"][i], 1, operation=op)
+            np.testing.assert_allclose(ranks, g[key][i], rtol=2e-4 if op == "entropy" else RTOL, atol=1e-6)
+    # an SDR method fits in the embedded space too: clusters of the reference's fit have 32 columns
+    assert ivis.clusters[0][0].shape[1] == 32
+    with pytest.raises(RuntimeError):
+        ou.IvisMethodL2(**kw).activations_transformation(np.zeros((2, ch[0]), np.float32), cls_idx=0, stride_idx=0)
+
+
+def test_fit_with_segments_of_4096_rows_and_more(ou, golden):
+    """Segments of 4096 .. 6000 rows through the class surface (generate_clusters KMeans_5 -> compute_scores_from_activations ->
+    generate_thresholds) against golden_bigfit.npz from the reference: FP32 fit scores (the arithmetic of the decision
+    path) to 1e-5, and the opt-in tensor-core scorer (vec_score_one(tensor_core=True)) to its 1e-3 tier."""
+    from ood_in_object_detection_b200 import ops
+    from tests.test_oracle_vs_golden import bigfit_activations
+    g = golden("golden_bigfit.npz")
+    acts = bigfit_activations(g)
+    for tag, cls in _classes(ou):
+        m = cls(**dict(DIST_KW, cluster_method="KMeans_5"))
+        clusters = m.generate_clusters(acts, LOG)
+        for c in range(3):
+            for s in range(3):
+                ref = g[f"{tag}_clusters_{c}_{s}"]
+                assert np.asarray(clusters[c][s]).shape == ref.shape, (tag, c, s)
+                if ref.size:
+                    np.testing.assert_allclose(clusters[c][s], ref, rtol=RTOL, atol=1e-7)
+        m.clusters = unpack_nested(g, f"{tag}_clusters", 3)
+        scores = m.compute_scores_from_activations(acts, LOG)
+        thr = m.generate_thresholds(scores, 0.95, LOG)
+        for c in range(3):
+            for s in range(3):
+                ref = g[f"{tag}_scores_{c}_{s}"]
+                if ref.size:
+                    np.testing.assert_allclose(np.asarray(scores[c][s], np.float64), ref, rtol=RTOL, atol=2e-7)
+                gt = g[f"{tag}_thr_{c}_{s}"]
+                assert (thr[c][s] == [] and gt.ndim == 1) or thr[c][s] == pytest.approx(float(gt), rel=RTOL)
+        if tag in ("l2", "cos"):                            # the tcgen05 scorer on the same segments
+            for c, s in ((0, 0), (1, 1), (1, 0)):
+                x = ops.normalize_rows(torch.from_numpy(acts[c][s].reshape(len(acts[c][s]), -1)).cuda())
+                cent = torch.from_numpy(np.ascontiguousarray(m.clusters[c][s])).cuda()
+                unit = torch.from_numpy(ops._unit_rows(m.clusters[c][s])).cuda()
+                slot = ops.METRIC_SLOT["l2" if tag == "l2" else "cosine"]
+                d, _ = ops.vec_score_one(x, [0, x.shape[0]], cent, unit, [0], [cent.shape[0]], slot, normalize=False, tensor_core=True)
+                np.testing.assert_allclose(d[slot].cpu().numpy(), g[f"{tag}_scores_{c}_{s}"], rtol=1e-3, atol=2e-6)

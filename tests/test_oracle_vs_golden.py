@@ -246,3 +246,87 @@ def test_eul_proposal_ranking(golden):
             np.testing.assert_allclose(eul.fold(g[f"{tag}_matrix"], op), g[f"{tag}_{op}"], rtol=1e-6)
         mn, closest = eul.fold(g[f"{tag}_matrix"], "min", True)
         assert np.array_equal(closest, g[f"{tag}_closest"]) and np.allclose(mn, g[f"{tag}_minthr"])
+
+
+def _c4_images(g):
+    from ood_in_object_detection_b200 import synth
+    seed, img, B = int(g["seed"]), int(g["img"]), int(g["batch"])
+    ch = tuple(int(c) for c in g["channels"])
+    maps = synth.feature_maps(seed + 2, B, ch, tuple(img // s for s in synth.STRIDES))
+    n = g["n_boxes"]
+    boxes, cls, strides, logit = split(g["boxes"], n), split(g["cls"], n), split(g["strides"], n), split(g["logits"], n)
+    return [dict(maps=[m[i] for m in maps], boxes=boxes[i], cls=cls[i], strides=strides[i], logits=logit[i], img_hw=(img, img))
+            for i in range(B)], maps
+
+
+def test_c4_shaped_methods(golden):
+    """BASELINE config 4 shapes (YOLOv8l maps, K = 10): vanilla Cosine, the SDR path (normalise -> 32-d embedding ->
+    un-normalised scoring), MSP, fusion and / or / score, EUL proposal ranking -- oracle vs the reference's outputs."""
+    from oracle import eul
+    from tests.helpers import Projection
+    g = golden("golden_c4.npz")
+    nc = int(g["nc"])
+    images, maps = _c4_images(g)
+    ch = [int(c) for c in g["channels"]]
+    proj = [Projection(900 + s, ch[s], 32) for s in range(3)]
+    embed = lambda x, c, s: proj[s].transform(distance.normalize_rows(x))
+    dec = {}
+    for tag, tf in (("cos", None), ("ivis", embed)):
+        clusters = unpack_nested(g, f"{tag}_clusters", nc)
+        thr = unpack_nested(g, f"{tag}_thr", nc, as_threshold=True)
+        d, det = decide.distance_decisions(images, clusters, thr, "cosine", return_details=True, transform=tf)
+        dist = np.array([t[0] for im in det for t in im])
+        np.testing.assert_allclose(dist, g[f"{tag}_dist"], rtol=1e-5, atol=2e-7)
+        flat = np.concatenate([np.asarray(v, np.int8) for v in d])
+        thr_box = np.array([thr[c][s] if thr[c][s] != [] else np.inf for c, s in zip(g[f"{tag}_cls_used"], g[f"{tag}_stride_of"])])
+        near = np.abs(g[f"{tag}_dist"] - thr_box) <= 1e-5 * thr_box
+        assert near.sum() <= 2 and np.array_equal(flat[~near], g[f"{tag}_decisions"][~near]), tag
+        assert np.array_equal(np.array([t[2] for im in det for t in im]), g[f"{tag}_cls_used"])
+        dec[tag] = d
+        assert clusters[0][0].shape[1] == (32 if tag == "ivis" else ch[0])
+    d_msp = decide.logit_decisions(images, "MSP", g["msp_thr"], 1.0)
+    assert np.array_equal(np.concatenate([np.asarray(v, np.int8) for v in d_msp]), g["msp_decisions"])
+    cat = lambda x: np.concatenate([np.asarray(v, np.int8) for v in x])
+    d_cos = [list(v) for v in split(g["cos_decisions"], g["n_boxes"])]
+    assert np.array_equal(cat(decide.fuse(d_msp, d_cos, "and")), g["fusion_and"])
+    assert np.array_equal(cat(decide.fuse(d_msp, d_cos, "or")), g["fusion_or"])
+    ind_msp = decide.logit_indness(images, "MSP", g["msp_thr"], g["msp_min"], g["msp_max"], 1.0)
+    np.testing.assert_allclose(np.concatenate([np.asarray(v) for v in ind_msp]), g["msp_indness"], atol=1e-4)
+    ind_cos = decide.distance_indness(images, clusters=unpack_nested(g, "cos_clusters", nc),
+                                      thresholds=unpack_nested(g, "cos_thr", nc, as_threshold=True), metric="cosine")
+    assert np.all(g["cos_indness"] == -1) and all(v == -1 for row in ind_cos for v in row)       # Q2
+    assert np.array_equal(cat(decide.fuse(ind_msp, ind_cos, "score")), g["fusion_score"])
+    clusters = unpack_nested(g, "cos_clusters", nc)
+    for i in range(len(images)):
+        d = eul.distance_matrix(maps[1][i], g["eul_props"][i], clusters, 1, "cosine")
+        np.testing.assert_allclose(d, g["eul_matrix"][i], rtol=1e-5, atol=5e-7)
+        np.testing.assert_allclose(eul.fold(g["eul_matrix"][i], "entropy"), g["eul_entropy"][i], rtol=1e-6)
+        np.testing.assert_allclose(eul.fold(g["eul_matrix"][i], "min"), g["eul_min"][i], rtol=1e-6)
+
+
+def bigfit_activations(g):
+    from ood_in_object_detection_b200 import synth
+    acts = [[np.empty(0) for _ in range(3)] for _ in range(3)]
+    for c, s, sd, n, d in g["spec"]:
+        acts[int(c)][int(s)] = np.abs(synth.blob_vectors(int(sd), int(n), int(d), 5, 7.0, unit_norm=False)[0])[:, :, None, None]
+    return acts
+
+
+def test_fit_with_segments_of_4096_rows_and_more(golden):
+    """Fit on segments of 4096 .. 6000 rows (KMeans_5 -> member means -> scores -> thresholds) against the reference's
+    outputs: the sizes at which the CUDA fit scorer runs its large-input path."""
+    g = golden("golden_bigfit.npz")
+    acts = bigfit_activations(g)
+    clusters = fit.generate_clusters(acts, "KMeans_5")
+    for tag, metric in (("l1", "l1"), ("l2", "l2"), ("cos", "cosine")):
+        scores, mn, mx = fit.compute_scores_from_activations(acts, clusters, metric)
+        thr = fit.generate_thresholds(scores, 0.95, True, True)
+        for c in range(3):
+            for s in range(3):
+                ref_cl = g[f"{tag}_clusters_{c}_{s}"]
+                assert np.asarray(clusters[c][s]).shape == ref_cl.shape, (tag, c, s)
+                if ref_cl.size:
+                    np.testing.assert_allclose(clusters[c][s], ref_cl, rtol=1e-5, atol=1e-7)
+                    np.testing.assert_allclose(np.asarray(scores[c][s], np.float64), g[f"{tag}_scores_{c}_{s}"], rtol=2e-5, atol=2e-7)
+                gt = g[f"{tag}_thr_{c}_{s}"]
+                assert (thr[c][s] == [] and gt.ndim == 1) or thr[c][s] == pytest.approx(float(gt), rel=2e-5)
