@@ -18,7 +18,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_abi_version_and_error_string():
     lib = _lib.load()
-    assert lib.oodb200_abi_version() == 1
+    assert lib.oodb200_abi_version() == 2
     # argument validation happens on the host, before any launch: no GPU needed
     rc = lib.oodb200_fuse_u8(None, None, None, -1, 0, None, None)
     assert rc == -1 and b"negative" in lib.oodb200_last_error()
