@@ -264,22 +264,71 @@ def fit_data(n_total, world, rank, device, seed=77, variant="separated"):
 
 
 # ------------------------------------------------------------------------------------- CPU reference
-def cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, images):
-    """One pass of the reference's CPU path (port) over `images` (indices); returns (#boxes, seconds)."""
+_REF = {}
+
+
+def load_reference():
+    """The reference's own modules (oracle/ref_shim.py: /root/reference in the build container, the byte-compiled
+    oracle/_ref on the GPU box) or None when neither is there -- then the loop-for-loop port oracle/cpu_path.py is timed."""
+    if "ref" not in _REF:
+        _REF["ref"], _REF["shim"] = None, None
+        try:
+            from oracle import ref_shim
+            if ref_shim.available():
+                _REF["ref"], _REF["shim"] = ref_shim.load(), ref_shim
+        except Exception as e:                          # a broken compiled build must not take the bench down
+            print(f"bench: the reference could not be imported ({type(e).__name__}: {e}); timing the port", file=sys.stderr)
+    return _REF["ref"], _REF["shim"]
+
+
+def cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, images, want_decisions=False):
+    """One pass of the reference's CPU path over `images` (indices): L1 + cosine FMap decisions and MSP + Energy logit
+    decisions, per image / stride / box like ood_utils.py:2038-2180.  Runs the REFERENCE'S OWN classes when they can be
+    imported (kind "reference"), else the port.  Returns (#boxes, seconds, kind[, decisions])."""
+    import logging
     import torch
+    ref, shim = load_reference()
+    n_boxes = sum(len(det["boxes"][i]) for i in images)
+    slot = {"l1": 0, "l2": 1, "cosine": 2}
+    if ref is not None:
+        ou = ref.ood_utils
+        log = logging.getLogger("bench-ref")
+        log.setLevel(logging.CRITICAL)
+        b6 = [torch.from_numpy(np.concatenate([det["boxes"][i], det["conf"][i][:, None], det["cls"][i][:, None]], 1).astype(np.float32))
+              for i in images]
+        res_f = shim.make_results(ref, [[m[i] for m in maps_cpu] for i in images], b6,
+                                  strides=[torch.from_numpy(det["strides"][i]) for i in images], batch_hw=(wl.img, wl.img), n_batch=len(images))
+        res_l = shim.make_results(ref, None, b6, logits=[torch.from_numpy(det["logits"][i]) for i in images],
+                                  batch_hw=(wl.img, wl.img), n_batch=len(images))
+        kw = dict(shim.DIST_KW, cluster_method="KMeans_10")
+        dm = {"l1": ou.L1DistanceOneClusterPerStride(**kw), "cosine": ou.CosineDistanceOneClusterPerStride(**kw)}
+        lm = {"MSP": ou.MSP(**shim.LOGIT_KW), "Energy": ou.Energy(temper=1, **shim.LOGIT_KW)}
+        for k, m in dm.items():
+            m.clusters, m.thresholds = clusters, thr[slot[k]]
+        for k, m in lm.items():
+            m.thresholds = lthr[{"MSP": 0, "Energy": 1}[k]].tolist()
+        out = {}
+        t0 = time.perf_counter()
+        for metric in FMAP_METRICS:
+            out[metric] = dm[metric].compute_ood_decision_on_results(res_f, log)
+        for name in LOGIT_METHODS:
+            if name != "MaxLogit":                     # no reference implementation exists
+                out[name] = lm[name].compute_ood_decision_on_results(res_l, log)
+        dt = time.perf_counter() - t0
+        return (n_boxes, dt, "reference", out) if want_decisions else (n_boxes, dt, "reference")
     from oracle import cpu_path
     ims = [dict(maps=[m[i] for m in maps_cpu], boxes=torch.from_numpy(det["boxes"][i]),
                 cls=torch.from_numpy(det["cls"][i]), strides=torch.from_numpy(det["strides"][i]),
                 logits=torch.from_numpy(det["logits"][i]), img_hw=(wl.img, wl.img)) for i in images]
+    out = {}
     t0 = time.perf_counter()
     for metric in FMAP_METRICS:
-        cpu_path.distance_decisions(ims, clusters, thr[{"l1": 0, "l2": 1, "cosine": 2}[metric]], metric)
+        out[metric] = cpu_path.distance_decisions(ims, clusters, thr[slot[metric]], metric)
     for name in LOGIT_METHODS:
-        if name == "MaxLogit":
-            continue                                   # no reference implementation exists
-        cpu_path.logit_decisions(ims, name, lthr[{"MSP": 0, "Energy": 1}[name]].tolist(), 1.0)
+        if name != "MaxLogit":
+            out[name] = cpu_path.logit_decisions(ims, name, lthr[{"MSP": 0, "Energy": 1}[name]].tolist(), 1.0)
     dt = time.perf_counter() - t0
-    return sum(len(det["boxes"][i]) for i in images), dt
+    return (n_boxes, dt, "port", out) if want_decisions else (n_boxes, dt, "port")
 
 
 def _best_label_agreement(a, b, k):
@@ -360,8 +409,10 @@ def run_reference(args, wl):
                           "cpu_baseline": cb, "e2e": {"value": v, "unit": FIT_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     n_img = CPU_SAMPLE_IMAGES
-    det = synth.detections(2000, n_img, wl.img, wl.nc, wl.lam, fixed=wl.fixed_boxes)
-    maps = [torch.from_numpy(m) for m in synth.feature_maps(1000, n_img, wl.channels, wl.map_hw)]
+    det = synth.detections(2000, wl.batch, wl.img, wl.nc, wl.lam, fixed=wl.fixed_boxes)     # the GPU arm's detections (rank 0)
+    g = torch.Generator()
+    g.manual_seed(1000)
+    maps = [torch.nn.functional.silu(1.2 * torch.randn((n_img, c, hw, hw), generator=g)) for c, hw in zip(wl.channels, wl.map_hw)]
     rng = np.random.default_rng(0)
     clusters = [[np.abs(rng.standard_normal((wl.k, c))).astype(np.float32) / np.sqrt(c) for c in wl.channels]
                 for _ in range(wl.nc)]
@@ -370,20 +421,22 @@ def run_reference(args, wl):
     imgs = list(range(n_img))
     for _ in range(max(args.warmup, 1)):                # imports and thread pools are not part of the metric
         cpu_reference_pass(det, maps, wl, clusters, thr, lthr, imgs[:1])
-    tot_n, tot_t = 0, 0.0
+    tot_n, tot_t, kind = 0, 0.0, "port"
     for _ in range(args.steps):
-        n, dt = cpu_reference_pass(det, maps, wl, clusters, thr, lthr, imgs)
+        n, dt, kind = cpu_reference_pass(det, maps, wl, clusters, thr, lthr, imgs)
         tot_n += n
         tot_t += dt
     v = tot_n / tot_t
     sample = (f"{n_img} images (~{tot_n // max(args.steps, 1)} boxes) of the {wl.batch}-image batch per step; L1+cosine FMap "
-              f"and MSP+Energy logit decisions, per-box sklearn/torchvision calls as in ood_utils.py:2038-2180")
+              f"and MSP+Energy logit decisions through " + ("the reference's own compute_ood_decision_on_results (ood_utils.py:2038-2180, "
+              ":1195-1208; byte-compiled build oracle/_ref)" if kind == "reference" else "oracle/cpu_path.py (loop-for-loop port, same "
+              "sklearn/torchvision calls)"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl.name, "sample_images": n_img},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -718,9 +771,17 @@ def run_ours(args, wl):
         alg, upper, _ = algorithmic_bytes(det, wl, wl.k)
         peak, how = _peaks()
         achieved = alg / (fmap_ms * 1e-3) / 1e9
-        maps_cpu = [m[:CPU_SAMPLE_IMAGES].cpu() for m in maps]
+        maps_cpu = [m[:CPU_SAMPLE_IMAGES].contiguous(memory_format=torch.contiguous_format).cpu() for m in maps]
         cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, [0])        # warm the imports / thread pools
-        cpu_n, cpu_t = cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, list(range(CPU_SAMPLE_IMAGES)))
+        cpu_n, cpu_t, cpu_kind, cpu_dec = cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, list(range(CPU_SAMPLE_IMAGES)),
+                                                             want_decisions=True)
+        # the CPU arm's decisions on its sample against the CUDA path's decisions on the same boxes (same order: per image,
+        # stride-major for the FMap methods, box order for the logit methods)
+        n6 = sum(len(det["boxes"][i]) for i in range(CPU_SAMPLE_IMAGES))
+        flat = lambda d: np.array([v for im in d for v in im], np.uint8)
+        cpu_vs_gpu = {m: int((flat(cpu_dec[m]) != fout.decision[ops.METRIC_SLOT[m]][:n6].cpu().numpy()).sum()) for m in FMAP_METRICS}
+        cpu_vs_gpu.update({m: int((flat(cpu_dec[m]) != lout.decision[ops.LOGIT_SLOT[m]][:n6].cpu().numpy()).sum())
+                           for m in LOGIT_METHODS if m in cpu_dec})
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
@@ -739,9 +800,11 @@ def run_ours(args, wl):
                                           "note": "the same fused pass over the same values with the maps in the other memory "
                                                   "layout (channels_last = what a detector run in torch.channels_last hands over)"},
                          "note": "HBM moves whole 128-byte lines; NCHW window rows are 8..52 B (DESIGN.md section 4)"},
-            "cpu_baseline": {"value": cpu_n / cpu_t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{CPU_SAMPLE_IMAGES} of {wl.batch} images ({cpu_n} boxes), L1+cosine FMap and "
-                                       f"MSP+Energy logits through oracle/cpu_path.py (per-box sklearn/torchvision calls)"},
+            "cpu_baseline": {"value": cpu_n / cpu_t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": cpu_kind,
+                             "sample": f"{CPU_SAMPLE_IMAGES} of {wl.batch} images ({cpu_n} boxes), L1+cosine FMap and MSP+Energy logits through "
+                                       + ("the reference's own compute_ood_decision_on_results (byte-compiled build oracle/_ref)"
+                                          if cpu_kind == "reference" else "oracle/cpu_path.py (loop-for-loop port, same sklearn/torchvision calls)"),
+                             "decisions_differing_from_gpu": cpu_vs_gpu},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "ood_utils.compute_ood_decisions_fused([L1, Cosine, MSP, Energy, MaxLogit], results)",
                     "matches_resident_path": bool(same),

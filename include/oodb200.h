@@ -85,9 +85,9 @@ int oodb200_roi_pool_f32(const float* const* map_ptrs, const int32_t* map_chw, c
 /* Scratch the two pooling entry points need (device memory, 256-byte aligned, owned by the caller; its
  * contents need not be preserved between calls): Q1 plan, per-box window geometry and RoIAlign weights,
  * the item work list, the (stride, class) ordering of the score kernel and the pooled vectors [n, round4(Cmax)].
- * map_chw as in roi_pool (host); n_img = images of the batch; nc = number of classes of the centroid table (0 for
- * roi_pool).  Returns -1 when map_chw is NULL. */
-int64_t oodb200_fmap_workspace_bytes(int n, int n_img, int nc, const int32_t* map_chw);
+ * map_chw as in roi_pool (host); nc = number of classes of the centroid table (0 for roi_pool).
+ * Returns -1 when map_chw is NULL. */
+int64_t oodb200_fmap_workspace_bytes(int n, int nc, const int32_t* map_chw);
 
 /* ---- K1+K2 fused: pool -> L2-normalise -> distance to the class/stride centroids -> min ->
  *      threshold.  Replaces the per-image/per-stride/per-box loop of
@@ -99,9 +99,9 @@ int64_t oodb200_fmap_workspace_bytes(int n, int n_img, int nc, const int32_t* ma
  *   flags        OODB200_FMAP_COMPAT_Q1 = the reference's behaviour (ood_utils.py:2152-2154): the class
  *                used for the centroid / threshold lookup is the one of the box with the same IN-STRIDE index, and
  *                results are written stride-major within each image; without it: class of the box itself, box order.
- *                OODB200_FMAP_GROUP_SCORE = score the boxes by (stride, class) groups with the group's centroid rows
- *                staged in shared memory (large tables: K * C_s * 4 bytes beyond what a per-box sweep from L2 should
- *                re-read) instead of scoring every box as soon as its last channel slice has been pooled.  Same results.
+ *                OODB200_FMAP_GROUP_SCORE = plan -> gather -> score by (stride, class) groups with the group's centroid
+ *                rows staged in shared memory (large tables: K * C_s * 4 bytes beyond what a per-box sweep from L2
+ *                should re-read, e.g. K = 64) instead of the single per-box kernel.  Same results.
  *   metric_mask  OR of (1<<OODB200_METRIC_*): every requested metric is scored in the same pass
  *   normalize    1 = L2-normalise the pooled vector first (vanilla FMap methods); 0 = score as is
  *   cent         packed float32 centroids; (stride s, class c) has cent_k[s*nc+c] rows of C_s floats

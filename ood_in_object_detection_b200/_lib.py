@@ -24,7 +24,7 @@ SIGNATURES = {
     "oodb200_abi_version": [],
     "oodb200_last_error": [],
     "oodb200_roi_pool_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _L, _P],
-    "oodb200_fmap_workspace_bytes": [_I, _I, _I, _P],
+    "oodb200_fmap_workspace_bytes": [_I, _I, _P],
     "oodb200_fmap_score_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P,
                                _P, _I, _P, _P, _P, _L, _P],
     "oodb200_q1_plan_i32": [_P, _P, _P, _I, _P, _P, _P],

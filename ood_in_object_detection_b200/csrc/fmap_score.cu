@@ -103,18 +103,7 @@ struct FmapParams {
     int4* items;                // [<= n * max ns][2] self-contained item records
     float* pooled;              // [n][pooled_ld] raw pooled vectors (workspace), rows in output order
     int pooled_ld;
-    // ---- v2 path (box-parallel plan, dense plane jobs, scoring at box completion)
-    int group_score;            // score by (stride, class) groups in score_kernel instead of at box completion (large tables)
-    int* grp_cost;              // [n_img*3] bytes per channel the windows of an (image, stride) group would fetch as lines
-    int* grp_arr;               // [n_img*3] boxes of the group that have been planned
-    int* done;                  // [n] channel slices of the box that have been pooled
-    int32_t* inv;               // [n] box at every stride-major slot (img_start + #boxes of smaller strides + in-stride index)
-    int4* geo;                  // [n] window record of the box: ylo|xa<<16, wh|nxc<<16, count bits, s|xoff<<2|ww<<4
-    int4* jobs;                 // dense jobs, one list per stride at jobs_off[s]: {img*3+s, first channel, first slot, boxes}
-    int64_t jobs_off[3];
-    int32_t* score_list;        // [n] boxes completed by the dense kernel, scored by the gather kernel that follows
-    int dense_G[3];             // channel planes per ring stage (0: this stride never runs dense)
-    int dense_pitch[3];         // floats between two planes in a stage (plane + pad: (pitch / 4) odd -> conflict-free LDS.128)
+    int group_score;            // OODB200_FMAP_GROUP_SCORE: plan -> gather -> score by (stride, class) groups (large tables)
 };
 
 struct AxisSample {
@@ -196,8 +185,9 @@ struct BoxGeo {
     int xoff, ww;                // first live column relative to xa, number of live columns (channels-last path)
 };
 
-// ROI geometry + separable weights of one box (one warp); writes the weights, returns what the item records need.
-__device__ __forceinline__ BoxGeo geo_compute(const FmapParams& p, int box, int s, float4 bx) {
+// ROI geometry + separable weights of one box (one warp); writes the weights (wy[ext_y] | wx padded to 16-byte chunks),
+// returns what the item records need.
+__device__ __forceinline__ BoxGeo geo_compute_into(const FmapParams& p, int s, float4 bx, float* __restrict__ wy, float* __restrict__ wx) {
     const int lane = threadIdx.x & 31;
     const int H = p.H[s], W = p.W[s];
     const float sc = p.scale[s];
@@ -225,8 +215,6 @@ __device__ __forceinline__ BoxGeo geo_compute(const FmapParams& p, int box, int 
         g.xoff = xlo - g.xa;
         g.ww = ww;
         g.nxc = ((xlo + ww + 3) >> 2) - (g.xa >> 2);
-        float* __restrict__ wy = p.wts + (size_t)box * p.wstride;
-        float* __restrict__ wx = wy + p.ext_y;
         for (int t = lane; t < g.wh + 4 * g.nxc; t += 32) {   // rows and columns share one pass over the lanes
             if (t < g.wh) {
                 wy[t] = axis_weight(sh, rh, gh, H, ylo + t);
@@ -237,6 +225,11 @@ __device__ __forceinline__ BoxGeo geo_compute(const FmapParams& p, int box, int 
         }
     }
     return g;
+}
+
+__device__ __forceinline__ BoxGeo geo_compute(const FmapParams& p, int box, int s, float4 bx) {
+    float* wy = p.wts + (size_t)box * p.wstride;
+    return geo_compute_into(p, s, bx, wy, wy + p.ext_y);
 }
 
 // record: everything an item warp needs except the weights; item(sl) = pos + sl * nbs
@@ -303,6 +296,7 @@ __global__ void __launch_bounds__(kPgThreads) plan_geo_kernel(const FmapParams p
         item0[1] = cnt[2] * p.ns[2];
         item0[0] = item0[1] + cnt[1] * p.ns[1];
         int run[4] = {0, 0, 0, 0};
+        const int base_all = m > kPgCap ? __shfl_sync(kFull, base, 0) : 0;   // awaited only for images beyond the shared-memory cap
         for (int c0 = 0; c0 < m; c0 += 32) {
             const int bb = c0 + lane;
             int cat;
@@ -331,7 +325,7 @@ __global__ void __launch_bounds__(kPgThreads) plan_geo_kernel(const FmapParams p
             p.out_index[b0 + bb] = out;
             if (bb < kPgCap) { s_out[bb] = out; s_pos[bb] = it0 + j; }
             if (ok) {
-                if (bb >= kPgCap) p.ipos[b0 + bb] = make_int2(__shfl_sync(__activemask(), base, 0) + it0 + j, nb);
+                if (bb >= kPgCap) p.ipos[b0 + bb] = make_int2(base_all + it0 + j, nb);
                 if (p.cent) atomicAdd(&p.hist[(cls_u >= 0 && cls_u < p.nc) ? cat * p.nc + cls_u : 3 * p.nc], 1);
             } else if (p.cent) {
                 for (int k = 0; k < OODB200_N_METRICS; ++k)
@@ -451,8 +445,8 @@ __device__ __forceinline__ void pool_slice(const float* __restrict__ img, int C,
         const int q = l + G * t;
         if (q < nch) {
             const int r = q / nxc, xc = q - r * nxc;
-            const float a = __ldg(wy + r);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(wx) + xc);
+            const float a = wy[r];
+            const float4 b = reinterpret_cast<const float4*>(wx)[xc];
             w[t] = make_float4(a * b.x, a * b.y, a * b.z, a * b.w);
             off[t] = (y0 + r) * W + xa + 4 * xc;
         } else {
@@ -504,7 +498,7 @@ __device__ __noinline__ void pool_scalar(const float* __restrict__ img, int HW, 
         float s = 0.f;
         for (int q = lane; q < P; q += 32) {
             const int r = q / ww, x = q - r * ww;
-            const float wgt = __ldg(wy + r) * __ldg(wx + x);
+            const float wgt = wy[r] * wx[x];
             if (wgt != 0.f) s = fmaf(wgt, __ldg(pc + (y0 + r) * W + xa + x), s);   // padding columns may lie outside the row
         }
         s = warp_sum(s);
@@ -719,26 +713,6 @@ __device__ __forceinline__ void finalize(const FmapParams& p, int s, int cls, in
     write_result(p, s, cls, cls_ok, K, out, b);
 }
 
-// scoring of one finished box by one warp (tables swept from L2; the warp-private vector sits in shared memory)
-__device__ __noinline__ void score_finished_box(const FmapParams& p, int box, float* xs) {
-    const int s = p.stride_idx[box];
-    finalize(p, s, p.cls_used[box], p.out_index[box], xs);
-}
-
-// v2 epilogue of a pooled item: count the slice; the warp that pools the LAST slice of a box scores it
-__device__ __forceinline__ void item_done(const FmapParams& p, int box, int s, float* xs) {
-    const int lane = threadIdx.x & 31;
-    __threadfence();
-    __syncwarp();
-    int d = 0;
-    if (lane == 0) d = atomicAdd(&p.done[box], 1) + 1;
-    d = __shfl_sync(kFull, d, 0);
-    if (d == p.ns[s] && p.cent && !p.group_score) {
-        __threadfence();
-        score_finished_box(p, box, xs);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------- channels-last pooling
 // Channels-last maps (what a detector run in torch.channels_last hands out): the C values of a cell are contiguous.  A
 // work item is a slice of 32 channels = ONE 128-byte line per cell: 8 lanes x 128 bits cover it, so a warp request fetches
@@ -768,14 +742,13 @@ __device__ __forceinline__ NhwcItem nhwc_decode(int4 r0, int4 r1) {
 }
 
 // (element offset, weight) of cell q0 + lane of the item's window (0 weight beyond the window)
-__device__ __forceinline__ void nhwc_cells(const FmapParams& p, const NhwcItem& it, int q0, float& wq, int& oq) {
+__device__ __forceinline__ void nhwc_cells(const FmapParams& p, const NhwcItem& it, const float* __restrict__ wy, int q0, float& wq, int& oq) {
     const int q = q0 + (threadIdx.x & 31);
     wq = 0.f;
     oq = 0;
     if (q < it.wh * it.ww) {
-        const float* __restrict__ wy = p.wts + (size_t)it.box * p.wstride;
         const int r = q / it.ww, x = q - r * it.ww;
-        wq = __ldg(wy + r) * __ldg(wy + p.ext_y + it.xoff + x);
+        wq = wy[r] * wy[p.ext_y + it.xoff + x];
         oq = ((it.y0 + r) * p.W[it.s] + it.x0 + x) * p.C[it.s];
     }
 }
@@ -807,22 +780,59 @@ __device__ __forceinline__ void nhwc_consume(int first, int left, const float4 (
 }
 
 // any C / alignment: lanes over channels, scalar loads
-__device__ __noinline__ void pool_nhwc_scalar(const FmapParams& p, const NhwcItem& it, float* __restrict__ out0,
-                                              float* __restrict__ out1) {
+__device__ __noinline__ void pool_nhwc_scalar(const FmapParams& p, const NhwcItem& it, const float* __restrict__ wy,
+                                              float* __restrict__ out0, float* __restrict__ out1) {
     const int lane = threadIdx.x & 31;
     const int C = p.C[it.s], W = p.W[it.s];
-    const float* __restrict__ wy = p.wts + (size_t)it.box * p.wstride;
     const float* __restrict__ wx = wy + p.ext_y + it.xoff;
     for (int cc = it.c_lo + lane; cc < min(C, it.c_lo + kSliceNhwc); cc += 32) {
         float acc = 0.f;
         for (int r = 0; r < it.wh; ++r)
             for (int x = 0; x < it.ww; ++x) {
-                const float w = __ldg(wy + r) * __ldg(wx + x);
+                const float w = wy[r] * wx[x];
                 if (w != 0.f) acc = fmaf(w, __ldg(it.img + ((size_t)(it.y0 + r) * W + it.x0 + x) * C + cc), acc);
             }
         const float val = __fdiv_rn(acc, it.count);
         out0[cc] = val;
         if (out1) out1[cc] = val;
+    }
+}
+
+// One channels-last work item: the kSliceNhwc channels from a.c_lo of the window, weights at wy (wy[ext_y] | wx)
+__device__ __forceinline__ void nhwc_pool_item(const FmapParams& p, const NhwcItem& a, const float* __restrict__ wy,
+                                               float* __restrict__ out0, float* __restrict__ out1) {
+    const int lane = threadIdx.x & 31, g = lane / kNhwcLanes, l = lane % kNhwcLanes;
+    const int C = p.C[a.s];
+    const int ncell = a.wh * a.ww;                 // 0: no sample inside the map (Q5) -> all-zero vector
+    if ((C % 4 == 0) && (((uintptr_t)a.img & 15) == 0)) {
+        const int c = a.c_lo + l * 4;
+        const bool mine = c < C;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q0 = 0; q0 < ncell; q0 += 32) {
+            float wq;
+            int oq;
+            nhwc_cells(p, a, wy, q0, wq, oq);
+            const int left = min(32, ncell - q0);
+            for (int first = 0; first < left; first += 8 * kNhwcCells) {
+                float4 v[8];
+                float w8[8];
+                nhwc_issue(a.img + c, mine, first, left, wq, oq, v, w8);
+                nhwc_consume(first, left, v, w8, acc);
+            }
+        }
+#pragma unroll
+        for (int o = kNhwcLanes; o <= 16; o <<= 1) {   // the cell groups
+            acc.x += __shfl_xor_sync(kFull, acc.x, o); acc.y += __shfl_xor_sync(kFull, acc.y, o);
+            acc.z += __shfl_xor_sync(kFull, acc.z, o); acc.w += __shfl_xor_sync(kFull, acc.w, o);
+        }
+        if (mine && g == 0) {
+            const float4 val = make_float4(__fdiv_rn(acc.x, a.count), __fdiv_rn(acc.y, a.count), __fdiv_rn(acc.z, a.count),
+                                           __fdiv_rn(acc.w, a.count));    // average over the sample grid (roi_align.py:192-196)
+            *reinterpret_cast<float4*>(out0 + c) = val;
+            if (out1) { out1[c] = val.x; out1[c + 1] = val.y; out1[c + 2] = val.z; out1[c + 3] = val.w; }
+        }
+    } else {
+        pool_nhwc_scalar(p, a, wy, out0, out1);
     }
 }
 
@@ -846,21 +856,14 @@ __device__ __forceinline__ void sort_boxes_by_key(const FmapParams& p, int warp_
     }
 }
 
-template <bool V2>
 __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kernel(const __grid_constant__ FmapParams p) {
-    extern __shared__ __align__(16) float s_xs_dyn[];  // V2: one pooled_ld-float row per warp for the scoring of finished boxes
-    float* xs = s_xs_dyn + (size_t)(threadIdx.x >> 5) * p.pooled_ld;
     const int lane = threadIdx.x & 31;
     const int n_items = p.counters[0];
     // Scheduling: the first kStaticPct % of the work list is handed out round-robin (no atomics: same-address atomics
     // serialise in L2 and their latency under contention is of the order of an item), the tail through an atomic queue
     // so that the last items balance.  The next item's index and record are requested while the current one runs.
     const int warp_g = blockIdx.x * kWarps + (threadIdx.x >> 5), n_warps = gridDim.x * kWarps;
-    if (!V2 || p.group_score) sort_boxes_by_key(p, warp_g, n_warps);
-    if (V2 && p.cent && !p.group_score) {              // boxes whose last slice the dense kernel pooled
-        const int n_list = p.counters[7];
-        for (int i = warp_g; i < n_list; i += n_warps) score_finished_box(p, p.score_list[i], xs);
-    }
+    sort_boxes_by_key(p, warp_g, n_warps);
     const int n_static = (int)((long long)n_items * OODB200_FMAP_STATIC_PCT / 100);
     int q_reg = 0;                                     // lane 0: result of the most recent queue fetch
     bool q_pending = false;
@@ -903,7 +906,6 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kerne
             if (vec) pool_dispatch(img, C, HW, W, geo, wy, wx, count, c_lo, c_hi, out0, out1);
             else pool_scalar(img, HW, W, geo.x, geo.y, geo.z, geo.w, wy, wx, count, c_lo, c_hi, out0, out1);
         }
-        if (V2) item_done(p, box, s, xs);
         r0 = n0; r1 = n1; it = nit;
     }
 }
@@ -915,14 +917,11 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_MIN_BLOCKS) items_kerne
 #ifndef OODB200_FMAP_NHWC_BLOCKS
 #define OODB200_FMAP_NHWC_BLOCKS 3
 #endif
-template <bool V2>
 __global__ void __launch_bounds__(kThreads, OODB200_FMAP_NHWC_BLOCKS) items_nhwc_kernel(const __grid_constant__ FmapParams p) {
-    extern __shared__ __align__(16) float s_xs_dyn[];
-    float* xs = s_xs_dyn + (size_t)(threadIdx.x >> 5) * p.pooled_ld;
     const int lane = threadIdx.x & 31, g = lane / kNhwcLanes, l = lane % kNhwcLanes;
     const int n_items = p.counters[0];
     const int warp_g = blockIdx.x * kWarps + (threadIdx.x >> 5), n_warps = gridDim.x * kWarps;
-    if (!V2 || p.group_score) sort_boxes_by_key(p, warp_g, n_warps);
+    sort_boxes_by_key(p, warp_g, n_warps);
     const int n_static = (int)((long long)n_items * OODB200_FMAP_STATIC_PCT / 100);
     int q_reg = 0;
     bool q_pending = false;
@@ -946,41 +945,8 @@ __global__ void __launch_bounds__(kThreads, OODB200_FMAP_NHWC_BLOCKS) items_nhwc
         int4 n0 = make_int4(0, 0, 0, 0), n1 = n0;
         if (nit < n_items) { n0 = __ldg(p.items + 2 * (size_t)nit); n1 = __ldg(p.items + 2 * (size_t)nit + 1); }
         const NhwcItem a = nhwc_decode(r0, r1);
-        const int C = p.C[a.s];
-        const int ncell = a.wh * a.ww;                 // 0: no sample inside the map (Q5) -> all-zero vector
-        float* __restrict__ out0 = p.pooled + (size_t)a.out * p.pooled_ld;
-        float* __restrict__ out1 = p.pooled_user ? p.pooled_user + (size_t)a.out * p.pooled_user_ld : nullptr;
-        if ((C % 4 == 0) && (((uintptr_t)a.img & 15) == 0)) {
-            const int c = a.c_lo + l * 4;
-            const bool mine = c < C;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q0 = 0; q0 < ncell; q0 += 32) {
-                float wq;
-                int oq;
-                nhwc_cells(p, a, q0, wq, oq);
-                const int left = min(32, ncell - q0);
-                for (int first = 0; first < left; first += 8 * kNhwcCells) {
-                    float4 v[8];
-                    float w8[8];
-                    nhwc_issue(a.img + c, mine, first, left, wq, oq, v, w8);
-                    nhwc_consume(first, left, v, w8, acc);
-                }
-            }
-#pragma unroll
-            for (int o = kNhwcLanes; o <= 16; o <<= 1) {   // the cell groups
-                acc.x += __shfl_xor_sync(kFull, acc.x, o); acc.y += __shfl_xor_sync(kFull, acc.y, o);
-                acc.z += __shfl_xor_sync(kFull, acc.z, o); acc.w += __shfl_xor_sync(kFull, acc.w, o);
-            }
-            if (mine && g == 0) {
-                const float4 val = make_float4(__fdiv_rn(acc.x, a.count), __fdiv_rn(acc.y, a.count), __fdiv_rn(acc.z, a.count),
-                                               __fdiv_rn(acc.w, a.count));    // average over the sample grid (roi_align.py:192-196)
-                *reinterpret_cast<float4*>(out0 + c) = val;
-                if (out1) { out1[c] = val.x; out1[c + 1] = val.y; out1[c + 2] = val.z; out1[c + 3] = val.w; }
-            }
-        } else {
-            pool_nhwc_scalar(p, a, out0, out1);
-        }
-        if (V2) item_done(p, a.box, a.s, xs);
+        nhwc_pool_item(p, a, p.wts + (size_t)a.box * p.wstride, p.pooled + (size_t)a.out * p.pooled_ld,
+                       p.pooled_user ? p.pooled_user + (size_t)a.out * p.pooled_user_ld : nullptr);
         r0 = n0; r1 = n1; it = nit;
     }
 }
@@ -1234,85 +1200,80 @@ static ScoreKernel score_kernel_for(int mask) {
     }
 }
 
-// =============================================================================================== v2 path
-// memset -> plan2_kernel -> dense_pool_kernel -> items_kernel<true> [-> score_kernel for large tables]
-//  plan2_kernel      ONE WARP PER BOX, no planner warp, no cluster: the Q1 rank of the box comes from ballots over its own
-//                    image's stride list (<= 10 loads of 32 strides), its geometry from geo_compute.  The last box of an
-//                    (image, stride) group to arrive (threadfence + counter) decides how the group is pooled and emits its
-//                    work: DENSE when the 128-byte lines its windows touch add up to >= 80 % of the plane (NCHW rows of a
-//                    window are 8..52 bytes: a line-granular gather then fetches the whole plane anyway), else item records
-//                    for the LDG gather as before.
-//  dense_pool_kernel persistent, 1 CTA per SM, warp-specialised.  A job = (image, stride, 64 channels, <= 32 boxes).  The
-//                    producer warp streams whole channel planes (1.6 .. 6.4 KB each, contiguous) into a 3-stage ring of
-//                    52 KB with cp.async.bulk (TMA) completing on mbarriers; the 8 consumer warps pool every box of the job
-//                    from shared memory with the separable RoIAlign weights: lane = channel (x box slot), one conflict-free
-//                    LDS.128 per 4 window cells (plane pitch / 16 B is odd), no cross-lane reduction, coalesced stores of
-//                    the pooled channels.  Every HBM line of the plane is fetched once, in full, by the copy engine.
-//  items_kernel<true> the LDG window gather for the sparse groups; a box is scored by the warp that pools its last slice
-//                    (counter per box), boxes completed by the dense kernel are scored in the prologue.
-constexpr int kDnConsumers = 8;                        // consumer warps of the dense kernel
-constexpr int kDnThreads = (kDnConsumers + 1) * 32;    // + the producer warp
-constexpr int kDnStages = 3;
-constexpr int kDnStageBytes = 52 * 1024;
-constexpr int kDnBatch = 32;                           // boxes per dense job
-constexpr int kDenseSlice = kSliceChannels;            // channels per dense job: same completion count as the sparse items
-#ifndef OODB200_DENSE_PCT
-#define OODB200_DENSE_PCT 80                           // dense when the windows' lines reach this share of the plane
+// =============================================================================================== per-box kernel
+// box_kernel: ONE launch for the whole path when the centroid tables are small enough to be swept from L2 per box (the
+// usual K <= 16): one CTA of 4 warps per detection, everything the box needs happens inside it, and the phases of
+// different boxes overlap on an SM (4 CTAs resident) instead of being separate, individually latency-bound launches.
+//   phase 0  warp 0: RoIAlign geometry + separable weights into shared memory (geo_compute_into);
+//            warp 1: quirk-Q1 class / output slot from ballots over the image's own stride list (<= 10 loads of 32).
+//   phase 1  the 4 warps pool a quarter of the channels each with the 128-bit window gather of items_kernel
+//            (pool_dispatch; channels-last: nhwc_pool_item per slice of 32 channels); the vector stays in shared memory.
+//   phase 2  warp 0 normalises the vector (sklearn normalize; per-lane partition and butterfly of score_box_smem), then the
+//            K centroid rows are split over the warps (rows w, w + 4, ...; <= 4 rows x metrics in flight per warp, read
+//            from L2), first minimum over the warps, float64 threshold compare.  Same arithmetic as score_box_smem /
+//            vec_score_fast_kernel: fit-time and decision-time distances of the same vector are bit-identical.
+constexpr int kBxWarps = 4, kBxThreads = kBxWarps * 32;
+#ifndef OODB200_BOX_BLOCKS
+#define OODB200_BOX_BLOCKS 4
 #endif
 
-__device__ __forceinline__ void mb_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fs_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fs_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_plane(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fs_smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(fs_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kDnConsumers * 32) : "memory"); }
-
-__global__ void __launch_bounds__(256) plan2_kernel(const __grid_constant__ FmapParams p) {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (b >= p.n) return;
+template <bool NHWC>
+__global__ void __launch_bounds__(kBxThreads, OODB200_BOX_BLOCKS) box_kernel(const __grid_constant__ FmapParams p) {
+    extern __shared__ __align__(16) float bsm[];
+    float* s_w = bsm;                                  // wy[ext_y] | wx (wstride floats)
+    float* xs = bsm + p.wstride;                       // the pooled vector (pooled_ld floats)
+    __shared__ int s_plan[2];                          // class used, output slot
+    __shared__ int s_geo[8];                           // ylo, xa, wh, nxc, count bits, xoff, ww
+    __shared__ float s_d[kBxWarps][OODB200_N_METRICS];
+    __shared__ int s_a[kBxWarps][OODB200_N_METRICS];
+    __shared__ float s_n2v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x;
     const int img = p.img_idx[b];
     const int s = p.stride_idx[b];
-    const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)b);
-    const int b0 = p.img_start[img], m = p.img_start[img + 1] - b0, bb = b - b0;
     const bool ok = s >= 0 && s <= 2;
-    const int mycat = ok ? s : 3;
-    int cnt[4] = {0, 0, 0, 0};
-    int j = 0;                                         // boxes of my category before me (Q1: the in-stride index)
-    for (int c0 = 0; c0 < m; c0 += 32) {
-        const int e = c0 + lane;
-        const int st = e < m ? p.stride_idx[b0 + e] : -2;
-        const int cat = e < m ? ((st >= 0 && st <= 2) ? st : 3) : 4;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const unsigned mk = __ballot_sync(kFull, cat == t);
-            cnt[t] += __popc(mk);
-            if (t == mycat) {
-                if (c0 + 32 <= bb) j += __popc(mk);
-                else if (c0 <= bb) j += __popc(mk & ((1u << (bb - c0)) - 1u));
+    if (warp == 0) {
+        if (ok) {
+            const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)b);
+            const BoxGeo g = geo_compute_into(p, s, bx, s_w, s_w + p.ext_y);
+            if (lane == 0) {
+                s_geo[0] = g.ylo; s_geo[1] = g.xa; s_geo[2] = g.wh; s_geo[3] = g.nxc;
+                s_geo[4] = __float_as_int(g.count); s_geo[5] = g.xoff; s_geo[6] = g.ww;
             }
         }
-    }
-    int before = 0;
+    } else if (warp == 1) {
+        const int b0 = p.img_start[img], m = p.img_start[img + 1] - b0, bb = b - b0;
+        const int mycat = ok ? s : 3;
+        int cnt[4] = {0, 0, 0, 0};
+        int j = 0;                                     // boxes of my category before me (Q1: the in-stride index)
+        for (int c0 = 0; c0 < m; c0 += 32) {
+            const int e = c0 + lane;
+            const int st = e < m ? p.stride_idx[b0 + e] : -2;
+            const int cat = e < m ? ((st >= 0 && st <= 2) ? st : 3) : 4;
 #pragma unroll
-    for (int t = 0; t < 3; ++t) if (t < mycat) before += cnt[t];
-    const int gslot = b0 + before + j;
-    int cls_u = p.cls ? p.cls[b] : 0, out = b;
-    if (p.compat_q1) {                                 // ood_utils.py:2152-2154: class of the box with the same in-stride index
-        cls_u = ok ? p.cls[b0 + j] : -1;
-        out = gslot;
+            for (int t = 0; t < 4; ++t) {
+                const unsigned mk = __ballot_sync(kFull, cat == t);
+                cnt[t] += __popc(mk);
+                if (t == mycat) {
+                    if (c0 + 32 <= bb) j += __popc(mk);
+                    else if (c0 <= bb) j += __popc(mk & ((1u << (bb - c0)) - 1u));
+                }
+            }
+        }
+        int before = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) if (t < mycat) before += cnt[t];
+        int cls_u = p.cls ? p.cls[b] : 0, out = b;
+        if (p.compat_q1) {                             // ood_utils.py:2152-2154: class of the box with the same in-stride index
+            cls_u = ok ? p.cls[b0 + j] : -1;
+            out = b0 + before + j;
+        }
+        if (lane == 0) { s_plan[0] = cls_u; s_plan[1] = out; p.cls_used[b] = cls_u; p.out_index[b] = out; }
     }
-    if (lane == 0) { p.cls_used[b] = cls_u; p.out_index[b] = out; p.inv[gslot] = b; }
+    __syncthreads();
+    const int cls_u = s_plan[0], out = s_plan[1];
     if (!ok) {                                         // never pooled by the reference either: answered here
-        if (p.cent && lane < OODB200_N_METRICS && (p.metric_mask >> lane & 1)) {
+        if (warp == 0 && p.cent && lane < OODB200_N_METRICS && (p.metric_mask >> lane & 1)) {
             const size_t o = (size_t)lane * p.n + out;
             p.dist[o] = nanf("");
             p.argmin[o] = -1;
@@ -1320,188 +1281,155 @@ __global__ void __launch_bounds__(256) plan2_kernel(const __grid_constant__ Fmap
         }
         return;
     }
-    const BoxGeo g = geo_compute(p, b, s, bx);
-    const int n_g = s == 0 ? cnt[0] : (s == 1 ? cnt[1] : cnt[2]);
-    const int g3 = img * 3 + s;
-    int arrived = 0;
-    if (lane == 0) {
-        p.geo[b] = make_int4(g.ylo | (g.xa << 16), g.wh | (g.nxc << 16), __float_as_int(g.count), s | (g.xoff << 2) | (g.ww << 4));
-        if (p.cent && p.group_score) atomicAdd(&p.hist[(cls_u >= 0 && cls_u < p.nc) ? s * p.nc + cls_u : 3 * p.nc], 1);
-        atomicAdd(&p.grp_cost[g3], g.wh * (4 * g.ww + 128));       // a row of L bytes at a random offset touches (L + 128) / 128 lines on average
-    }
-    __threadfence();                                   // weights, geo, inv visible before the arrival is counted
-    if (lane == 0) arrived = atomicAdd(&p.grp_arr[g3], 1) + 1;
-    arrived = __shfl_sync(kFull, arrived, 0);
-    if (arrived != n_g) return;
-    __threadfence();
-    // ---- last box of the (image, stride) group: emit the group's work
-    const int first = b0 + before;                     // the group's slots are [first, first + n_g)
-    const unsigned long long mapp = (unsigned long long)p.map_ptrs[g3];
-    bool dense = false;
-    if (p.dense_G[s] > 0 && (mapp & 15) == 0) {
-        const long long plane = 4LL * p.H[s] * p.W[s];
-        dense = 100LL * (*reinterpret_cast<volatile int*>(&p.grp_cost[g3])) >= (long long)OODB200_DENSE_PCT * plane;
-    }
-    const int ns = p.ns[s];
-    if (dense) {
-        const int nbat = (n_g + kDnBatch - 1) / kDnBatch, njobs = nbat * ns;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&p.counters[4 + s], njobs);
-        base = __shfl_sync(kFull, base, 0);
-        for (int i = lane; i < njobs; i += 32) {
-            const int bat = i / ns, sl = i - bat * ns;
-            p.jobs[p.jobs_off[s] + base + i] = make_int4(g3, sl * kDenseSlice, first + bat * kDnBatch, min(kDnBatch, n_g - bat * kDnBatch));
+    // ---- phase 1: pooling
+    const int C = p.C[s], W = p.W[s], HW = p.H[s] * W;
+    const float* __restrict__ imgp = p.map_ptrs[img * 3 + s];
+    float* __restrict__ out1 = p.pooled_user ? p.pooled_user + (size_t)out * p.pooled_user_ld : nullptr;
+    const int4 geo = make_int4(s_geo[0], s_geo[1], s_geo[2], s_geo[3]);
+    const float count = __int_as_float(s_geo[4]);
+    if (geo.w == 0) {                                  // no sample inside the map (Q5): all-zero vector
+        for (int c = threadIdx.x; c < C; c += kBxThreads) { xs[c] = 0.f; if (out1) out1[c] = 0.f; }
+    } else if (!NHWC) {
+        const int cpw = ((C + 32 * kBxWarps - 1) / (32 * kBxWarps)) * 32;      // channels per warp, a multiple of 32
+        const int c_lo = warp * cpw, c_hi = min(C, c_lo + cpw);
+        if (c_lo < C) {
+            const bool vec = (W % 4 == 0) && (((uintptr_t)imgp & 15) == 0) && (HW % 4 == 0);
+            if (vec) pool_dispatch(imgp, C, HW, W, geo, s_w, s_w + p.ext_y, count, c_lo, c_hi, xs, out1);
+            else pool_scalar(imgp, HW, W, geo.x, geo.y, geo.z, geo.w, s_w, s_w + p.ext_y, count, c_lo, c_hi, xs, out1);
         }
     } else {
-        const int tot = n_g * ns;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&p.counters[0], tot);
-        base = __shfl_sync(kFull, base, 0);
-        for (int i = lane; i < tot; i += 32) {         // slice-major: the slices of one box are n_g items apart
-            const int sl = i / n_g, k = i - sl * n_g;
-            const int box = p.inv[first + k];
-            const int4 ge = p.geo[box];
-            int4* rec = p.items + 2 * (size_t)(base + i);
-            rec[0] = make_int4((int)(((uint32_t)sl << 24) | (uint32_t)box), ge.x, ge.y, p.out_index[box]);
-            rec[1] = make_int4((int)(mapp & 0xffffffffu), (int)(mapp >> 32), ge.z, ge.w);
+        NhwcItem a;
+        a.img = imgp; a.box = b; a.s = s; a.out = out; a.y0 = geo.x; a.xoff = s_geo[5]; a.x0 = geo.y + s_geo[5];
+        a.wh = geo.z; a.ww = s_geo[6]; a.count = count;
+        for (int sl = warp; sl * kSliceNhwc < C; sl += kBxWarps) {
+            a.c_lo = sl * kSliceNhwc;
+            nhwc_pool_item(p, a, s_w, xs, out1);
         }
     }
-}
-
-struct DnMeta { int seq, g3, c0, nch, first, nb, last, term; };
-
-__global__ void __launch_bounds__(kDnThreads, 1) dense_pool_kernel(const __grid_constant__ FmapParams p, int wrow) {
-    extern __shared__ __align__(128) unsigned char dsm[];
-    float* ring = reinterpret_cast<float*>(dsm);                                   // kDnStages x kDnStageBytes
-    float* s_wts = reinterpret_cast<float*>(dsm + (size_t)kDnStages * kDnStageBytes);   // [kDnBatch][wrow]: wy | wx per box
-    __shared__ __align__(8) uint64_t s_full[kDnStages], s_empty[kDnStages];
-    __shared__ DnMeta s_meta[kDnStages];
-    __shared__ int4 s_box[kDnBatch];                   // ylo|xa<<16, wh|nxc<<16, count bits, output row
-    __shared__ int s_boxid[kDnBatch];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        for (int i = 0; i < kDnStages; ++i) { mb_init(&s_full[i], 1); mb_init(&s_empty[i], kDnConsumers); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     __syncthreads();
-    const int nj0 = p.counters[4], nj1 = p.counters[5], nj2 = p.counters[6];
-    const int total = nj0 + nj1 + nj2;
-    if (warp == kDnConsumers) {
-        // ---- producer: next job from the queue (largest planes first), its planes into the ring
-        if (lane == 0) {
-            int it = 0, seq = 0;
-            for (;;) {
-                const int q = atomicAdd(&p.counters[3], 1);
-                if (q >= total) break;
-                int s = 0, qi = q;
-                if (qi >= nj0) { qi -= nj0; s = 1; if (qi >= nj1) { qi -= nj1; s = 2; } }
-                const int4 job = p.jobs[p.jobs_off[s] + qi];
-                const float* __restrict__ base = p.map_ptrs[job.x];
-                const int HW = p.H[s] * p.W[s], G = p.dense_G[s], pitch = p.dense_pitch[s];
-                const int cend = min(p.C[s], job.y + kDenseSlice);
-                for (int cs = job.y; cs < cend; cs += G) {
-                    const int st = it % kDnStages;
-                    if (it >= kDnStages) mbar_wait_bounded(&s_empty[st], (uint32_t)((it / kDnStages) - 1) & 1u);
-                    const int nch = min(G, cend - cs);
-                    s_meta[st] = DnMeta{seq, job.x, cs, nch, job.z, job.w, cs + G >= cend ? 1 : 0, 0};
-                    mb_expect_tx(&s_full[st], (uint32_t)nch * (uint32_t)HW * 4u);
-                    float* dst = ring + (size_t)st * (kDnStageBytes / 4);
-                    for (int ch = 0; ch < nch; ++ch)
-                        bulk_plane(dst + (size_t)ch * pitch, base + (size_t)(cs + ch) * HW, (uint32_t)HW * 4u, &s_full[st]);
-                    ++it;
-                }
-                ++seq;
-            }
-            const int st = it % kDnStages;
-            if (it >= kDnStages) mbar_wait_bounded(&s_empty[st], (uint32_t)((it / kDnStages) - 1) & 1u);
-            s_meta[st].term = 1;
-            mb_arrive(&s_full[st]);
+    if (!p.cent) return;
+    // ---- phase 2: distance to the nearest centroid of (class used, stride), threshold
+    const bool cls_ok = cls_u >= 0 && cls_u < p.nc;
+    const int K = cls_ok ? p.cent_k[s * p.nc + cls_u] : 0;
+    const int64_t off = K > 0 ? p.cent_off[s * p.nc + cls_u] : 0;
+    const bool vecs = (C % 4 == 0) && (off % 4 == 0) && ((((uintptr_t)p.cent) | ((uintptr_t)p.cent_unit)) & 15) == 0;
+    if (!vecs) {                                       // odd shapes: the row goes to the workspace and warp 0 sweeps like finalize()
+        if (warp == 0) {
+            float* row = p.pooled + (size_t)out * p.pooled_ld;
+            for (int c = lane; c < C; c += 32) row[c] = xs[c];
+            __threadfence_block();
+            __syncwarp();
+            const Best bb = finalize_generic(row, C, p.normalize, p.metric_mask, p.cent + off, p.cent_unit + off, K);
+            write_result(p, s, cls_u, cls_ok, K, out, bb);
         }
         return;
     }
-    // ---- consumers
-    int cur = -1;
-    for (int it = 0;; ++it) {
-        const int st = it % kDnStages;
-        mbar_wait_bounded(&s_full[st], (uint32_t)(it / kDnStages) & 1u);
-        const DnMeta m = s_meta[st];
-        if (m.term) break;
-        const int s = m.g3 % 3;
-        const int W = p.W[s], hpad = (p.H[s] + 3) & ~3;
-        if (m.seq != cur) {                            // a new job: its box table and weights (consumers only)
-            consumer_bar();                            // everybody is done with the previous job's tables
-            for (int i = warp; i < m.nb; i += kDnConsumers) {
-                const int box = p.inv[m.first + i];
-                const int4 ge = p.geo[box];
-                const int wh = ge.y & 0xFFFF, nxc = (int)((uint32_t)ge.y >> 16);
-                const float* __restrict__ src = p.wts + (size_t)box * p.wstride;
-                float* dst = s_wts + (size_t)i * wrow;
-                for (int t = lane; t < wh; t += 32) dst[t] = src[t];
-                for (int t = lane; t < 4 * nxc; t += 32) dst[hpad + t] = src[p.ext_y + t];
-                if (lane == 0) { s_box[i] = make_int4(ge.x, ge.y, ge.z, p.out_index[box]); s_boxid[i] = box; }
+    const bool want_l1 = p.metric_mask & (1 << OODB200_METRIC_L1);
+    const bool want_l2 = p.metric_mask & (1 << OODB200_METRIC_L2);
+    const bool want_cos = p.metric_mask & (1 << OODB200_METRIC_COS);
+    const int nj = (C + 127) >> 7;
+    if (warp == 0) {                                   // ood_utils.py:2409 -> sklearn normalize; cosine re-normalises (pairwise.py:1171-1182)
+        float ss = 0.f;
+        for (int t = 0; t < nj; ++t) {
+            const int d = lane * 4 + 128 * t;
+            if (d < C) {
+                const float4 v = *reinterpret_cast<const float4*>(xs + d);
+                ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
             }
-            consumer_bar();
-            cur = m.seq;
         }
-        const int G = p.dense_G[s], pitch = p.dense_pitch[s];
-        const int lg = G == 32 ? 5 : (G == 16 ? 4 : 3);
-        const int ch = lane & (G - 1), slot = lane >> lg, spw = 32 >> lg;
-        const float* __restrict__ stage = ring + (size_t)st * (kDnStageBytes / 4);
-        for (int i0 = 0; i0 < m.nb; i0 += kDnConsumers * spw) {
-            const int bi = i0 + warp * spw + slot;
-            const bool have = bi < m.nb && ch < m.nch;
-            const int4 bq = have ? s_box[bi] : make_int4(0, 0, 0, 0);
-            const int ylo = bq.x & 0xFFFF, xa = (int)((uint32_t)bq.x >> 16);
-            const int wh = have ? (bq.y & 0xFFFF) : 0, nxc = (int)((uint32_t)bq.y >> 16);
-            const int whm = __reduce_max_sync(kFull, wh);
-            const float* __restrict__ wy = s_wts + (size_t)(have ? bi : 0) * wrow;
-            const float4* __restrict__ wx = reinterpret_cast<const float4*>(wy + hpad);
-            const float* __restrict__ src = stage + (size_t)ch * pitch + ylo * W + xa;
-            float acc = 0.f;
-            for (int r = 0; r < whm; ++r) {
-                if (r < wh) {
-                    const float4* __restrict__ pr = reinterpret_cast<const float4*>(src + r * W);
-                    float ra = 0.f;
-                    for (int xc = 0; xc < nxc; ++xc) {
-                        const float4 v = pr[xc], w = wx[xc];
-                        ra = fmaf(w.x, v.x, ra); ra = fmaf(w.y, v.y, ra); ra = fmaf(w.z, v.z, ra); ra = fmaf(w.w, v.w, ra);
+        float n2v = 1.f;
+        if (p.normalize) {
+            float nrm = sqrtf(warp_sum(ss));
+            if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;   // _handle_zeros_in_scale
+            ss = 0.f;
+            for (int t = 0; t < nj; ++t) {
+                const int d = lane * 4 + 128 * t;
+                if (d < C) {
+                    float4 v = *reinterpret_cast<const float4*>(xs + d);
+                    v.x = __fdiv_rn(v.x, nrm); v.y = __fdiv_rn(v.y, nrm); v.z = __fdiv_rn(v.z, nrm); v.w = __fdiv_rn(v.w, nrm);
+                    *reinterpret_cast<float4*>(xs + d) = v;
+                    ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+                }
+            }
+        }
+        if (want_cos) {
+            n2v = sqrtf(warp_sum(ss));
+            if (n2v < 10.f * FLT_EPSILON) n2v = 1.f;
+        }
+        if (lane == 0) s_n2v = n2v;
+    }
+    __syncthreads();
+    const float n2v = s_n2v;
+    Best bst = {{FLT_MAX, FLT_MAX, FLT_MAX}, {INT_MAX, INT_MAX, INT_MAX}};
+    for (int k0 = warp; k0 < K; k0 += 4 * kBxWarps) {  // rows k0, k0 + 4, k0 + 8, k0 + 12 of this warp: independent reductions
+        float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f}, ac[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int t = 0; t < nj; ++t) {
+            const int d = lane * 4 + 128 * t;
+            if (d < C) {
+                const float4 x = *reinterpret_cast<const float4*>(xs + d);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int k = min(k0 + kBxWarps * r, K - 1);         // short batch: repeat the last row, result dropped
+                    if (want_l1 || want_l2) {
+                        const float4 c = __ldg(reinterpret_cast<const float4*>(p.cent + off + (int64_t)k * C + d));
+                        const float e0 = x.x - c.x, e1 = x.y - c.y, e2 = x.z - c.z, e3 = x.w - c.w;
+                        a1[r] += (fabsf(e0) + fabsf(e1)) + (fabsf(e2) + fabsf(e3));
+                        a2[r] = fmaf(e0, e0, a2[r]); a2[r] = fmaf(e1, e1, a2[r]); a2[r] = fmaf(e2, e2, a2[r]); a2[r] = fmaf(e3, e3, a2[r]);
                     }
-                    acc = fmaf(wy[r], ra, acc);
-                }
-            }
-            if (have) {
-                const float val = wh > 0 ? __fdiv_rn(acc, __int_as_float(bq.z)) : 0.f;    // average over the sample grid; no sample inside the map (Q5): 0
-                const int c = m.c0 + ch;
-                p.pooled[(size_t)bq.w * p.pooled_ld + c] = val;
-                if (p.pooled_user) p.pooled_user[(size_t)bq.w * p.pooled_user_ld + c] = val;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mb_arrive(&s_empty[st]);
-        if (m.last) {                                  // this (batch, 64 channels) is pooled: count it for the warp's boxes
-            __threadfence();
-            __syncwarp();
-            for (int i0 = 0; i0 < m.nb; i0 += kDnConsumers * spw) {
-                const int bi = i0 + warp * spw + slot;
-                if (bi < m.nb && ch == 0) {
-                    const int box = s_boxid[bi];
-                    const int d = atomicAdd(&p.done[box], 1) + 1;
-                    if (d == p.ns[s] && p.cent && !p.group_score) p.score_list[atomicAdd(&p.counters[7], 1)] = box;
+                    if (want_cos) {
+                        const float4 u = __ldg(reinterpret_cast<const float4*>(p.cent_unit + off + (int64_t)k * C + d));
+                        ac[r] = fmaf(x.x, u.x, ac[r]); ac[r] = fmaf(x.y, u.y, ac[r]); ac[r] = fmaf(x.z, u.z, ac[r]); ac[r] = fmaf(x.w, u.w, ac[r]);
+                    }
                 }
             }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (want_l1) a1[r] += __shfl_xor_sync(kFull, a1[r], o);
+                if (want_l2) a2[r] += __shfl_xor_sync(kFull, a2[r], o);
+                if (want_cos) ac[r] += __shfl_xor_sync(kFull, ac[r], o);
+            }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {                  // rows in increasing order, strict '<': first minimum
+            const int k = k0 + kBxWarps * r;
+            if (k < K) {
+                if (want_l1 && a1[r] < bst.d[0]) { bst.d[0] = a1[r]; bst.a[0] = k; }
+                if (want_l2) { const float v = sqrtf(fmaxf(a2[r], 0.f)); if (v < bst.d[1]) { bst.d[1] = v; bst.a[1] = k; } }
+                if (want_cos) {                        // X / ||X|| applied to the sum (same value to float32 rounding)
+                    const float v = fminf(fmaxf(1.0f - __fdiv_rn(ac[r], n2v), 0.f), 2.f);
+                    if (v < bst.d[2]) { bst.d[2] = v; bst.a[2] = k; }
+                }
+            }
+        }
+    }
+    if (lane < OODB200_N_METRICS) {
+        s_d[warp][lane] = lane == 0 ? bst.d[0] : (lane == 1 ? bst.d[1] : bst.d[2]);
+        s_a[warp][lane] = lane == 0 ? bst.a[0] : (lane == 1 ? bst.a[1] : bst.a[2]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        Best fin = {{FLT_MAX, FLT_MAX, FLT_MAX}, {INT_MAX, INT_MAX, INT_MAX}};
+#pragma unroll
+        for (int m = 0; m < OODB200_N_METRICS; ++m)
+#pragma unroll
+            for (int w = 0; w < kBxWarps; ++w) {       // first minimum over the warps: smaller distance, then smaller index
+                const float od = s_d[w][m];
+                const int oa = s_a[w][m];
+                if (od < fin.d[m] || (od == fin.d[m] && oa < fin.a[m])) { fin.d[m] = od; fin.a[m] = oa; }
+            }
+        write_result(p, s, cls_u, cls_ok, K, out, fin);
     }
 }
 
 struct WorkspaceLayout {
-    size_t counters, hist, cursor, grp_cost, grp_arr, done, sorted, cls_used, out_index, ipos, inv, geo, score_list, wts, items,
-        jobs, pooled, total;
+    size_t counters, hist, cursor, sorted, cls_used, out_index, ipos, wts, items, pooled, total;
     size_t zero_bytes;
-    size_t jobs_off[3];
     int ext_y, wstride, pooled_ld, max_ns;
 };
 
-static WorkspaceLayout layout_of(int n, int n_img, int nc, const int32_t* map_chw) {
+static WorkspaceLayout layout_of(int n, int nc, const int32_t* map_chw) {
     WorkspaceLayout L;
     int hmax = 1, wmax = 1, cmax = 1;
     for (int s = 0; s < 3; ++s) {
@@ -1517,46 +1445,37 @@ static WorkspaceLayout layout_of(int n, int n_img, int nc, const int32_t* map_ch
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;
     const size_t nn = (size_t)(n > 0 ? n : 1);
-    const size_t ng = 3 * (size_t)(n_img > 0 ? n_img : 1);
     const size_t nk = 3 * (size_t)(nc > 0 ? nc : 1) + 1;
-    L.counters = o; o += 32;                          // counters, hist, cursor, group and box counters are zeroed by one memset
+    L.counters = o; o += 16;                          // counters, hist and cursor are zeroed by one memset
     L.hist = o; o += 4 * nk;
     L.cursor = o; o += 4 * nk;
-    L.grp_cost = o; o += 4 * ng;
-    L.grp_arr = o; o += 4 * ng;
-    L.done = o; o += 4 * nn;
     L.zero_bytes = o;
     o = up(o);
     L.sorted = o; o = up(o + 4 * nn);
     L.cls_used = o; o = up(o + 4 * nn);
     L.out_index = o; o = up(o + 4 * nn);
     L.ipos = o; o = up(o + 8 * nn);
-    L.inv = o; o = up(o + 4 * nn);
-    L.geo = o; o = up(o + 16 * nn);
-    L.score_list = o; o = up(o + 4 * nn);
     L.wts = o; o = up(o + 4 * nn * L.wstride);
     L.items = o; o = up(o + 32 * nn * L.max_ns);
-    L.jobs = o;                                       // dense jobs: a group of m boxes gives ceil(m / 32) * ns <= m * ns jobs
-    size_t jo = 0;
-    for (int s = 0; s < 3; ++s) {
-        L.jobs_off[s] = jo;
-        jo += nn * (size_t)((map_chw[3 * s] + kSliceChannels - 1) / kSliceChannels);
-    }
-    o = up(o + 16 * jo);
     L.pooled = o; o = up(o + 4 * nn * L.pooled_ld);
     L.total = o;
     return L;
 }
 
-struct DeviceInfo { int sms, items_per_sm[2], items_per_sm_nhwc[2]; size_t score_attr[8]; size_t items_attr[4]; size_t dense_attr; bool init; };
+struct DeviceInfo { bool init; int sms, items_per_sm, items_per_sm_nhwc; size_t score_attr[8], box_attr[2]; };
 static DeviceInfo g_dev[64];
 
-static DeviceInfo& device_info() {                     // per device: SM count, occupancy, the attributes already raised
+static DeviceInfo& device_info() {                     // per device: SM count, occupancy, attributes already raised
     int dev = 0;
     cudaGetDevice(&dev);
     DeviceInfo& d = g_dev[dev & 63];
     if (!d.init) {
         if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.sms <= 0) d.sms = 148;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.items_per_sm, items_kernel, kThreads, 0) != cudaSuccess || d.items_per_sm <= 0)
+            d.items_per_sm = OODB200_FMAP_MIN_BLOCKS;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.items_per_sm_nhwc, items_nhwc_kernel, kThreads, 0) != cudaSuccess ||
+            d.items_per_sm_nhwc <= 0)
+            d.items_per_sm_nhwc = OODB200_FMAP_MIN_BLOCKS;
         d.init = true;
     }
     return d;
@@ -1583,7 +1502,7 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     }
     OODB200_REQUIRE(p.n < (1 << 24), "%s: at most %d boxes per call", what, (1 << 24) - 1);
     if (p.n == 0) return OODB200_OK;
-    const WorkspaceLayout L = layout_of(p.n, p.n_img, p.cent ? p.nc : 0, map_chw);
+    const WorkspaceLayout L = layout_of(p.n, p.cent ? p.nc : 0, map_chw);
     OODB200_REQUIRE(workspace && workspace_bytes >= (int64_t)L.total, "%s: workspace too small (%lld < %zu bytes)", what,
                     (long long)workspace_bytes, L.total);
     OODB200_REQUIRE(((uintptr_t)workspace & 255) == 0, "%s: workspace must be 256-byte aligned", what);
@@ -1591,49 +1510,39 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     p.counters = (int*)(ws + L.counters);
     p.hist = (int*)(ws + L.hist);
     p.cursor = (int*)(ws + L.cursor);
-    p.grp_cost = (int*)(ws + L.grp_cost);
-    p.grp_arr = (int*)(ws + L.grp_arr);
-    p.done = (int*)(ws + L.done);
     p.sorted = (int32_t*)(ws + L.sorted);
     p.cls_used = cls_used_out ? cls_used_out : (int32_t*)(ws + L.cls_used);
     p.out_index = out_index_out ? out_index_out : (int32_t*)(ws + L.out_index);
     p.ipos = (int2*)(ws + L.ipos);
-    p.inv = (int32_t*)(ws + L.inv);
-    p.geo = (int4*)(ws + L.geo);
-    p.score_list = (int32_t*)(ws + L.score_list);
     p.wts = (float*)(ws + L.wts);
     p.ext_y = L.ext_y;
     p.wstride = L.wstride;
     p.items = (int4*)(ws + L.items);
-    p.jobs = (int4*)(ws + L.jobs);
-    for (int s = 0; s < 3; ++s) p.jobs_off[s] = (int64_t)L.jobs_off[s];
     p.pooled = (float*)(ws + L.pooled);
     p.pooled_ld = L.pooled_ld;
     cudaStream_t st = (cudaStream_t)stream;
     DeviceInfo& dv = device_info();
-    static const int use_v1 = env_int("OODB200_FMAP_V1", 0);       // the round-1 launch sequence (A/B runs)
-    static const int no_dense = env_int("OODB200_FMAP_NO_DENSE", 0);
-    // dense plane jobs: NCHW strides whose plane (+ pad) fits the ring stage at least 8 times, 16-byte rows
-    int wrow = 0;
-    bool any_dense = false;
-    for (int s = 0; s < 3; ++s) {
-        p.dense_G[s] = 0;
-        p.dense_pitch[s] = 0;
-        if (use_v1 || no_dense || p.nhwc || p.W[s] % 4 != 0) continue;
-        int pitch = p.H[s] * p.W[s];                               // floats; (pitch / 4) odd: 8 consecutive planes hit 8 different 16-byte bank groups
-        if ((pitch / 4) % 2 == 0) pitch += 4;
-        int G = 32;
-        while (G >= 8 && (size_t)G * pitch * 4 > (size_t)kDnStageBytes) G >>= 1;
-        if (G < 8) continue;
-        p.dense_G[s] = G;
-        p.dense_pitch[s] = pitch;
-        wrow = max(wrow, ((p.H[s] + 3) & ~3) + ((p.W[s] + 3) & ~3) + 4);
-        any_dense = true;
-    }
-    cudaError_t e = cudaMemsetAsync(ws, 0, L.zero_bytes, st);
-    if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+    cudaError_t e;
     int rc;
-    if (use_v1) {
+    static const int force_group = env_int("OODB200_FMAP_GROUP_SCORE", -1);    // 1 / 0: override the caller's mode (A/B runs)
+    if (force_group >= 0) p.group_score = force_group;
+    const size_t box_smem = sizeof(float) * ((size_t)L.wstride + L.pooled_ld);
+    if (!p.group_score && box_smem <= 200 * 1024) {
+        // ---- one launch: a CTA per box plans, pools and scores it
+        if (box_smem > 48 * 1024 && box_smem > dv.box_attr[p.nhwc ? 1 : 0]) {
+            e = p.nhwc ? cudaFuncSetAttribute(box_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_smem)
+                       : cudaFuncSetAttribute(box_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_smem);
+            if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+            dv.box_attr[p.nhwc ? 1 : 0] = box_smem;
+        }
+        if (p.nhwc) box_kernel<true><<<p.n, kBxThreads, box_smem, st>>>(p);
+        else box_kernel<false><<<p.n, kBxThreads, box_smem, st>>>(p);
+        return check_launch(what);
+    }
+    // ---- large tables: memset -> plan + geometry -> gather -> score by (stride, class) groups
+    e = cudaMemsetAsync(p.counters, 0, L.zero_bytes, st);
+    if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+    {
         int G = 1;                                                 // CTAs per image: one warp per box in one round if possible
         while (G < 8 && (long long)G * kPgWarps * p.n_img < p.n) G *= 2;
         static const int g_force = env_int("OODB200_PLAN_CLUSTER", 0);   // tuning override (1, 2, 4 or 8)
@@ -1654,58 +1563,15 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
         if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
         rc = check_launch(what);
         if (rc) return rc;
-    } else {
-        plan2_kernel<<<(p.n + 7) / 8, 256, 0, st>>>(p);
-        rc = check_launch(what);
-        if (rc) return rc;
-        if (any_dense) {
-            const size_t smem = (size_t)kDnStages * kDnStageBytes + sizeof(float) * (size_t)kDnBatch * wrow;
-            OODB200_REQUIRE(smem <= 220 * 1024, "%s: dense pooling needs %zu bytes of shared memory", what, smem);
-            if (smem > dv.dense_attr) {
-                e = cudaFuncSetAttribute(dense_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
-                dv.dense_attr = smem;
-            }
-            long long ctas = ((long long)p.n + 0) * L.max_ns;      // never more CTAs than there can be jobs
-            if (ctas > dv.sms) ctas = dv.sms;
-            dense_pool_kernel<<<(int)ctas, kDnThreads, smem, st>>>(p, wrow);
-            rc = check_launch(what);
-            if (rc) return rc;
-        }
-    }
-    const int v2 = use_v1 ? 0 : 1;
-    const size_t xs_smem = v2 ? sizeof(float) * (size_t)kWarps * L.pooled_ld : 0;
-    OODB200_REQUIRE(xs_smem <= 96 * 1024, "%s: too many channels (%d)", what, L.pooled_ld);
-    if (dv.items_per_sm[v2] == 0) {
-        if (xs_smem > 48 * 1024 || dv.items_attr[v2] < xs_smem) {
-            if (xs_smem > 48 * 1024) {
-                cudaFuncSetAttribute(items_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs_smem);
-                cudaFuncSetAttribute(items_nhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs_smem);
-            }
-            dv.items_attr[v2] = xs_smem;
-        }
-        if ((v2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dv.items_per_sm[1], items_kernel<true>, kThreads, xs_smem)
-                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dv.items_per_sm[0], items_kernel<false>, kThreads, 0)) != cudaSuccess ||
-            dv.items_per_sm[v2] <= 0)
-            dv.items_per_sm[v2] = OODB200_FMAP_MIN_BLOCKS;
-        if ((v2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dv.items_per_sm_nhwc[1], items_nhwc_kernel<true>, kThreads, xs_smem)
-                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dv.items_per_sm_nhwc[0], items_nhwc_kernel<false>, kThreads, 0)) != cudaSuccess ||
-            dv.items_per_sm_nhwc[v2] <= 0)
-            dv.items_per_sm_nhwc[v2] = OODB200_FMAP_MIN_BLOCKS;
     }
     long long max_items = (long long)p.n * L.max_ns;
-    long long grid = (long long)dv.sms * (p.nhwc ? dv.items_per_sm_nhwc[v2] : dv.items_per_sm[v2]);   // persistent: every resident warp pulls from the queue
+    long long grid = (long long)dv.sms * (p.nhwc ? dv.items_per_sm_nhwc : dv.items_per_sm);   // persistent: every resident warp pulls from the queue
     if (grid * kWarps > max_items) grid = (max_items + kWarps - 1) / kWarps;
-    if (v2) {
-        if (p.nhwc) items_nhwc_kernel<true><<<(int)grid, kThreads, xs_smem, st>>>(p);
-        else items_kernel<true><<<(int)grid, kThreads, xs_smem, st>>>(p);
-    } else {
-        if (p.nhwc) items_nhwc_kernel<false><<<(int)grid, kThreads, 0, st>>>(p);
-        else items_kernel<false><<<(int)grid, kThreads, 0, st>>>(p);
-    }
+    if (p.nhwc) items_nhwc_kernel<<<(int)grid, kThreads, 0, st>>>(p);
+    else items_kernel<<<(int)grid, kThreads, 0, st>>>(p);
     rc = check_launch(what);
     if (rc) return rc;
-    if (p.cent && (use_v1 || p.group_score)) {
+    if (p.cent) {
         // shared memory per score CTA: the centroid tables of one (stride, class) group when they fit this budget
         // (OODB200_SCORE_SMEM_KB, default 72 KB = 3 CTAs per SM), at least the warp-private vectors of the global sweep
         static const int budget_env = env_int("OODB200_SCORE_SMEM_KB", 72);
@@ -1731,9 +1597,9 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
 
 using namespace oodb200;
 
-extern "C" int64_t oodb200_fmap_workspace_bytes(int n, int n_img, int nc, const int32_t* map_chw) {
-    if (!map_chw || nc < 0 || n_img < 0) return -1;
-    return (int64_t)layout_of(n, n_img, nc, map_chw).total;
+extern "C" int64_t oodb200_fmap_workspace_bytes(int n, int nc, const int32_t* map_chw) {
+    if (!map_chw || nc < 0) return -1;
+    return (int64_t)layout_of(n, nc, map_chw).total;
 }
 
 static int roi_pool_impl(int nhwc, const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,

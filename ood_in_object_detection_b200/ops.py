@@ -389,7 +389,7 @@ def _workspace(batch: DetectionBatch, nc: int) -> torch.Tensor:
     """Scratch for the pooling kernels, grown on demand: one per (device, stream) -- kernels on one stream reuse it in
     order, passes issued on different streams (sub-batches side by side) must not share work lists."""
     lib = _lib.load()
-    need = int(lib.oodb200_fmap_workspace_bytes(batch.n, batch.n_img, int(nc), batch.map_chw.ctypes.data_as(C.c_void_p)))
+    need = int(lib.oodb200_fmap_workspace_bytes(batch.n, int(nc), batch.map_chw.ctypes.data_as(C.c_void_p)))
     dev = batch.boxes.device
     key = (dev, torch.cuda.current_stream(dev).cuda_stream)
     ws = _workspaces.get(key)

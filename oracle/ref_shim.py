@@ -1,9 +1,11 @@
-"""Import shim for the UNMODIFIED reference at /root/reference.  Test infrastructure.
+"""Import shim for the UNMODIFIED reference.  Test / measurement infrastructure.
 
-Only usable where /root/reference exists (the build container).  It never
-travels to the GPU box: nothing in `-m gpu` tests, `smoke()` or `bench.py`
-calls `load()`.  Used by `tests/golden/make_golden.py` (to freeze golden
-vectors) and by the live-reference half of `tests/test_oracle_vs_golden.py`.
+Source of the modules: /root/reference where it exists (the build container), else oracle/_ref, the byte-compiled build
+of the same files that `oracle/make_ref.py` produces in the build container and that travels to the GPU box with the
+snapshot (git-ignored, like a compiled .so).  Used by `tests/golden/make_golden.py` (to freeze golden vectors),
+`tests/test_live_reference.py`, `tests/test_gpu_pipeline.py` (the reference's evaluation driver over this repo's
+classes) and by the reference arm / `cpu_baseline` leg of `bench.py` (the reference's own per-box code timed on the
+host cores).  Nothing under ood_in_object_detection_b200/ imports it.
 
 Why a shim is needed:
   * `ood_utils.py:26-37` pulls in matplotlib / hdbscan / skimage / tap / ...
@@ -24,14 +26,30 @@ import warnings
 from types import SimpleNamespace
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = "/root/reference"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_COMPILED = os.path.join(_HERE, "_ref")
+
+
+def _root() -> str:
+    forced = os.environ.get("OODB200_REF_ROOT")                  # tests: force the compiled build
+    if forced:
+        return forced
+    return "/root/reference" if os.path.isfile("/root/reference/ood_utils.py") else _COMPILED
+
+
+REFERENCE_ROOT = _root()
 _MISSING = ("matplotlib", "hdbscan", "skimage", "seaborn", "tap", "natsort", "umap", "ivis",
             "openpyxl", "adjustText")
 _loaded = None
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "ood_utils.py"))
+    return any(os.path.isfile(os.path.join(REFERENCE_ROOT, "ood_utils" + ext)) for ext in (".py", ".pyc"))
+
+
+def kind() -> str:
+    """"source" (/root/reference) or "compiled" (oracle/_ref)."""
+    return "source" if os.path.isfile(os.path.join(REFERENCE_ROOT, "ood_utils.py")) else "compiled"
 
 
 class _Stub(importlib.abc.MetaPathFinder, importlib.abc.Loader):
@@ -79,6 +97,8 @@ def load() -> SimpleNamespace:
         dataclasses.dataclass = _dc
     import cluster_utils
     import ood_utils
+    assert os.path.dirname(os.path.abspath(ood_utils.__file__)) == os.path.abspath(REFERENCE_ROOT), \
+        f"`ood_utils` resolved to {ood_utils.__file__}, not to the reference under {REFERENCE_ROOT}"
     from ultralytics.engine.results import Results
     from ultralytics.models.yolo.detect.predict import extract_roi_aligned_features_from_correct_stride
 
