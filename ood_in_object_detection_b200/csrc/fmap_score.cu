@@ -1200,226 +1200,317 @@ static ScoreKernel score_kernel_for(int mask) {
     }
 }
 
-// =============================================================================================== per-box kernel
-// box_kernel: ONE launch for the whole path when the centroid tables are small enough to be swept from L2 per box (the
-// usual K <= 16): one CTA of 4 warps per detection, everything the box needs happens inside it, and the phases of
-// different boxes overlap on an SM (4 CTAs resident) instead of being separate, individually latency-bound launches.
-//   phase 0  warp 0: RoIAlign geometry + separable weights into shared memory (geo_compute_into);
-//            warp 1: quirk-Q1 class / output slot from ballots over the image's own stride list (<= 10 loads of 32).
-//   phase 1  the 4 warps pool a quarter of the channels each with the 128-bit window gather of items_kernel
-//            (pool_dispatch; channels-last: nhwc_pool_item per slice of 32 channels); the vector stays in shared memory.
-//   phase 2  warp 0 normalises the vector (sklearn normalize; per-lane partition and butterfly of score_box_smem), then the
-//            K centroid rows are split over the warps (rows w, w + 4, ...; <= 4 rows x metrics in flight per warp, read
-//            from L2), first minimum over the warps, float64 threshold compare.  Same arithmetic as score_box_smem /
-//            vec_score_fast_kernel: fit-time and decision-time distances of the same vector are bit-identical.
-constexpr int kBxWarps = 4, kBxThreads = kBxWarps * 32;
-#ifndef OODB200_BOX_BLOCKS
-#define OODB200_BOX_BLOCKS 4
-#endif
+// =============================================================================================== channels-last pipeline
+// pipe_nhwc_kernel: ONE launch for the whole path on channels-last maps when the centroid tables are small enough to be
+// swept from L2 per box (the usual K <= 16).  In [H, W, C] memory a window row is ONE contiguous run of ww * C floats
+// (3 .. 40 KB): the window is staged into shared memory by the copy engine (cp.async.bulk, TMA) in pieces of <= 7 KB, and
+// every fetched 128-byte line is used in full.
+// Persistent grid; a CTA is kPipeGroups independent two-warp pipelines, each with its own 3-stage ring (8 pipelines = 144 KB
+// of copies in flight per SM):
+//   planner warp   next box from the atomic queue; quirk-Q1 class / output slot from ballots over the image's stride list;
+//                  RoIAlign geometry + separable weights into one of two descriptor slots (it runs ONE BOX AHEAD of the
+//                  consumer); then one bulk copy per piece of the window as ring stages free up.
+//   consumer warp  waits for a piece (mbarrier), adds w[cell] * v[cell][c] for its channels (lane = 4 channels x NJ, one
+//                  conflict-free LDS.128 per cell, no cross-lane reduction, fixed cell order), frees the stage; after the
+//                  last piece it normalises the vector and sweeps the K centroid rows from L2 (4 rows in flight), then
+//                  writes distance / arg-min / decision.  Planning, copies and scoring of consecutive boxes overlap.
+// Same per-lane partition and reduction tree as score_box_smem / vec_score_fast_kernel: fit-time and decision-time distances
+// of the same vector are bit-identical.
+constexpr int kPipeGroups = 4;                         // two-warp pipelines per CTA
+constexpr int kPipeThreads = kPipeGroups * 64;
+constexpr int kPipeStages = 3;
+constexpr int kPipeStageBytes = 7168;
+constexpr int kPipeMaxNJ = 5;                          // C <= 640 (beyond: the plan / gather / score sequence)
 
-template <bool NHWC>
-__global__ void __launch_bounds__(kBxThreads, OODB200_BOX_BLOCKS) box_kernel(const __grid_constant__ FmapParams p) {
-    extern __shared__ __align__(16) float bsm[];
-    float* s_w = bsm;                                  // wy[ext_y] | wx (wstride floats)
-    float* xs = bsm + p.wstride;                       // the pooled vector (pooled_ld floats)
-    __shared__ int s_plan[2];                          // class used, output slot
-    __shared__ int s_geo[8];                           // ylo, xa, wh, nxc, count bits, xoff, ww
-    __shared__ float s_d[kBxWarps][OODB200_N_METRICS];
-    __shared__ int s_a[kBxWarps][OODB200_N_METRICS];
-    __shared__ float s_n2v;
+struct PipeDesc {                                      // one box, written by the planner, read by the consumer
+    int box, s, cls_u, out;                            // box < 0: no more work
+    int y0, x0, wh, ww, xoff;                          // first live row / column, live rows / columns
+    float count;
+    int direct;                                        // 1: map not 16-byte aligned -> the consumer pools from global memory
+    unsigned long long mapp;
+};
+
+__device__ __forceinline__ void mb_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fs_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fs_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fs_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(fs_smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kPipeThreads, 2) pipe_nhwc_kernel(const __grid_constant__ FmapParams p, int group_bytes) {
+    extern __shared__ __align__(128) unsigned char psm[];
+    __shared__ __align__(8) uint64_t s_bar[kPipeGroups][2 * kPipeStages + 4];   // ring full / empty, descriptor full / empty
+    __shared__ PipeDesc s_desc[kPipeGroups][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x;
-    const int img = p.img_idx[b];
-    const int s = p.stride_idx[b];
-    const bool ok = s >= 0 && s <= 2;
-    if (warp == 0) {
-        if (ok) {
-            const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)b);
-            const BoxGeo g = geo_compute_into(p, s, bx, s_w, s_w + p.ext_y);
+    const int grp = warp >> 1;
+    const bool planner = (warp & 1) == 0;
+    unsigned char* gbase = psm + (size_t)grp * group_bytes;
+    float* ring = reinterpret_cast<float*>(gbase);                               // kPipeStages x kPipeStageBytes
+    float* s_wts = reinterpret_cast<float*>(gbase + kPipeStages * kPipeStageBytes);   // 2 x wstride: wy[ext_y] | wx
+    float* xs = s_wts + 2 * (size_t)p.wstride;                                   // pooled_ld floats
+    uint64_t* ring_full = &s_bar[grp][0];
+    uint64_t* ring_empty = &s_bar[grp][kPipeStages];
+    uint64_t* desc_full = &s_bar[grp][2 * kPipeStages];
+    uint64_t* desc_empty = &s_bar[grp][2 * kPipeStages + 2];
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < kPipeGroups; ++g)
+            for (int i = 0; i < 2 * kPipeStages + 4; ++i) mb_init(&s_bar[g][i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (planner) {
+        int pc = 0;                                    // pieces issued by this pipeline so far
+        for (int bc = 0;; ++bc) {
+            const int slot = bc & 1;
+            int b = 0;
+            if (lane == 0) b = atomicAdd(&p.counters[1], 1);
+            b = __shfl_sync(kFull, b, 0);
+            const bool more = b < p.n;
+            int img = 0, s = -1;
+            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (more) {
+                img = p.img_idx[b];
+                s = p.stride_idx[b];
+                bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)b);
+            }
+            const bool ok = more && s >= 0 && s <= 2;
+            int cls_u = 0, out = b;
+            if (more) {                                // quirk Q1 (ood_utils.py:2152-2154) from the image's own stride list
+                const int b0 = p.img_start[img], m = p.img_start[img + 1] - b0, bb = b - b0;
+                const int mycat = ok ? s : 3;
+                int cnt[4] = {0, 0, 0, 0};
+                int j = 0;
+                for (int c0 = 0; c0 < m; c0 += 32) {
+                    const int e = c0 + lane;
+                    const int st = e < m ? p.stride_idx[b0 + e] : -2;
+                    const int cat = e < m ? ((st >= 0 && st <= 2) ? st : 3) : 4;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const unsigned mk = __ballot_sync(kFull, cat == t);
+                        cnt[t] += __popc(mk);
+                        if (t == mycat) {
+                            if (c0 + 32 <= bb) j += __popc(mk);
+                            else if (c0 <= bb) j += __popc(mk & ((1u << (bb - c0)) - 1u));
+                        }
+                    }
+                }
+                int before = 0;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) if (t < mycat) before += cnt[t];
+                cls_u = p.cls ? p.cls[b] : 0;
+                if (p.compat_q1) {
+                    cls_u = ok ? p.cls[b0 + j] : -1;
+                    out = b0 + before + j;
+                }
+            }
+            if (bc >= 2) mbar_wait_bounded(&desc_empty[slot], (uint32_t)((bc >> 1) - 1) & 1u);   // the consumer is done with this slot
+            float* wy = s_wts + (size_t)slot * p.wstride;
+            BoxGeo g = {0, 0, 0, 0, 1.f, 0, 0};
+            unsigned long long mapp = 0;
+            if (ok) {
+                g = geo_compute_into(p, s, bx, wy, wy + p.ext_y);
+                mapp = (unsigned long long)p.map_ptrs[img * 3 + s];
+            }
+            const int C = ok ? p.C[s] : 4;
+            const int direct = ok && ((mapp & 15) != 0 || (C & 3) != 0);
             if (lane == 0) {
-                s_geo[0] = g.ylo; s_geo[1] = g.xa; s_geo[2] = g.wh; s_geo[3] = g.nxc;
-                s_geo[4] = __float_as_int(g.count); s_geo[5] = g.xoff; s_geo[6] = g.ww;
+                PipeDesc d;
+                d.box = more ? b : -1; d.s = s; d.cls_u = cls_u; d.out = out;
+                d.y0 = g.ylo; d.x0 = g.xa + g.xoff; d.wh = g.nxc ? g.wh : 0; d.ww = g.ww; d.xoff = g.xoff;
+                d.count = g.count; d.direct = direct; d.mapp = mapp;
+                s_desc[grp][slot] = d;
+                if (more) { p.cls_used[b] = cls_u; p.out_index[b] = out; }
             }
-        }
-    } else if (warp == 1) {
-        const int b0 = p.img_start[img], m = p.img_start[img + 1] - b0, bb = b - b0;
-        const int mycat = ok ? s : 3;
-        int cnt[4] = {0, 0, 0, 0};
-        int j = 0;                                     // boxes of my category before me (Q1: the in-stride index)
-        for (int c0 = 0; c0 < m; c0 += 32) {
-            const int e = c0 + lane;
-            const int st = e < m ? p.stride_idx[b0 + e] : -2;
-            const int cat = e < m ? ((st >= 0 && st <= 2) ? st : 3) : 4;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const unsigned mk = __ballot_sync(kFull, cat == t);
-                cnt[t] += __popc(mk);
-                if (t == mycat) {
-                    if (c0 + 32 <= bb) j += __popc(mk);
-                    else if (c0 <= bb) j += __popc(mk & ((1u << (bb - c0)) - 1u));
-                }
-            }
-        }
-        int before = 0;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) if (t < mycat) before += cnt[t];
-        int cls_u = p.cls ? p.cls[b] : 0, out = b;
-        if (p.compat_q1) {                             // ood_utils.py:2152-2154: class of the box with the same in-stride index
-            cls_u = ok ? p.cls[b0 + j] : -1;
-            out = b0 + before + j;
-        }
-        if (lane == 0) { s_plan[0] = cls_u; s_plan[1] = out; p.cls_used[b] = cls_u; p.out_index[b] = out; }
-    }
-    __syncthreads();
-    const int cls_u = s_plan[0], out = s_plan[1];
-    if (!ok) {                                         // never pooled by the reference either: answered here
-        if (warp == 0 && p.cent && lane < OODB200_N_METRICS && (p.metric_mask >> lane & 1)) {
-            const size_t o = (size_t)lane * p.n + out;
-            p.dist[o] = nanf("");
-            p.argmin[o] = -1;
-            p.decision[o] = 0;
-        }
-        return;
-    }
-    // ---- phase 1: pooling
-    const int C = p.C[s], W = p.W[s], HW = p.H[s] * W;
-    const float* __restrict__ imgp = p.map_ptrs[img * 3 + s];
-    float* __restrict__ out1 = p.pooled_user ? p.pooled_user + (size_t)out * p.pooled_user_ld : nullptr;
-    const int4 geo = make_int4(s_geo[0], s_geo[1], s_geo[2], s_geo[3]);
-    const float count = __int_as_float(s_geo[4]);
-    if (geo.w == 0) {                                  // no sample inside the map (Q5): all-zero vector
-        for (int c = threadIdx.x; c < C; c += kBxThreads) { xs[c] = 0.f; if (out1) out1[c] = 0.f; }
-    } else if (!NHWC) {
-        const int cpw = ((C + 32 * kBxWarps - 1) / (32 * kBxWarps)) * 32;      // channels per warp, a multiple of 32
-        const int c_lo = warp * cpw, c_hi = min(C, c_lo + cpw);
-        if (c_lo < C) {
-            const bool vec = (W % 4 == 0) && (((uintptr_t)imgp & 15) == 0) && (HW % 4 == 0);
-            if (vec) pool_dispatch(imgp, C, HW, W, geo, s_w, s_w + p.ext_y, count, c_lo, c_hi, xs, out1);
-            else pool_scalar(imgp, HW, W, geo.x, geo.y, geo.z, geo.w, s_w, s_w + p.ext_y, count, c_lo, c_hi, xs, out1);
-        }
-    } else {
-        NhwcItem a;
-        a.img = imgp; a.box = b; a.s = s; a.out = out; a.y0 = geo.x; a.xoff = s_geo[5]; a.x0 = geo.y + s_geo[5];
-        a.wh = geo.z; a.ww = s_geo[6]; a.count = count;
-        for (int sl = warp; sl * kSliceNhwc < C; sl += kBxWarps) {
-            a.c_lo = sl * kSliceNhwc;
-            nhwc_pool_item(p, a, s_w, xs, out1);
-        }
-    }
-    __syncthreads();
-    if (!p.cent) return;
-    // ---- phase 2: distance to the nearest centroid of (class used, stride), threshold
-    const bool cls_ok = cls_u >= 0 && cls_u < p.nc;
-    const int K = cls_ok ? p.cent_k[s * p.nc + cls_u] : 0;
-    const int64_t off = K > 0 ? p.cent_off[s * p.nc + cls_u] : 0;
-    const bool vecs = (C % 4 == 0) && (off % 4 == 0) && ((((uintptr_t)p.cent) | ((uintptr_t)p.cent_unit)) & 15) == 0;
-    if (!vecs) {                                       // odd shapes: the row goes to the workspace and warp 0 sweeps like finalize()
-        if (warp == 0) {
-            float* row = p.pooled + (size_t)out * p.pooled_ld;
-            for (int c = lane; c < C; c += 32) row[c] = xs[c];
-            __threadfence_block();
             __syncwarp();
-            const Best bb = finalize_generic(row, C, p.normalize, p.metric_mask, p.cent + off, p.cent_unit + off, K);
-            write_result(p, s, cls_u, cls_ok, K, out, bb);
+            if (lane == 0) mb_arrive(&desc_full[slot]);
+            if (!more) break;
+            if (ok && !direct && g.nxc && lane == 0) {                            // the window, row by row, in pieces of <= cps cells
+                const int W = p.W[s];
+                const int cps = kPipeStageBytes / (C * 4);
+                const float* __restrict__ src = reinterpret_cast<const float*>(mapp);
+                for (int r = 0; r < g.wh; ++r)
+                    for (int a = 0; a < g.ww; a += cps) {
+                        const int st = pc % kPipeStages;
+                        if (pc >= kPipeStages) mbar_wait_bounded(&ring_empty[st], (uint32_t)((pc / kPipeStages) - 1) & 1u);
+                        const uint32_t bytes = (uint32_t)min(cps, g.ww - a) * (uint32_t)C * 4u;
+                        mb_expect_tx(&ring_full[st], bytes);
+                        bulk_g2s(ring + (size_t)st * (kPipeStageBytes / 4),
+                                 src + ((size_t)(g.ylo + r) * W + (g.xa + g.xoff + a)) * C, bytes, &ring_full[st]);
+                        ++pc;
+                    }
+            }
+            pc = __shfl_sync(kFull, pc, 0);
         }
         return;
     }
-    const bool want_l1 = p.metric_mask & (1 << OODB200_METRIC_L1);
-    const bool want_l2 = p.metric_mask & (1 << OODB200_METRIC_L2);
-    const bool want_cos = p.metric_mask & (1 << OODB200_METRIC_COS);
-    const int nj = (C + 127) >> 7;
-    if (warp == 0) {                                   // ood_utils.py:2409 -> sklearn normalize; cosine re-normalises (pairwise.py:1171-1182)
-        float ss = 0.f;
-        for (int t = 0; t < nj; ++t) {
-            const int d = lane * 4 + 128 * t;
-            if (d < C) {
-                const float4 v = *reinterpret_cast<const float4*>(xs + d);
-                ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    // ---- consumer warp
+    int pc = 0;
+    for (int bc = 0;; ++bc) {
+        const int slot = bc & 1;
+        mbar_wait_bounded(&desc_full[slot], (uint32_t)(bc >> 1) & 1u);
+        const PipeDesc d = s_desc[grp][slot];
+        if (d.box < 0) break;
+        const int s = d.s, out = d.out;
+        if (s < 0 || s > 2) {                          // never pooled by the reference either: answered here
+            if (p.cent && lane < OODB200_N_METRICS && (p.metric_mask >> lane & 1)) {
+                const size_t o = (size_t)lane * p.n + out;
+                p.dist[o] = nanf("");
+                p.argmin[o] = -1;
+                p.decision[o] = 0;
             }
+            __syncwarp();
+            if (lane == 0) mb_arrive(&desc_empty[slot]);
+            continue;
         }
-        float n2v = 1.f;
-        if (p.normalize) {
-            float nrm = sqrtf(warp_sum(ss));
-            if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;   // _handle_zeros_in_scale
-            ss = 0.f;
-            for (int t = 0; t < nj; ++t) {
-                const int d = lane * 4 + 128 * t;
-                if (d < C) {
-                    float4 v = *reinterpret_cast<const float4*>(xs + d);
-                    v.x = __fdiv_rn(v.x, nrm); v.y = __fdiv_rn(v.y, nrm); v.z = __fdiv_rn(v.z, nrm); v.w = __fdiv_rn(v.w, nrm);
-                    *reinterpret_cast<float4*>(xs + d) = v;
-                    ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-                }
-            }
-        }
-        if (want_cos) {
-            n2v = sqrtf(warp_sum(ss));
-            if (n2v < 10.f * FLT_EPSILON) n2v = 1.f;
-        }
-        if (lane == 0) s_n2v = n2v;
-    }
-    __syncthreads();
-    const float n2v = s_n2v;
-    Best bst = {{FLT_MAX, FLT_MAX, FLT_MAX}, {INT_MAX, INT_MAX, INT_MAX}};
-    for (int k0 = warp; k0 < K; k0 += 4 * kBxWarps) {  // rows k0, k0 + 4, k0 + 8, k0 + 12 of this warp: independent reductions
-        float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f}, ac[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int t = 0; t < nj; ++t) {
-            const int d = lane * 4 + 128 * t;
-            if (d < C) {
-                const float4 x = *reinterpret_cast<const float4*>(xs + d);
+        const int C = p.C[s];
+        const int nj = (C + 127) >> 7;
+        const float* __restrict__ wy = s_wts + (size_t)slot * p.wstride;
+        const float* __restrict__ wx = wy + p.ext_y + d.xoff;
+        float* __restrict__ out1 = p.pooled_user ? p.pooled_user + (size_t)out * p.pooled_user_ld : nullptr;
+        if (d.direct) {                                // odd alignment / channel count: lanes over channels, scalar loads
+            NhwcItem a;
+            a.img = reinterpret_cast<const float*>(d.mapp); a.box = d.box; a.s = s; a.out = out; a.y0 = d.y0; a.x0 = d.x0;
+            a.wh = d.wh; a.ww = d.ww; a.xoff = d.xoff; a.count = d.count;
+            for (a.c_lo = 0; a.c_lo < C; a.c_lo += kSliceNhwc) pool_nhwc_scalar(p, a, wy, xs, out1);
+        } else {
+            float4 acc[kPipeMaxNJ];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int k = min(k0 + kBxWarps * r, K - 1);         // short batch: repeat the last row, result dropped
-                    if (want_l1 || want_l2) {
-                        const float4 c = __ldg(reinterpret_cast<const float4*>(p.cent + off + (int64_t)k * C + d));
-                        const float e0 = x.x - c.x, e1 = x.y - c.y, e2 = x.z - c.z, e3 = x.w - c.w;
-                        a1[r] += (fabsf(e0) + fabsf(e1)) + (fabsf(e2) + fabsf(e3));
-                        a2[r] = fmaf(e0, e0, a2[r]); a2[r] = fmaf(e1, e1, a2[r]); a2[r] = fmaf(e2, e2, a2[r]); a2[r] = fmaf(e3, e3, a2[r]);
+            for (int t = 0; t < kPipeMaxNJ; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int cps = kPipeStageBytes / (C * 4);
+            for (int r = 0; r < d.wh; ++r) {
+                const float wr = wy[r];
+                for (int a = 0; a < d.ww; a += cps) {
+                    const int st = pc % kPipeStages;
+                    mbar_wait_bounded(&ring_full[st], (uint32_t)(pc / kPipeStages) & 1u);
+                    const float* __restrict__ piece = ring + (size_t)st * (kPipeStageBytes / 4) + lane * 4;
+                    const int nc_ = min(cps, d.ww - a);
+                    for (int x = 0; x < nc_; ++x) {
+                        const float w = wr * wx[a + x];
+#pragma unroll
+                        for (int t = 0; t < kPipeMaxNJ; ++t)
+                            if (t < nj && lane * 4 + 128 * t < C) {
+                                const float4 v = *reinterpret_cast<const float4*>(piece + (size_t)x * C + 128 * t);
+                                acc[t].x = fmaf(w, v.x, acc[t].x); acc[t].y = fmaf(w, v.y, acc[t].y);
+                                acc[t].z = fmaf(w, v.z, acc[t].z); acc[t].w = fmaf(w, v.w, acc[t].w);
+                            }
                     }
-                    if (want_cos) {
-                        const float4 u = __ldg(reinterpret_cast<const float4*>(p.cent_unit + off + (int64_t)k * C + d));
-                        ac[r] = fmaf(x.x, u.x, ac[r]); ac[r] = fmaf(x.y, u.y, ac[r]); ac[r] = fmaf(x.z, u.z, ac[r]); ac[r] = fmaf(x.w, u.w, ac[r]);
+                    __syncwarp();
+                    if (lane == 0) mb_arrive(&ring_empty[st]);
+                    ++pc;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < kPipeMaxNJ; ++t) {
+                const int c = lane * 4 + 128 * t;
+                if (t < nj && c < C) {                 // average over the sample grid (roi_align.py:192-196); no sample inside the map (Q5): 0
+                    const float4 val = d.wh ? make_float4(__fdiv_rn(acc[t].x, d.count), __fdiv_rn(acc[t].y, d.count),
+                                                          __fdiv_rn(acc[t].z, d.count), __fdiv_rn(acc[t].w, d.count))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(xs + c) = val;
+                    if (out1) { out1[c] = val.x; out1[c + 1] = val.y; out1[c + 2] = val.z; out1[c + 3] = val.w; }
+                }
+            }
+        }
+        __syncwarp();
+        if (p.cent) {
+            // ---- distance to the nearest centroid of (class used, stride), threshold: one warp, 4 rows in flight
+            const int cls_u = d.cls_u;
+            const bool cls_ok = cls_u >= 0 && cls_u < p.nc;
+            const int K = cls_ok ? p.cent_k[s * p.nc + cls_u] : 0;
+            const int64_t off = K > 0 ? p.cent_off[s * p.nc + cls_u] : 0;
+            const bool vecs = (C % 4 == 0) && (off % 4 == 0) && ((((uintptr_t)p.cent) | ((uintptr_t)p.cent_unit)) & 15) == 0;
+            if (!vecs) {                               // odd shapes: through the workspace row, like finalize()
+                float* row = p.pooled + (size_t)out * p.pooled_ld;
+                for (int c = lane; c < C; c += 32) row[c] = xs[c];
+                __threadfence_block();
+                __syncwarp();
+                const Best bb = finalize_generic(row, C, p.normalize, p.metric_mask, p.cent + off, p.cent_unit + off, K);
+                write_result(p, s, cls_u, cls_ok, K, out, bb);
+            } else {
+                const bool want_l1 = p.metric_mask & (1 << OODB200_METRIC_L1);
+                const bool want_l2 = p.metric_mask & (1 << OODB200_METRIC_L2);
+                const bool want_cos = p.metric_mask & (1 << OODB200_METRIC_COS);
+                float4 x[kPipeMaxNJ];
+                float ss = 0.f;
+#pragma unroll
+                for (int t = 0; t < kPipeMaxNJ; ++t) {
+                    const int c = lane * 4 + 128 * t;
+                    x[t] = (t < nj && c < C) ? *reinterpret_cast<const float4*>(xs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    ss = fmaf(x[t].x, x[t].x, ss); ss = fmaf(x[t].y, x[t].y, ss); ss = fmaf(x[t].z, x[t].z, ss); ss = fmaf(x[t].w, x[t].w, ss);
+                }
+                float n2v = 1.f;
+                if (p.normalize) {                     // ood_utils.py:2409 -> sklearn normalize
+                    float nrm = sqrtf(warp_sum(ss));
+                    if (nrm < 10.f * FLT_EPSILON) nrm = 1.f;       // _handle_zeros_in_scale
+                    ss = 0.f;
+#pragma unroll
+                    for (int t = 0; t < kPipeMaxNJ; ++t) {
+                        x[t].x = __fdiv_rn(x[t].x, nrm); x[t].y = __fdiv_rn(x[t].y, nrm);
+                        x[t].z = __fdiv_rn(x[t].z, nrm); x[t].w = __fdiv_rn(x[t].w, nrm);
+                        ss = fmaf(x[t].x, x[t].x, ss); ss = fmaf(x[t].y, x[t].y, ss); ss = fmaf(x[t].z, x[t].z, ss); ss = fmaf(x[t].w, x[t].w, ss);
                     }
                 }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (want_l1) a1[r] += __shfl_xor_sync(kFull, a1[r], o);
-                if (want_l2) a2[r] += __shfl_xor_sync(kFull, a2[r], o);
-                if (want_cos) ac[r] += __shfl_xor_sync(kFull, ac[r], o);
-            }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {                  // rows in increasing order, strict '<': first minimum
-            const int k = k0 + kBxWarps * r;
-            if (k < K) {
-                if (want_l1 && a1[r] < bst.d[0]) { bst.d[0] = a1[r]; bst.a[0] = k; }
-                if (want_l2) { const float v = sqrtf(fmaxf(a2[r], 0.f)); if (v < bst.d[1]) { bst.d[1] = v; bst.a[1] = k; } }
-                if (want_cos) {                        // X / ||X|| applied to the sum (same value to float32 rounding)
-                    const float v = fminf(fmaxf(1.0f - __fdiv_rn(ac[r], n2v), 0.f), 2.f);
-                    if (v < bst.d[2]) { bst.d[2] = v; bst.a[2] = k; }
+                if (want_cos) {                        // cosine_distances re-normalises X (pairwise.py:1171-1182)
+                    n2v = sqrtf(warp_sum(ss));
+                    if (n2v < 10.f * FLT_EPSILON) n2v = 1.f;
                 }
+                Best bst = {{FLT_MAX, FLT_MAX, FLT_MAX}, {-1, -1, -1}};
+                for (int k0 = 0; k0 < K; k0 += 4) {    // rows k0 .. k0 + 3: independent reductions
+                    float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f}, ac[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int t = 0; t < kPipeMaxNJ; ++t) {
+                        const int c = lane * 4 + 128 * t;
+                        if (t < nj && c < C) {
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const int k = min(k0 + r, K - 1);                 // short batch: repeat the last row, result dropped
+                                if (want_l1 || want_l2) {
+                                    const float4 cc = __ldg(reinterpret_cast<const float4*>(p.cent + off + (int64_t)k * C + c));
+                                    const float e0 = x[t].x - cc.x, e1 = x[t].y - cc.y, e2 = x[t].z - cc.z, e3 = x[t].w - cc.w;
+                                    a1[r] += (fabsf(e0) + fabsf(e1)) + (fabsf(e2) + fabsf(e3));
+                                    a2[r] = fmaf(e0, e0, a2[r]); a2[r] = fmaf(e1, e1, a2[r]); a2[r] = fmaf(e2, e2, a2[r]); a2[r] = fmaf(e3, e3, a2[r]);
+                                }
+                                if (want_cos) {
+                                    const float4 u = __ldg(reinterpret_cast<const float4*>(p.cent_unit + off + (int64_t)k * C + c));
+                                    ac[r] = fmaf(x[t].x, u.x, ac[r]); ac[r] = fmaf(x[t].y, u.y, ac[r]);
+                                    ac[r] = fmaf(x[t].z, u.z, ac[r]); ac[r] = fmaf(x[t].w, u.w, ac[r]);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (want_l1) a1[r] += __shfl_xor_sync(kFull, a1[r], o);
+                            if (want_l2) a2[r] += __shfl_xor_sync(kFull, a2[r], o);
+                            if (want_cos) ac[r] += __shfl_xor_sync(kFull, ac[r], o);
+                        }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {      // rows in increasing order, strict '<': first minimum
+                        const int k = k0 + r;
+                        if (k < K) {
+                            if (want_l1 && a1[r] < bst.d[0]) { bst.d[0] = a1[r]; bst.a[0] = k; }
+                            if (want_l2) { const float v = sqrtf(fmaxf(a2[r], 0.f)); if (v < bst.d[1]) { bst.d[1] = v; bst.a[1] = k; } }
+                            if (want_cos) {            // X / ||X|| applied to the sum (same value to float32 rounding)
+                                const float v = fminf(fmaxf(1.0f - __fdiv_rn(ac[r], n2v), 0.f), 2.f);
+                                if (v < bst.d[2]) { bst.d[2] = v; bst.a[2] = k; }
+                            }
+                        }
+                    }
+                }
+                write_result(p, s, cls_u, cls_ok, K, out, bst);
             }
         }
-    }
-    if (lane < OODB200_N_METRICS) {
-        s_d[warp][lane] = lane == 0 ? bst.d[0] : (lane == 1 ? bst.d[1] : bst.d[2]);
-        s_a[warp][lane] = lane == 0 ? bst.a[0] : (lane == 1 ? bst.a[1] : bst.a[2]);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        Best fin = {{FLT_MAX, FLT_MAX, FLT_MAX}, {INT_MAX, INT_MAX, INT_MAX}};
-#pragma unroll
-        for (int m = 0; m < OODB200_N_METRICS; ++m)
-#pragma unroll
-            for (int w = 0; w < kBxWarps; ++w) {       // first minimum over the warps: smaller distance, then smaller index
-                const float od = s_d[w][m];
-                const int oa = s_a[w][m];
-                if (od < fin.d[m] || (od == fin.d[m] && oa < fin.a[m])) { fin.d[m] = od; fin.a[m] = oa; }
-            }
-        write_result(p, s, cls_u, cls_ok, K, out, fin);
+        __syncwarp();
+        if (lane == 0) mb_arrive(&desc_empty[slot]);
     }
 }
 
@@ -1462,7 +1553,7 @@ static WorkspaceLayout layout_of(int n, int nc, const int32_t* map_chw) {
     return L;
 }
 
-struct DeviceInfo { bool init; int sms, items_per_sm, items_per_sm_nhwc; size_t score_attr[8], box_attr[2]; };
+struct DeviceInfo { bool init; int sms, items_per_sm, items_per_sm_nhwc; size_t score_attr[8], pipe_attr; };
 static DeviceInfo g_dev[64];
 
 static DeviceInfo& device_info() {                     // per device: SM count, occupancy, attributes already raised
@@ -1526,17 +1617,24 @@ static int launch_fmap(FmapParams& p, const int32_t* map_chw, const float* scale
     int rc;
     static const int force_group = env_int("OODB200_FMAP_GROUP_SCORE", -1);    // 1 / 0: override the caller's mode (A/B runs)
     if (force_group >= 0) p.group_score = force_group;
-    const size_t box_smem = sizeof(float) * ((size_t)L.wstride + L.pooled_ld);
-    if (!p.group_score && box_smem <= 200 * 1024) {
-        // ---- one launch: a CTA per box plans, pools and scores it
-        if (box_smem > 48 * 1024 && box_smem > dv.box_attr[p.nhwc ? 1 : 0]) {
-            e = p.nhwc ? cudaFuncSetAttribute(box_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_smem)
-                       : cudaFuncSetAttribute(box_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_smem);
+    static const int no_pipe = env_int("OODB200_FMAP_NO_PIPE", 0);              // 1: the plan / gather / score sequence (A/B runs)
+    int cmax = 0;
+    for (int s = 0; s < 3; ++s) cmax = max(cmax, p.C[s]);
+    const size_t group_bytes = ((size_t)kPipeStages * kPipeStageBytes + sizeof(float) * (2 * (size_t)L.wstride + L.pooled_ld) + 127) & ~(size_t)127;
+    const size_t pipe_smem = group_bytes * kPipeGroups;
+    if (p.nhwc && !p.group_score && !no_pipe && cmax <= 128 * kPipeMaxNJ && pipe_smem <= 110 * 1024) {
+        // ---- channels-last, small tables: one persistent launch, windows staged by TMA, plan / pool / score pipelined per box
+        e = cudaMemsetAsync(p.counters, 0, 16, st);
+        if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+        if (pipe_smem > dv.pipe_attr) {
+            e = cudaFuncSetAttribute(pipe_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem);
             if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
-            dv.box_attr[p.nhwc ? 1 : 0] = box_smem;
+            dv.pipe_attr = pipe_smem;
         }
-        if (p.nhwc) box_kernel<true><<<p.n, kBxThreads, box_smem, st>>>(p);
-        else box_kernel<false><<<p.n, kBxThreads, box_smem, st>>>(p);
+        long long ctas = 2LL * dv.sms;
+        const long long need = ((long long)p.n + kPipeGroups - 1) / kPipeGroups;
+        if (ctas > need) ctas = need;
+        pipe_nhwc_kernel<<<(int)ctas, kPipeThreads, pipe_smem, st>>>(p, (int)group_bytes);
         return check_launch(what);
     }
     // ---- large tables: memset -> plan + geometry -> gather -> score by (stride, class) groups
