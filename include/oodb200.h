@@ -36,9 +36,6 @@ extern "C" {
 #define OODB200_METRIC_L2 1
 #define OODB200_METRIC_COS 2
 #define OODB200_N_METRICS 3
-/* flag bits of oodb200_fmap_score_*_f32 */
-#define OODB200_FMAP_COMPAT_Q1 1
-#define OODB200_FMAP_GROUP_SCORE 2
 
 /* logit-method slots (reference: /root/reference/ood_utils.py:1388-1443; MaxLogit has no
  * counterpart there) */
@@ -96,12 +93,9 @@ int64_t oodb200_fmap_workspace_bytes(int n, int nc, const int32_t* map_chw);
  * `compute_distance` (:2422-2430).
  *   cls          [n] predicted class of every box (`res.boxes.cls`)
  *   img_start    [n_img+1] int32 prefix of boxes per image
- *   flags        OODB200_FMAP_COMPAT_Q1 = the reference's behaviour (ood_utils.py:2152-2154): the class
- *                used for the centroid / threshold lookup is the one of the box with the same IN-STRIDE index, and
- *                results are written stride-major within each image; without it: class of the box itself, box order.
- *                OODB200_FMAP_GROUP_SCORE = plan -> gather -> score by (stride, class) groups with the group's centroid
- *                rows staged in shared memory (large tables: K * C_s * 4 bytes beyond what a per-box sweep from L2
- *                should re-read, e.g. K = 64) instead of the single per-box kernel.  Same results.
+ *   compat_q1    1 = the reference's behaviour (ood_utils.py:2152-2154): the class used for
+ *                the centroid / threshold lookup is the one of the box with the same IN-STRIDE index, and
+ *                results are written stride-major within each image.  0: class of the box itself, box order.
  *   metric_mask  OR of (1<<OODB200_METRIC_*): every requested metric is scored in the same pass
  *   normalize    1 = L2-normalise the pooled vector first (vanilla FMap methods); 0 = score as is
  *   cent         packed float32 centroids; (stride s, class c) has cent_k[s*nc+c] rows of C_s floats
@@ -117,7 +111,7 @@ int64_t oodb200_fmap_workspace_bytes(int n, int nc, const int32_t* map_chw);
  */
 int oodb200_fmap_score_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
                            const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
-                           const int32_t* cls, const int32_t* img_start, int flags, int n,
+                           const int32_t* cls, const int32_t* img_start, int compat_q1, int n,
                            int metric_mask, int normalize,
                            const float* cent, const float* cent_unit, const int64_t* cent_off, const int32_t* cent_k,
                            int nc, const double* thr,
@@ -135,7 +129,7 @@ int oodb200_roi_pool_nhwc_f32(const float* const* map_ptrs, const int32_t* map_c
                          float* out, int out_ld, void* workspace, int64_t workspace_bytes, void* stream);
 int oodb200_fmap_score_nhwc_f32(const float* const* map_ptrs, const int32_t* map_chw, const float* scale, int n_img,
                            const float* boxes, const int32_t* img_idx, const int32_t* stride_idx,
-                           const int32_t* cls, const int32_t* img_start, int flags, int n,
+                           const int32_t* cls, const int32_t* img_start, int compat_q1, int n,
                            int metric_mask, int normalize,
                            const float* cent, const float* cent_unit, const int64_t* cent_off, const int32_t* cent_k,
                            int nc, const double* thr,

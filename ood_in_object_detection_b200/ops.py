@@ -433,24 +433,13 @@ def alloc_fmap_scores(n: int, device, cmax: int = 0, want_pooled: bool = False, 
                       out_index=torch.empty(n, dtype=torch.int32, device=device) if want_plan else None)
 
 
-FMAP_COMPAT_Q1, FMAP_GROUP_SCORE = 1, 2
-GROUP_SCORE_TABLE_BYTES = 96 << 10   # per-box sweep of the (class, stride) tables from L2 up to this size, group scoring beyond
-
-
 def fmap_score(batch: DetectionBatch, table: CentroidTable, metric_mask: int, normalize: bool = True,
                compat_q1: bool = True, want_pooled: bool = False, want_plan: bool = False,
-               out: Optional[FmapScores] = None, group_score: Optional[bool] = None) -> FmapScores:
+               out: Optional[FmapScores] = None) -> FmapScores:
     """K1+K2 fused pass over every box of the batch.  compat_q1=True reproduces the reference's class lookup by
-    in-stride index and its stride-major output order; False = class of the box itself, box order.
-    group_score: score by (stride, class) groups with the tables staged in shared memory (default: when the largest
-    group's tables exceed GROUP_SCORE_TABLE_BYTES, e.g. K = 64 clusters of 640 floats) -- same results either way."""
+    in-stride index and its stride-major output order; False = class of the box itself, box order."""
     lib = _lib.load()
     n = batch.n
-    if group_score is None:
-        ntab = (1 if metric_mask & 0b011 else 0) + (1 if metric_mask & 0b100 else 0)
-        kc = (table.k_host.astype(np.int64) * batch.map_chw.reshape(3, 3)[:, 0:1].astype(np.int64)).max() if table.k_host.size else 0
-        group_score = int(kc) * 4 * ntab > GROUP_SCORE_TABLE_BYTES
-    flags = (FMAP_COMPAT_Q1 if compat_q1 else 0) | (FMAP_GROUP_SCORE if group_score else 0)
     if out is None:
         cmax = int(batch.map_chw.reshape(3, 3)[:, 0].max())
         out = alloc_fmap_scores(n, batch.boxes.device, cmax, want_pooled, want_plan)
@@ -459,7 +448,7 @@ def fmap_score(batch: DetectionBatch, table: CentroidTable, metric_mask: int, no
     _lib.check(fn(
         _ptr(batch.map_ptrs), batch.map_chw.ctypes.data_as(C.c_void_p), batch.scale.ctypes.data_as(C.c_void_p),
         batch.n_img, _ptr(batch.boxes), _ptr(batch.img_idx), _ptr(batch.stride_idx), _ptr(batch.cls),
-        _ptr(batch.img_start), int(flags), n, int(metric_mask), int(bool(normalize)),
+        _ptr(batch.img_start), int(bool(compat_q1)), n, int(metric_mask), int(bool(normalize)),
         _ptr(table.cent), _ptr(table.cent_unit), _ptr(table.cent_off), _ptr(table.cent_k), table.nc, _ptr(table.thr),
         _ptr(out.dist), _ptr(out.argmin), _ptr(out.decision),
         _ptr(out.pooled), int(out.pooled.stride(0)) if out.pooled is not None else 0,
