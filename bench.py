@@ -520,7 +520,7 @@ def run_fit(device, world, rank, n_total, reps, warm, variant="realistic"):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         cur = dict(total=float(t[0]), lloyd=float(t[1]), init=float(t[2]), center=float(t[3]), seeding=r.seconds.get("seeding"),
                    iters=int(r.seconds["lloyd_iters"]), issued=int(r.seconds.get("lloyd_issued", 0)),
-                   n_iter=[int(v) for v in r.n_iter], strict=all(r.strict), thr0=thr[0])
+                   n_iter=[int(v) for v in r.n_iter], strict=all(r.strict), thr0=thr[0], collective=r.seconds.get("collective"))
         if it >= warm and (best is None or cur["total"] < best["total"]):
             best = cur
     rows = torch.tensor([x.shape[0]], dtype=torch.int64, device=device)
@@ -542,7 +542,7 @@ def run_fit(device, world, rank, n_total, reps, warm, variant="realistic"):
             "means_scores_thresholds_ms": 1e3 * (best["total"] - best["init"] - best["lloyd"] - best["center"]),
             "fit_ms": 1e3 * best["total"], "rows_on_fullest_rank": int(rows_max),
             "e2e_vectors_per_s": n_total / best["total"], "strict_convergence": best["strict"], "scaling": "strong",
-            "collective": "1 all-reduce per Lloyd iteration + 1 per radix pass" if world > 1 else "none (1 GPU)",
+            "collective": (f"per Lloyd iteration: {best['collective']}; per radix pass: 1 NCCL all-reduce of histograms") if world > 1 else "none (1 GPU)",
             "roofline": {"bound": "hbm", "kernel": "kmeans_step_tc_kernel (tcgen05 assignment + partial sums; + reduce/update, host loop)",
                          "unit": "GB/s",
                          "achieved": it_bytes * (vec_iters / n_total / max(best["iters"], 1)) / world / lloyd_per_iter / 1e9, "peak": peak,

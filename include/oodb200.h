@@ -230,6 +230,19 @@ int oodb200_kmeans_update_f32(const float* sums, const float* counts, const floa
                               const int32_t* active, int n_seg, int k, int dim, float* cent_new, float* shift_sq,
                               int32_t* n_empty, void* stream);
 
+/* ---- the Lloyd iteration's all-reduce fused into the centre update (N > 1 ranks on one NVLink / NVSwitch node):
+ * every rank has written its reduced partials [n_seg*k*dim sums | n_seg*k counts | n_seg changed-label counts] into a
+ * SYMMETRIC buffer (torch.distributed._symmetric_memory); peer_bufs is the device array of the n_peers buffer addresses as
+ * mapped into this process.  The kernel reads every peer's values straight over NVLink, adds them in rank order (every
+ * rank computes identical bits) and does what oodb200_kmeans_update_f32 does; the summed counts and changed-label counts
+ * are written to cnts_out [n_seg, k] / chg_out [n_seg] for oodb200_kmeans_converge_f32.  The caller orders the ranks
+ * around it (a device-side barrier before: all partials written; buffers alternate between iterations).
+ * Replaces the NCCL all-reduce + update of `kmeans.kmeans_fit` (same sklearn statements as kmeans_update). */
+int oodb200_kmeans_update_peers_f32(const float* const* peer_bufs, int n_peers, int64_t counts_off, int64_t chg_off,
+                                    const float* cent_old, const int32_t* seg_k, const int32_t* active, int n_seg,
+                                    int k, int dim, float* cent_new, float* shift_sq, int32_t* n_empty,
+                                    float* cnts_out, float* chg_out, void* stream);
+
 /* ---- Lloyd convergence bookkeeping on the device: replaces the per-iteration host decisions of sklearn's
  * `_kmeans_single_lloyd` (`_kmeans.py:712-740`, behind /root/reference/cluster_utils.py:62-73) so that the host does
  * not read flags back every iteration.  For every ACTIVE segment: state[0][g] += 1 (iterations), state[3][g] +=

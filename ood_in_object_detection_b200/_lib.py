@@ -42,6 +42,7 @@ SIGNATURES = {
     "oodb200_kmeans_step_f32": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P],
     "oodb200_kmeans_reduce_f32": [_P, _P, _I, _L, _P, _P],
     "oodb200_kmeans_update_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "oodb200_kmeans_update_peers_f32": [_P, _I, _L, _L, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "oodb200_kmeans_converge_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
     "oodb200_sqdist_cand_f32": [_P, _I, _P, _I, _L, _P, _I, _P, _P, _P, _P],
     "oodb200_vec_score_tc_workspace_bytes": [_I, _L, _I],

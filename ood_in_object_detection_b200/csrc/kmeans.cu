@@ -422,51 +422,76 @@ __global__ void kmeans_reduce_kernel(const float* __restrict__ in, const int32_t
 }
 
 // sklearn _average_centers + _center_shift (squared, summed per segment); empty clusters keep their old centre.
-// An inactive (converged) segment copies its centres through, so that the caller can ping-pong two buffers.
-__global__ void kmeans_update_kernel(const float* __restrict__ sums, const float* __restrict__ counts,
+// One CTA per segment, one WARP per cluster (clusters w, w + n_warps, ...): the K rows are independent, only the shift is
+// summed over the clusters, in cluster order (fixed: bit-reproducible).  An inactive (converged) segment copies its centres
+// through, so that the caller can ping-pong two buffers.
+// PEERS > 0: the sums / counts are not in `sums` / `counts` but in the symmetric buffers of the `PEERS` ranks of the
+// fit (peer[r] + sums_off / counts_off), read straight over NVLink and added in rank order -- the all-reduce of the Lloyd
+// iteration fused into the update; every rank computes identical bits.  The summed counts and changed-label counts are
+// written to cnts_out / chg_out for the convergence kernel.
+constexpr int kUpdThreads = 512;
+
+__global__ void __launch_bounds__(kUpdThreads) kmeans_update_kernel(const float* __restrict__ sums, const float* __restrict__ counts,
+                                     const float* const* __restrict__ peer, int n_peers, int64_t counts_off, int64_t chg_off,
                                      const float* __restrict__ cent_old, const int32_t* __restrict__ seg_k,
                                      const int32_t* __restrict__ active, int k, int dim, float* __restrict__ cent_new,
-                                     float* __restrict__ shift_sq, int32_t* __restrict__ n_empty) {
+                                     float* __restrict__ shift_sq, int32_t* __restrict__ n_empty,
+                                     float* __restrict__ cnts_out, float* __restrict__ chg_out) {
     const int g = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    if (n_peers > 0 && threadIdx.x == 0 && chg_out) {   // changed labels of the segment over all ranks (exact: small integers in float32)
+        float c = 0.f;
+        for (int r = 0; r < n_peers; ++r) c += peer[r][chg_off + g];
+        chg_out[g] = c;
+    }
     if (active && !active[g]) {
         for (int i = threadIdx.x; i < k * dim; i += blockDim.x) cent_new[(size_t)g * k * dim + i] = cent_old[(size_t)g * k * dim + i];
         if (threadIdx.x == 0) { shift_sq[g] = 0.f; n_empty[g] = 0; }
         return;
     }
-    __shared__ float s_red[32];
+    extern __shared__ float s_shift[];                 // [k] squared shift per cluster, [k] empty flags
     const int Kg = seg_k[g];
-    float tot = 0.f;
-    int empties = 0;
-    for (int kk = 0; kk < k; ++kk) {
-        if (kk >= Kg) {                                     // slots beyond the segment's own cluster count: carried through
-            for (int d = threadIdx.x; d < dim; d += blockDim.x) {
-                const size_t i = ((size_t)g * k + kk) * dim + d;
-                cent_new[i] = cent_old[i];
-            }
+    for (int kk = warp; kk < k; kk += n_warps) {
+        const size_t row = ((size_t)g * k + kk) * dim;
+        if (kk >= Kg) {                                // slots beyond the segment's own cluster count: carried through
+            for (int d = lane; d < dim; d += 32) cent_new[row + d] = cent_old[row + d];
+            if (lane == 0) { s_shift[kk] = 0.f; s_shift[k + kk] = 0.f; }
             continue;
         }
-        const float w = counts[(size_t)g * k + kk];
+        float w;
+        if (n_peers > 0) {
+            w = 0.f;
+            for (int r = 0; r < n_peers; ++r) w += peer[r][counts_off + (size_t)g * k + kk];
+            if (lane == 0 && cnts_out) cnts_out[(size_t)g * k + kk] = w;
+        } else {
+            w = counts[(size_t)g * k + kk];
+        }
         const float alpha = w > 0.f ? (float)(1.0 / (double)w) : 0.f;
         float sh = 0.f;
-        for (int d = threadIdx.x; d < dim; d += blockDim.x) {
-            const size_t i = ((size_t)g * k + kk) * dim + d;
-            const float c = w > 0.f ? sums[i] * alpha : cent_old[i];
-            cent_new[i] = c;
-            const float df = c - cent_old[i];
+        for (int d = lane; d < dim; d += 32) {
+            float sm;
+            if (n_peers > 0) {
+                sm = 0.f;
+                for (int r = 0; r < n_peers; ++r) sm += peer[r][row + d];
+            } else {
+                sm = sums[row + d];
+            }
+            const float c = w > 0.f ? sm * alpha : cent_old[row + d];
+            cent_new[row + d] = c;
+            const float df = c - cent_old[row + d];
             sh = fmaf(df, df, sh);
         }
-        sh = warp_sum(sh);
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sh;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float t = 0.f;
-            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
-            tot += t;                                   // (sqrt(t))^2 in sklearn; equal up to one rounding
-            if (!(w > 0.f)) ++empties;
-        }
+        sh = warp_sum(sh);                             // (sqrt(t))^2 in sklearn; equal up to one rounding
+        if (lane == 0) { s_shift[kk] = sh; s_shift[k + kk] = w > 0.f ? 0.f : 1.f; }
     }
-    if (threadIdx.x == 0) { shift_sq[g] = tot; n_empty[g] = empties; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        int empties = 0;
+        for (int kk = 0; kk < Kg; ++kk) { tot += s_shift[kk]; empties += s_shift[k + kk] != 0.f; }
+        shift_sq[g] = tot;
+        n_empty[g] = empties;
+    }
 }
 
 // Convergence bookkeeping of one Lloyd iteration on the device (sklearn _kmeans_single_lloyd, _kmeans.py:712-740): a
@@ -762,12 +787,27 @@ extern "C" int oodb200_kmeans_reduce_f32(const float* in, const int32_t* first, 
 extern "C" int oodb200_kmeans_update_f32(const float* sums, const float* counts, const float* cent_old, const int32_t* seg_k,
                                          const int32_t* active, int n_seg, int k, int dim, float* cent_new, float* shift_sq,
                                          int32_t* n_empty, void* stream) {
-    OODB200_REQUIRE(n_seg >= 0 && k > 0 && dim > 0, "kmeans_update: bad size");
+    OODB200_REQUIRE(n_seg >= 0 && k > 0 && dim > 0 && k <= 4096, "kmeans_update: bad size");
     if (n_seg == 0) return OODB200_OK;
     OODB200_REQUIRE(sums && counts && cent_old && seg_k && cent_new && shift_sq && n_empty, "kmeans_update: null pointer");
-    kmeans_update_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(sums, counts, cent_old, seg_k, active, k, dim, cent_new,
-                                                                   shift_sq, n_empty);
+    kmeans_update_kernel<<<n_seg, kUpdThreads, 2 * sizeof(float) * k, (cudaStream_t)stream>>>(
+        sums, counts, nullptr, 0, 0, 0, cent_old, seg_k, active, k, dim, cent_new, shift_sq, n_empty, nullptr, nullptr);
     return check_launch("kmeans_update");
+}
+
+extern "C" int oodb200_kmeans_update_peers_f32(const float* const* peer_bufs, int n_peers, int64_t counts_off, int64_t chg_off,
+                                               const float* cent_old, const int32_t* seg_k, const int32_t* active, int n_seg,
+                                               int k, int dim, float* cent_new, float* shift_sq, int32_t* n_empty,
+                                               float* cnts_out, float* chg_out, void* stream) {
+    OODB200_REQUIRE(n_seg >= 0 && k > 0 && dim > 0 && k <= 4096, "kmeans_update_peers: bad size");
+    OODB200_REQUIRE(n_peers >= 1 && n_peers <= 64, "kmeans_update_peers: %d peers", n_peers);
+    if (n_seg == 0) return OODB200_OK;
+    OODB200_REQUIRE(peer_bufs && cent_old && seg_k && cent_new && shift_sq && n_empty && cnts_out && chg_out,
+                    "kmeans_update_peers: null pointer");
+    kmeans_update_kernel<<<n_seg, kUpdThreads, 2 * sizeof(float) * k, (cudaStream_t)stream>>>(
+        nullptr, nullptr, peer_bufs, n_peers, counts_off, chg_off, cent_old, seg_k, active, k, dim, cent_new, shift_sq, n_empty,
+        cnts_out, chg_out);
+    return check_launch("kmeans_update_peers");
 }
 
 extern "C" int oodb200_kmeans_converge_f32(const int32_t* n_changed_i, const float* n_changed_f, const float* shift,

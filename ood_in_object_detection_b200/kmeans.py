@@ -206,6 +206,50 @@ class CudaBackend:
                         "oodb200_kmeans_update_f32")
         return new, shift, n_empty
 
+    def update_peers(self, peer_ptrs_dev, world, n_sum, n_cnt, cent, seg_k, active, out, cnts_out, chg_out):
+        """Centre update with the iteration's all-reduce fused in: the partial sums / counts / changed-label counts of every
+        rank are read from the peers' symmetric buffers over NVLink and added in rank order
+        (csrc/kmeans.cu::kmeans_update_kernel, n_peers > 0)."""
+        n_seg, k, dim = cent.shape
+        new, shift, n_empty = out
+        self._lib.check(self.lib.oodb200_kmeans_update_peers_f32(
+            C.c_void_p(int(peer_ptrs_dev)), int(world), int(n_sum), int(n_sum + n_cnt), _ptr(cent), _ptr(seg_k), _ptr(active),
+            n_seg, k, dim, _ptr(new), _ptr(shift), _ptr(n_empty), _ptr(cnts_out), _ptr(chg_out), _stream()),
+            "oodb200_kmeans_update_peers_f32")
+        return new, shift, n_empty
+
+    def peer_buffers(self, numel, group):
+        """Two symmetric buffers of `numel` floats (alternating between Lloyd iterations) shared with the ranks of `group`
+        over NVLink / NVSwitch peer memory, or None when symmetric memory is unavailable (then NCCL reduces).  Cached: the
+        rendezvous exchanges memory handles between the ranks."""
+        import torch.distributed as dist
+        key = (int(numel), id(group))
+        hit = getattr(self, "_peers", {}).get(key)
+        if hit is not None or key in getattr(self, "_peers", {}):
+            return hit
+        self._peers = getattr(self, "_peers", {})
+        ok = torch.zeros(1, dtype=torch.int32, device=self.device)
+        bufs = None
+        try:
+            if os.environ.get("OODB200_KMEANS_PEERS", "1") == "0" or dist.get_backend(group) != "nccl":
+                raise RuntimeError("disabled")
+            import torch.distributed._symmetric_memory as symm
+            t = [symm.empty(int(numel), dtype=torch.float32, device=self.device) for _ in range(2)]
+            h = [symm.rendezvous(b, group) for b in t]
+            for b in t:
+                b.zero_()
+            bufs = dict(t=t, h=h, ptrs=[int(x.buffer_ptrs_dev) for x in h], world=int(h[0].world_size))
+            ok.fill_(1)
+        except Exception as e:                                    # every rank must take the same path: agree below
+            if str(e) != "disabled":
+                import sys
+                print(f"kmeans: symmetric memory unavailable ({type(e).__name__}: {e}); the Lloyd all-reduce stays on NCCL", file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            bufs = None
+        self._peers[key] = bufs
+        return bufs
+
     def converge(self, n_changed, shift, n_empty, tol_abs, cnts, k, active, state, counts, any_active):
         """Device-side convergence bookkeeping of one iteration (csrc/kmeans.cu::kmeans_converge_kernel)."""
         n_seg = int(active.shape[0])
@@ -400,6 +444,14 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
     other = (torch.empty_like(cent), torch.empty(n_seg, dtype=torch.float32, device=dev),
              torch.empty(n_seg, dtype=torch.int32, device=dev))
     has_into = hasattr(backend, "reduce_into")
+    # N > 1 on one NVLink node: the all-reduce is fused into the centre update -- every rank writes its reduced partials into a
+    # symmetric buffer and the update kernel adds the peers' values in rank order (kmeans_update_peers); else NCCL.
+    peers = backend.peer_buffers(flat.numel(), group) if (distributed and cuda and reduce != "ordered" and has_into
+                                                          and hasattr(backend, "peer_buffers")) else None
+    if peers is not None:
+        cnts_sum = torch.zeros((n_seg, k), dtype=torch.float32, device=dev)
+        chg_sum = torch.zeros(n_seg, dtype=torch.float32, device=dev)
+    timing["collective"] = "peer-memory update" if peers is not None else ("nccl all-reduce" if distributed else "none")
     polls = []                                                              # (host flag, event) per issued iteration
     flag_ring = torch.empty(POLL_LAG + 2, dtype=torch.int32).pin_memory() if cuda else None
     issued = 0
@@ -409,6 +461,19 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
         if reduce == "ordered":
             sums, cnts = _ordered_reduce(backend, psums, pcounts, table, n_seg, world, group)
             chg = allreduce(n_changed) if distributed else n_changed
+        elif peers is not None:
+            buf = peers["t"][it & 1]                                        # alternate: nobody still reads the buffer written now
+            b_sums, b_cnts = buf[:n_sum].view(n_seg, k, dim), buf[n_sum:n_sum + n_cnt].view(n_seg, k)
+            if table.n_blocks:
+                backend.reduce_into(psums, seg_first, n_seg, b_sums)
+                backend.reduce_into(pcounts, seg_first, n_seg, b_cnts)
+            else:
+                buf[:n_sum + n_cnt].zero_()
+            buf[n_sum + n_cnt:].copy_(n_changed)                            # exact in float32 below 2^24 rows per segment
+            peers["h"][it & 1].barrier(channel=0)                           # every rank's partials are written
+            new_cent, shift, n_empty = backend.update_peers(peers["ptrs"][it & 1], peers["world"], n_sum, n_cnt, cent, seg_k,
+                                                            active, other, cnts_sum, chg_sum)
+            backend.converge(chg_sum, shift, n_empty, tol_d, cnts_sum, k, active, state, counts, any_active)
         else:
             if table.n_blocks and has_into:
                 backend.reduce_into(psums, seg_first, n_seg, sums_v)
@@ -423,8 +488,9 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
                 chg_f.copy_(n_changed)                                      # exact in float32 below 2^24 rows per segment
                 allreduce(flat)                                             # the one collective of the iteration
                 chg = chg_f
-        new_cent, shift, n_empty = backend.update(sums, cnts, cent, seg_k, active, out=other)
-        backend.converge(chg, shift, n_empty, tol_d, cnts, k, active, state, counts, any_active)
+        if peers is None or reduce == "ordered":
+            new_cent, shift, n_empty = backend.update(sums, cnts, cent, seg_k, active, out=other)
+            backend.converge(chg, shift, n_empty, tol_d, cnts, k, active, state, counts, any_active)
         other = (cent, shift, n_empty)
         cent = new_cent
         issued += 1

@@ -8,7 +8,10 @@ TEST / MEASUREMENT INFRASTRUCTURE: `__graft_entry__.build()` runs it in the buil
   * tests/test_gpu_pipeline.py (the reference's unmodified evaluation driver run against this repo's classes).
 Nothing under ood_in_object_detection_b200/ imports it.
 
-    python oracle/make_ref.py            # -> oracle/_ref/**.pyc (+ the yaml defaults ultralytics reads at import time)
+    python oracle/make_ref.py            # -> oracle/_ref/**.pyb (+ the yaml defaults ultralytics reads at import time)
+
+The compiled modules carry the suffix .pyb (the content is what py_compile writes into a .pyc): snapshots of the repo skip
+*.pyc, so oracle/ref_shim.py registers a finder that loads <module>.pyb through importlib's SourcelessFileLoader.
 """
 from __future__ import annotations
 
@@ -43,8 +46,8 @@ def build(verbose: bool = False) -> int:
         dst = os.path.join(OUT, rel)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         if rel.endswith(".py"):
-            try:                                       # sourceless import: <module>.pyc next to where the .py would be
-                py_compile.compile(src, cfile=dst + "c", dfile=rel, doraise=True)
+            try:                                       # sourceless import: <module>.pyb where the .py would be
+                py_compile.compile(src, cfile=dst + "b", dfile=rel, doraise=True)
                 n += 1
             except py_compile.PyCompileError as e:     # a reference file that does not even parse is not on the path
                 if verbose:

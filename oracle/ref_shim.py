@@ -44,7 +44,7 @@ _loaded = None
 
 
 def available() -> bool:
-    return any(os.path.isfile(os.path.join(REFERENCE_ROOT, "ood_utils" + ext)) for ext in (".py", ".pyc"))
+    return any(os.path.isfile(os.path.join(REFERENCE_ROOT, "ood_utils" + ext)) for ext in (".py", ".pyb"))
 
 
 def kind() -> str:
@@ -69,6 +69,24 @@ class _Stub(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         pass
 
 
+class _Compiled(importlib.abc.MetaPathFinder):
+    """Finder for the byte-compiled build (oracle/make_ref.py): module a.b -> <root>/a/b.pyb or <root>/a/b/__init__.pyb,
+    loaded by importlib's SourcelessFileLoader (`__file__` stays a real path: ultralytics reads its yaml defaults next to it)."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, name, path, target=None):
+        import importlib.util
+        base = os.path.join(self.root, *name.split("."))
+        for cand, pkg in ((base + ".pyb", False), (os.path.join(base, "__init__.pyb"), True)):
+            if os.path.isfile(cand):
+                loader = importlib.machinery.SourcelessFileLoader(name, cand)
+                return importlib.util.spec_from_file_location(name, cand, loader=loader,
+                                                              submodule_search_locations=[base] if pkg else None)
+        return None
+
+
 def load() -> SimpleNamespace:
     """Import the reference modules; returns a namespace with the pieces the tests use."""
     global _loaded
@@ -79,6 +97,8 @@ def load() -> SimpleNamespace:
     os.environ.setdefault("YOLO_CONFIG_DIR", "/tmp")
     warnings.filterwarnings("ignore")
     sys.meta_path.insert(0, _Stub())
+    if kind() == "compiled":
+        sys.meta_path.insert(0, _Compiled(REFERENCE_ROOT))
     # our own package has modules called ood_utils / cluster_utils too, but they live inside
     # the package namespace, so the top-level names resolve to the reference here.
     sys.path.insert(0, REFERENCE_ROOT)

@@ -563,16 +563,14 @@ def main():
         OUT = sys.argv[sys.argv.index("--out") + 1]
         os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
-    if "--only-c4" in sys.argv:
-        return golden_c4(ref)
-    if "--only-bigfit" in sys.argv:
-        return golden_bigfit(ref)
-    if "--only-eul" in sys.argv:
-        return golden_eul_rank(ref)
-    if "--only-matching" in sys.argv:
-        return golden_matching(ref)
-    if "--only-ksearch" in sys.argv:
-        return golden_ksearch(ref)
+    only = {"--only-c4": golden_c4, "--only-bigfit": golden_bigfit, "--only-eul": golden_eul_rank, "--only-matching": golden_matching,
+            "--only-ksearch": golden_ksearch, "--only-quirks": golden_quirks, "--only-fusion": golden_fusion,
+            "--only-thresholds": golden_thresholds}
+    picked = [fn for flag, fn in only.items() if flag in sys.argv]
+    if picked:
+        for fn in picked:
+            fn(ref)
+        return
     golden_c4(ref)
     golden_bigfit(ref)
     golden_ksearch(ref)
