@@ -750,6 +750,28 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     e2e_value = n_all * e2e_steps / e2e_s
+    # the same call with the inputs where a detector leaves them: feature maps and detections already on the device (only the
+    # decisions cross PCIe) -- the deployment case; the host-input figure above is bound by the 367 MB map upload per step
+    res_fd = [Results(orig_img=shape, boxes=r.boxes.data.to(device), extra_item=([m[i] for m in maps], r.extra_item[1].to(device)))
+              for i, r in enumerate(res_f)]
+    res_ld = [Results(orig_img=shape, boxes=r.boxes.data.to(device), extra_item=r.extra_item.to(device)) for r in res_l]
+    ood_utils.compute_ood_decisions_fused(methods, res_fd, log, logits_results=res_ld)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dev_steps = max(e2e_steps, 20)
+    t0 = time.perf_counter()
+    for _ in range(dev_steps):
+        dec_d = ood_utils.compute_ood_decisions_fused(methods, res_fd, log, logits_results=res_ld)
+    torch.cuda.synchronize()
+    dev_s = time.perf_counter() - t0
+    same_d = dec_d[m_cos.name] == dec[m_cos.name] and dec_d[m_l1.name] == dec[m_l1.name]
+    if world > 1:
+        t = torch.tensor([dev_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s = float(t[0])
+    e2e_dev_value = n_all * dev_steps / dev_s
+    del res_fd, res_ld
 
     fit = None
     if args.fit_n != 0:
@@ -808,7 +830,14 @@ def run_ours(args, wl):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "ood_utils.compute_ood_decisions_fused([L1, Cosine, MSP, Energy, MaxLogit], results)",
                     "matches_resident_path": bool(same),
-                    "note": "host pinned feature maps + detections -> per-image decision lists on the host"},
+                    "note": "host pinned feature maps + detections -> per-image decision lists on the host",
+                    "pcie_bound_value": n_all / (h2d / 55e9),
+                    "pcie_note": "upper bound of this figure at the 55 GB/s the box's pinned H2D copies reach (profiles/r1_h2d_bw.log): "
+                                 "the boxes' windows are scattered over ~all rows of every plane, a partial upload would need one "
+                                 "strided copy per box",
+                    "device_inputs": {"value": e2e_dev_value, "unit": UNIT, "steps": dev_steps, "same_decisions": bool(same_d),
+                                      "note": "same API call with the feature maps and detections already on the device (where the "
+                                              "detector leaves them); D2H of the decisions and all host-side packing included"}},
             "gpu_launches": KERNELS_PER_STEP * args.steps, "clocks": clk.summary(), "wall_s_timed_region": t_wall,
         }
         if fit is not None:

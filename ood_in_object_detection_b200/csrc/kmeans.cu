@@ -430,6 +430,7 @@ __global__ void kmeans_reduce_kernel(const float* __restrict__ in, const int32_t
 // iteration fused into the update; every rank computes identical bits.  The summed counts and changed-label counts are
 // written to cnts_out / chg_out for the convergence kernel.
 constexpr int kUpdThreads = 512;
+constexpr int kUpdMaxPeers = 8;                        // peers whose loads are kept in flight together (more: in groups of 8)
 
 __global__ void __launch_bounds__(kUpdThreads) kmeans_update_kernel(const float* __restrict__ sums, const float* __restrict__ counts,
                                      const float* const* __restrict__ peer, int n_peers, int64_t counts_off, int64_t chg_off,
@@ -444,51 +445,93 @@ __global__ void __launch_bounds__(kUpdThreads) kmeans_update_kernel(const float*
         for (int r = 0; r < n_peers; ++r) c += peer[r][chg_off + g];
         chg_out[g] = c;
     }
+    const size_t seg = (size_t)g * k * dim;
     if (active && !active[g]) {
-        for (int i = threadIdx.x; i < k * dim; i += blockDim.x) cent_new[(size_t)g * k * dim + i] = cent_old[(size_t)g * k * dim + i];
+        for (int i = threadIdx.x; i < k * dim; i += blockDim.x) cent_new[seg + i] = cent_old[seg + i];
         if (threadIdx.x == 0) { shift_sq[g] = 0.f; n_empty[g] = 0; }
         return;
     }
-    extern __shared__ float s_shift[];                 // [k] squared shift per cluster, [k] empty flags
+    extern __shared__ float s_upd[];                   // [k] counts, [k] squared shift per cluster, [k * dim / 4] partial shifts
+    float* s_w = s_upd;
+    float* s_shift = s_upd + k;
+    float* s_part = s_upd + 2 * k;
     const int Kg = seg_k[g];
-    for (int kk = warp; kk < k; kk += n_warps) {
-        const size_t row = ((size_t)g * k + kk) * dim;
-        if (kk >= Kg) {                                // slots beyond the segment's own cluster count: carried through
-            for (int d = lane; d < dim; d += 32) cent_new[row + d] = cent_old[row + d];
-            if (lane == 0) { s_shift[kk] = 0.f; s_shift[k + kk] = 0.f; }
-            continue;
-        }
-        float w;
-        if (n_peers > 0) {
-            w = 0.f;
-            for (int r = 0; r < n_peers; ++r) w += peer[r][counts_off + (size_t)g * k + kk];
-            if (lane == 0 && cnts_out) cnts_out[(size_t)g * k + kk] = w;
-        } else {
-            w = counts[(size_t)g * k + kk];
-        }
-        const float alpha = w > 0.f ? (float)(1.0 / (double)w) : 0.f;
-        float sh = 0.f;
-        for (int d = lane; d < dim; d += 32) {
-            float sm;
+    for (int kk = threadIdx.x; kk < k; kk += blockDim.x) {            // cluster sizes (over the ranks, in rank order)
+        float w = 0.f;
+        if (kk < Kg) {
             if (n_peers > 0) {
-                sm = 0.f;
-                for (int r = 0; r < n_peers; ++r) sm += peer[r][row + d];
+                for (int r = 0; r < n_peers; ++r) w += peer[r][counts_off + (size_t)g * k + kk];
+                if (cnts_out) cnts_out[(size_t)g * k + kk] = w;
             } else {
-                sm = sums[row + d];
+                w = counts[(size_t)g * k + kk];
             }
-            const float c = w > 0.f ? sm * alpha : cent_old[row + d];
-            cent_new[row + d] = c;
-            const float df = c - cent_old[row + d];
-            sh = fmaf(df, df, sh);
+        }
+        s_w[kk] = w;
+    }
+    __syncthreads();
+    const bool vec = (dim & 3) == 0;
+    const int nv = vec ? k * dim / 4 : 0;
+    // every thread owns float4 elements of the segment's K x dim block: all its loads (x peers) are in flight together
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const int kk = (4 * i) / dim;
+        const float4 old = *reinterpret_cast<const float4*>(cent_old + seg + 4 * (size_t)i);
+        float4 c = old;
+        float part = 0.f;
+        if (kk < Kg) {
+            float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n_peers > 0) {
+                for (int r0 = 0; r0 < n_peers; r0 += kUpdMaxPeers) {
+                    float4 v[kUpdMaxPeers];
+#pragma unroll
+                    for (int r = 0; r < kUpdMaxPeers; ++r)
+                        v[r] = r0 + r < n_peers ? *reinterpret_cast<const float4*>(peer[r0 + r] + seg + 4 * (size_t)i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int r = 0; r < kUpdMaxPeers; ++r)
+                        if (r0 + r < n_peers) { sm.x += v[r].x; sm.y += v[r].y; sm.z += v[r].z; sm.w += v[r].w; }
+                }
+            } else {
+                sm = *reinterpret_cast<const float4*>(sums + seg + 4 * (size_t)i);
+            }
+            const float w = s_w[kk];
+            if (w > 0.f) {
+                const float alpha = (float)(1.0 / (double)w);
+                c = make_float4(sm.x * alpha, sm.y * alpha, sm.z * alpha, sm.w * alpha);
+            }
+            const float d0 = c.x - old.x, d1 = c.y - old.y, d2 = c.z - old.z, d3 = c.w - old.w;
+            part = fmaf(d0, d0, part); part = fmaf(d1, d1, part); part = fmaf(d2, d2, part); part = fmaf(d3, d3, part);
+        }
+        *reinterpret_cast<float4*>(cent_new + seg + 4 * (size_t)i) = c;
+        s_part[i] = part;
+    }
+    __syncthreads();
+    for (int kk = warp; kk < k; kk += n_warps) {       // squared shift of every cluster: fixed lane partition + butterfly
+        float sh = 0.f;
+        if (vec) {
+            const int per = dim / 4;
+            for (int j = lane; j < per; j += 32) sh += s_part[kk * per + j];
+        } else if (kk < Kg) {                          // dim % 4 != 0: scalar path
+            const float w = s_w[kk];
+            const float alpha = w > 0.f ? (float)(1.0 / (double)w) : 0.f;
+            for (int d = lane; d < dim; d += 32) {
+                const size_t e = seg + (size_t)kk * dim + d;
+                float sm = 0.f;
+                if (n_peers > 0) { for (int r = 0; r < n_peers; ++r) sm += peer[r][e]; } else sm = sums[e];
+                const float c = w > 0.f ? sm * alpha : cent_old[e];
+                cent_new[e] = c;
+                const float df = c - cent_old[e];
+                sh = fmaf(df, df, sh);
+            }
+        } else {
+            for (int d = lane; d < dim; d += 32) cent_new[seg + (size_t)kk * dim + d] = cent_old[seg + (size_t)kk * dim + d];
         }
         sh = warp_sum(sh);                             // (sqrt(t))^2 in sklearn; equal up to one rounding
-        if (lane == 0) { s_shift[kk] = sh; s_shift[k + kk] = w > 0.f ? 0.f : 1.f; }
+        if (lane == 0) s_shift[kk] = sh;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         float tot = 0.f;
         int empties = 0;
-        for (int kk = 0; kk < Kg; ++kk) { tot += s_shift[kk]; empties += s_shift[k + kk] != 0.f; }
+        for (int kk = 0; kk < Kg; ++kk) { tot += s_shift[kk]; empties += !(s_w[kk] > 0.f); }
         shift_sq[g] = tot;
         n_empty[g] = empties;
     }
@@ -790,7 +833,13 @@ extern "C" int oodb200_kmeans_update_f32(const float* sums, const float* counts,
     OODB200_REQUIRE(n_seg >= 0 && k > 0 && dim > 0 && k <= 4096, "kmeans_update: bad size");
     if (n_seg == 0) return OODB200_OK;
     OODB200_REQUIRE(sums && counts && cent_old && seg_k && cent_new && shift_sq && n_empty, "kmeans_update: null pointer");
-    kmeans_update_kernel<<<n_seg, kUpdThreads, 2 * sizeof(float) * k, (cudaStream_t)stream>>>(
+    const size_t smem = sizeof(float) * (2 * (size_t)k + (size_t)k * dim / 4 + 4);
+    OODB200_REQUIRE(smem <= 200 * 1024, "kmeans_update: k * dim too large");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kmeans_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("kmeans_update: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+    }
+    kmeans_update_kernel<<<n_seg, kUpdThreads, smem, (cudaStream_t)stream>>>(
         sums, counts, nullptr, 0, 0, 0, cent_old, seg_k, active, k, dim, cent_new, shift_sq, n_empty, nullptr, nullptr);
     return check_launch("kmeans_update");
 }
@@ -804,7 +853,13 @@ extern "C" int oodb200_kmeans_update_peers_f32(const float* const* peer_bufs, in
     if (n_seg == 0) return OODB200_OK;
     OODB200_REQUIRE(peer_bufs && cent_old && seg_k && cent_new && shift_sq && n_empty && cnts_out && chg_out,
                     "kmeans_update_peers: null pointer");
-    kmeans_update_kernel<<<n_seg, kUpdThreads, 2 * sizeof(float) * k, (cudaStream_t)stream>>>(
+    const size_t smem = sizeof(float) * (2 * (size_t)k + (size_t)k * dim / 4 + 4);
+    OODB200_REQUIRE(smem <= 200 * 1024, "kmeans_update_peers: k * dim too large");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kmeans_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("kmeans_update_peers: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
+    }
+    kmeans_update_kernel<<<n_seg, kUpdThreads, smem, (cudaStream_t)stream>>>(
         nullptr, nullptr, peer_bufs, n_peers, counts_off, chg_off, cent_old, seg_k, active, k, dim, cent_new, shift_sq, n_empty,
         cnts_out, chg_out);
     return check_launch("kmeans_update_peers");
