@@ -147,6 +147,26 @@ int oodb200_fmap_score_nhwc_f32(const float* const* map_ptrs, const int32_t* map
 int oodb200_q1_plan_i32(const int32_t* img_start, const int32_t* stride_idx, const int32_t* cls, int n_img,
                         int32_t* cls_used, int32_t* out_index, void* stream);
 
+/* ---- fit-data collection: which predictions are valid in-distribution samples.  Replaces
+ * `OODMethod.match_predicted_boxes_to_targets` (/root/reference/ood_utils.py:233-292): per image the IoU (torchvision
+ * `box_iou`, float32) x same-class mask of every prediction against every ground-truth box (:251-257),
+ * `scipy.optimize.linear_sum_assignment(score, maximize=True)` (:283; scipy's shortest-augmenting-path algorithm with its
+ * scan order and tie rules, float64) and the walk over the assignment (:288-291).  One CTA per image; max(P, G) <= 1024.
+ *   pred_xyxy [n, 4] / pred_cls [n] / pred_start [n_img+1]    predictions, images back to back
+ *   gt_xyxy [m, 4] / gt_cls [m] / gt_start [n_img+1]          ground truth in absolute pixels (create_targets_dict, :201-231)
+ *   score_off [n_img+1] int64   element offset of every image's [P, G] row-major score matrix inside `score`
+ *   compat    1 = the reference's quirk Q8: the walk tests score[POSITION in the assignment, col] and records the position
+ *             (identical to the assigned row when P <= G); 0 = tests the assigned (row, col) pair
+ *   row_ind / col_ind [n]   the assignment of every image, rows ascending, first min(P, G) entries, rest -1
+ *   valid [n] u8            1 at the indices the reference appends to `valid_preds`
+ *   status [1] int32        must be 0 on entry; set to 1 when an image exceeds 1024 boxes or a score is not finite
+ */
+int oodb200_match_boxes_f32(const float* pred_xyxy, const int32_t* pred_cls, const int32_t* pred_start,
+                            const float* gt_xyxy, const int32_t* gt_cls, const int32_t* gt_start,
+                            const int64_t* score_off, int n_img, float iou_threshold, int compat,
+                            float* score, int32_t* row_ind, int32_t* col_ind, uint8_t* valid, int32_t* status,
+                            void* stream);
+
 /* ---- K3: logit methods.  Replaces `LogitsMethod.compute_ood_decision_on_results` /
  * `compute_INDness_scores_on_results` (/root/reference/ood_utils.py:1195-1257) and the scorers
  * (:1388-1443).  One pass computes every method in method_mask.
@@ -235,11 +255,14 @@ int oodb200_kmeans_update_f32(const float* sums, const float* counts, const floa
  * SYMMETRIC buffer (torch.distributed._symmetric_memory); peer_bufs is the device array of the n_peers buffer addresses as
  * mapped into this process.  The kernel reads every peer's values straight over NVLink, adds them in rank order (every
  * rank computes identical bits) and does what oodb200_kmeans_update_f32 does; the summed counts and changed-label counts
- * are written to cnts_out [n_seg, k] / chg_out [n_seg] for oodb200_kmeans_converge_f32.  The caller orders the ranks
- * around it (a device-side barrier before: all partials written; buffers alternate between iterations).
+ * are written to cnts_out [n_seg, k] / chg_out [n_seg] for oodb200_kmeans_converge_f32.
+ * The barrier between the ranks is part of the kernel: peer_flags (device array of the n_peers addresses of a symmetric
+ * uint32[n_peers] array, or NULL when the caller orders the ranks itself) -- rank my_rank stores `epoch` into slot my_rank of
+ * every peer's array (release, system scope) and waits until every slot of its own array has reached `epoch`; epoch must
+ * increase from call to call (wrap-around safe), the partial buffers alternate between iterations.
  * Replaces the NCCL all-reduce + update of `kmeans.kmeans_fit` (same sklearn statements as kmeans_update). */
 int oodb200_kmeans_update_peers_f32(const float* const* peer_bufs, int n_peers, int64_t counts_off, int64_t chg_off,
-                                    const float* cent_old, const int32_t* seg_k, const int32_t* active, int n_seg,
+                                    uint32_t* const* peer_flags, int my_rank, uint32_t epoch, const float* cent_old, const int32_t* seg_k, const int32_t* active, int n_seg,
                                     int k, int dim, float* cent_new, float* shift_sq, int32_t* n_empty,
                                     float* cnts_out, float* chg_out, void* stream);
 

@@ -31,6 +31,7 @@ SIGNATURES = {
     "oodb200_roi_pool_nhwc_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _L, _P],
     "oodb200_fmap_score_nhwc_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P,
                                     _P, _I, _P, _P, _P, _L, _P],
+    "oodb200_match_boxes_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P],
     "oodb200_logit_score_f32": [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "oodb200_fuse_u8": [_P, _P, _P, _I, _I, _P, _P],
     "oodb200_fuse_score_f32": [_P, _P, _I, _P, _P],
@@ -42,7 +43,7 @@ SIGNATURES = {
     "oodb200_kmeans_step_f32": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P],
     "oodb200_kmeans_reduce_f32": [_P, _P, _I, _L, _P, _P],
     "oodb200_kmeans_update_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
-    "oodb200_kmeans_update_peers_f32": [_P, _I, _L, _L, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "oodb200_kmeans_update_peers_f32": [_P, _I, _L, _L, _P, _I, C.c_uint32, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "oodb200_kmeans_converge_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
     "oodb200_sqdist_cand_f32": [_P, _I, _P, _I, _L, _P, _I, _P, _P, _P, _P],
     "oodb200_vec_score_tc_workspace_bytes": [_I, _L, _I],

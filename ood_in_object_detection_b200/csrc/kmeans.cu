@@ -434,12 +434,33 @@ constexpr int kUpdMaxPeers = 8;                        // peers whose loads are 
 
 __global__ void __launch_bounds__(kUpdThreads) kmeans_update_kernel(const float* __restrict__ sums, const float* __restrict__ counts,
                                      const float* const* __restrict__ peer, int n_peers, int64_t counts_off, int64_t chg_off,
+                                     uint32_t* const* __restrict__ peer_flags, int my_rank, uint32_t epoch,
                                      const float* __restrict__ cent_old, const int32_t* __restrict__ seg_k,
                                      const int32_t* __restrict__ active, int k, int dim, float* __restrict__ cent_new,
                                      float* __restrict__ shift_sq, int32_t* __restrict__ n_empty,
                                      float* __restrict__ cnts_out, float* __restrict__ chg_out) {
     const int g = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    if (n_peers > 0 && peer_flags) {
+        // Cross-GPU barrier of the iteration, inside the kernel: this rank's partials were written by earlier launches of the
+        // stream; CTA 0 publishes `epoch` in every peer's flag array (release, system scope), every CTA waits until all peers
+        // have published theirs in the LOCAL array (acquire).  Bounded: a missing peer traps instead of hanging the GPU.
+        if (blockIdx.x == 0 && threadIdx.x < n_peers) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[threadIdx.x] + my_rank), "r"(epoch) : "memory");
+        }
+        if (threadIdx.x < n_peers) {
+            const uint32_t* f = peer_flags[my_rank] + threadIdx.x;
+            uint32_t v = 0;
+            const long long t0 = clock64();
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if ((int32_t)(v - epoch) >= 0) break;
+                if (clock64() - t0 > 8000000000LL) __trap();
+            }
+        }
+        __syncthreads();
+    }
     if (n_peers > 0 && threadIdx.x == 0 && chg_out) {   // changed labels of the segment over all ranks (exact: small integers in float32)
         float c = 0.f;
         for (int r = 0; r < n_peers; ++r) c += peer[r][chg_off + g];
@@ -840,16 +861,17 @@ extern "C" int oodb200_kmeans_update_f32(const float* sums, const float* counts,
         if (e != cudaSuccess) { set_error("kmeans_update: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
     }
     kmeans_update_kernel<<<n_seg, kUpdThreads, smem, (cudaStream_t)stream>>>(
-        sums, counts, nullptr, 0, 0, 0, cent_old, seg_k, active, k, dim, cent_new, shift_sq, n_empty, nullptr, nullptr);
+        sums, counts, nullptr, 0, 0, 0, nullptr, 0, 0u, cent_old, seg_k, active, k, dim, cent_new, shift_sq, n_empty, nullptr, nullptr);
     return check_launch("kmeans_update");
 }
 
 extern "C" int oodb200_kmeans_update_peers_f32(const float* const* peer_bufs, int n_peers, int64_t counts_off, int64_t chg_off,
-                                               const float* cent_old, const int32_t* seg_k, const int32_t* active, int n_seg,
+                                               uint32_t* const* peer_flags, int my_rank, uint32_t epoch, const float* cent_old, const int32_t* seg_k, const int32_t* active, int n_seg,
                                                int k, int dim, float* cent_new, float* shift_sq, int32_t* n_empty,
                                                float* cnts_out, float* chg_out, void* stream) {
     OODB200_REQUIRE(n_seg >= 0 && k > 0 && dim > 0 && k <= 4096, "kmeans_update_peers: bad size");
     OODB200_REQUIRE(n_peers >= 1 && n_peers <= 64, "kmeans_update_peers: %d peers", n_peers);
+    OODB200_REQUIRE(!peer_flags || (my_rank >= 0 && my_rank < n_peers), "kmeans_update_peers: rank %d of %d", my_rank, n_peers);
     if (n_seg == 0) return OODB200_OK;
     OODB200_REQUIRE(peer_bufs && cent_old && seg_k && cent_new && shift_sq && n_empty && cnts_out && chg_out,
                     "kmeans_update_peers: null pointer");
@@ -860,8 +882,8 @@ extern "C" int oodb200_kmeans_update_peers_f32(const float* const* peer_bufs, in
         if (e != cudaSuccess) { set_error("kmeans_update_peers: %s", cudaGetErrorString(e)); return OODB200_ERR_CUDA; }
     }
     kmeans_update_kernel<<<n_seg, kUpdThreads, smem, (cudaStream_t)stream>>>(
-        nullptr, nullptr, peer_bufs, n_peers, counts_off, chg_off, cent_old, seg_k, active, k, dim, cent_new, shift_sq, n_empty,
-        cnts_out, chg_out);
+        nullptr, nullptr, peer_bufs, n_peers, counts_off, chg_off, peer_flags, my_rank, epoch, cent_old, seg_k, active, k, dim,
+        cent_new, shift_sq, n_empty, cnts_out, chg_out);
     return check_launch("kmeans_update_peers");
 }
 

@@ -206,16 +206,17 @@ class CudaBackend:
                         "oodb200_kmeans_update_f32")
         return new, shift, n_empty
 
-    def update_peers(self, peer_ptrs_dev, world, n_sum, n_cnt, cent, seg_k, active, out, cnts_out, chg_out):
+    def update_peers(self, peers, slot, n_sum, n_cnt, cent, seg_k, active, out, cnts_out, chg_out):
         """Centre update with the iteration's all-reduce fused in: the partial sums / counts / changed-label counts of every
         rank are read from the peers' symmetric buffers over NVLink and added in rank order
         (csrc/kmeans.cu::kmeans_update_kernel, n_peers > 0)."""
         n_seg, k, dim = cent.shape
         new, shift, n_empty = out
+        peers["epoch"] = (peers["epoch"] + 1) & 0xFFFFFFFF                    # same sequence on every rank: the barrier's ticket
         self._lib.check(self.lib.oodb200_kmeans_update_peers_f32(
-            C.c_void_p(int(peer_ptrs_dev)), int(world), int(n_sum), int(n_sum + n_cnt), _ptr(cent), _ptr(seg_k), _ptr(active),
-            n_seg, k, dim, _ptr(new), _ptr(shift), _ptr(n_empty), _ptr(cnts_out), _ptr(chg_out), _stream()),
-            "oodb200_kmeans_update_peers_f32")
+            C.c_void_p(peers["ptrs"][slot]), peers["world"], int(n_sum), int(n_sum + n_cnt), C.c_void_p(peers["flag_ptrs"]),
+            peers["rank"], peers["epoch"], _ptr(cent), _ptr(seg_k), _ptr(active), n_seg, k, dim, _ptr(new), _ptr(shift),
+            _ptr(n_empty), _ptr(cnts_out), _ptr(chg_out), _stream()), "oodb200_kmeans_update_peers_f32")
         return new, shift, n_empty
 
     def peer_buffers(self, numel, group):
@@ -235,16 +236,20 @@ class CudaBackend:
                 raise RuntimeError("disabled")
             import torch.distributed._symmetric_memory as symm
             t = [symm.empty(int(numel), dtype=torch.float32, device=self.device) for _ in range(2)]
+            flags = symm.empty(64, dtype=torch.int32, device=self.device)      # the in-kernel barrier's tickets, one slot per rank
             h = [symm.rendezvous(b, group) for b in t]
+            hf = symm.rendezvous(flags, group)
             for b in t:
                 b.zero_()
-            bufs = dict(t=t, h=h, ptrs=[int(x.buffer_ptrs_dev) for x in h], world=int(h[0].world_size))
+            flags.zero_()
+            bufs = dict(t=t, h=h, flags=flags, hf=hf, ptrs=[int(x.buffer_ptrs_dev) for x in h], flag_ptrs=int(hf.buffer_ptrs_dev),
+                        world=int(h[0].world_size), rank=int(h[0].rank), epoch=0)
             ok.fill_(1)
         except Exception as e:                                    # every rank must take the same path: agree below
             if str(e) != "disabled":
                 import sys
                 print(f"kmeans: symmetric memory unavailable ({type(e).__name__}: {e}); the Lloyd all-reduce stays on NCCL", file=sys.stderr)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)              # also: every rank has zeroed its tickets before anyone signals
         if int(ok.item()) == 0:
             bufs = None
         self._peers[key] = bufs
@@ -470,9 +475,8 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
             else:
                 buf[:n_sum + n_cnt].zero_()
             buf[n_sum + n_cnt:].copy_(n_changed)                            # exact in float32 below 2^24 rows per segment
-            peers["h"][it & 1].barrier(channel=0)                           # every rank's partials are written
-            new_cent, shift, n_empty = backend.update_peers(peers["ptrs"][it & 1], peers["world"], n_sum, n_cnt, cent, seg_k,
-                                                            active, other, cnts_sum, chg_sum)
+            # the update kernel itself waits for every rank's partials (tickets in symmetric memory), then adds them over NVLink
+            new_cent, shift, n_empty = backend.update_peers(peers, it & 1, n_sum, n_cnt, cent, seg_k, active, other, cnts_sum, chg_sum)
             backend.converge(chg_sum, shift, n_empty, tol_d, cnts_sum, k, active, state, counts, any_active)
         else:
             if table.n_blocks and has_into:

@@ -220,31 +220,23 @@ class OODMethod(ABC):
     @staticmethod
     def match_predicted_boxes_to_targets(results, targets, iou_threshold: float, compat: bool = True):
         """`res.valid_preds` = predictions matched (Hungarian on IoU x same-class mask) to a ground-truth box with
-        IoU above the threshold (ood_utils.py:233-292).  Host logic: a [P, G] problem per image.
+        IoU above the threshold (ood_utils.py:233-292).  The whole batch is one launch (csrc/matching.cu): score matrices,
+        scipy's assignment algorithm with its tie rules, and the walk over the assignment; `res.assignment_score_matrix`
+        and `res.assignment` are filled like the reference does.
 
         compat=True keeps the reference's indexing (Q8): it walks `enumerate(assignment[1])` and tests
         `score[i, col]` with i = POSITION in the assignment, not the assigned row `assignment[0][i]`
         (ood_utils.py:288-291) -- identical when every prediction is assigned (P <= G), different when P > G.
         compat=False tests the assigned (row, col) pairs."""
-        from scipy.optimize import linear_sum_assignment
-        for img_idx, res in enumerate(results):
-            p = res.boxes.xyxy.detach().cpu().float()
-            g = targets['bboxes'][img_idx].detach().cpu().float()
-            area_p = (p[:, 2] - p[:, 0]) * (p[:, 3] - p[:, 1])
-            area_g = (g[:, 2] - g[:, 0]) * (g[:, 3] - g[:, 1])
-            lt = torch.max(p[:, None, :2], g[None, :, :2])
-            rb = torch.min(p[:, None, 2:], g[None, :, 2:])
-            wh = (rb - lt).clamp(min=0)
-            inter = wh[..., 0] * wh[..., 1]
-            iou = inter / (area_p[:, None] + area_g[None, :] - inter)
-            mask = (res.boxes.cls.detach().cpu()[:, None] == targets['cls'][img_idx].detach().cpu()[None, :]).float()
-            res.assignment_score_matrix = iou * mask
-            res.assignment = linear_sum_assignment(res.assignment_score_matrix, maximize=True)
-            res.valid_preds = []
-            for i, (row, col) in enumerate(zip(*res.assignment)):
-                r = i if compat else int(row)
-                if res.assignment_score_matrix[r, col] > iou_threshold:
-                    res.valid_preds.append(r)
+        if not len(results):
+            return
+        out = ops.match_boxes([res.boxes.xyxy.detach() for res in results], [res.boxes.cls.detach() for res in results],
+                              [targets['bboxes'][i].detach() for i in range(len(results))],
+                              [targets['cls'][i].detach() for i in range(len(results))], iou_threshold, compat=compat)
+        for res, (valid, score, assignment) in zip(results, out):
+            res.assignment_score_matrix = torch.from_numpy(score)
+            res.assignment = assignment
+            res.valid_preds = valid
 
     def prepare_data_for_model(self, data, device):
         if isinstance(data, dict):

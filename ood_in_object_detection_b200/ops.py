@@ -632,6 +632,59 @@ def normalize_rows(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------------------ fit-data collection
+def match_boxes(pred_xyxy: Sequence, pred_cls: Sequence, gt_xyxy: Sequence, gt_cls: Sequence, iou_threshold: float,
+                compat: bool = True, device=None):
+    """Per image: IoU x same-class score matrix, scipy-compatible assignment and the valid predictions
+    (/root/reference/ood_utils.py:233-292) in ONE launch for the batch.  Inputs are per-image sequences ([P_i, 4], [P_i],
+    [G_i, 4], [G_i]; torch tensors on any device or arrays).  -> list over images of (valid_preds list, score [P, G] float32
+    numpy, (row_ind, col_ind) int64 numpy), what the reference stores on every Results object."""
+    lib = _lib.load()
+    device = device or default_device()
+    n_img = len(pred_xyxy)
+
+    def flat(seq, dtype, width=None):
+        ts = [t if isinstance(t, torch.Tensor) else torch.as_tensor(np.asarray(t)) for t in seq]
+        shape = (-1, width) if width else (-1,)
+        if not ts:
+            return torch.zeros((0, width) if width else (0,), dtype=dtype, device=device)
+        if all(not t.is_cuda for t in ts):
+            return h2d(torch.cat([t.reshape(shape).to(dtype) for t in ts]), device, dtype)
+        return torch.cat([t.to(device).reshape(shape) for t in ts]).to(dtype).contiguous()
+
+    pc = [int(len(b)) for b in pred_xyxy]
+    gc = [int(len(b)) for b in gt_xyxy]
+    p_start = np.zeros(n_img + 1, np.int32)
+    g_start = np.zeros(n_img + 1, np.int32)
+    s_off = np.zeros(n_img + 1, np.int64)
+    np.cumsum(pc, out=p_start[1:])
+    np.cumsum(gc, out=g_start[1:])
+    np.cumsum([a * b for a, b in zip(pc, gc)], out=s_off[1:])
+    n, tot = int(p_start[-1]), int(s_off[-1])
+    pb, pcl = flat(pred_xyxy, torch.float32, 4), flat(pred_cls, torch.int32)
+    gb, gcl = flat(gt_xyxy, torch.float32, 4), flat(gt_cls, torch.int32)
+    score = torch.zeros(max(tot, 1), dtype=torch.float32, device=device)
+    rows = torch.full((max(n, 1),), -1, dtype=torch.int32, device=device)
+    cols = torch.full((max(n, 1),), -1, dtype=torch.int32, device=device)
+    valid = torch.zeros(max(n, 1), dtype=torch.uint8, device=device)
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    ps_d, gs_d, so_d = h2d(p_start, device), h2d(g_start, device), h2d(s_off, device)
+    _lib.check(lib.oodb200_match_boxes_f32(_ptr(pb), _ptr(pcl), _ptr(ps_d), _ptr(gb), _ptr(gcl), _ptr(gs_d), _ptr(so_d), n_img,
+                                           float(iou_threshold), int(bool(compat)), _ptr(score), _ptr(rows), _ptr(cols),
+                                           _ptr(valid), _ptr(status), _stream()), "oodb200_match_boxes_f32")
+    if int(status.item()):
+        raise ValueError("match_boxes: an image has more than 1024 boxes, or a box with zero area gives a non-finite IoU "
+                         "(scipy's linear_sum_assignment rejects such matrices too)")
+    score_h, rows_h, cols_h, valid_h = score.cpu().numpy(), rows.cpu().numpy(), cols.cpu().numpy(), valid.cpu().numpy()
+    out = []
+    for i in range(n_img):
+        a, b = int(p_start[i]), int(p_start[i + 1])
+        m = min(pc[i], gc[i])
+        out.append((np.nonzero(valid_h[a:b])[0].tolist(), score_h[s_off[i]:s_off[i + 1]].reshape(pc[i], gc[i]),
+                    (rows_h[a:a + m].astype(np.int64), cols_h[a:a + m].astype(np.int64))))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ k-search scores (K7)
 def pair_cluster_sums(x: torch.Tensor, labels: torch.Tensor, kc: int, metric: str) -> torch.Tensor:
     """sums[i][c] = sum of dist(x_i, x_j) over the rows j with labels[j] == c (float64 [n, kc]); x float32 [n, D] rows of

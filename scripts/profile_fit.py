@@ -8,8 +8,14 @@ from ood_in_object_detection_b200 import kmeans
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 variant = sys.argv[2] if len(sys.argv) > 2 else "separated"
-dev = torch.device("cuda", 0)
-x, gsizes, lsizes = bench.fit_data(n, 1, 0, dev, variant=variant)
+import torch.distributed as dist
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+group = dist.group.WORLD if world > 1 else None
+x, gsizes, lsizes = bench.fit_data(n, world, rank, dev, variant=variant)
 
 
 class Timed(kmeans.CudaBackend):
@@ -17,7 +23,7 @@ class Timed(kmeans.CudaBackend):
         super().__init__(device)
         self.log = []
 
-for name in ("step", "reduce", "reduce_into", "update", "converge", "seed_scan", "seed_sqdist", "seed_gather", "seed_pick", "colsum", "center"):
+for name in ("step", "reduce", "reduce_into", "update", "update_peers", "converge", "seed_scan", "seed_sqdist", "seed_gather", "seed_pick", "colsum", "center"):
     def wrap(name):
         base = getattr(kmeans.CudaBackend, name)
         def f(self, *a, **k):
@@ -32,7 +38,11 @@ out = {}
 for rep in range(2):
     be = Timed(dev)
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    r = kmeans.kmeans_fit_predict_single(x, gsizes, bench.FIT_K, random_state=10, backend=be, max_iter=int(os.environ.get("MAX_ITER", "300")))
+    if world > 1:
+        r = kmeans.kmeans_fit_sharded(x, lsizes, gsizes, bench.FIT_K, world, rank, group, random_state=10, backend=be,
+                                      max_iter=int(os.environ.get("MAX_ITER", "300")))
+    else:
+        r = kmeans.kmeans_fit_predict_single(x, gsizes, bench.FIT_K, random_state=10, backend=be, max_iter=int(os.environ.get("MAX_ITER", "300")))
     torch.cuda.synchronize(); wall = time.perf_counter() - t0
     agg = {}
     for name, e0, e1 in be.log:
@@ -40,4 +50,8 @@ for rep in range(2):
     out = {"n": n, "variant": variant, "wall_ms": 1e3 * wall, "phases_ms": {k: round(1e3 * v, 3) for k, v in r.seconds.items() if isinstance(v, float)},
            "lloyd_iters": r.seconds["lloyd_iters"], "issued": r.seconds.get("lloyd_issued"),
            "device_ms": {k: {"calls": v[0], "total_ms": round(v[1], 3), "per_call_ms": round(v[1] / v[0], 4)} for k, v in agg.items()}}
-print(json.dumps(out))
+out["collective"] = r.seconds.get("collective")
+if rank == 0:
+    print(json.dumps(out))
+if world > 1:
+    dist.destroy_process_group()

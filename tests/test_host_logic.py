@@ -18,21 +18,34 @@ LOGIT_KW = dict(per_class=True, per_stride=False, iou_threshold_for_matching=0.5
 COMMON = dict(iou_threshold_for_matching=0.5, min_conf_threshold_train=0.15, min_conf_threshold_test=0.15)
 
 
-def test_matching_matches_reference(golden):
+def test_matching_oracle_matches_reference(golden):
+    """oracle/matching.py (box_iou, scipy's assignment restated, the reference's walk with quirk Q8) against the valid_preds
+    the reference produced (golden_matching.npz), and its assignment solver against scipy on random and tie-heavy matrices.
+    The CUDA kernel (csrc/matching.cu) is held to both in tests/test_gpu_matching.py."""
+    from scipy.optimize import linear_sum_assignment
+    from oracle import matching
     g = golden("golden_matching.npz")
     for k, (P, G) in enumerate(g["shapes"]):
-        b6 = np.concatenate([g[f"pred_{k}"], np.full((P, 1), 0.5, np.float32), g[f"pcls_{k}"][:, None]], 1).astype(np.float32)
-        res = [Results(orig_img=batch_shape(1, 640, 640), boxes=torch.from_numpy(b6).reshape(P, 6))]
-        targets = dict(bboxes=[torch.from_numpy(g[f"gt_{k}"])], cls=[torch.from_numpy(g[f"gcls_{k}"])])
         for thr in (0.5, 0.3):
-            ou.OODMethod.match_predicted_boxes_to_targets(res, targets, thr)
-            assert res[0].valid_preds == g[f"valid_{k}_{thr}"].tolist(), (k, thr)
-        # intended semantics: every kept prediction really overlaps a same-class target above the threshold
-        ou.OODMethod.match_predicted_boxes_to_targets(res, targets, 0.5, compat=False)
-        m = res[0].assignment_score_matrix
-        assert all(float(m[i].max()) > 0.5 for i in res[0].valid_preds)
-        if P <= G:
-            assert res[0].valid_preds == g[f"valid_{k}_0.5"].tolist()
+            valid, score, _ = matching.match_predictions(g[f"pred_{k}"], g[f"pcls_{k}"], g[f"gt_{k}"], g[f"gcls_{k}"], thr)
+            assert valid == g[f"valid_{k}_{thr}"].tolist(), (k, thr)
+        valid, score, _ = matching.match_predictions(g[f"pred_{k}"], g[f"pcls_{k}"], g[f"gt_{k}"], g[f"gcls_{k}"], 0.5, compat=False)
+        assert all(float(score[i].max()) > 0.5 for i in valid)              # intended semantics: a real same-class overlap
+    rng = np.random.default_rng(0)
+    for trial in range(800):
+        P, G = int(rng.integers(0, 14)), int(rng.integers(0, 10))
+        kind = trial % 4
+        c = rng.uniform(0, 1, (P, G))
+        if kind == 1:
+            c = c * (rng.uniform(size=(P, G)) < 0.25)                     # mostly zeros, like IoU x mask
+        elif kind == 2:
+            c = rng.integers(0, 3, (P, G)).astype(float)                  # small integers: heavy ties
+        elif kind == 3:
+            c = np.round(c, 1) * (rng.uniform(size=(P, G)) < 0.5)
+        c = c.astype(np.float32)
+        for mx in (True, False):
+            a, b = linear_sum_assignment(c, maximize=mx), matching.lsap(c, mx)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (trial, mx)
 
 
 def test_targets_dict_matches_reference(golden):
