@@ -232,7 +232,9 @@ class CudaBackend:
         ok = torch.zeros(1, dtype=torch.int32, device=self.device)
         bufs = None
         try:
-            if os.environ.get("OODB200_KMEANS_PEERS", "1") == "0" or dist.get_backend(group) != "nccl":
+            # opt-in (OODB200_KMEANS_PEERS=1): measured on 2 x B200 the fused path is SLOWER end to end than NCCL's all-reduce
+            # (5.3 vs 2.0 ms per iteration at C3 / 2 although its kernels take 30 us: DESIGN.md section 6), so NCCL is the default
+            if os.environ.get("OODB200_KMEANS_PEERS", "0") != "1" or dist.get_backend(group) != "nccl":
                 raise RuntimeError("disabled")
             import torch.distributed._symmetric_memory as symm
             t = [symm.empty(int(numel), dtype=torch.float32, device=self.device) for _ in range(2)]

@@ -145,8 +145,8 @@ def test_reference_driver_fits_and_decides_with_our_classes(reference_driver, tm
     assert type(method) is ours.L2DistanceOneClusterPerStride and method.cluster_method == "KMeans_5"
     ood_evaluation.execute_pipeline_for_in_distribution_configuration(method, det, "cuda:0", _Loader(train), _Loader(train), log, args)
     files = sorted(os.listdir(tmp_path))
-    assert any(f.endswith("_activations.pt") for f in files) and any("_clusters_KMeans_5_" in f for f in files) \
-        and any(f.endswith("_thresholds_KMeans_5.json") for f in files), files
+    assert any("_activations" in f and f.endswith(".pt") for f in files) and any("_clusters_KMeans_5_" in f for f in files) \
+        and any("_thresholds_KMeans_5" in f and f.endswith(".json") for f in files), files
     thr_file = [f for f in files if f.endswith(".json")][0]
     assert json.load(open(os.path.join(tmp_path, thr_file))) == method.thresholds          # json-able, as the reference stores it
     # the oracle on the same activations: same clusters (well-separated or not, k-means labels follow sklearn), thresholds
