@@ -167,6 +167,23 @@ int oodb200_match_boxes_f32(const float* pred_xyxy, const int32_t* pred_cls, con
                             float* score, int32_t* row_ind, int32_t* col_ind, uint8_t* valid, int32_t* status,
                             void* stream);
 
+/* ---- NMS with the OoD payload.  Replaces the default path of
+ * `non_max_suppression_old` (/root/reference/ultralytics/utils/ops.py:348-530): candidates by best class confidence
+ * (:412, :463-466), xywh -> xyxy (:455-456), descending confidence order (:478-482), class-aware greedy NMS with boxes offset
+ * by cls * max_wh (torchvision nms semantics: float32 IoU, strict '>'; :485-489), max_det (:490), and the gather of the
+ * per-anchor payload rows `extra_item` (raw class logits) and `strides` with the same indices (:433-436, :479-481, :503-506).
+ * One CTA per image.
+ *   prediction [bs, 4 + nc, A] float32 (cx, cy, w, h, class confidences); extra_item [bs, n_extra, A] or NULL; strides [A] or NULL
+ *   det [bs, max_det, 6] (xyxy, confidence, class), out_extra [bs, max_det, n_extra], out_strides [bs, max_det],
+ *   out_anchor [bs, max_det] anchor index of every kept detection, count [bs] detections kept per image (max_det <= 1024)
+ *   workspace: oodb200_nms_workspace_bytes(bs, A) bytes, 16-byte aligned
+ */
+int64_t oodb200_nms_workspace_bytes(int bs, int n_anchors);
+int oodb200_nms_payload_f32(const float* prediction, const float* extra_item, const float* strides, int bs, int nc,
+                            int n_extra, int n_anchors, float conf_thres, float iou_thres, float max_wh, int max_det,
+                            int max_nms, float* det, float* out_extra, float* out_strides, int32_t* out_anchor,
+                            int32_t* count, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- K3: logit methods.  Replaces `LogitsMethod.compute_ood_decision_on_results` /
  * `compute_INDness_scores_on_results` (/root/reference/ood_utils.py:1195-1257) and the scorers
  * (:1388-1443).  One pass computes every method in method_mask.

@@ -32,6 +32,8 @@ SIGNATURES = {
     "oodb200_fmap_score_nhwc_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P,
                                     _P, _I, _P, _P, _P, _L, _P],
     "oodb200_match_boxes_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P],
+    "oodb200_nms_workspace_bytes": [_I, _I],
+    "oodb200_nms_payload_f32": [_P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _I, _I, _P, _P, _P, _P, _P, _P, _L, _P],
     "oodb200_logit_score_f32": [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "oodb200_fuse_u8": [_P, _P, _P, _I, _I, _P, _P],
     "oodb200_fuse_score_f32": [_P, _P, _I, _P, _P],
@@ -62,7 +64,7 @@ SIGNATURES = {
 }
 _RESTYPE = {"oodb200_last_error": C.c_char_p, "oodb200_fmap_workspace_bytes": C.c_int64,
             "oodb200_kmeans_smem_bytes": C.c_int64, "oodb200_kmeans_tc_workspace_bytes": C.c_int64,
-            "oodb200_segment_scratch_doubles": C.c_int64, "oodb200_vec_score_tc_workspace_bytes": C.c_int64}
+            "oodb200_segment_scratch_doubles": C.c_int64, "oodb200_vec_score_tc_workspace_bytes": C.c_int64, "oodb200_nms_workspace_bytes": C.c_int64}
 
 _lib = None
 

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liboodb200.so")
-SOURCES = ["fmap_score.cu", "logit_score.cu", "fit_kernels.cu", "kmeans.cu", "kmeans_tc.cu", "seed.cu", "silhouette.cu", "matching.cu"]
+SOURCES = ["fmap_score.cu", "logit_score.cu", "fit_kernels.cu", "kmeans.cu", "kmeans_tc.cu", "seed.cu", "silhouette.cu", "matching.cu", "nms.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--shared", "-cudart", "shared"]
 

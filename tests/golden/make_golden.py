@@ -557,6 +557,26 @@ def golden_bigfit(ref):
     print("golden_bigfit ok", {k: float(np.asarray(store[k])) for k in ("l2_thr_0_0", "cos_thr_1_1")})
 
 
+def golden_nms(ref):
+    """`non_max_suppression_old` (ultralytics/utils/ops.py:348-530) with the OoD payload (extra_item = raw logits, strides),
+    default path, at two confidence / IoU settings."""
+    from ultralytics.utils import ops as uops
+    from tests.helpers import nms_inputs
+    pred, logits, strides = nms_inputs()
+    store = dict(seed=91)
+    for tag, (conf, iou, max_det) in {"a": (0.25, 0.45, 300), "b": (0.15, 0.7, 50)}.items():
+        out, extra, st = uops.non_max_suppression_old(torch.from_numpy(pred), conf, iou, max_det=max_det, max_time_img=100.0,
+                                                     extra_item=torch.from_numpy(logits), strides=torch.from_numpy(strides))
+        # (max_time_img: the reference abandons the remaining images after 0.5 s + 0.05 s per image on a slow CPU)
+        store[f"{tag}_n"] = np.array([len(o) for o in out])
+        store[f"{tag}_det"] = np.concatenate([o.numpy() for o in out]).astype(F32)
+        store[f"{tag}_extra"] = np.concatenate([e.numpy().reshape(len(o), -1) for e, o in zip(extra, out)]).astype(F32)
+        store[f"{tag}_strides"] = np.concatenate([s.numpy().reshape(-1) for s in st]).astype(F32)
+        store[f"{tag}_cfg"] = np.array([conf, iou, max_det], np.float64)
+    np.savez_compressed(os.path.join(OUT, "golden_nms.npz"), **store)
+    print("golden_nms kept per image", {t: store[f"{t}_n"].tolist() for t in "ab"})
+
+
 def main():
     global OUT
     if "--out" in sys.argv:                                  # regenerate into another directory (tests/test_live_reference.py)
@@ -565,7 +585,7 @@ def main():
     ref = ref_shim.load()
     only = {"--only-c4": golden_c4, "--only-bigfit": golden_bigfit, "--only-eul": golden_eul_rank, "--only-matching": golden_matching,
             "--only-ksearch": golden_ksearch, "--only-quirks": golden_quirks, "--only-fusion": golden_fusion,
-            "--only-thresholds": golden_thresholds}
+            "--only-thresholds": golden_thresholds, "--only-nms": golden_nms}
     picked = [fn for flag, fn in only.items() if flag in sys.argv]
     if picked:
         for fn in picked:
@@ -573,6 +593,7 @@ def main():
         return
     golden_c4(ref)
     golden_bigfit(ref)
+    golden_nms(ref)
     golden_ksearch(ref)
     golden_eul_rank(ref)
     golden_matching(ref)

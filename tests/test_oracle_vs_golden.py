@@ -330,3 +330,19 @@ def test_fit_with_segments_of_4096_rows_and_more(golden):
                     np.testing.assert_allclose(np.asarray(scores[c][s], np.float64), g[f"{tag}_scores_{c}_{s}"], rtol=2e-5, atol=2e-7)
                 gt = g[f"{tag}_thr_{c}_{s}"]
                 assert (thr[c][s] == [] and gt.ndim == 1) or thr[c][s] == pytest.approx(float(gt), rel=2e-5)
+
+
+def test_nms_with_payload(golden):
+    """oracle/nms.py against `non_max_suppression_old` of the reference's ultralytics fork (boxes, confidences, classes, the
+    gathered logits and strides), bit for bit, at two threshold settings."""
+    from oracle import nms
+    from tests.helpers import nms_inputs
+    g = golden("golden_nms.npz")
+    pred, logits, strides = nms_inputs(int(g["seed"]))
+    for tag in "ab":
+        conf, iou, max_det = g[f"{tag}_cfg"]
+        out, extra, st = nms.non_max_suppression(pred, conf, iou, int(max_det), extra_item=logits, strides=strides)
+        assert [len(o) for o in out] == g[f"{tag}_n"].tolist()
+        assert np.array_equal(np.concatenate(out), g[f"{tag}_det"])
+        assert np.array_equal(np.concatenate([e.reshape(len(o), -1) for e, o in zip(extra, out)]), g[f"{tag}_extra"])
+        assert np.array_equal(np.concatenate(st), g[f"{tag}_strides"])
