@@ -551,6 +551,135 @@ def run_fit(device, world, rank, n_total, reps, warm, variant="realistic"):
                          "traffic": (_traffic("C3", "kmeans_step_dram_bytes_per_vector") or 0) * n_total / world or None}}
 
 
+# ------------------------------------------------------------------------------------- other BASELINE configs
+def _time_graph(fn, steps, flush):
+    """CUDA-event time per replay of `fn` captured as one CUDA graph, L2 flushed between replays."""
+    import torch
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        g.replay()
+        b.record()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / steps
+
+
+def other_config(name, device, flush, steps=10):
+    """Resident-input scoring of another BASELINE.json config on this GPU (C1: YOLOv8n B=8 vanilla L2, K=1; C4: YOLOv8l
+    B=32 per GPU, K=10, Cosine + MSP with and/or/score fusion; C5: YOLOv8x 1280x1280, 300 boxes per image, K=64, FP32 fused
+    path next to the tcgen05 cross-term path).  Same timing rules as the main line."""
+    import torch
+    from ood_in_object_detection_b200 import ops, synth
+    wl = synth.CONFIGS[name]
+    maps = device_maps(wl, 1100, device)
+    det = synth.detections(2100, wl.batch, wl.img, wl.nc, wl.lam, fixed=wl.fixed_boxes)
+    clusters, thr, table, lthr = fit_tables(ops, wl, maps, 3100, device)
+    batch = ops.make_batch(maps, det["boxes"], det["strides"], det["cls"], wl.img, device)
+    n = batch.n
+    metrics = {"C1": ("l2",), "C4": ("cosine",), "C5": ("l2", "cosine")}[name]
+    mask = sum(1 << ops.METRIC_SLOT[m] for m in metrics)
+    out = ops.alloc_fmap_scores(n, device)
+    alg, upper, _ = algorithmic_bytes(det, wl, wl.k, n_tables=len(metrics))
+    peak, _ = _peaks()
+    res = {"workload": wl.name, "boxes": n, "fmap_metrics": list(metrics), "k_per_class_stride": wl.k}
+    if name == "C4":                                    # + MSP and the three fusion rules in the same step
+        logits = torch.from_numpy(np.concatenate(det["logits"])).to(device)
+        lthr_d = torch.from_numpy(lthr).to(device)
+        lout = ops.LogitScores(scores=torch.zeros((5, n), dtype=torch.float32, device=device),
+                               indness=torch.zeros((5, n), dtype=torch.float32, device=device),
+                               decision=torch.ones((5, n), dtype=torch.uint8, device=device),
+                               sigmoid_mismatch=torch.zeros(1, dtype=torch.int32, device=device))
+        smin = torch.zeros((5, wl.nc), dtype=torch.float64, device=device)
+        smax = torch.ones((5, wl.nc), dtype=torch.float64, device=device)
+        neg1 = torch.full((n,), -1.0, dtype=torch.float32, device=device)       # the reference's distance INDness (Q2)
+
+        def step():
+            ops.fmap_score(batch, table, mask, True, compat_q1=True, out=out)
+            ops.logit_score(logits, batch.cls, 1 << ops.LOGIT_SLOT["MSP"], thr=lthr_d, smin=smin, smax=smax, out=lout)
+            ops.fuse_decisions(lout.decision[0], out.decision[2], "and")
+            ops.fuse_decisions(lout.decision[0], out.decision[2], "or")
+            ops.fuse_scores(lout.indness[0], neg1)
+        res["fusion"] = "fusion-MSP-Cosine_cl_stride: and / or / score in the same step"
+    else:
+        def step():
+            ops.fmap_score(batch, table, mask, True, compat_q1=True, out=out)
+    ms = _time_graph(step, steps, flush)
+    res.update({"ms_per_step": ms, "value": n / (ms * 1e-3), "unit": UNIT, "algorithmic_bytes": alg,
+                "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak})
+    if name == "C5":
+        # the dense-contraction variant (BASELINE.json configs[4]): pool -> rows grouped by (stride, class used) -> normalise ->
+        # x.c cross-term on tcgen05 (vec_score_tc) for l2 and cosine
+        pooled = ops.roi_pool(batch)
+        cls_used, out_index = ops.q1_plan(batch)
+        st_h = batch.stride_idx.cpu().numpy()
+        cu_h = cls_used.cpu().numpy()
+        oi = out_index.long()
+        groups = []
+        for s in range(3):
+            idx = np.nonzero(st_h == s)[0]
+            order = idx[np.argsort(cu_h[idx], kind="stable")]
+            seg_off = np.searchsorted(cu_h[order], np.arange(wl.nc + 1)).tolist()
+            cents = [np.asarray(clusters[c][s], np.float32).reshape(-1, wl.channels[s]) for c in range(wl.nc)]
+            ks = [len(a) for a in cents]
+            crow = np.concatenate([[0], np.cumsum(ks)])[:-1].tolist()
+            cent = torch.from_numpy(np.concatenate(cents)).to(device)
+            unit = torch.from_numpy(ops._unit_rows(np.concatenate(cents))).to(device)
+            tthr = torch.full((3, wl.nc), float("nan"), dtype=torch.float64, device=device)
+            for m in metrics:
+                tthr[ops.METRIC_SLOT[m]] = torch.tensor([thr[ops.METRIC_SLOT[m]][c][s] if thr[ops.METRIC_SLOT[m]][c][s] != [] else float("nan")
+                                                         for c in range(wl.nc)], dtype=torch.float64)
+            groups.append((torch.from_numpy(order).to(device), seg_off, cent, unit, crow, ks, tthr, wl.channels[s]))
+        tc_dec = torch.zeros((3, n), dtype=torch.uint8, device=device)
+        tc_arg = torch.zeros((3, n), dtype=torch.int32, device=device)
+
+        def tensor_step():
+            pooled_now = ops.roi_pool(batch, out=pooled)
+            for order, seg_off, cent, unit, crow, ks, tthr, c_s in groups:
+                x = ops.normalize_rows(pooled_now.index_select(0, order)[:, :c_s].contiguous())
+                for m in metrics:
+                    d, a, de = ops.vec_score_tc(x, seg_off, unit if m == "cosine" else cent, crow, ks, m, thr=tthr)
+                    slot = ops.METRIC_SLOT[m]
+                    tc_dec[slot].index_copy_(0, oi.index_select(0, order), de[slot])
+                    tc_arg[slot].index_copy_(0, oi.index_select(0, order), a[slot])
+        for _ in range(2):
+            tensor_step()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            tensor_step()
+            b.record()
+        torch.cuda.synchronize()
+        tms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        step()
+        torch.cuda.synchronize()
+        slots = [ops.METRIC_SLOT[m] for m in metrics]
+        kmax = max(max(len(np.atleast_2d(clusters[c][s])) if np.size(clusters[c][s]) else 0 for s in range(3)) for c in range(wl.nc))
+        flops = float(sum(2.0 * wl.k * wl.channels[int(s)] for s in st_h)) * len(metrics) * 3      # split-float: 3 tensor-core products
+        res["tensor_path"] = {"ms_per_step": tms, "value": n / (tms * 1e-3),
+                              "what": "roi_pool + per-stride gather / normalise + vec_score_tc (tcgen05 kind::tf32, split-float x, K <= 64) "
+                                      "for l2 and cosine, launched eagerly (index_select / index_copy plumbing included)",
+                              "decisions_differing_from_fp32": int((tc_dec[slots] != out.decision[slots]).sum()),
+                              "argmin_differing_from_fp32": int((tc_arg[slots] != out.argmin[slots]).sum()),
+                              "tensor_flops_per_step": flops, "k": kmax,
+                              "note": "the fused FP32 pass is the faster one at 4800 boxes: the contraction is 2*K*C flop per box = "
+                                      f"{flops / 1e9:.2f} GFLOP per step, far below what keeps the tensor pipe busy; tcgen05 pays off on the "
+                                      "fit side (millions of rows: Lloyd step, fit scores)"}
+    del maps, batch, out
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args, wl):
     import torch
@@ -787,23 +916,44 @@ def run_ours(args, wl):
             fit["matches_single_gpu_realistic"] = verify_against_single_gpu(device, world, rank, n_fit, "realistic")
         if rank == 0:
             fit["cpu_baseline"] = cpu_fit_baseline(variant="realistic", device=device)
+    others = {}
+    if rank == 0 and world == 1 and args.config == "C2" and not args.no_other_configs:
+        del batch_alt, maps_cl
+        torch.cuda.empty_cache()
+        for name in ("C1", "C4", "C5"):
+            try:
+                others[name] = other_config(name, device, flush)
+            except Exception as e:                          # a side measurement must not take the headline down
+                others[name] = {"error": f"{type(e).__name__}: {e}"}
     clk.stop()
+    if world > 1:                                        # every collective is done: only rank 0 has host work left
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
 
     if rank == 0:
         alg, upper, _ = algorithmic_bytes(det, wl, wl.k)
         peak, how = _peaks()
         achieved = alg / (fmap_ms * 1e-3) / 1e9
-        maps_cpu = [m[:CPU_SAMPLE_IMAGES].contiguous(memory_format=torch.contiguous_format).cpu() for m in maps]
-        cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, [0])        # warm the imports / thread pools
-        cpu_n, cpu_t, cpu_kind, cpu_dec = cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, list(range(CPU_SAMPLE_IMAGES)),
-                                                             want_decisions=True)
-        # the CPU arm's decisions on its sample against the CUDA path's decisions on the same boxes (same order: per image,
-        # stride-major for the FMap methods, box order for the logit methods)
-        n6 = sum(len(det["boxes"][i]) for i in range(CPU_SAMPLE_IMAGES))
-        flat = lambda d: np.array([v for im in d for v in im], np.uint8)
-        cpu_vs_gpu = {m: int((flat(cpu_dec[m]) != fout.decision[ops.METRIC_SLOT[m]][:n6].cpu().numpy()).sum()) for m in FMAP_METRICS}
-        cpu_vs_gpu.update({m: int((flat(cpu_dec[m]) != lout.decision[ops.LOGIT_SLOT[m]][:n6].cpu().numpy()).sum())
-                           for m in LOGIT_METHODS if m in cpu_dec})
+        cpu_baseline = {"value": None, "unit": UNIT, "note": "the CPU arm is timed at N = 1 only"}
+        if world == 1:
+            maps_cpu = [m[:CPU_SAMPLE_IMAGES].contiguous(memory_format=torch.contiguous_format).cpu() for m in maps]
+            cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, [0])        # warm the imports / thread pools
+            cpu_n, cpu_t, cpu_kind, cpu_dec = cpu_reference_pass(det, maps_cpu, wl, clusters, thr, lthr, list(range(CPU_SAMPLE_IMAGES)),
+                                                                 want_decisions=True)
+            # the CPU arm's decisions on its sample against the CUDA path's decisions on the same boxes (same order: per image,
+            # stride-major for the FMap methods, box order for the logit methods)
+            n6 = sum(len(det["boxes"][i]) for i in range(CPU_SAMPLE_IMAGES))
+            flat = lambda d: np.array([v for im in d for v in im], np.uint8)
+            cpu_vs_gpu = {m: int((flat(cpu_dec[m]) != fout.decision[ops.METRIC_SLOT[m]][:n6].cpu().numpy()).sum()) for m in FMAP_METRICS}
+            cpu_vs_gpu.update({m: int((flat(cpu_dec[m]) != lout.decision[ops.LOGIT_SLOT[m]][:n6].cpu().numpy()).sum())
+                               for m in LOGIT_METHODS if m in cpu_dec})
+            cpu_baseline = {"value": cpu_n / cpu_t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": cpu_kind,
+                            "sample": f"{CPU_SAMPLE_IMAGES} of {wl.batch} images ({cpu_n} boxes), L1+cosine FMap and MSP+Energy logits through "
+                                      + ("the reference's own compute_ood_decision_on_results (byte-compiled build oracle/_ref)"
+                                         if cpu_kind == "reference" else "oracle/cpu_path.py (loop-for-loop port, same sklearn/torchvision calls)"),
+                            "decisions_differing_from_gpu": cpu_vs_gpu}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
@@ -822,11 +972,7 @@ def run_ours(args, wl):
                                           "note": "the same fused pass over the same values with the maps in the other memory "
                                                   "layout (channels_last = what a detector run in torch.channels_last hands over)"},
                          "note": "HBM moves whole 128-byte lines; NCHW window rows are 8..52 B (DESIGN.md section 4)"},
-            "cpu_baseline": {"value": cpu_n / cpu_t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": cpu_kind,
-                             "sample": f"{CPU_SAMPLE_IMAGES} of {wl.batch} images ({cpu_n} boxes), L1+cosine FMap and MSP+Energy logits through "
-                                       + ("the reference's own compute_ood_decision_on_results (byte-compiled build oracle/_ref)"
-                                          if cpu_kind == "reference" else "oracle/cpu_path.py (loop-for-loop port, same sklearn/torchvision calls)"),
-                             "decisions_differing_from_gpu": cpu_vs_gpu},
+            "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "ood_utils.compute_ood_decisions_fused([L1, Cosine, MSP, Energy, MaxLogit], results)",
                     "matches_resident_path": bool(same),
@@ -842,9 +988,9 @@ def run_ours(args, wl):
         }
         if fit is not None:
             out["fit"] = fit
+        if others:
+            out["other_configs"] = others
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
@@ -862,6 +1008,7 @@ def main():
                     "BASELINE config 3, the same on every N)")
     ap.add_argument("--fit-variant", default="realistic", choices=list(FIT_VARIANTS),
                     help="--workload fit / --impl reference --workload fit: which C3 set (SURVEY.md section 8d)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C1 / C4 / C5 side measurements of the default line")
     ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the e2e, fit and cpu_baseline legs (tuning sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

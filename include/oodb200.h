@@ -263,6 +263,11 @@ int oodb200_kmeans_step_f32(const float* x, int dim, int n_seg, int k, const int
                             const int32_t* active, int32_t* labels, float* psums, float* pcounts, int32_t* n_changed,
                             int update, void* stream);
 int oodb200_kmeans_reduce_f32(const float* in, const int32_t* first, int n_groups, int64_t elems, float* out, void* stream);
+/* kmeans_reduce_step: the two reductions of an iteration (sums [n_blocks, elems_s] and counts [n_blocks, elems_c] ->
+ * out_s / out_c per group, fixed block order) in one launch; also chg_f[g] = (float)n_changed[g], n_changed[g] = 0. */
+int oodb200_kmeans_reduce_step_f32(const float* psums, const float* pcounts, const int32_t* first, int n_groups,
+                                   int64_t elems_s, int64_t elems_c, float* out_s, float* out_c, int32_t* n_changed,
+                                   float* chg_f, void* stream);
 int oodb200_kmeans_update_f32(const float* sums, const float* counts, const float* cent_old, const int32_t* seg_k,
                               const int32_t* active, int n_seg, int k, int dim, float* cent_new, float* shift_sq,
                               int32_t* n_empty, void* stream);

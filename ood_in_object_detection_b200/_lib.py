@@ -44,6 +44,7 @@ SIGNATURES = {
     "oodb200_kmeans_smem_bytes": [_I, _I],
     "oodb200_kmeans_step_f32": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P],
     "oodb200_kmeans_reduce_f32": [_P, _P, _I, _L, _P, _P],
+    "oodb200_kmeans_reduce_step_f32": [_P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P],
     "oodb200_kmeans_update_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "oodb200_kmeans_update_peers_f32": [_P, _I, _L, _L, _P, _I, C.c_uint32, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "oodb200_kmeans_converge_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],

@@ -421,6 +421,32 @@ __global__ void kmeans_reduce_kernel(const float* __restrict__ in, const int32_t
     }
 }
 
+// The block partials of one Lloyd iteration in ONE launch: sums and counts reduced in fixed block order (like
+// kmeans_reduce_kernel), the changed-label counters converted to float32 next to them (they ride in the all-reduce buffer)
+// and cleared for the next iteration.
+__global__ void kmeans_reduce_step_kernel(const float* __restrict__ psums, const float* __restrict__ pcounts,
+                                          const int32_t* __restrict__ first, int64_t elems_s, int64_t elems_c,
+                                          float* __restrict__ out_s, float* __restrict__ out_c, int32_t* __restrict__ n_changed,
+                                          float* __restrict__ chg_f) {
+    const int grp = blockIdx.y;
+    const int b0 = first[grp], b1 = first[grp + 1];
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < elems_s + elems_c; e += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        if (e < elems_s) {
+            for (int b = b0; b < b1; ++b) s += psums[(size_t)b * elems_s + e];
+            out_s[(size_t)grp * elems_s + e] = s;
+        } else {
+            const int64_t ec = e - elems_s;
+            for (int b = b0; b < b1; ++b) s += pcounts[(size_t)b * elems_c + ec];
+            out_c[(size_t)grp * elems_c + ec] = s;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        chg_f[grp] = (float)n_changed[grp];            // exact below 2^24 rows per segment
+        n_changed[grp] = 0;
+    }
+}
+
 // sklearn _average_centers + _center_shift (squared, summed per segment); empty clusters keep their old centre.
 // One CTA per segment, one WARP per cluster (clusters w, w + n_warps, ...): the K rows are independent, only the shift is
 // summed over the clusters, in cluster order (fixed: bit-reproducible).  An inactive (converged) segment copies its centres
@@ -846,6 +872,21 @@ extern "C" int oodb200_kmeans_reduce_f32(const float* in, const int32_t* first, 
     if (gx > 1024) gx = 1024;
     kmeans_reduce_kernel<<<dim3((unsigned)gx, (unsigned)n_groups), 256, 0, (cudaStream_t)stream>>>(in, first, n_groups, elems, out);
     return check_launch("kmeans_reduce");
+}
+
+extern "C" int oodb200_kmeans_reduce_step_f32(const float* psums, const float* pcounts, const int32_t* first, int n_groups,
+                                              int64_t elems_s, int64_t elems_c, float* out_s, float* out_c, int32_t* n_changed,
+                                              float* chg_f, void* stream) {
+    OODB200_REQUIRE(n_groups >= 0 && elems_s >= 0 && elems_c >= 0, "kmeans_reduce_step: negative size");
+    if (n_groups == 0) return OODB200_OK;
+    OODB200_REQUIRE(psums && pcounts && first && out_s && out_c && n_changed && chg_f, "kmeans_reduce_step: null pointer");
+    OODB200_REQUIRE(n_groups <= 65535, "kmeans_reduce_step: too many groups");
+    long long gx = (elems_s + elems_c + 255) / 256;
+    if (gx > 1024) gx = 1024;
+    if (gx < 1) gx = 1;
+    kmeans_reduce_step_kernel<<<dim3((unsigned)gx, (unsigned)n_groups), 256, 0, (cudaStream_t)stream>>>(psums, pcounts, first, elems_s,
+                                                                                                       elems_c, out_s, out_c, n_changed, chg_f);
+    return check_launch("kmeans_reduce_step");
 }
 
 extern "C" int oodb200_kmeans_update_f32(const float* sums, const float* counts, const float* cent_old, const int32_t* seg_k,

@@ -195,6 +195,12 @@ class CudaBackend:
                         "oodb200_kmeans_reduce_f32")
         return out
 
+    def reduce_step(self, psums, pcounts, first, n_groups, out_s, out_c, n_changed, chg_f):
+        """Both reductions of a Lloyd iteration + the changed-label counters (to float32, then cleared) in one launch."""
+        self._lib.check(self.lib.oodb200_kmeans_reduce_step_f32(
+            _ptr(psums), _ptr(pcounts), _ptr(first), n_groups, int(np.prod(psums.shape[1:])), int(np.prod(pcounts.shape[1:])),
+            _ptr(out_s), _ptr(out_c), _ptr(n_changed), _ptr(chg_f), _stream()), "oodb200_kmeans_reduce_step_f32")
+
     def update(self, sums, counts, cent, seg_k, active, out=None):
         n_seg, k, dim = cent.shape
         if out is None:
@@ -462,8 +468,10 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
     polls = []                                                              # (host flag, event) per issued iteration
     flag_ring = torch.empty(POLL_LAG + 2, dtype=torch.int32).pin_memory() if cuda else None
     issued = 0
+    fused_reduce = hasattr(backend, "reduce_step") and reduce != "ordered" and peers is None and table.n_blocks > 0
     for it in range(max_iter):
-        n_changed.zero_()
+        if not fused_reduce:
+            n_changed.zero_()
         psums, pcounts = backend.step(x, k, seg_k, cent, table, active, labels, n_changed, True)
         if reduce == "ordered":
             sums, cnts = _ordered_reduce(backend, psums, pcounts, table, n_seg, world, group)
@@ -480,6 +488,11 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
             # the update kernel itself waits for every rank's partials (tickets in symmetric memory), then adds them over NVLink
             new_cent, shift, n_empty = backend.update_peers(peers, it & 1, n_sum, n_cnt, cent, seg_k, active, other, cnts_sum, chg_sum)
             backend.converge(chg_sum, shift, n_empty, tol_d, cnts_sum, k, active, state, counts, any_active)
+        elif fused_reduce:
+            backend.reduce_step(psums, pcounts, seg_first, n_seg, sums_v, cnts_v, n_changed, chg_f)   # also clears n_changed
+            if distributed:
+                allreduce(flat)                                             # the one collective of the iteration
+            sums, cnts, chg = sums_v, cnts_v, chg_f
         else:
             if table.n_blocks and has_into:
                 backend.reduce_into(psums, seg_first, n_seg, sums_v)
