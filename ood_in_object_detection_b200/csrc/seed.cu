@@ -28,7 +28,7 @@
 namespace oodb200 {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kScanThreads = 128;
+constexpr int kScanThreads = 512;      // 15 warps stage a batch in a few round trips while lane 0 of warp 0 runs the chain
 constexpr int kScanBatch = 4096;       // values staged per buffer
 constexpr int kScanChunk = 128;        // running sum recorded every kScanChunk values
 constexpr int kMaxPieces = 16;         // ranks
@@ -48,8 +48,28 @@ struct ScanParams {
     int64_t* cand_id;                  // [n_seg, n_trials] global row index within the segment
 };
 
+// 32 consecutive floats from shared memory / the sequential float32 sum over them (program order pinned: see seed_scan_kernel)
+__device__ __forceinline__ void scan_ld32(float (&v)[32], uint32_t addr) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[4 * q]), "=f"(v[4 * q + 1]), "=f"(v[4 * q + 2]), "=f"(v[4 * q + 3])
+                     : "r"(addr + 16u * q)
+                     : "memory");
+}
+__device__ __forceinline__ float scan_chain32(float run, const float (&v)[32]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        asm volatile("add.rn.f32 %0, %0, %1;\n add.rn.f32 %0, %0, %2;\n add.rn.f32 %0, %0, %3;\n add.rn.f32 %0, %0, %4;\n"
+                     " add.rn.f32 %0, %0, %5;\n add.rn.f32 %0, %0, %6;\n add.rn.f32 %0, %0, %7;\n add.rn.f32 %0, %0, %8;"
+                     : "+f"(run)
+                     : "f"(v[8 * q]), "f"(v[8 * q + 1]), "f"(v[8 * q + 2]), "f"(v[8 * q + 3]), "f"(v[8 * q + 4]), "f"(v[8 * q + 5]),
+                       "f"(v[8 * q + 6]), "f"(v[8 * q + 7]));
+    return run;
+}
+
 __global__ void __launch_bounds__(kScanThreads) seed_scan_kernel(const ScanParams p) {
-    __shared__ __align__(16) float s_buf[2][kScanBatch];
+    __shared__ __align__(16) float s_buf[2][kScanBatch + 32];   // + one group: the look-ahead load of the chain needs no bounds test
     __shared__ int64_t s_start[kMaxPieces + 1];        // global index of the first row of every piece
     __shared__ int64_t s_off[kMaxPieces];
     const int g = blockIdx.x, tid = threadIdx.x;
@@ -89,36 +109,36 @@ __global__ void __launch_bounds__(kScanThreads) seed_scan_kernel(const ScanParam
             const int64_t i0 = b * kScanBatch;
             const int valid = (int)min((int64_t)kScanBatch, n - i0);
             const int n_chunks = (valid + kScanChunk - 1) / kScanChunk;
-            const float4* __restrict__ v4 = reinterpret_cast<const float4*>(s_buf[cur]);
-            // the FADD chain (4 cycles per value) must never wait for shared memory: 8 float4 are loaded one group ahead
-            float4 nxt[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) nxt[q] = v4[q];
-            const int n_groups = n_chunks * (kScanChunk / 32);                 // padding values are +0.0f: x + 0 == x for x >= 0
-            for (int gq = 0; gq < n_groups; ++gq) {
-                float4 curv[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) curv[q] = nxt[q];
-                if (gq + 1 < n_groups) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) nxt[q] = v4[(gq + 1) * 8 + q];
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    run = __fadd_rn(run, curv[q].x);
-                    run = __fadd_rn(run, curv[q].y);
-                    run = __fadd_rn(run, curv[q].z);
-                    run = __fadd_rn(run, curv[q].w);
-                }
-                if ((gq & 3) == 3) cs[b * (kScanBatch / kScanChunk) + (gq >> 2)] = run;
+            // The FADD chain (4 cycles per value) must never wait for shared memory: two register sets of 32 values, the loads
+            // of one set issued before the chain over the other (volatile asm keeps that order through the compiler).
+            const uint32_t base = (uint32_t)__cvta_generic_to_shared(s_buf[cur]);
+            const int n_groups = n_chunks * (kScanChunk / 32);                 // even; padding values are +0.0f: x + 0 == x for x >= 0
+            float va[32], vb[32];
+            scan_ld32(va, base);
+            for (int gq = 0; gq < n_groups; gq += 2) {
+                scan_ld32(vb, base + (uint32_t)(gq + 1) * 128u);
+                run = scan_chain32(run, va);
+                scan_ld32(va, base + (uint32_t)(gq + 2) * 128u);               // beyond the last group: the pad, never added
+                run = scan_chain32(run, vb);
+                if ((gq & 3) == 2) cs[b * (kScanBatch / kScanChunk) + (gq >> 2)] = run;
             }
         } else if (tid >= 32 && b + 1 < n_batches) {
             // warps 1.. stage the next batch meanwhile; the other lanes of warp 0 stay idle: a divergent warp would
             // interleave their global loads with the FADD chain of lane 0
             const int64_t i0 = (b + 1) * kScanBatch;
-            for (int j = tid - 32; j < kScanBatch; j += kScanThreads - 32) {
-                const int64_t i = i0 + j;
-                s_buf[cur ^ 1][j] = i < n ? value(i) : 0.f;
+            constexpr int kStagers = kScanThreads - 32;
+            for (int j0 = tid - 32; j0 < kScanBatch; j0 += 4 * kStagers) {     // 4 independent loads in flight per thread
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * kStagers;
+                    v[u] = (j < kScanBatch && i0 + j < n) ? value(i0 + j) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * kStagers;
+                    if (j < kScanBatch) s_buf[cur ^ 1][j] = v[u];
+                }
             }
         }
         __syncthreads();
@@ -126,26 +146,47 @@ __global__ void __launch_bounds__(kScanThreads) seed_scan_kernel(const ScanParam
     // ---- searchsorted(cumsum, u * pot), side='left', then clip to n - 1
     const int64_t n_chunks_tot = (n + kScanChunk - 1) / kScanChunk;
     const int trials = p.seg_trials ? p.seg_trials[g] : p.n_trials;
+    __shared__ int64_t s_lo[32];                       // per trial: first chunk whose end sum reaches the threshold
+    __shared__ float s_thr[32];
+    if (tid < trials) {
+        const double v = p.uniform[(size_t)g * p.n_trials + tid] * (double)p.pot[g];
+        const float thr = __double2float_ru(v);        // cum >= v  <=>  cum >= thr for float32 cum
+        int64_t lo = 0, hi = n_chunks_tot;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (cs[mid] >= thr) hi = mid; else lo = mid + 1;
+        }
+        s_lo[tid] = lo;
+        s_thr[tid] = thr;
+    }
+    __syncthreads();
+    // the chunk of every trial is staged by all threads (independent loads), then re-scanned from its exact start value
+    for (int e = tid; e < trials * kScanChunk; e += kScanThreads) {
+        const int t = e / kScanChunk;
+        const int64_t i = s_lo[t] * kScanChunk + (e - t * kScanChunk);
+        s_buf[0][e] = (s_lo[t] < n_chunks_tot && i < n) ? value(i) : 0.f;
+    }
+    __syncthreads();
     if (tid < p.n_trials) {
         int64_t id = 0;
         if (tid < trials) {
-            const double v = p.uniform[(size_t)g * p.n_trials + tid] * (double)p.pot[g];
-            const float thr = __double2float_ru(v);    // cum >= v  <=>  cum >= thr for float32 cum
-            int64_t lo = 0, hi = n_chunks_tot;         // first chunk whose end sum reaches thr
-            while (lo < hi) {
-                const int64_t mid = (lo + hi) >> 1;
-                if (cs[mid] >= thr) hi = mid; else lo = mid + 1;
-            }
+            const int64_t lo = s_lo[tid];
+            const float thr = s_thr[tid];
             if (lo >= n_chunks_tot) {
                 id = n - 1;                            // beyond the total: np.clip(ids, None, n - 1)
             } else {
                 float s = lo > 0 ? cs[lo - 1] : 0.f;
-                const int64_t i0 = lo * kScanChunk, i1 = min(n, i0 + kScanChunk);
-                id = i1 - 1;
-                for (int64_t i = i0; i < i1; ++i) {
-                    s = __fadd_rn(s, value(i));
-                    if (s >= thr) { id = i; break; }
+                const int64_t i0 = lo * kScanChunk;
+                const int cnt = (int)min((int64_t)kScanChunk, n - i0);
+                int hit = cnt - 1;
+                bool found = false;
+                const float* __restrict__ vals = s_buf[0] + tid * kScanChunk;
+#pragma unroll 8
+                for (int q = 0; q < kScanChunk; ++q) {                         // no early exit: the loads pipeline
+                    s = __fadd_rn(s, vals[q]);
+                    if (!found && q < cnt && s >= thr) { hit = q; found = true; }
                 }
+                id = i0 + hit;
             }
         }
         p.cand_id[(size_t)g * p.n_trials + tid] = id;

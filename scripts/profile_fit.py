@@ -23,7 +23,7 @@ class Timed(kmeans.CudaBackend):
         super().__init__(device)
         self.log = []
 
-for name in ("step", "reduce", "reduce_into", "update", "update_peers", "converge", "seed_scan", "seed_sqdist", "seed_gather", "seed_pick", "colsum", "center"):
+for name in ("step", "reduce", "reduce_into", "reduce_step", "update", "update_peers", "converge", "seed_scan", "seed_sqdist", "seed_gather", "seed_pick", "colsum", "center"):
     def wrap(name):
         base = getattr(kmeans.CudaBackend, name)
         def f(self, *a, **k):
