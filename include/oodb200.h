@@ -380,6 +380,19 @@ int oodb200_seed_pick_f32(const double* pots, const int32_t* seg_trials, const i
 int oodb200_pair_cluster_sums_f32(const float* x, int n, int d, int64_t ld, const int32_t* labels, int kc, int metric,
                                   double* sums, void* stream);
 
+/* The k-search (/root/reference/cluster_utils.py:203-302) scores up to 13 labelings of the SAME rows: the pair distances
+ * can be stored once and folded per labeling.
+ *   oodb200_pair_dist_matrix_f32:    dist [n, ld_dist] float32, dist[i][j] = dist(x_i, x_j) as above (exactly symmetric,
+ *                                    zero diagonal); same x / metric contract as oodb200_pair_cluster_sums_f32
+ *   oodb200_matrix_cluster_sums_f32: order int32 [n] = the rows sorted by label (stable: ascending row inside a label),
+ *                                    member_off int64 [kc + 1] = start of every label's run in `order`;
+ *                                    sums float64 [n, kc] as above, members added in ascending row order (deterministic)
+ */
+int oodb200_pair_dist_matrix_f32(const float* x, int n, int d, int64_t ld, int metric, float* dist, int64_t ld_dist,
+                                 void* stream);
+int oodb200_matrix_cluster_sums_f32(const float* dist, int n, int64_t ld_dist, const int32_t* order,
+                                    const int64_t* member_off, int kc, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

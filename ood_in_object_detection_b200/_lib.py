@@ -62,6 +62,8 @@ SIGNATURES = {
     "oodb200_seed_gather_f32": [_P, _I, _P, _I, _I, _P, _P, _P, _P],
     "oodb200_seed_pick_f32": [_P, _P, _P, _I, _I, _P, _L, _P, _P, _I, _P, _P, _P, _L, _P, _P],
     "oodb200_pair_cluster_sums_f32": [_P, _I, _I, _L, _P, _I, _I, _P, _P],
+    "oodb200_pair_dist_matrix_f32": [_P, _I, _I, _L, _I, _P, _L, _P],
+    "oodb200_matrix_cluster_sums_f32": [_P, _I, _L, _P, _P, _I, _P, _P],
 }
 _RESTYPE = {"oodb200_last_error": C.c_char_p, "oodb200_fmap_workspace_bytes": C.c_int64,
             "oodb200_kmeans_smem_bytes": C.c_int64, "oodb200_kmeans_tc_workspace_bytes": C.c_int64,

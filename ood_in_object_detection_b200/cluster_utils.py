@@ -33,6 +33,7 @@ def search_number_of_clusters(x, metric: str, perf_score_metric: str, logger: Lo
     assert len(ks) > 1, "Parameter n_clusters must have more than one value to evaluate"
     scores: List[float] = []
     found = {}
+    pairs = None                                              # the pair distances of x, shared by every candidate k
     for k in ks:
         score = default
         if k > n:
@@ -48,7 +49,9 @@ def search_number_of_clusters(x, metric: str, perf_score_metric: str, logger: Lo
                     logger.error(f"Error with parameters {{'n_clusters': {k}, 'random_state': {random_state}}}: "
                                  f"Cluster {bad} has less than {CUSTOM_HYP.clusters.MIN_SAMPLES} samples.")
                 elif perf_score_metric == "silhouette":
-                    score = ops.silhouette_score(x, labels, metric)
+                    if pairs is None:
+                        pairs = ops.PairDistances(x, metric)
+                    score = ops.silhouette_score(x, labels, metric, pairs=pairs)
                     logger.debug(f"Silhouette score: {score}")
                 else:
                     score = ops.calinski_harabasz_score(x, labels)

@@ -7,6 +7,7 @@ on the host are copied to the device, the kernels run there.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -700,18 +701,56 @@ def pair_cluster_sums(x: torch.Tensor, labels: torch.Tensor, kc: int, metric: st
     return out
 
 
-def silhouette_score(x: torch.Tensor, labels: torch.Tensor, metric: str) -> float:
+class PairDistances:
+    """The pair distances of ONE set of rows, shared by every labeling the k-search scores (cluster_utils.py:203-302 calls
+    `silhouette_score` once per candidate k on the same rows).  When the n x n float32 matrix fits the budget
+    (OODB200_PAIR_MATRIX_GB, default 8 GB: n <= 46 340) it is computed once (K7 in store mode) and every labeling costs one
+    pass over it; otherwise every labeling recomputes the distances (K7 in fold mode, nothing stored)."""
+
+    def __init__(self, x: torch.Tensor, metric: str, max_bytes: Optional[int] = None):
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise TypeError("PairDistances: float32 rows on the device expected")
+        self.metric = metric
+        self.xs = (normalize_rows(x) if metric == "cosine" else x).contiguous()
+        self.n = int(x.shape[0])
+        if max_bytes is None:
+            max_bytes = int(float(os.environ.get("OODB200_PAIR_MATRIX_GB", "8")) * (1 << 30))
+        self.matrix = None
+        if 0 < 4 * self.n * self.n <= max_bytes:
+            lib = _lib.load()
+            self.matrix = torch.empty((self.n, self.n), dtype=torch.float32, device=x.device)
+            _lib.check(lib.oodb200_pair_dist_matrix_f32(_ptr(self.xs), self.n, int(self.xs.shape[1]), int(self.xs.stride(0)),
+                                                        METRIC_SLOT[metric], _ptr(self.matrix), self.n, _stream()),
+                       "oodb200_pair_dist_matrix_f32")
+
+    def cluster_sums(self, labels: torch.Tensor, kc: int) -> torch.Tensor:
+        """sums[i][c] like pair_cluster_sums; labels int32 in [0, kc) on the device."""
+        if self.matrix is None:
+            return pair_cluster_sums(self.xs, labels, kc, self.metric)
+        lib = _lib.load()
+        order = torch.argsort(labels, stable=True).to(torch.int32)
+        off = torch.zeros(int(kc) + 1, dtype=torch.int64, device=labels.device)
+        off[1:] = torch.cumsum(torch.bincount(labels.long(), minlength=int(kc)), 0)
+        out = torch.empty((self.n, int(kc)), dtype=torch.float64, device=labels.device)
+        _lib.check(lib.oodb200_matrix_cluster_sums_f32(_ptr(self.matrix), self.n, self.n, _ptr(order), _ptr(off), int(kc),
+                                                       _ptr(out), _stream()), "oodb200_matrix_cluster_sums_f32")
+        return out
+
+
+def silhouette_score(x: torch.Tensor, labels: torch.Tensor, metric: str, pairs: Optional[PairDistances] = None) -> float:
     """sklearn.metrics.silhouette_score(X, labels, metric='l1' | 'l2' | 'cosine') (cluster_utils.py:277): mean over the
     samples of (b - a) / max(a, b), a = mean distance to the other members of the own cluster, b = smallest mean distance
     to another cluster; members of one-sample clusters count 0.  The pair distances are summed per cluster on the GPU
-    (K7), the n x n matrix is never stored."""
+    (K7); `pairs` = the distances of these rows kept from an earlier call (PairDistances) so that a search over k computes
+    them once."""
     uniq, enc = torch.unique(labels, return_inverse=True)
     kc, n = int(uniq.numel()), int(labels.numel())
     if not 1 < kc < n:
         raise ValueError(f"Number of labels is {kc}. Valid values are 2 to n_samples - 1 (inclusive)")
     enc32 = enc.to(torch.int32)
-    xs = normalize_rows(x) if metric == "cosine" else x
-    sums = pair_cluster_sums(xs, enc32, kc, metric)
+    if pairs is None:
+        pairs = PairDistances(x, metric, max_bytes=0)          # one labeling: fold, nothing stored
+    sums = pairs.cluster_sums(enc32, kc)
     freq = torch.bincount(enc, minlength=kc).to(torch.float64)
     rows = torch.arange(n, device=x.device)
     intra = sums[rows, enc] / (freq - 1.0)[enc]

@@ -427,6 +427,20 @@ def test_pair_cluster_sums_match_the_oracle(dev):
             xs = torch.from_numpy(D.normalize_rows(x) if metric == "cosine" else x).to(dev)
             got = ops.pair_cluster_sums(xs, torch.from_numpy(lab).to(dev), kc, metric).cpu().numpy()
             np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6 * n if metric == "cosine" else 1e-9)
+            # the stored-matrix route of the k-search: the same float32 distances (symmetric, zero diagonal), folded per labeling
+            pairs = ops.PairDistances(torch.from_numpy(x).to(dev), metric)
+            m = pairs.matrix.cpu().numpy()
+            assert m.shape == (n, n) and np.array_equal(m, m.T) and not m.diagonal().any()
+            np.testing.assert_allclose(m, d, rtol=2e-6, atol=3e-7 if metric == "cosine" else 1e-9)
+            got_m = pairs.cluster_sums(torch.from_numpy(lab).to(dev), kc).cpu().numpy()
+            fold = ops.pair_cluster_sums(pairs.xs, torch.from_numpy(lab).to(dev), kc, metric).cpu().numpy()     # same rows, fold route
+            np.testing.assert_allclose(got_m, fold, rtol=1e-12, atol=1e-12 * n)
+            np.testing.assert_allclose(got_m, want, rtol=1e-5, atol=2e-6 * n if metric == "cosine" else 1e-9)
+            lab2 = rng.integers(0, kc, size=n).astype(np.int32)             # a second labeling of the same rows
+            want2 = np.stack([d[:, lab2 == c].sum(1) for c in range(kc)], 1)
+            np.testing.assert_allclose(pairs.cluster_sums(torch.from_numpy(lab2).to(dev), kc).cpu().numpy(), want2,
+                                       rtol=1e-5, atol=2e-6 * n if metric == "cosine" else 1e-9)
+            assert ops.PairDistances(torch.from_numpy(x).to(dev), metric, max_bytes=0).matrix is None
 
 
 def test_silhouette_score_matches_sklearn(dev, golden):
