@@ -7,6 +7,7 @@ outside the hot path and raise NotImplementedError.
 """
 from __future__ import annotations
 
+import os
 from logging import Logger
 from typing import List, Optional, Tuple
 
@@ -34,13 +35,24 @@ def search_number_of_clusters(x, metric: str, perf_score_metric: str, logger: Lo
     scores: List[float] = []
     found = {}
     pairs = None                                              # the pair distances of x, shared by every candidate k
+    # Every candidate k is an independent KMeans(n_clusters=k, random_state) on the same rows: they are fitted together as
+    # the segments of ONE segmented fit over copies of x (the small fits are launch-bound one by one), when the copies fit
+    # the budget (OODB200_KSEARCH_BATCH_GB, default 4 GB).
+    fitted = {}
+    valid = [k for k in ks if k <= n]
+    batch_bytes = 4 * n * int(x.shape[1]) * len(valid)
+    if len(valid) > 1 and batch_bytes <= float(os.environ.get("OODB200_KSEARCH_BATCH_GB", "4")) * (1 << 30):
+        seeding = "device" if n >= kmeans.DEVICE_SEEDING_MIN_ROWS else "host"      # what a fit of x alone would use
+        res = kmeans.kmeans_fit_predict_single(x.repeat(len(valid), 1), [n] * len(valid), max(valid), random_state=random_state,
+                                               seg_k=valid, seeding=seeding)
+        fitted = {k: res.labels[i * n:(i + 1) * n] for i, k in enumerate(valid)}
     for k in ks:
         score = default
         if k > n:
             logger.error(f"Error with parameters {{'n_clusters': {k}, 'random_state': {random_state}}}: "
                          f"n_samples={n} should be >= n_clusters={k}.")
         else:
-            labels = kmeans.kmeans_fit_predict_single(x, [n], k, random_state=random_state).labels
+            labels = fitted[k] if k in fitted else kmeans.kmeans_fit_predict_single(x, [n], k, random_state=random_state).labels
             counts = torch.bincount(labels.long(), minlength=k).cpu().numpy()
             present = counts[counts > 0]
             if n - 1 > len(present) > 1:

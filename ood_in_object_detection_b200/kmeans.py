@@ -373,9 +373,12 @@ def _sklearn_first_center(rs: np.random.RandomState, n: int) -> int:
 
 def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table: BlockTable, local_off: Sequence[int],
                shard: Sequence[tuple], random_state: int = 10, max_iter: int = 300, tol: float = 1e-4,
-               backend=None, group=None, reduce: str = "allreduce", seeding: str = "auto") -> KMeansResult:
+               backend=None, group=None, reduce: str = "allreduce", seeding: str = "auto",
+               seg_k: Optional[Sequence[int]] = None) -> KMeansResult:
     """x_local: this rank's rows [n_local, dim] (segment-major, each segment's shard contiguous), float32.
     global_sizes: rows per segment over all ranks.  Returns labels for the local rows and the global centres.
+    seg_k: clusters per segment (each <= k; default k everywhere): every segment is an independent
+    `KMeans(n_clusters=seg_k[g], random_state=random_state)` -- the k-search fits all its candidates in one call.
 
     seeding: "device" -- the whole k-means++ loop runs on the device (csrc/seed.cu): exact sequential float32 cumsum +
              searchsorted, float64 candidate distances, potentials = correctly rounded float32 of the exact sum;
@@ -392,7 +395,9 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
     dev = x_local.device
     backend = backend or CudaBackend(dev)
     n_seg, dim = len(global_sizes), int(x_local.shape[1])
-    seg_k_host = [min(k, int(n)) for n in global_sizes]
+    if seg_k is not None and (len(seg_k) != len(global_sizes) or any(not 0 < int(kk) <= k for kk in seg_k)):
+        raise ValueError("seg_k: one value in 1..k per segment expected")
+    seg_k_host = [min(k if seg_k is None else int(seg_k[g]), int(n)) for g, n in enumerate(global_sizes)]
     seg_k = torch.tensor(seg_k_host, dtype=torch.int32, device=dev)
     seg_off_d = torch.tensor(list(local_off), dtype=torch.int64, device=dev)
     timing = {}

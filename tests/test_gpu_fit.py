@@ -499,3 +499,21 @@ def test_k_search_matches_the_reference(dev, golden):
         k_true = {"a": 5, "b": 3, "c": 4, "d": 6}[tag]
         assert clusters[c][s].shape == (k_true, g[f"{tag}_x"].shape[1]), (tag, clusters[c][s].shape)
     assert len(clusters[0][2]) == 0 and len(clusters[1][0]) == 0
+
+
+def test_k_search_batched_fits_equal_single_fits(dev):
+    """The k-search fits every candidate k as one segment of ONE segmented fit over copies of the rows: labels and centres
+    equal those of a fit of the rows alone with that k (FP32 kernels at D = 64, the tcgen05 step at D = 128)."""
+    from ood_in_object_detection_b200 import kmeans
+    rng = np.random.default_rng(21)
+    for n, dim in ((2500, 64), (4500, 128)):
+        cen = rng.standard_normal((5, dim)).astype(np.float32) * 1.5
+        x = torch.from_numpy(np.abs(cen[rng.integers(0, 5, n)] + rng.standard_normal((n, dim)).astype(np.float32))).to(dev)
+        ks = list(range(2, 15))
+        res = kmeans.kmeans_fit_predict_single(x.repeat(len(ks), 1), [n] * len(ks), max(ks), seg_k=ks, seeding="host")
+        for i, k in enumerate(ks):
+            one = kmeans.kmeans_fit_predict_single(x, [n], k, seeding="host")
+            assert torch.equal(res.labels[i * n:(i + 1) * n], one.labels), (n, dim, k)
+            assert torch.equal(res.centers[i, :k], one.centers[0, :k]), (n, dim, k)
+    with pytest.raises(ValueError):
+        kmeans.kmeans_fit_predict_single(x, [n], 4, seg_k=[5])
