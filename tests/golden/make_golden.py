@@ -577,6 +577,44 @@ def golden_nms(ref):
     print("golden_nms kept per image", {t: store[f"{t}_n"].tolist() for t in "ab"})
 
 
+def golden_postprocess(ref):
+    """The OoD branch of `DetectionPredictor.postprocess` (ultralytics/models/yolo/detect/predict.py:117-363) driven with a
+    stand-in predictor: every extraction mode, raw-logit and sigmoid heads, a confidence that empties an image."""
+    from ultralytics.models.yolo.detect.predict import DetectionPredictor
+    from tests.helpers import fake_predictor, postprocess_inputs
+    pred, logits, maps = postprocess_inputs()
+    p = torch.from_numpy(pred)
+    raw = torch.cat([p[:, :4], torch.from_numpy(logits)], 1)
+    tmaps = [torch.from_numpy(m) for m in maps]
+    img = torch.zeros((4, 3, 320, 320))
+    store = dict(seed=93)
+    cases = {"fs": ("ftmaps_and_strides", False, 0.25), "fs_hi": ("ftmaps_and_strides", False, 0.97),
+             "pos": ("ftmaps_and_strides_exact_pos", False, 0.25), "all": ("all_ftmaps", False, 0.25),
+             "roi": ("roi_aligned_ftmaps", False, 0.25), "lg": ("logits", False, 0.25), "lg_raw": ("logits", True, 0.25),
+             "lg_hi": ("logits", True, 0.97)}
+    for tag, (mode, before, conf) in cases.items():
+        head = raw.clone() if before else p.clone()
+        res = DetectionPredictor.postprocess(fake_predictor(mode, before, conf), ((head,), None if mode == "logits" else tmaps), img, img)
+        n = np.array([len(r.boxes) for r in res])
+        store[f"{tag}_n"] = n
+        store[f"{tag}_boxes"] = np.concatenate([r.boxes.data.numpy().reshape(-1, 6) for r in res]).astype(F32)
+        store[f"{tag}_shape"] = np.array(res[0].orig_img.shape)
+        if mode == "logits":
+            store[f"{tag}_extra"] = np.concatenate([r.extra_item.numpy().reshape(len(r.boxes), 20) for r in res]).astype(F32)
+        elif mode in ("ftmaps_and_strides", "ftmaps_and_strides_exact_pos"):
+            store[f"{tag}_extra"] = np.concatenate([r.extra_item[1].numpy().reshape(-1) for r in res]).astype(np.float64)
+            assert all(torch.equal(r.extra_item[0][s], tmaps[s][i]) for i, r in enumerate(res) for s in range(3))
+        elif mode == "roi_aligned_ftmaps":
+            for s in range(3):
+                store[f"{tag}_idx{s}"] = np.concatenate([r.extra_item[s][0].numpy().reshape(-1).astype(np.int64) for r in res])
+                store[f"{tag}_cnt{s}"] = np.array([len(r.extra_item[s][0]) for r in res])
+                store[f"{tag}_feat{s}"] = np.concatenate([r.extra_item[s][1].numpy().reshape(len(r.extra_item[s][0]), -1) for r in res]).astype(F32)
+        else:
+            assert all(torch.equal(r.extra_item[s], tmaps[s][i]) for i, r in enumerate(res) for s in range(3))
+    np.savez_compressed(os.path.join(OUT, "golden_postprocess.npz"), **store)
+    print("golden_postprocess kept per image", {t: store[f"{t}_n"].tolist() for t in cases})
+
+
 def main():
     global OUT
     if "--out" in sys.argv:                                  # regenerate into another directory (tests/test_live_reference.py)
@@ -585,7 +623,7 @@ def main():
     ref = ref_shim.load()
     only = {"--only-c4": golden_c4, "--only-bigfit": golden_bigfit, "--only-eul": golden_eul_rank, "--only-matching": golden_matching,
             "--only-ksearch": golden_ksearch, "--only-quirks": golden_quirks, "--only-fusion": golden_fusion,
-            "--only-thresholds": golden_thresholds, "--only-nms": golden_nms}
+            "--only-thresholds": golden_thresholds, "--only-nms": golden_nms, "--only-postprocess": golden_postprocess}
     picked = [fn for flag, fn in only.items() if flag in sys.argv]
     if picked:
         for fn in picked:
@@ -594,6 +632,7 @@ def main():
     golden_c4(ref)
     golden_bigfit(ref)
     golden_nms(ref)
+    golden_postprocess(ref)
     golden_ksearch(ref)
     golden_eul_rank(ref)
     golden_matching(ref)

@@ -83,3 +83,20 @@ def nms_inputs(seed=91, bs=4, nc=20, img=640):
             logits[b, cls_obj[obj[hot]], np.nonzero(hot)[0]] += rng.uniform(6, 11, int(hot.sum())).astype(F32)
         pred[b, 4:] = 1.0 / (1.0 + np.exp(-logits[b].astype(np.float64)))
     return pred, logits, strides
+
+
+def postprocess_inputs():
+    """Head output + hooked maps of golden_postprocess.npz (make_golden.py and tests/test_gpu_postprocess.py build the same)."""
+    from ood_in_object_detection_b200 import synth
+    pred, logits, _ = nms_inputs(seed=93, bs=4, nc=20, img=320)
+    maps = synth.feature_maps(7, 4, (16, 24, 32), (40, 20, 10))
+    return pred, logits, maps
+
+
+def fake_predictor(mode, before_sigmoid, conf, device="cpu"):
+    """The attributes `DetectionPredictor.postprocess` reads (predict.py:117-363), nothing else."""
+    from types import SimpleNamespace as NS
+    return NS(args=NS(conf=conf, iou=0.45, agnostic_nms=False, max_det=300, classes=None, model="yolov8s.pt", task="detect"),
+              model=NS(model=NS(extraction_mode=mode, model=[NS(output_values_before_sigmoid=before_sigmoid)]),
+                       names={i: str(i) for i in range(20)}),
+              device=__import__('torch').device(device), batch=[[f"im{i}.jpg" for i in range(4)]])

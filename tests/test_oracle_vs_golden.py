@@ -346,3 +346,33 @@ def test_nms_with_payload(golden):
         assert np.array_equal(np.concatenate(out), g[f"{tag}_det"])
         assert np.array_equal(np.concatenate([e.reshape(len(o), -1) for e, o in zip(extra, out)]), g[f"{tag}_extra"])
         assert np.array_equal(np.concatenate(st), g[f"{tag}_strides"])
+
+
+def test_postprocess_restated(golden):
+    """The OoD branch of `DetectionPredictor.postprocess` restated with oracle/nms.py (NMS + payload, box clipping to the
+    input, raw-logit heads pass through a sigmoid first) against the frozen outputs of the reference's method."""
+    from oracle import nms
+    from tests.helpers import postprocess_inputs
+    g = golden("golden_postprocess.npz")
+    pred, logits, _ = postprocess_inputs()
+    stride_of = np.concatenate([np.full((320 // s) ** 2, i, np.float32) for i, s in enumerate((8, 16, 32))])
+    for tag, conf, extra_item, strides in (("fs", 0.25, None, stride_of), ("fs_hi", 0.97, None, stride_of),
+                                           ("pos", 0.25, None, np.arange(len(stride_of), dtype=np.float32)),
+                                           ("lg_raw", 0.25, np.concatenate([pred[:, :4], logits], 1), None),
+                                           ("lg", 0.25, pred, None)):
+        head = pred
+        if tag == "lg_raw":                                      # predict.py:199-209: the head emits raw logits, NMS sees their sigmoid
+            import torch
+            head = np.concatenate([pred[:, :4], torch.from_numpy(logits).sigmoid().numpy()], 1)
+        res = nms.non_max_suppression(head, conf, 0.45, 300, extra_item=extra_item, strides=strides)
+        out, payload = res[0], (res[2] if strides is not None else res[1])
+        assert [len(o) for o in out] == g[f"{tag}_n"].tolist()
+        boxes = np.concatenate([o.reshape(-1, 6) for o in out]).copy()
+        boxes[:, [0, 2]] = boxes[:, [0, 2]].clip(0, 320)
+        boxes[:, [1, 3]] = boxes[:, [1, 3]].clip(0, 320)
+        assert np.array_equal(boxes, g[f"{tag}_boxes"])
+        if strides is not None:
+            assert np.array_equal(np.concatenate([np.asarray(p).reshape(-1) for p in payload]).astype(np.float64), g[f"{tag}_extra"])
+        else:
+            assert np.array_equal(np.concatenate([np.asarray(p).reshape(len(o), -1)[:, 4:] for p, o in zip(payload, out)]), g[f"{tag}_extra"])
+
