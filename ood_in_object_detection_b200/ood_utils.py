@@ -104,25 +104,29 @@ def extract_roi_aligned_features_from_correct_stride(ftmaps: List[Tensor], boxes
     cls0 = [torch.zeros(len(b), dtype=torch.int32) for b in boxes]
     out = [[[None, None] for _ in range(3)] for _ in range(n_img)]
     passes = range(3) if extract_all_strides else (None,)
+    counts = [int(len(b)) for b in boxes]
+    start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    img_of = np.repeat(np.arange(n_img), counts)
     for forced in passes:
         st = strides if forced is None else [torch.full((len(b),), forced, dtype=torch.int32) for b in boxes]
         batch = ops.make_batch(list(ftmaps), boxes, st, cls0, int(img_shape[1]), device)
         pooled = ops.roi_pool(batch)
-        st_host = [_np(s).astype(np.int64).reshape(-1) for s in st]
         chw = batch.map_chw.reshape(3, 3)
-        pos = 0
-        for i in range(n_img):
-            m = batch.counts[i]
-            for s in (range(3) if forced is None else (forced,)):
-                sel = np.nonzero(st_host[i] == s)[0] if m else np.zeros(0, np.int64)
-                idx = torch.from_numpy(sel.astype(np.int16)).to(device)
-                if len(sel):
-                    rows = pooled[pos:pos + m].index_select(0, torch.from_numpy(sel).to(device))[:, :int(chw[s, 0])]
-                    feats = rows.reshape(len(sel), int(chw[s, 0]), 1, 1)
+        st_host = batch.stride_idx.cpu().numpy().astype(np.int64) if forced is None else np.full(int(start[-1]), forced, np.int64)  # ONE read
+        for s in (range(3) if forced is None else (forced,)):
+            sel = np.nonzero(st_host == s)[0]                      # box rows of this stride, image-major
+            per_img = np.bincount(img_of[sel], minlength=n_img) if len(sel) else np.zeros(n_img, np.int64)
+            cut = np.concatenate([[0], np.cumsum(per_img)]).astype(np.int64)
+            C = int(chw[s, 0])
+            if len(sel):                                           # one gather per stride for the whole batch; per image: views
+                rows = pooled.index_select(0, torch.from_numpy(sel).to(device))[:, :C].reshape(len(sel), C, 1, 1)
+                idx_all = torch.from_numpy((sel - start[img_of[sel]]).astype(np.int16)).to(device)
+            for i in range(n_img):
+                a, b = int(cut[i]), int(cut[i + 1])
+                if b > a:
+                    out[i][s] = [idx_all[a:b], rows[a:b]]
                 else:
-                    feats = torch.empty(0, device=device)
-                out[i][s] = [idx, feats]
-            pos += m
+                    out[i][s] = [torch.zeros(0, dtype=torch.int16, device=device), torch.empty(0, device=device)]
     return out
 
 
