@@ -901,6 +901,36 @@ def run_ours(args, wl):
         dev_s = float(t[0])
     e2e_dev_value = n_all * dev_steps / dev_s
     del res_fd, res_ld
+    # the producer side in front of it: from the detector head's raw output [B, 4 + nc, A] and the hooked maps,
+    # both on the device, through postprocess (NMS + payload + Results of views) and the same fused class call, to the host
+    from_head = None
+    if world == 1:
+        try:
+            from types import SimpleNamespace as NS
+            from ood_in_object_detection_b200.postprocess import postprocess
+            head = torch.from_numpy(synth.head_output(7100, wl.batch, wl.nc, wl.img)[0]).to(device)
+            pred_like = NS(args=NS(conf=0.25, iou=0.45, agnostic_nms=False, max_det=300, classes=None, model="yolov8s.pt"),
+                           model=NS(model=NS(extraction_mode="ftmaps_and_strides", model=[NS(output_values_before_sigmoid=False)]),
+                                    names={i: str(i) for i in range(wl.nc)}), batch=None)
+            img_t = torch.empty((wl.batch, 3, wl.img, wl.img), device="meta")           # only its shape is read
+
+            def head_step():
+                results = postprocess(pred_like, ((head,), maps), img_t, img_t)
+                return results, ood_utils.compute_ood_decisions_fused([m_l1, m_cos], results, log)
+            results, dec_h = head_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(dev_steps):
+                results, dec_h = head_step()
+            torch.cuda.synchronize()
+            head_s = (time.perf_counter() - t0) / dev_steps
+            n_head = sum(len(r.boxes) for r in results)
+            from_head = {"value": n_head / head_s, "unit": UNIT, "ms_per_batch": 1e3 * head_s, "detections_kept": n_head,
+                         "anchors": int(head.shape[2]), "steps": dev_steps,
+                         "path": "head output + maps on the device -> postprocess (NMS with payload, Results) -> fused L1 + cosine decisions -> host"}
+            del head, results
+        except Exception as e:                              # a side measurement must not take the headline down
+            from_head = {"error": f"{type(e).__name__}: {e}"}
 
     fit = None
     if args.fit_n != 0:
@@ -981,6 +1011,7 @@ def run_ours(args, wl):
                     "pcie_note": "upper bound of this figure at the 55 GB/s the box's pinned H2D copies reach (profiles/r1_h2d_bw.log): "
                                  "the boxes' windows are scattered over ~all rows of every plane, a partial upload would need one "
                                  "strided copy per box",
+                    "from_head": from_head,
                     "device_inputs": {"value": e2e_dev_value, "unit": UNIT, "steps": dev_steps, "same_decisions": bool(same_d),
                                       "note": "same API call with the feature maps and detections already on the device (where the "
                                               "detector leaves them); D2H of the decisions and all host-side packing included"}},

@@ -29,7 +29,8 @@ import torch
 BLOCK_ROWS = 512          # rows per CTA partial
 SUPER_BLOCKS = 8          # block partials per super-block (unit of ownership; 4096 rows: C3's 200 000-row segments split
                           # into 49 units, so 8 ranks own 6-7 each)
-POLL_LAG = 2              # Lloyd iterations the device may run ahead of the host's convergence poll
+POLL_LAG = 2              # Lloyd iterations the device may run ahead of the host's convergence poll (1 when an iteration is long:
+                          # see kmeans_fit)
 
 
 def range_index(seg: int, world: int, rank: int) -> int:
@@ -471,6 +472,9 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
         chg_sum = torch.zeros(n_seg, dtype=torch.float32, device=dev)
     timing["collective"] = "peer-memory update" if peers is not None else ("nccl all-reduce" if distributed else "none")
     polls = []                                                              # (host flag, event) per issued iteration
+    # every iteration issued past the converged one is a wasted step: one iteration of lag hides the host loop when an
+    # iteration takes >= ~0.2 ms of device time (rows per rank x dim, the same figure on every rank), short ones need two
+    lag = 1 if sum(int(n) for n in global_sizes) // world * dim >= 100_000_000 else POLL_LAG
     flag_ring = torch.empty(POLL_LAG + 2, dtype=torch.int32).pin_memory() if cuda else None
     issued = 0
     fused_reduce = hasattr(backend, "reduce_step") and reduce != "ordered" and peers is None and table.n_blocks > 0
@@ -524,8 +528,8 @@ def kmeans_fit(x_local: torch.Tensor, global_sizes: Sequence[int], k: int, table
             ev = torch.cuda.Event()
             ev.record()
             polls.append((flag, ev))
-            if len(polls) > POLL_LAG:
-                f, e = polls[len(polls) - 1 - POLL_LAG]
+            if len(polls) > lag:
+                f, e = polls[len(polls) - 1 - lag]
                 e.synchronize()
                 if int(f[0]) == 0:
                     break

@@ -64,25 +64,9 @@ class Projection:
 
 
 def nms_inputs(seed=91, bs=4, nc=20, img=640):
-    """Detector-head-shaped inputs of golden_nms.npz (same statements as tests/golden/make_golden.py::nms_inputs)."""
-    rng = np.random.default_rng(seed)
-    strides = np.concatenate([np.full((img // s) ** 2, s, F32) for s in (8, 16, 32)])
-    A = len(strides)
-    pred = np.zeros((bs, 4 + nc, A), F32)
-    logits = (2.0 * rng.standard_normal((bs, nc, A)) - 7.0).astype(F32)
-    for b in range(bs):
-        n_obj = [6, 0, 14, 30][b % 4]
-        centres = rng.uniform(40, img - 40, (max(n_obj, 1), 2))
-        sizes = rng.uniform(30, 260, (max(n_obj, 1), 2))
-        obj = rng.integers(0, max(n_obj, 1), A)
-        pred[b, 0:2] = (centres[obj] + rng.normal(0, 6, (A, 2))).T
-        pred[b, 2:4] = (sizes[obj] * rng.uniform(0.85, 1.15, (A, 2))).T
-        if n_obj:
-            hot = rng.uniform(size=A) < 0.04
-            cls_obj = rng.integers(0, nc, n_obj)
-            logits[b, cls_obj[obj[hot]], np.nonzero(hot)[0]] += rng.uniform(6, 11, int(hot.sum())).astype(F32)
-        pred[b, 4:] = 1.0 / (1.0 + np.exp(-logits[b].astype(np.float64)))
-    return pred, logits, strides
+    """Detector-head-shaped inputs of golden_nms.npz / golden_postprocess.npz (the generator lives in the package: synth.head_output)."""
+    from ood_in_object_detection_b200 import synth
+    return synth.head_output(seed, bs, nc, img)
 
 
 def postprocess_inputs():
