@@ -5,9 +5,17 @@
 // (class, stride).  Per new centre:
 //
 //   seed_scan      `np.searchsorted(np.cumsum(closest_dist_sq), rand_vals)` (:252-257).  np.cumsum on float32 is a
-//                  sequential float32 sum, so the scan is a single dependent FADD chain per segment (one CTA per
-//                  segment: all threads stage 4096 values into shared memory, double buffered, one thread runs the
-//                  chain at 4 cycles per value and records the running sum at the end of every 128-value chunk).
+//                  sequential float32 sum: a single dependent FADD chain per segment (4 cycles per value: 0.5 ms for the
+//                  200 000 rows of a C3 segment, and it does not shrink with the number of ranks).  The kernel (one CTA per
+//                  segment) evaluates that chain in PARALLEL and bit for bit: inside one binade the running sum is an
+//                  integer number of ulps and every addend contributes a fixed integer increment (its value rounded to the
+//                  ulp; an exact tie goes to the even total, which makes a thread's result a function of the parity it
+//                  starts from), so 512 threads each sum the increments of 128 values for both parities and a prefix scan
+//                  over the composition of those parity maps gives the exact sum at every 128-value boundary; where the sum
+//                  leaves the binade (~20 times per segment) one block is redone with the float chain itself and the pass
+//                  restarts behind it (details at the code).  `OODB200_SEED_SCAN=serial` selects the single-thread chain
+//                  (staged through shared memory, look-ahead loads pinned ahead of the FADDs).  Both record the running sum
+//                  at the end of every 128-value chunk.
 //                  The search is a binary search over the chunk sums followed by a re-scan of ONE chunk from its
 //                  exact start value, which reproduces the sequential sums bit for bit.  rand_vals = u * pot is
 //                  float64 (u ~ RandomState.uniform drawn on the host up front: the stream does not depend on the
@@ -28,10 +36,11 @@
 namespace oodb200 {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kScanThreads = 512;      // 15 warps stage a batch in a few round trips while lane 0 of warp 0 runs the chain
+constexpr int kScanThreads = 512;      // parallel evaluation: one 128-value block per thread and pass; serial: 15 staging warps + the chain
 constexpr int kScanBatch = 4096;       // values staged per buffer
 constexpr int kScanChunk = 128;        // running sum recorded every kScanChunk values
 constexpr int kMaxPieces = 16;         // ranks
+constexpr int kScanPitch = 65;         // floats per block row of a warp's tile in the parallel evaluation (64 values + 1)
 
 struct ScanParams {
     const float* closest_all;          // all-gathered closest distances
@@ -46,6 +55,7 @@ struct ScanParams {
     float* chunk_sum;                  // [n_seg, max_chunks] scratch
     int64_t max_chunks;
     int64_t* cand_id;                  // [n_seg, n_trials] global row index within the segment
+    int serial;                        // 1: the single-thread FADD chain (A/B and fallback), 0: the parallel exact evaluation
 };
 
 // 32 consecutive floats from shared memory / the sequential float32 sum over them (program order pinned: see seed_scan_kernel)
@@ -70,6 +80,7 @@ __device__ __forceinline__ float scan_chain32(float run, const float (&v)[32]) {
 
 __global__ void __launch_bounds__(kScanThreads) seed_scan_kernel(const ScanParams p) {
     __shared__ __align__(16) float s_buf[2][kScanBatch + 32];   // + one group: the look-ahead load of the chain needs no bounds test
+    extern __shared__ float s_tile[];                  // [warps][32][kScanPitch], parallel evaluation only
     __shared__ int64_t s_start[kMaxPieces + 1];        // global index of the first row of every piece
     __shared__ int64_t s_off[kMaxPieces];
     const int g = blockIdx.x, tid = threadIdx.x;
@@ -99,8 +110,152 @@ __global__ void __launch_bounds__(kScanThreads) seed_scan_kernel(const ScanParam
         }
     };
     float* __restrict__ cs = p.chunk_sum + (size_t)g * p.max_chunks;
-    const int64_t n_batches = (n + kScanBatch - 1) / kScanBatch;
-    stage(0, 0);
+    const int64_t n_blocks = (n + kScanChunk - 1) / kScanChunk;
+    if (!p.serial) {
+        // ---- the sequential float32 sum at every 128-value boundary, evaluated in parallel and bit for bit ----
+        // While the running sum s stays inside one binade [2^e, 2^(e+1)) it is an integer multiple S of u = 2^(e-23), and
+        // RN(s + v) = (S + rn(v / u)) * u: the increment rn(v / u) does not depend on s, except that an exact tie (fraction
+        // 0.5) rounds to the side that makes S even.  So a thread can sum the increments of its 128 values on its own, once
+        // for each parity its start value can have (T0, T1); the threads' results are combined by a prefix scan over the
+        // composition "parity in -> (increment, parity out)"; every sum the float chain would have produced at a 128-value
+        // boundary is then S0 + prefix, exactly.  The assumption fails where the sum leaves the binade (at most ~40 times per
+        // segment, plus the start where s is tiny): the first block whose end reaches 2^24 units is redone with the plain float
+        // chain from its exact start value, and the pass restarts behind it with the new unit.  The number of blocks per pass
+        // grows with the blocks already summed (the next binade ends about where the sum has doubled).
+        __shared__ float s_run;
+        __shared__ long long s_blk, s_w0[kScanThreads / 32], s_w1[kScanThreads / 32];
+        __shared__ int s_cross;
+        const int lane = tid & 31, warp = tid >> 5;
+        if (tid == 0) { s_run = 0.f; s_blk = 0; }
+        __syncthreads();
+        // the plain float chain over one block: all threads stage its values (one round trip), one thread adds them in order
+        auto chain_block = [&](float s0, int64_t blk, int owner) {      // called by every thread; results through s_run / s_blk / cs
+            const int64_t i0 = blk * kScanChunk;
+            if (tid < kScanChunk) s_buf[0][tid] = i0 + tid < n ? value(i0 + tid) : 0.f;   // + 0.0f leaves a sum >= 0 unchanged
+            __syncthreads();
+            if (tid == owner) {
+                const float4* __restrict__ v4 = reinterpret_cast<const float4*>(s_buf[0]);
+#pragma unroll 8
+                for (int q = 0; q < kScanChunk / 4; ++q) {
+                    const float4 v = v4[q];
+                    s0 = __fadd_rn(s0, v.x); s0 = __fadd_rn(s0, v.y); s0 = __fadd_rn(s0, v.z); s0 = __fadd_rn(s0, v.w);
+                }
+                cs[blk] = s0;
+                s_run = s0;
+                s_blk = blk + 1;
+            }
+        };
+        for (;;) {
+            const int64_t blk0 = s_blk;
+            const float s = s_run;
+            if (blk0 >= n_blocks) break;
+            const int eb = (__float_as_int(s) >> 23) & 0xff;           // biased exponent (s >= 0)
+            if (eb < 27 || eb > 250) {                                   // zero / tiny / huge: no unit to count in, take the block serially
+                __syncthreads();
+                chain_block(s, blk0, 0);
+                __syncthreads();
+                continue;
+            }
+            const float scale = __int_as_float((277 - eb) << 23);       // 2^(23 - e): v * scale = v / u, exact
+            const float u = __int_as_float((eb - 23) << 23);            // 2^(e - 23)
+            const long long Sint = (long long)(s * scale);              // in [2^23, 2^24)
+            long long lim = 2 * blk0 + 4;                                // blocks this pass (see above)
+            if (lim > kScanThreads) lim = kScanThreads;
+            const int nb = (int)min((long long)(n_blocks - blk0), lim);
+            unsigned t0 = 0, t1 = 0;                                     // increments for start parity 0 / 1 (<= 128 * 2^24 < 2^32)
+            if (warp * 32 < nb) {                                        // warp-uniform: this warp's 32 blocks = 4096 consecutive values
+                // The warp loads them with coalesced requests into its own shared-memory tile (a lane reading its own block
+                // straight from global memory touches 32 different lines per request) and every lane then walks its block there
+                // (row pitch 65 floats: conflict-free).  Two halves of 64 values per block keep the tile at 8.3 KB per warp.
+                float* __restrict__ tile = s_tile + (size_t)warp * (32 * kScanPitch);
+                const int64_t w0 = (blk0 + warp * 32) * kScanChunk;
+                const float* __restrict__ src = p.closest_all + s_off[0] + w0;      // np == 1: the segment is one piece
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    if (np == 1 && w0 + 32 * kScanChunk <= n) {          // the common case, free of branches: the loads batch
+#pragma unroll 1
+                        for (int e0 = 0; e0 < 32 * 64; e0 += 32 * 32) {
+                            float vv[32];
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) {               // element e: block e / 64, value h * 64 + e % 64
+                                const int e = e0 + q * 32 + lane;
+                                vv[q] = __ldg(src + (e >> 6) * kScanChunk + h * 64 + (e & 63));
+                            }
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) {
+                                const int e = e0 + q * 32 + lane;
+                                tile[(e >> 6) * kScanPitch + (e & 63)] = vv[q];
+                            }
+                        }
+                    } else {
+                        for (int e = lane; e < 32 * 64; e += 32) {
+                            const int b = e >> 6, j = e & 63;
+                            const int64_t i = w0 + b * kScanChunk + h * 64 + j;
+                            tile[b * kScanPitch + j] = i < n ? value(i) : 0.f;
+                        }
+                    }
+                    __syncwarp();
+                    if (tid < nb) {
+                        const float* __restrict__ mine = tile + lane * kScanPitch;
+#pragma unroll 8
+                        for (int j = 0; j < 64; ++j) {
+                            float x = mine[j] * scale;
+                            if (!(x < 16777216.f)) x = 16777216.f;      // leaves the binade anyway (also inf / nan)
+                            const float fl = floorf(x), fr = x - fl;    // exact
+                            const unsigned qi = (unsigned)fl;
+                            if (fr == 0.5f) {                            // tie: to the even total
+                                t0 += qi + ((t0 + qi) & 1u);
+                                t1 += qi + ((1u + t1 + qi) & 1u);
+                            } else {
+                                const unsigned up = fr > 0.5f ? 1u : 0u;
+                                t0 += qi + up;
+                                t1 += qi + up;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            // inclusive scan of the composition inside the warp: (b then a)(p) = b_p + a_{p ^ (b_p & 1)}
+            long long a0 = t0, a1 = t1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long b0 = __shfl_up_sync(kFull, a0, o), b1 = __shfl_up_sync(kFull, a1, o);
+                if (lane >= o) {
+                    const long long n0 = b0 + ((b0 & 1) ? a1 : a0), n1 = b1 + ((b1 & 1) ? a0 : a1);
+                    a0 = n0;
+                    a1 = n1;
+                }
+            }
+            const long long up0 = __shfl_up_sync(kFull, a0, 1), up1 = __shfl_up_sync(kFull, a1, 1);
+            if (lane == 31) { s_w0[warp] = a0; s_w1[warp] = a1; }
+            if (tid == 0) s_cross = nb;
+            __syncthreads();
+            long long acc = 0;
+            int par = (int)(Sint & 1);
+            for (int w = 0; w < warp; ++w) {
+                const long long t = par ? s_w1[w] : s_w0[w];
+                acc += t;
+                par ^= (int)(t & 1);
+            }
+            const long long incl = acc + (par ? a1 : a0);               // units added up to and including this thread's block
+            const long long excl = acc + (lane ? (par ? up1 : up0) : 0);
+            const bool crossing = tid < nb && Sint + incl >= 16777216ll;
+            if (crossing) atomicMin(&s_cross, tid);
+            __syncthreads();
+            const int tc = s_cross;
+            if (tid < nb && tid < tc) cs[blk0 + tid] = (float)(Sint + incl) * u;   // < 2^24 units: exact
+            if (tc < nb) {
+                chain_block((float)(Sint + excl) * u, blk0 + tc, tc);     // only thread tc's start value is used
+            } else if (tid == nb - 1) {
+                s_run = (float)(Sint + incl) * u;
+                s_blk = blk0 + nb;
+            }
+            __syncthreads();
+        }
+    }
+    const int64_t n_batches = p.serial ? (n + kScanBatch - 1) / kScanBatch : 0;
+    if (p.serial) stage(0, 0);
     __syncthreads();
     float run = 0.f;                                   // thread 0: the sequential float32 sum
     for (int64_t b = 0; b < n_batches; ++b) {
@@ -552,9 +707,16 @@ extern "C" int oodb200_seed_scan_f32(const float* closest_all, const int64_t* pi
     OODB200_REQUIRE(n_trials >= 1 && n_trials <= 32, "seed_scan: 1..32 trials");
     if (n_seg == 0) return OODB200_OK;
     OODB200_REQUIRE(closest_all && piece_off && piece_cnt && uniform && pot && chunk_sum && cand_id, "seed_scan: null pointer");
+    static int serial = -1;                                         // OODB200_SEED_SCAN=serial: the single-thread chain (A/B runs)
+    if (serial < 0) { const char* env = getenv("OODB200_SEED_SCAN"); serial = (env && env[0] == 's') ? 1 : 0; }
     ScanParams p = {closest_all, piece_off, piece_cnt, n_pieces, uniform, pot, seg_trials, seg_on, n_trials, chunk_sum,
-                    max_chunks, cand_id};
-    seed_scan_kernel<<<n_seg, kScanThreads, 0, (cudaStream_t)stream>>>(p);
+                    max_chunks, cand_id, serial};
+    const size_t tile_bytes = serial ? 0 : sizeof(float) * (kScanThreads / 32) * 32 * kScanPitch;
+    if (tile_bytes && cudaFuncSetAttribute(seed_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes) != cudaSuccess) {
+        set_error("seed_scan: cannot reserve %zu bytes of shared memory", tile_bytes);
+        return OODB200_ERR_CUDA;
+    }
+    seed_scan_kernel<<<n_seg, kScanThreads, tile_bytes, (cudaStream_t)stream>>>(p);
     return check_launch("seed_scan");
 }
 

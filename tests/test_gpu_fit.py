@@ -178,6 +178,47 @@ def test_seed_scan_is_numpy_cumsum_searchsorted(dev):
         assert (got[g, trials[g]:] == ids[0]).all()
 
 
+def test_seed_scan_boundary_sums_are_the_sequential_float32_sums(dev):
+    """The running sums the scan records at every 128-value boundary == np.cumsum(float32) there, bit for bit, on data built to
+    break a parallel evaluation of a sequential float chain: exact rounding ties (values on a coarse binary grid), outliers that
+    jump several binades at once, long runs of zeros, denormals, an all-zero segment, a constant segment, heavy tails."""
+    from ood_in_object_detection_b200 import kmeans
+    be = kmeans.CudaBackend(dev)
+    rng = np.random.default_rng(23)
+    n = 70001
+    grid = rng.integers(0, 1024, n).astype(np.float32)                            # integers: ties once ulp(sum) = 2 (sum >= 2^24), 4, ...
+    jumps = (rng.random(n) ** 6).astype(np.float32)
+    jumps[[5, 1000, 1001, 30000, 65000]] = [3.0e4, 7.0e6, 1.0e-30, 4.0e9, 1.5e3]
+    zeros = np.zeros(n, np.float32); zeros[40000:] = rng.random(n - 40000).astype(np.float32) * 1e-3
+    den = (rng.random(n) * 1e-41).astype(np.float32); den[60000:] = 1e-20
+    const = np.full(n, 0.1, np.float32)
+    tails = np.exp(rng.standard_normal(n) * 4).astype(np.float32)
+    halves = np.full(n, 513.0, np.float32); halves[::7] = 1025.0                  # odd: EVERY add is a tie once the sum passes 2^24
+    big_ties = np.full(200000, 131.0, np.float32); big_ties[::2] = 129.0          # crosses 2^24 after ~129 k odd addends (ties above it)
+    segs = [grid, jumps, zeros, den, const, tails, np.zeros(300, np.float32), halves, big_ties,
+            (rng.random(200000) ** 4).astype(np.float32)]
+    sizes = [len(v) for v in segs]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    buf = np.concatenate(segs)
+    piece_off, piece_cnt = off[:-1].reshape(-1, 1).copy(), np.array(sizes, np.int64).reshape(-1, 1)
+    n_trials = 8
+    uni = rng.random((len(segs), n_trials))
+    pot = np.array([np.cumsum(v)[-1] for v in segs], np.float32)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    cand = torch.zeros((len(segs), n_trials), dtype=torch.int64, device=dev)
+    be.seed_scan(t(buf), t(piece_off), t(piece_cnt), t(uni), t(pot), t(np.full(len(segs), n_trials, np.int32)),
+                 t(np.ones(len(segs), np.int32)), max(sizes), cand)
+    sums = be._sbuf.cpu().numpy()
+    got = cand.cpu().numpy()
+    for g, v in enumerate(segs):
+        cum = np.cumsum(v)                                                        # numpy: sequential float32 adds
+        ends = np.concatenate([cum[127::128], cum[-1:]]) if len(v) % 128 else cum[127::128]
+        assert np.array_equal(sums[g, :len(ends)].view(np.uint32), ends.view(np.uint32)), \
+            (g, int(np.flatnonzero(sums[g, :len(ends)] != ends)[0]))
+        ids = np.clip(np.searchsorted(cum, uni[g] * pot[g]), None, len(v) - 1)
+        assert np.array_equal(got[g], ids), (g, got[g], ids)
+
+
 def test_seed_sqdist_matches_float64_expansion(dev):
     """Candidate distances: float32(float64 expansion) exactly like sklearn's `_euclidean_distances_upcast`, min
     against `closest`, bit-reproducible potentials; D = 576 (4 rows per warp) and an odd D (one row per warp)."""
