@@ -169,10 +169,13 @@ __global__ void __launch_bounds__(kScanThreads) seed_scan_kernel(const ScanParam
                 // (row pitch 65 floats: conflict-free).  Two halves of 64 values per block keep the tile at 8.3 KB per warp.
                 float* __restrict__ tile = s_tile + (size_t)warp * (32 * kScanPitch);
                 const int64_t w0 = (blk0 + warp * 32) * kScanChunk;
-                const float* __restrict__ src = p.closest_all + s_off[0] + w0;      // np == 1: the segment is one piece
+                int pr = 0;                                              // the piece (rank) the warp's range starts in
+                while (pr + 1 < np && w0 >= s_start[pr + 1]) ++pr;
+                const bool inside = w0 + 32 * kScanChunk <= s_start[pr + 1];       // ... and ends in: one contiguous source
+                const float* __restrict__ src = p.closest_all + s_off[pr] + (w0 - s_start[pr]);
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
-                    if (np == 1 && w0 + 32 * kScanChunk <= n) {          // the common case, free of branches: the loads batch
+                    if (inside) {                                        // the common case, free of branches: the loads batch
 #pragma unroll 1
                         for (int e0 = 0; e0 < 32 * 64; e0 += 32 * 32) {
                             float vv[32];

@@ -199,8 +199,17 @@ def test_seed_scan_boundary_sums_are_the_sequential_float32_sums(dev):
             (rng.random(200000) ** 4).astype(np.float32)]
     sizes = [len(v) for v in segs]
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    buf = np.concatenate(segs)
-    piece_off, piece_cnt = off[:-1].reshape(-1, 1).copy(), np.array(sizes, np.int64).reshape(-1, 1)
+    # every segment in 3 pieces (ranks) stored out of order: [piece 2 | piece 0 | piece 1], cuts off the 128-value grid
+    buf = np.zeros(int(off[-1]), np.float32)
+    piece_off, piece_cnt = np.zeros((len(segs), 3), np.int64), np.zeros((len(segs), 3), np.int64)
+    for g, v in enumerate(segs):
+        c = [0, len(v) // 3 + 5, (2 * len(v)) // 3 + 77, len(v)]
+        pos = int(off[g])
+        for r in (2, 0, 1):
+            cnt = c[r + 1] - c[r]
+            buf[pos:pos + cnt] = v[c[r]:c[r + 1]]
+            piece_off[g, r], piece_cnt[g, r] = pos, cnt
+            pos += cnt
     n_trials = 8
     uni = rng.random((len(segs), n_trials))
     pot = np.array([np.cumsum(v)[-1] for v in segs], np.float32)
