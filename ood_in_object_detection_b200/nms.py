@@ -8,8 +8,7 @@ launch (csrc/nms.cu, a CTA per image); the result lists have the reference's str
 """
 from __future__ import annotations
 
-import ctypes as C
-from typing import List, Optional
+from typing import Optional
 
 import torch
 

@@ -17,9 +17,8 @@ HWC image there), `classes` / `agnostic_nms` filters (raise, like nms.non_max_su
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import List, Sequence
 
-import numpy as np
 import torch
 
 from . import nms as _nms
