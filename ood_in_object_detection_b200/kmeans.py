@@ -26,8 +26,11 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-BLOCK_ROWS = 512          # rows per CTA partial
-SUPER_BLOCKS = 8          # block partials per super-block (unit of ownership; 4096 rows: C3's 200 000-row segments split
+BLOCK_ROWS = 512          # rows per CTA partial (the fixed partition of the rank-count-invariant "ordered" reduction)
+BIG_BLOCK_ROWS = 1024     # ... of large fits in all-reduce mode: a CTA's set-up (centroid image, TMEM, barriers) is paid once per
+                          # block, and 1024-row blocks make the C3 step 6.6 % faster (3.52 -> 3.29 ms); not below ~6 waves of CTAs
+SUPER_ROWS = 4096         # unit of row ownership, whatever the block size
+SUPER_BLOCKS = SUPER_ROWS // BLOCK_ROWS          # block partials per super-block (unit of ownership; 4096 rows: C3's 200 000-row segments split
                           # into 49 units, so 8 ranks own 6-7 each)
 POLL_LAG = 2              # Lloyd iterations the device may run ahead of the host's convergence poll (1 when an iteration is long:
                           # see kmeans_fit)
@@ -293,31 +296,41 @@ class BlockTable:
 _BLOCK_CACHE: dict = {}
 
 
-def build_blocks(global_sizes: Sequence[int], world: int, rank: int, device, rot: Optional[Sequence[int]] = None) -> tuple:
+def auto_block_rows(global_sizes: Sequence[int], world: int, reduce: str = "allreduce") -> int:
+    """Rows per CTA block of a fit: BIG_BLOCK_ROWS when every rank still gets >= 6 waves of CTAs on 148 SMs and the result need
+    not be identical for every rank count (reduce != "ordered"), else BLOCK_ROWS."""
+    per_rank = sum(int(n) for n in global_sizes) // max(int(world), 1)
+    return BIG_BLOCK_ROWS if reduce != "ordered" and per_rank >= 6 * 148 * BIG_BLOCK_ROWS else BLOCK_ROWS
+
+
+def build_blocks(global_sizes: Sequence[int], world: int, rank: int, device, rot: Optional[Sequence[int]] = None,
+                 block_rows: Optional[int] = None) -> tuple:
     """Row sharding + block tables.  Rank r owns a contiguous range of super-blocks of every segment.
     rot[g]: rotation key of segment g (default: its index) -- callers that fit a SUBSET of their segments pass a stable id
     (the class index) so that the rows a rank must hold do not depend on which other segments take part.
     The tables only depend on (sizes, world, rank, rot): the last few are kept (a C3 table has 7.8 k blocks built in Python)."""
     rot = list(range(len(global_sizes))) if rot is None else [int(v) for v in rot]
-    key = (tuple(int(n) for n in global_sizes), int(world), int(rank), str(device), tuple(rot))
+    block_rows = int(block_rows or BLOCK_ROWS)
+    assert SUPER_ROWS % block_rows == 0 and block_rows % 128 == 0, "block_rows: a multiple of 128 dividing 4096"
+    key = (tuple(int(n) for n in global_sizes), int(world), int(rank), str(device), tuple(rot), block_rows)
     hit = _BLOCK_CACHE.get(key)
     if hit is not None:
         return hit
-    out = _build_blocks(global_sizes, world, rank, device, rot)
+    out = _build_blocks(global_sizes, world, rank, device, rot, block_rows)
     if len(_BLOCK_CACHE) >= 8:
         _BLOCK_CACHE.pop(next(iter(_BLOCK_CACHE)))
     _BLOCK_CACHE[key] = out
     return out
 
 
-def _build_blocks(global_sizes: Sequence[int], world: int, rank: int, device, rot) -> tuple:
+def _build_blocks(global_sizes: Sequence[int], world: int, rank: int, device, rot, block_rows: int = BLOCK_ROWS) -> tuple:
     seg_l, r0_l, r1_l, sfirst = [], [], [], [0]
     local_sizes, local_off = [], [0]
     super_seg_first = [0]
     owner_counts = [0] * world
     shard = []                                           # per segment: (global start row, rows) owned by this rank
     for g, n in enumerate(global_sizes):
-        n_super = (n + BLOCK_ROWS * SUPER_BLOCKS - 1) // (BLOCK_ROWS * SUPER_BLOCKS)
+        n_super = (n + SUPER_ROWS - 1) // (SUPER_ROWS)
         bounds = [(n_super * r) // world for r in range(world + 1)]       # super-blocks per range, contiguous
         for r in range(world):
             ri = range_index(rot[g], world, r)
@@ -325,17 +338,17 @@ def _build_blocks(global_sizes: Sequence[int], world: int, rank: int, device, ro
         super_seg_first.append(super_seg_first[-1] + n_super)
         ri = range_index(rot[g], world, rank)
         s0, s1 = bounds[ri], bounds[ri + 1]
-        row_a = min(n, s0 * BLOCK_ROWS * SUPER_BLOCKS)
-        row_b = min(n, s1 * BLOCK_ROWS * SUPER_BLOCKS)
+        row_a = min(n, s0 * SUPER_ROWS)
+        row_b = min(n, s1 * SUPER_ROWS)
         shard.append((row_a, row_b - row_a))
         base = local_off[-1]
         for sb in range(s0, s1):
-            a = sb * BLOCK_ROWS * SUPER_BLOCKS
-            b = min(n, a + BLOCK_ROWS * SUPER_BLOCKS)
-            for blk in range(a, b, BLOCK_ROWS):
+            a = sb * SUPER_ROWS
+            b = min(n, a + SUPER_ROWS)
+            for blk in range(a, b, block_rows):
                 seg_l.append(g)
                 r0_l.append(base + blk - row_a)
-                r1_l.append(base + min(b, blk + BLOCK_ROWS) - row_a)
+                r1_l.append(base + min(b, blk + block_rows) - row_a)
             sfirst.append(len(seg_l))
         local_sizes.append(row_b - row_a)
         local_off.append(base + row_b - row_a)
@@ -823,7 +836,8 @@ def kmeans_fit_sharded(x_local: torch.Tensor, local_sizes: Sequence[int], global
     """N > 1 entry: this rank holds `local_sizes[g]` rows of segment g (segment-major in x_local).  The block table
     only depends on the GLOBAL sizes, and build_blocks prescribes which rows each rank owns; the caller must have
     sharded accordingly (see shard_rows)."""
-    table, shard, local_off = build_blocks(global_sizes, world, rank, x_local.device, rot)
+    table, shard, local_off = build_blocks(global_sizes, world, rank, x_local.device, rot,
+                                           auto_block_rows(global_sizes, world, kw.get("reduce", "allreduce")))
     mine = [cnt for _, cnt in shard]
     if list(mine) != [int(v) for v in local_sizes]:
         raise ValueError(f"rank {rank}: row shard {list(local_sizes)} does not match the block table's {mine}; "
@@ -836,10 +850,10 @@ def shard_rows(global_sizes: Sequence[int], world: int, rank: int, rot: Optional
     `world` ranges of a segment a rank owns rotates with the segment index (range_index)."""
     out = []
     for g, n in enumerate(global_sizes):
-        n_super = (n + BLOCK_ROWS * SUPER_BLOCKS - 1) // (BLOCK_ROWS * SUPER_BLOCKS)
+        n_super = (n + SUPER_ROWS - 1) // (SUPER_ROWS)
         ri = range_index(g if rot is None else int(rot[g]), world, rank)
         s0, s1 = (n_super * ri) // world, (n_super * (ri + 1)) // world
-        a, b = min(n, s0 * BLOCK_ROWS * SUPER_BLOCKS), min(n, s1 * BLOCK_ROWS * SUPER_BLOCKS)
+        a, b = min(n, s0 * SUPER_ROWS), min(n, s1 * SUPER_ROWS)
         out.append((a, b - a))
     return out
 
@@ -920,5 +934,5 @@ def member_medians(x: torch.Tensor, sizes: Sequence[int], labels: Optional[torch
 
 def kmeans_fit_predict_single(x: torch.Tensor, sizes: Sequence[int], k: int, random_state: int = 10, **kw) -> KMeansResult:
     """Single-process convenience wrapper: x [sum(sizes), dim] holds the segments back to back."""
-    table, shard, local_off = build_blocks(sizes, 1, 0, x.device)
+    table, shard, local_off = build_blocks(sizes, 1, 0, x.device, block_rows=auto_block_rows(sizes, 1, kw.get("reduce", "allreduce")))
     return kmeans_fit(x, sizes, k, table, local_off, shard, random_state=random_state, **kw)
