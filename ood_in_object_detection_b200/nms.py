@@ -65,14 +65,17 @@ def non_max_suppression(prediction, conf_thres: float = 0.25, iou_thres: float =
     """prediction [bs, 4 + nc, A] (cx, cy, w, h, class confidences) CUDA float32; extra_item [bs, E, A]; strides [A].
     Returns like the reference: `output` (list of [k, 6] tensors: xyxy, confidence, class), followed by the list of [k, E]
     payload rows when `extra_item` is given and the list of [k] strides when `strides` is given.
-    Options outside the path the OoD pipeline uses (multi_label, class filter, agnostic, apriori labels, v10, mask columns)
-    raise NotImplementedError; `max_time_img` has no meaning here (the reference abandons the remaining images on timeout)."""
+    `agnostic=True` is the reference's class offset of 0 (ops.py:487: all classes suppress each other).  Options outside the
+    path the OoD pipeline uses raise NotImplementedError: multi_label, apriori labels, v10, mask columns, and the class filter
+    (the reference's own filter, ops.py:470-474, leaves `extra_item` unfiltered and indexes `strides` with a mask of the wrong
+    length: there is no payload behaviour to reproduce).  `max_time_img` has no meaning here (the reference abandons the
+    remaining images on timeout)."""
     assert 0 <= conf_thres <= 1, f'Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0'
     assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
     if isinstance(prediction, (list, tuple)):
         prediction = prediction[0]
-    if multi_label or classes or agnostic or (labels and len(labels)) or v10:
-        raise NotImplementedError("only the default path of non_max_suppression_old (best class, class-aware, no filters) runs on the GPU")
+    if multi_label or classes or (labels and len(labels)) or v10:
+        raise NotImplementedError("only the best-class path of non_max_suppression_old (no class filter, labels, multi_label, v10) runs on the GPU")
     det, out_ex, out_st, _, counts = nms_padded(prediction, conf_thres, iou_thres, max_det=max_det, nc=nc, max_nms=max_nms,
-                                                max_wh=max_wh, extra_item=extra_item, strides=strides)
+                                                max_wh=0 if agnostic else max_wh, extra_item=extra_item, strides=strides)
     return slice_results(det, out_ex, out_st, counts)

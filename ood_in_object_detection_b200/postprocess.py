@@ -13,7 +13,7 @@ Binding in the reference: `DetectionPredictor.postpro
 same attributes of the predictor (`args.conf / iou / max_det / agnostic_nms / classes / model`, `model.names`,
 `model.model.extraction_mode`, `model.model.model[-1].output_values_before_sigmoid`, `batch[0]`).
 Outside the path: image lists as `orig_imgs` (the OoD pipeline feeds tensors; the reference rescales to `shape[1:3]` of an
-HWC image there), `classes` / `agnostic_nms` filters (raise, like nms.non_max_suppression).
+HWC image there) and the `classes` filter (raises, like nms.non_max_suppression; `agnostic_nms` is served).
 """
 from __future__ import annotations
 
@@ -66,8 +66,8 @@ def postprocess(self, preds, img, orig_imgs, keep_images: bool = False, **kwargs
     if isinstance(orig_imgs, (list, tuple)):
         raise NotImplementedError("postprocess: image lists are outside the OoD path (the pipeline feeds [B, 3, H, W] tensors)")
     args = self.args
-    if args.agnostic_nms or args.classes:
-        raise NotImplementedError("postprocess: agnostic / class-filtered NMS is outside the OoD path")
+    if args.classes:
+        raise NotImplementedError("postprocess: class-filtered NMS is outside the OoD path (see nms.non_max_suppression)")
     # predict.py:143-148
     output_extra = preds[0][0] if (before_sigmoid or mode == "logits") else preds[1]
     pred = preds[0][0]
@@ -93,7 +93,7 @@ def postprocess(self, preds, img, orig_imgs, keep_images: bool = False, **kwargs
     elif mode != "all_ftmaps":
         raise ValueError(f"postprocess: unknown extraction mode {mode!r}")
     det, out_ex, out_st, anchor, counts = _nms.nms_padded(pred, args.conf, args.iou, max_det=args.max_det, extra_item=payload_in,
-                                                          strides=strides)
+                                                          strides=strides, max_wh=0 if args.agnostic_nms else 7680)
     if mode == "roi_aligned_ftmaps":                                                    # predict.py:184-193: boxes in network pixels
         from .ood_utils import extract_roi_aligned_features_from_correct_stride
         extra = extract_roi_aligned_features_from_correct_stride(

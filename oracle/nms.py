@@ -1,7 +1,7 @@
 """NMS-with-payload oracle.  TEST INFRASTRUCTURE (see oracle/__init__.py).
 
 Restates the default path of /root/reference/ultralytics/utils/ops.py:348-530 (`non_max_suppression_old`: best class only,
-no apriori labels, no class filter, class-aware, not v10) including the payload the reference threads through it for the OoD
+no apriori labels, no class filter, class-aware or agnostic, not v10) including the payload the reference threads through it for the OoD
 methods -- the per-anchor `extra_item` rows (raw class logits) and `strides` -- and torchvision's `nms` (greedy suppression in
 score order, IoU in float32, strict `>` against the threshold) that it calls at :489.
 """
@@ -35,7 +35,7 @@ def nms_keep(boxes: np.ndarray, iou_thres: float) -> np.ndarray:
 
 
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, max_det=300, max_nms=30000, max_wh=7680,
-                        extra_item=None, strides=None):
+                        extra_item=None, strides=None, agnostic=False):
     """prediction [bs, 4 + nc, A] (cx, cy, w, h, class confidences); extra_item [bs, E, A]; strides [A].
     -> (list of [k, 6] arrays (xyxy, conf, cls), list of [k, E] payload rows, list of [k] strides)."""
     pred = np.asarray(prediction, F32)
@@ -58,7 +58,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, max_det=300
         cls = x[:, 4:].argmax(1).astype(F32)
         order = np.argsort(-conf, kind="stable")[:max_nms]         # :478-482 (ties: anchor order)
         det = np.concatenate([box, conf[:, None], cls[:, None]], 1)[order]
-        keep = nms_keep(det[:, :4] + det[:, 5:6] * F32(max_wh), iou_thres)[:max_det]     # :485-489
+        keep = nms_keep(det[:, :4] + det[:, 5:6] * F32(0 if agnostic else max_wh), iou_thres)[:max_det]     # :485-489
         out.append(det[keep])
         extras.append(e[order][keep] if e is not None else None)
         strs.append(s[order][keep] if s is not None else None)

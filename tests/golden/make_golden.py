@@ -564,8 +564,9 @@ def golden_nms(ref):
     from tests.helpers import nms_inputs
     pred, logits, strides = nms_inputs()
     store = dict(seed=91)
-    for tag, (conf, iou, max_det) in {"a": (0.25, 0.45, 300), "b": (0.15, 0.7, 50)}.items():
+    for tag, (conf, iou, max_det) in {"a": (0.25, 0.45, 300), "b": (0.15, 0.7, 50), "agn": (0.25, 0.45, 300)}.items():
         out, extra, st = uops.non_max_suppression_old(torch.from_numpy(pred), conf, iou, max_det=max_det, max_time_img=100.0,
+                                                     agnostic=tag == "agn",
                                                      extra_item=torch.from_numpy(logits), strides=torch.from_numpy(strides))
         # (max_time_img: the reference abandons the remaining images after 0.5 s + 0.05 s per image on a slow CPU)
         store[f"{tag}_n"] = np.array([len(o) for o in out])
@@ -574,7 +575,7 @@ def golden_nms(ref):
         store[f"{tag}_strides"] = np.concatenate([s.numpy().reshape(-1) for s in st]).astype(F32)
         store[f"{tag}_cfg"] = np.array([conf, iou, max_det], np.float64)
     np.savez_compressed(os.path.join(OUT, "golden_nms.npz"), **store)
-    print("golden_nms kept per image", {t: store[f"{t}_n"].tolist() for t in "ab"})
+    print("golden_nms kept per image", {t: store[f"{t}_n"].tolist() for t in ("a", "b", "agn")})
 
 
 def golden_postprocess(ref):

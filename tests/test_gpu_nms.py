@@ -23,9 +23,9 @@ def test_nms_matches_reference_golden(nms, golden):
     g = golden("golden_nms.npz")
     pred, logits, strides = nms_inputs(int(g["seed"]))
     tp, tl, ts = torch.from_numpy(pred).cuda(), torch.from_numpy(logits).cuda(), torch.from_numpy(strides).cuda()
-    for tag in "ab":
+    for tag in ("a", "b", "agn"):                                                             # agn: class-agnostic suppression
         conf, iou, max_det = g[f"{tag}_cfg"]
-        out, extra, st = nms.non_max_suppression(tp, conf, iou, max_det=int(max_det), extra_item=tl, strides=ts)
+        out, extra, st = nms.non_max_suppression(tp, conf, iou, max_det=int(max_det), extra_item=tl, strides=ts, agnostic=tag == "agn")
         assert [len(o) for o in out] == g[f"{tag}_n"].tolist()
         assert np.array_equal(torch.cat(out).cpu().numpy(), g[f"{tag}_det"])                 # boxes, confidence, class: bit for bit
         assert np.array_equal(torch.cat([e.reshape(len(o), -1) for e, o in zip(extra, out)]).cpu().numpy(), g[f"{tag}_extra"])
@@ -33,7 +33,7 @@ def test_nms_matches_reference_golden(nms, golden):
     only = nms.non_max_suppression(tp, 0.25, 0.45)                                            # no payload: just the list
     assert isinstance(only, list) and [len(o) for o in only] == g["a_n"].tolist()
     with pytest.raises(NotImplementedError):
-        nms.non_max_suppression(tp, 0.25, 0.45, agnostic=True)
+        nms.non_max_suppression(tp, 0.25, 0.45, classes=[1, 2])
 
 
 def test_nms_matches_oracle_on_ragged_batches(nms):

@@ -111,6 +111,12 @@ def test_postprocess_rejects_what_it_does_not_serve(inputs):
     fp.args.classes = [1]
     with pytest.raises(NotImplementedError):
         postprocess(fp, ((inputs["p"],), inputs["maps"]), inputs["img"], inputs["img"])
+    fa = fake_predictor("ftmaps_and_strides", False, 0.25, device="cuda:0")
+    fa.args.agnostic_nms = True                                                                # served: fewer boxes survive
+    res_a = postprocess(fa, ((inputs["p"].clone(),), inputs["maps"]), inputs["img"], inputs["img"])
+    res_c = postprocess(fake_predictor("ftmaps_and_strides", False, 0.25, device="cuda:0"), ((inputs["p"].clone(),), inputs["maps"]),
+                        inputs["img"], inputs["img"])
+    assert sum(len(r.boxes) for r in res_a) < sum(len(r.boxes) for r in res_c)
     with pytest.raises(RuntimeError):
         postprocess(fake_predictor("all_ftmaps", False, 0.25), ((inputs["p"].cpu(),), [m.cpu() for m in inputs["maps"]]),
                     inputs["img"].cpu(), inputs["img"].cpu())

@@ -339,9 +339,9 @@ def test_nms_with_payload(golden):
     from tests.helpers import nms_inputs
     g = golden("golden_nms.npz")
     pred, logits, strides = nms_inputs(int(g["seed"]))
-    for tag in "ab":
+    for tag in ("a", "b", "agn"):
         conf, iou, max_det = g[f"{tag}_cfg"]
-        out, extra, st = nms.non_max_suppression(pred, conf, iou, int(max_det), extra_item=logits, strides=strides)
+        out, extra, st = nms.non_max_suppression(pred, conf, iou, int(max_det), extra_item=logits, strides=strides, agnostic=tag == "agn")
         assert [len(o) for o in out] == g[f"{tag}_n"].tolist()
         assert np.array_equal(np.concatenate(out), g[f"{tag}_det"])
         assert np.array_equal(np.concatenate([e.reshape(len(o), -1) for e, o in zip(extra, out)]), g[f"{tag}_extra"])
