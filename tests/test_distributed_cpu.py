@@ -149,6 +149,40 @@ def test_block_table_is_rank_count_invariant():
         assert sum(t.n_blocks for t in tabs) == kmeans.build_blocks(SIZES, 1, 0, torch.device("cpu"))[0].n_blocks
 
 
+def test_block_size_choice_and_big_block_tables():
+    """Large all-reduce-mode fits take 1024-row CTA blocks, everything else (and always the rank-count-invariant "ordered"
+    reduction) the fixed 512-row partition; a table of either block size covers the same rows, owns the same 4096-row
+    super-blocks per rank, and the numpy stand-in fits to identical labels on both."""
+    big = [200_000] * 20
+    assert kmeans.auto_block_rows(big, 1) == kmeans.BIG_BLOCK_ROWS and kmeans.auto_block_rows(big, 4) == kmeans.BIG_BLOCK_ROWS
+    assert kmeans.auto_block_rows(big, 8) == kmeans.BLOCK_ROWS                       # 3.3 waves of big blocks: not worth it
+    assert kmeans.auto_block_rows(big, 1, "ordered") == kmeans.BLOCK_ROWS
+    assert kmeans.auto_block_rows(SIZES, 1) == kmeans.BLOCK_ROWS
+    dev = torch.device("cpu")
+    sizes = [9000, 0, 4096, 4097, 1, 20000]
+    for world in (1, 2, 3):
+        for r in range(world):
+            t_small, sh_small, off_small = kmeans.build_blocks(sizes, world, r, dev)
+            t_big, sh_big, off_big = kmeans.build_blocks(sizes, world, r, dev, block_rows=1024)
+            assert sh_small == sh_big and list(off_small) == list(off_big)           # ownership does not depend on the block size
+            assert t_big.n_super_local == t_small.n_super_local and t_big.n_super_global == t_small.n_super_global
+            for t, rows in ((t_small, 512), (t_big, 1024)):
+                r0, r1, seg = t.row0.numpy(), t.row1.numpy(), t.seg.numpy()
+                assert ((r1 - r0) > 0).all() and ((r1 - r0) <= rows).all()
+                assert (r0[1:] == r1[:-1]).all() and (len(r0) == 0 or (r0[0] == 0 and r1[-1] == off_small[-1]))   # contiguous cover
+                assert (np.diff(seg) >= 0).all()
+                sf = t.super_first.numpy()
+                assert sf[0] == 0 and sf[-1] == t.n_blocks and ((r1[sf[1:] - 1] - r0[sf[:-1]]) <= kmeans.SUPER_ROWS).all()
+    with pytest.raises(AssertionError):
+        kmeans.build_blocks(sizes, 1, 0, dev, block_rows=768)
+    be = NumpyBackend()
+    x = torch.from_numpy(np.concatenate(_data()))
+    tab, shard, off = kmeans.build_blocks(SIZES, 1, 0, dev, block_rows=1024)
+    a = kmeans.kmeans_fit(x, SIZES, K, tab, off, shard, backend=be)
+    b = kmeans.kmeans_fit_predict_single(x, SIZES, K, backend=be)
+    assert np.array_equal(a.labels.numpy(), b.labels.numpy())
+
+
 def test_device_seeding_control_flow_matches_host_seeding():
     """seeding="device" (scan + search, gather, distance pass, pick as backend steps; uniforms drawn up front) picks
     the same seeds as the host loop written with sklearn's expressions, hence identical labels."""
