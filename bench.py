@@ -148,6 +148,18 @@ def algorithmic_bytes(det, wl, k, n_tables=1):
     return int(total), int(upper), n
 
 
+def _traffic_channels_last(key):
+    """DRAM bytes per launch of the fused path on channels-last maps: the gather's own capture + the plan / score kernels."""
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(tp) as f:
+            c = json.load(f)[key]
+        b, cl = c["breakdown_bytes"], c["channels_last"]
+        return int(cl["items_nhwc_kernel_read"] + cl["items_nhwc_kernel_write"] + b["plan_geo_kernel"] + b["score_kernel_read"])
+    except Exception:
+        return None
+
+
 def _traffic(key, field):
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
@@ -878,7 +890,7 @@ def run_ours(args, wl):
     import logging
     log = logging.getLogger("bench")
     log.setLevel(logging.ERROR)
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = args.e2e_steps or max(2, min(args.steps, 20))
 
     def e2e_step():
         return ood_utils.compute_ood_decisions_fused(methods, res_f, log, logits_results=res_l)
@@ -1019,6 +1031,7 @@ def run_ours(args, wl):
                          "upper_bound_bytes": upper, "kernel_ms": fmap_ms, "peak_source": how, "layout": args.layout,
                          "other_layout": {"layout": alt_name, "kernel_ms": alt_ms, "achieved": alg / (alt_ms * 1e-3) / 1e9,
                                           "frac": alg / (alt_ms * 1e-3) / 1e9 / peak, "decisions_or_argmin_differing": alt_same,
+                                          "traffic": _traffic_channels_last(args.config) if alt_name == "channels_last" else None,
                                           "note": "the same fused pass over the same values with the maps in the other memory "
                                                   "layout (channels_last = what a detector run in torch.channels_last hands over)"},
                          "note": "HBM moves whole 128-byte lines; NCHW window rows are 8..52 B (DESIGN.md section 4)"},
@@ -1063,6 +1076,7 @@ def main():
     ap.add_argument("--fit-variant", default="realistic", choices=list(FIT_VARIANTS),
                     help="--workload fit / --impl reference --workload fit: which C3 set (SURVEY.md section 8d)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C1 / C4 / C5 side measurements of the default line")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the end-to-end leg (default: min(steps, 20))")
     ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the e2e, fit and cpu_baseline legs (tuning sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
