@@ -35,3 +35,27 @@ def test_no_product_import_of_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
     assert os.path.isdir(os.path.join(root, "oracle"))
+
+
+def test_product_path_fails_loudly_without_a_cuda_device():
+    """No CPU fallback anywhere on the product path: with host tensors (or no CUDA device at all) the entry points raise."""
+    import numpy as np
+    import pytest
+    import torch
+    from ood_in_object_detection_b200 import nms, ops
+    from ood_in_object_detection_b200.postprocess import postprocess
+    from tests.helpers import fake_predictor
+    pred = torch.zeros((2, 4 + 3, 100))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        nms.non_max_suppression(pred, 0.25, 0.45)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        postprocess(fake_predictor("all_ftmaps", False, 0.25), ((pred,), [torch.zeros((2, 8, 4, 4))] * 3),
+                    torch.zeros((2, 3, 32, 32)), torch.zeros((2, 3, 32, 32)))
+    with pytest.raises(TypeError):
+        ops.PairDistances(torch.zeros((4, 8)), "l2")                      # host rows
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            ops.default_device()
+        with pytest.raises(RuntimeError):
+            ops.match_boxes([np.zeros((1, 4), np.float32)], [np.zeros(1, np.int32)], [np.zeros((1, 4), np.float32)],
+                            [np.zeros(1, np.int32)], 0.5)
