@@ -116,3 +116,33 @@ def test_first_centre_draw_is_randomstate_choice():
             ref = int(a.choice(n, p=w / w.sum()))
             assert kmeans._sklearn_first_center(b, n) == ref, (n, seed)
             assert a.uniform() == b.uniform()
+
+
+def test_parallel_evaluation_of_the_sequential_float32_cumsum():
+    """oracle/scan_model.py (the arithmetic of csrc/seed.cu::seed_scan_kernel in numpy: integer increments per binade, tie
+    parity through a scan of parity maps, crossing blocks redone with the float chain) == np.cumsum(float32) at every
+    128-value boundary, bit for bit, on data where ties, binade jumps, zeros and denormals occur."""
+    from oracle import scan_model
+    rng = np.random.default_rng(23)
+    n = 30001
+    jumps = rng.random(n).astype(np.float32) ** 6
+    jumps[[5, 1000, 1001, 20000]] = [3e4, 7e6, 1e-30, 4e9]
+    cases = {"integers": rng.integers(0, 1024, n).astype(np.float32) * np.float32(40.0),                     # ties once ulp(sum) >= 80
+             "odd": np.where(np.arange(n) % 7 == 0, 1025.0, 513.0).astype(np.float32) * np.float32(64.0),     # EVERY add a tie later on
+             "tails": np.exp(rng.standard_normal(n) * 4).astype(np.float32), "jumps": jumps,
+             "zeros": np.concatenate([np.zeros(5000, np.float32), rng.random(n - 5000).astype(np.float32) * 1e-3]),
+             "denormals": (rng.random(n) * 1e-41).astype(np.float32), "plain": (rng.random(n) ** 4).astype(np.float32),
+             "short": np.float32([0.1, 0.2, 0.3]), "empty_tail": np.full(256, 0.25, np.float32)}
+    ties = 0
+    for name, v in cases.items():
+        cum = np.cumsum(v)
+        ends = np.concatenate([cum[127::128], cum[-1:]]) if len(v) % 128 else cum[127::128]
+        got = scan_model.boundary_sums(v)
+        assert np.array_equal(got.view(np.uint32), ends.view(np.uint32)), name
+        assert np.array_equal(scan_model.boundary_sums(v, blocks_per_pass=7).view(np.uint32), ends.view(np.uint32)), name
+        s = cum[len(cum) // 2]
+        if 1e-30 < s < 1e30:                                                     # ties against the unit of the sum half-way through
+            with np.errstate(over="ignore", invalid="ignore"):
+                x = v * np.float32(2.0 ** (23 - (np.frexp(s)[1] - 1)))
+                ties += int((x - np.floor(x) == 0.5).sum())
+    assert ties > 1000                                                                                     # the tie rule is exercised
